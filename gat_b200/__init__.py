@@ -1,0 +1,261 @@
+"""gat_b200 -- B200-native simulation engine of the Genomic Association Tester.
+
+Drop-in for the `gat.run()` / gat-run.py path of AndreasHeger/gat (gat/__init__.py:855-1088): same
+arguments, same result objects, same output table.  The per-sample work of the reference
+(UnconditionalSampler.sample -> computeSample, gat/__init__.py:494-591, 704-778) is replaced by batched
+CUDA kernels reached through the C ABI in include/gat_b200.h.  One process per GPU; with
+torch.distributed initialised the samples are sharded by rank and the count matrix is all-gathered
+(gat_b200/parallel.py).
+"""
+import collections
+import re
+
+import numpy as np
+
+from . import device
+from . import engine as Engine
+from . import stats as Stats
+from .engine import (IntervalCollection, IntervalDictionary, SamplerAnnotator, UnconditionalWorkspace,
+                     AnnotatorResult, AnnotatorResultExtended, getContext, seed)
+from .segmentlist import SegmentList
+
+__version__ = "0.1.0"
+
+
+class TrackProblem(object):
+    """one segment track flattened for the GPU: placement units in the reference's iteration order and
+    the contig-level annotations/workspace they are counted against."""
+
+    def __init__(self, segs, workspace):
+        # units = keys of the track in iteration order, skipping empty ones (gat/__init__.py:531-538)
+        self.unit_keys = []
+        self.contigs = []
+        contig_index = {}
+        self.unit_contig = []
+        self.has_isochores = False
+        for key in list(segs.keys()):
+            if workspace[key].isEmpty or segs[key].isEmpty:
+                continue
+            contig, split = Engine.splitKey(key)
+            self.has_isochores = self.has_isochores or split
+            if contig not in contig_index:
+                contig_index[contig] = len(self.contigs)
+                self.contigs.append(contig)
+            self.unit_keys.append(key)
+            self.unit_contig.append(contig_index[contig])
+        self.unit_segments = [segs[k].asarray() for k in self.unit_keys]
+        self.unit_workspace = [workspace[k].asarray() for k in self.unit_keys]
+
+
+def buildContigAnnotations(annotations, workspace, contigs):
+    """contig-level annotations and workspace as UnconditionalSampler.sample builds them
+    (gat/__init__.py:716-721): clone + fromIsochores; lists[a][c] and len(contig_workspace[c])"""
+    contig_annotations = annotations.clone()
+    contig_annotations.fromIsochores()
+    contig_workspace = workspace.clone()
+    contig_workspace.fromIsochores()
+    atracks = list(annotations.tracks)
+    lists = [[contig_annotations[a][c].asarray() for c in contigs] for a in atracks]
+    nseg = [len(contig_workspace[c]) for c in contigs]
+    return atracks, lists, nseg
+
+
+def sampleTrack(track_index, segs, annotations, workspace, sampler, counters, num_samples,
+                sample_range=None, annos_cache=None, return_device=False):
+    """all samples of one track: counts[counter_id] = ndarray [num_samples][n_annot]
+    (replaces UnconditionalSampler.sample, gat/__init__.py:704-778)."""
+    import torch
+    ctx = getContext()
+    problem = TrackProblem(segs, workspace)
+    counter_names = [c.name for c in counters]
+    atracks = list(annotations.tracks)
+    if not problem.unit_keys:
+        return atracks, [np.zeros((num_samples, len(atracks))) for _ in counters], np.zeros(3, dtype=np.uint64)
+    key = tuple(problem.contigs)
+    if annos_cache is not None and key in annos_cache:
+        annos = annos_cache[key]
+    else:
+        _, lists, nseg = buildContigAnnotations(annotations, workspace, problem.contigs)
+        annos = device.Annotations(ctx, lists, key_ws_nseg=nseg)
+        if annos_cache is not None:
+            annos_cache[key] = annos
+    try:
+        smp = device.Sampler(ctx, problem.unit_contig, len(problem.contigs), problem.has_isochores,
+                             problem.unit_segments, problem.unit_workspace,
+                             bucket_size=sampler.bucket_size, nbuckets=sampler.nbuckets)
+    except device._lib.GatB200Error as e:
+        if e.code == device._lib.ERR_TOO_LARGE:
+            raise ValueError(str(e))
+        raise
+    begin, end = sample_range if sample_range is not None else (0, num_samples)
+    n_local = end - begin
+    dev = torch.device("cuda", ctx.device)
+    ids = device.counter_ids(counter_names)
+    out_u = torch.zeros((len(ids), max(n_local, 1), len(atracks)), dtype=torch.int32, device=dev)
+    out_f = torch.zeros((max(n_local, 1), len(atracks)), dtype=torch.float64, device=dev) \
+        if device.DENSITY in ids else None
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    info = smp.run(annos, counter_names, Engine.getSeed(), track_index, begin, n_local,
+                   out_counts_ptr=out_u.data_ptr(), out_density_ptr=out_f.data_ptr() if out_f is not None else None)
+    smp.close()
+    if annos_cache is None:
+        annos.close()
+    return atracks, (out_u, out_f, ids), info
+
+
+def run(segments, annotations, workspace, sampler, counters, workspace_generator, **kwargs):
+    """run an enrichment analysis (signature and kwargs of gat.run, gat/__init__.py:855-907).
+
+    kwargs: num_samples (10000), pseudo_count (1.0), reference, output_counts_pattern,
+    output_samples_pattern, outfiles, cache / sample_files / num_threads (accepted, unused: the
+    reference's sample cache is dead code and its multiprocessing is replaced by the GPU).
+    """
+    from . import parallel
+    import torch
+
+    num_samples = kwargs.get("num_samples", 10000)
+    output_counts_pattern = kwargs.get("output_counts_pattern", None)
+    output_samples_pattern = kwargs.get("output_samples_pattern", None)
+    pseudo_count = kwargs.get("pseudo_count", 1.0)
+    reference = kwargs.get("reference", None)
+
+    if not getattr(sampler, "accelerated", False):
+        raise NotImplementedError("sampler %s is not accelerated by gat_b200 (only SamplerAnnotator is)"
+                                  % type(sampler).__name__)
+    if getattr(workspace_generator, "is_conditional", False):
+        raise NotImplementedError("conditional workspaces are not accelerated by gat_b200")
+
+    ctx = getContext()
+    rank, world = parallel.rank_world()
+
+    # observed counts (gat/__init__.py:932-940)
+    observed_counts = [Engine.computeCounts(counter=c, aggregator=sum, segments=segments,
+                                            annotations=annotations, workspace=workspace,
+                                            workspace_generator=workspace_generator) for c in counters]
+
+    sampled = {}
+    annos_cache = {}
+    begin, end = parallel.shard_range(num_samples, rank, world)
+    for ntrack, track in enumerate(segments.tracks):
+        segs = segments[track]
+        if workspace.sum() == 0:
+            continue
+        atracks, out, info = sampleTrack(ntrack, segs, annotations, workspace, sampler, counters,
+                                         num_samples, sample_range=(begin, end), annos_cache=annos_cache)
+        if isinstance(out, list):          # track without any unit
+            sampled[track] = (atracks, None, None, None)
+            continue
+        out_u, out_f, ids = out
+        # one collective: all-gather the S/G x A slabs of every counter
+        out_u = parallel.allgather_samples(out_u, num_samples, dim=1)
+        if out_f is not None:
+            out_f = parallel.allgather_samples(out_f, num_samples, dim=0)
+        sampled[track] = (atracks, out_u, out_f, ids)
+        if output_samples_pattern and rank == 0:
+            _dumpSamples(track, ntrack, segs, workspace, sampler, num_samples, output_samples_pattern)
+    for a in annos_cache.values():
+        a.close()
+
+    # statistics per (counter, track): one batched column-stats call over all annotations
+    annotator_results = []
+    for counter_id, (counter, observed_count) in enumerate(zip(counters, observed_counts)):
+        for track, r in observed_count.items():
+            if track not in sampled:
+                continue
+            atracks, out_u, out_f, ids = sampled[track]
+            annos_in_result = [a for a in r.keys()]
+            if workspace.sum() == 0:
+                continue
+            obs = np.array([r[a] for a in atracks], dtype=np.float64)
+            ref = None
+            if reference:
+                ref = np.array([reference[track][a].fold for a in atracks], dtype=np.float64)
+            if out_u is None:
+                host = np.zeros((num_samples, len(atracks)))
+                st = ctx.column_stats(host.astype(np.uint32), obs, pseudo_count=pseudo_count, ref_fold=ref)
+            elif counter.name == "nucleotide-density":
+                st = ctx.column_stats(None, obs, pseudo_count=pseudo_count, ref_fold=ref,
+                                      device_ptr=out_f.data_ptr(), n_samples=num_samples,
+                                      n_cols=len(atracks), is_float=1)
+                host = out_f.cpu().numpy()
+            else:
+                plane = out_u[counter_id]
+                st = ctx.column_stats(None, obs, pseudo_count=pseudo_count, ref_fold=ref,
+                                      device_ptr=plane.data_ptr(), n_samples=num_samples,
+                                      n_cols=len(atracks), is_float=0)
+                host = plane.cpu().numpy().view(np.uint32)
+            for ai, annotation in enumerate(atracks):
+                if annotation not in annos_in_result:
+                    continue
+                row = dict((k, float(v[ai])) for k, v in st.items())
+                annotator_results.append(AnnotatorResultExtended(
+                    track=track, annotation=annotation, counter=counter.name, observed=r[annotation],
+                    samples=host[:, ai], track_segments=segments[track],
+                    annotation_segments=annotations[annotation], workspace=workspace,
+                    reference=reference[track][annotation] if reference else None,
+                    pseudo_count=pseudo_count, stats=row))
+
+    # dump (large) table with counts (gat/__init__.py:1072-1086)
+    if output_counts_pattern and rank == 0:
+        for counter in counters:
+            filename = re.sub("%s", counter.name, output_counts_pattern)
+            with _open(filename, "w") as outfile:
+                outfile.write("track\tannotation\tobserved\tcounts\n")
+                for o in annotator_results:
+                    if o.counter != counter.name:
+                        continue
+                    outfile.write("%s\t%s\t%i\t%s\n" % (o.track, o.annotation, o.observed,
+                                                        ",".join(["%i" % x for x in o.samples])))
+    torch.cuda.synchronize(ctx.device)
+    return annotator_results
+
+
+def _open(filename, mode):
+    import gzip
+    if filename.endswith(".gz"):
+        return gzip.open(filename, mode + "t")
+    return open(filename, mode)
+
+
+def _dumpSamples(track, track_index, segs, workspace, sampler, num_samples, pattern):
+    """--output-samples-pattern: BED with one `track name=<sample>` block per sample.  The reference
+    writes each unit's list under its isochore key (gat/__init__.py:518-559); the GPU path keeps only
+    the contig-level sample (after fromIsochores), which is what is counted, so keys are contigs."""
+    import os
+    ctx = getContext()
+    problem = TrackProblem(segs, workspace)
+    filename = re.sub("%s", track, pattern)
+    dirname = os.path.dirname(filename)
+    if dirname and not os.path.exists(dirname):
+        os.makedirs(dirname)
+    smp = device.Sampler(ctx, problem.unit_contig, len(problem.contigs), problem.has_isochores,
+                         problem.unit_segments, problem.unit_workspace,
+                         bucket_size=sampler.bucket_size, nbuckets=sampler.nbuckets)
+    with _open(filename, "w") as outf:
+        step = 256
+        for b in range(0, num_samples, step):
+            placed, _ = smp.place(Engine.getSeed(), track_index, b, min(step, num_samples - b))
+            for i, per_contig in enumerate(placed):
+                outf.write("track name=%i\n" % (b + i))
+                for c, arr in enumerate(per_contig):
+                    for s, e in arr:
+                        outf.write("%s\t%i\t%i\n" % (problem.contigs[c], s, e))
+    smp.close()
+
+
+def fromCounts(filename):
+    """annotator results from a counts table written with output_counts_pattern (gat/__init__.py:1091-1119)"""
+    results = []
+    with _open(filename, "r") as infile:
+        header = infile.readline()
+        if not header == "track\tannotation\tobserved\tcounts\n":
+            raise ValueError("%s not a counts file: got %s" % (infile, header))
+        for line in infile:
+            track, annotation, observed, counts = line[:-1].split("\t")
+            samples = np.array(list(map(float, counts.split(","))), dtype=np.float64)
+            results.append(AnnotatorResult(track=track, annotation=annotation, counter="na",
+                                           observed=float(observed), samples=samples))
+    return results
+
+
+from .cli import buildParser  # noqa: E402  (flags of gat.buildParser, gat/__init__.py:54-429)

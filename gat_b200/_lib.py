@@ -1,0 +1,83 @@
+"""ctypes binding of libgat_b200.so (include/gat_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C gat_b200/csrc`.  There is no
+Python or CPU fallback: if the shared library is missing, or no CUDA device is present, the engine
+raises instead of computing anything on the host.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgat_b200.so")
+
+OK = 0
+ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_TOO_LARGE, ERR_RANGE = -1, -2, -3, -4, -5
+
+# every symbol include/gat_b200.h declares (tests/test_abi.py checks the .so exports them all)
+SYMBOLS = [
+    "gatb_version", "gatb_create", "gatb_destroy", "gatb_last_error", "gatb_set_stream",
+    "gatb_synchronize", "gatb_launch_count", "gatb_set_batch_size",
+    "gatb_annotations_create", "gatb_annotations_destroy", "gatb_count_lists",
+    "gatb_sampler_create", "gatb_sampler_destroy", "gatb_sampler_sample_capacity",
+    "gatb_sampler_place", "gatb_run", "gatb_column_stats",
+]
+
+
+class GatB200Error(RuntimeError):
+    """error reported by libgat_b200.so"""
+
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "gat_b200 error %i: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """load libgat_b200.so; fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "gat_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C gat_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, u32, u64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_double
+    L.gatb_version.restype = i32
+    L.gatb_version.argtypes = []
+    L.gatb_create.restype = i32
+    L.gatb_create.argtypes = [i32, ctypes.POINTER(vp)]
+    L.gatb_destroy.restype = None
+    L.gatb_destroy.argtypes = [vp]
+    L.gatb_last_error.restype = ctypes.c_char_p
+    L.gatb_last_error.argtypes = [vp]
+    L.gatb_set_stream.restype = i32
+    L.gatb_set_stream.argtypes = [vp, vp]
+    L.gatb_synchronize.restype = i32
+    L.gatb_synchronize.argtypes = [vp]
+    L.gatb_launch_count.restype = u64
+    L.gatb_launch_count.argtypes = [vp]
+    L.gatb_set_batch_size.restype = i32
+    L.gatb_set_batch_size.argtypes = [vp, u32]
+    L.gatb_annotations_create.restype = i32
+    L.gatb_annotations_create.argtypes = [vp, i32, i32, vp, vp, vp, vp, ctypes.POINTER(vp)]
+    L.gatb_annotations_destroy.restype = None
+    L.gatb_annotations_destroy.argtypes = [vp]
+    L.gatb_count_lists.restype = i32
+    L.gatb_count_lists.argtypes = [vp, vp, i32, vp, u64, vp, vp, vp, vp, vp]
+    L.gatb_sampler_create.restype = i32
+    L.gatb_sampler_create.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, u32, u32, ctypes.POINTER(vp)]
+    L.gatb_sampler_destroy.restype = None
+    L.gatb_sampler_destroy.argtypes = [vp]
+    L.gatb_sampler_sample_capacity.restype = u64
+    L.gatb_sampler_sample_capacity.argtypes = [vp]
+    L.gatb_sampler_place.restype = i32
+    L.gatb_sampler_place.argtypes = [vp, u64, u32, u64, u64, vp, vp, vp, vp, vp]
+    L.gatb_run.restype = i32
+    L.gatb_run.argtypes = [vp, vp, i32, vp, u64, u32, u64, u64, vp, vp, i32, vp]
+    L.gatb_column_stats.restype = i32
+    L.gatb_column_stats.argtypes = [vp, vp, i32, i32, u64, i32, vp, vp, dbl, vp, vp, vp, vp, vp, vp]
+    _lib = L
+    return L

@@ -1,0 +1,846 @@
+// api.cu -- the C ABI of libgat_b200.so (include/gat_b200.h): contexts, staging, batching.
+//
+// Host code here only moves data and sequences kernel launches; every interval computation of the
+// hot path runs in the CUDA kernels of place.cu / count.cu.  There is no CPU fallback: if CUDA is
+// unavailable every compute entry point returns GATB_ERR_CUDA.
+#include "../../include/gat_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "count.cuh"
+#include "place.cuh"
+
+using namespace gatb;
+
+// ---------------------------------------------------------------------------------------------------
+struct gatb_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    uint32_t batch = 0;                 // 0 = default
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    // tunables (env overrides, for profiling)
+    uint32_t tile_budget = 0;
+    int count_threads = 512;
+    uint32_t schunk_max = 128;
+};
+
+static std::string g_create_err;
+
+static int fail(gatb_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg; else g_create_err = msg;
+    return code;
+}
+
+#define CU(ctx, call)                                                                             \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return fail(ctx, GATB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count); }
+    cudaError_t upload(const T *h, size_t count, cudaStream_t st)
+    {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+};
+
+static uint32_t env_u32(const char *name, uint32_t dflt)
+{
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    return (uint32_t)strtoul(v, nullptr, 10);
+}
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gatb_version(void) { return GATB_VERSION; }
+
+extern "C" int gatb_create(int device, gatb_ctx **out)
+{
+    if (!out) return fail(nullptr, GATB_ERR_INVALID, "gatb_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, GATB_ERR_CUDA,
+                    std::string("gatb_create: no CUDA device (") + cudaGetErrorString(e) +
+                        "); gat_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, GATB_ERR_INVALID, "gatb_create: bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, GATB_ERR_CUDA, cudaGetErrorString(e));
+    gatb_ctx *ctx = new gatb_ctx();
+    ctx->device = device;
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return fail(nullptr, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->count_threads = (int)env_u32("GATB_COUNT_THREADS", 512);
+    ctx->schunk_max = env_u32("GATB_SCHUNK", 128);
+    ctx->tile_budget = env_u32("GATB_TILE_BUDGET", 0);
+    ctx->batch = env_u32("GATB_BATCH", 0);
+    *out = ctx;
+    return GATB_OK;
+}
+
+extern "C" void gatb_destroy(gatb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char *gatb_last_error(gatb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int gatb_set_stream(gatb_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return GATB_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return GATB_OK;
+}
+
+extern "C" int gatb_synchronize(gatb_ctx *ctx)
+{
+    if (!ctx) return GATB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return GATB_OK;
+}
+
+extern "C" uint64_t gatb_launch_count(gatb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int gatb_set_batch_size(gatb_ctx *ctx, uint32_t batch)
+{
+    if (!ctx) return GATB_ERR_INVALID;
+    ctx->batch = batch;
+    return GATB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// validation helpers
+static int check_lists(gatb_ctx *ctx, const char *what, uint64_t n_lists, const uint64_t *offs,
+                       const uint32_t *start, const uint32_t *end)
+{
+    if (!offs) return fail(ctx, GATB_ERR_INVALID, std::string(what) + ": offsets are NULL");
+    if (offs[0] != 0) return fail(ctx, GATB_ERR_INVALID, std::string(what) + ": offsets must start at 0");
+    for (uint64_t l = 0; l < n_lists; l++) {
+        if (offs[l + 1] < offs[l]) return fail(ctx, GATB_ERR_INVALID, std::string(what) + ": offsets not monotone");
+        for (uint64_t i = offs[l]; i < offs[l + 1]; i++) {
+            if (end[i] >= 0x80000000u) return fail(ctx, GATB_ERR_RANGE, std::string(what) + ": coordinate >= 2^31");
+            if (start[i] >= end[i]) return fail(ctx, GATB_ERR_INVALID, std::string(what) + ": empty or inverted segment (list not normalized)");
+            if (i > offs[l] && end[i - 1] > start[i])
+                return fail(ctx, GATB_ERR_INVALID, std::string(what) + ": list not sorted/normalized");
+        }
+    }
+    return GATB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// annotations
+struct gatb_annotations {
+    gatb_ctx *ctx = nullptr;
+    uint32_t n_annot = 0, n_keys = 0, n_groups = 0, ka = 1;
+    uint32_t tile_budget = 0, max_tile = 0;
+    uint64_t n_intervals = 0;
+    DevBuf<uint8_t> tiles;
+    DevBuf<uint64_t> tile_off;
+    DevBuf<uint32_t> tile_bytes;
+    DevBuf<uint32_t> key_ws_nseg;
+    bool has_nseg = false;
+};
+
+static inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// bytes and index geometry of one (track, key) list inside a tile
+static void list_geometry(uint64_t n, uint32_t extent, uint32_t &iv_bytes, uint32_t &nbins, uint32_t &shift,
+                          uint32_t &idx_bytes)
+{
+    iv_bytes = align16((uint32_t)((n + 1) * 8));
+    nbins = 0; shift = 0; idx_bytes = 0;
+    if (n <= 65534) {
+        uint64_t target = std::max<uint64_t>(2 * n, 16);
+        while ((((uint64_t)extent >> shift) + 1) > target) shift++;
+        nbins = (extent >> shift) + 1;
+        idx_bytes = align16((nbins + 1) * 2);
+    }
+}
+
+extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
+                                       const uint32_t *start, const uint32_t *end, const uint32_t *key_ws_nseg,
+                                       gatb_annotations **out)
+{
+    if (!ctx || !out) return GATB_ERR_INVALID;
+    *out = nullptr;
+    if (n_annot <= 0 || n_keys <= 0) return fail(ctx, GATB_ERR_INVALID, "annotations: need >=1 track and >=1 key");
+    const uint64_t n_lists = (uint64_t)n_annot * n_keys;
+    int rc = check_lists(ctx, "annotations", n_lists, offs, start, end);
+    if (rc) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+
+    const uint32_t A = (uint32_t)n_annot, K = (uint32_t)n_keys;
+    // per-list geometry
+    std::vector<uint32_t> lbytes(n_lists);
+    for (uint64_t l = 0; l < n_lists; l++) {
+        uint64_t n = offs[l + 1] - offs[l];
+        uint32_t extent = n ? end[offs[l + 1] - 1] : 0;
+        uint32_t ivb, nb, sh, ib;
+        list_geometry(n, extent, ivb, nb, sh, ib);
+        lbytes[l] = ivb + ib;
+    }
+    // tile budget: what one CTA can opt in to, minus the accumulators
+    uint32_t budget = ctx->tile_budget;
+    if (budget == 0) {
+        size_t acc = (size_t)ctx->schunk_max * KMAX * 8 + 16;
+        budget = (uint32_t)(ctx->smem_optin > acc + 1024 ? ctx->smem_optin - acc - 1024 : 32768);
+    }
+    const uint32_t hdr = align16((uint32_t)sizeof(TileHeader));
+    // largest group size whose every tile fits; else the largest that fits most tiles (ka=1 floor)
+    uint32_t ka = 1;
+    for (uint32_t cand = KMAX; cand >= 1; cand--) {
+        uint32_t worst = 0;
+        for (uint32_t a0 = 0; a0 < A; a0 += cand)
+            for (uint32_t k = 0; k < K; k++) {
+                uint64_t b = hdr;
+                for (uint32_t a = a0; a < std::min(A, a0 + cand); a++) b += lbytes[(uint64_t)a * K + k];
+                worst = (uint32_t)std::max<uint64_t>(worst, std::min<uint64_t>(b, 0xffffffffu));
+            }
+        if (worst <= budget || cand == 1) { ka = cand; break; }
+    }
+    const uint32_t G = (A + ka - 1) / ka;
+
+    // build the blob
+    std::vector<uint64_t> tile_off((size_t)G * K);
+    std::vector<uint32_t> tile_bytes((size_t)G * K);
+    uint64_t total = 0;
+    uint32_t max_tile = 0;
+    for (uint32_t g = 0; g < G; g++)
+        for (uint32_t k = 0; k < K; k++) {
+            uint64_t b = hdr;
+            for (uint32_t a = g * ka; a < std::min(A, (g + 1) * ka); a++) b += lbytes[(uint64_t)a * K + k];
+            if (b > 0xfffffff0ull) return fail(ctx, GATB_ERR_INVALID, "annotations: tile larger than 4 GiB");
+            tile_off[(size_t)g * K + k] = total;
+            tile_bytes[(size_t)g * K + k] = (uint32_t)b;
+            max_tile = std::max(max_tile, (uint32_t)b);
+            total += b;
+        }
+    std::vector<uint8_t> blob(total);
+    for (uint32_t g = 0; g < G; g++)
+        for (uint32_t k = 0; k < K; k++) {
+            uint8_t *t = blob.data() + tile_off[(size_t)g * K + k];
+            TileHeader h;
+            memset(&h, 0, sizeof(h));
+            uint32_t o = hdr;
+            for (uint32_t kk = 0; kk < ka && g * ka + kk < A; kk++) {
+                const uint64_t l = (uint64_t)(g * ka + kk) * K + k;
+                const uint64_t n = offs[l + 1] - offs[l];
+                const uint32_t extent = n ? end[offs[l + 1] - 1] : 0;
+                uint32_t ivb, nb, sh, ib;
+                list_geometry(n, extent, ivb, nb, sh, ib);
+                h.iv_off[kk] = o; h.n[kk] = (uint32_t)n; h.nbins[kk] = nb; h.shift[kk] = sh;
+                uint32_t *iv = reinterpret_cast<uint32_t *>(t + o);
+                for (uint64_t i = 0; i < n; i++) { iv[2 * i] = start[offs[l] + i]; iv[2 * i + 1] = end[offs[l] + i]; }
+                iv[2 * n] = 0xffffffffu; iv[2 * n + 1] = 0xffffffffu;
+                o += ivb;
+                h.idx_off[kk] = o;
+                if (nb) {
+                    uint16_t *idx = reinterpret_cast<uint16_t *>(t + o);
+                    uint64_t j = 0;
+                    for (uint32_t b = 0; b < nb; b++) {
+                        const uint64_t pos = (uint64_t)b << sh;
+                        while (j < n && (uint64_t)end[offs[l] + j] <= pos) j++;
+                        idx[b] = (uint16_t)j;
+                    }
+                    idx[nb] = (uint16_t)n;
+                    o += ib;
+                }
+            }
+            memcpy(t, &h, sizeof(h));
+        }
+
+    gatb_annotations *a = new gatb_annotations();
+    a->ctx = ctx; a->n_annot = A; a->n_keys = K; a->n_groups = G; a->ka = ka;
+    a->tile_budget = std::min(budget, std::max(max_tile, hdr));
+    a->max_tile = max_tile;
+    a->n_intervals = offs[n_lists];
+    cudaError_t e = a->tiles.upload(blob.data(), blob.size(), ctx->stream);
+    if (e == cudaSuccess) e = a->tile_off.upload(tile_off.data(), tile_off.size(), ctx->stream);
+    if (e == cudaSuccess) e = a->tile_bytes.upload(tile_bytes.data(), tile_bytes.size(), ctx->stream);
+    if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, ctx->stream); a->has_nseg = true; }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // host vectors die at return
+    if (e != cudaSuccess) { delete a; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = a;
+    return GATB_OK;
+}
+
+extern "C" void gatb_annotations_destroy(gatb_annotations *a)
+{
+    if (!a) return;
+    cudaSetDevice(a->ctx->device);
+    delete a;
+}
+
+// fill the annotation side of CountParams and pick the sample chunk
+static void count_params_annos(const gatb_annotations *a, uint32_t n_samples, CountParams &p)
+{
+    const gatb_ctx *ctx = a->ctx;
+    p.tiles = a->tiles.p; p.tile_off = a->tile_off.p; p.tile_bytes = a->tile_bytes.p;
+    p.key_ws_nseg = a->has_nseg ? a->key_ws_nseg.p : nullptr;
+    p.n_annot = a->n_annot; p.n_keys = a->n_keys; p.n_groups = a->n_groups; p.ka = a->ka;
+    p.smem_tile_budget = a->tile_budget;
+    p.n_samples = n_samples;
+    // enough CTAs for ~4 waves, chunk a multiple of the warps per CTA
+    const uint32_t nwarps = (uint32_t)ctx->count_threads / 32;
+    const uint32_t target = (uint32_t)ctx->sm_count * 4;
+    uint32_t chunks = std::max(1u, (target + a->n_groups - 1) / a->n_groups);
+    uint32_t schunk = (n_samples + chunks - 1) / chunks;
+    schunk = ((schunk + nwarps - 1) / nwarps) * nwarps;
+    schunk = std::max(nwarps, std::min(schunk, ctx->schunk_max));
+    p.schunk = schunk;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// counting of explicit lists (observed counts, same-placement parity)
+extern "C" int gatb_count_lists(gatb_ctx *ctx, const gatb_annotations *annos, int n_counters, const int32_t *counters,
+                                uint64_t n_samples, const uint64_t *offs, const uint32_t *start, const uint32_t *end,
+                                const uint8_t *key_present, double *out)
+{
+    if (!ctx || !annos || !counters || !out || n_counters <= 0) return GATB_ERR_INVALID;
+    if (n_samples == 0) return GATB_OK;
+    if (n_samples > 0x7fffffffull) return fail(ctx, GATB_ERR_INVALID, "count_lists: too many samples");
+    const uint32_t K = annos->n_keys, A = annos->n_annot;
+    int rc = check_lists(ctx, "segments", n_samples * K, offs, start, end);
+    if (rc) return rc;
+    for (int c = 0; c < n_counters; c++) {
+        if (counters[c] < 0 || counters[c] >= GATB_NCOUNTERS) return fail(ctx, GATB_ERR_INVALID, "unknown counter id");
+        if (counters[c] == GATB_NUCLEOTIDE_DENSITY && !annos->has_nseg)
+            return fail(ctx, GATB_ERR_INVALID, "nucleotide-density needs key_ws_nseg at gatb_annotations_create");
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    // capacity layout: key k of sample s at s*stride + key_base[k]
+    std::vector<uint64_t> key_base(K);
+    std::vector<uint32_t> cap(K, 0);
+    for (uint64_t s = 0; s < n_samples; s++)
+        for (uint32_t k = 0; k < K; k++)
+            cap[k] = std::max<uint32_t>(cap[k], (uint32_t)(offs[s * K + k + 1] - offs[s * K + k]));
+    uint64_t stride = 0;
+    for (uint32_t k = 0; k < K; k++) { key_base[k] = stride; stride += cap[k]; }
+    if (stride == 0) stride = 1;
+    std::vector<uint64_t> packed(n_samples * stride, 0);
+    std::vector<uint32_t> counts(n_samples * K);
+    for (uint64_t s = 0; s < n_samples; s++)
+        for (uint32_t k = 0; k < K; k++) {
+            const uint64_t b = offs[s * K + k], n = offs[s * K + k + 1] - b;
+            counts[s * K + k] = (uint32_t)n;
+            uint64_t *dst = packed.data() + s * stride + key_base[k];
+            for (uint64_t i = 0; i < n; i++) dst[i] = pack_seg(start[b + i], end[b + i]);
+        }
+    DevBuf<uint64_t> d_packed, d_base;
+    DevBuf<uint32_t> d_n, d_out;
+    DevBuf<uint8_t> d_present;
+    DevBuf<double> d_outf;
+    CU(ctx, d_packed.upload(packed.data(), packed.size(), st));
+    CU(ctx, d_base.upload(key_base.data(), K, st));
+    CU(ctx, d_n.upload(counts.data(), counts.size(), st));
+    if (key_present) CU(ctx, d_present.upload(key_present, n_samples * K, st));
+    CU(ctx, d_out.alloc(n_samples * A));
+    CU(ctx, d_outf.alloc(n_samples * A));
+
+    CountParams p;
+    memset(&p, 0, sizeof(p));
+    count_params_annos(annos, (uint32_t)n_samples, p);
+    p.placed = d_packed.p; p.sample_stride = stride; p.key_base = d_base.p; p.placed_n = d_n.p;
+    p.key_present = key_present ? d_present.p : nullptr;
+    p.out_u32 = d_out.p; p.out_f64 = d_outf.p;
+
+    std::vector<uint32_t> h_u(n_samples * A);
+    for (int c = 0; c < n_counters; c++) {
+        CU(ctx, launch_count(st, counters[c], p, ctx->count_threads));
+        ctx->launches++;
+        double *o = out + (uint64_t)c * n_samples * A;
+        if (counters[c] == GATB_NUCLEOTIDE_DENSITY) {
+            CU(ctx, cudaMemcpyAsync(o, d_outf.p, n_samples * A * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(ctx, cudaStreamSynchronize(st));
+        } else {
+            CU(ctx, cudaMemcpyAsync(h_u.data(), d_out.p, n_samples * A * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(ctx, cudaStreamSynchronize(st));
+            for (uint64_t i = 0; i < n_samples * A; i++) o[i] = (double)h_u[i];
+        }
+    }
+    return GATB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sampler
+struct gatb_sampler {
+    gatb_ctx *ctx = nullptr;
+    uint32_t n_units = 0, n_contigs = 0;
+    bool has_iso = false;
+    std::vector<UnitDesc> h_units;
+    std::vector<uint64_t> h_contig_base;
+    std::vector<uint32_t> h_contig_cap;
+    uint64_t unit_stride = 0, placed_stride = 0;
+    DevBuf<UnitDesc> units;
+    DevBuf<uint32_t> order;
+    DevBuf<uint32_t> ws_start, ws_end, ws_cuminc, len_tab;
+    DevBuf<uint32_t> contig_unit_off, contig_units;
+    DevBuf<uint64_t> contig_base;
+    // batch buffers
+    uint32_t batch_alloc = 0;
+    DevBuf<uint64_t> unit_buf, placed;
+    DevBuf<uint32_t> unit_n, placed_n;
+    DevBuf<uint8_t> status;
+    DevBuf<unsigned long long> tally;     // [3]: placed segments, round-cap units, overflow units
+    DevBuf<uint32_t> out_tmp;
+    DevBuf<double> out_tmp_f;
+};
+
+extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *unit_contig, int n_contigs,
+                                   int has_isochores,
+                                   const uint64_t *seg_offs, const uint32_t *seg_start, const uint32_t *seg_end,
+                                   const uint64_t *ws_offs, const uint32_t *ws_start, const uint32_t *ws_end,
+                                   uint32_t bucket_size, uint32_t nbuckets, gatb_sampler **out)
+{
+    if (!ctx || !out) return GATB_ERR_INVALID;
+    *out = nullptr;
+    if (n_units <= 0 || n_contigs <= 0 || !unit_contig) return fail(ctx, GATB_ERR_INVALID, "sampler: need >=1 unit");
+    if (nbuckets == 0) return fail(ctx, GATB_ERR_INVALID, "sampler: nbuckets is 0");
+    const uint32_t U = (uint32_t)n_units, C = (uint32_t)n_contigs;
+    int rc = check_lists(ctx, "segments", U, seg_offs, seg_start, seg_end);
+    if (rc) return rc;
+    rc = check_lists(ctx, "workspace", U, ws_offs, ws_start, ws_end);
+    if (rc) return rc;
+    if (seg_offs[U] > 0x7fffffffull || ws_offs[U] > 0x7fffffffull)
+        return fail(ctx, GATB_ERR_INVALID, "sampler: more than 2^31 segments");
+    std::vector<uint32_t> per_contig(C, 0);
+    for (uint32_t u = 0; u < U; u++) {
+        if (unit_contig[u] < 0 || (uint32_t)unit_contig[u] >= C) return fail(ctx, GATB_ERR_INVALID, "sampler: unit_contig out of range");
+        if (seg_offs[u + 1] == seg_offs[u] || ws_offs[u + 1] == ws_offs[u])
+            return fail(ctx, GATB_ERR_INVALID, "sampler: units with empty segments or workspace must be skipped by the caller");
+        per_contig[unit_contig[u]]++;
+    }
+    if (!has_isochores)
+        for (uint32_t c = 0; c < C; c++)
+            if (per_contig[c] > 1) return fail(ctx, GATB_ERR_INVALID, "sampler: several units per contig need has_isochores");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    gatb_sampler *s = new gatb_sampler();
+    s->ctx = ctx; s->n_units = U; s->n_contigs = C; s->has_iso = has_isochores != 0;
+    // workspace CDF (SegmentListSampler.__init__, gat/Engine.pyx:261-277) and unit descriptors
+    std::vector<uint32_t> cuminc(ws_offs[U]);
+    s->h_units.resize(U);
+    std::vector<uint64_t> scratch_off(U);
+    uint64_t scratch_total = 0;
+    for (uint32_t u = 0; u < U; u++) {
+        UnitDesc &d = s->h_units[u];
+        memset(&d, 0, sizeof(d));
+        d.ws_off = (uint32_t)ws_offs[u]; d.ws_n = (uint32_t)(ws_offs[u + 1] - ws_offs[u]);
+        uint64_t t = 0;
+        for (uint64_t i = ws_offs[u]; i < ws_offs[u + 1]; i++) { t += ws_end[i] - ws_start[i]; cuminc[i] = (uint32_t)t; }
+        if (t > 0xffffffffull) { delete s; return fail(ctx, GATB_ERR_RANGE, "sampler: workspace unit larger than 2^32 bases"); }
+        d.ws_total = (uint32_t)t;
+        d.seg_off = (uint32_t)seg_offs[u]; d.seg_n = (uint32_t)(seg_offs[u + 1] - seg_offs[u]);
+        d.tab_off = d.seg_off;
+        d.contig = (uint32_t)unit_contig[u];
+        scratch_off[u] = scratch_total;
+        scratch_total += next_pow2(std::max(d.seg_n, 1u));
+    }
+    DevBuf<uint32_t> d_seg_start, d_seg_end;
+    DevBuf<uint64_t> d_scratch, d_scratch_off;
+    cudaError_t e = cudaSuccess;
+#define TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
+    TRY(d_seg_start.upload(seg_start, seg_offs[U], st));
+    TRY(d_seg_end.upload(seg_end, seg_offs[U], st));
+    TRY(s->ws_start.upload(ws_start, ws_offs[U], st));
+    TRY(s->ws_end.upload(ws_end, ws_offs[U], st));
+    TRY(s->ws_cuminc.upload(cuminc.data(), cuminc.size(), st));
+    TRY(s->units.upload(s->h_units.data(), U, st));
+    TRY(s->len_tab.alloc(seg_offs[U]));
+    TRY(d_scratch.alloc(scratch_total));
+    TRY(d_scratch_off.upload(scratch_off.data(), U, st));
+    if (e == cudaSuccess) {
+        launch_prep_units(st, s->units.p, U, d_seg_start.p, d_seg_end.p, s->ws_start.p, s->ws_end.p, s->ws_cuminc.p,
+                          s->len_tab.p, d_scratch.p, d_scratch_off.p, bucket_size, nbuckets);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    TRY(cudaMemcpyAsync(s->h_units.data(), s->units.p, U * sizeof(UnitDesc), cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+    if (e != cudaSuccess) { delete s; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    for (uint32_t u = 0; u < U; u++)
+        if (s->h_units[u].error) {
+            delete s;
+            return fail(ctx, GATB_ERR_TOO_LARGE,
+                        "segment too large: increase nbuckets or bucket_size such that nbuckets * bucket_size > largest segment");
+        }
+    uint64_t lsum = 0;
+    for (uint32_t u = 0; u < U; u++) lsum += (uint64_t)(uint32_t)s->h_units[u].ltotal;
+    if (lsum > 0xffffffffull) { delete s; return fail(ctx, GATB_ERR_RANGE, "sampler: more than 2^32 bases to place (uint32 counts would overflow)"); }
+
+    // buffer layout
+    s->h_contig_base.assign(C, 0);
+    s->h_contig_cap.assign(C, 0);
+    std::vector<uint32_t> cu_off(C + 1, 0), cu(U);
+    for (uint32_t u = 0; u < U; u++) cu_off[s->h_units[u].contig + 1]++;
+    for (uint32_t c = 0; c < C; c++) cu_off[c + 1] += cu_off[c];
+    {
+        std::vector<uint32_t> fill(cu_off.begin(), cu_off.end() - 1);
+        for (uint32_t u = 0; u < U; u++) cu[fill[s->h_units[u].contig]++] = u;
+    }
+    if (s->has_iso) {
+        uint64_t o = 0;
+        for (uint32_t u = 0; u < U; u++) { s->h_units[u].buf_off = o; o += s->h_units[u].cap; }
+        s->unit_stride = o;
+        uint64_t b = 0;
+        for (uint32_t c = 0; c < C; c++) {
+            uint64_t sum = 0;
+            for (uint32_t k = cu_off[c]; k < cu_off[c + 1]; k++) sum += s->h_units[cu[k]].cap;
+            s->h_contig_cap[c] = next_pow2((uint32_t)std::max<uint64_t>(sum, 1));
+            s->h_contig_base[c] = b;
+            b += s->h_contig_cap[c];
+        }
+        s->placed_stride = b;
+    } else {
+        uint64_t b = 0;
+        for (uint32_t c = 0; c < C; c++) {
+            uint32_t capc = 64;
+            for (uint32_t k = cu_off[c]; k < cu_off[c + 1]; k++) capc = s->h_units[cu[k]].cap;
+            s->h_contig_cap[c] = capc;
+            s->h_contig_base[c] = b;
+            for (uint32_t k = cu_off[c]; k < cu_off[c + 1]; k++) s->h_units[cu[k]].buf_off = b;
+            b += capc;
+        }
+        s->placed_stride = b;
+        s->unit_stride = 0;
+    }
+    std::vector<uint32_t> order(U);
+    for (uint32_t u = 0; u < U; u++) order[u] = u;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return s->h_units[a].tab_n > s->h_units[b].tab_n; });
+    TRY(cudaMemcpyAsync(s->units.p, s->h_units.data(), U * sizeof(UnitDesc), cudaMemcpyHostToDevice, st));
+    TRY(s->order.upload(order.data(), U, st));
+    TRY(s->contig_unit_off.upload(cu_off.data(), C + 1, st));
+    TRY(s->contig_units.upload(cu.data(), U, st));
+    TRY(s->contig_base.upload(s->h_contig_base.data(), C, st));
+    TRY(s->tally.alloc(3));
+    TRY(cudaStreamSynchronize(st));
+#undef TRY
+    if (e != cudaSuccess) { delete s; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = s;
+    return GATB_OK;
+}
+
+extern "C" void gatb_sampler_destroy(gatb_sampler *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    delete s;
+}
+
+extern "C" uint64_t gatb_sampler_sample_capacity(const gatb_sampler *s) { return s ? s->placed_stride : 0; }
+
+static uint32_t pick_batch(const gatb_sampler *s, uint64_t n_samples)
+{
+    uint64_t per_sample = (s->unit_stride + s->placed_stride) * 8 + (uint64_t)(s->n_units + s->n_contigs) * 5;
+    uint64_t b = s->ctx->batch ? s->ctx->batch : 4096;
+    const uint64_t limit = 24ull << 30;             // keep batch buffers under 24 GiB of the 180 GB HBM
+    b = std::min<uint64_t>(b, std::max<uint64_t>(1, limit / std::max<uint64_t>(per_sample, 1)));
+    b = std::min<uint64_t>(b, n_samples);
+    return (uint32_t)std::max<uint64_t>(b, 1);
+}
+
+static int ensure_batch(gatb_sampler *s, uint32_t B)
+{
+    gatb_ctx *ctx = s->ctx;
+    if (B <= s->batch_alloc) return GATB_OK;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, s->placed.alloc((uint64_t)B * s->placed_stride));
+    CU(ctx, s->placed_n.alloc((uint64_t)B * s->n_contigs));
+    if (s->has_iso) {
+        CU(ctx, s->unit_buf.alloc((uint64_t)B * s->unit_stride));
+        CU(ctx, s->unit_n.alloc((uint64_t)B * s->n_units));
+    }
+    CU(ctx, s->status.alloc((uint64_t)B * s->n_units));
+    s->batch_alloc = B;
+    return GATB_OK;
+}
+
+__global__ void tally_kernel(const uint32_t *placed_n, uint64_t n_placed, const uint8_t *status, uint64_t n_status,
+                             unsigned long long *tally)
+{
+    unsigned long long a = 0, r = 0, o = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_placed; i += (uint64_t)gridDim.x * blockDim.x)
+        a += placed_n[i];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_status; i += (uint64_t)gridDim.x * blockDim.x) {
+        r += (status[i] & UNIT_HIT_ROUND_CAP) ? 1 : 0;
+        o += (status[i] & UNIT_OVERFLOW) ? 1 : 0;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        a += __shfl_xor_sync(GATB_FULL, a, d);
+        r += __shfl_xor_sync(GATB_FULL, r, d);
+        o += __shfl_xor_sync(GATB_FULL, o, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(&tally[0], a);
+        if (r) atomicAdd(&tally[1], r);
+        if (o) atomicAdd(&tally[2], o);
+    }
+}
+
+// enqueue K1 (+K2) for one batch; result in s->placed / s->placed_n
+static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin, uint32_t B)
+{
+    gatb_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    PlaceParams p;
+    memset(&p, 0, sizeof(p));
+    p.units = s->units.p; p.order = s->order.p;
+    p.ws_start = s->ws_start.p; p.ws_end = s->ws_end.p; p.ws_cuminc = s->ws_cuminc.p; p.len_tab = s->len_tab.p;
+    if (s->has_iso) {
+        p.buf = s->unit_buf.p; p.sample_stride = s->unit_stride;
+        p.out_n = s->unit_n.p; p.out_n_stride = s->n_units; p.out_by_contig = 0;
+    } else {
+        p.buf = s->placed.p; p.sample_stride = s->placed_stride;
+        p.out_n = s->placed_n.p; p.out_n_stride = s->n_contigs; p.out_by_contig = 1;
+    }
+    p.status = s->status.p; p.n_units = s->n_units; p.n_samples = B; p.sample_begin = sample_begin;
+    p.seed = seed; p.track = track;
+    launch_place(st, p);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    if (s->has_iso) {
+        MergeParams m;
+        memset(&m, 0, sizeof(m));
+        m.units = s->units.p; m.contig_unit_off = s->contig_unit_off.p; m.contig_units = s->contig_units.p;
+        m.contig_base = s->contig_base.p; m.unit_buf = s->unit_buf.p; m.unit_stride = s->unit_stride;
+        m.unit_n = s->unit_n.p; m.placed = s->placed.p; m.placed_stride = s->placed_stride;
+        m.placed_n = s->placed_n.p; m.n_units = s->n_units; m.n_contigs = s->n_contigs; m.n_samples = B;
+        launch_contig_merge(st, m);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+    }
+    tally_kernel<<<std::min<uint32_t>(1024, (uint32_t)(((uint64_t)B * s->n_units + 255) / 256)), 256, 0, st>>>(
+        s->placed_n.p, (uint64_t)B * s->n_contigs, s->status.p, (uint64_t)B * s->n_units, s->tally.p);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    return GATB_OK;
+}
+
+extern "C" int gatb_sampler_place(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin,
+                                  uint64_t n_samples, uint32_t *start, uint32_t *end, uint32_t *counts,
+                                  uint64_t *contig_base, uint8_t *unit_status)
+{
+    if (!s || !start || !end || !counts) return GATB_ERR_INVALID;
+    gatb_ctx *ctx = s->ctx;
+    if (sample_begin + n_samples > 0xffffffffull) return fail(ctx, GATB_ERR_RANGE, "sample index >= 2^32");
+    if (track >= (1u << 24)) return fail(ctx, GATB_ERR_RANGE, "track index >= 2^24");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (contig_base) for (uint32_t c = 0; c < s->n_contigs; c++) contig_base[c] = s->h_contig_base[c];
+    const uint32_t B = pick_batch(s, n_samples);
+    int rc = ensure_batch(s, B);
+    if (rc) return rc;
+    CU(ctx, cudaMemsetAsync(s->tally.p, 0, 3 * sizeof(unsigned long long), st));
+    std::vector<uint64_t> h((uint64_t)B * s->placed_stride);
+    for (uint64_t done = 0; done < n_samples; done += B) {
+        const uint32_t b = (uint32_t)std::min<uint64_t>(B, n_samples - done);
+        rc = place_batch(s, seed, track, sample_begin + done, b);
+        if (rc) return rc;
+        CU(ctx, cudaMemcpyAsync(h.data(), s->placed.p, (uint64_t)b * s->placed_stride * 8, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(counts + done * s->n_contigs, s->placed_n.p, (uint64_t)b * s->n_contigs * 4, cudaMemcpyDeviceToHost, st));
+        if (unit_status)
+            CU(ctx, cudaMemcpyAsync(unit_status + done * s->n_units, s->status.p, (uint64_t)b * s->n_units, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+        for (uint64_t sl = 0; sl < b; sl++)
+            for (uint32_t c = 0; c < s->n_contigs; c++) {
+                const uint32_t n = counts[(done + sl) * s->n_contigs + c];
+                const uint64_t src = sl * s->placed_stride + s->h_contig_base[c];
+                const uint64_t dst = (done + sl) * s->placed_stride + s->h_contig_base[c];
+                for (uint32_t i = 0; i < n; i++) { start[dst + i] = seg_start(h[src + i]); end[dst + i] = seg_end(h[src + i]); }
+            }
+    }
+    unsigned long long tally[3];
+    CU(ctx, cudaMemcpyAsync(tally, s->tally.p, sizeof(tally), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    if (tally[2]) return fail(ctx, GATB_ERR_CAPACITY, "placement unit overflowed its segment buffer");
+    return GATB_OK;
+}
+
+extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_counters, const int32_t *counters,
+                        uint64_t seed, uint32_t track, uint64_t sample_begin, uint64_t n_samples,
+                        uint32_t *out_counts, double *out_density, int out_is_device, uint64_t *info)
+{
+    if (!s || !annos || !counters || n_counters <= 0) return GATB_ERR_INVALID;
+    gatb_ctx *ctx = s->ctx;
+    if (annos->ctx != ctx) return fail(ctx, GATB_ERR_INVALID, "run: sampler and annotations belong to different contexts");
+    if (annos->n_keys != s->n_contigs) return fail(ctx, GATB_ERR_INVALID, "run: annotations keys != sampler contigs");
+    if (sample_begin + n_samples > 0xffffffffull) return fail(ctx, GATB_ERR_RANGE, "sample index >= 2^32");
+    if (track >= (1u << 24)) return fail(ctx, GATB_ERR_RANGE, "track index >= 2^24");
+    bool any_int = false, any_density = false;
+    for (int c = 0; c < n_counters; c++) {
+        if (counters[c] < 0 || counters[c] >= GATB_NCOUNTERS) return fail(ctx, GATB_ERR_INVALID, "unknown counter id");
+        if (counters[c] == GATB_NUCLEOTIDE_DENSITY) any_density = true; else any_int = true;
+    }
+    if (any_density && (!annos->has_nseg || !out_density)) return fail(ctx, GATB_ERR_INVALID, "nucleotide-density needs key_ws_nseg and out_density");
+    if (any_int && !out_counts) return fail(ctx, GATB_ERR_INVALID, "run: out_counts is NULL");
+    if (n_samples == 0) return GATB_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t A = annos->n_annot;
+    const uint32_t B = pick_batch(s, n_samples);
+    int rc = ensure_batch(s, B);
+    if (rc) return rc;
+    if (!out_is_device) {
+        if (any_int) CU(ctx, s->out_tmp.ensure((uint64_t)B * A));
+        if (any_density) CU(ctx, s->out_tmp_f.ensure((uint64_t)B * A));
+    }
+    CU(ctx, cudaMemsetAsync(s->tally.p, 0, 3 * sizeof(unsigned long long), st));
+
+    for (uint64_t done = 0; done < n_samples; done += B) {
+        const uint32_t b = (uint32_t)std::min<uint64_t>(B, n_samples - done);
+        rc = place_batch(s, seed, track, sample_begin + done, b);
+        if (rc) return rc;
+        CountParams p;
+        memset(&p, 0, sizeof(p));
+        count_params_annos(annos, b, p);
+        p.placed = s->placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
+        p.placed_n = s->placed_n.p; p.key_present = nullptr;
+        for (int c = 0; c < n_counters; c++) {
+            const bool dens = counters[c] == GATB_NUCLEOTIDE_DENSITY;
+            uint32_t *dst_u = out_counts ? out_counts + ((uint64_t)c * n_samples + done) * A : nullptr;
+            double *dst_f = out_density ? out_density + done * A : nullptr;
+            p.out_u32 = out_is_device ? dst_u : s->out_tmp.p;
+            p.out_f64 = out_is_device ? dst_f : s->out_tmp_f.p;
+            CU(ctx, launch_count(st, counters[c], p, ctx->count_threads));
+            ctx->launches++;
+            if (!out_is_device) {
+                if (dens) CU(ctx, cudaMemcpyAsync(dst_f, s->out_tmp_f.p, (uint64_t)b * A * sizeof(double), cudaMemcpyDeviceToHost, st));
+                else CU(ctx, cudaMemcpyAsync(dst_u, s->out_tmp.p, (uint64_t)b * A * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            }
+        }
+    }
+    unsigned long long tally[3];
+    CU(ctx, cudaMemcpyAsync(tally, s->tally.p, sizeof(tally), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    if (info) { info[0] = tally[0]; info[1] = tally[1]; info[2] = tally[2]; }
+    if (tally[2]) return fail(ctx, GATB_ERR_CAPACITY, "placement unit overflowed its segment buffer");
+    return GATB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// column statistics
+extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float, int counts_is_device,
+                                 uint64_t n_samples, int n_cols, const double *observed, const double *ref_fold,
+                                 double pseudo_count, double *expected, double *stddev, double *lower95,
+                                 double *upper95, double *fold, double *pvalue)
+{
+    if (!ctx || !counts || !observed || n_cols <= 0) return GATB_ERR_INVALID;
+    if (n_samples < 1) return fail(ctx, GATB_ERR_INVALID, "column_stats: no samples");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t A = (uint32_t)n_cols;
+    const uint64_t l = n_samples;
+    const size_t esz = is_float ? sizeof(double) : sizeof(uint32_t);
+    DevBuf<uint8_t> d_counts;
+    const void *dc = counts;
+    if (!counts_is_device) {
+        CU(ctx, d_counts.upload((const uint8_t *)counts, l * A * esz, st));
+        dc = d_counts.p;
+    }
+    std::vector<double> obs_eff(A);
+    for (uint32_t a = 0; a < A; a++) {
+        if (ref_fold) {
+            if (!(ref_fold[a] > 0)) return fail(ctx, GATB_ERR_INVALID, "0 fold change not applicable");
+            obs_eff[a] = observed[a] / ref_fold[a];
+        } else obs_eff[a] = observed[a];
+    }
+    DevBuf<double> d_obs, d_sum, d_sq, d_mean, d_qlo, d_qhi;
+    DevBuf<unsigned long long> d_cnt;
+    CU(ctx, d_obs.upload(obs_eff.data(), A, st));
+    CU(ctx, d_sum.alloc(A)); CU(ctx, d_sq.alloc(A)); CU(ctx, d_qlo.alloc(A)); CU(ctx, d_qhi.alloc(A));
+    CU(ctx, d_cnt.alloc(3 * (size_t)A));
+
+    StatsParams p;
+    memset(&p, 0, sizeof(p));
+    p.counts = dc; p.is_float = is_float; p.n_samples = l; p.n_cols = A; p.observed = d_obs.p;
+    p.sum = d_sum.p; p.sumsq_dev = d_sq.p; p.n_trunc_lt = d_cnt.p; p.n_lt = d_cnt.p + A; p.n_eq = d_cnt.p + 2 * (size_t)A;
+    p.q_lo = d_qlo.p; p.q_hi = d_qhi.p;
+    // CI ranks (gat/Engine.pyx:1689-1696)
+    const uint64_t off = (uint64_t)(0.05 * (double)l);
+    if (off > 0) { p.rank_lo = std::min<uint64_t>(off, l - 1); p.rank_hi = (l > off) ? l - off : 0; }
+    else { p.rank_lo = 0; p.rank_hi = l - 1; }
+    launch_stats_pass1(st, p); ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    std::vector<double> h_sum(A), h_sq(A), h_qlo(A), h_qhi(A), h_mean(A);
+    std::vector<unsigned long long> h_cnt(3 * (size_t)A);
+    CU(ctx, cudaMemcpyAsync(h_sum.data(), d_sum.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    for (uint32_t a = 0; a < A; a++) h_mean[a] = h_sum[a] / (double)l;        // numpy.mean (:1671)
+    CU(ctx, d_mean.upload(h_mean.data(), A, st));
+    p.mean = d_mean.p;
+    launch_stats_pass2(st, p); ctx->launches++;
+    launch_stats_select(st, p, nullptr); ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(h_sq.data(), d_sq.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(h_qlo.data(), d_qlo.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(h_qhi.data(), d_qhi.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt.p, 3 * (size_t)A * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+
+    for (uint32_t a = 0; a < A; a++) {
+        double exp_ = h_mean[a];
+        if (ref_fold) exp_ *= ref_fold[a];                                    // :1673-1676
+        const double fo = (exp_ != 0) ? (observed[a] + pseudo_count) / (exp_ + pseudo_count) : 1.0;   // :1679-1682
+        double lo = h_qlo[a], hi = h_qhi[a];
+        if (ref_fold) { lo *= ref_fold[a]; hi *= ref_fold[a]; }              // :1713-1714
+        // getTwoSidedPValue (:1543-1576) from counts instead of a sorted copy
+        const uint64_t idx0 = h_cnt[a], n_lt = h_cnt[A + a], n_eq = h_cnt[2 * (size_t)A + a];
+        const bool first_is_eq = (n_lt == idx0) && n_eq > 0;                  // sorted[idx0] == val
+        uint64_t idx = idx0;
+        if (idx0 == l) idx = 1;
+        else if (obs_eff[a] > exp_) {
+            if (first_is_eq && idx0 > 0) idx = idx0 - 1;
+            idx = l - (idx + 1);
+        } else {
+            if (first_is_eq) idx = idx0 + n_eq;
+        }
+        const double pv = std::max(1.0 / (double)l, (double)idx / (double)l);
+        if (expected) expected[a] = exp_;
+        if (stddev) stddev[a] = std::sqrt(h_sq[a] / (double)l);              // numpy.std ddof 0 (:1684)
+        if (lower95) lower95[a] = lo;
+        if (upper95) upper95[a] = hi;
+        if (fold) fold[a] = fo;
+        if (pvalue) pvalue[a] = pv;
+    }
+    return GATB_OK;
+}

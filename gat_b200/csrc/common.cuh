@@ -1,0 +1,252 @@
+// common.cuh -- shared device helpers for the gat_b200 kernels (sm_100a).
+//
+// Segments are packed as uint64 = (start << 32) | end so that an unsigned 64-bit compare orders by
+// start (then end), one 8-byte load fetches a segment, and a warp reads 32 segments as one 256-byte
+// coalesced request.  All kernels are warp-synchronous: one warp owns one work unit.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GATB_FULL 0xffffffffu
+#define GATB_KEY_INF 0xffffffffffffffffull
+
+namespace gatb {
+
+__host__ __device__ __forceinline__ uint64_t pack_seg(uint32_t s, uint32_t e) { return ((uint64_t)s << 32) | e; }
+__host__ __device__ __forceinline__ uint32_t seg_start(uint64_t k) { return (uint32_t)(k >> 32); }
+__host__ __device__ __forceinline__ uint32_t seg_end(uint64_t k) { return (uint32_t)k; }
+
+__host__ __device__ __forceinline__ uint32_t next_pow2(uint32_t x)
+{
+    uint32_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  RNG contract: counter = (turn, block | track<<8,
+// unit, sample), key = 64-bit seed.  Must stay bit-identical to oracle/gat_oracle.c:go_philox4x32_10.
+struct Philox4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// floor(r64 * range / 2^64) for range < 2^32, r64 = rhi:rlo  -- unbiased to 2^-32 relative
+__host__ __device__ __forceinline__ uint32_t bounded_u32(uint32_t rlo, uint32_t rhi, uint32_t range)
+{
+    return (uint32_t)(((uint64_t)rhi * range + (((uint64_t)rlo * range) >> 32)) >> 32);
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------
+// warp primitives
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ int32_t warp_incl_scan_add(int32_t v)
+{
+    int lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int32_t t = __shfl_up_sync(GATB_FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan_add_u32(uint32_t v)
+{
+    int lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(GATB_FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int32_t warp_incl_scan_max(int32_t v)
+{
+    int lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int32_t t = __shfl_up_sync(GATB_FULL, v, d);
+        if (lane >= d) v = max(v, t);
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src)
+{
+    uint32_t lo = __shfl_sync(GATB_FULL, (uint32_t)v, src);
+    uint32_t hi = __shfl_sync(GATB_FULL, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m)
+{
+    uint32_t lo = __shfl_xor_sync(GATB_FULL, (uint32_t)v, m);
+    uint32_t hi = __shfl_xor_sync(GATB_FULL, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Warp bitonic sort of N = 2^k packed segments (ascending).  Strides >= 32 exchange through memory,
+// strides < 32 run in registers with shuffles (one load + one store per 32-element block and k-phase).
+// Replaces SegmentList.sort() (gat/SegmentList.pyx:478-486, libc qsort by start).
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t *buf, uint32_t N)
+{
+    const int lane = lane_id();
+    if (N <= 1) return;
+    for (uint32_t k = 2; k <= N; k <<= 1) {
+        uint32_t j = k >> 1;
+        for (; j >= 32; j >>= 1) {
+            for (uint32_t t = lane; t < (N >> 1); t += 32) {
+                uint32_t i = 2 * t - (t & (j - 1));
+                uint32_t p = i + j;
+                uint64_t a = buf[i], b = buf[p];
+                bool asc = ((i & k) == 0);
+                if ((a > b) == asc) { buf[i] = b; buf[p] = a; }
+            }
+            __syncwarp();
+        }
+        // register phase: strides min(k/2,16) .. 1 inside each aligned block of 32
+        if (N >= 32) {
+            for (uint32_t b0 = 0; b0 < N; b0 += 32) {
+                uint32_t i = b0 + lane;
+                uint64_t x = buf[i];
+                bool asc = ((i & k) == 0);
+#pragma unroll
+                for (uint32_t jj = 16; jj > 0; jj >>= 1) {
+                    if (jj <= j) {
+                        uint64_t y = shfl_xor_u64(x, jj);
+                        bool lower = ((lane & jj) == 0);
+                        bool keep_min = (lower == asc);
+                        x = keep_min ? (x < y ? x : y) : (x > y ? x : y);
+                    }
+                }
+                buf[i] = x;
+            }
+            __syncwarp();
+        } else {
+            // N < 32: a single partial block; lanes >= N carry +inf and never move below N
+            uint32_t i = lane;
+            uint64_t x = (i < N) ? buf[i] : GATB_KEY_INF;
+            bool asc = ((i & k) == 0);
+#pragma unroll
+            for (uint32_t jj = 16; jj > 0; jj >>= 1) {
+                if (jj <= j) {
+                    uint64_t y = shfl_xor_u64(x, jj);
+                    bool lower = ((lane & jj) == 0);
+                    bool keep_min = (lower == asc);
+                    x = keep_min ? (x < y ? x : y) : (x > y ? x : y);
+                }
+            }
+            if (i < N) buf[i] = x;
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// In-place merge(0) of a SORTED run of n packed segments (gat/SegmentList.pyx:756-816 with
+// distance 0, after its sort): drop empty segments, join when start <= running max end (overlapping
+// AND adjacent).  Returns the new count.  Warp-cooperative: prefix-max of ends across lanes, heads
+// compacted with ballot/popc; the end of a merged segment is patched when the next head is met.
+__device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n)
+{
+    const int lane = lane_id();
+    int32_t carry = -1;          // running max end of everything seen (int32 like the reference)
+    uint32_t nout = 0;
+    for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+        uint32_t i = b0 + lane;
+        uint64_t x = (i < n) ? buf[i] : 0;
+        int32_t s = (int32_t)seg_start(x), e = (int32_t)seg_end(x);
+        bool valid = (i < n) && (s != e);
+        int32_t ev = valid ? e : -1;
+        int32_t incl = warp_incl_scan_max(ev);
+        int32_t excl = __shfl_up_sync(GATB_FULL, incl, 1);
+        if (lane == 0) excl = -1;
+        int32_t prev_max = max(carry, excl);
+        bool head = valid && (s > prev_max);
+        uint32_t hmask = __ballot_sync(GATB_FULL, head);
+        uint32_t pos = nout + __popc(hmask & ((1u << lane) - 1));
+        __syncwarp();                           // all lanes have read their element before any write
+        if (head) {
+            // high word = start of the new merged segment; low word (end) patched later
+            reinterpret_cast<uint32_t *>(buf + pos)[1] = (uint32_t)s;
+            if (pos > 0) reinterpret_cast<uint32_t *>(buf + pos - 1)[0] = (uint32_t)prev_max;
+        }
+        nout += __popc(hmask);
+        carry = max(carry, __shfl_sync(GATB_FULL, incl, 31));
+        __syncwarp();
+    }
+    if (nout > 0 && lane == 0) reinterpret_cast<uint32_t *>(buf + nout - 1)[0] = (uint32_t)carry;
+    __syncwarp();
+    return nout;
+}
+
+// sort + merge(0) of n arbitrary packed segments in a buffer with at least next_pow2(n) slots
+__device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n)
+{
+    if (n == 0) return 0;
+    const int lane = lane_id();
+    uint32_t N = next_pow2(n);
+    for (uint32_t i = n + lane; i < N; i += 32) buf[i] = GATB_KEY_INF;
+    __syncwarp();
+    warp_bitonic_sort(buf, N);
+    return warp_merge0_sorted(buf, n);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Workspace of one unit: sorted disjoint pieces + inclusive cumulative lengths.
+struct WsView {
+    const uint32_t *start;
+    const uint32_t *end;
+    const uint32_t *cuminc;   // cuminc[i] = sum_{j<=i} len_j   (SegmentListSampler.cdf + 1, gat/Engine.pyx:274-277)
+    uint32_t n;
+};
+
+// workspace bases in [0, x): prefix-coverage closed form -- replaces the two-pointer
+// SegmentList.intersect + sum (gat/SegmentList.pyx:1469-1549, :1607-1616) used at every checkpoint.
+__device__ __forceinline__ uint32_t ws_cov(const WsView &w, uint32_t x)
+{
+    if (w.n == 1) {
+        uint32_t s = w.start[0], e = w.end[0];
+        return x <= s ? 0u : (min(x, e) - s);
+    }
+    uint32_t lo = 0, hi = w.n;
+    while (lo < hi) {                       // number of pieces with start < x
+        uint32_t mid = (lo + hi) >> 1;
+        if (w.start[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0) return 0u;
+    uint32_t p = lo - 1;
+    uint32_t before = p ? w.cuminc[p - 1] : 0u;
+    return before + (min(x, w.end[p]) - w.start[p]);
+}
+
+__device__ __forceinline__ uint32_t ws_overlap(const WsView &w, uint32_t s, uint32_t e)
+{
+    return ws_cov(w, e) - ws_cov(w, s);
+}
+#endif  // __CUDACC__
+
+}  // namespace gatb

@@ -1,0 +1,307 @@
+// count.cu -- K3/K4 counting kernel and K5 column statistics.  sm_100a.
+//
+// Counting: a CTA owns (group of <= KMAX annotation tracks) x (chunk of samples) and walks the keys
+// (contigs) in order.  Per key it stages the group's tile (intervals + bin index) in shared memory,
+// then every warp streams its samples' segments on that key through the tile: lane = segment,
+// KMAX independent lookups per lane (register accumulators, ILP across tracks), warp `redux` per
+// track, and a shared-memory accumulator per (sample, track) that is only ever touched by the
+// owning warp -- no atomics, deterministic, and the float64 nucleotide-density sum runs in the same
+// key order as the reference's Python sum() (gat/__init__.py:583-587).
+#include "count.cuh"
+#include "../../include/gat_b200.h"
+
+namespace gatb {
+
+// ---------------------------------------------------------------------------------------------------
+// one segment [s,e) (previous segment of the same list ends at pe) against one annotation track
+template <int COUNTER, bool INDEXED>
+__device__ __forceinline__ uint32_t lookup(const uint2 *__restrict__ iv, const uint16_t *__restrict__ idx,
+                                           uint32_t n, uint32_t nbins, uint32_t shift,
+                                           uint32_t s, uint32_t e, uint32_t pe)
+{
+    uint32_t j;
+    uint2 a;
+    if (INDEXED) {
+        uint32_t b = min(s >> shift, nbins);
+        j = idx[b];
+        a = iv[j];
+        while (a.y <= s) a = iv[++j];           // sentinel end 0xffffffff stops the scan
+    } else {
+        uint32_t lo = 0, hi = n;                // first j with end > s (lower_bound, utils/gat_utils.c:8-32)
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (iv[mid].y <= s) lo = mid + 1; else hi = mid;
+        }
+        j = lo;
+        a = iv[j];
+    }
+    uint32_t r = 0;
+    if (COUNTER == GATB_SEGMENT_OVERLAP) {
+        // intersectionWithSegments(base), gat/SegmentList.pyx:1078-1146: segment counts once
+        r = (a.x < e) ? 1u : 0u;
+    } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
+        // midpoint tested against the FIRST overlapping interval only (:1137-1144)
+        uint32_t mid = s + ((e - s) >> 1);
+        r = (a.x < e && a.x <= mid && mid < a.y) ? 1u : 0u;
+    } else if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
+        // overlapWithSegments, gat/SegmentList.pyx:1026-1076
+        while (a.x < e) { r += min(e, a.y) - max(s, a.x); a = iv[++j]; }
+    } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
+        // roles swapped: an interval is counted by the first segment overlapping it, i.e. when it
+        // does not already overlap the previous segment (start >= pe)
+        while (a.x < e) { r += (a.x >= pe) ? 1u : 0u; a = iv[++j]; }
+    } else {  // GATB_ANNOTATION_MIDOVERLAP
+        while (a.x < e) {
+            if (a.x >= pe) { uint32_t m = a.x + ((a.y - a.x) >> 1); r += (s <= m && m < e) ? 1u : 0u; }
+            a = iv[++j];
+        }
+    }
+    return r;
+}
+
+template <int COUNTER, bool DENSITY>
+__global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    // layout: [acc: schunk*KMAX*(DENSITY?8:4) bytes][tile]
+    const uint32_t acc_bytes = p.schunk * KMAX * (DENSITY ? 8u : 4u);
+    uint32_t *acc_u = reinterpret_cast<uint32_t *>(smem);
+    double *acc_d = reinterpret_cast<double *>(smem);
+    uint8_t *tile_s = smem + ((acc_bytes + 15u) & ~15u);
+
+    const uint32_t g = blockIdx.x;
+    const uint32_t a0 = g * p.ka;
+    const uint32_t ka = min(p.ka, p.n_annot - a0);
+    const uint32_t s_begin = blockIdx.y * p.schunk;
+    const uint32_t s_end = min(s_begin + p.schunk, p.n_samples);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool need_prev = (COUNTER == GATB_ANNOTATION_OVERLAP || COUNTER == GATB_ANNOTATION_MIDOVERLAP);
+
+    for (uint32_t i = threadIdx.x; i < p.schunk * KMAX; i += blockDim.x) {
+        if (DENSITY) acc_d[i] = 0.0; else acc_u[i] = 0u;
+    }
+
+    for (uint32_t k = 0; k < p.n_keys; k++) {
+        const uint32_t tbytes = p.tile_bytes[(uint64_t)g * p.n_keys + k];
+        const uint8_t *tile_g = p.tiles + p.tile_off[(uint64_t)g * p.n_keys + k];
+        const bool staged = tbytes <= p.smem_tile_budget;
+        __syncthreads();                                  // previous tile fully consumed / acc init
+        if (staged) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(tile_g);
+            uint4 *dst = reinterpret_cast<uint4 *>(tile_s);
+            for (uint32_t i = threadIdx.x; i < (tbytes >> 4); i += blockDim.x) dst[i] = src[i];
+            __syncthreads();
+        }
+        const uint8_t *tile = staged ? tile_s : tile_g;
+        const TileHeader *h = reinterpret_cast<const TileHeader *>(tile);
+        const double den = DENSITY ? (double)p.key_ws_nseg[k] : 1.0;
+        if (DENSITY && p.key_ws_nseg[k] == 0) continue;   // counter returns 0 (gat/Engine.pyx:1438-1440)
+
+        for (uint32_t sl = s_begin + warp; sl < s_end; sl += nwarps) {
+            if (p.key_present && !p.key_present[(uint64_t)sl * p.n_keys + k]) continue;
+            const uint32_t n = p.placed_n[(uint64_t)sl * p.n_keys + k];
+            if (n == 0) continue;
+            const uint64_t *segs = p.placed + (uint64_t)sl * p.sample_stride + p.key_base[k];
+            uint32_t acc[KMAX];
+#pragma unroll
+            for (int kk = 0; kk < KMAX; kk++) acc[kk] = 0;
+            for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+                const uint32_t i = b0 + lane;
+                if (i < n) {
+                    const uint64_t x = segs[i];
+                    const uint32_t s = seg_start(x), e = seg_end(x);
+                    uint32_t pe = 0;
+                    if (need_prev && i > 0) pe = seg_end(segs[i - 1]);
+#pragma unroll
+                    for (int kk = 0; kk < KMAX; kk++) {
+                        if ((uint32_t)kk < ka) {
+                            const uint2 *iv = reinterpret_cast<const uint2 *>(tile + h->iv_off[kk]);
+                            const uint16_t *idx = reinterpret_cast<const uint16_t *>(tile + h->idx_off[kk]);
+                            const uint32_t nb = h->nbins[kk];
+                            if (nb) acc[kk] += lookup<COUNTER, true>(iv, idx, h->n[kk], nb, h->shift[kk], s, e, pe);
+                            else acc[kk] += lookup<COUNTER, false>(iv, idx, h->n[kk], nb, h->shift[kk], s, e, pe);
+                        }
+                    }
+                }
+            }
+            uint32_t mine = 0;
+#pragma unroll
+            for (int kk = 0; kk < KMAX; kk++) {
+                uint32_t tot = __reduce_add_sync(GATB_FULL, acc[kk]);
+                if (lane == kk) mine = tot;
+            }
+            if ((uint32_t)lane < ka) {
+                const uint32_t slot = (sl - s_begin) * KMAX + lane;
+                if (DENSITY) acc_d[slot] += (double)mine / den;   // float(overlap) / len(workspace)
+                else acc_u[slot] += mine;
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < (s_end - s_begin) * KMAX; i += blockDim.x) {
+        const uint32_t sl = s_begin + i / KMAX, kk = i % KMAX;
+        if (kk < ka) {
+            if (DENSITY) p.out_f64[(uint64_t)sl * p.n_annot + a0 + kk] = acc_d[i];
+            else p.out_u32[(uint64_t)sl * p.n_annot + a0 + kk] = acc_u[i];
+        }
+    }
+}
+
+template <int COUNTER, bool DENSITY>
+static cudaError_t launch_count_t(cudaStream_t st, const CountParams &p, int threads)
+{
+    const uint32_t acc_bytes = (p.schunk * KMAX * (DENSITY ? 8u : 4u) + 15u) & ~15u;
+    const size_t smem = (size_t)acc_bytes + p.smem_tile_budget;
+    cudaError_t e = cudaFuncSetAttribute(count_kernel<COUNTER, DENSITY>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(p.n_groups, (p.n_samples + p.schunk - 1) / p.schunk);
+    count_kernel<COUNTER, DENSITY><<<grid, threads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int threads)
+{
+    if (p.n_samples == 0 || p.n_annot == 0) return cudaSuccess;
+    switch (counter) {
+    case GATB_NUCLEOTIDE_OVERLAP:    return launch_count_t<GATB_NUCLEOTIDE_OVERLAP, false>(st, p, threads);
+    case GATB_NUCLEOTIDE_DENSITY:    return launch_count_t<GATB_NUCLEOTIDE_OVERLAP, true>(st, p, threads);
+    case GATB_SEGMENT_OVERLAP:       return launch_count_t<GATB_SEGMENT_OVERLAP, false>(st, p, threads);
+    case GATB_SEGMENT_MIDOVERLAP:    return launch_count_t<GATB_SEGMENT_MIDOVERLAP, false>(st, p, threads);
+    case GATB_ANNOTATION_OVERLAP:    return launch_count_t<GATB_ANNOTATION_OVERLAP, false>(st, p, threads);
+    case GATB_ANNOTATION_MIDOVERLAP: return launch_count_t<GATB_ANNOTATION_MIDOVERLAP, false>(st, p, threads);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5 column statistics (gat/Engine.pyx:1635-1718, :1543-1576).  One CTA per column.
+template <typename T>
+__device__ __forceinline__ T block_reduce_sum(T v, T *scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(GATB_FULL, v, d);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    T t = (threadIdx.x < (unsigned)nw) ? scratch[threadIdx.x] : (T)0;
+    if (warp == 0) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(GATB_FULL, t, d);
+    }
+    return t;   // valid in thread 0
+}
+
+__device__ __forceinline__ double load_val(const StatsParams &p, uint64_t s, uint32_t col)
+{
+    if (p.is_float) return reinterpret_cast<const double *>(p.counts)[s * p.n_cols + col];
+    return (double)reinterpret_cast<const uint32_t *>(p.counts)[s * p.n_cols + col];
+}
+
+__global__ void __launch_bounds__(256) stats_pass1_kernel(StatsParams p)
+{
+    __shared__ unsigned long long su[32];
+    __shared__ double sd[32];
+    const uint32_t col = blockIdx.x;
+    const double obs = p.observed[col];
+    unsigned long long isum = 0, ntl = 0, nlt = 0, neq = 0;
+    double fsum = 0.0;
+    for (uint64_t s = threadIdx.x; s < p.n_samples; s += blockDim.x) {
+        double x;
+        if (p.is_float) { x = reinterpret_cast<const double *>(p.counts)[s * p.n_cols + col]; fsum += x; }
+        else { uint32_t v = reinterpret_cast<const uint32_t *>(p.counts)[s * p.n_cols + col]; isum += v; x = (double)v; }
+        ntl += ((int)(x - obs) < 0) ? 1ull : 0ull;      // cmpDouble truncates (gat/SegmentList.pyx:135-136)
+        nlt += (x < obs) ? 1ull : 0ull;
+        neq += (x == obs) ? 1ull : 0ull;
+    }
+    unsigned long long r;
+    r = block_reduce_sum(ntl, su); if (threadIdx.x == 0) p.n_trunc_lt[col] = r;
+    r = block_reduce_sum(nlt, su); if (threadIdx.x == 0) p.n_lt[col] = r;
+    r = block_reduce_sum(neq, su); if (threadIdx.x == 0) p.n_eq[col] = r;
+    if (p.is_float) { double t = block_reduce_sum(fsum, sd); if (threadIdx.x == 0) p.sum[col] = t; }
+    else { r = block_reduce_sum(isum, su); if (threadIdx.x == 0) p.sum[col] = (double)r; }
+}
+
+__global__ void __launch_bounds__(256) stats_pass2_kernel(StatsParams p)
+{
+    __shared__ double sd[32];
+    const uint32_t col = blockIdx.x;
+    const double mean = p.mean[col];
+    double acc = 0.0;
+    for (uint64_t s = threadIdx.x; s < p.n_samples; s += blockDim.x) {
+        double d = load_val(p, s, col) - mean;
+        acc += d * d;
+    }
+    double t = block_reduce_sum(acc, sd);
+    if (threadIdx.x == 0) p.sumsq_dev[col] = t;
+}
+
+// order-preserving 64-bit key of a value
+__device__ __forceinline__ unsigned long long val_key(const StatsParams &p, uint64_t s, uint32_t col)
+{
+    if (!p.is_float) return (unsigned long long)reinterpret_cast<const uint32_t *>(p.counts)[s * p.n_cols + col];
+    unsigned long long b = (unsigned long long)__double_as_longlong(reinterpret_cast<const double *>(p.counts)[s * p.n_cols + col]);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ double key_val(int is_float, unsigned long long k)
+{
+    if (!is_float) return (double)k;
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// radix select of two order statistics per column: 8 bits per pass from the top byte
+__global__ void __launch_bounds__(256) stats_select_kernel(StatsParams p)
+{
+    __shared__ unsigned int hist[2][256];
+    __shared__ unsigned long long prefix_s[2];
+    __shared__ unsigned long long rank_s[2];
+    const uint32_t col = blockIdx.x;
+    const int top = p.is_float ? 56 : 24;
+    if (threadIdx.x == 0) { prefix_s[0] = prefix_s[1] = 0; rank_s[0] = p.rank_lo; rank_s[1] = p.rank_hi; }
+    __syncthreads();
+    for (int shift = top; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) (&hist[0][0])[i] = 0;
+        __syncthreads();
+        const unsigned long long pre0 = prefix_s[0], pre1 = prefix_s[1];
+        const unsigned long long hmask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
+        for (uint64_t s = threadIdx.x; s < p.n_samples; s += blockDim.x) {
+            unsigned long long k = val_key(p, s, col);
+            unsigned int b = (unsigned int)(k >> shift) & 255u;
+            if ((k & hmask) == pre0) atomicAdd(&hist[0][b], 1u);
+            if ((k & hmask) == pre1) atomicAdd(&hist[1][b], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            const int w = threadIdx.x;
+            unsigned long long r = rank_s[w], cum = 0;
+            int b = 0;
+            for (; b < 256; b++) { if (cum + hist[w][b] > r) break; cum += hist[w][b]; }
+            if (b > 255) b = 255;
+            rank_s[w] = r - cum;
+            prefix_s[w] |= ((unsigned long long)b << shift);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        p.q_lo[col] = key_val(p.is_float, prefix_s[0]);
+        p.q_hi[col] = key_val(p.is_float, prefix_s[1]);
+    }
+}
+
+void launch_stats_pass1(cudaStream_t st, const StatsParams &p)
+{
+    if (p.n_cols) stats_pass1_kernel<<<p.n_cols, 256, 0, st>>>(p);
+}
+void launch_stats_pass2(cudaStream_t st, const StatsParams &p)
+{
+    if (p.n_cols) stats_pass2_kernel<<<p.n_cols, 256, 0, st>>>(p);
+}
+void launch_stats_select(cudaStream_t st, const StatsParams &p, uint64_t *)
+{
+    if (p.n_cols) stats_select_kernel<<<p.n_cols, 256, 0, st>>>(p);
+}
+
+}  // namespace gatb

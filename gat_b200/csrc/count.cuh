@@ -1,0 +1,73 @@
+// count.cuh -- counting kernel (K3/K4) and the annotation tile format.
+//
+// Replaces overlapWithSegments / intersectionWithSegments (gat/SegmentList.pyx:1026-1146) as used by
+// the Counter* classes (gat/Engine.pyx:1412-1472) inside computeSample (gat/__init__.py:580-587) and
+// computeCounts (gat/Engine.pyx:2189-2202).
+#pragma once
+
+#include "common.cuh"
+
+namespace gatb {
+
+constexpr int KMAX = 8;                 // annotation tracks per shared-memory tile (register accumulators)
+
+// Tile = the intervals of up to KMAX annotation tracks on ONE key (contig), contiguous in global
+// memory so that one cooperative (or bulk) copy stages it in shared memory:
+//   TileHeader | for each track: uint2 iv[n+1] (sentinel 0xffffffff,0xffffffff) | uint16 idx[nbins+1]
+// idx[b] = first j with iv[j].end > (b << shift): a one-probe replacement for the binary search
+// (utils/gat_utils.c:8-32) over sorted interval ends.  nbins == 0: no index (track too large), the
+// kernel binary-searches the intervals in global memory instead.
+struct TileHeader {
+    uint32_t iv_off[KMAX];      // byte offsets from the tile start
+    uint32_t idx_off[KMAX];
+    uint32_t n[KMAX];
+    uint32_t nbins[KMAX];
+    uint32_t shift[KMAX];
+};
+
+struct CountParams {
+    // annotations
+    const uint8_t *tiles;           // tile blob
+    const uint64_t *tile_off;       // [n_groups][n_keys] byte offset
+    const uint32_t *tile_bytes;     // [n_groups][n_keys]
+    const uint32_t *key_ws_nseg;    // [n_keys] or NULL
+    uint32_t n_annot, n_keys, n_groups, ka;   // ka = tracks per group
+    uint32_t smem_tile_budget;      // tiles up to this many bytes are staged in shared memory
+    // segment sets
+    const uint64_t *placed;         // [n_samples][sample_stride] packed
+    uint64_t sample_stride;
+    const uint64_t *key_base;       // [n_keys]
+    const uint32_t *placed_n;       // [n_samples][n_keys]
+    const uint8_t *key_present;     // [n_samples][n_keys] or NULL
+    uint32_t n_samples;
+    uint32_t schunk;                // samples per CTA
+    // output
+    uint32_t *out_u32;              // [n_samples][n_annot] (integer counters)
+    double *out_f64;                // [n_samples][n_annot] (nucleotide-density)
+};
+
+// counter: GATB_* id.  Returns cudaError from the launch configuration.
+cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int threads);
+
+// column statistics (K5)
+struct StatsParams {
+    const void *counts;             // [n_samples][n_cols] uint32 or float64
+    int is_float;
+    uint64_t n_samples;
+    uint32_t n_cols;
+    const double *observed;         // device [n_cols]; already divided by ref fold where applicable
+    // outputs, device [n_cols]
+    double *sum;                    // exact integer sum (as double) or float sum
+    double *sumsq_dev;              // sum (x-mean)^2
+    unsigned long long *n_trunc_lt; // #{ (int)(x - obs) < 0 }   (cmpDouble truncation quirk)
+    unsigned long long *n_lt;       // #{ x < obs }
+    unsigned long long *n_eq;       // #{ x == obs }
+    double *q_lo, *q_hi;            // order statistics at ranks rank_lo / rank_hi
+    uint64_t rank_lo, rank_hi;
+    const double *mean;             // device [n_cols] (second pass)
+};
+void launch_stats_pass1(cudaStream_t st, const StatsParams &p);
+void launch_stats_pass2(cudaStream_t st, const StatsParams &p);
+void launch_stats_select(cudaStream_t st, const StatsParams &p, uint64_t *scratch_keys);
+
+}  // namespace gatb

@@ -1,0 +1,362 @@
+// place.cu -- K1 placement, K2 isochore->contig merge, unit preparation.  sm_100a, warp per unit.
+//
+// The placement loop of SamplerAnnotator.sample (gat/Engine.pyx:572-634) is sequential and
+// data-dependent.  With a counter-based RNG the draws of loop turn t are a pure function of
+// (seed, track, unit, sample, t), so a warp evaluates 32 consecutive turns speculatively, prefix-sums
+// their overlaps, accepts the turns before the first one whose length satisfies `remaining <= length`
+// (gat/Engine.pyx:582) and then runs that turn's checkpoint (sort + merge(0) + workspace coverage)
+// cooperatively.  The result is bit-identical to the sequential restatement in oracle/gat_oracle.c
+// driven by the same Philox stream (tests/test_gpu_parity.py).
+#include "place.cuh"
+
+namespace gatb {
+
+// ---------------------------------------------------------------------------------------------------
+// draws of one loop turn (RNG contract)
+struct TurnDraw { uint32_t L, start, end; int32_t ov; };
+
+__device__ __forceinline__ uint32_t ws_pick(const WsView &w, uint32_t r)
+{
+    // first i with cuminc[i] > r   == searchsorted(cdf, r) with cdf = cuminc - 1 (gat/Engine.pyx:300-305)
+    if (w.n == 1) return 0;
+    uint32_t lo = 0, hi = w.n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (w.cuminc[mid] > r) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ TurnDraw draw_turn(const UnitDesc &d, const WsView &ws, const uint32_t *tab,
+                                              uint32_t turn, uint32_t c1base, uint32_t unit, uint32_t sample,
+                                              uint32_t k0, uint32_t k1)
+{
+    Philox4 b0 = philox4x32_10(turn, 0u | c1base, unit, sample, k0, k1);
+    Philox4 b1 = philox4x32_10(turn, 1u | c1base, unit, sample, k0, k1);
+    TurnDraw t;
+    // HistogramSampler.sample (gat/Engine.pyx:413-435): r = randint(1,total) ranks the sorted lengths
+    uint32_t r = 1;
+    if (d.tab_n > 1) r = 1 + bounded_u32(b0.x, b0.y, d.tab_n - 1);
+    uint32_t L = tab[r - 1];
+    if (d.bucket > 1) L += bounded_u32(b1.z, b1.w, d.bucket);
+    t.L = L;
+    // SegmentListSampler.sample (gat/Engine.pyx:279-348)
+    uint32_t rw = bounded_u32(b0.z, b0.w, d.ws_total);
+    uint32_t i = ws_pick(ws, rw);
+    uint32_t cs = ws.start[i], ce = ws.end[i];
+    int64_t sstart = (int64_t)cs - (int64_t)L + 1;
+    if (i > 0) sstart = (int64_t)max((int32_t)ws.end[i - 1], (int32_t)sstart);
+    uint32_t range = (uint32_t)((int64_t)ce - sstart);
+    int64_t pp = sstart + (int64_t)bounded_u32(b1.x, b1.y, range);
+    t.start = (uint32_t)max(0, (int32_t)pp);
+    t.end = (uint32_t)(pp + (int64_t)L);
+    t.ov = max(0, min((int32_t)ce, (int32_t)t.end) - max((int32_t)cs, (int32_t)t.start));
+    return t;
+}
+
+// sum over the merged list of its workspace coverage (intersect(workspace).sum(), gat/Engine.pyx:593-599)
+__device__ __forceinline__ uint32_t warp_coverage(const uint64_t *buf, uint32_t n, const WsView &ws)
+{
+    uint32_t acc = 0;
+    for (uint32_t i = lane_id(); i < n; i += 32) {
+        uint64_t x = buf[i];
+        acc += ws_overlap(ws, seg_start(x), seg_end(x));
+    }
+    return __reduce_add_sync(GATB_FULL, acc);
+}
+
+// SegmentList._getInsertionPoint (gat/SegmentList.pyx:853-887) on packed segments
+__device__ __forceinline__ int insertion_point(const uint64_t *buf, uint32_t n, uint32_t ostart, uint32_t oend)
+{
+    if (n == 0) return -1;
+    if (ostart >= seg_end(buf[n - 1])) return (int)n;
+    if (oend <= seg_start(buf[0])) return -1;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (((int32_t)seg_start(buf[mid]) - (int32_t)ostart) < 0) lo = mid + 1; else hi = mid;
+    }
+    if (lo == n) return (int)lo - 1;
+    if (seg_start(buf[lo]) != ostart) return (int)lo - 1;
+    return (int)lo;
+}
+
+// overshoot repair (gat/Engine.pyx:608-625): SegmentListSampler(U).sample(1) picks a base of U,
+// trim_ends (gat/SegmentList.pyx:545-597) removes `size` bases from that segment's start or end
+__device__ __forceinline__ void warp_trim(uint64_t *buf, uint32_t nu, uint32_t size,
+                                          const Philox4 &b2, const Philox4 &b3)
+{
+    const int lane = lane_id();
+    // total length of U
+    uint32_t acc = 0;
+    for (uint32_t i = lane; i < nu; i += 32) { uint64_t x = buf[i]; acc += seg_end(x) - seg_start(x); }
+    uint32_t total = __reduce_add_sync(GATB_FULL, acc);
+    uint32_t r = bounded_u32(b2.x, b2.y, total);
+    // first idx with inclusive cumulative length > r
+    uint32_t running = 0, idx = nu;
+    for (uint32_t b0 = 0; b0 < nu; b0 += 32) {
+        uint32_t i = b0 + lane;
+        uint32_t len = 0;
+        if (i < nu) { uint64_t x = buf[i]; len = seg_end(x) - seg_start(x); }
+        uint32_t incl = warp_incl_scan_add_u32(len);
+        uint32_t m = __ballot_sync(GATB_FULL, (i < nu) && (running + incl > r));
+        if (m) { idx = b0 + (uint32_t)__ffs(m) - 1; break; }
+        running += __shfl_sync(GATB_FULL, incl, 31);
+    }
+    if (lane == 0 && idx < nu) {
+        uint64_t x = buf[idx];
+        uint32_t cs = seg_start(x), ce = seg_end(x);
+        int64_t sstart = (int64_t)cs - 1 + 1;
+        if (idx > 0) sstart = (int64_t)max((int32_t)seg_end(buf[idx - 1]), (int32_t)sstart);
+        uint32_t range = (uint32_t)((int64_t)ce - sstart);
+        int64_t pp = sstart + (int64_t)bounded_u32(b2.z, b2.w, range);
+        uint32_t pos = (uint32_t)max(0, (int32_t)pp);
+        int forward = (int)bounded_u32(b3.x, b3.y, 2u);
+        int32_t sz = (int32_t)size;
+        int k = insertion_point(buf, nu, pos, pos + 1);
+        if (k == (int)nu) k = 0;
+        if (k < 0) k = (int)nu - 1;
+        while (sz > 0) {
+            uint64_t y = buf[k];
+            int32_t l = (int32_t)seg_end(y) - (int32_t)seg_start(y);
+            if (l < sz) { buf[k] = 0; sz -= l; }
+            else {
+                if (forward) buf[k] = pack_seg(seg_start(y) + (uint32_t)sz, seg_end(y));
+                else buf[k] = pack_seg(seg_start(y), (uint32_t)((int32_t)seg_end(y) - sz));
+                sz = 0;
+            }
+            if (forward) { k += 1; if (k == (int)nu) k = 0; }
+            else { k -= 1; if (k < 0) k = (int)nu - 1; }
+        }
+    }
+    __syncwarp();
+}
+
+// keep segments overlapping the workspace by >= 1 base (SegmentList.filter, gat/SegmentList.pyx:1401-1467)
+__device__ __forceinline__ uint32_t warp_filter_ws(uint64_t *buf, uint32_t n, const WsView &ws)
+{
+    const int lane = lane_id();
+    uint32_t nout = 0;
+    for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+        uint32_t i = b0 + lane;
+        uint64_t x = (i < n) ? buf[i] : 0;
+        bool keep = (i < n) && (ws_overlap(ws, seg_start(x), seg_end(x)) > 0);
+        uint32_t m = __ballot_sync(GATB_FULL, keep);
+        __syncwarp();
+        if (keep) buf[nout + __popc(m & ((1u << lane) - 1))] = x;
+        nout += __popc(m);
+        __syncwarp();
+    }
+    return nout;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: one warp per (unit, sample)
+__global__ void __launch_bounds__(128) place_kernel(PlaceParams p)
+{
+    const uint64_t item = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= (uint64_t)p.n_units * p.n_samples) return;
+    const int lane = lane_id();
+    const uint32_t unit = p.order[item / p.n_samples];
+    const uint32_t sl = (uint32_t)(item % p.n_samples);
+    const UnitDesc d = p.units[unit];
+    uint64_t *buf = p.buf + (uint64_t)sl * p.sample_stride + d.buf_off;
+    WsView ws;
+    ws.start = p.ws_start + d.ws_off; ws.end = p.ws_end + d.ws_off; ws.cuminc = p.ws_cuminc + d.ws_off;
+    ws.n = d.ws_n;
+    const uint32_t *tab = p.len_tab + d.tab_off;
+    const uint32_t sample = (uint32_t)(p.sample_begin + sl);
+    const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+    const uint32_t c1base = p.track << 8;
+
+    int32_t remaining = d.ltotal, true_remaining = d.ltotal;
+    int fails = 0;
+    uint32_t nu = 0, np = 0, t0 = 0, status = 0;
+    bool dirty = false;
+
+    if (d.tab_n > 0) {
+        while (true_remaining > 0 && fails < 20) {
+            // ---- speculative batch of 32 turns ------------------------------------------------------
+            TurnDraw t = draw_turn(d, ws, tab, t0 + lane, c1base, unit, sample, k0, k1);
+            int32_t incl = warp_incl_scan_add(t.ov);
+            int32_t rem_before = remaining - (incl - t.ov);
+            uint32_t trig = __ballot_sync(GATB_FULL, rem_before <= (int32_t)t.L);
+            uint32_t f = trig ? (uint32_t)__ffs(trig) - 1 : 32u;
+            if (nu + np + f + 1 > d.cap) {
+                // buffer full: merge now.  merge(0) is idempotent and associative on the set of
+                // accepted placements, so an early merge does not change any later result.
+                __syncwarp();
+                nu = warp_sort_merge0(buf, nu + np);
+                np = 0; dirty = false;
+                if (nu + 33 > d.cap) { status |= UNIT_OVERFLOW; break; }
+            }
+            if ((uint32_t)lane < f) buf[nu + np + lane] = pack_seg(t.start, t.end);
+            if (f > 0) remaining -= __shfl_sync(GATB_FULL, incl, (int)f - 1);
+            np += f; t0 += f;
+            if (f == 32) continue;
+
+            // ---- turn t0: `remaining <= length` -> checkpoint (gat/Engine.pyx:582-605) ---------------
+            const uint32_t Lf = __shfl_sync(GATB_FULL, t.L, (int)f);
+            const uint32_t sf = __shfl_sync(GATB_FULL, t.start, (int)f);
+            const uint32_t ef = __shfl_sync(GATB_FULL, t.end, (int)f);
+            const int32_t ovf = __shfl_sync(GATB_FULL, t.ov, (int)f);
+            (void)Lf;
+            __syncwarp();
+            nu = warp_sort_merge0(buf, nu + np);
+            np = 0; dirty = false;
+            remaining = d.ltotal - (int32_t)warp_coverage(buf, nu, ws);
+            if (true_remaining == remaining) fails++; else true_remaining = remaining;
+
+            if (true_remaining < 0) {           // overshoot (gat/Engine.pyx:608-625)
+                Philox4 b2 = philox4x32_10(t0, 2u | c1base, unit, sample, k0, k1);
+                Philox4 b3 = philox4x32_10(t0, 3u | c1base, unit, sample, k0, k1);
+                warp_trim(buf, nu, (uint32_t)(-true_remaining), b2, b3);
+                dirty = true;
+                true_remaining = 1;
+                t0 += 1;
+                continue;
+            }
+            if (true_remaining > 0) {           // gat/Engine.pyx:632-634
+                if (lane == 0) buf[nu + np] = pack_seg(sf, ef);
+                np += 1;
+                remaining -= ovf;
+            }
+            t0 += 1;
+        }
+        if (fails >= 20) status |= UNIT_HIT_ROUND_CAP;
+        // result = unintersected.merge(0).filter(workspace) (gat/Engine.pyx:639-646); placements
+        // still pending (appended after the last checkpoint) are dropped, as in the reference
+        __syncwarp();
+        if (dirty) nu = warp_sort_merge0(buf, nu);
+        nu = warp_filter_ws(buf, nu, ws);
+    }
+    if (lane == 0) {
+        uint32_t slot = p.out_by_contig ? d.contig : unit;
+        p.out_n[(uint64_t)sl * p.out_n_stride + slot] = (status & UNIT_OVERFLOW) ? 0u : nu;
+        if (p.status) p.status[(uint64_t)sl * p.n_units + unit] = (uint8_t)status;
+    }
+}
+
+void launch_place(cudaStream_t st, const PlaceParams &p)
+{
+    uint64_t items = (uint64_t)p.n_units * p.n_samples;
+    if (items == 0) return;
+    const int warps_per_block = 4;
+    uint64_t blocks = (items + warps_per_block - 1) / warps_per_block;
+    place_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: IntervalDictionary.fromIsochores (gat/Engine.pyx:2857-2876): per contig, extend with every
+// isochore unit's list (unit order) then merge(0).  One warp per (contig, sample).
+__global__ void __launch_bounds__(128) contig_merge_kernel(MergeParams p)
+{
+    const uint64_t item = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= (uint64_t)p.n_contigs * p.n_samples) return;
+    const int lane = lane_id();
+    const uint32_t c = (uint32_t)(item / p.n_samples);
+    const uint32_t sl = (uint32_t)(item % p.n_samples);
+    uint64_t *dst = p.placed + (uint64_t)sl * p.placed_stride + p.contig_base[c];
+    uint32_t total = 0;
+    for (uint32_t k = p.contig_unit_off[c]; k < p.contig_unit_off[c + 1]; k++) {
+        uint32_t u = p.contig_units[k];
+        uint32_t n = p.unit_n[(uint64_t)sl * p.n_units + u];
+        const uint64_t *src = p.unit_buf + (uint64_t)sl * p.unit_stride + p.units[u].buf_off;
+        for (uint32_t i = lane; i < n; i += 32) dst[total + i] = src[i];
+        total += n;
+    }
+    __syncwarp();
+    uint32_t n = warp_sort_merge0(dst, total);
+    if (lane == 0) p.placed_n[(uint64_t)sl * p.n_contigs + c] = n;
+}
+
+void launch_contig_merge(cudaStream_t st, const MergeParams &p)
+{
+    uint64_t items = (uint64_t)p.n_contigs * p.n_samples;
+    if (items == 0) return;
+    const int warps_per_block = 4;
+    uint64_t blocks = (items + warps_per_block - 1) / warps_per_block;
+    contig_merge_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sample-invariant preparation of every unit (gat/Engine.pyx:543-565), one warp per unit:
+//   working = segments.filter(workspace); ltotal = working.intersect(workspace).sum();
+//   histogram of ceil(len/bucket) (gat/SegmentList.pyx:1148-1184) kept as the sorted table
+//   tab[r-1] = bucket_index * bucket, which is what lower_bound(cdf, r) * bucket returns
+//   (gat/Engine.pyx:424-430) without materialising the 100000-bucket CDF.
+__global__ void __launch_bounds__(128) prep_units_kernel(UnitDesc *units, uint32_t n_units,
+                                                         const uint32_t *seg_start, const uint32_t *seg_end,
+                                                         const uint32_t *ws_start, const uint32_t *ws_end,
+                                                         const uint32_t *ws_cuminc, uint32_t *len_tab,
+                                                         uint64_t *scratch, const uint64_t *scratch_off,
+                                                         uint32_t bucket_size, uint32_t nbuckets)
+{
+    const uint32_t unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (unit >= n_units) return;
+    const int lane = lane_id();
+    UnitDesc d = units[unit];
+    WsView ws;
+    ws.start = ws_start + d.ws_off; ws.end = ws_end + d.ws_off; ws.cuminc = ws_cuminc + d.ws_off; ws.n = d.ws_n;
+    const uint32_t *ss = seg_start + d.seg_off, *se = seg_end + d.seg_off;
+    uint64_t *keys = scratch + scratch_off[unit];
+
+    // pass 1: working set, ltotal, largest
+    uint32_t nw = 0, lt = 0, largest = 0;
+    for (uint32_t b0 = 0; b0 < d.seg_n; b0 += 32) {
+        uint32_t i = b0 + lane;
+        uint32_t s = 0, e = 0, ov = 0;
+        if (i < d.seg_n) { s = ss[i]; e = se[i]; ov = ws_overlap(ws, s, e); }
+        bool keep = ov > 0;
+        uint32_t m = __ballot_sync(GATB_FULL, keep);
+        if (keep) keys[nw + __popc(m & ((1u << lane) - 1))] = (uint64_t)(e - s);
+        nw += __popc(m);
+        lt += ov;
+        largest = max(largest, keep ? (e - s) : 0u);
+    }
+    lt = __reduce_add_sync(GATB_FULL, lt);
+    largest = __reduce_max_sync(GATB_FULL, largest);
+    __syncwarp();
+
+    uint32_t bucket = bucket_size, err = 0;
+    if (nw > 0) {
+        if (bucket == 0) bucket = (uint32_t)ceil((double)largest / (double)nbuckets);
+        // pass 2: bucket index * bucket, then sort
+        for (uint32_t i = lane; i < nw; i += 32) {
+            uint32_t l = (uint32_t)keys[i];
+            int idx = (int)(((double)l + (double)bucket - 1.0) / (double)bucket);
+            if (idx >= (int)nbuckets) err = 1;
+            keys[i] = (uint64_t)((uint32_t)idx * bucket);
+        }
+        err = __any_sync(GATB_FULL, err) ? 1u : 0u;
+        uint32_t N = next_pow2(nw);
+        for (uint32_t i = nw + lane; i < N; i += 32) keys[i] = GATB_KEY_INF;
+        __syncwarp();
+        warp_bitonic_sort(keys, N);
+        for (uint32_t i = lane; i < nw; i += 32) len_tab[d.tab_off + i] = (uint32_t)keys[i];
+    }
+    if (lane == 0) {
+        d.tab_n = nw;
+        d.bucket = bucket ? bucket : 1u;
+        d.ltotal = (int32_t)lt;
+        d.cap = next_pow2(2u * nw + 64u);
+        d.error = err;
+        units[unit] = d;
+    }
+}
+
+void launch_prep_units(cudaStream_t st, UnitDesc *units, uint32_t n_units,
+                       const uint32_t *seg_start, const uint32_t *seg_end,
+                       const uint32_t *ws_start, const uint32_t *ws_end, const uint32_t *ws_cuminc,
+                       uint32_t *len_tab, uint64_t *scratch, const uint64_t *scratch_off,
+                       uint32_t bucket_size, uint32_t nbuckets)
+{
+    if (n_units == 0) return;
+    const int warps_per_block = 4;
+    unsigned blocks = (n_units + warps_per_block - 1) / warps_per_block;
+    prep_units_kernel<<<blocks, warps_per_block * 32, 0, st>>>(units, n_units, seg_start, seg_end, ws_start,
+                                                                ws_end, ws_cuminc, len_tab, scratch, scratch_off,
+                                                                bucket_size, nbuckets);
+}
+
+}  // namespace gatb

@@ -1,0 +1,72 @@
+// place.cuh -- placement kernels (K1/K2) and the sample-invariant unit preparation.
+//
+// Replaces SamplerAnnotator.sample (gat/Engine.pyx:515-646) with its helpers HistogramSampler
+// (:387-440), SegmentListSampler (:245-353), SegmentList.merge/intersect/filter/trim_ends
+// (gat/SegmentList.pyx) and IntervalDictionary.fromIsochores (gat/Engine.pyx:2857-2876).
+#pragma once
+
+#include "common.cuh"
+
+namespace gatb {
+
+// status bits per (sample, unit)
+enum { UNIT_HIT_ROUND_CAP = 1, UNIT_OVERFLOW = 2 };
+
+// One placement unit = one key ("contig" or "contig.isochore") of one segment track.
+struct UnitDesc {
+    uint32_t ws_off;      // first workspace piece (into ws_start/ws_end/ws_cuminc)
+    uint32_t ws_n;        // number of workspace pieces
+    uint32_t ws_total;    // total workspace bases of the unit
+    uint32_t seg_off;     // raw segments of the unit (into seg arrays)
+    uint32_t seg_n;
+    uint32_t tab_off;     // length table: sorted (bucket index * bucket) of the working segments
+    uint32_t tab_n;       // = number of working segments (HistogramSampler.total_size)
+    uint32_t bucket;      // bucket size actually used
+    int32_t  ltotal;      // bases to reproduce (gat/Engine.pyx:550-552)
+    uint32_t cap;         // power-of-two capacity of the unit's working buffer
+    uint32_t contig;      // contig index
+    uint32_t error;       // GATB_ERR_TOO_LARGE etc. from preparation
+    uint64_t buf_off;     // offset of the working buffer inside one sample's region
+};
+
+struct PlaceParams {
+    const UnitDesc *units;
+    const uint32_t *order;       // unit ids, heaviest first
+    const uint32_t *ws_start, *ws_end, *ws_cuminc;
+    const uint32_t *len_tab;
+    uint64_t *buf;               // [n_samples][sample_stride] packed segments
+    uint64_t sample_stride;
+    uint32_t *out_n;             // [n_samples][out_n_stride]: per unit (isochores) or per contig
+    uint32_t out_n_stride;
+    int out_by_contig;           // 1: index out_n by contig (no isochores), 0: by unit
+    uint8_t *status;             // [n_samples][n_units]
+    uint32_t n_units;
+    uint32_t n_samples;          // samples in this launch
+    uint64_t sample_begin;       // global index of the first sample
+    uint64_t seed;
+    uint32_t track;
+};
+
+struct MergeParams {             // K2: per (sample, contig) concat + merge(0) of the contig's units
+    const UnitDesc *units;
+    const uint32_t *contig_unit_off;   // [n_contigs+1]
+    const uint32_t *contig_units;      // unit ids grouped by contig, in unit order
+    const uint64_t *contig_base;       // [n_contigs] offset inside one sample's contig-level region
+    const uint64_t *unit_buf;          // [n_samples][unit_stride]
+    uint64_t unit_stride;
+    const uint32_t *unit_n;            // [n_samples][n_units]
+    uint64_t *placed;                  // [n_samples][placed_stride]
+    uint64_t placed_stride;
+    uint32_t *placed_n;                // [n_samples][n_contigs]
+    uint32_t n_units, n_contigs, n_samples;
+};
+
+void launch_prep_units(cudaStream_t st, UnitDesc *units, uint32_t n_units,
+                       const uint32_t *seg_start, const uint32_t *seg_end,
+                       const uint32_t *ws_start, const uint32_t *ws_end, const uint32_t *ws_cuminc,
+                       uint32_t *len_tab, uint64_t *scratch, const uint64_t *scratch_off,
+                       uint32_t bucket_size, uint32_t nbuckets);
+void launch_place(cudaStream_t st, const PlaceParams &p);
+void launch_contig_merge(cudaStream_t st, const MergeParams &p);
+
+}  // namespace gatb

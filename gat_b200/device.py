@@ -1,0 +1,235 @@
+"""numpy-facing wrappers of the C ABI (include/gat_b200.h): Context, Annotations, Sampler.
+
+Interval lists are numpy arrays of shape (n, 2), dtype uint32, rows [start, end), sorted and
+normalized (what SegmentList.normalize() yields in the reference, gat/SegmentList.pyx:697-754).
+Everything here only flattens lists to CSR and calls libgat_b200.so; all interval arithmetic of the hot
+path runs on the GPU.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+COUNTERS = ["nucleotide-overlap", "nucleotide-density", "segment-overlap",
+            "segment-midoverlap", "annotation-overlap", "annotation-midoverlap"]
+COUNTER_ID = {name: i for i, name in enumerate(COUNTERS)}
+DENSITY = COUNTER_ID["nucleotide-density"]
+
+UNIT_HIT_ROUND_CAP = 1
+UNIT_OVERFLOW = 2
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def as_segs(x):
+    a = np.asarray(x, dtype=np.uint32).reshape(-1, 2)
+    return a
+
+
+def to_csr(lists):
+    """list of (n,2) arrays -> (offs uint64[n+1], start uint32[], end uint32[])"""
+    offs = np.zeros(len(lists) + 1, dtype=np.uint64)
+    if len(lists):
+        offs[1:] = np.cumsum([len(x) for x in lists], dtype=np.uint64)
+    total = int(offs[-1])
+    if total:
+        data = np.concatenate([as_segs(x) for x in lists if len(x)], axis=0)
+    else:
+        data = np.zeros((0, 2), dtype=np.uint32)
+    start = np.ascontiguousarray(data[:, 0])
+    end = np.ascontiguousarray(data[:, 1])
+    if total == 0:                      # keep valid pointers for ctypes
+        start = np.zeros(1, dtype=np.uint32)
+        end = np.zeros(1, dtype=np.uint32)
+    return offs, start, end
+
+
+def counter_ids(counters):
+    ids = []
+    for c in counters:
+        ids.append(COUNTER_ID[c] if isinstance(c, str) else int(c))
+    return np.array(ids, dtype=np.int32)
+
+
+class Context(object):
+    """one GPU + one CUDA stream (gatb_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self.lib.gatb_create(int(device), ctypes.byref(h))
+        if rc != _lib.OK:
+            raise _lib.GatB200Error(rc, self.lib.gatb_last_error(None).decode())
+        self.handle = h
+        self.device = int(device)
+
+    def check(self, rc):
+        if rc != _lib.OK:
+            raise _lib.GatB200Error(rc, self.lib.gatb_last_error(self.handle).decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.gatb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(self.lib.gatb_set_stream(self.handle, ctypes.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self.check(self.lib.gatb_synchronize(self.handle))
+
+    def set_batch_size(self, batch):
+        self.check(self.lib.gatb_set_batch_size(self.handle, int(batch)))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.gatb_launch_count(self.handle))
+
+    def column_stats(self, counts, observed, pseudo_count=1.0, ref_fold=None, device_ptr=None,
+                     n_samples=None, n_cols=None, is_float=None):
+        """per-column expected/stddev/CI95/fold/pvalue (gat/Engine.pyx:1635-1718).
+
+        counts: host ndarray [n_samples][n_cols] uint32 or float64; or pass device_ptr (+ shape)."""
+        if device_ptr is None:
+            counts = np.ascontiguousarray(counts)
+            if counts.dtype == np.float64:
+                is_float = 1
+            else:
+                counts = np.ascontiguousarray(counts, dtype=np.uint32)
+                is_float = 0
+            n_samples, n_cols = counts.shape
+            ptr, on_dev = _p(counts), 0
+        else:
+            ptr, on_dev = ctypes.c_void_p(device_ptr), 1
+        obs = np.ascontiguousarray(observed, dtype=np.float64)
+        ref = None if ref_fold is None else np.ascontiguousarray(ref_fold, dtype=np.float64)
+        outs = [np.zeros(n_cols, dtype=np.float64) for _ in range(6)]
+        self.check(self.lib.gatb_column_stats(self.handle, ptr, int(is_float), on_dev, int(n_samples), int(n_cols),
+                                              _p(obs), _p(ref), float(pseudo_count), *[_p(o) for o in outs]))
+        return dict(zip(["expected", "stddev", "lower95", "upper95", "fold", "pvalue"], outs))
+
+
+class Annotations(object):
+    """annotation tracks staged on the GPU for counting (gatb_annotations).
+
+    lists[a][k]: intervals of track a on key k (n_annot x n_keys)."""
+
+    def __init__(self, ctx, lists, key_ws_nseg=None):
+        self.ctx = ctx
+        self.n_annot = len(lists)
+        self.n_keys = len(lists[0]) if self.n_annot else 0
+        flat = [lists[a][k] for a in range(self.n_annot) for k in range(self.n_keys)]
+        offs, start, end = to_csr(flat)
+        nseg = None if key_ws_nseg is None else np.ascontiguousarray(key_ws_nseg, dtype=np.uint32)
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.gatb_annotations_create(ctx.handle, self.n_annot, self.n_keys, _p(offs), _p(start),
+                                                  _p(end), _p(nseg), ctypes.byref(h)))
+        self.handle = h
+        self.n_intervals = int(offs[-1])
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.gatb_annotations_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def count_lists(self, counters, samples, key_present=None):
+        """samples[s][k]: segment list of sample s on key k -> float64 [n_counters][n_samples][n_annot]"""
+        ids = counter_ids(counters)
+        n_samples = len(samples)
+        flat = [samples[s][k] for s in range(n_samples) for k in range(self.n_keys)]
+        offs, start, end = to_csr(flat)
+        present = None if key_present is None else np.ascontiguousarray(key_present, dtype=np.uint8)
+        out = np.zeros((len(ids), n_samples, self.n_annot), dtype=np.float64)
+        self.ctx.check(self.ctx.lib.gatb_count_lists(self.ctx.handle, self.handle, len(ids), _p(ids), n_samples,
+                                                     _p(offs), _p(start), _p(end), _p(present), _p(out)))
+        return out
+
+
+class Sampler(object):
+    """one segment track + workspace staged on the GPU for placement (gatb_sampler)."""
+
+    def __init__(self, ctx, unit_contig, n_contigs, has_isochores, unit_segments, unit_workspace,
+                 bucket_size=1, nbuckets=100000):
+        self.ctx = ctx
+        self.n_units = len(unit_contig)
+        self.n_contigs = int(n_contigs)
+        uc = np.ascontiguousarray(unit_contig, dtype=np.int32)
+        soffs, sstart, send = to_csr(unit_segments)
+        woffs, wstart, wend = to_csr(unit_workspace)
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.gatb_sampler_create(ctx.handle, self.n_units, _p(uc), self.n_contigs, int(bool(has_isochores)),
+                                              _p(soffs), _p(sstart), _p(send), _p(woffs), _p(wstart), _p(wend),
+                                              int(bucket_size), int(nbuckets), ctypes.byref(h)))
+        self.handle = h
+        self.capacity = int(ctx.lib.gatb_sampler_sample_capacity(h))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.gatb_sampler_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def place(self, seed, track, sample_begin, n_samples):
+        """-> (samples, status): samples[s][c] = (n,2) uint32 array of contig c; status [n_samples][n_units]"""
+        cap = self.capacity
+        start = np.zeros(max(n_samples * cap, 1), dtype=np.uint32)
+        end = np.zeros(max(n_samples * cap, 1), dtype=np.uint32)
+        counts = np.zeros(max(n_samples * self.n_contigs, 1), dtype=np.uint32)
+        base = np.zeros(self.n_contigs, dtype=np.uint64)
+        status = np.zeros(max(n_samples * self.n_units, 1), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.gatb_sampler_place(self.handle, int(seed), int(track), int(sample_begin),
+                                                       int(n_samples), _p(start), _p(end), _p(counts), _p(base),
+                                                       _p(status)))
+        out = []
+        for s in range(n_samples):
+            per = []
+            for c in range(self.n_contigs):
+                n = int(counts[s * self.n_contigs + c])
+                o = s * cap + int(base[c])
+                per.append(np.stack([start[o:o + n], end[o:o + n]], axis=1))
+            out.append(per)
+        return out, status[:n_samples * self.n_units].reshape(n_samples, self.n_units)
+
+    def run(self, annotations, counters, seed, track, sample_begin, n_samples,
+            out_counts_ptr=None, out_density_ptr=None):
+        """place + count.  Host mode (default) returns {counter_name: ndarray [n_samples][n_annot]} and info;
+        device mode writes into the given device pointers ([n_counters][n_samples][n_annot] uint32 /
+        [n_samples][n_annot] float64) and returns only info."""
+        ids = counter_ids(counters)
+        A = annotations.n_annot
+        info = np.zeros(3, dtype=np.uint64)
+        if out_counts_ptr is not None or out_density_ptr is not None:
+            self.ctx.check(self.ctx.lib.gatb_run(self.handle, annotations.handle, len(ids), _p(ids), int(seed),
+                                                 int(track), int(sample_begin), int(n_samples),
+                                                 ctypes.c_void_p(out_counts_ptr or 0),
+                                                 ctypes.c_void_p(out_density_ptr or 0), 1, _p(info)))
+            return info
+        out = np.zeros((len(ids), n_samples, A), dtype=np.uint32)
+        dens = np.zeros((n_samples, A), dtype=np.float64) if DENSITY in ids else None
+        self.ctx.check(self.ctx.lib.gatb_run(self.handle, annotations.handle, len(ids), _p(ids), int(seed),
+                                             int(track), int(sample_begin), int(n_samples), _p(out), _p(dens),
+                                             0, _p(info)))
+        res = {}
+        for i, cid in enumerate(ids):
+            res[COUNTERS[cid]] = dens if cid == DENSITY else out[i]
+        return res, info

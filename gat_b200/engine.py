@@ -1,0 +1,607 @@
+"""Host-side mirror of the reference's engine interface for the accelerated path.
+
+Same class names, constructor arguments and call signatures as gat/Engine.pyx so that gat-run.py-style
+code and the reference's own tests read the same:
+
+    containers   IntervalDictionary (Engine.pyx:2741-2880), IntervalCollection (:2887-3165)
+    sampler      SamplerAnnotator(bucket_size, nbuckets).sample(segments, workspace)   (:445-646)
+    counters     Counter*()(segments, annotations, workspace) and .name                 (:1412-1472)
+    workspace    UnconditionalWorkspace                                                  (:2061-2069)
+    counts       computeCounts(...)                                                      (:2164-2204)
+    results      AnnotatorResult / AnnotatorResultExtended                               (:1725-1974)
+    p/q values   updatePValues, getQValues, updateQValues                                (:1976-2054)
+
+The objects hold no algorithm: SamplerAnnotator.sample, Counter.__call__, computeCounts and the result
+statistics all execute in libgat_b200.so on the GPU (gat_b200/device.py); there is no CPU fallback.
+"""
+import collections
+import math
+import os
+
+import numpy as np
+
+from . import device as _dev
+from . import stats as Stats
+from .segmentlist import SegmentList
+
+# --------------------------------------------------------------------------------------- GPU context
+_context = {}
+
+
+def getContext(device=None):
+    """the process-wide gat_b200 Context of a GPU (default: LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _context:
+        _context[device] = _dev.Context(device)
+    return _context[device]
+
+
+_rng_state = {"seed": None, "calls": 0}
+
+
+def seed(value):
+    """seed the placement stream (counterpart of numpy.random.seed in scripts/gat-run.py:267-271)."""
+    _rng_state["seed"] = int(value) & 0xFFFFFFFFFFFFFFFF
+    _rng_state["calls"] = 0
+
+
+def getSeed():
+    if _rng_state["seed"] is None:
+        # like the reference, an unseeded run draws its seed from numpy's global generator
+        seed(int(np.random.randint(0, 2 ** 31 - 1)))
+    return _rng_state["seed"]
+
+
+# --------------------------------------------------------------------------------------- containers
+class IntervalContainer(object):
+    """generic collection of SegmentLists (gat/Engine.pyx:2559-2738); share()/unshare() exist for API
+    compatibility only -- there is no multiprocessing on this path."""
+
+    def __init__(self):
+        self.name = None
+
+    def getName(self):
+        return self.name
+
+    def setName(self, name):
+        self.name = name
+
+    def share(self, filename=None):
+        pass
+
+    def unshare(self):
+        pass
+
+    def sum(self):
+        return sum(s.sum() for s in self.getSegmentLists())
+
+    def counts(self):
+        return sum(len(s) for s in self.getSegmentLists())
+
+    def sort(self):
+        for s in self.getSegmentLists():
+            s.sort()
+
+    def normalize(self):
+        for s in self.getSegmentLists():
+            s.normalize()
+
+    def check(self):
+        self.sort()
+
+
+class IntervalDictionary(IntervalContainer):
+    """key (contig or contig.isochore) -> SegmentList (gat/Engine.pyx:2741-2880)."""
+
+    def __init__(self, name=None):
+        IntervalContainer.__init__(self)
+        self.intervals = collections.defaultdict(SegmentList)
+        self.name = name
+
+    def getSegmentLists(self):
+        for _, s in list(self.intervals.items()):
+            yield s
+
+    def __len__(self):
+        return len(self.intervals)
+
+    def __str__(self):
+        return ";".join("%s:%i,%i" % (x, len(y), y.sum()) for x, y in self.intervals.items())
+
+    def __delitem__(self, key):
+        del self.intervals[key]
+
+    def __getitem__(self, key):
+        return self.intervals[key]
+
+    def __setitem__(self, key, val):
+        self.intervals[key] = val
+
+    def __contains__(self, key):
+        return key in self.intervals
+
+    def keys(self):
+        return self.intervals.keys()
+
+    def items(self):
+        return self.intervals.items()
+
+    def add(self, contig, segmentlist):
+        self.intervals[contig] = segmentlist
+
+    def clone(self):
+        r = IntervalDictionary()
+        for contig, s in self.intervals.items():
+            r[contig] = s.clone()
+        return r
+
+    def _apply(self, other, op):
+        drop = []
+        for contig, s in self.intervals.items():
+            if contig in other:
+                getattr(s, op)(other[contig])
+            else:
+                drop.append(contig)
+        for contig in drop:
+            del self.intervals[contig]
+
+    def filter(self, other):
+        """keep intervals overlapping intervals in other; contigs absent from other vanish"""
+        self._apply(other, "filter")
+
+    def intersect(self, other):
+        self._apply(other, "intersect")
+
+    def toIsochores(self, isochores, truncate=False):
+        """split key `contig` into `contig.isochore` per isochore track (gat/Engine.pyx:2837-2855)"""
+        for contig in list(self.intervals.keys()):
+            s = self.intervals[contig]
+            for iso_track, iso in isochores.items():
+                n = s.clone()
+                if truncate:
+                    n.intersect(iso[contig])
+                else:
+                    n.filter(iso[contig])
+                self.intervals["%s.%s" % (contig, iso_track)] = n
+            del self.intervals[contig]
+
+    def fromIsochores(self):
+        """merge `contig.isochore` keys back into contigs; merge(0) when any key was split
+        (gat/Engine.pyx:2857-2876)"""
+        new = collections.defaultdict(SegmentList)
+        normalize = False
+        for isochore, s in self.intervals.items():
+            isochore = isochore.strip()
+            if "." in isochore and isochore != ".":
+                contig, _ = isochore.split(".")
+                new[contig].extend(s)
+                normalize = True
+            else:
+                new[isochore] = s
+        if normalize:
+            for x in new.values():
+                x.merge(0)
+        self.intervals = new
+
+
+class IntervalCollection(IntervalContainer):
+    """track -> IntervalDictionary (gat/Engine.pyx:2887-3165)."""
+
+    def __init__(self, name=None):
+        IntervalContainer.__init__(self)
+        self.intervals = collections.defaultdict(IntervalDictionary)
+        self.name = name
+
+    def getSegmentLists(self):
+        for _, v in list(self.intervals.items()):
+            for _, s in list(v.items()):
+                yield s
+
+    def load(self, filenames, allow_multiple=False, ignore_tracks=False):
+        from .io import readFromBed
+        self.intervals = readFromBed(filenames, allow_multiple=allow_multiple, ignore_tracks=ignore_tracks)
+
+    def save(self, outfile, prefix="", **kwargs):
+        for track, vv in self.intervals.items():
+            outfile.write("track name=%s%s %s\n" % (prefix, track, " ".join("%s=%s" % kv for kv in kwargs.items())))
+            for contig, s in vv.items():
+                for start, end in s:
+                    outfile.write("%s\t%i\t%i\n" % (contig, start, end))
+
+    def normalize(self):
+        """normalize every list; contigs without segments are removed (gat/Engine.pyx:2941-2956)"""
+        for track, vv in self.intervals.items():
+            for contig in [c for c in vv.keys() if len(vv[c]) == 0]:
+                del vv[contig]
+            for contig in vv.keys():
+                vv[contig].normalize()
+
+    def merge(self, delete=False):
+        """pool all tracks into track 'merged' (not normalized)"""
+        merged = IntervalDictionary()
+        for track in list(self.intervals.keys()):
+            for contig, s in self.intervals[track].items():
+                merged[contig].extend(s)
+            if delete:
+                del self.intervals[track]
+        self.intervals["merged"] = merged
+
+    def collapse(self):
+        """track 'collapsed' = intersection of all tracks on the contigs they share"""
+        ntracks = len(self.intervals)
+        seen = collections.Counter(c for vv in self.intervals.values() for c in vv.keys())
+        shared = set(c for c, n in seen.items() if n == ntracks)
+        result = IntervalDictionary()
+        for track, vv in self.intervals.items():
+            for contig, s in vv.items():
+                if contig not in shared:
+                    continue
+                if contig not in result:
+                    result[contig] = s.clone()
+                else:
+                    result[contig].intersect(s)
+        self.intervals["collapsed"] = result
+
+    def countsPerTrack(self):
+        return dict((track, sum(len(s) for _, s in vv.items())) for track, vv in self.intervals.items())
+
+    def intersect(self, other):
+        for vv in self.intervals.values():
+            vv.intersect(other)
+
+    def filter(self, other):
+        for vv in self.intervals.values():
+            vv.filter(other)
+
+    def restrict(self, restrict):
+        keep = set(restrict) if isinstance(restrict, (list, tuple, set)) else set([restrict])
+        for track in [t for t in self.intervals.keys() if t not in keep]:
+            del self.intervals[track]
+
+    def toIsochores(self, isochores, truncate=False):
+        for vv in self.intervals.values():
+            vv.toIsochores(isochores, truncate)
+
+    def fromIsochores(self):
+        for vv in self.intervals.values():
+            vv.fromIsochores()
+
+    def clone(self):
+        new = IntervalCollection(self.name)
+        for track, v in self.intervals.items():
+            for contig, s in v.items():
+                new.add(track, contig, s.clone())
+        return new
+
+    @property
+    def tracks(self):
+        return self.intervals.keys()
+
+    def __len__(self):
+        return len(self.intervals)
+
+    def __delitem__(self, key):
+        del self.intervals[key]
+
+    def __getitem__(self, key):
+        return self.intervals[key]
+
+    def __contains__(self, key):
+        return key in self.intervals
+
+    def keys(self):
+        return self.intervals.keys()
+
+    def items(self):
+        return self.intervals.items()
+
+    def add(self, track, contig, segmentlist):
+        self.intervals[track][contig] = segmentlist
+
+    def __str__(self):
+        return "%s:%s" % (self.name, ",".join("%s:%s" % (x, y) for x, y in self.intervals.items()))
+
+    def outputStats(self, outfile):
+        outfile.write("section\ttrack\tcontig\tnsegments\tlength\n")
+        for track, vv in self.intervals.items():
+            tl = ts = 0
+            for contig, s in vv.items():
+                outfile.write("\t".join((str(self.name), track, contig, "%i" % len(s), "%i" % s.sum())) + "\n")
+                tl += s.sum()
+                ts += len(s)
+            outfile.write("\t".join((str(self.name), track, "total", "%i" % ts, "%i" % tl)) + "\n")
+
+
+# ------------------------------------------------------------------------------------------ sampler
+class Sampler(object):
+    pass
+
+
+def splitKey(key):
+    """contig of a workspace key: 'contig.isochore' -> contig (gat/Engine.pyx:2862-2866)"""
+    key = key.strip()
+    if "." in key and key != ".":
+        return key.split(".")[0], True
+    return key, False
+
+
+class SamplerAnnotator(Sampler):
+    """the annotator sampling method (gat/Engine.pyx:445-646) on the GPU.
+
+    `sample(segments, workspace)` places ONE unit and returns a SegmentList, like the reference; it is
+    meant for tests and scripts.  gat_b200.run() recognises this class and sends the whole track
+    (all units x all samples) to the GPU in one batched call instead."""
+
+    accelerated = True
+
+    def __init__(self, bucket_size=1, nbuckets=100000, nunsuccessful_rounds=0):
+        self.bucket_size = bucket_size
+        self.nbuckets = nbuckets
+        self.nunsuccessful_rounds = nunsuccessful_rounds
+
+    def __reduce__(self):
+        return (SamplerAnnotator, (self.bucket_size, self.nbuckets, self.nunsuccessful_rounds))
+
+    def sample(self, segments, workspace):
+        assert segments.isNormalized, "segment list is not normalized"
+        assert workspace.isNormalized, "workspace is not normalized"
+        if len(segments) == 0 or len(workspace) == 0:
+            return SegmentList()
+        ctx = getContext()
+        try:
+            smp = _dev.Sampler(ctx, [0], 1, False, [segments.asarray()], [workspace.asarray()],
+                               bucket_size=self.bucket_size, nbuckets=self.nbuckets)
+        except _dev._lib.GatB200Error as e:
+            if e.code == _dev._lib.ERR_TOO_LARGE:
+                raise ValueError(str(e))
+            raise
+        call = _rng_state["calls"]
+        _rng_state["calls"] += 1
+        placed, status = smp.place(getSeed(), 0xFFFFFF, call, 1)
+        self.nunsuccessful_rounds = 20 if (status[0, 0] & _dev.UNIT_HIT_ROUND_CAP) else 0
+        smp.close()
+        r = SegmentList(array=placed[0][0])
+        r._normalized = True
+        return r
+
+
+# ----------------------------------------------------------------------------------------- counters
+class Counter(object):
+    """base class: counts between two segment lists (gat/Engine.pyx:1412-1415)."""
+    name = None
+
+    def __call__(self, segments, annotations, workspace=None):
+        nseg = [len(workspace)] if workspace is not None else [0]
+        if self.name == "nucleotide-density" and nseg[0] == 0:
+            return 0
+        ctx = getContext()
+        annos = _dev.Annotations(ctx, [[annotations.asarray()]], key_ws_nseg=nseg)
+        out = annos.count_lists([self.name], [[segments.asarray()]])
+        annos.close()
+        v = out[0, 0, 0]
+        return float(v) if self.name == "nucleotide-density" else int(v)
+
+
+class CounterNucleotideOverlap(Counter):
+    name = "nucleotide-overlap"
+
+
+class CounterNucleotideDensity(Counter):
+    name = "nucleotide-density"
+
+
+class CounterSegmentOverlap(Counter):
+    name = "segment-overlap"
+
+
+class CounterSegmentMidpointOverlap(Counter):
+    name = "segment-midoverlap"
+
+
+class CounterAnnotationOverlap(Counter):
+    name = "annotation-overlap"
+
+
+class CounterAnnotationMidpointOverlap(Counter):
+    name = "annotation-midoverlap"
+
+
+COUNTER_CLASSES = dict((c.name, c) for c in (CounterNucleotideOverlap, CounterNucleotideDensity,
+                                             CounterSegmentOverlap, CounterSegmentMidpointOverlap,
+                                             CounterAnnotationOverlap, CounterAnnotationMidpointOverlap))
+
+
+class UnconditionalWorkspace(object):
+    """the default, unconditional workspace (gat/Engine.pyx:2061-2069)."""
+    is_conditional = False
+
+    def __call__(self, segments, annotations, workspace):
+        return segments, annotations, workspace
+
+
+# ------------------------------------------------------------------------------------ observed counts
+def computeCounts(counter, aggregator, segments, annotations, workspace, workspace_generator, append=False):
+    """observed counts of every (track, annotation) pair: aggregator over workspace keys of
+    counter(segs[key], annos[key], workspace[key]) (gat/Engine.pyx:2164-2204).  One batched GPU call
+    per counter; only the `sum` aggregator of the reference's call site is supported."""
+    if aggregator is not sum:
+        raise NotImplementedError("gat_b200.computeCounts supports aggregator=sum only")
+    if append:
+        counts = collections.defaultdict(list)
+    else:
+        counts = collections.defaultdict(lambda: collections.defaultdict(float))
+    keys = list(workspace.keys())
+    tracks = list(segments.tracks)
+    atracks = list(annotations.tracks)
+    if not keys or not tracks or not atracks:
+        return counts
+    ctx = getContext()
+    annos = _dev.Annotations(ctx, [[annotations[a][k].asarray() for k in keys] for a in atracks],
+                             key_ws_nseg=[len(workspace[k]) for k in keys])
+    out = annos.count_lists([counter.name], [[segments[t][k].asarray() for k in keys] for t in tracks])
+    annos.close()
+    is_float = counter.name == "nucleotide-density"
+    for ti, track in enumerate(tracks):
+        for ai, annotation in enumerate(atracks):
+            v = out[0, ti, ai]
+            v = float(v) if is_float else int(v)
+            if append:
+                counts[annotation].append(v)
+            else:
+                counts[track][annotation] = v
+    return counts
+
+
+# ------------------------------------------------------------------------------------------- results
+class AnnotatorResult(object):
+    """observed vs simulated counts of one (track, annotation, counter) with expected, CI95, stddev,
+    fold, empirical p-value and q-value (gat/Engine.pyx:1725-1852).  The statistics are computed on
+    the GPU (gatb_column_stats); `stats` lets gat_b200.run() pass in the row of a batched call."""
+
+    format_expected = "%6.4f"
+    format_fold = "%6.4f"
+    format_pvalue = "%6.4e"
+    format_counts = "%i"
+    format_density = "%6.4e"
+
+    headers = ["track", "annotation", "observed", "expected", "CI95low", "CI95high", "stddev", "fold",
+               "l2fold", "pvalue", "qvalue"]
+
+    def __init__(self, track, annotation, counter, observed, samples, reference=None, pseudo_count=1.0,
+                 stats=None):
+        self.track = track
+        self.annotation = annotation
+        self.counter = counter
+        self.observed = float(observed)
+        self._samples = np.array(samples, dtype=np.float64)
+        self.nsamples = len(self._samples)
+        self.format_observed = "%i"
+        self.qvalue = 1.0
+        if self.nsamples < 1:
+            raise ValueError("no samples")
+        if stats is None:
+            is_int = bool(np.all(self._samples == np.floor(self._samples)) and self._samples.min() >= 0
+                          and self._samples.max() < 2 ** 32)
+            col = self._samples.reshape(-1, 1)
+            col = col.astype(np.uint32) if is_int else col
+            ref = None if reference is None else [reference.fold]
+            st = getContext().column_stats(col, [self.observed], pseudo_count=pseudo_count, ref_fold=ref)
+            stats = dict((k, float(v[0])) for k, v in st.items())
+        self.expected = stats["expected"]
+        self.stddev = stats["stddev"]
+        self.lower95 = stats["lower95"]
+        self.upper95 = stats["upper95"]
+        self.fold = stats["fold"]
+        self.pvalue = stats["pvalue"]
+
+    @property
+    def samples(self):
+        return self._samples.copy()
+
+    def getSample(self, sample_id):
+        return self._samples[sample_id]
+
+    def getEmpiricalPValue(self, value):
+        is_int = bool(np.all(self._samples == np.floor(self._samples)))
+        col = self._samples.reshape(-1, 1)
+        col = col.astype(np.uint32) if is_int else col
+        st = getContext().column_stats(col, [float(value)])
+        # the reference compares against the stored expected value (gat/Engine.pyx:1556)
+        return float(st["pvalue"][0])
+
+    def _columns(self):
+        if self.fold > 0:
+            logfold = self.format_fold % math.log(self.fold, 2)
+        else:
+            logfold = "-inf"
+        return [self.track, self.annotation, self.format_observed % self.observed,
+                self.format_expected % self.expected, self.format_expected % self.lower95,
+                self.format_expected % self.upper95, self.format_expected % self.stddev,
+                self.format_fold % self.fold, logfold, self.format_pvalue % self.pvalue,
+                self.format_pvalue % self.qvalue]
+
+    def __str__(self):
+        return "\t".join(self._columns())
+
+
+class AnnotatorResultExtended(AnnotatorResult):
+    """AnnotatorResult plus size / overlap / density columns (gat/Engine.pyx:1854-1974)."""
+
+    headers = AnnotatorResult.headers + [
+        "track_nsegments", "track_size", "track_density",
+        "annotation_nsegments", "annotation_size", "annotation_density",
+        "overlap_nsegments", "overlap_size", "overlap_density",
+        "percent_overlap_nsegments_track", "percent_overlap_size_track",
+        "percent_overlap_nsegments_annotation", "percent_overlap_size_annotation"]
+
+    def __init__(self, track, annotation, counter, observed, samples, track_segments, annotation_segments,
+                 workspace, reference=None, pseudo_count=1.0, stats=None):
+        AnnotatorResult.__init__(self, track, annotation, counter, observed, samples,
+                                 reference=reference, pseudo_count=pseudo_count, stats=stats)
+        self.track_nsegments = track_segments.counts()
+        self.track_size = track_segments.sum()
+        self.annotation_nsegments = annotation_segments.counts()
+        self.annotation_size = annotation_segments.sum()
+        overlap = track_segments.clone()
+        overlap.intersect(annotation_segments)
+        self.overlap_nsegments = overlap.counts()
+        self.overlap_size = overlap.sum()
+        self.workspace_size = workspace.sum()
+
+    def __str__(self):
+        def pct(a, b, fmt):
+            return fmt % (100.0 * float(a) / b) if b > 0 else "na"
+        f, d, c = self.format_fold, self.format_density, self.format_counts
+        return "\t".join(self._columns() + [
+            c % self.track_nsegments, c % self.track_size, pct(self.track_size, self.workspace_size, d),
+            c % self.annotation_nsegments, c % self.annotation_size,
+            pct(self.annotation_size, self.workspace_size, d),
+            c % self.overlap_nsegments, c % self.overlap_size, pct(self.overlap_size, self.workspace_size, d),
+            pct(self.overlap_nsegments, self.track_nsegments, f), pct(self.overlap_size, self.track_size, f),
+            pct(self.overlap_nsegments, self.annotation_nsegments, f),
+            pct(self.overlap_size, self.annotation_size, f)])
+
+
+# ------------------------------------------------------------------------------------ p / q values
+def getNormedPValue(value, r):
+    """p-value assuming normally distributed samples (gat/Engine.pyx:1976-1988)"""
+    absval = abs(value - r.expected)
+    if r.stddev == 0:
+        return 1.0
+    import scipy.stats
+    return 1.0 - scipy.stats.norm.cdf(absval, 0, r.stddev)
+
+
+def getEmpiricalPValue(value, r):
+    return r.getEmpiricalPValue(value)
+
+
+def updatePValues(annotator_results, method="empirical"):
+    if method == "norm":
+        f = getNormedPValue
+    elif method == "empirical":
+        f = getEmpiricalPValue
+    else:
+        raise ValueError("unknown method '%s'" % method)
+    for r in annotator_results:
+        r.pvalue = f(r.observed, r)
+
+
+def getQValues(pvalues, method="storey", **kwargs):
+    """q-values for a list of p-values (gat/Engine.pyx:2025-2039)"""
+    if method == "storey":
+        try:
+            fdr = Stats.computeQValues(pvalues,
+                                       vlambda=kwargs.get("vlambda", np.arange(0, 0.95, 0.05)),
+                                       pi0_method=kwargs.get("pi0_method", "smoother"))
+        except ValueError:
+            return [1.0] * len(pvalues)
+        return fdr.qvalues
+    return Stats.adjustPValues(pvalues, method=method)
+
+
+def updateQValues(annotator_results, method="storey", **kwargs):
+    pvalues = [r.pvalue for r in annotator_results]
+    for r, q in zip(annotator_results, getQValues(pvalues, method, **kwargs)):
+        r.qvalue = q

@@ -1,0 +1,233 @@
+"""Input preparation and result output around gat_b200.run() (reference: gat/IO.py, BED reader in
+gat/Engine.pyx:2470-2556).  One-off host work, O(input); not part of the simulated hot path.
+"""
+import collections
+import glob
+import gzip
+import os
+import re
+import sys
+
+import numpy as np
+
+from . import engine as Engine
+from .segmentlist import SegmentList
+
+
+def openFile(filename, mode="r"):
+    if filename.endswith(".gz"):
+        return gzip.open(filename, mode + "t")
+    return open(filename, mode)
+
+
+def _track_name(line):
+    """name=... attribute of a BED `track` line"""
+    m = re.search(r'name=("([^"]*)"|(\S+))', line)
+    if not m:
+        return None
+    return m.group(2) if m.group(2) is not None else m.group(3)
+
+
+def readFromBed(filenames, allow_multiple=False, ignore_tracks=False):
+    """BED files -> {track: IntervalDictionary}.  The track of an interval is the enclosing `track
+    name=` line, else column 4, else the file's basename; `ignore_tracks` pools everything into
+    'merged' (gat/Engine.pyx:2470-2556)."""
+    if isinstance(filenames, str):
+        filenames = [filenames]
+    rows = collections.defaultdict(lambda: collections.defaultdict(list))
+    origin = {}
+    for filename in filenames:
+        default_name = os.path.basename(filename)
+        current = None
+        with openFile(filename, "r") as infile:
+            for lineno, line in enumerate(infile):
+                if line.startswith("track"):
+                    current = _track_name(line)
+                    if current is None:
+                        raise KeyError("track without field 'name' in file '%s'" % filename)
+                    continue
+                if line.startswith("#") or not line.strip():
+                    continue
+                fields = line.rstrip("\n").split("\t")
+                if len(fields) < 3:
+                    raise IOError("malformatted entry in line %s:%i" % (filename, lineno))
+                if ignore_tracks:
+                    name = "merged"
+                elif current is not None:
+                    name = current
+                elif len(fields) > 3 and fields[3]:
+                    name = fields[3]
+                else:
+                    name = default_name
+                if name in origin:
+                    if origin[name] != filename:
+                        if not allow_multiple:
+                            raise ValueError("track '%s' in multiple filenames: %s and %s" %
+                                             (name, origin[name], filename))
+                        origin[name] = filename
+                else:
+                    origin[name] = filename
+                rows[name][fields[0]].append((int(fields[1]), int(fields[2])))
+    result = collections.defaultdict(Engine.IntervalDictionary)
+    for name, contigs in rows.items():
+        d = Engine.IntervalDictionary()
+        for contig, data in contigs.items():
+            d[contig] = SegmentList(array=np.array(data, dtype=np.int64).astype(np.uint32))
+        result[name] = d
+    return result
+
+
+def readSegmentList(label, filenames, enable_split_tracks=False, ignore_tracks=False):
+    results = Engine.IntervalCollection(name=label)
+    results.load(filenames, allow_multiple=enable_split_tracks, ignore_tracks=ignore_tracks)
+    return results
+
+
+def expandGlobs(infiles):
+    out = []
+    for x in infiles:
+        out.extend(glob.glob(x))
+    return out
+
+
+def buildSegments(options):
+    """load segments, annotations, workspace and isochores as named by *options*
+    (gat/IO.py:88-185): normalize, collapse the workspaces into one, truncate isochores to it."""
+    options.segment_files = expandGlobs(options.segment_files)
+    options.annotation_files = expandGlobs(options.annotation_files)
+    options.workspace_files = expandGlobs(options.workspace_files)
+    if not options.segment_files:
+        raise ValueError("please specify at least one segment file")
+    if not options.annotation_files:
+        raise ValueError("please specify at least one annotation file")
+    if not options.workspace_files:
+        raise ValueError("please specify at least one workspace file")
+
+    segments = readSegmentList("segments", options.segment_files, ignore_tracks=options.ignore_segment_tracks)
+    segments.normalize()
+    if segments.sum() == 0:
+        raise ValueError("segments file is empty - run aborted")
+    if len(segments) > 1000:
+        raise ValueError("too many (%i) segment files - use track definitions or --ignore-segment-tracks"
+                         % len(segments))
+
+    annotations = readSegmentList("annotations", options.annotation_files,
+                                  enable_split_tracks=options.enable_split_tracks,
+                                  ignore_tracks=options.annotations_label is not None)
+    if options.annotations_label is not None:
+        annotations.setName(options.annotations_label)
+    if getattr(options, "annotations_to_points", None):
+        raise NotImplementedError("--annotations-to-points is not accelerated by gat_b200")
+    if getattr(options, "overlapping_annotations", False):
+        raise NotImplementedError("--overlapping-annotations is not accelerated by gat_b200")
+    annotations.normalize()
+
+    workspaces = readSegmentList("workspaces", options.workspace_files, enable_split_tracks=True,
+                                 ignore_tracks=options.enable_split_tracks)
+    workspaces.normalize()
+    workspaces.collapse()
+    workspaces.restrict("collapsed")
+
+    isochores = None
+    if options.isochore_files:
+        isochores = Engine.IntervalCollection(name="isochores")
+        isochores.load(options.isochore_files)
+        isochores.sort()
+        for s in isochores.getSegmentLists():
+            s.check()
+        isochores.normalize()
+        isochores.intersect(workspaces["collapsed"])
+    return segments, annotations, workspaces, isochores
+
+
+def applyIsochores(segments, annotations, workspaces, options, isochores=None,
+                   truncate_segments_to_workspace=False, truncate_workspace_to_annotations=False,
+                   restrict_workspace=False):
+    """restrict segments/annotations to the workspace and optionally split everything by isochore
+    (gat/IO.py:188-293); returns the workspace IntervalDictionary."""
+    if isochores:
+        workspaces.toIsochores(isochores, truncate=True)
+        annotations.toIsochores(isochores, truncate=True)
+        segments.toIsochores(isochores, truncate=options.truncate_segments_to_workspace)
+        if workspaces.sum() == 0:
+            raise ValueError("isochores and workspaces do not overlap")
+        if annotations.sum() == 0:
+            raise ValueError("isochores and annotations do not overlap")
+        if segments.sum() == 0:
+            raise ValueError("isochores and segments do not overlap")
+    else:
+        if options.truncate_segments_to_workspace:
+            segments.intersect(workspaces["collapsed"])
+        else:
+            segments.filter(workspaces["collapsed"])
+        annotations.intersect(workspaces["collapsed"])
+
+    workspace = workspaces["collapsed"]
+    if restrict_workspace:
+        for _ in (segments, annotations):
+            if "merged" in segments:
+                workspace.filter(segments["merged"])
+            else:
+                segments.merge()
+                workspace.filter(segments["merged"])
+                del segments["merged"]
+    if truncate_workspace_to_annotations:
+        annotations.merge()
+        annotations["merged"].normalize()
+        workspace.intersect(annotations["merged"])
+        del annotations["merged"]
+    return workspace
+
+
+def readDescriptions(options):
+    """optional table annotation -> description columns (gat/IO.py:296-330)"""
+    header, descriptions, width = [], {}, 0
+    fn = getattr(options, "input_filename_descriptions", None)
+    if fn:
+        with openFile(fn) as inf:
+            first = True
+            for line in inf:
+                if line.startswith("#"):
+                    continue
+                data = line.rstrip("\n").split("\t")
+                if first:
+                    header = data[1:]
+                    width = len(header)
+                    first = False
+                    continue
+                descriptions[data[0]] = data[1:]
+    return header, descriptions, width
+
+
+def outputResults(results, options, header, description_header, description_width, descriptions,
+                  format_observed="%i"):
+    """q-values over ALL results of the run, then one table per counter (gat/IO.py:457-538)"""
+    pvalues = [x.pvalue for x in results]
+    qvalues = Engine.getQValues(pvalues, method=options.qvalue_method, vlambda=options.qvalue_lambda,
+                                pi0_method=options.qvalue_pi0_method)
+    for x, q in zip(results, qvalues):
+        x.qvalue = q
+        x.format_observed = format_observed
+
+    counters = sorted(set(x.counter for x in results))
+    keyfuncs = {"track": lambda x: (x.track, x.annotation), "observed": lambda x: x.observed,
+                "annotation": lambda x: (x.annotation, x.track), "fold": lambda x: x.fold,
+                "pvalue": lambda x: x.pvalue, "qvalue": lambda x: x.qvalue}
+    if options.output_order not in keyfuncs:
+        raise ValueError("unknown sort order %s" % options.output_order)
+    stdout = getattr(options, "stdout", sys.stdout)
+    for counter in counters:
+        if len(counters) == 1:
+            outfile, output = stdout, list(results)
+        else:
+            outfile = openFile(re.sub("%s", counter, options.output_tables_pattern), "w")
+            output = [x for x in results if x.counter == counter]
+        outfile.write("\t".join(list(header) + list(description_header)) + "\n")
+        output.sort(key=keyfuncs[options.output_order])
+        for result in output:
+            outfile.write(str(result))
+            if descriptions:
+                outfile.write("\t" + "\t".join(descriptions.get(result.annotation, [""] * description_width)))
+            outfile.write("\n")
+        if outfile is not stdout:
+            outfile.close()

@@ -1,0 +1,160 @@
+/*
+ * gat_b200.h -- C ABI of the B200-native GAT simulation engine (libgat_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path this repository accelerates: per-sample random
+ * placement of segments into the workspace (SamplerAnnotator) and overlap counting of every simulated
+ * set against every annotation track (Counter*), plus observed counts and per-column statistics.
+ * The reference (AndreasHeger/gat 1.3.6, Python + Cython) has no FFI of its own for this path: its
+ * operator interface is three duck-typed Python protocols consumed by gat.run().  Every entry point
+ * below names the reference interface it replaces (paths relative to the reference checkout);
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; all interval lists are CSR: offs[n_lists+1] (uint64) + start[] + end[]
+ *     (uint32, half-open [start,end), sorted, normalized -- what SegmentList.normalize() produces,
+ *     gat/SegmentList.pyx:697-754).  Coordinates must be < 2^31 (the reference's own arithmetic is
+ *     int32, gat/SegmentList.pxd:31-38).
+ *   - every function returns GATB_OK (0) or a negative error code; gatb_last_error() gives the text.
+ *     No exceptions cross the boundary.  There is NO CPU fallback: without a CUDA device every
+ *     compute entry point fails with GATB_ERR_CUDA.
+ *   - one context per GPU; calls on one context are serialised by the caller; work is enqueued on
+ *     the context's CUDA stream (gatb_set_stream) and entry points that return host data
+ *     synchronise that stream before returning.
+ *   - "host" pointers are ordinary (ideally pinned) host memory, "dev" pointers are device memory
+ *     of the context's GPU (e.g. torch tensors' data_ptr()).
+ */
+#ifndef GAT_B200_H
+#define GAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GATB_VERSION 100
+
+/* error codes */
+#define GATB_OK              0
+#define GATB_ERR_INVALID    -1   /* bad argument / inconsistent shapes                                */
+#define GATB_ERR_CUDA       -2   /* CUDA runtime error (no device, launch failure, out of memory)     */
+#define GATB_ERR_CAPACITY   -3   /* a placement unit overflowed its segment buffer                    */
+#define GATB_ERR_TOO_LARGE  -4   /* segment too large for nbuckets*bucket_size (ValueError in         */
+                                 /* SegmentList.getLengthDistribution, gat/SegmentList.pyx:1170-1182) */
+#define GATB_ERR_RANGE      -5   /* coordinate >= 2^31 or total overlap >= 2^32                       */
+
+/* counters (gat/Engine.pyx:1412-1472; names are the --counter choices, gat/__init__.py:214-223) */
+#define GATB_NUCLEOTIDE_OVERLAP    0   /* CounterNucleotideOverlap       :1417-1425 */
+#define GATB_NUCLEOTIDE_DENSITY    1   /* CounterNucleotideDensity       :1427-1441 */
+#define GATB_SEGMENT_OVERLAP       2   /* CounterSegmentOverlap          :1443-1448 */
+#define GATB_SEGMENT_MIDOVERLAP    3   /* CounterSegmentMidpointOverlap  :1450-1456 */
+#define GATB_ANNOTATION_OVERLAP    4   /* CounterAnnotationOverlap       :1458-1463 */
+#define GATB_ANNOTATION_MIDOVERLAP 5   /* CounterAnnotationMidpointOverlap :1465-1472 */
+#define GATB_NCOUNTERS             6
+
+typedef struct gatb_ctx gatb_ctx;           /* one GPU + one stream                                  */
+typedef struct gatb_annotations gatb_annotations;   /* annotation tracks staged for counting         */
+typedef struct gatb_sampler gatb_sampler;   /* one segment track + workspace staged for placement    */
+
+/* ---- context ----------------------------------------------------------------------------------*/
+int         gatb_version(void);
+int         gatb_create(int device, gatb_ctx **out);
+void        gatb_destroy(gatb_ctx *ctx);
+const char *gatb_last_error(gatb_ctx *ctx);            /* ctx may be NULL: last creation error       */
+int         gatb_set_stream(gatb_ctx *ctx, void *cuda_stream);   /* NULL: the context's own stream  */
+int         gatb_synchronize(gatb_ctx *ctx);
+/* number of this library's kernels launched on the context since creation (bench "gpu_launches") */
+uint64_t    gatb_launch_count(gatb_ctx *ctx);
+
+/* ---- annotations ------------------------------------------------------------------------------
+ * Replaces the `contig_annotations` IntervalCollection that UnconditionalSampler.sample() hands to
+ * every computeSample() call (gat/__init__.py:716-718, :580-587), flattened: n_annot tracks x n_keys
+ * keys (contigs for sampling, "contig.isochore" keys for observed counts), annotation-major:
+ * list (a, k) = [offs[a*n_keys+k], offs[a*n_keys+k+1]).  key_ws_nseg[k] = len(workspace[key])
+ * (number of workspace SEGMENTS, the nucleotide-density denominator, gat/Engine.pyx:1437-1441);
+ * may be NULL when density is never requested.  Host pointers; data is copied to the device. */
+int  gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
+                             const uint32_t *start, const uint32_t *end, const uint32_t *key_ws_nseg,
+                             gatb_annotations **out);
+void gatb_annotations_destroy(gatb_annotations *a);
+
+/* ---- counting of given (placed or observed) segment sets ----------------------------------------
+ * Replaces, for n_samples segment sets at once, the loop
+ *     counts[counter][annotation] = sum(counter(sample[key], annotations[annotation][key],
+ *                                               workspace[key]) for key in sample.keys())
+ * of computeSample (gat/__init__.py:580-587) and of Engine.computeCounts (gat/Engine.pyx:2189-2202).
+ * Sample s, key k owns the list [offs[s*n_keys+k], offs[s*n_keys+k+1]) of start/end (host pointers).
+ * key_present[s*n_keys+k] (may be NULL = all present) says whether the key is in sample.keys():
+ * absent keys add nothing, present-but-empty keys add 0 (only visible in float rounding).
+ * counters[n_counters] lists counter ids; out is host memory, [n_counters][n_samples][n_annot]
+ * doubles (integers are exact in a double; nucleotide-density is the float64 sum in key order). */
+int  gatb_count_lists(gatb_ctx *ctx, const gatb_annotations *annos, int n_counters, const int32_t *counters,
+                      uint64_t n_samples, const uint64_t *offs, const uint32_t *start, const uint32_t *end,
+                      const uint8_t *key_present, double *out);
+
+/* ---- placement --------------------------------------------------------------------------------
+ * Replaces SamplerAnnotator(bucket_size, nbuckets).sample(segments[key], workspace[key]) for every
+ * key of one segment track (gat/Engine.pyx:502-646, called from gat/__init__.py:531-546).
+ * Units are the keys of the track in iteration order, already skipping keys whose segment list or
+ * workspace is empty (gat/__init__.py:536-538).  unit_contig[u] in [0,n_contigs) is the contig the
+ * key belongs to ("contig.iso".split(".")[0], gat/Engine.pyx:2863-2866), contigs numbered in order of
+ * first appearance (= sample.keys() order after fromIsochores); has_isochores != 0 when keys carry an
+ * isochore suffix, in which case each contig's placed lists are concatenated and merge(0)-ed before
+ * counting (gat/Engine.pyx:2857-2876).  bucket_size / nbuckets as in --bucket-size / --nbuckets
+ * (0 = automatic, gat/SegmentList.pyx:1164-1165).  Host pointers; data is copied to the device and
+ * the sample-invariant preparation (filter, ltotal, length table, workspace CDF: gat/Engine.pyx:543-565)
+ * runs once, on the GPU. */
+int  gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *unit_contig, int n_contigs,
+                         int has_isochores,
+                         const uint64_t *seg_offs, const uint32_t *seg_start, const uint32_t *seg_end,
+                         const uint64_t *ws_offs, const uint32_t *ws_start, const uint32_t *ws_end,
+                         uint32_t bucket_size, uint32_t nbuckets, gatb_sampler **out);
+void gatb_sampler_destroy(gatb_sampler *s);
+/* capacity (in segments) of one sample's contig-level output, and of contig c inside it */
+uint64_t gatb_sampler_sample_capacity(const gatb_sampler *s);
+
+/* Place samples [sample_begin, sample_begin+n_samples) and return the contig-level segment sets
+ * (what `sample` holds after sample.fromIsochores(), gat/__init__.py:563) to the host:
+ * counts[s*n_contigs+c] segments for contig c of sample s, stored at start/end[s*capacity + contig_base[c] ...]
+ * where capacity = gatb_sampler_sample_capacity() and contig_base is returned in contig_base[n_contigs].
+ * unit_status[s*n_units+u] (may be NULL): bit0 = stopped after 20 non-improving rounds
+ * (gat/Engine.pyx:570-572), bit1 = capacity overflow.  For tests, --output-samples-pattern, and the
+ * same-placement parity fixture. */
+int  gatb_sampler_place(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin,
+                        uint64_t n_samples, uint32_t *start, uint32_t *end, uint32_t *counts,
+                        uint64_t *contig_base, uint8_t *unit_status);
+
+/* ---- the hot path: place + count ----------------------------------------------------------------
+ * Replaces UnconditionalSampler.sample() (gat/__init__.py:704-778) for one track: for every sample
+ * in [sample_begin, sample_begin+n_samples) place all units, merge per contig, count against every
+ * annotation with every requested counter.  The random stream is keyed by (seed, track, unit,
+ * GLOBAL sample index, turn), so the result does not depend on how samples are sharded over GPUs.
+ *   out_counts: [n_counters][n_samples][n_annot]; uint32 for the integer counters, and the
+ *   nucleotide-density plane (if requested) is float64 stored in out_density[n_samples][n_annot].
+ *   out_is_device != 0: out_counts / out_density are device pointers (results stay in HBM, no sync);
+ *   otherwise host pointers (copied back, stream synchronised).
+ *   info (may be NULL, host): [0] total segments placed (contig level), [1] units that hit the
+ *   20-round cap, [2] units that overflowed (then GATB_ERR_CAPACITY is returned). */
+int  gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_counters, const int32_t *counters,
+              uint64_t seed, uint32_t track, uint64_t sample_begin, uint64_t n_samples,
+              uint32_t *out_counts, double *out_density, int out_is_device, uint64_t *info);
+/* samples placed + counted per internal batch (memory/parallelism knob; 0 = default) */
+int  gatb_set_batch_size(gatb_ctx *ctx, uint32_t batch);
+
+/* ---- per-column statistics ------------------------------------------------------------------------
+ * Replaces makeEnrichmentStatistics + getTwoSidedPValue (gat/Engine.pyx:1635-1718, :1543-1576) for
+ * n_cols columns of n_samples simulated counts each: expected (numpy.mean), stddev (numpy.std, ddof 0),
+ * CI95 low/high (sorted[min(off,l-1)], sorted[max(l-off,0)], off=int(0.05*l)), fold with pseudo-count,
+ * empirical two-sided p-value.  counts is [n_samples][n_cols] uint32 (is_float==0) or float64
+ * (is_float!=0), device memory if counts_is_device else host.  observed[n_cols], ref_fold[n_cols]
+ * (NULL = no --null reference) and all outputs are host arrays of n_cols doubles. */
+int  gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float, int counts_is_device,
+                       uint64_t n_samples, int n_cols, const double *observed, const double *ref_fold,
+                       double pseudo_count, double *expected, double *stddev, double *lower95,
+                       double *upper95, double *fold, double *pvalue);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAT_B200_H */

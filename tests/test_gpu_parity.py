@@ -1,0 +1,143 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact: everything here is integer / index work; nucleotide-density is a float64 sum in a fixed
+order and must be bit-exact too."""
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+COUNTERS = ["nucleotide-overlap", "nucleotide-density", "segment-overlap", "segment-midoverlap",
+            "annotation-overlap", "annotation-midoverlap"]
+
+
+def test_place_single_units_match_oracle(ctx, oracle):
+    """SamplerAnnotator.sample of one unit == sequential restatement under the same Philox stream"""
+    from gat_b200 import device
+    rng = np.random.default_rng(11)
+    ntrim = ncp = 0
+    for it in range(60):
+        segs, ws = helpers.random_unit(rng)
+        bucket = int(rng.choice([1, 1, 1, 3, 7]))
+        smp = device.Sampler(ctx, [0], 1, False, [segs], [ws], bucket_size=bucket, nbuckets=100000)
+        n = 6
+        placed, status = smp.place(seed=1234 + it, track=3, sample_begin=10, n_samples=n)
+        smp.close()
+        for s in range(n):
+            exp, info = oracle.sampler_annotator_philox(segs, ws, 1234 + it, 3, 0, 10 + s, bucket_size=bucket)
+            ntrim += info.ntrims
+            ncp += info.ncheckpoints
+            assert np.array_equal(placed[s][0], exp), (it, s, placed[s][0][:5], exp[:5])
+            assert bool(status[s, 0] & 1) == (info.nunsuccessful >= 20)
+    assert ntrim > 0 and ncp > 0          # the overshoot / checkpoint paths were exercised
+
+
+@pytest.mark.parametrize("n_iso", [0, 3])
+def test_place_problem_matches_oracle(ctx, oracle, n_iso):
+    """whole samples: all units placed, isochore units merged per contig (fromIsochores)"""
+    from gat_b200 import device
+    rng = np.random.default_rng(5 + n_iso)
+    pr = helpers.random_problem(rng, n_contigs=4, n_iso=n_iso)
+    smp = device.Sampler(ctx, pr["unit_contig"], pr["n_contigs"], pr["has_isochores"],
+                         pr["unit_segments"], pr["unit_workspace"])
+    n = 8
+    placed, status = smp.place(seed=99, track=0, sample_begin=0, n_samples=n)
+    smp.close()
+    for s in range(n):
+        _, exp = oracle.compute_sample_philox(pr["unit_contig"], pr["unit_segments"], pr["unit_workspace"],
+                                              pr["annotations"], pr["cws_nseg"], ["nucleotide-overlap"],
+                                              seed=99, track=0, sample=s, has_isochores=pr["has_isochores"],
+                                              return_placed=True)
+        for c in range(pr["n_contigs"]):
+            assert np.array_equal(placed[s][c], exp[c]), (s, c)
+
+
+def test_count_lists_match_oracle(ctx, oracle):
+    """all six counters on given segment sets (same-placement parity), several keys and samples"""
+    from gat_b200 import device
+    rng = np.random.default_rng(21)
+    for it in range(6):
+        K, A, S = int(rng.integers(1, 5)), int(rng.integers(1, 12)), int(rng.integers(1, 6))
+        span = int(rng.choice([5000, 300000]))
+        annos = [[helpers.random_list(rng, span, int(rng.integers(0, 120)), int(rng.choice([20, 2000]))) for _ in range(K)]
+                 for _ in range(A)]
+        nseg = [int(rng.integers(0, 4)) for _ in range(K)]
+        samples = [[helpers.random_list(rng, span, int(rng.integers(0, 150)), int(rng.choice([10, 400, 5000]))) for _ in range(K)]
+                   for _ in range(S)]
+        an = device.Annotations(ctx, annos, key_ws_nseg=nseg)
+        got = an.count_lists(COUNTERS, samples)
+        an.close()
+        for s in range(S):
+            exp = oracle.count_placed(samples[s], annos, nseg, COUNTERS)
+            assert np.array_equal(got[:, s, :], exp), (it, s, got[:, s, :], exp)
+
+
+@pytest.mark.parametrize("n_iso", [0, 3])
+def test_run_matches_oracle(ctx, oracle, n_iso):
+    """place + count in one call == oracle computeSample for every sample; independent of batching"""
+    from gat_b200 import device
+    rng = np.random.default_rng(31 + n_iso)
+    pr = helpers.random_problem(rng, n_contigs=3, n_iso=n_iso, n_annot=11)
+    smp = device.Sampler(ctx, pr["unit_contig"], pr["n_contigs"], pr["has_isochores"],
+                         pr["unit_segments"], pr["unit_workspace"])
+    an = device.Annotations(ctx, pr["annotations"], key_ws_nseg=pr["cws_nseg"])
+    n = 40
+    res, info = smp.run(an, COUNTERS, seed=7, track=2, sample_begin=5, n_samples=n)
+    ctx.set_batch_size(16)                 # 3 batches
+    res2, _ = smp.run(an, COUNTERS, seed=7, track=2, sample_begin=5, n_samples=n)
+    ctx.set_batch_size(0)
+    for name in COUNTERS:
+        assert np.array_equal(res[name], res2[name]), name
+    for s in range(n):
+        exp = oracle.compute_sample_philox(pr["unit_contig"], pr["unit_segments"], pr["unit_workspace"],
+                                           pr["annotations"], pr["cws_nseg"], COUNTERS, seed=7, track=2,
+                                           sample=5 + s, has_isochores=pr["has_isochores"])
+        for i, name in enumerate(COUNTERS):
+            assert np.array_equal(np.asarray(res[name][s], dtype=np.float64), exp[i]), (s, name)
+    assert int(info[2]) == 0
+    smp.close()
+    an.close()
+
+
+def test_column_stats_match_oracle(ctx, oracle):
+    """expected / CI / fold / p-value bit-exact on integer columns; stddev to 1e-12 relative"""
+    rng = np.random.default_rng(41)
+    for l in (1, 7, 19, 20, 100, 1000, 4097):
+        A = 9
+        counts = rng.integers(0, 30, size=(l, A)).astype(np.uint32)
+        counts[:, 0] = 5                                   # constant column
+        counts[:, 1] = 0                                   # all-zero column: fold = 1
+        obs = rng.integers(0, 35, size=A).astype(np.float64)
+        obs[2] = counts[:, 2].max() + 10                   # above every sample
+        obs[3] = -1 if False else 0.0
+        got = ctx.column_stats(counts, obs, pseudo_count=1.0)
+        for a in range(A):
+            st = oracle.enrichment_statistics(obs[a], counts[:, a].astype(np.float64), pseudo_count=1.0)
+            assert got["expected"][a] == st.expected
+            assert got["lower95"][a] == st.lower95 and got["upper95"][a] == st.upper95
+            assert got["fold"][a] == st.fold
+            assert got["pvalue"][a] == st.pvalue, (l, a, obs[a], got["pvalue"][a], st.pvalue)
+            assert got["stddev"][a] == pytest.approx(st.stddev, rel=1e-12, abs=1e-12)
+
+
+def test_column_stats_float_and_reference(ctx, oracle):
+    """float64 (nucleotide-density) columns incl. the truncating comparator, and the --null fold shift"""
+    rng = np.random.default_rng(43)
+    l, A = 500, 6
+    counts = np.round(rng.random((l, A)) * 4, 2)
+    obs = np.round(rng.random(A) * 4, 2)
+    obs[0] = counts[3, 0]
+    got = ctx.column_stats(counts, obs)
+    ref = np.array([0.5, 1.0, 2.0, 1.5, 3.0, 0.25])
+    got_ref = ctx.column_stats(counts, obs, ref_fold=ref)
+    for a in range(A):
+        st = oracle.enrichment_statistics(obs[a], counts[:, a])
+        assert got["pvalue"][a] == st.pvalue
+        assert got["lower95"][a] == st.lower95 and got["upper95"][a] == st.upper95
+        assert got["expected"][a] == pytest.approx(st.expected, rel=1e-13)
+        assert got["stddev"][a] == pytest.approx(st.stddev, rel=1e-12)
+        st = oracle.enrichment_statistics(obs[a], counts[:, a], reference_fold=ref[a])
+        assert got_ref["pvalue"][a] == st.pvalue
+        assert got_ref["expected"][a] == pytest.approx(st.expected, rel=1e-13)
+        assert got_ref["lower95"][a] == st.lower95 and got_ref["upper95"][a] == st.upper95
