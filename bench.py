@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- samples/sec of the GAT simulation hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): the metric's own shape -- synthetic hg19 (24 contigs), 10 000 segments
+against 1 000 annotation tracks of 20 000 intervals, contig workspace, nucleotide-overlap counter.
+A step = one pass of the hot path (placement of every unit + counting against every annotation) over
+one batch of `--samples-per-step` Monte-Carlo samples per GPU; sample indices advance every step, so no
+step repeats another's work.  Weak scaling: every rank runs the same batch size on its own shard of the
+global sample index space; for N > 1 the per-step count slab is all-gathered over NCCL (the path's one
+exchange step) inside the timed region.
+
+value   whole-job samples/s, inputs resident in HBM, counts left in HBM (CUDA events, max over ranks)
+e2e     same metric through the C ABI with HOST buffers: every step uploads segments, workspace and
+        annotations (gatb_sampler_create / gatb_annotations_create), runs, and reads the count matrix
+        back to the host
+roofline  dominant kernel (counting): SURVEY 8d algorithmic bytes per launch / CUDA-event kernel time
+cpu_baseline  the reference itself (oracle/_ref) on the host cores, bounded sample, rank 0, N=1
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "samples/sec (10k segs x 1k annotations)"
+UNIT = "samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--segments", type=int, default=10000)
+    ap.add_argument("--annotations", type=int, default=1000)
+    ap.add_argument("--annotation-intervals", type=int, default=20000)
+    ap.add_argument("--samples-per-step", type=int, default=4096)
+    ap.add_argument("--counter", default="nucleotide-overlap")
+    ap.add_argument("--isochores", action="store_true")
+    ap.add_argument("--cpu-samples", type=int, default=0, help="reference samples (0 = about 10-30 s worth)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- workload
+def build_workload(args):
+    """synthetic inputs, prepared as gat-run.py prepares them, flattened to the CSR of the C ABI"""
+    import gat_b200
+    from gat_b200 import synthetic, device
+    segments, annotations, workspaces, iso = synthetic.make(args.segments, args.annotations,
+                                                            args.annotation_intervals, isochores=args.isochores)
+    workspace = synthetic.prepare(segments, annotations, workspaces, iso)
+    problem = gat_b200.TrackProblem(segments["merged"], workspace)
+    atracks, lists, nseg = gat_b200.buildContigAnnotations(annotations, workspace, problem.contigs)
+    A, C = len(atracks), len(problem.contigs)
+    anno_csr = device.to_csr([lists[a][c] for a in range(A) for c in range(C)])
+    seg_csr = device.to_csr(problem.unit_segments)
+    ws_csr = device.to_csr(problem.unit_workspace)
+    n_a_total = int(anno_csr[0][-1])
+    wl = dict(problem=problem, A=A, C=C, nseg=np.array(nseg, dtype=np.uint32), anno_csr=anno_csr, seg_csr=seg_csr,
+              ws_csr=ws_csr, n_a_total=n_a_total, n_segments=int(seg_csr[0][-1]),
+              collections=(segments, annotations, workspace))
+    return wl
+
+
+def config_of(args, wl, world):
+    return {"workload": "synthetic hg19 (24 contigs, contig workspace%s): %i segments x %i annotation tracks "
+                        "(%i intervals after normalize), counter %s, sampler annotator"
+                        % (", 8 GC isochores" if args.isochores else "", wl["n_segments"], wl["A"],
+                           wl["n_a_total"], args.counter),
+            "samples_per_step_per_gpu": args.samples_per_step,
+            "global_samples_per_step": args.samples_per_step * world,
+            "parallelism": "samples sharded over %i GPU(s), inputs replicated, one NCCL all-gather of the "
+                           "count slab per step" % world if world > 1 else "1 GPU",
+            "l2": "inputs larger than L2: annotation tiles %.0f MB + placed segments of the batch"
+                  % (wl["n_a_total"] * 12 / 1e6),
+            "data_seed": 20260101}
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """DRAM bytes per count-kernel launch from the committed ncu --set full capture, if any"""
+    p = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------- reference arm
+def reference_rate(args, wl, seconds_target=15.0):
+    """the reference's UnconditionalSampler.sample on this box's host cores: single process and its
+    multiprocessing path, each on a bounded sample; returns the faster with both reported"""
+    from oracle import ref_bench
+    segments, annotations, workspace = wl["collections"]
+    cores = os.cpu_count() or 1
+    # probe to size the sample
+    dt, _ = ref_bench.time_sampling(segments, annotations, workspace, [args.counter], 2, num_threads=0)
+    per = dt / 2
+    n1 = args.cpu_samples or int(max(4, min(200, seconds_target / max(per, 1e-3))))
+    dt1, _ = ref_bench.time_sampling(segments, annotations, workspace, [args.counter], n1, num_threads=0)
+    r1 = n1 / dt1
+    # its multiprocessing path: every task re-pickles all interval arrays, so bound it hard
+    nm = max(cores, 8) if per * wl["A"] < 1e9 else cores
+    nm = min(nm, 4 * n1)
+    rm, dtm = None, None
+    try:
+        dtm, _ = ref_bench.time_sampling(segments, annotations, workspace, [args.counter], nm, num_threads=cores)
+        rm = nm / dtm
+    except Exception as e:  # pragma: no cover
+        rm = None
+        sys.stderr.write("reference multiprocessing path failed: %s\n" % e)
+    best, used = (r1, 1)
+    if rm is not None and rm > r1:
+        best, used = rm, cores
+    sample = ("reference UnconditionalSampler.sample: %i samples single-process in %.1f s (%.3f samples/s); "
+              "%s; faster mode reported" %
+              (n1, dt1, r1, ("%i samples with --num-threads=%i in %.1f s (%.3f samples/s)" % (nm, cores, dtm, rm))
+               if rm is not None else "multiprocessing path failed"))
+    return best, used, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_bench
+    if not ref_bench.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (python oracle/build_ref.py)"}))
+        return
+    wl = build_workload(args)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    t0 = time.perf_counter()
+    rate, cores, sample = reference_rate(args, wl, seconds_target=20.0 * max(args.steps, 1) / 5.0)
+    line = {"metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * args.samples_per_step / rate,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic", "impl": "reference", "config": config_of(args, wl, world),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gat_b200 import device
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    wl = build_workload(args)
+    pr, A, C, B = wl["problem"], wl["A"], wl["C"], args.samples_per_step
+    cid = device.COUNTER_ID[args.counter]
+    is_density = cid == device.DENSITY
+
+    ctx = device.Context(local)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_batch_size(B)
+    annos = device.Annotations(ctx, None, key_ws_nseg=wl["nseg"], csr=(A, C) + wl["anno_csr"])
+    smp = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(wl["seg_csr"], wl["ws_csr"]))
+    out_u = torch.zeros((1, B, A), dtype=torch.int32, device=dev)
+    out_f = torch.zeros((B, A), dtype=torch.float64, device=dev) if is_density else None
+    gathered = torch.empty((world * B, A), dtype=torch.float64 if is_density else torch.int32, device=dev) \
+        if world > 1 else None
+
+    def step(i):
+        begin = (i * world + rank) * B             # global sample indices of this rank's shard
+        info = smp.run(annos, [args.counter], 20260101, 0, begin, B, out_counts_ptr=out_u.data_ptr(),
+                       out_density_ptr=out_f.data_ptr() if is_density else None)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_f if is_density else out_u[0])
+        return info
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        info = step(i)
+    placed_per_sample = float(info[0]) / B if args.warmup else None
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        info = step(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clock_info = clocks.stop() if rank == 0 else None
+    placed_per_sample = float(info[0]) / B
+    value = world * B * args.steps / (ms / 1000.0)
+
+    # ---- per-kernel times (CUDA events around each launch, same stream), for the roofline
+    ctx.profile(True)
+    nprof = max(1, min(args.steps, 3))
+    for i in range(nprof):
+        step(args.warmup + args.steps + i)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    count_ms = prof["count"][0] / max(prof["count"][1], 1)
+    place_ms = prof["place"][0] / max(prof["place"][1], 1)
+    merge_ms = prof["merge"][0] / max(prof["merge"][1], 1)
+    # SURVEY 8d algorithmic bytes, per launch = B samples
+    count_bytes = B * (8.0 * (A * placed_per_sample + wl["n_a_total"]) + 4.0 * A)
+    place_bytes = B * 8.0 * 2.0 * placed_per_sample
+    peak, peak_src = measured_peak()
+    achieved = count_bytes / (count_ms / 1000.0) / 1e9
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                "algorithmic_bytes_per_launch": count_bytes, "kernel_ms": count_ms,
+                "kernel_share_of_step": prof["count"][0] / max(sum(v[0] for v in prof.values()), 1e-9),
+                "other_kernels": {"place_kernel_ms": place_ms, "contig_merge_kernel_ms": merge_ms,
+                                  "place_algorithmic_GBps": place_bytes / max(place_ms, 1e-9) / 1e6,
+                                  "placements_per_s": placed_per_sample * B / max(place_ms, 1e-9) * 1e3}}
+
+    # ---- e2e: host buffers in, host count matrix out, through the C ABI, every step
+    e2e = None
+    if not args.no_e2e:
+        def pinned(x):       # pinned copies of the CSR buffers (viewed signed: torch lacks some unsigned ops)
+            signed = {np.dtype(np.uint64): np.int64, np.dtype(np.uint32): np.int32}[x.dtype]
+            return torch.from_numpy(np.ascontiguousarray(x).view(signed)).pin_memory()
+
+        pin = [pinned(x) for x in wl["anno_csr"] + wl["seg_csr"] + wl["ws_csr"]]
+        unsign = {torch.int64: np.uint64, torch.int32: np.uint32}
+        pa = tuple(t.numpy().view(unsign[t.dtype]) for t in pin[0:3])
+        ps = tuple(t.numpy().view(unsign[t.dtype]) for t in pin[3:6])
+        pw = tuple(t.numpy().view(unsign[t.dtype]) for t in pin[6:9])
+        h2d = sum(t.numel() * t.element_size() for t in pin)
+        host_out = torch.empty((B, A), dtype=torch.int32).pin_memory()
+        host_np = host_out.numpy().view(np.uint32)
+        host_f = np.zeros((B, A), dtype=np.float64) if is_density else None
+        ids = device.counter_ids([args.counter])
+        info_np = np.zeros(3, dtype=np.uint64)
+
+        def e2e_step(i):
+            a2 = device.Annotations(ctx, None, key_ws_nseg=wl["nseg"], csr=(A, C) + pa)
+            s2 = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(ps, pw))
+            begin = (i * world + rank) * B
+            ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), 20260101, 0, begin, B,
+                                       device._p(host_np), device._p(host_f), 0, device._p(info_np)))
+            s2.close()
+            a2.close()
+            return int(host_np[0, 0])
+
+        e2e_step(10 ** 5)                           # warm-up (allocator, pinned paths)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(10 ** 5 + 1 + i)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(B * A * (8 if is_density else 4)),
+               "what": "gatb_annotations_create + gatb_sampler_create + gatb_run with host in/out buffers per step"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_bench
+        if ref_bench.available():
+            rate, cores, sample = reference_rate(args, wl)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample}
+        else:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64" if is_density else "u32",
+                "data": "synthetic", "config": config_of(args, wl, world), "clocks": clock_info,
+                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "placed_segments_per_sample": placed_per_sample,
+                "segment_placements_per_s": value * placed_per_sample}
+        print(json.dumps(line))
+    smp.close()
+    annos.close()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,7 +16,7 @@ ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_TOO_LARGE, ERR_RANGE = -1, -2, -3, -4, 
 # every symbol include/gat_b200.h declares (tests/test_abi.py checks the .so exports them all)
 SYMBOLS = [
     "gatb_version", "gatb_create", "gatb_destroy", "gatb_last_error", "gatb_set_stream",
-    "gatb_synchronize", "gatb_launch_count", "gatb_set_batch_size",
+    "gatb_synchronize", "gatb_launch_count", "gatb_set_batch_size", "gatb_profile", "gatb_profile_read",
     "gatb_annotations_create", "gatb_annotations_destroy", "gatb_count_lists",
     "gatb_sampler_create", "gatb_sampler_destroy", "gatb_sampler_sample_capacity",
     "gatb_sampler_place", "gatb_run", "gatb_column_stats",
@@ -61,6 +61,10 @@ def load():
     L.gatb_launch_count.argtypes = [vp]
     L.gatb_set_batch_size.restype = i32
     L.gatb_set_batch_size.argtypes = [vp, u32]
+    L.gatb_profile.restype = i32
+    L.gatb_profile.argtypes = [vp, i32]
+    L.gatb_profile_read.restype = i32
+    L.gatb_profile_read.argtypes = [vp, vp, vp]
     L.gatb_annotations_create.restype = i32
     L.gatb_annotations_create.argtypes = [vp, i32, i32, vp, vp, vp, vp, ctypes.POINTER(vp)]
     L.gatb_annotations_destroy.restype = None

@@ -32,6 +32,29 @@ struct gatb_ctx {
     uint32_t tile_budget = 0;
     int count_threads = 512;
     uint32_t schunk_max = 128;
+    // optional per-kernel timing (bench.py roofline): CUDA events around every launch
+    bool profiling = false;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+};
+
+enum { PROF_PLACE = 0, PROF_MERGE = 1, PROF_COUNT = 2, PROF_OTHER = 3, PROF_NCLS = 4 };
+
+struct ProfScope {
+    gatb_ctx *ctx; int cls; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(gatb_ctx *c, int k) : ctx(c), cls(k)
+    {
+        ctx->launches++;
+        if (!ctx->profiling) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~ProfScope()
+    {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->spans.push_back({cls, a, b});
+    }
 };
 
 static std::string g_create_err;
@@ -137,6 +160,29 @@ extern "C" int gatb_synchronize(gatb_ctx *ctx)
 }
 
 extern "C" uint64_t gatb_launch_count(gatb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int gatb_profile(gatb_ctx *ctx, int enable)
+{
+    if (!ctx) return GATB_ERR_INVALID;
+    ctx->profiling = enable != 0;
+    return GATB_OK;
+}
+
+extern "C" int gatb_profile_read(gatb_ctx *ctx, double *ms, uint64_t *launches)
+{
+    if (!ctx || !ms || !launches) return GATB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < PROF_NCLS; i++) { ms[i] = 0; launches[i] = 0; }
+    for (auto &sp : ctx->spans) {
+        float t = 0;
+        cudaEventElapsedTime(&t, sp.a, sp.b);
+        ms[sp.cls] += t; launches[sp.cls]++;
+        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    ctx->spans.clear();
+    return GATB_OK;
+}
 
 extern "C" int gatb_set_batch_size(gatb_ctx *ctx, uint32_t batch)
 {
@@ -385,8 +431,7 @@ extern "C" int gatb_count_lists(gatb_ctx *ctx, const gatb_annotations *annos, in
 
     std::vector<uint32_t> h_u(n_samples * A);
     for (int c = 0; c < n_counters; c++) {
-        CU(ctx, launch_count(st, counters[c], p, ctx->count_threads));
-        ctx->launches++;
+        { ProfScope ps(ctx, PROF_COUNT); CU(ctx, launch_count(st, counters[c], p, ctx->count_threads)); }
         double *o = out + (uint64_t)c * n_samples * A;
         if (counters[c] == GATB_NUCLEOTIDE_DENSITY) {
             CU(ctx, cudaMemcpyAsync(o, d_outf.p, n_samples * A * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -490,9 +535,9 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
     TRY(d_scratch.alloc(scratch_total));
     TRY(d_scratch_off.upload(scratch_off.data(), U, st));
     if (e == cudaSuccess) {
+        ProfScope ps(ctx, PROF_OTHER);
         launch_prep_units(st, s->units.p, U, d_seg_start.p, d_seg_end.p, s->ws_start.p, s->ws_end.p, s->ws_cuminc.p,
                           s->len_tab.p, d_scratch.p, d_scratch_off.p, bucket_size, nbuckets);
-        ctx->launches++;
         e = cudaGetLastError();
     }
     TRY(cudaMemcpyAsync(s->h_units.data(), s->units.p, U * sizeof(UnitDesc), cudaMemcpyDeviceToHost, st));
@@ -635,8 +680,7 @@ static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t 
     }
     p.status = s->status.p; p.n_units = s->n_units; p.n_samples = B; p.sample_begin = sample_begin;
     p.seed = seed; p.track = track;
-    launch_place(st, p);
-    ctx->launches++;
+    { ProfScope ps(ctx, PROF_PLACE); launch_place(st, p); }
     CU(ctx, cudaGetLastError());
     if (s->has_iso) {
         MergeParams m;
@@ -645,13 +689,14 @@ static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t 
         m.contig_base = s->contig_base.p; m.unit_buf = s->unit_buf.p; m.unit_stride = s->unit_stride;
         m.unit_n = s->unit_n.p; m.placed = s->placed.p; m.placed_stride = s->placed_stride;
         m.placed_n = s->placed_n.p; m.n_units = s->n_units; m.n_contigs = s->n_contigs; m.n_samples = B;
-        launch_contig_merge(st, m);
-        ctx->launches++;
+        { ProfScope ps(ctx, PROF_MERGE); launch_contig_merge(st, m); }
         CU(ctx, cudaGetLastError());
     }
-    tally_kernel<<<std::min<uint32_t>(1024, (uint32_t)(((uint64_t)B * s->n_units + 255) / 256)), 256, 0, st>>>(
-        s->placed_n.p, (uint64_t)B * s->n_contigs, s->status.p, (uint64_t)B * s->n_units, s->tally.p);
-    ctx->launches++;
+    {
+        ProfScope ps(ctx, PROF_OTHER);
+        tally_kernel<<<std::min<uint32_t>(1024, (uint32_t)(((uint64_t)B * s->n_units + 255) / 256)), 256, 0, st>>>(
+            s->placed_n.p, (uint64_t)B * s->n_contigs, s->status.p, (uint64_t)B * s->n_units, s->tally.p);
+    }
     CU(ctx, cudaGetLastError());
     return GATB_OK;
 }
@@ -741,8 +786,7 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
             double *dst_f = out_density ? out_density + done * A : nullptr;
             p.out_u32 = out_is_device ? dst_u : s->out_tmp.p;
             p.out_f64 = out_is_device ? dst_f : s->out_tmp_f.p;
-            CU(ctx, launch_count(st, counters[c], p, ctx->count_threads));
-            ctx->launches++;
+            { ProfScope ps(ctx, PROF_COUNT); CU(ctx, launch_count(st, counters[c], p, ctx->count_threads)); }
             if (!out_is_device) {
                 if (dens) CU(ctx, cudaMemcpyAsync(dst_f, s->out_tmp_f.p, (uint64_t)b * A * sizeof(double), cudaMemcpyDeviceToHost, st));
                 else CU(ctx, cudaMemcpyAsync(dst_u, s->out_tmp.p, (uint64_t)b * A * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -799,7 +843,7 @@ extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float
     const uint64_t off = (uint64_t)(0.05 * (double)l);
     if (off > 0) { p.rank_lo = std::min<uint64_t>(off, l - 1); p.rank_hi = (l > off) ? l - off : 0; }
     else { p.rank_lo = 0; p.rank_hi = l - 1; }
-    launch_stats_pass1(st, p); ctx->launches++;
+    { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass1(st, p); }
     CU(ctx, cudaGetLastError());
     std::vector<double> h_sum(A), h_sq(A), h_qlo(A), h_qhi(A), h_mean(A);
     std::vector<unsigned long long> h_cnt(3 * (size_t)A);
@@ -808,8 +852,8 @@ extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float
     for (uint32_t a = 0; a < A; a++) h_mean[a] = h_sum[a] / (double)l;        // numpy.mean (:1671)
     CU(ctx, d_mean.upload(h_mean.data(), A, st));
     p.mean = d_mean.p;
-    launch_stats_pass2(st, p); ctx->launches++;
-    launch_stats_select(st, p, nullptr); ctx->launches++;
+    { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass2(st, p); }
+    { ProfScope ps(ctx, PROF_OTHER); launch_stats_select(st, p, nullptr); }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(h_sq.data(), d_sq.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaMemcpyAsync(h_qlo.data(), d_qlo.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));

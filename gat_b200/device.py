@@ -94,6 +94,17 @@ class Context(object):
     def launch_count(self):
         return int(self.lib.gatb_launch_count(self.handle))
 
+    def profile(self, enable=True):
+        """bracket every kernel launch with CUDA events (see profile_read)"""
+        self.check(self.lib.gatb_profile(self.handle, int(bool(enable))))
+
+    def profile_read(self):
+        """-> {class: (device ms, launches)} accumulated since the last read; classes place/merge/count/other"""
+        ms = np.zeros(4, dtype=np.float64)
+        n = np.zeros(4, dtype=np.uint64)
+        self.check(self.lib.gatb_profile_read(self.handle, _p(ms), _p(n)))
+        return dict((k, (float(ms[i]), int(n[i]))) for i, k in enumerate(["place", "merge", "count", "other"]))
+
     def column_stats(self, counts, observed, pseudo_count=1.0, ref_fold=None, device_ptr=None,
                      n_samples=None, n_cols=None, is_float=None):
         """per-column expected/stddev/CI95/fold/pvalue (gat/Engine.pyx:1635-1718).
@@ -123,12 +134,16 @@ class Annotations(object):
 
     lists[a][k]: intervals of track a on key k (n_annot x n_keys)."""
 
-    def __init__(self, ctx, lists, key_ws_nseg=None):
+    def __init__(self, ctx, lists, key_ws_nseg=None, csr=None):
+        """lists[a][k], or csr=(n_annot, n_keys, offs, start, end) already flattened annotation-major"""
         self.ctx = ctx
-        self.n_annot = len(lists)
-        self.n_keys = len(lists[0]) if self.n_annot else 0
-        flat = [lists[a][k] for a in range(self.n_annot) for k in range(self.n_keys)]
-        offs, start, end = to_csr(flat)
+        if csr is not None:
+            self.n_annot, self.n_keys, offs, start, end = csr
+        else:
+            self.n_annot = len(lists)
+            self.n_keys = len(lists[0]) if self.n_annot else 0
+            flat = [lists[a][k] for a in range(self.n_annot) for k in range(self.n_keys)]
+            offs, start, end = to_csr(flat)
         nseg = None if key_ws_nseg is None else np.ascontiguousarray(key_ws_nseg, dtype=np.uint32)
         h = ctypes.c_void_p()
         ctx.check(ctx.lib.gatb_annotations_create(ctx.handle, self.n_annot, self.n_keys, _p(offs), _p(start),
@@ -164,13 +179,18 @@ class Sampler(object):
     """one segment track + workspace staged on the GPU for placement (gatb_sampler)."""
 
     def __init__(self, ctx, unit_contig, n_contigs, has_isochores, unit_segments, unit_workspace,
-                 bucket_size=1, nbuckets=100000):
+                 bucket_size=1, nbuckets=100000, csr=None):
+        """unit_segments / unit_workspace: lists of (n,2) arrays per unit, or csr=(seg_csr, ws_csr) with
+        each (offs, start, end) already flattened"""
         self.ctx = ctx
         self.n_units = len(unit_contig)
         self.n_contigs = int(n_contigs)
         uc = np.ascontiguousarray(unit_contig, dtype=np.int32)
-        soffs, sstart, send = to_csr(unit_segments)
-        woffs, wstart, wend = to_csr(unit_workspace)
+        if csr is not None:
+            (soffs, sstart, send), (woffs, wstart, wend) = csr
+        else:
+            soffs, sstart, send = to_csr(unit_segments)
+            woffs, wstart, wend = to_csr(unit_workspace)
         h = ctypes.c_void_p()
         ctx.check(ctx.lib.gatb_sampler_create(ctx.handle, self.n_units, _p(uc), self.n_contigs, int(bool(has_isochores)),
                                               _p(soffs), _p(sstart), _p(send), _p(woffs), _p(wstart), _p(wend),

@@ -67,6 +67,13 @@ int         gatb_synchronize(gatb_ctx *ctx);
 /* number of this library's kernels launched on the context since creation (bench "gpu_launches") */
 uint64_t    gatb_launch_count(gatb_ctx *ctx);
 
+/* optional per-kernel timing: when enabled, every kernel launch is bracketed by CUDA events on the
+ * context's stream.  gatb_profile_read synchronises and returns (and clears) the accumulated device
+ * milliseconds and launch counts per kernel class: [0] placement K1, [1] isochore merge K2,
+ * [2] counting K3/K4, [3] everything else (preparation, tally, statistics). */
+int         gatb_profile(gatb_ctx *ctx, int enable);
+int         gatb_profile_read(gatb_ctx *ctx, double *ms /*[4]*/, uint64_t *launches /*[4]*/);
+
 /* ---- annotations ------------------------------------------------------------------------------
  * Replaces the `contig_annotations` IntervalCollection that UnconditionalSampler.sample() hands to
  * every computeSample() call (gat/__init__.py:716-718, :580-587), flattened: n_annot tracks x n_keys
