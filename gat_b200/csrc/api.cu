@@ -226,18 +226,42 @@ struct gatb_annotations {
 
 static inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-// bytes and index geometry of one (track, key) list inside a tile
-static void list_geometry(uint64_t n, uint32_t extent, uint32_t &iv_bytes, uint32_t &nbins, uint32_t &shift,
-                          uint32_t &idx_bytes)
+// geometry of tile (group g, key k): header | idx8[nbins+1] | KMAX interval lists (n+2 entries each)
+struct TileGeom { uint32_t bytes, nbins, shift, idx_off, iv_off[KMAX]; bool ok; };
+
+static TileGeom tile_geometry(const uint64_t *offs, const uint32_t *end, uint32_t A, uint32_t K,
+                              uint32_t a0, uint32_t ka, uint32_t k, uint32_t bin_factor)
 {
-    iv_bytes = align16((uint32_t)((n + 1) * 8));
-    nbins = 0; shift = 0; idx_bytes = 0;
-    if (n <= 65534) {
-        uint64_t target = std::max<uint64_t>(2 * n, 16);
-        while ((((uint64_t)extent >> shift) + 1) > target) shift++;
-        nbins = (extent >> shift) + 1;
-        idx_bytes = align16((nbins + 1) * 2);
+    TileGeom t;
+    memset(&t, 0, sizeof(t));
+    t.ok = true;
+    uint64_t max_n = 0;
+    uint32_t extent = 0;
+    bool indexable = true;
+    for (uint32_t kk = 0; kk < ka && a0 + kk < A; kk++) {
+        const uint64_t l = (uint64_t)(a0 + kk) * K + k;
+        const uint64_t n = offs[l + 1] - offs[l];
+        max_n = std::max(max_n, n);
+        if (n) extent = std::max(extent, end[offs[l + 1] - 1]);
+        if (n > 65534) indexable = false;
     }
+    uint64_t o = align16((uint32_t)sizeof(TileHeader));
+    if (indexable) {
+        const uint64_t target = std::max<uint64_t>((uint64_t)bin_factor * max_n, 16);
+        while ((((uint64_t)extent >> t.shift) + 1) > target) t.shift++;
+        t.nbins = (extent >> t.shift) + 1;
+        t.idx_off = (uint32_t)o;
+        o += (uint64_t)(t.nbins + 1) * 16;
+    }
+    for (uint32_t kk = 0; kk < (uint32_t)KMAX; kk++) {
+        uint64_t n = 0;
+        if (kk < ka && a0 + kk < A) { const uint64_t l = (uint64_t)(a0 + kk) * K + k; n = offs[l + 1] - offs[l]; }
+        t.iv_off[kk] = (uint32_t)o;
+        o += ((n + 2) * 8 + 15) & ~15ull;
+        if (o > 0xfffffff0ull) { t.ok = false; return t; }
+    }
+    t.bytes = (uint32_t)o;
+    return t;
 }
 
 extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
@@ -253,33 +277,26 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
     CU(ctx, cudaSetDevice(ctx->device));
 
     const uint32_t A = (uint32_t)n_annot, K = (uint32_t)n_keys;
-    // per-list geometry
-    std::vector<uint32_t> lbytes(n_lists);
-    for (uint64_t l = 0; l < n_lists; l++) {
-        uint64_t n = offs[l + 1] - offs[l];
-        uint32_t extent = n ? end[offs[l + 1] - 1] : 0;
-        uint32_t ivb, nb, sh, ib;
-        list_geometry(n, extent, ivb, nb, sh, ib);
-        lbytes[l] = ivb + ib;
-    }
+    const uint32_t bin_factor = std::max(1u, env_u32("GATB_BIN_FACTOR", 2));
     // tile budget: what one CTA can opt in to, minus the accumulators
     uint32_t budget = ctx->tile_budget;
     if (budget == 0) {
         size_t acc = (size_t)ctx->schunk_max * KMAX * 8 + 16;
         budget = (uint32_t)(ctx->smem_optin > acc + 1024 ? ctx->smem_optin - acc - 1024 : 32768);
     }
-    const uint32_t hdr = align16((uint32_t)sizeof(TileHeader));
-    // largest group size whose every tile fits; else the largest that fits most tiles (ka=1 floor)
+    // largest group size whose every tile fits the budget (floor: one track per tile; oversized tiles
+    // are then read from global memory by the kernel)
     uint32_t ka = 1;
     for (uint32_t cand = KMAX; cand >= 1; cand--) {
         uint32_t worst = 0;
-        for (uint32_t a0 = 0; a0 < A; a0 += cand)
+        bool ok = true;
+        for (uint32_t a0 = 0; a0 < A && ok; a0 += cand)
             for (uint32_t k = 0; k < K; k++) {
-                uint64_t b = hdr;
-                for (uint32_t a = a0; a < std::min(A, a0 + cand); a++) b += lbytes[(uint64_t)a * K + k];
-                worst = (uint32_t)std::max<uint64_t>(worst, std::min<uint64_t>(b, 0xffffffffu));
+                TileGeom t = tile_geometry(offs, end, A, K, a0, cand, k, bin_factor);
+                if (!t.ok) { ok = false; break; }
+                worst = std::max(worst, t.bytes);
             }
-        if (worst <= budget || cand == 1) { ka = cand; break; }
+        if ((ok && worst <= budget) || cand == 1) { ka = cand; break; }
     }
     const uint32_t G = (A + ka - 1) / ka;
 
@@ -290,51 +307,50 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
     uint32_t max_tile = 0;
     for (uint32_t g = 0; g < G; g++)
         for (uint32_t k = 0; k < K; k++) {
-            uint64_t b = hdr;
-            for (uint32_t a = g * ka; a < std::min(A, (g + 1) * ka); a++) b += lbytes[(uint64_t)a * K + k];
-            if (b > 0xfffffff0ull) return fail(ctx, GATB_ERR_INVALID, "annotations: tile larger than 4 GiB");
+            TileGeom t = tile_geometry(offs, end, A, K, g * ka, ka, k, bin_factor);
+            if (!t.ok) return fail(ctx, GATB_ERR_INVALID, "annotations: tile larger than 4 GiB");
             tile_off[(size_t)g * K + k] = total;
-            tile_bytes[(size_t)g * K + k] = (uint32_t)b;
-            max_tile = std::max(max_tile, (uint32_t)b);
-            total += b;
+            tile_bytes[(size_t)g * K + k] = t.bytes;
+            max_tile = std::max(max_tile, t.bytes);
+            total += t.bytes;
         }
     std::vector<uint8_t> blob(total);
     for (uint32_t g = 0; g < G; g++)
         for (uint32_t k = 0; k < K; k++) {
-            uint8_t *t = blob.data() + tile_off[(size_t)g * K + k];
+            uint8_t *tp = blob.data() + tile_off[(size_t)g * K + k];
+            const TileGeom t = tile_geometry(offs, end, A, K, g * ka, ka, k, bin_factor);
             TileHeader h;
             memset(&h, 0, sizeof(h));
-            uint32_t o = hdr;
-            for (uint32_t kk = 0; kk < ka && g * ka + kk < A; kk++) {
-                const uint64_t l = (uint64_t)(g * ka + kk) * K + k;
-                const uint64_t n = offs[l + 1] - offs[l];
-                const uint32_t extent = n ? end[offs[l + 1] - 1] : 0;
-                uint32_t ivb, nb, sh, ib;
-                list_geometry(n, extent, ivb, nb, sh, ib);
-                h.iv_off[kk] = o; h.n[kk] = (uint32_t)n; h.nbins[kk] = nb; h.shift[kk] = sh;
-                uint32_t *iv = reinterpret_cast<uint32_t *>(t + o);
-                for (uint64_t i = 0; i < n; i++) { iv[2 * i] = start[offs[l] + i]; iv[2 * i + 1] = end[offs[l] + i]; }
-                iv[2 * n] = 0xffffffffu; iv[2 * n + 1] = 0xffffffffu;
-                o += ivb;
-                h.idx_off[kk] = o;
-                if (nb) {
-                    uint16_t *idx = reinterpret_cast<uint16_t *>(t + o);
+            h.idx_off = t.idx_off; h.nbins = t.nbins; h.shift = t.shift;
+            uint16_t *idx = reinterpret_cast<uint16_t *>(tp + t.idx_off);
+            for (uint32_t kk = 0; kk < (uint32_t)KMAX; kk++) {
+                h.iv_off[kk] = t.iv_off[kk];
+                uint64_t n = 0, base = 0;
+                if (kk < ka && g * ka + kk < A) {
+                    const uint64_t l = (uint64_t)(g * ka + kk) * K + k;
+                    base = offs[l];
+                    n = offs[l + 1] - base;
+                }
+                h.n[kk] = (uint32_t)n;
+                uint32_t *iv = reinterpret_cast<uint32_t *>(tp + t.iv_off[kk]);
+                for (uint64_t i = 0; i < n; i++) { iv[2 * i] = start[base + i]; iv[2 * i + 1] = end[base + i]; }
+                iv[2 * n] = iv[2 * n + 1] = iv[2 * n + 2] = iv[2 * n + 3] = 0x7fffffffu;     // two sentinels
+                if (t.nbins) {
                     uint64_t j = 0;
-                    for (uint32_t b = 0; b < nb; b++) {
-                        const uint64_t pos = (uint64_t)b << sh;
-                        while (j < n && (uint64_t)end[offs[l] + j] <= pos) j++;
-                        idx[b] = (uint16_t)j;
+                    for (uint32_t b = 0; b < t.nbins; b++) {
+                        const uint64_t pos = (uint64_t)b << t.shift;
+                        while (j < n && (uint64_t)end[base + j] <= pos) j++;
+                        idx[(size_t)b * 8 + kk] = (uint16_t)j;
                     }
-                    idx[nb] = (uint16_t)n;
-                    o += ib;
+                    idx[(size_t)t.nbins * 8 + kk] = (uint16_t)n;
                 }
             }
-            memcpy(t, &h, sizeof(h));
+            memcpy(tp, &h, sizeof(h));
         }
 
     gatb_annotations *a = new gatb_annotations();
     a->ctx = ctx; a->n_annot = A; a->n_keys = K; a->n_groups = G; a->ka = ka;
-    a->tile_budget = std::min(budget, std::max(max_tile, hdr));
+    a->tile_budget = std::min(budget, max_tile);
     a->max_tile = max_tile;
     a->n_intervals = offs[n_lists];
     cudaError_t e = a->tiles.upload(blob.data(), blob.size(), ctx->stream);

@@ -13,50 +13,117 @@
 namespace gatb {
 
 // ---------------------------------------------------------------------------------------------------
-// one segment [s,e) (previous segment of the same list ends at pe) against one annotation track
-template <int COUNTER, bool INDEXED>
-__device__ __forceinline__ uint32_t lookup(const uint2 *__restrict__ iv, const uint16_t *__restrict__ idx,
-                                           uint32_t n, uint32_t nbins, uint32_t shift,
-                                           uint32_t s, uint32_t e, uint32_t pe)
+// Exact count of one segment [s,e) against one annotation track, starting the scan at interval j
+// (any j not past the first interval whose end is > s).  pe = end of the previous segment of the list.
+// Coordinates are < 2^31, so signed compares are exact and the two sentinels are (INT_MAX, INT_MAX).
+template <int COUNTER>
+__device__ __forceinline__ uint32_t scan_from(const uint2 *__restrict__ iv, uint32_t j, int s, int e, int pe)
 {
-    uint32_t j;
-    uint2 a;
-    if (INDEXED) {
-        uint32_t b = min(s >> shift, nbins);
-        j = idx[b];
-        a = iv[j];
-        while (a.y <= s) a = iv[++j];           // sentinel end 0xffffffff stops the scan
-    } else {
-        uint32_t lo = 0, hi = n;                // first j with end > s (lower_bound, utils/gat_utils.c:8-32)
-        while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (iv[mid].y <= s) lo = mid + 1; else hi = mid;
-        }
-        j = lo;
-        a = iv[j];
-    }
+    uint2 a = iv[j];
+    while ((int)a.y <= s) a = iv[++j];          // first interval with end > s; the sentinel stops the scan
     uint32_t r = 0;
     if (COUNTER == GATB_SEGMENT_OVERLAP) {
-        // intersectionWithSegments(base), gat/SegmentList.pyx:1078-1146: segment counts once
-        r = (a.x < e) ? 1u : 0u;
+        // intersectionWithSegments(base), gat/SegmentList.pyx:1078-1146: the segment counts once
+        r = ((int)a.x < e) ? 1u : 0u;
     } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
         // midpoint tested against the FIRST overlapping interval only (:1137-1144)
-        uint32_t mid = s + ((e - s) >> 1);
-        r = (a.x < e && a.x <= mid && mid < a.y) ? 1u : 0u;
+        int mid = s + ((e - s) >> 1);
+        r = ((int)a.x < e && (int)a.x <= mid && mid < (int)a.y) ? 1u : 0u;
     } else if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
         // overlapWithSegments, gat/SegmentList.pyx:1026-1076
-        while (a.x < e) { r += min(e, a.y) - max(s, a.x); a = iv[++j]; }
+        while ((int)a.x < e) { r += (uint32_t)(min(e, (int)a.y) - max(s, (int)a.x)); a = iv[++j]; }
     } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
-        // roles swapped: an interval is counted by the first segment overlapping it, i.e. when it
-        // does not already overlap the previous segment (start >= pe)
-        while (a.x < e) { r += (a.x >= pe) ? 1u : 0u; a = iv[++j]; }
+        // roles swapped: an interval is counted by the first segment overlapping it, i.e. when it does
+        // not already overlap the previous segment (start >= pe)
+        while ((int)a.x < e) { r += ((int)a.x >= pe) ? 1u : 0u; a = iv[++j]; }
     } else {  // GATB_ANNOTATION_MIDOVERLAP
-        while (a.x < e) {
-            if (a.x >= pe) { uint32_t m = a.x + ((a.y - a.x) >> 1); r += (s <= m && m < e) ? 1u : 0u; }
+        while ((int)a.x < e) {
+            if ((int)a.x >= pe) { int m = (int)a.x + (((int)a.y - (int)a.x) >> 1); r += (s <= m && m < e) ? 1u : 0u; }
             a = iv[++j];
         }
     }
     return r;
+}
+
+// One sample's segments on one key against the <= KMAX tracks of a tile.  `tile` points into shared
+// memory (staged tiles) or global memory; the code is instantiated once per address space.
+//
+// Indexed fast path per (segment, track): ONE 16-byte load fetches the bin entry of all 8 tracks,
+// two independent 8-byte loads fetch the candidate interval and its successor, and the result is
+// resolved branch-free; only lanes that need a longer scan (more than one interval ends inside the
+// bin before s, or the segment runs past the candidate's end) take the exact loop afterwards.
+template <int COUNTER, bool INDEXED>
+__device__ __forceinline__ void count_sample(const uint8_t *__restrict__ tile, const uint32_t (&iv_off)[KMAX],
+                                             const uint32_t (&nn)[KMAX], uint32_t idx_off, uint32_t nbins,
+                                             uint32_t shift, uint32_t ka,
+                                             const uint64_t *__restrict__ segs, uint32_t n, int lane,
+                                             uint32_t (&acc)[KMAX])
+{
+    const bool need_prev = (COUNTER == GATB_ANNOTATION_OVERLAP || COUNTER == GATB_ANNOTATION_MIDOVERLAP);
+    for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+        const uint32_t i = b0 + lane;
+        if (i >= n) continue;
+        const uint64_t x = segs[i];
+        const int s = (int)seg_start(x), e = (int)seg_end(x);
+        int pe = 0;
+        if (need_prev && i > 0) pe = (int)seg_end(segs[i - 1]);
+        if (INDEXED) {
+            const uint32_t b = min((uint32_t)s >> shift, nbins);
+            const uint4 q = *reinterpret_cast<const uint4 *>(tile + idx_off + (size_t)b * 16);
+            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+            uint32_t slow = 0;
+#pragma unroll
+            for (int kk = 0; kk < KMAX; kk++) {
+                const uint32_t j = (kk & 1) ? (qw[kk >> 1] >> 16) : (qw[kk >> 1] & 0xffffu);
+                const uint2 *iv = reinterpret_cast<const uint2 *>(tile + iv_off[kk]);
+                const uint2 c0 = iv[j], c1 = iv[j + 1];
+                const bool skip = (int)c0.y <= s;
+                const int ax = (int)(skip ? c1.x : c0.x), ay = (int)(skip ? c1.y : c0.y);
+                bool more = skip && ((int)c1.y <= s);
+                uint32_t r;
+                if (COUNTER == GATB_SEGMENT_OVERLAP) {
+                    r = (ax < e) ? 1u : 0u;
+                } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
+                    const int mid = s + ((e - s) >> 1);
+                    r = (ax < e && ax <= mid && mid < ay) ? 1u : 0u;
+                } else if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
+                    r = (uint32_t)max(min(e, ay) - max(s, ax), 0);
+                    more = more || (ay < e);
+                } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
+                    r = (ax < e && ax >= pe) ? 1u : 0u;
+                    more = more || (ay < e);
+                } else {
+                    const int m = ax + ((ay - ax) >> 1);
+                    r = (ax < e && ax >= pe && s <= m && m < e) ? 1u : 0u;
+                    more = more || (ay < e);
+                }
+                acc[kk] += more ? 0u : r;
+                slow |= more ? (1u << kk) : 0u;
+            }
+            if (slow) {
+#pragma unroll
+                for (int kk = 0; kk < KMAX; kk++) {
+                    if (slow & (1u << kk)) {
+                        const uint32_t j = (kk & 1) ? (qw[kk >> 1] >> 16) : (qw[kk >> 1] & 0xffffu);
+                        acc[kk] += scan_from<COUNTER>(reinterpret_cast<const uint2 *>(tile + iv_off[kk]), j, s, e, pe);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < KMAX; kk++) {
+                if ((uint32_t)kk < ka) {
+                    const uint2 *iv = reinterpret_cast<const uint2 *>(tile + iv_off[kk]);
+                    uint32_t lo = 0, hi = nn[kk];         // first j with end > s (utils/gat_utils.c:8-32)
+                    while (lo < hi) {
+                        uint32_t mid = (lo + hi) >> 1;
+                        if ((int)iv[mid].y <= s) lo = mid + 1; else hi = mid;
+                    }
+                    acc[kk] += scan_from<COUNTER>(iv, lo, s, e, pe);
+                }
+            }
+        }
+    }
 }
 
 template <int COUNTER, bool DENSITY>
@@ -75,7 +142,6 @@ __global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
     const uint32_t s_begin = blockIdx.y * p.schunk;
     const uint32_t s_end = min(s_begin + p.schunk, p.n_samples);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const bool need_prev = (COUNTER == GATB_ANNOTATION_OVERLAP || COUNTER == GATB_ANNOTATION_MIDOVERLAP);
 
     for (uint32_t i = threadIdx.x; i < p.schunk * KMAX; i += blockDim.x) {
         if (DENSITY) acc_d[i] = 0.0; else acc_u[i] = 0u;
@@ -92,10 +158,14 @@ __global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
             for (uint32_t i = threadIdx.x; i < (tbytes >> 4); i += blockDim.x) dst[i] = src[i];
             __syncthreads();
         }
-        const uint8_t *tile = staged ? tile_s : tile_g;
-        const TileHeader *h = reinterpret_cast<const TileHeader *>(tile);
-        const double den = DENSITY ? (double)p.key_ws_nseg[k] : 1.0;
         if (DENSITY && p.key_ws_nseg[k] == 0) continue;   // counter returns 0 (gat/Engine.pyx:1438-1440)
+        const double den = DENSITY ? (double)p.key_ws_nseg[k] : 1.0;
+        // tile metadata -> registers, once per key
+        const TileHeader *h = reinterpret_cast<const TileHeader *>(tile_g);
+        uint32_t iv_off[KMAX], nn[KMAX];
+#pragma unroll
+        for (int kk = 0; kk < KMAX; kk++) { iv_off[kk] = h->iv_off[kk]; nn[kk] = h->n[kk]; }
+        const uint32_t idx_off = h->idx_off, nbins = h->nbins, shift = h->shift;
 
         for (uint32_t sl = s_begin + warp; sl < s_end; sl += nwarps) {
             if (p.key_present && !p.key_present[(uint64_t)sl * p.n_keys + k]) continue;
@@ -105,24 +175,12 @@ __global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
             uint32_t acc[KMAX];
 #pragma unroll
             for (int kk = 0; kk < KMAX; kk++) acc[kk] = 0;
-            for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-                const uint32_t i = b0 + lane;
-                if (i < n) {
-                    const uint64_t x = segs[i];
-                    const uint32_t s = seg_start(x), e = seg_end(x);
-                    uint32_t pe = 0;
-                    if (need_prev && i > 0) pe = seg_end(segs[i - 1]);
-#pragma unroll
-                    for (int kk = 0; kk < KMAX; kk++) {
-                        if ((uint32_t)kk < ka) {
-                            const uint2 *iv = reinterpret_cast<const uint2 *>(tile + h->iv_off[kk]);
-                            const uint16_t *idx = reinterpret_cast<const uint16_t *>(tile + h->idx_off[kk]);
-                            const uint32_t nb = h->nbins[kk];
-                            if (nb) acc[kk] += lookup<COUNTER, true>(iv, idx, h->n[kk], nb, h->shift[kk], s, e, pe);
-                            else acc[kk] += lookup<COUNTER, false>(iv, idx, h->n[kk], nb, h->shift[kk], s, e, pe);
-                        }
-                    }
-                }
+            if (staged) {
+                if (nbins) count_sample<COUNTER, true>(tile_s, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, acc);
+                else count_sample<COUNTER, false>(tile_s, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, acc);
+            } else {
+                if (nbins) count_sample<COUNTER, true>(tile_g, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, acc);
+                else count_sample<COUNTER, false>(tile_g, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, acc);
             }
             uint32_t mine = 0;
 #pragma unroll

@@ -13,16 +13,20 @@ constexpr int KMAX = 8;                 // annotation tracks per shared-memory t
 
 // Tile = the intervals of up to KMAX annotation tracks on ONE key (contig), contiguous in global
 // memory so that one cooperative (or bulk) copy stages it in shared memory:
-//   TileHeader | for each track: uint2 iv[n+1] (sentinel 0xffffffff,0xffffffff) | uint16 idx[nbins+1]
-// idx[b] = first j with iv[j].end > (b << shift): a one-probe replacement for the binary search
-// (utils/gat_utils.c:8-32) over sorted interval ends.  nbins == 0: no index (track too large), the
-// kernel binary-searches the intervals in global memory instead.
+//   TileHeader | uint4 idx8[nbins+1] | for each of the KMAX slots: uint2 iv[n+2]
+// iv ends with two sentinels (INT_MAX, INT_MAX); unused slots (tile with fewer than KMAX tracks) hold
+// only the sentinels.  idx8[b] packs, for all 8 slots, the uint16 index of the first interval whose
+// end is > (b << shift): a one-probe replacement for the binary search (utils/gat_utils.c:8-32) over
+// the sorted interval ends, fetched for 8 tracks with a single 16-byte load.  The bin width
+// (1 << shift) is common to the tile.  nbins == 0: no index (a track with > 65534 intervals); the
+// kernel then binary-searches the intervals.
 struct TileHeader {
     uint32_t iv_off[KMAX];      // byte offsets from the tile start
-    uint32_t idx_off[KMAX];
     uint32_t n[KMAX];
-    uint32_t nbins[KMAX];
-    uint32_t shift[KMAX];
+    uint32_t idx_off;
+    uint32_t nbins;
+    uint32_t shift;
+    uint32_t pad;
 };
 
 struct CountParams {
