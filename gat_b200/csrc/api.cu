@@ -277,7 +277,7 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
     CU(ctx, cudaSetDevice(ctx->device));
 
     const uint32_t A = (uint32_t)n_annot, K = (uint32_t)n_keys;
-    const uint32_t bin_factor = std::max(1u, env_u32("GATB_BIN_FACTOR", 2));
+    const uint32_t bin_factor = std::max(1u, env_u32("GATB_BIN_FACTOR", 4));
     // tile budget: what one CTA can opt in to, minus the accumulators
     uint32_t budget = ctx->tile_budget;
     if (budget == 0) {

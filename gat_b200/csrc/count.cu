@@ -80,6 +80,9 @@ __device__ __forceinline__ void count_sample(const uint8_t *__restrict__ tile, c
                 const bool skip = (int)c0.y <= s;
                 const int ax = (int)(skip ? c1.x : c0.x), ay = (int)(skip ? c1.y : c0.y);
                 bool more = skip && ((int)c1.y <= s);
+                // the segment runs past the candidate's end: exact only if the next interval starts at
+                // or after e (known when the candidate is c0, whose successor c1 is already loaded)
+                const bool tail = (ay < e) && (skip || ((int)c1.x < e));
                 uint32_t r;
                 if (COUNTER == GATB_SEGMENT_OVERLAP) {
                     r = (ax < e) ? 1u : 0u;
@@ -88,26 +91,28 @@ __device__ __forceinline__ void count_sample(const uint8_t *__restrict__ tile, c
                     r = (ax < e && ax <= mid && mid < ay) ? 1u : 0u;
                 } else if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
                     r = (uint32_t)max(min(e, ay) - max(s, ax), 0);
-                    more = more || (ay < e);
+                    more = more || tail;
                 } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
                     r = (ax < e && ax >= pe) ? 1u : 0u;
-                    more = more || (ay < e);
+                    more = more || tail;
                 } else {
                     const int m = ax + ((ay - ax) >> 1);
                     r = (ax < e && ax >= pe && s <= m && m < e) ? 1u : 0u;
-                    more = more || (ay < e);
+                    more = more || tail;
                 }
                 acc[kk] += more ? 0u : r;
                 slow |= more ? (1u << kk) : 0u;
             }
-            if (slow) {
+            // rare: exact scan for the flagged (lane, slot) pairs, one slot per loop turn
+            while (slow) {
+                const int kk = __ffs(slow) - 1;
+                slow &= slow - 1;
+                const uint32_t w = (kk & 4) ? ((kk & 2) ? q.w : q.z) : ((kk & 2) ? q.y : q.x);
+                const uint32_t j = (kk & 1) ? (w >> 16) : (w & 0xffffu);
+                const uint32_t off = reinterpret_cast<const TileHeader *>(tile)->iv_off[kk];
+                const uint32_t r = scan_from<COUNTER>(reinterpret_cast<const uint2 *>(tile + off), j, s, e, pe);
 #pragma unroll
-                for (int kk = 0; kk < KMAX; kk++) {
-                    if (slow & (1u << kk)) {
-                        const uint32_t j = (kk & 1) ? (qw[kk >> 1] >> 16) : (qw[kk >> 1] & 0xffffu);
-                        acc[kk] += scan_from<COUNTER>(reinterpret_cast<const uint2 *>(tile + iv_off[kk]), j, s, e, pe);
-                    }
-                }
+                for (int t = 0; t < KMAX; t++) acc[t] += (t == kk) ? r : 0u;
             }
         } else {
 #pragma unroll
