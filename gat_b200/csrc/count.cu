@@ -135,8 +135,8 @@ template <int COUNTER, bool DENSITY>
 __global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    // layout: [acc: schunk*KMAX*(DENSITY?8:4) bytes][tile]
-    const uint32_t acc_bytes = p.schunk * KMAX * (DENSITY ? 8u : 4u);
+    // layout: [acc: schunk*KMAX*(DENSITY?16:4) bytes][tile]; density keeps (sum, compensation) per slot
+    const uint32_t acc_bytes = p.schunk * KMAX * (DENSITY ? 16u : 4u);
     uint32_t *acc_u = reinterpret_cast<uint32_t *>(smem);
     double *acc_d = reinterpret_cast<double *>(smem);
     uint8_t *tile_s = smem + ((acc_bytes + 15u) & ~15u);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
     for (uint32_t i = threadIdx.x; i < p.schunk * KMAX; i += blockDim.x) {
-        if (DENSITY) acc_d[i] = 0.0; else acc_u[i] = 0u;
+        if (DENSITY) { acc_d[2 * i] = 0.0; acc_d[2 * i + 1] = 0.0; } else acc_u[i] = 0u;
     }
 
     for (uint32_t k = 0; k < p.n_keys; k++) {
@@ -195,8 +195,13 @@ __global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
             }
             if ((uint32_t)lane < ka) {
                 const uint32_t slot = (sl - s_begin) * KMAX + lane;
-                if (DENSITY) acc_d[slot] += (double)mine / den;   // float(overlap) / len(workspace)
-                else acc_u[slot] += mine;
+                if (DENSITY) {
+                    // float(overlap) / len(workspace), accumulated like the reference's Python sum():
+                    // CPython >= 3.12 sums floats with Neumaier compensation (Python/bltinmodule.c)
+                    const double x = (double)mine / den, f = acc_d[2 * slot], t = f + x;
+                    acc_d[2 * slot + 1] += (fabs(f) >= fabs(x)) ? ((f - t) + x) : ((x - t) + f);
+                    acc_d[2 * slot] = t;
+                } else acc_u[slot] += mine;
             }
         }
     }
@@ -204,7 +209,10 @@ __global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
     for (uint32_t i = threadIdx.x; i < (s_end - s_begin) * KMAX; i += blockDim.x) {
         const uint32_t sl = s_begin + i / KMAX, kk = i % KMAX;
         if (kk < ka) {
-            if (DENSITY) p.out_f64[(uint64_t)sl * p.n_annot + a0 + kk] = acc_d[i];
+            if (DENSITY) {
+                const double f = acc_d[2 * i], c = acc_d[2 * i + 1];
+                p.out_f64[(uint64_t)sl * p.n_annot + a0 + kk] = (c != 0.0 && isfinite(c)) ? f + c : f;
+            }
             else p.out_u32[(uint64_t)sl * p.n_annot + a0 + kk] = acc_u[i];
         }
     }
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
 template <int COUNTER, bool DENSITY>
 static cudaError_t launch_count_t(cudaStream_t st, const CountParams &p, int threads)
 {
-    const uint32_t acc_bytes = (p.schunk * KMAX * (DENSITY ? 8u : 4u) + 15u) & ~15u;
+    const uint32_t acc_bytes = (p.schunk * KMAX * (DENSITY ? 16u : 4u) + 15u) & ~15u;
     const size_t smem = (size_t)acc_bytes + p.smem_tile_budget;
     cudaError_t e = cudaFuncSetAttribute(count_kernel<COUNTER, DENSITY>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -274,7 +282,7 @@ __global__ void __launch_bounds__(256) stats_pass1_kernel(StatsParams p)
         double x;
         if (p.is_float) { x = reinterpret_cast<const double *>(p.counts)[s * p.n_cols + col]; fsum += x; }
         else { uint32_t v = reinterpret_cast<const uint32_t *>(p.counts)[s * p.n_cols + col]; isum += v; x = (double)v; }
-        ntl += ((int)(x - obs) < 0) ? 1ull : 0ull;      // cmpDouble truncates (gat/SegmentList.pyx:135-136)
+        ntl += (x < obs) ? 1ull : 0ull;                 // searchargsorted + cmpDouble (gat/Engine.pyx:122-127)
         nlt += (x < obs) ? 1ull : 0ull;
         neq += (x == obs) ? 1ull : 0ull;
     }

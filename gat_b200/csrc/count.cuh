@@ -63,7 +63,7 @@ struct StatsParams {
     // outputs, device [n_cols]
     double *sum;                    // exact integer sum (as double) or float sum
     double *sumsq_dev;              // sum (x-mean)^2
-    unsigned long long *n_trunc_lt; // #{ (int)(x - obs) < 0 }   (cmpDouble truncation quirk)
+    unsigned long long *n_trunc_lt; // insertion point of obs = #{ x < obs } (lower_bound, gat/Engine.pyx:1549-1557)
     unsigned long long *n_lt;       // #{ x < obs }
     unsigned long long *n_eq;       // #{ x == obs }
     double *q_lo, *q_hi;            // order statistics at ranks rank_lo / rank_hi

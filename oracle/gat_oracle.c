@@ -41,15 +41,15 @@ long go_searchsorted_seg(const go_seg *base, size_t n, go_seg target)
     return (long)imin;
 }
 
-/* utils/gat_utils.c:37-61 with cmpDouble (gat/SegmentList.pyx:135-136): the comparator TRUNCATES the
- * difference to int, so values closer than 1.0 compare equal (matters for nucleotide-density). */
+/* utils/gat_utils.c:37-61 with Engine.pyx's own cmpDouble (gat/Engine.pyx:122-127, a proper three-way
+ * compare -- NOT the truncating cmpDouble of gat/SegmentList.pyx:135-136, which this path never uses) */
 long go_searchargsorted_f64(const double *base, const int *sorted, size_t n, double target)
 {
     size_t imin = 0, imax = n;
     while (imin < imax) {
         size_t imid = imin + ((imax - imin) >> 1);
         double v = sorted ? base[sorted[imid]] : base[imid];
-        if ((int)(v - target) < 0) imin = imid + 1; else imax = imid;
+        if (((v > target) - (v < target)) < 0) imin = imid + 1; else imax = imid;
     }
     return (long)imin;
 }
@@ -517,15 +517,23 @@ void go_count_placed(int C, int A, const uint64_t *placed_off, const go_seg *pla
 {
     for (int k = 0; k < ncounters; k++)
         for (int a = 0; a < A; a++) {
-            double total = 0.0;
+            /* Python sum(): ints add plainly, floats with Neumaier compensation (CPython >= 3.12,
+             * Python/bltinmodule.c builtin_sum; the reference in oracle/_ref runs on such a Python) */
+            double total = 0.0, comp = 0.0;
             for (int c = 0; c < C; c++) {
                 /* contigs absent from the sample contribute nothing; present-but-empty contigs add 0 */
                 const go_seg *s = placed + placed_off[c];
                 size_t n = (size_t)(placed_off[c + 1] - placed_off[c]);
                 const go_seg *an = anno + anno_off[(size_t)a * C + c];
                 size_t m = (size_t)(anno_off[(size_t)a * C + c + 1] - anno_off[(size_t)a * C + c]);
-                total += go_counter(counters[k], s, n, an, m, cws_nseg ? cws_nseg[c] : 0);
+                double x = go_counter(counters[k], s, n, an, m, cws_nseg ? cws_nseg[c] : 0);
+                if (counters[k] == GO_NUCLEOTIDE_DENSITY && cws_nseg && cws_nseg[c] != 0) {
+                    double t = total + x;
+                    if (fabs(total) >= fabs(x)) comp += (total - t) + x; else comp += (x - t) + total;
+                    total = t;
+                } else total += x;
             }
+            if (comp != 0.0 && isfinite(comp)) total += comp;
             counts[(size_t)k * A + a] = total;
         }
 }

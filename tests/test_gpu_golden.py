@@ -1,0 +1,255 @@
+"""GPU tests against the reference's golden vectors (tests/golden/, produced by the compiled reference):
+observed counts bit-exact, same-placement per-sample counts bit-exact, sampled distributions
+statistically equivalent (KS, 3 SE, binomial CI), and the gat.run()-style API end to end."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+COUNTERS = ["nucleotide-overlap", "nucleotide-density", "segment-overlap", "segment-midoverlap",
+            "annotation-overlap", "annotation-midoverlap"]
+
+
+def counters_of(names):
+    from gat_b200 import engine as Engine
+    return [Engine.COUNTER_CLASSES[n]() for n in names]
+
+
+def load_prepared(name):
+    z, meta = G.load_npz(name)
+    segments = G.collection(z, "segments", meta["segments"], coded=True)
+    annotations = G.collection(z, "annotations", meta["annotations"], coded=True)
+    workspace = G.dictionary(z, "workspace", meta["workspace"], coded=True)
+    return segments, annotations, workspace, meta
+
+
+def test_observed_counts_reference_golden_run(ctx):
+    """the 28 observed values of the reference's golden run (test/data/output_single.tsv; the check of
+    test/check_run.py:108-112) through Engine.computeCounts on the GPU"""
+    from gat_b200 import engine as Engine
+    segments, annotations, workspace, meta = load_prepared("observed_testdata")
+    counts = Engine.computeCounts(Engine.CounterNucleotideOverlap(), sum, segments, annotations, workspace,
+                                  Engine.UnconditionalWorkspace())
+    got = dict(("%s|%s" % (t, a), v) for t, r in counts.items() for a, v in r.items())
+    assert len(got) == 28 and got == meta["golden"]
+    assert all(isinstance(v, int) for v in got.values())
+
+
+def test_observed_count_tutorial(ctx):
+    """BASELINE config 1: SRF x Jurkat DHS, observed 20183 (doc/tutorialIntervalOverlap.rst:103)"""
+    from gat_b200 import engine as Engine
+    segments, annotations, workspace, meta = load_prepared("observed_tutorial")
+    counts = Engine.computeCounts(Engine.CounterNucleotideOverlap(), sum, segments, annotations, workspace,
+                                  Engine.UnconditionalWorkspace())
+    (track, r), = counts.items()
+    assert list(r.values()) == [20183]
+
+
+def test_tutorial_run_matches_published_statistics(ctx):
+    """config 1 end to end, 1000 samples: observed exact; expected / stddev / fold agree with the published
+    table (246.565, 105.59, 81.53) within Monte-Carlo error; p = 1/1000"""
+    import gat_b200
+    from gat_b200 import engine as Engine
+    segments, annotations, workspace, meta = load_prepared("observed_tutorial")
+    Engine.seed(1)
+    res = gat_b200.run(segments, annotations, workspace, Engine.SamplerAnnotator(bucket_size=1, nbuckets=100000),
+                       [Engine.CounterNucleotideOverlap()], Engine.UnconditionalWorkspace(), num_samples=1000)
+    assert len(res) == 1
+    r, pub = res[0], meta["published"]
+    assert r.observed == 20183 and r.nsamples == 1000
+    se = pub["stddev"] / np.sqrt(1000) * np.sqrt(2)          # two independent 1000-sample estimates
+    assert abs(r.expected - pub["expected"]) < 4 * se
+    assert abs(r.stddev - pub["stddev"]) / pub["stddev"] < 0.15
+    assert abs(r.fold - pub["fold"]) / pub["fold"] < 0.08
+    assert r.pvalue == 1e-3
+    row = str(r).split("\t")
+    assert row[2] == "20183" and row[9] == "1.0000e-03" and len(row) == len(Engine.AnnotatorResultExtended.headers)
+
+
+def _track_problem(z, tag, m):
+    import gat_b200
+    segments = G.collection(z, tag + "/segments", m["segments"])
+    annotations = G.collection(z, tag + "/annotations", m["annotations"])
+    workspace = G.dictionary(z, tag + "/workspace", m["workspace"])
+    problem = gat_b200.TrackProblem(segments["merged"], workspace)
+    atracks, lists, nseg = gat_b200.buildContigAnnotations(annotations, workspace, problem.contigs)
+    return segments, annotations, workspace, problem, atracks, lists, nseg
+
+
+@pytest.mark.parametrize("tag", ["plain", "iso"])
+def test_same_placement_counts_match_reference(ctx, tag):
+    """feed the reference's OWN placed samples (its --output-samples-pattern dump) to the counting kernel:
+    per-sample counts of all six counters must equal the reference's, bit for bit"""
+    from gat_b200 import device
+    from gat_b200.segmentlist import SegmentList
+    z, meta = G.load_npz("run_small")
+    m = meta[tag]
+    _, _, _, problem, atracks, lists, nseg = _track_problem(z, tag, m)
+    samples = []
+    for placed in m["placed"]:
+        per = dict((c, []) for c in problem.contigs)
+        for key, segs in placed.items():
+            per[key.split(".")[0]].extend(segs)
+        row = []
+        for c in problem.contigs:
+            s = SegmentList(array=np.array(per[c], dtype=np.uint32).reshape(-1, 2))
+            if tag == "iso":
+                s.merge(0)                     # sample.fromIsochores() (gat/__init__.py:563)
+            row.append(s.asarray())
+        samples.append(row)
+    annos = device.Annotations(ctx, lists, key_ws_nseg=nseg)
+    got = annos.count_lists(COUNTERS, samples)
+    annos.close()
+    for ci, counter in enumerate(COUNTERS):
+        for ai, anno in enumerate(atracks):
+            want = np.array(m["results"][counter][anno]["samples"])
+            assert np.array_equal(got[ci, :, ai], want), (counter, anno)
+
+
+@pytest.mark.parametrize("tag", ["plain", "iso"])
+def test_observed_counts_all_counters_match_reference(ctx, tag):
+    """observed counts of all six counters incl. the isochore convention (per-isochore keys, segments
+    filtered not truncated -- quirk C-7) equal the reference's"""
+    from gat_b200 import engine as Engine
+    z, meta = G.load_npz("run_small")
+    m = meta[tag]
+    segments, annotations, workspace, _, atracks, _, _ = _track_problem(z, tag, m)
+    for counter in counters_of(COUNTERS):
+        counts = Engine.computeCounts(counter, sum, segments, annotations, workspace, Engine.UnconditionalWorkspace())
+        for anno in atracks:
+            assert counts["merged"][anno] == m["results"][counter.name][anno]["observed"], (counter.name, anno)
+
+
+def ks_statistic(a, b):
+    a, b = np.sort(a), np.sort(b)
+    allv = np.concatenate([a, b])
+    ca = np.searchsorted(a, allv, side="right") / len(a)
+    cb = np.searchsorted(b, allv, side="right") / len(b)
+    return np.abs(ca - cb).max()
+
+
+@pytest.mark.parametrize("tag", ["plain", "iso"])
+def test_sampled_distributions_equivalent_to_reference(ctx, tag):
+    """stochastic outputs differ only through the RNG: per annotation, two-sample KS against 2000
+    reference samples, expected within 3 SE, empirical p-values within the binomial CI"""
+    import gat_b200
+    from gat_b200 import engine as Engine
+    z, meta = G.load_npz("distribution")
+    m = meta[tag]
+    segments, annotations, workspace, _, _, _, _ = _track_problem(z, tag, m)
+    counters = m["counters"]
+    n = 4000
+    Engine.seed(2026)
+    res = gat_b200.run(segments, annotations, workspace, Engine.SamplerAnnotator(), counters_of(counters),
+                       Engine.UnconditionalWorkspace(), num_samples=n)
+    assert len(res) == len(counters) * len(m["annotation_order"])
+    nref = m["num_samples"]
+    crit = 1.95 * np.sqrt((n + nref) / (n * nref))             # alpha ~ 0.001 per test
+    for r in res:
+        ai = m["annotation_order"].index(r.annotation)
+        ref = z["%s/samples/%s" % (tag, r.counter)][:, ai].astype(np.float64)
+        assert r.observed == z["%s/observed/%s" % (tag, r.counter)][ai]
+        mine = r.samples
+        assert ks_statistic(mine, ref) < crit, (r.counter, r.annotation, ks_statistic(mine, ref), crit)
+        se = np.sqrt(ref.var() / nref + mine.var() / n)
+        assert abs(mine.mean() - ref.mean()) <= 3 * se + 1e-9, (r.counter, r.annotation)
+        # fold within 3 SE (delta method on the expected value)
+        fold_ref = (r.observed + 1.0) / (ref.mean() + 1.0)
+        assert abs(r.fold - fold_ref) <= 3 * se * (r.observed + 1.0) / (ref.mean() + 1.0) ** 2 + 1e-9
+        # p-values: both estimate the same tail probability
+        pref = float(z["%s/pvalue/%s" % (tag, r.counter)][ai])
+        p = 0.5 * (pref + r.pvalue)
+        sd = np.sqrt(p * (1 - p) * (1.0 / n + 1.0 / nref))
+        assert abs(r.pvalue - pref) <= 3.5 * sd + 1.0 / nref, (r.counter, r.annotation, r.pvalue, pref)
+
+
+def test_run_api_results_and_output(ctx, tmp_path):
+    """gat.run()-style call: result objects, counts dump, q-values and the output table"""
+    import gat_b200
+    from gat_b200 import engine as Engine, io as IO, synthetic
+    segments, annotations, workspaces, iso = synthetic.make(
+        n_segments=300, n_annotations=5, n_annotation_intervals=400, isochores=True,
+        genome=[("chrA", 2000000), ("chrB", 1000000)], isochore_tile=50000, n_isochores=3)
+    workspace = synthetic.prepare(segments, annotations, workspaces, iso)
+    counters = counters_of(["nucleotide-overlap", "nucleotide-density", "segment-overlap"])
+    Engine.seed(5)
+    pattern = str(tmp_path / "counts_%s.tsv")
+    res = gat_b200.run(segments, annotations, workspace, Engine.SamplerAnnotator(), counters,
+                       Engine.UnconditionalWorkspace(), num_samples=200, output_counts_pattern=pattern)
+    assert len(res) == 15
+    Engine.seed(5)
+    res2 = gat_b200.run(segments, annotations, workspace, Engine.SamplerAnnotator(), counters,
+                        Engine.UnconditionalWorkspace(), num_samples=200)
+    for a, b in zip(res, res2):                                   # same seed -> same samples
+        assert np.array_equal(a.samples, b.samples) and a.pvalue == b.pvalue
+    for r in res:
+        assert r.nsamples == 200 and len(r.samples) == 200
+        assert r.expected == pytest.approx(r.samples.mean(), rel=1e-12)
+        assert 0 < r.pvalue <= 1 and r.qvalue == 1.0
+        if r.counter == "nucleotide-density":
+            nuc = [x for x in res if x.counter == "nucleotide-overlap" and x.annotation == r.annotation][0]
+            assert r.observed > 0 and r.observed <= nuc.observed
+    # counts table round trip (gat/__init__.py:1072-1119)
+    back = gat_b200.fromCounts(pattern % "segment-overlap")
+    so = [r for r in res if r.counter == "segment-overlap"]
+    assert len(back) == len(so)
+    for a, b in zip(back, so):
+        assert np.array_equal(a.samples, b.samples) and a.pvalue == b.pvalue and a.expected == b.expected
+
+    class Opt(object):
+        qvalue_method = "BH"
+        qvalue_lambda = None
+        qvalue_pi0_method = "smoother"
+        output_order = "fold"
+        output_tables_pattern = str(tmp_path / "table_%s.tsv")
+        stdout = io.StringIO()
+    IO.outputResults(res, Opt, Engine.AnnotatorResultExtended.headers, [], 0, {})
+    lines = open(str(tmp_path / "table_nucleotide-overlap.tsv")).read().strip().split("\n")
+    assert lines[0].split("\t") == Engine.AnnotatorResultExtended.headers and len(lines) == 6
+    folds = [float(l.split("\t")[7]) for l in lines[1:]]
+    assert folds == sorted(folds)
+    assert all(0 < r.qvalue <= 1 for r in res)
+    q = Engine.getQValues([r.pvalue for r in res], method="BH")
+    assert np.allclose([r.qvalue for r in res], q)
+
+
+def test_unaccelerated_options_raise(ctx):
+    import gat_b200
+    from gat_b200 import engine as Engine
+
+    class Other(object):
+        pass
+
+    class Cond(Engine.UnconditionalWorkspace):
+        is_conditional = True
+    with pytest.raises(NotImplementedError):
+        gat_b200.run(None, None, None, Other(), [], Engine.UnconditionalWorkspace())
+    with pytest.raises(NotImplementedError):
+        gat_b200.run(None, None, None, Engine.SamplerAnnotator(), [], Cond())
+
+
+def test_operator_protocols_single_calls(ctx, oracle):
+    """the reference's per-call protocols: sampler.sample(segments, workspace) and counter(segments,
+    annotations, workspace) work on single lists (gat/Engine.pyx:515-517, 1417-1472)"""
+    from gat_b200 import engine as Engine
+    from gat_b200.segmentlist import SegmentList
+    segs = SegmentList(iter=[(100, 200), (1000, 1300), (5000, 5050)], normalize=True)
+    ws = SegmentList(iter=[(0, 3000), (4000, 10000)], normalize=True)
+    Engine.seed(3)
+    out = Engine.SamplerAnnotator().sample(segs, ws)
+    assert out.isNormalized and len(out) >= 1
+    t = out.clone()
+    t.intersect(ws)
+    assert t.sum() == 450                                   # exactly the input's workspace coverage
+    annos = SegmentList(iter=[(150, 1100), (5040, 6000)], normalize=True)
+    for name, cls in Engine.COUNTER_CLASSES.items():
+        got = cls()(segs, annos, ws)
+        assert got == oracle.counter(name, segs.asarray(), annos.asarray(), len(ws)), name
+    assert Engine.SamplerAnnotator().sample(SegmentList(), ws).isEmpty
+    with pytest.raises(ValueError):                          # segment too large for the histogram
+        Engine.SamplerAnnotator(bucket_size=1, nbuckets=100).sample(segs, ws)

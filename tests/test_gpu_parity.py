@@ -122,7 +122,7 @@ def test_column_stats_match_oracle(ctx, oracle):
 
 
 def test_column_stats_float_and_reference(ctx, oracle):
-    """float64 (nucleotide-density) columns incl. the truncating comparator, and the --null fold shift"""
+    """float64 (nucleotide-density) columns and the --null fold shift"""
     rng = np.random.default_rng(43)
     l, A = 500, 6
     counts = np.round(rng.random((l, A)) * 4, 2)

@@ -1,0 +1,188 @@
+"""CPU tests of the host-side mirror: SegmentList / containers (input preparation), multiple-testing
+correction, flag parser.  Pinned against golden vectors of the reference (tests/golden/)."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from tests import golden_util as G
+from gat_b200.segmentlist import SegmentList
+from gat_b200 import engine as Engine
+from gat_b200 import stats as Stats
+
+
+def SL(x, normalize=True):
+    return SegmentList(iter=[tuple(t) for t in x], normalize=normalize)
+
+
+def test_segmentlist_matches_reference():
+    for c in G.load_json("segmentlist"):
+        na, nb = SL(c["a"]), SL(c["b"])
+        assert na.asList() == [tuple(x) for x in c["normalize_a"]]
+        for d in (0, 1, 5):
+            m = SL(c["a"], normalize=False)
+            m.merge(d)
+            assert m.asList() == [tuple(x) for x in c["merge_%i" % d]]
+        f = na.clone()
+        f.filter(nb)
+        assert f.asList() == [tuple(x) for x in c["filter"]]
+        i = na.clone()
+        i.intersect(nb)
+        assert i.asList() == [tuple(x) for x in c["intersect"]]
+        assert na.sum() == c["sum_a"]
+        assert na.overlapWithSegments(nb) == c["overlap"]
+        assert na.intersectionWithSegments(nb) == c["isect_base"]
+        assert na.intersectionWithSegments(nb, mode="midpoint") == c["isect_mid"]
+        for bucket in (0, 1, 4):
+            key = "lengthdist_%i" % bucket
+            if key not in c:
+                continue
+            if "error" in c[key]:
+                with pytest.raises(ValueError):
+                    na.getLengthDistribution(bucket, 1000)
+                continue
+            h, bs = na.getLengthDistribution(bucket, 1000)
+            assert bs == c[key]["bucket_size"]
+            assert [[int(k), int(h[k])] for k in np.flatnonzero(h)] == c[key]["nonzero"]
+
+
+def test_segmentlist_reference_unit_tests():
+    """test/test_SegmentList.py: normalize variants (:27-142), negatives raise OverflowError (:332-366)"""
+    assert SL([(0, 10), (10, 20)]).asList() == [(0, 10), (10, 20)]
+    assert SL([(0, 10), (9, 20)]).asList() == [(0, 20)]
+    s = SegmentList()
+    assert s.isNormalized and s.isEmpty and len(s) == 0
+    s.add(5, 10)
+    assert not s.isNormalized
+    s.normalize()
+    assert s.isNormalized and s.sum() == 5
+    with pytest.raises(OverflowError):
+        SegmentList(iter=[(-1, 5)])
+    with pytest.raises(ValueError):
+        SL([(0, 10), (5, 15)], normalize=False).check()
+    e = SL([(0, 10)])
+    e.extend(SL([(20, 30)]))
+    assert not e.isNormalized and len(e) == 2
+
+
+def test_isochore_round_trip():
+    """toIsochores / fromIsochores (test/test_gat.py:55-114; gat/Engine.pyx:2837-2876)"""
+    d = Engine.IntervalDictionary()
+    d.add("chr1", SL([(0, 100), (200, 300), (290, 310)]))
+    iso = Engine.IntervalCollection("isochores")
+    iso.add("lo", "chr1", SL([(0, 150)]))
+    iso.add("hi", "chr1", SL([(150, 400)]))
+    t = d.clone()
+    t.toIsochores(iso, truncate=True)
+    assert sorted(t.keys()) == ["chr1.hi", "chr1.lo"]
+    assert t["chr1.lo"].asList() == [(0, 100)] and t["chr1.hi"].asList() == [(200, 310)]
+    t.fromIsochores()
+    assert list(t.keys()) == ["chr1"] and t["chr1"].asList() == [(0, 100), (200, 310)]
+    # without truncation a segment spanning two isochores is present in both (quirk C-7) ...
+    d2 = Engine.IntervalDictionary()
+    d2.add("chr1", SL([(100, 200)]))
+    d2.toIsochores(iso, truncate=False)
+    assert d2["chr1.lo"].asList() == [(100, 200)] and d2["chr1.hi"].asList() == [(100, 200)]
+    # ... and merge(0) joins adjacent pieces on the way back
+    d3 = Engine.IntervalDictionary()
+    d3.add("chr1", SL([(100, 200)]))
+    d3.toIsochores(iso, truncate=True)
+    d3.fromIsochores()
+    assert d3["chr1"].asList() == [(100, 200)]
+
+
+def test_collection_collapse_merge_restrict():
+    c = Engine.IntervalCollection("ws")
+    c.add("a", "chr1", SL([(0, 100)]))
+    c.add("a", "chr2", SL([(0, 50)]))
+    c.add("b", "chr1", SL([(50, 150)]))
+    c.collapse()
+    assert c["collapsed"]["chr1"].asList() == [(50, 100)] and "chr2" not in c["collapsed"]
+    c.restrict("collapsed")
+    assert list(c.tracks) == ["collapsed"]
+    m = Engine.IntervalCollection("s")
+    m.add("x", "chr1", SL([(0, 10)]))
+    m.add("y", "chr1", SL([(5, 20)]))
+    m.merge()
+    assert len(m["merged"]["chr1"]) == 2 and m.countsPerTrack()["merged"] == 2
+
+
+def test_adjust_pvalues_match_reference():
+    for c in G.load_json("qvalues"):
+        for method, want in c["adjusted"].items():
+            assert np.array_equal(Stats.adjustPValues(c["pvalues"], method=method), np.array(want)), method
+
+
+def test_storey_qvalues_match_reference():
+    n = 0
+    for c in G.load_json("qvalues"):
+        if "storey_lambda05" in c:
+            r = Stats.computeQValues(c["pvalues"], vlambda=0.5)
+            assert r.pi0 == pytest.approx(c["storey_lambda05"]["pi0"], rel=1e-14)
+            assert np.allclose(r.qvalues, c["storey_lambda05"]["qvalues"], rtol=1e-13, atol=0)
+            n += 1
+        if "storey_smoother" in c and "qvalues" in c["storey_smoother"]:
+            r = Stats.computeQValues(c["pvalues"], vlambda=np.arange(0, 0.95, 0.05), pi0_method="smoother")
+            assert r.pi0 == pytest.approx(c["storey_smoother"]["pi0"], rel=1e-12)
+            assert np.allclose(r.qvalues, c["storey_smoother"]["qvalues"], rtol=1e-12, atol=0)
+            n += 1
+    assert n >= 4
+    with pytest.raises(ValueError):
+        Stats.computeQValues([0.5, 1.5])
+    assert Engine.getQValues([0.01, 0.5, 0.9], method="BH")[0] == pytest.approx(0.03)
+
+
+def test_parser_flags_and_defaults():
+    """the flags north_star names and the reference's defaults (gat/__init__.py:385-427)"""
+    import gat_b200
+    p = gat_b200.buildParser()
+    o, _ = p.parse_args(["--segments=s.bed", "--annotations=a.bed", "--workspace=w.bed", "--isochore-file=i.bed",
+                         "--counter=segment-overlap", "--num-samples=77", "--sampler=annotator"])
+    assert o.segment_files == ["s.bed"] and o.annotation_files == ["a.bed"] and o.workspace_files == ["w.bed"]
+    assert o.isochore_files == ["i.bed"] and o.counters == ["segment-overlap"] and o.num_samples == 77
+    d, _ = gat_b200.buildParser().parse_args([])      # fresh parser: optparse shares list defaults
+    assert (d.num_samples, d.bucket_size, d.nbuckets, d.pseudo_count) == (1000, 0, 100000, 1.0)
+    assert d.ignore_segment_tracks is True and d.qvalue_method == "BH" and d.sampler == "annotator"
+    assert d.output_order == "fold" and d.pvalue_method == "empirical" and d.counters == []
+
+
+def test_bed_reader_tracks(tmp_path):
+    from gat_b200 import io as IO
+    f = tmp_path / "x.bed"
+    f.write_text("track name=t1\nchr1\t10\t20\nchr1\t15\t30\ntrack name=\"t2\"\nchr2\t0\t5\n")
+    r = IO.readFromBed([str(f)])
+    assert sorted(r.keys()) == ["t1", "t2"] and r["t1"]["chr1"].asList() == [(10, 20), (15, 30)]
+    g = tmp_path / "y.bed"
+    g.write_text("chr1\t1\t2\tnameA\nchr1\t3\t4\n")
+    r = IO.readFromBed([str(g)])
+    assert sorted(r.keys()) == ["nameA", "y.bed"]
+    with pytest.raises(ValueError):          # like the reference: one track may not span files ...
+        IO.readFromBed([str(f), str(g)], ignore_tracks=True)
+    r = IO.readFromBed([str(f), str(g)], ignore_tracks=True, allow_multiple=True)   # ... unless allowed
+    assert list(r.keys()) == ["merged"] and r["merged"]["chr1"].counts() == 4
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/test/data"), reason="reference data only in the build container")
+def test_input_preparation_matches_reference_io():
+    """our buildSegments + applyIsochores on the reference's test data == the arrays the reference's own
+    IO produced (stored in tests/golden/observed_testdata.npz)"""
+    import gat_b200
+    from gat_b200 import io as IO
+    d = "/root/reference/test/data"
+    options, _ = gat_b200.buildParser().parse_args([
+        "--segments=%s/segments_single.bed.gz" % d, "--annotations=%s/annotations.bed.gz" % d,
+        "--workspace=%s/workspace.bed.gz" % d, "--with-segment-tracks"])
+    segments, annotations, workspaces, isochores = IO.buildSegments(options)
+    workspace = IO.applyIsochores(segments, annotations, workspaces, options, isochores)
+    z, meta = G.load_npz("observed_testdata")
+    assert sorted(workspace.keys()) == sorted(meta["workspace"])
+    for key in meta["workspace"]:
+        assert np.array_equal(workspace[key].asarray(), G.undelta(z["workspace/%s" % key]))
+    for name, coll in (("segments", segments), ("annotations", annotations)):
+        # (the fixture was dumped after computeCounts, whose defaultdict look-ups leave empty lists behind
+        # for every workspace key: compare the non-empty lists)
+        ref_keys = sorted([t, k] for t, k in meta[name] if len(z["%s/%s/%s" % (name, t, k)]))
+        assert sorted([t, k] for t, vv in coll.items() for k in vv.keys() if len(vv[k])) == ref_keys
+        for track, key in ref_keys:
+            assert np.array_equal(coll[track][key].asarray(), G.undelta(z["%s/%s/%s" % (name, track, key)])), (track, key)
