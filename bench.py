@@ -241,7 +241,10 @@ def run_ours(args):
     is_density = cid == device.DENSITY
 
     ctx = device.Context(local)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) stream: kernels, NCCL and the timing events all live on it; the legacy
+    # default stream would add implicit synchronisation with every other stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_batch_size(B)
     annos = device.Annotations(ctx, None, key_ws_nseg=wl["nseg"], csr=(A, C) + wl["anno_csr"])
@@ -308,7 +311,8 @@ def run_ours(args):
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "kernel": "count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                "traffic": (traffic["dram_bytes_per_sample"] * B) if traffic and "dram_bytes_per_sample" in traffic else None,
+                "traffic_source": traffic.get("capture") if traffic else None,
                 "algorithmic_bytes_per_launch": count_bytes, "kernel_ms": count_ms,
                 "kernel_share_of_step": prof["count"][0] / max(sum(v[0] for v in prof.values()), 1e-9),
                 "other_kernels": {"place_kernel_ms": place_ms, "contig_merge_kernel_ms": merge_ms,
@@ -344,6 +348,7 @@ def run_ours(args):
             a2.close()
             return int(host_np[0, 0])
 
+        ctx.set_stream(None)                        # host in / host out: the context's own stream
         e2e_step(10 ** 5)                           # warm-up (allocator, pinned paths)
         barrier()
         t0 = time.perf_counter()

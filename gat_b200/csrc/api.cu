@@ -272,8 +272,12 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
     *out = nullptr;
     if (n_annot <= 0 || n_keys <= 0) return fail(ctx, GATB_ERR_INVALID, "annotations: need >=1 track and >=1 key");
     const uint64_t n_lists = (uint64_t)n_annot * n_keys;
-    int rc = check_lists(ctx, "annotations", n_lists, offs, start, end);
-    if (rc) return rc;
+    // offsets are checked here; the intervals themselves (range, order, normalisation) on the GPU
+    if (!offs || !start || !end) return fail(ctx, GATB_ERR_INVALID, "annotations: NULL array");
+    if (offs[0] != 0) return fail(ctx, GATB_ERR_INVALID, "annotations: offsets must start at 0");
+    for (uint64_t l = 0; l < n_lists; l++)
+        if (offs[l + 1] < offs[l]) return fail(ctx, GATB_ERR_INVALID, "annotations: offsets not monotone");
+    if (offs[n_lists] > 0xffffffffull) return fail(ctx, GATB_ERR_INVALID, "annotations: more than 2^32 intervals");
     CU(ctx, cudaSetDevice(ctx->device));
 
     const uint32_t A = (uint32_t)n_annot, K = (uint32_t)n_keys;
@@ -314,38 +318,22 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
             max_tile = std::max(max_tile, t.bytes);
             total += t.bytes;
         }
-    std::vector<uint8_t> blob(total);
+    // tile headers on the host (O(tracks x keys)); intervals, sentinels and bin indices are written
+    // by build_tiles_kernel from the raw CSR arrays, which also validates the lists
+    std::vector<TileHeader> headers((size_t)G * K);
     for (uint32_t g = 0; g < G; g++)
         for (uint32_t k = 0; k < K; k++) {
-            uint8_t *tp = blob.data() + tile_off[(size_t)g * K + k];
             const TileGeom t = tile_geometry(offs, end, A, K, g * ka, ka, k, bin_factor);
-            TileHeader h;
+            TileHeader &h = headers[(size_t)g * K + k];
             memset(&h, 0, sizeof(h));
             h.idx_off = t.idx_off; h.nbins = t.nbins; h.shift = t.shift;
-            uint16_t *idx = reinterpret_cast<uint16_t *>(tp + t.idx_off);
             for (uint32_t kk = 0; kk < (uint32_t)KMAX; kk++) {
                 h.iv_off[kk] = t.iv_off[kk];
-                uint64_t n = 0, base = 0;
                 if (kk < ka && g * ka + kk < A) {
                     const uint64_t l = (uint64_t)(g * ka + kk) * K + k;
-                    base = offs[l];
-                    n = offs[l + 1] - base;
-                }
-                h.n[kk] = (uint32_t)n;
-                uint32_t *iv = reinterpret_cast<uint32_t *>(tp + t.iv_off[kk]);
-                for (uint64_t i = 0; i < n; i++) { iv[2 * i] = start[base + i]; iv[2 * i + 1] = end[base + i]; }
-                iv[2 * n] = iv[2 * n + 1] = iv[2 * n + 2] = iv[2 * n + 3] = 0x7fffffffu;     // two sentinels
-                if (t.nbins) {
-                    uint64_t j = 0;
-                    for (uint32_t b = 0; b < t.nbins; b++) {
-                        const uint64_t pos = (uint64_t)b << t.shift;
-                        while (j < n && (uint64_t)end[base + j] <= pos) j++;
-                        idx[(size_t)b * 8 + kk] = (uint16_t)j;
-                    }
-                    idx[(size_t)t.nbins * 8 + kk] = (uint16_t)n;
+                    h.n[kk] = (uint32_t)(offs[l + 1] - offs[l]);
                 }
             }
-            memcpy(tp, &h, sizeof(h));
         }
 
     gatb_annotations *a = new gatb_annotations();
@@ -353,12 +341,38 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
     a->tile_budget = std::min(budget, max_tile);
     a->max_tile = max_tile;
     a->n_intervals = offs[n_lists];
-    cudaError_t e = a->tiles.upload(blob.data(), blob.size(), ctx->stream);
-    if (e == cudaSuccess) e = a->tile_off.upload(tile_off.data(), tile_off.size(), ctx->stream);
-    if (e == cudaSuccess) e = a->tile_bytes.upload(tile_bytes.data(), tile_bytes.size(), ctx->stream);
-    if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, ctx->stream); a->has_nseg = true; }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // host vectors die at return
+    cudaStream_t st = ctx->stream;
+    DevBuf<uint64_t> d_offs;
+    DevBuf<uint32_t> d_start, d_end, d_err;
+    DevBuf<TileHeader> d_headers;
+    uint32_t h_err = 0;
+    cudaError_t e = a->tiles.alloc(total);
+    if (e == cudaSuccess) e = a->tile_off.upload(tile_off.data(), tile_off.size(), st);
+    if (e == cudaSuccess) e = a->tile_bytes.upload(tile_bytes.data(), tile_bytes.size(), st);
+    if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, st); a->has_nseg = true; }
+    if (e == cudaSuccess) e = d_offs.upload(offs, n_lists + 1, st);
+    if (e == cudaSuccess) e = d_start.upload(start, offs[n_lists], st);
+    if (e == cudaSuccess) e = d_end.upload(end, offs[n_lists], st);
+    if (e == cudaSuccess) e = d_headers.upload(headers.data(), headers.size(), st);
+    if (e == cudaSuccess) e = d_err.alloc(1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_err.p, 0, sizeof(uint32_t), st);
+    if (e == cudaSuccess) {
+        BuildTilesParams bp;
+        bp.tiles = a->tiles.p; bp.tile_off = a->tile_off.p; bp.headers = d_headers.p;
+        bp.offs = d_offs.p; bp.start = d_start.p; bp.end = d_end.p;
+        bp.n_annot = A; bp.n_keys = K; bp.n_groups = G; bp.ka = ka; bp.error = d_err.p;
+        ProfScope ps(ctx, PROF_OTHER);
+        launch_build_tiles(st, bp);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_err, d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // host vectors die at return
     if (e != cudaSuccess) { delete a; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    if (h_err) {
+        delete a;
+        if (h_err & 1u) return fail(ctx, GATB_ERR_RANGE, "annotations: coordinate >= 2^31");
+        return fail(ctx, GATB_ERR_INVALID, "annotations: empty or inverted segment, or list not sorted/normalized");
+    }
     *out = a;
     return GATB_OK;
 }

@@ -231,6 +231,61 @@ static cudaError_t launch_count_t(cudaStream_t st, const CountParams &p, int thr
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// tile construction on the device (replaces a host loop over every interval and bin)
+__global__ void __launch_bounds__(256) build_tiles_kernel(BuildTilesParams p)
+{
+    const uint32_t tile = blockIdx.x;
+    const uint32_t g = tile / p.n_keys, k = tile % p.n_keys;
+    const TileHeader h = p.headers[tile];
+    uint8_t *tp = p.tiles + p.tile_off[tile];
+    if (threadIdx.x < sizeof(TileHeader) / 4)
+        reinterpret_cast<uint32_t *>(tp)[threadIdx.x] = reinterpret_cast<const uint32_t *>(&p.headers[tile])[threadIdx.x];
+    uint32_t err = 0;
+    for (uint32_t kk = 0; kk < (uint32_t)KMAX; kk++) {
+        uint64_t base = 0;
+        uint32_t n = 0;
+        if (kk < p.ka && g * p.ka + kk < p.n_annot) {
+            const uint64_t l = (uint64_t)(g * p.ka + kk) * p.n_keys + k;
+            base = p.offs[l];
+            n = (uint32_t)(p.offs[l + 1] - base);
+        }
+        const uint32_t *ls = p.start + base, *le = p.end + base;
+        uint2 *iv = reinterpret_cast<uint2 *>(tp + h.iv_off[kk]);
+        for (uint32_t i = threadIdx.x; i < n + 2; i += blockDim.x) {
+            uint2 v = make_uint2(0x7fffffffu, 0x7fffffffu);          // two sentinels after the list
+            if (i < n) {
+                v = make_uint2(ls[i], le[i]);
+                if (v.y >= 0x80000000u) err |= 1u;
+                if (v.x >= v.y) err |= 2u;
+                if (i > 0 && le[i - 1] > v.x) err |= 2u;
+            }
+            iv[i] = v;
+        }
+        if (h.nbins) {
+            uint16_t *idx = reinterpret_cast<uint16_t *>(tp + h.idx_off);
+            for (uint32_t b = threadIdx.x; b <= h.nbins; b += blockDim.x) {
+                uint32_t lo = 0, hi = n;                               // first j with end > (b << shift)
+                if (b < h.nbins) {
+                    const uint64_t pos = (uint64_t)b << h.shift;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if ((uint64_t)le[mid] <= pos) lo = mid + 1; else hi = mid;
+                    }
+                } else lo = n;
+                idx[(size_t)b * 8 + kk] = (uint16_t)lo;
+            }
+        }
+    }
+    if (err) atomicOr(p.error, err);
+}
+
+void launch_build_tiles(cudaStream_t st, const BuildTilesParams &p)
+{
+    const uint32_t tiles = p.n_groups * p.n_keys;
+    if (tiles) build_tiles_kernel<<<tiles, 256, 0, st>>>(p);
+}
+
 cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int threads)
 {
     if (p.n_samples == 0 || p.n_annot == 0) return cudaSuccess;

@@ -50,6 +50,20 @@ struct CountParams {
     double *out_f64;                // [n_samples][n_annot] (nucleotide-density)
 };
 
+// Builds every tile from the raw annotation CSR arrays on the device (one CTA per tile): copies the
+// intervals, writes sentinels and the interleaved bin index, and validates the lists (error bit 0:
+// coordinate >= 2^31, bit 1: empty / unsorted / overlapping = not normalized).
+struct BuildTilesParams {
+    uint8_t *tiles;
+    const uint64_t *tile_off;       // [n_groups][n_keys]
+    const TileHeader *headers;      // [n_groups][n_keys], geometry computed on the host
+    const uint64_t *offs;           // [n_annot*n_keys+1]
+    const uint32_t *start, *end;
+    uint32_t n_annot, n_keys, n_groups, ka;
+    uint32_t *error;
+};
+void launch_build_tiles(cudaStream_t st, const BuildTilesParams &p);
+
 // counter: GATB_* id.  Returns cudaError from the launch configuration.
 cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int threads);
 
