@@ -285,7 +285,8 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
     // tile budget: what one CTA can opt in to, minus the accumulators
     uint32_t budget = ctx->tile_budget;
     if (budget == 0) {
-        size_t acc = (size_t)ctx->schunk_max * KMAX * 16 + 16;
+        // accumulators + per-warp deferred-scan queues (count.cu: QCAP 64 entries x 16 B + tail per warp)
+        size_t acc = (size_t)ctx->schunk_max * KMAX * 16 + 16 + (size_t)(ctx->count_threads / 32) * (64 * 16 + 4) + 16;
         budget = (uint32_t)(ctx->smem_optin > acc + 1024 ? ctx->smem_optin - acc - 1024 : 32768);
     }
     // largest group size whose every tile fits the budget (floor: one track per tile; oversized tiles

@@ -45,76 +45,134 @@ __device__ __forceinline__ uint32_t scan_from(const uint2 *__restrict__ iv, uint
     return r;
 }
 
+// Deferred exact scans.  A (segment, track) pair whose count the branch-free fast path cannot prove
+// (about 2 % of the pairs) is pushed on a per-warp queue in shared memory instead of being resolved
+// on the spot with 2-3 of 32 lanes active; whenever 32 entries are waiting the warp resolves them
+// with all lanes busy.  The queue is drained at the end of every sample.
+constexpr uint32_t QCAP = 64;            // entries per warp; the flush threshold is 32
+struct __align__(16) QEntry { int s, e, pe; uint32_t jk; };     // jk = j | slot << 16
+__host__ __device__ inline uint32_t count_queue_bytes(uint32_t threads)
+{
+    return (threads >> 5) * QCAP * (uint32_t)sizeof(QEntry) + (((threads >> 5) * 4u + 15u) & ~15u);
+}
+
+template <int COUNTER>
+__device__ __forceinline__ void queue_resolve(const uint8_t *__restrict__ tile, const QEntry *__restrict__ q,
+                                              uint32_t first, uint32_t count, int lane, uint32_t (&acc)[KMAX])
+{
+    if ((uint32_t)lane < count) {
+        const QEntry en = q[first + lane];
+        const uint32_t kk = en.jk >> 16, j = en.jk & 0xffffu;
+        const uint32_t off = reinterpret_cast<const TileHeader *>(tile)->iv_off[kk];
+        const uint32_t r = scan_from<COUNTER>(reinterpret_cast<const uint2 *>(tile + off), j, en.s, en.e, en.pe);
+#pragma unroll
+        for (int t = 0; t < KMAX; t++) acc[t] += ((uint32_t)t == kk) ? r : 0u;
+    }
+}
+
 // One sample's segments on one key against the <= KMAX tracks of a tile.  `tile` points into shared
 // memory (staged tiles) or global memory; the code is instantiated once per address space.
 //
 // Indexed fast path per (segment, track): ONE 16-byte load fetches the bin entry of all 8 tracks,
 // two independent 8-byte loads fetch the candidate interval and its successor, and the result is
-// resolved branch-free; only lanes that need a longer scan (more than one interval ends inside the
-// bin before s, or the segment runs past the candidate's end) take the exact loop afterwards.
+// resolved branch-free; pairs that need a longer scan (more than one interval ends inside the bin
+// before s, or the segment runs past the candidate's end into the next interval) are deferred to
+// the warp's queue.  The next batch of segments is loaded while the current one is processed.
 template <int COUNTER, bool INDEXED>
 __device__ __forceinline__ void count_sample(const uint8_t *__restrict__ tile, const uint32_t (&iv_off)[KMAX],
                                              const uint32_t (&nn)[KMAX], uint32_t idx_off, uint32_t nbins,
                                              uint32_t shift, uint32_t ka,
                                              const uint64_t *__restrict__ segs, uint32_t n, int lane,
+                                             QEntry *__restrict__ queue, uint32_t *__restrict__ qtail,
                                              uint32_t (&acc)[KMAX])
 {
     const bool need_prev = (COUNTER == GATB_ANNOTATION_OVERLAP || COUNTER == GATB_ANNOTATION_MIDOVERLAP);
+    uint64_t xnext = ((uint32_t)lane < n) ? segs[lane] : 0;
     for (uint32_t b0 = 0; b0 < n; b0 += 32) {
         const uint32_t i = b0 + lane;
-        if (i >= n) continue;
-        const uint64_t x = segs[i];
+        const uint64_t x = xnext;
+        xnext = (i + 32 < n) ? segs[i + 32] : 0;                      // software prefetch of the next batch
         const int s = (int)seg_start(x), e = (int)seg_end(x);
         int pe = 0;
-        if (need_prev && i > 0) pe = (int)seg_end(segs[i - 1]);
+        if (need_prev && i > 0 && i < n) pe = (int)seg_end(segs[i - 1]);
         if (INDEXED) {
-            const uint32_t b = min((uint32_t)s >> shift, nbins);
-            const uint4 q = *reinterpret_cast<const uint4 *>(tile + idx_off + (size_t)b * 16);
-            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
             uint32_t slow = 0;
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (i < n) {
+                const uint32_t b = min((uint32_t)s >> shift, nbins);
+                q = *reinterpret_cast<const uint4 *>(tile + idx_off + (size_t)b * 16);
+                const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int kk = 0; kk < KMAX; kk++) {
-                const uint32_t j = (kk & 1) ? (qw[kk >> 1] >> 16) : (qw[kk >> 1] & 0xffffu);
-                const uint2 *iv = reinterpret_cast<const uint2 *>(tile + iv_off[kk]);
-                const uint2 c0 = iv[j], c1 = iv[j + 1];
-                const bool skip = (int)c0.y <= s;
-                const int ax = (int)(skip ? c1.x : c0.x), ay = (int)(skip ? c1.y : c0.y);
-                bool more = skip && ((int)c1.y <= s);
-                // the segment runs past the candidate's end: exact only if the next interval starts at
-                // or after e (known when the candidate is c0, whose successor c1 is already loaded)
-                const bool tail = (ay < e) && (skip || ((int)c1.x < e));
-                uint32_t r;
-                if (COUNTER == GATB_SEGMENT_OVERLAP) {
-                    r = (ax < e) ? 1u : 0u;
-                } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
-                    const int mid = s + ((e - s) >> 1);
-                    r = (ax < e && ax <= mid && mid < ay) ? 1u : 0u;
-                } else if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
-                    r = (uint32_t)max(min(e, ay) - max(s, ax), 0);
-                    more = more || tail;
-                } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
-                    r = (ax < e && ax >= pe) ? 1u : 0u;
-                    more = more || tail;
-                } else {
-                    const int m = ax + ((ay - ax) >> 1);
-                    r = (ax < e && ax >= pe && s <= m && m < e) ? 1u : 0u;
-                    more = more || tail;
+                for (int kk = 0; kk < KMAX; kk++) {
+                    const uint32_t j = (kk & 1) ? (qw[kk >> 1] >> 16) : (qw[kk >> 1] & 0xffffu);
+                    const uint2 *iv = reinterpret_cast<const uint2 *>(tile + iv_off[kk]);
+                    const uint2 c0 = iv[j], c1 = iv[j + 1];
+                    const bool skip = (int)c0.y <= s;
+                    const int ax = (int)(skip ? c1.x : c0.x), ay = (int)(skip ? c1.y : c0.y);
+                    bool more = skip && ((int)c1.y <= s);
+                    // the segment runs past the candidate's end: exact only if the next interval starts
+                    // at or after e (known when the candidate is c0, whose successor c1 is loaded)
+                    const bool tail = (ay < e) && (skip || ((int)c1.x < e));
+                    uint32_t r;
+                    if (COUNTER == GATB_SEGMENT_OVERLAP) {
+                        r = (ax < e) ? 1u : 0u;
+                    } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
+                        const int mid = s + ((e - s) >> 1);
+                        r = (ax < e && ax <= mid && mid < ay) ? 1u : 0u;
+                    } else if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
+                        r = (uint32_t)max(min(e, ay) - max(s, ax), 0);
+                        more = more || tail;
+                    } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
+                        r = (ax < e && ax >= pe) ? 1u : 0u;
+                        more = more || tail;
+                    } else {
+                        const int m = ax + ((ay - ax) >> 1);
+                        r = (ax < e && ax >= pe && s <= m && m < e) ? 1u : 0u;
+                        more = more || tail;
+                    }
+                    acc[kk] += more ? 0u : r;
+                    slow |= more ? (1u << kk) : 0u;
                 }
-                acc[kk] += more ? 0u : r;
-                slow |= more ? (1u << kk) : 0u;
             }
-            // rare: exact scan for the flagged (lane, slot) pairs, one slot per loop turn
-            while (slow) {
-                const int kk = __ffs(slow) - 1;
-                slow &= slow - 1;
-                const uint32_t w = (kk & 4) ? ((kk & 2) ? q.w : q.z) : ((kk & 2) ? q.y : q.x);
-                const uint32_t j = (kk & 1) ? (w >> 16) : (w & 0xffffu);
-                const uint32_t off = reinterpret_cast<const TileHeader *>(tile)->iv_off[kk];
-                const uint32_t r = scan_from<COUNTER>(reinterpret_cast<const uint2 *>(tile + off), j, s, e, pe);
+            const uint32_t cnt = __popc(slow);
+            const uint32_t total = __reduce_add_sync(GATB_FULL, cnt);
+            if (total) {
+                if (total <= QCAP - 32) {
+                    if (slow) {                                        // push this lane's pairs
+                        uint32_t pos = atomicAdd(qtail, cnt);
+                        while (slow) {
+                            const int kk = __ffs(slow) - 1;
+                            slow &= slow - 1;
+                            const uint32_t w = (kk & 4) ? ((kk & 2) ? q.w : q.z) : ((kk & 2) ? q.y : q.x);
+                            QEntry en;
+                            en.s = s; en.e = e; en.pe = pe;
+                            en.jk = ((kk & 1) ? (w >> 16) : (w & 0xffffu)) | ((uint32_t)kk << 16);
+                            queue[pos++] = en;
+                        }
+                    }
+                    __syncwarp();
+                    const uint32_t t = *qtail;
+                    if (t >= 32) {
+                        queue_resolve<COUNTER>(tile, queue, t - 32, 32, lane, acc);
+                        __syncwarp();
+                        if (lane == 0) *qtail = t - 32;
+                        __syncwarp();
+                    }
+                } else {
+                    // a batch with more than 32 unresolved pairs (dense overlaps): resolve in place
+                    while (slow) {
+                        const int kk = __ffs(slow) - 1;
+                        slow &= slow - 1;
+                        const uint32_t w = (kk & 4) ? ((kk & 2) ? q.w : q.z) : ((kk & 2) ? q.y : q.x);
+                        const uint32_t j = (kk & 1) ? (w >> 16) : (w & 0xffffu);
+                        const uint32_t off = reinterpret_cast<const TileHeader *>(tile)->iv_off[kk];
+                        const uint32_t r = scan_from<COUNTER>(reinterpret_cast<const uint2 *>(tile + off), j, s, e, pe);
 #pragma unroll
-                for (int t = 0; t < KMAX; t++) acc[t] += (t == kk) ? r : 0u;
+                        for (int t = 0; t < KMAX; t++) acc[t] += (t == kk) ? r : 0u;
+                    }
+                }
             }
-        } else {
+        } else if (i < n) {
 #pragma unroll
             for (int kk = 0; kk < KMAX; kk++) {
                 if ((uint32_t)kk < ka) {
@@ -129,17 +187,29 @@ __device__ __forceinline__ void count_sample(const uint8_t *__restrict__ tile, c
             }
         }
     }
+    if (INDEXED) {                                                     // drain the queue: acc is per sample
+        const uint32_t t = *qtail;
+        if (t) {
+            queue_resolve<COUNTER>(tile, queue, 0, t, lane, acc);
+            __syncwarp();
+            if (lane == 0) *qtail = 0;
+            __syncwarp();
+        }
+    }
 }
 
 template <int COUNTER, bool DENSITY>
 __global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    // layout: [acc: schunk*KMAX*(DENSITY?16:4) bytes][tile]; density keeps (sum, compensation) per slot
-    const uint32_t acc_bytes = p.schunk * KMAX * (DENSITY ? 16u : 4u);
+    // layout: [acc: schunk*KMAX*(DENSITY?16:4) bytes][per-warp queues + tails][tile]; density keeps
+    // (sum, compensation) per slot
+    const uint32_t acc_bytes = (p.schunk * KMAX * (DENSITY ? 16u : 4u) + 15u) & ~15u;
     uint32_t *acc_u = reinterpret_cast<uint32_t *>(smem);
     double *acc_d = reinterpret_cast<double *>(smem);
-    uint8_t *tile_s = smem + ((acc_bytes + 15u) & ~15u);
+    QEntry *queues = reinterpret_cast<QEntry *>(smem + acc_bytes);
+    uint32_t *qtails = reinterpret_cast<uint32_t *>(smem + acc_bytes + (blockDim.x >> 5) * QCAP * sizeof(QEntry));
+    uint8_t *tile_s = smem + acc_bytes + count_queue_bytes(blockDim.x);
 
     const uint32_t g = blockIdx.x;
     const uint32_t a0 = g * p.ka;
@@ -151,6 +221,9 @@ __global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
     for (uint32_t i = threadIdx.x; i < p.schunk * KMAX; i += blockDim.x) {
         if (DENSITY) { acc_d[2 * i] = 0.0; acc_d[2 * i + 1] = 0.0; } else acc_u[i] = 0u;
     }
+    if (lane == 0) qtails[warp] = 0;
+    QEntry *queue = queues + (size_t)warp * QCAP;
+    uint32_t *qtail = qtails + warp;
 
     for (uint32_t k = 0; k < p.n_keys; k++) {
         const uint32_t tbytes = p.tile_bytes[(uint64_t)g * p.n_keys + k];
@@ -181,11 +254,11 @@ __global__ void __launch_bounds__(512, 1) count_kernel(CountParams p)
 #pragma unroll
             for (int kk = 0; kk < KMAX; kk++) acc[kk] = 0;
             if (staged) {
-                if (nbins) count_sample<COUNTER, true>(tile_s, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, acc);
-                else count_sample<COUNTER, false>(tile_s, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, acc);
+                if (nbins) count_sample<COUNTER, true>(tile_s, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, queue, qtail, acc);
+                else count_sample<COUNTER, false>(tile_s, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, queue, qtail, acc);
             } else {
-                if (nbins) count_sample<COUNTER, true>(tile_g, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, acc);
-                else count_sample<COUNTER, false>(tile_g, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, acc);
+                if (nbins) count_sample<COUNTER, true>(tile_g, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, queue, qtail, acc);
+                else count_sample<COUNTER, false>(tile_g, iv_off, nn, idx_off, nbins, shift, ka, segs, n, lane, queue, qtail, acc);
             }
             uint32_t mine = 0;
 #pragma unroll
@@ -222,7 +295,7 @@ template <int COUNTER, bool DENSITY>
 static cudaError_t launch_count_t(cudaStream_t st, const CountParams &p, int threads)
 {
     const uint32_t acc_bytes = (p.schunk * KMAX * (DENSITY ? 16u : 4u) + 15u) & ~15u;
-    const size_t smem = (size_t)acc_bytes + p.smem_tile_budget;
+    const size_t smem = (size_t)acc_bytes + count_queue_bytes((uint32_t)threads) + p.smem_tile_budget;
     cudaError_t e = cudaFuncSetAttribute(count_kernel<COUNTER, DENSITY>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
