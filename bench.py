@@ -177,19 +177,22 @@ def reference_rate(args, wl, seconds_target=15.0):
     n1 = args.cpu_samples or int(max(4, min(200, seconds_target / max(per, 1e-3))))
     dt1, _ = ref_bench.time_sampling(segments, annotations, workspace, [args.counter], n1, num_threads=0)
     r1 = n1 / dt1
-    # its multiprocessing path: every task re-pickles all interval arrays, so bound it hard
-    nm = max(cores, 8) if per * wl["A"] < 1e9 else cores
-    nm = min(nm, 4 * n1)
+    # its multiprocessing path (--num-threads): the parent re-pickles ALL interval arrays for every task
+    # (SURVEY section 5), so throughput stops growing after a few workers; at most 32 workers, one
+    # sample per worker, keeps this leg bounded on many-core hosts
+    workers = min(cores, 32)
+    nm = workers
     rm, dtm = None, None
     try:
-        dtm, _ = ref_bench.time_sampling(segments, annotations, workspace, [args.counter], nm, num_threads=cores)
+        dtm, _ = ref_bench.time_sampling(segments, annotations, workspace, [args.counter], nm, num_threads=workers)
         rm = nm / dtm
     except Exception as e:  # pragma: no cover
         rm = None
         sys.stderr.write("reference multiprocessing path failed: %s\n" % e)
     best, used = (r1, 1)
     if rm is not None and rm > r1:
-        best, used = rm, cores
+        best, used = rm, workers
+    cores = workers
     sample = ("reference UnconditionalSampler.sample: %i samples single-process in %.1f s (%.3f samples/s); "
               "%s; faster mode reported" %
               (n1, dt1, r1, ("%i samples with --num-threads=%i in %.1f s (%.3f samples/s)" % (nm, cores, dtm, rm))

@@ -72,25 +72,36 @@ static int fail(gatb_ctx *ctx, int code, const std::string &msg)
             return fail(ctx, GATB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
+// Device buffers come from the stream-ordered allocator (cudaMallocAsync on the context's stream, pool
+// release threshold unlimited): creating and destroying samplers / annotation sets per call re-uses
+// pooled memory instead of paying cudaMalloc/cudaFree (which synchronise the device) every time.
+static thread_local cudaStream_t tl_stream = nullptr;
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t st = nullptr;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release()
+    {
+        if (p && cudaFreeAsync(p, st) != cudaSuccess) { cudaGetLastError(); cudaFree(p); }
+        p = nullptr; n = 0;
+    }
     cudaError_t alloc(size_t count)
     {
         release();
         n = count;
+        st = tl_stream;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc((void **)&p, count * sizeof(T));
+        return cudaMallocAsync((void **)&p, count * sizeof(T), st);
     }
     cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count); }
-    cudaError_t upload(const T *h, size_t count, cudaStream_t st)
+    cudaError_t upload(const T *h, size_t count, cudaStream_t stream)
     {
         cudaError_t e = alloc(count);
         if (e != cudaSuccess || count == 0) return e;
-        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st);
+        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, stream);
     }
 };
 
@@ -124,6 +135,13 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     ctx->stream = ctx->own_stream;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     ctx->count_threads = (int)env_u32("GATB_COUNT_THREADS", 512);
@@ -147,6 +165,8 @@ extern "C" const char *gatb_last_error(gatb_ctx *ctx) { return ctx ? ctx->err.c_
 extern "C" int gatb_set_stream(gatb_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) return GATB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);           // buffers allocated on the old stream are complete
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return GATB_OK;
 }
@@ -155,6 +175,7 @@ extern "C" int gatb_synchronize(gatb_ctx *ctx)
 {
     if (!ctx) return GATB_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return GATB_OK;
 }
@@ -172,6 +193,7 @@ extern "C" int gatb_profile_read(gatb_ctx *ctx, double *ms, uint64_t *launches)
 {
     if (!ctx || !ms || !launches) return GATB_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < PROF_NCLS; i++) { ms[i] = 0; launches[i] = 0; }
     for (auto &sp : ctx->spans) {
@@ -279,6 +301,7 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
         if (offs[l + 1] < offs[l]) return fail(ctx, GATB_ERR_INVALID, "annotations: offsets not monotone");
     if (offs[n_lists] > 0xffffffffull) return fail(ctx, GATB_ERR_INVALID, "annotations: more than 2^32 intervals");
     CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
 
     const uint32_t A = (uint32_t)n_annot, K = (uint32_t)n_keys;
     const uint32_t bin_factor = std::max(1u, env_u32("GATB_BIN_FACTOR", 4));
@@ -422,6 +445,7 @@ extern "C" int gatb_count_lists(gatb_ctx *ctx, const gatb_annotations *annos, in
             return fail(ctx, GATB_ERR_INVALID, "nucleotide-density needs key_ws_nseg at gatb_annotations_create");
     }
     CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
 
     // capacity layout: key k of sample s at s*stride + key_base[k]
@@ -529,6 +553,7 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
         for (uint32_t c = 0; c < C; c++)
             if (per_contig[c] > 1) return fail(ctx, GATB_ERR_INVALID, "sampler: several units per contig need has_isochores");
     CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
 
     gatb_sampler *s = new gatb_sampler();
@@ -741,6 +766,7 @@ extern "C" int gatb_sampler_place(gatb_sampler *s, uint64_t seed, uint32_t track
     if (sample_begin + n_samples > 0xffffffffull) return fail(ctx, GATB_ERR_RANGE, "sample index >= 2^32");
     if (track >= (1u << 24)) return fail(ctx, GATB_ERR_RANGE, "track index >= 2^24");
     CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
     if (contig_base) for (uint32_t c = 0; c < s->n_contigs; c++) contig_base[c] = s->h_contig_base[c];
     const uint32_t B = pick_batch(s, n_samples);
@@ -791,6 +817,7 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
     if (any_int && !out_counts) return fail(ctx, GATB_ERR_INVALID, "run: out_counts is NULL");
     if (n_samples == 0) return GATB_OK;
     CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
     const uint32_t A = annos->n_annot;
     const uint32_t B = pick_batch(s, n_samples);
@@ -842,6 +869,7 @@ extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float
     if (!ctx || !counts || !observed || n_cols <= 0) return GATB_ERR_INVALID;
     if (n_samples < 1) return fail(ctx, GATB_ERR_INVALID, "column_stats: no samples");
     CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
     const uint32_t A = (uint32_t)n_cols;
     const uint64_t l = n_samples;

@@ -215,6 +215,60 @@ __device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n)
     return warp_merge0_sorted(buf, n);
 }
 
+// merge(0) of a sorted, merged run U = buf[0,nu) with np <= 32 new segments stored behind it
+// (buf[nu, nu+np)): the common checkpoint late in the placement loop, where one or two placements
+// join an already merged list.  The new keys are sorted across lanes with shuffles, U is shifted
+// right in place (top chunk first) by the number of new keys that precede each element, the new
+// keys are dropped into the gaps and the usual merge(0) scan runs once.  O(nu/32) instead of a
+// full bitonic sort.  Same result as warp_sort_merge0(buf, nu + np).
+__device__ __forceinline__ uint32_t warp_insert_merge0(uint64_t *buf, uint32_t nu, uint32_t np)
+{
+    const int lane = lane_id();
+    uint64_t key = ((uint32_t)lane < np) ? buf[nu + lane] : GATB_KEY_INF;
+    // bitonic sort of the 32 lane-resident keys (ascending)
+#pragma unroll
+    for (uint32_t k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            const uint64_t y = shfl_xor_u64(key, (int)j);
+            const bool asc = ((lane & k) == 0), lower = ((lane & j) == 0);
+            key = (lower == asc) ? (key < y ? key : y) : (key > y ? key : y);
+        }
+    }
+    // insertion point of each new key in U: number of U elements <= key (ties keep U first)
+    uint32_t pos = nu;
+    if ((uint32_t)lane < np) {
+        uint32_t lo = 0, hi = nu;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (buf[mid] <= key) lo = mid + 1; else hi = mid;
+        }
+        pos = lo;
+    }
+    const uint32_t first = __shfl_sync(GATB_FULL, pos, 0);
+    __syncwarp();
+    // shift U[i] to i + #{new keys with pos <= i}, chunks from the top down so nothing unread is overwritten
+    if (nu > first) {
+        const uint32_t lowest_chunk = first >> 5;
+        for (int c = (int)((nu - 1) >> 5); c >= (int)lowest_chunk; c--) {
+            const uint32_t i = ((uint32_t)c << 5) + lane;
+            const uint64_t x = (i < nu) ? buf[i] : 0;
+            uint32_t cnt = 0;                      // upper_bound of i in the lane-resident sorted pos[]
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t probe = __shfl_sync(GATB_FULL, pos, (int)(cnt + step - 1));
+                if (cnt + step <= np && probe <= i) cnt += step;
+            }
+            __syncwarp();
+            if (i < nu && i >= first) buf[i + cnt] = x;
+            __syncwarp();
+        }
+    }
+    if ((uint32_t)lane < np) buf[pos + lane] = key;
+    __syncwarp();
+    return warp_merge0_sorted(buf, nu + np);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Workspace of one unit: sorted disjoint pieces + inclusive cumulative lengths.
 struct WsView {

@@ -202,7 +202,10 @@ __global__ void __launch_bounds__(128) place_kernel(PlaceParams p)
             const int32_t ovf = __shfl_sync(GATB_FULL, t.ov, (int)f);
             (void)Lf;
             __syncwarp();
-            nu = warp_sort_merge0(buf, nu + np);
+            // late checkpoints add a handful of placements to an already merged list: insert them
+            // instead of re-sorting everything (same result, see warp_insert_merge0)
+            if (nu > 0 && np < 32 && !dirty) nu = warp_insert_merge0(buf, nu, np);
+            else nu = warp_sort_merge0(buf, nu + np);
             np = 0; dirty = false;
             remaining = d.ltotal - (int32_t)warp_coverage(buf, nu, ws);
             if (true_remaining == remaining) fails++; else true_remaining = remaining;
