@@ -30,7 +30,7 @@ struct gatb_ctx {
     size_t smem_optin = 0;
     // tunables (env overrides, for profiling)
     uint32_t tile_budget = 0;
-    int count_threads = 512;
+    int count_threads = 1024;
     uint32_t schunk_max = 128;
     // optional per-kernel timing (bench.py roofline): CUDA events around every launch
     bool profiling = false;
@@ -144,7 +144,7 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
-    ctx->count_threads = (int)env_u32("GATB_COUNT_THREADS", 512);
+    ctx->count_threads = (int)std::min(1024u, std::max(32u, env_u32("GATB_COUNT_THREADS", 1024) / 32 * 32));
     ctx->schunk_max = env_u32("GATB_SCHUNK", 128);
     ctx->tile_budget = env_u32("GATB_TILE_BUDGET", 0);
     ctx->batch = env_u32("GATB_BATCH", 0);
@@ -237,53 +237,71 @@ static int check_lists(gatb_ctx *ctx, const char *what, uint64_t n_lists, const 
 struct gatb_annotations {
     gatb_ctx *ctx = nullptr;
     uint32_t n_annot = 0, n_keys = 0, n_groups = 0, ka = 1;
-    uint32_t tile_budget = 0, max_tile = 0;
+    uint32_t max_stage = 0;             // largest filter (bytes) over all tiles
     uint64_t n_intervals = 0;
     DevBuf<uint8_t> tiles;
     DevBuf<uint64_t> tile_off;
-    DevBuf<uint32_t> tile_bytes;
+    DevBuf<uint32_t> tile_stage;
     DevBuf<uint32_t> key_ws_nseg;
     bool has_nseg = false;
 };
 
-static inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+static inline uint64_t align16(uint64_t x) { return (x + 15u) & ~(uint64_t)15u; }
 
-// geometry of tile (group g, key k): header | idx8[nbins+1] | KMAX interval lists (n+2 entries each)
-struct TileGeom { uint32_t bytes, nbins, shift, idx_off, iv_off[KMAX]; bool ok; };
-
-static TileGeom tile_geometry(const uint64_t *offs, const uint32_t *end, uint32_t A, uint32_t K,
-                              uint32_t a0, uint32_t ka, uint32_t k, uint32_t bin_factor)
+// shared memory left for a staged filter under the most demanding launch (density accumulators)
+static uint32_t filter_budget(const gatb_ctx *ctx)
 {
-    TileGeom t;
-    memset(&t, 0, sizeof(t));
-    t.ok = true;
-    uint64_t max_n = 0;
+    if (ctx->tile_budget) return ctx->tile_budget;
+    const size_t over = count_smem_overhead(ctx->count_threads, ctx->schunk_max, true) + 1024;
+    return (uint32_t)(ctx->smem_optin > over + 16384 ? ctx->smem_optin - over : 16384);
+}
+
+// geometry of tile (tracks a0 .. a0+ka-1, key k); see count.cuh.  ok == false: larger than 4 GiB.
+static bool tile_geometry(const uint64_t *offs, const uint32_t *end, uint32_t A, uint32_t K, uint32_t a0,
+                          uint32_t ka, uint32_t k, uint32_t bin_factor, uint32_t budget, TileHeader &h,
+                          uint64_t &bytes)
+{
+    memset(&h, 0, sizeof(h));
+    uint64_t nc = 0;
     uint32_t extent = 0;
-    bool indexable = true;
     for (uint32_t kk = 0; kk < ka && a0 + kk < A; kk++) {
         const uint64_t l = (uint64_t)(a0 + kk) * K + k;
         const uint64_t n = offs[l + 1] - offs[l];
-        max_n = std::max(max_n, n);
+        nc += n;
         if (n) extent = std::max(extent, end[offs[l + 1] - 1]);
-        if (n > 65534) indexable = false;
     }
-    uint64_t o = align16((uint32_t)sizeof(TileHeader));
-    if (indexable) {
-        const uint64_t target = std::max<uint64_t>((uint64_t)bin_factor * max_n, 16);
-        while ((((uint64_t)extent >> t.shift) + 1) > target) t.shift++;
-        t.nbins = (extent >> t.shift) + 1;
-        t.idx_off = (uint32_t)o;
-        o += (uint64_t)(t.nbins + 1) * 16;
+    if (nc > 0x7fffffffull) return false;
+    h.n_cons = (uint32_t)nc;
+    const uint64_t hdr = align16(sizeof(TileHeader));
+    const uint64_t uiv_bytes = align16((nc + 2) * 8);
+    // bin index: bin_factor bins per interval, but no more than fit next to the union in the budget
+    // (and never more bins than positions); lists with > 65534 intervals are binary-searched instead
+    uint64_t nbins = 0;
+    if (nc > 0 && nc <= 65534 && extent > 1) {
+        nbins = (uint64_t)bin_factor * nc;
+        if (hdr + uiv_bytes + 2 * (nbins + 1) + 16 > budget) {
+            const uint64_t room = budget > hdr + uiv_bytes + 64 ? (budget - hdr - uiv_bytes - 32) / 2 : 0;
+            nbins = std::max<uint64_t>(std::min<uint64_t>(nbins, room), std::min<uint64_t>(nc, nbins));
+        }
+        nbins = std::min<uint64_t>(nbins, extent);
     }
-    for (uint32_t kk = 0; kk < (uint32_t)KMAX; kk++) {
-        uint64_t n = 0;
-        if (kk < ka && a0 + kk < A) { const uint64_t l = (uint64_t)(a0 + kk) * K + k; n = offs[l + 1] - offs[l]; }
-        t.iv_off[kk] = (uint32_t)o;
-        o += ((n + 2) * 8 + 15) & ~15ull;
-        if (o > 0xfffffff0ull) { t.ok = false; return t; }
-    }
-    t.bytes = (uint32_t)o;
-    return t;
+    h.nbins = (uint32_t)nbins;
+    h.inv = nbins ? (uint32_t)(((uint64_t)nbins << 32) / ((uint64_t)extent + 1)) : 0;
+    if (nbins && h.inv == 0) { h.nbins = 0; nbins = 0; }
+    uint64_t o = hdr;
+    h.idx_off = (uint32_t)o;
+    o += nbins ? align16((nbins + 1) * 2) : 0;
+    h.uiv_off = (uint32_t)o;
+    o += uiv_bytes;
+    if (o > 0xfffffff0ull) return false;
+    h.stage_bytes = (uint32_t)o;
+    h.uoff_off = (uint32_t)o;
+    o += align16((nc + 2) * 4);
+    if (o > 0xfffffff0ull) return false;
+    h.cons_off = (uint32_t)o;
+    o += align16(nc * 16);
+    bytes = o;
+    return true;
 }
 
 extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
@@ -305,65 +323,45 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
 
     const uint32_t A = (uint32_t)n_annot, K = (uint32_t)n_keys;
     const uint32_t bin_factor = std::max(1u, env_u32("GATB_BIN_FACTOR", 4));
-    // tile budget: what one CTA can opt in to, minus the accumulators
-    uint32_t budget = ctx->tile_budget;
-    if (budget == 0) {
-        // accumulators + per-warp deferred-scan queues (count.cu: QCAP 64 entries x 16 B + tail per warp)
-        size_t acc = (size_t)ctx->schunk_max * KMAX * 16 + 16 + (size_t)(ctx->count_threads / 32) * (64 * 16 + 4) + 16;
-        budget = (uint32_t)(ctx->smem_optin > acc + 1024 ? ctx->smem_optin - acc - 1024 : 32768);
-    }
-    // largest group size whose every tile fits the budget (floor: one track per tile; oversized tiles
-    // are then read from global memory by the kernel)
+    const uint32_t budget = filter_budget(ctx);
+    // largest group size whose every filter fits the budget (floor: one track per tile; oversized
+    // filters are then read from global memory by the kernel)
     uint32_t ka = 1;
-    for (uint32_t cand = KMAX; cand >= 1; cand--) {
-        uint32_t worst = 0;
+    TileHeader h;
+    uint64_t bytes = 0;
+    for (uint32_t cand = (uint32_t)KMAX; cand >= 1; cand--) {
         bool ok = true;
         for (uint32_t a0 = 0; a0 < A && ok; a0 += cand)
-            for (uint32_t k = 0; k < K; k++) {
-                TileGeom t = tile_geometry(offs, end, A, K, a0, cand, k, bin_factor);
-                if (!t.ok) { ok = false; break; }
-                worst = std::max(worst, t.bytes);
-            }
-        if ((ok && worst <= budget) || cand == 1) { ka = cand; break; }
+            for (uint32_t k = 0; k < K; k++)
+                if (!tile_geometry(offs, end, A, K, a0, cand, k, bin_factor, budget, h, bytes) || h.stage_bytes > budget) {
+                    ok = false;
+                    break;
+                }
+        if (ok || cand == 1) { ka = cand; break; }
     }
     const uint32_t G = (A + ka - 1) / ka;
 
-    // build the blob
+    // tile headers on the host (O(tracks x keys)); everything else is written by build_tiles_kernel
+    // from the raw CSR arrays, which also validates the lists
     std::vector<uint64_t> tile_off((size_t)G * K);
-    std::vector<uint32_t> tile_bytes((size_t)G * K);
-    uint64_t total = 0;
-    uint32_t max_tile = 0;
-    for (uint32_t g = 0; g < G; g++)
-        for (uint32_t k = 0; k < K; k++) {
-            TileGeom t = tile_geometry(offs, end, A, K, g * ka, ka, k, bin_factor);
-            if (!t.ok) return fail(ctx, GATB_ERR_INVALID, "annotations: tile larger than 4 GiB");
-            tile_off[(size_t)g * K + k] = total;
-            tile_bytes[(size_t)g * K + k] = t.bytes;
-            max_tile = std::max(max_tile, t.bytes);
-            total += t.bytes;
-        }
-    // tile headers on the host (O(tracks x keys)); intervals, sentinels and bin indices are written
-    // by build_tiles_kernel from the raw CSR arrays, which also validates the lists
+    std::vector<uint32_t> tile_stage((size_t)G * K);
     std::vector<TileHeader> headers((size_t)G * K);
+    uint64_t total = 0;
+    uint32_t max_stage = 0;
     for (uint32_t g = 0; g < G; g++)
         for (uint32_t k = 0; k < K; k++) {
-            const TileGeom t = tile_geometry(offs, end, A, K, g * ka, ka, k, bin_factor);
-            TileHeader &h = headers[(size_t)g * K + k];
-            memset(&h, 0, sizeof(h));
-            h.idx_off = t.idx_off; h.nbins = t.nbins; h.shift = t.shift;
-            for (uint32_t kk = 0; kk < (uint32_t)KMAX; kk++) {
-                h.iv_off[kk] = t.iv_off[kk];
-                if (kk < ka && g * ka + kk < A) {
-                    const uint64_t l = (uint64_t)(g * ka + kk) * K + k;
-                    h.n[kk] = (uint32_t)(offs[l + 1] - offs[l]);
-                }
-            }
+            const size_t t = (size_t)g * K + k;
+            if (!tile_geometry(offs, end, A, K, g * ka, ka, k, bin_factor, budget, headers[t], bytes))
+                return fail(ctx, GATB_ERR_INVALID, "annotations: tile larger than 4 GiB");
+            tile_off[t] = total;
+            tile_stage[t] = headers[t].stage_bytes;
+            max_stage = std::max(max_stage, headers[t].stage_bytes);
+            total += bytes;
         }
 
     gatb_annotations *a = new gatb_annotations();
     a->ctx = ctx; a->n_annot = A; a->n_keys = K; a->n_groups = G; a->ka = ka;
-    a->tile_budget = std::min(budget, max_tile);
-    a->max_tile = max_tile;
+    a->max_stage = max_stage;
     a->n_intervals = offs[n_lists];
     cudaStream_t st = ctx->stream;
     DevBuf<uint64_t> d_offs;
@@ -372,7 +370,7 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
     uint32_t h_err = 0;
     cudaError_t e = a->tiles.alloc(total);
     if (e == cudaSuccess) e = a->tile_off.upload(tile_off.data(), tile_off.size(), st);
-    if (e == cudaSuccess) e = a->tile_bytes.upload(tile_bytes.data(), tile_bytes.size(), st);
+    if (e == cudaSuccess) e = a->tile_stage.upload(tile_stage.data(), tile_stage.size(), st);
     if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, st); a->has_nseg = true; }
     if (e == cudaSuccess) e = d_offs.upload(offs, n_lists + 1, st);
     if (e == cudaSuccess) e = d_start.upload(start, offs[n_lists], st);
@@ -409,13 +407,12 @@ extern "C" void gatb_annotations_destroy(gatb_annotations *a)
 }
 
 // fill the annotation side of CountParams and pick the sample chunk
-static void count_params_annos(const gatb_annotations *a, uint32_t n_samples, CountParams &p)
+static void count_params_annos(const gatb_annotations *a, uint32_t n_samples, bool density, CountParams &p)
 {
     const gatb_ctx *ctx = a->ctx;
-    p.tiles = a->tiles.p; p.tile_off = a->tile_off.p; p.tile_bytes = a->tile_bytes.p;
+    p.tiles = a->tiles.p; p.tile_off = a->tile_off.p; p.tile_stage = a->tile_stage.p;
     p.key_ws_nseg = a->has_nseg ? a->key_ws_nseg.p : nullptr;
     p.n_annot = a->n_annot; p.n_keys = a->n_keys; p.n_groups = a->n_groups; p.ka = a->ka;
-    p.smem_tile_budget = a->tile_budget;
     p.n_samples = n_samples;
     // enough CTAs for ~4 waves, chunk a multiple of the warps per CTA
     const uint32_t nwarps = (uint32_t)ctx->count_threads / 32;
@@ -423,8 +420,12 @@ static void count_params_annos(const gatb_annotations *a, uint32_t n_samples, Co
     uint32_t chunks = std::max(1u, (target + a->n_groups - 1) / a->n_groups);
     uint32_t schunk = (n_samples + chunks - 1) / chunks;
     schunk = ((schunk + nwarps - 1) / nwarps) * nwarps;
-    schunk = std::max(nwarps, std::min(schunk, ctx->schunk_max));
+    schunk = std::max(nwarps, std::min(schunk, std::max(nwarps, ctx->schunk_max)));
     p.schunk = schunk;
+    // what this launch can stage: the device limit minus its own accumulators and queues
+    const size_t over = count_smem_overhead(ctx->count_threads, schunk, density) + 1024;
+    const size_t room = ctx->smem_optin > over ? ctx->smem_optin - over : 0;
+    p.smem_tile_budget = (uint32_t)std::min<size_t>(room, a->max_stage);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -479,13 +480,14 @@ extern "C" int gatb_count_lists(gatb_ctx *ctx, const gatb_annotations *annos, in
 
     CountParams p;
     memset(&p, 0, sizeof(p));
-    count_params_annos(annos, (uint32_t)n_samples, p);
+    count_params_annos(annos, (uint32_t)n_samples, false, p);
     p.placed = d_packed.p; p.sample_stride = stride; p.key_base = d_base.p; p.placed_n = d_n.p;
     p.key_present = key_present ? d_present.p : nullptr;
     p.out_u32 = d_out.p; p.out_f64 = d_outf.p;
 
     std::vector<uint32_t> h_u(n_samples * A);
     for (int c = 0; c < n_counters; c++) {
+        count_params_annos(annos, (uint32_t)n_samples, counters[c] == GATB_NUCLEOTIDE_DENSITY, p);
         { ProfScope ps(ctx, PROF_COUNT); CU(ctx, launch_count(st, counters[c], p, ctx->count_threads)); }
         double *o = out + (uint64_t)c * n_samples * A;
         if (counters[c] == GATB_NUCLEOTIDE_DENSITY) {
@@ -835,11 +837,12 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
         if (rc) return rc;
         CountParams p;
         memset(&p, 0, sizeof(p));
-        count_params_annos(annos, b, p);
+        count_params_annos(annos, b, false, p);
         p.placed = s->placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
         p.placed_n = s->placed_n.p; p.key_present = nullptr;
         for (int c = 0; c < n_counters; c++) {
             const bool dens = counters[c] == GATB_NUCLEOTIDE_DENSITY;
+            count_params_annos(annos, b, dens, p);
             uint32_t *dst_u = out_counts ? out_counts + ((uint64_t)c * n_samples + done) * A : nullptr;
             double *dst_f = out_density ? out_density + done * A : nullptr;
             p.out_u32 = out_is_device ? dst_u : s->out_tmp.p;
@@ -891,12 +894,12 @@ extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float
     DevBuf<unsigned long long> d_cnt;
     CU(ctx, d_obs.upload(obs_eff.data(), A, st));
     CU(ctx, d_sum.alloc(A)); CU(ctx, d_sq.alloc(A)); CU(ctx, d_qlo.alloc(A)); CU(ctx, d_qhi.alloc(A));
-    CU(ctx, d_cnt.alloc(3 * (size_t)A));
+    CU(ctx, d_cnt.alloc(2 * (size_t)A));
 
     StatsParams p;
     memset(&p, 0, sizeof(p));
     p.counts = dc; p.is_float = is_float; p.n_samples = l; p.n_cols = A; p.observed = d_obs.p;
-    p.sum = d_sum.p; p.sumsq_dev = d_sq.p; p.n_trunc_lt = d_cnt.p; p.n_lt = d_cnt.p + A; p.n_eq = d_cnt.p + 2 * (size_t)A;
+    p.sum = d_sum.p; p.sumsq_dev = d_sq.p; p.n_lt = d_cnt.p; p.n_eq = d_cnt.p + A;
     p.q_lo = d_qlo.p; p.q_hi = d_qhi.p;
     // CI ranks (gat/Engine.pyx:1689-1696)
     const uint64_t off = (uint64_t)(0.05 * (double)l);
@@ -905,19 +908,19 @@ extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float
     { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass1(st, p); }
     CU(ctx, cudaGetLastError());
     std::vector<double> h_sum(A), h_sq(A), h_qlo(A), h_qhi(A), h_mean(A);
-    std::vector<unsigned long long> h_cnt(3 * (size_t)A);
+    std::vector<unsigned long long> h_cnt(2 * (size_t)A);
     CU(ctx, cudaMemcpyAsync(h_sum.data(), d_sum.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     for (uint32_t a = 0; a < A; a++) h_mean[a] = h_sum[a] / (double)l;        // numpy.mean (:1671)
     CU(ctx, d_mean.upload(h_mean.data(), A, st));
     p.mean = d_mean.p;
     { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass2(st, p); }
-    { ProfScope ps(ctx, PROF_OTHER); launch_stats_select(st, p, nullptr); }
+    { ProfScope ps(ctx, PROF_OTHER); launch_stats_select(st, p); }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(h_sq.data(), d_sq.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaMemcpyAsync(h_qlo.data(), d_qlo.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaMemcpyAsync(h_qhi.data(), d_qhi.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt.p, 3 * (size_t)A * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt.p, 2 * (size_t)A * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
 
     for (uint32_t a = 0; a < A; a++) {
@@ -927,8 +930,9 @@ extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float
         double lo = h_qlo[a], hi = h_qhi[a];
         if (ref_fold) { lo *= ref_fold[a]; hi *= ref_fold[a]; }              // :1713-1714
         // getTwoSidedPValue (:1543-1576) from counts instead of a sorted copy
-        const uint64_t idx0 = h_cnt[a], n_lt = h_cnt[A + a], n_eq = h_cnt[2 * (size_t)A + a];
-        const bool first_is_eq = (n_lt == idx0) && n_eq > 0;                  // sorted[idx0] == val
+        const uint64_t n_lt = h_cnt[a], n_eq = h_cnt[A + a];
+        const uint64_t idx0 = n_lt;                                           // lower_bound of val in the sorted samples
+        const bool first_is_eq = n_eq > 0;                                    // sorted[idx0] == val
         uint64_t idx = idx0;
         if (idx0 == l) idx = 1;
         else if (obs_eff[a] > exp_) {
