@@ -31,7 +31,7 @@ struct gatb_ctx {
     // tunables (env overrides, for profiling)
     uint32_t tile_budget = 0;
     int count_threads = 1024;
-    uint32_t schunk_max = 128;
+    uint32_t schunk_max = 256;
     // optional per-kernel timing (bench.py roofline): CUDA events around every launch
     bool profiling = false;
     struct Span { int cls; cudaEvent_t a, b; };
@@ -145,7 +145,7 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     ctx->count_threads = (int)std::min(1024u, std::max(32u, env_u32("GATB_COUNT_THREADS", 1024) / 32 * 32));
-    ctx->schunk_max = env_u32("GATB_SCHUNK", 128);
+    ctx->schunk_max = std::min(256u, std::max(32u, env_u32("GATB_SCHUNK", 256)));
     ctx->tile_budget = env_u32("GATB_TILE_BUDGET", 0);
     ctx->batch = env_u32("GATB_BATCH", 0);
     *out = ctx;
@@ -248,11 +248,13 @@ struct gatb_annotations {
 
 static inline uint64_t align16(uint64_t x) { return (x + 15u) & ~(uint64_t)15u; }
 
-// shared memory left for a staged filter under the most demanding launch (density accumulators)
+// shared memory left for a staged filter
 static uint32_t filter_budget(const gatb_ctx *ctx)
 {
     if (ctx->tile_budget) return ctx->tile_budget;
-    const size_t over = count_smem_overhead(ctx->count_threads, ctx->schunk_max, true) + 1024;
+    // sized for the integer counters; a nucleotide-density launch (larger accumulators) reads the
+    // few filters that no longer fit from global memory
+    const size_t over = count_smem_overhead(ctx->count_threads, ctx->schunk_max, false) + 1024;
     return (uint32_t)(ctx->smem_optin > over + 16384 ? ctx->smem_optin - over : 16384);
 }
 

@@ -16,19 +16,15 @@
 namespace gatb {
 
 constexpr uint32_t QCAP = 64;            // queue entries per warp; flushed whenever 32 are waiting
-struct __align__(16) QEntry { int s, e; uint32_t i, j; };   // segment, its index in the list, union start index
+struct __align__(16) QEntry { int s, e; uint32_t i, js; }; // segment, its index in the list, union start index | sample slot << 16
 
 size_t count_smem_overhead(int threads, uint32_t schunk, bool density)
 {
-    const size_t acc = ((size_t)schunk * KMAX * (density ? 16u : 4u) + 15u) & ~(size_t)15u;
-    return acc + (size_t)(threads / 32) * QCAP * sizeof(QEntry);
+    // integer accumulators [schunk][KMAX] (+ for density: (sum, compensation) doubles per slot)
+    const size_t acc = (size_t)schunk * KMAX * (density ? 20u : 4u);
+    return ((acc + 15u) & ~(size_t)15u) + (size_t)(threads / 32) * QCAP * sizeof(QEntry);
 }
 
-__device__ __forceinline__ void acc_add(uint32_t (&acc)[KMAX], uint32_t t, uint32_t r)
-{
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) acc[k] += ((uint32_t)k == t) ? r : 0u;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // Exact counts of one queued segment [s,e) against every track of the tile.  Coordinates are < 2^31,
@@ -42,17 +38,20 @@ __device__ __forceinline__ void acc_add(uint32_t (&acc)[KMAX], uint32_t t, uint3
 template <int COUNTER>
 __device__ __forceinline__ void resolve_entry(const uint8_t *__restrict__ filt, const uint8_t *__restrict__ tile_g,
                                               uint32_t uiv_off, uint32_t uoff_off, uint32_t cons_off,
-                                              const QEntry en, const uint64_t *__restrict__ segs,
-                                              uint32_t (&acc)[KMAX])
+                                              const QEntry en, const uint64_t *__restrict__ placed_key,
+                                              uint64_t sample_stride, uint32_t s_begin, uint32_t *__restrict__ acc_s)
 {
     const bool need_prev = (COUNTER == GATB_ANNOTATION_OVERLAP || COUNTER == GATB_ANNOTATION_MIDOVERLAP);
     const uint2 *uiv = reinterpret_cast<const uint2 *>(filt + uiv_off);
     const uint32_t *uoff = reinterpret_cast<const uint32_t *>(tile_g + uoff_off);
     const uint4 *cons = reinterpret_cast<const uint4 *>(tile_g + cons_off);
     const int s = en.s, e = en.e;
-    int pe = 0;
-    if (need_prev && en.i > 0) pe = (int)seg_end(segs[en.i - 1]);
-    uint32_t u = en.j;
+    const uint32_t slot = en.js >> 16;
+    uint32_t *acc = acc_s + slot * KMAX;            // shared accumulators of this sample: integer atomics,
+    int pe = 0;                                     // so the result does not depend on the order of arrival
+    if (need_prev && en.i > 0)
+        pe = (int)seg_end(placed_key[(uint64_t)(s_begin + slot) * sample_stride + en.i - 1]);
+    uint32_t u = en.js & 0xffffu;
     uint2 a = uiv[u];
     while ((int)a.y <= s) a = uiv[++u];         // first union interval with end > s; the sentinel stops the scan
     uint32_t seen = 0, hit = 0;
@@ -65,7 +64,7 @@ __device__ __forceinline__ void resolve_entry(const uint8_t *__restrict__ filt, 
             if ((int)v.y <= s) continue;
             const uint32_t t = v.z;
             if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
-                acc_add(acc, t, (uint32_t)(min(e, (int)v.y) - max(s, (int)v.x)));
+                atomicAdd(acc + t, (uint32_t)(min(e, (int)v.y) - max(s, (int)v.x)));
             } else if (COUNTER == GATB_SEGMENT_OVERLAP) {
                 hit |= 1u << t;
             } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
@@ -75,78 +74,94 @@ __device__ __forceinline__ void resolve_entry(const uint8_t *__restrict__ filt, 
                     if ((int)v.x <= mid && mid < (int)v.y) hit |= 1u << t;
                 }
             } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
-                if ((int)v.x >= pe) acc_add(acc, t, 1u);
+                if ((int)v.x >= pe) atomicAdd(acc + t, 1u);
             } else {
                 if ((int)v.x >= pe) {
                     const int m = (int)v.x + (((int)v.y - (int)v.x) >> 1);
-                    acc_add(acc, t, (s <= m && m < e) ? 1u : 0u);
+                    if (s <= m && m < e) atomicAdd(acc + t, 1u);
                 }
             }
         }
         a = uiv[++u];
     }
     if (COUNTER == GATB_SEGMENT_OVERLAP || COUNTER == GATB_SEGMENT_MIDOVERLAP) {
-#pragma unroll
-        for (int k = 0; k < KMAX; k++) acc[k] += (hit >> k) & 1u;
+        while (hit) {
+            const int t = __ffs(hit) - 1;
+            hit &= hit - 1;
+            atomicAdd(acc + t, 1u);
+        }
     }
 }
 
-// One sample's segments on one key against the tile.  `filt` points into shared memory (staged
-// filters) or global memory; the code is instantiated once per address space.  The next batch of
-// segments is loaded while the current one is processed.
+// All samples of one warp on one key against the tile.  `filt` points into shared memory (staged
+// filters) or global memory; the code is instantiated once per address space.  Segments are loaded two
+// batches ahead; the queue is carried across the warp's samples and drained once per key.
 template <int COUNTER, bool INDEXED>
-__device__ __forceinline__ void count_sample(const uint8_t *__restrict__ filt, const uint8_t *__restrict__ tile_g,
-                                             const TileHeader &h, const uint64_t *__restrict__ segs, uint32_t n,
-                                             int lane, QEntry *__restrict__ queue, uint32_t (&acc)[KMAX])
+__device__ __forceinline__ void count_key(const uint8_t *__restrict__ filt, const uint8_t *__restrict__ tile_g,
+                                          const TileHeader &h, const CountParams &p, uint32_t k,
+                                          uint32_t s_begin, uint32_t s_end, int lane, int warp, int nwarps,
+                                          QEntry *__restrict__ queue, uint32_t *__restrict__ acc_s)
 {
     const uint2 *uiv = reinterpret_cast<const uint2 *>(filt + h.uiv_off);
     const uint16_t *idx = reinterpret_cast<const uint16_t *>(filt + h.idx_off);
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint64_t *placed_key = p.placed + p.key_base[k];
     uint32_t qn = 0;                                                   // warp-uniform queue fill
-    uint64_t xnext = ((uint32_t)lane < n) ? segs[lane] : 0;
-    for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-        const uint32_t i = b0 + lane;
-        const uint64_t x = xnext;
-        xnext = (i + 32 < n) ? segs[i + 32] : 0;                      // software prefetch of the next batch
-        const int s = (int)seg_start(x), e = (int)seg_end(x);
-        bool flag = false;
-        uint32_t j = 0;
-        if (i < n) {
-            if (INDEXED) {
-                j = idx[min(__umulhi((uint32_t)s, h.inv), h.nbins)];
-            } else {
-                uint32_t lo = 0, hi = h.n_union;                       // lower_bound (utils/gat_utils.c:8-32)
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if ((int)uiv[mid].y <= s) lo = mid + 1; else hi = mid;
+    for (uint32_t sl = s_begin + warp; sl < s_end; sl += nwarps) {
+        if (p.key_present && !p.key_present[(uint64_t)sl * p.n_keys + k]) continue;
+        const uint32_t n = p.placed_n[(uint64_t)sl * p.n_keys + k];
+        if (n == 0) continue;
+        const uint64_t *segs = placed_key + (uint64_t)sl * p.sample_stride;
+        const uint32_t slot16 = (sl - s_begin) << 16;
+        uint64_t x1 = ((uint32_t)lane < n) ? segs[lane] : 0;           // batch b0
+        uint64_t x2 = ((uint32_t)lane + 32 < n) ? segs[lane + 32] : 0; // batch b0 + 32
+        for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+            const uint32_t i = b0 + lane;
+            const uint64_t x = x1;
+            x1 = x2;
+            x2 = (i + 64 < n) ? segs[i + 64] : 0;                     // software prefetch, two batches ahead
+            const int s = (int)seg_start(x), e = (int)seg_end(x);
+            bool flag = false;
+            uint32_t j = 0;
+            if (i < n) {
+                if (INDEXED) {
+                    j = idx[min(__umulhi((uint32_t)s, h.inv), h.nbins)];
+                } else {
+                    uint32_t lo = 0, hi = h.n_union;                   // lower_bound (utils/gat_utils.c:8-32)
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if ((int)uiv[mid].y <= s) lo = mid + 1; else hi = mid;
+                    }
+                    j = lo;
                 }
-                j = lo;
+                const uint2 c0 = uiv[j], c1 = uiv[j + 1];
+                const bool skip = (int)c0.y <= s;
+                const int ax = (int)(skip ? c1.x : c0.x);
+                // more than one union interval ends inside the bin before s: let the exact pass scan
+                flag = (skip && (int)c1.y <= s) || (ax < e);
             }
-            const uint2 c0 = uiv[j], c1 = uiv[j + 1];
-            const bool skip = (int)c0.y <= s;
-            const int ax = (int)(skip ? c1.x : c0.x);
-            // more than one union interval ends inside the bin before s: let the exact pass scan
-            flag = (skip && (int)c1.y <= s) || (ax < e);
-        }
-        const uint32_t m = __ballot_sync(GATB_FULL, flag);
-        if (m) {
-            if (flag) {
-                QEntry en;
-                en.s = s; en.e = e; en.i = i; en.j = j;
-                queue[qn + __popc(m & lt_mask)] = en;
-            }
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32) {
-                qn -= 32;
-                resolve_entry<COUNTER>(filt, tile_g, h.uiv_off, h.uoff_off, h.cons_off, queue[qn + lane], segs, acc);
+            const uint32_t m = __ballot_sync(GATB_FULL, flag);
+            if (m) {
+                if (flag) {
+                    QEntry en;
+                    en.s = s; en.e = e; en.i = i; en.js = j | slot16;
+                    queue[qn + __popc(m & lt_mask)] = en;
+                }
+                qn += __popc(m);
                 __syncwarp();
+                if (qn >= 32) {
+                    qn -= 32;
+                    resolve_entry<COUNTER>(filt, tile_g, h.uiv_off, h.uoff_off, h.cons_off, queue[qn + lane],
+                                           placed_key, p.sample_stride, s_begin, acc_s);
+                    __syncwarp();
+                }
             }
         }
     }
-    if (qn) {                                                          // drain: acc is per sample
+    if (qn) {                                                          // drain once per key
         if ((uint32_t)lane < qn)
-            resolve_entry<COUNTER>(filt, tile_g, h.uiv_off, h.uoff_off, h.cons_off, queue[lane], segs, acc);
+            resolve_entry<COUNTER>(filt, tile_g, h.uiv_off, h.uoff_off, h.cons_off, queue[lane],
+                                   placed_key, p.sample_stride, s_begin, acc_s);
         __syncwarp();
     }
 }
@@ -155,10 +170,11 @@ template <int COUNTER, bool DENSITY>
 __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    // layout: [acc: schunk*KMAX*(DENSITY?16:4) bytes][per-warp queues][filter]; density keeps
-    // (sum, compensation) per slot
-    const uint32_t acc_bytes = (p.schunk * KMAX * (DENSITY ? 16u : 4u) + 15u) & ~15u;
-    uint32_t *acc_u = reinterpret_cast<uint32_t *>(smem);
+    // layout: [acc_u: schunk*KMAX u32][density only: acc_d: schunk*KMAX (sum, compensation) doubles]
+    //         [per-warp queues][filter]
+    const uint32_t nslots = p.schunk * KMAX;
+    const uint32_t acc_bytes = (nslots * (DENSITY ? 20u : 4u) + 15u) & ~15u;
+    uint32_t *acc_u = reinterpret_cast<uint32_t *>(smem + (DENSITY ? nslots * 16u : 0u));
     double *acc_d = reinterpret_cast<double *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     QEntry *queue = reinterpret_cast<QEntry *>(smem + acc_bytes) + (size_t)warp * QCAP;
@@ -170,8 +186,9 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
     const uint32_t s_begin = blockIdx.y * p.schunk;
     const uint32_t s_end = min(s_begin + p.schunk, p.n_samples);
 
-    for (uint32_t i = threadIdx.x; i < p.schunk * KMAX; i += blockDim.x) {
-        if (DENSITY) { acc_d[2 * i] = 0.0; acc_d[2 * i + 1] = 0.0; } else acc_u[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < nslots; i += blockDim.x) {
+        acc_u[i] = 0u;
+        if (DENSITY) { acc_d[2 * i] = 0.0; acc_d[2 * i + 1] = 0.0; }
     }
 
     for (uint32_t k = 0; k < p.n_keys; k++) {
@@ -180,6 +197,7 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
         const bool staged = p.tile_stage[(uint64_t)g * p.n_keys + k] <= p.smem_tile_budget;
         __syncthreads();                                  // previous filter fully consumed / acc init
         if (h.n_union == 0) continue;                     // no interval of any track on this key
+        if (DENSITY && p.key_ws_nseg[k] == 0) continue;   // counter returns 0 (gat/Engine.pyx:1438-1440)
         if (staged) {
             // header + bin index + the union intervals actually present (+ 2 sentinels)
             const uint32_t bytes = (h.uiv_off + (h.n_union + 2) * 8 + 15u) & ~15u;
@@ -188,39 +206,26 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
             for (uint32_t i = threadIdx.x; i < (bytes >> 4); i += blockDim.x) dst[i] = src[i];
             __syncthreads();
         }
-        if (DENSITY && p.key_ws_nseg[k] == 0) continue;   // counter returns 0 (gat/Engine.pyx:1438-1440)
-        const double den = DENSITY ? (double)p.key_ws_nseg[k] : 1.0;
-
-        for (uint32_t sl = s_begin + warp; sl < s_end; sl += nwarps) {
-            if (p.key_present && !p.key_present[(uint64_t)sl * p.n_keys + k]) continue;
-            const uint32_t n = p.placed_n[(uint64_t)sl * p.n_keys + k];
-            if (n == 0) continue;
-            const uint64_t *segs = p.placed + (uint64_t)sl * p.sample_stride + p.key_base[k];
-            uint32_t acc[KMAX];
-#pragma unroll
-            for (int kk = 0; kk < KMAX; kk++) acc[kk] = 0;
-            if (staged) {
-                if (h.nbins) count_sample<COUNTER, true>(filt_s, tile_g, h, segs, n, lane, queue, acc);
-                else count_sample<COUNTER, false>(filt_s, tile_g, h, segs, n, lane, queue, acc);
-            } else {
-                if (h.nbins) count_sample<COUNTER, true>(tile_g, tile_g, h, segs, n, lane, queue, acc);
-                else count_sample<COUNTER, false>(tile_g, tile_g, h, segs, n, lane, queue, acc);
-            }
-            uint32_t mine = 0;
-#pragma unroll
-            for (int kk = 0; kk < KMAX; kk++) {
-                uint32_t tot = __reduce_add_sync(GATB_FULL, acc[kk]);
-                if (lane == kk) mine = tot;
-            }
-            if ((uint32_t)lane < ka) {
-                const uint32_t slot = (sl - s_begin) * KMAX + lane;
-                if (DENSITY) {
-                    // float(overlap) / len(workspace), accumulated like the reference's Python sum():
-                    // CPython >= 3.12 sums floats with Neumaier compensation (Python/bltinmodule.c)
-                    const double x = (double)mine / den, f = acc_d[2 * slot], t = f + x;
-                    acc_d[2 * slot + 1] += (fabs(f) >= fabs(x)) ? ((f - t) + x) : ((x - t) + f);
-                    acc_d[2 * slot] = t;
-                } else acc_u[slot] += mine;
+        if (staged) {
+            if (h.nbins) count_key<COUNTER, true>(filt_s, tile_g, h, p, k, s_begin, s_end, lane, warp, nwarps, queue, acc_u);
+            else count_key<COUNTER, false>(filt_s, tile_g, h, p, k, s_begin, s_end, lane, warp, nwarps, queue, acc_u);
+        } else {
+            if (h.nbins) count_key<COUNTER, true>(tile_g, tile_g, h, p, k, s_begin, s_end, lane, warp, nwarps, queue, acc_u);
+            else count_key<COUNTER, false>(tile_g, tile_g, h, p, k, s_begin, s_end, lane, warp, nwarps, queue, acc_u);
+        }
+        if (DENSITY) {
+            // per key: float(overlap) / len(workspace), accumulated in key order like the reference's
+            // Python sum(): CPython >= 3.12 sums floats with Neumaier compensation (Python/bltinmodule.c)
+            __syncthreads();
+            const double den = (double)p.key_ws_nseg[k];
+            for (uint32_t i = threadIdx.x; i < nslots; i += blockDim.x) {
+                const uint32_t v = acc_u[i];
+                if (v) {
+                    const double x = (double)v / den, f = acc_d[2 * i], t = f + x;
+                    acc_d[2 * i + 1] += (fabs(f) >= fabs(x)) ? ((f - t) + x) : ((x - t) + f);
+                    acc_d[2 * i] = t;
+                    acc_u[i] = 0u;
+                }
             }
         }
     }
