@@ -458,7 +458,10 @@ extern "C" int gatb_count_lists(gatb_ctx *ctx, const gatb_annotations *annos, in
         for (uint32_t k = 0; k < K; k++)
             cap[k] = std::max<uint32_t>(cap[k], (uint32_t)(offs[s * K + k + 1] - offs[s * K + k]));
     uint64_t stride = 0;
-    for (uint32_t k = 0; k < K; k++) { key_base[k] = stride; stride += cap[k]; }
+    for (uint32_t k = 0; k < K; k++) {
+        if (cap[k] >= (1u << 24)) return fail(ctx, GATB_ERR_INVALID, "count_lists: 2^24 or more segments on one key");
+        key_base[k] = stride; stride += cap[k];
+    }
     if (stride == 0) stride = 1;
     std::vector<uint64_t> packed(n_samples * stride, 0);
     std::vector<uint32_t> counts(n_samples * K);
@@ -649,6 +652,11 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
         s->placed_stride = b;
         s->unit_stride = 0;
     }
+    for (uint32_t c = 0; c < C; c++)
+        if (s->h_contig_cap[c] > (1u << 24)) {
+            delete s;
+            return fail(ctx, GATB_ERR_INVALID, "sampler: more than 2^23 segments on one contig");
+        }
     std::vector<uint32_t> order(U);
     for (uint32_t u = 0; u < U; u++) order[u] = u;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return s->h_units[a].tab_n > s->h_units[b].tab_n; });

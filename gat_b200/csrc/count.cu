@@ -16,7 +16,7 @@
 namespace gatb {
 
 constexpr uint32_t QCAP = 64;            // queue entries per warp; flushed whenever 32 are waiting
-struct __align__(16) QEntry { int s, e; uint32_t i, js; }; // segment, its index in the list, union start index | sample slot << 16
+struct __align__(16) QEntry { int s, e; uint32_t is, j; }; // segment; its index in the list (< 2^24) | sample slot << 24; union start index
 
 size_t count_smem_overhead(int threads, uint32_t schunk, bool density)
 {
@@ -46,12 +46,12 @@ __device__ __forceinline__ void resolve_entry(const uint8_t *__restrict__ filt, 
     const uint32_t *uoff = reinterpret_cast<const uint32_t *>(tile_g + uoff_off);
     const uint4 *cons = reinterpret_cast<const uint4 *>(tile_g + cons_off);
     const int s = en.s, e = en.e;
-    const uint32_t slot = en.js >> 16;
+    const uint32_t slot = en.is >> 24, i = en.is & 0xffffffu;
     uint32_t *acc = acc_s + slot * KMAX;            // shared accumulators of this sample: integer atomics,
     int pe = 0;                                     // so the result does not depend on the order of arrival
-    if (need_prev && en.i > 0)
-        pe = (int)seg_end(placed_key[(uint64_t)(s_begin + slot) * sample_stride + en.i - 1]);
-    uint32_t u = en.js & 0xffffu;
+    if (need_prev && i > 0)
+        pe = (int)seg_end(placed_key[(uint64_t)(s_begin + slot) * sample_stride + i - 1]);
+    uint32_t u = en.j;
     uint2 a = uiv[u];
     while ((int)a.y <= s) a = uiv[++u];         // first union interval with end > s; the sentinel stops the scan
     uint32_t seen = 0, hit = 0;
@@ -112,7 +112,7 @@ __device__ __forceinline__ void count_key(const uint8_t *__restrict__ filt, cons
         const uint32_t n = p.placed_n[(uint64_t)sl * p.n_keys + k];
         if (n == 0) continue;
         const uint64_t *segs = placed_key + (uint64_t)sl * p.sample_stride;
-        const uint32_t slot16 = (sl - s_begin) << 16;
+        const uint32_t slot24 = (sl - s_begin) << 24;
         uint64_t x1 = ((uint32_t)lane < n) ? segs[lane] : 0;           // batch b0
         uint64_t x2 = ((uint32_t)lane + 32 < n) ? segs[lane + 32] : 0; // batch b0 + 32
         for (uint32_t b0 = 0; b0 < n; b0 += 32) {
@@ -144,7 +144,7 @@ __device__ __forceinline__ void count_key(const uint8_t *__restrict__ filt, cons
             if (m) {
                 if (flag) {
                     QEntry en;
-                    en.s = s; en.e = e; en.i = i; en.js = j | slot16;
+                    en.s = s; en.e = e; en.is = i | slot24; en.j = j;
                     queue[qn + __popc(m & lt_mask)] = en;
                 }
                 qn += __popc(m);

@@ -141,3 +141,70 @@ def test_column_stats_float_and_reference(ctx, oracle):
         assert got_ref["pvalue"][a] == st.pvalue
         assert got_ref["expected"][a] == pytest.approx(st.expected, rel=1e-13)
         assert got_ref["lower95"][a] == st.lower95 and got_ref["upper95"][a] == st.upper95
+
+
+def _fallback_problem(rng, oracle, big_list=False):
+    """random lists; with big_list one track has > 65534 intervals on a key (no bin index possible)"""
+    K, A, S = 2, 11, 3
+    span = 4000000 if big_list else 300000
+    annos = [[helpers.random_list(rng, span, int(rng.integers(0, 150)), 900) for _ in range(K)] for _ in range(A)]
+    if big_list:
+        starts = np.arange(0, 70000, dtype=np.int64) * 50
+        annos[3][1] = np.stack([starts, starts + rng.integers(1, 40, len(starts))], axis=1).astype(np.uint32)
+    nseg = [2, 3]
+    samples = [[helpers.random_list(rng, span, int(rng.integers(1, 400)), int(rng.choice([30, 700, 9000]))) for _ in range(K)]
+               for _ in range(S)]
+    return annos, nseg, samples
+
+
+def test_count_fallback_paths_match_oracle(ctx, oracle, monkeypatch):
+    """the slow-but-general code paths of the count kernel: filters read from global memory (tile budget
+    forced tiny), unions without a bin index (> 65534 intervals), groups with fewer than 8 tracks"""
+    from gat_b200 import device
+    rng = np.random.default_rng(77)
+    for big_list, budget in ((False, "256"), (True, "0"), (True, "256")):
+        annos, nseg, samples = _fallback_problem(rng, oracle, big_list)
+        if budget != "0":
+            monkeypatch.setenv("GATB_TILE_BUDGET", budget)
+        else:
+            monkeypatch.delenv("GATB_TILE_BUDGET", raising=False)
+        c2 = device.Context(0)                       # the budget is read when the context is created
+        an = device.Annotations(c2, annos, key_ws_nseg=nseg)
+        got = an.count_lists(COUNTERS, samples)
+        an.close()
+        c2.close()
+        for s in range(len(samples)):
+            exp = oracle.count_placed(samples[s], annos, nseg, COUNTERS)
+            assert np.array_equal(got[:, s, :], exp), (big_list, budget, s)
+    monkeypatch.delenv("GATB_TILE_BUDGET", raising=False)
+
+
+def test_invalid_inputs_fail_loudly(ctx):
+    """error behaviour at the boundary: non-normalized lists, out-of-range coordinates, too-large segments"""
+    from gat_b200 import device, _lib
+    good = np.array([[10, 20], [30, 40]], dtype=np.uint32)
+    with pytest.raises(_lib.GatB200Error) as e:
+        device.Annotations(ctx, [[np.array([[10, 20], [15, 40]], dtype=np.uint32)]])      # overlapping
+    assert e.value.code == _lib.ERR_INVALID
+    with pytest.raises(_lib.GatB200Error) as e:
+        device.Annotations(ctx, [[np.array([[10, 2 ** 31 + 5]], dtype=np.uint32)]])        # coordinate >= 2^31
+    assert e.value.code == _lib.ERR_RANGE
+    with pytest.raises(_lib.GatB200Error) as e:
+        device.Sampler(ctx, [0], 1, False, [np.array([[30, 40], [10, 20]], dtype=np.uint32)], [good])   # unsorted
+    assert e.value.code == _lib.ERR_INVALID
+    with pytest.raises(_lib.GatB200Error) as e:
+        device.Sampler(ctx, [0, 0], 1, False, [good, good], [good, good])                   # 2 units, no isochores
+    assert e.value.code == _lib.ERR_INVALID
+    with pytest.raises(_lib.GatB200Error) as e:
+        device.Sampler(ctx, [0], 1, False, [np.array([[0, 5000]], dtype=np.uint32)],
+                       [np.array([[0, 100000]], dtype=np.uint32)], bucket_size=1, nbuckets=1000)
+    assert e.value.code == _lib.ERR_TOO_LARGE
+    an = device.Annotations(ctx, [[good]])
+    with pytest.raises(_lib.GatB200Error):
+        an.count_lists(["nucleotide-density"], [[good]])          # density needs key_ws_nseg
+    an.close()
+    # empty annotation tracks and empty samples are fine
+    an = device.Annotations(ctx, [[np.zeros((0, 2), dtype=np.uint32)], [good]], key_ws_nseg=[1])
+    out = an.count_lists(COUNTERS, [[good], [np.zeros((0, 2), dtype=np.uint32)]])
+    assert out[0, 0, 0] == 0 and out[0, 0, 1] == 20 and (out[:, 1, :] == 0).all()
+    an.close()
