@@ -109,59 +109,57 @@ __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m)
 
 // ---------------------------------------------------------------------------------------------------
 // Warp bitonic sort of N = 2^k packed segments (ascending).  Strides >= 32 exchange through memory,
-// strides < 32 run in registers with shuffles (one load + one store per 32-element block and k-phase).
+// strides < 32 run in registers with shuffles: the phases k = 2..32 take ONE load/store pass per
+// 32-element block, every later phase one more.  The packed keys are a total order (start, then end),
+// so both lanes of a compare-exchange agree on the outcome.
 // Replaces SegmentList.sort() (gat/SegmentList.pyx:478-486, libc qsort by start).
+__device__ __forceinline__ uint64_t cmpxchg_lane(uint64_t x, int lane, uint32_t jj, bool asc)
+{
+    const uint64_t y = shfl_xor_u64(x, (int)jj);
+    const bool keep_min = (((lane & jj) == 0) == asc);
+    return ((x > y) == keep_min) ? y : x;          // take the partner's key iff it is the one to keep
+}
+
 __device__ __forceinline__ void warp_bitonic_sort(uint64_t *buf, uint32_t N)
 {
     const int lane = lane_id();
     if (N <= 1) return;
-    for (uint32_t k = 2; k <= N; k <<= 1) {
-        uint32_t j = k >> 1;
-        for (; j >= 32; j >>= 1) {
+    // phases k = 2 .. min(N, 32): entirely inside aligned 32-element blocks
+    for (uint32_t b0 = 0; b0 < N; b0 += 32) {
+        const uint32_t i = b0 + lane;
+        uint64_t x = (i < N) ? buf[i] : GATB_KEY_INF;   // N < 32: idle lanes carry +inf and never move below N
+#pragma unroll
+        for (uint32_t k = 2; k <= 32; k <<= 1) {
+            if (k <= N) {
+                const bool asc = ((i & k) == 0);
+#pragma unroll
+                for (uint32_t jj = 16; jj > 0; jj >>= 1)
+                    if (jj < k) x = cmpxchg_lane(x, lane, jj, asc);
+            }
+        }
+        if (i < N) buf[i] = x;
+    }
+    __syncwarp();
+    for (uint32_t k = 64; k <= N; k <<= 1) {
+        for (uint32_t j = k >> 1; j >= 32; j >>= 1) {
             for (uint32_t t = lane; t < (N >> 1); t += 32) {
-                uint32_t i = 2 * t - (t & (j - 1));
-                uint32_t p = i + j;
-                uint64_t a = buf[i], b = buf[p];
-                bool asc = ((i & k) == 0);
+                const uint32_t i = 2 * t - (t & (j - 1));
+                const uint32_t p = i + j;
+                const uint64_t a = buf[i], b = buf[p];
+                const bool asc = ((i & k) == 0);
                 if ((a > b) == asc) { buf[i] = b; buf[p] = a; }
             }
             __syncwarp();
         }
-        // register phase: strides min(k/2,16) .. 1 inside each aligned block of 32
-        if (N >= 32) {
-            for (uint32_t b0 = 0; b0 < N; b0 += 32) {
-                uint32_t i = b0 + lane;
-                uint64_t x = buf[i];
-                bool asc = ((i & k) == 0);
+        for (uint32_t b0 = 0; b0 < N; b0 += 32) {       // strides 16 .. 1 in registers
+            const uint32_t i = b0 + lane;
+            uint64_t x = buf[i];
+            const bool asc = ((i & k) == 0);
 #pragma unroll
-                for (uint32_t jj = 16; jj > 0; jj >>= 1) {
-                    if (jj <= j) {
-                        uint64_t y = shfl_xor_u64(x, jj);
-                        bool lower = ((lane & jj) == 0);
-                        bool keep_min = (lower == asc);
-                        x = keep_min ? (x < y ? x : y) : (x > y ? x : y);
-                    }
-                }
-                buf[i] = x;
-            }
-            __syncwarp();
-        } else {
-            // N < 32: a single partial block; lanes >= N carry +inf and never move below N
-            uint32_t i = lane;
-            uint64_t x = (i < N) ? buf[i] : GATB_KEY_INF;
-            bool asc = ((i & k) == 0);
-#pragma unroll
-            for (uint32_t jj = 16; jj > 0; jj >>= 1) {
-                if (jj <= j) {
-                    uint64_t y = shfl_xor_u64(x, jj);
-                    bool lower = ((lane & jj) == 0);
-                    bool keep_min = (lower == asc);
-                    x = keep_min ? (x < y ? x : y) : (x > y ? x : y);
-                }
-            }
-            if (i < N) buf[i] = x;
-            __syncwarp();
+            for (uint32_t jj = 16; jj > 0; jj >>= 1) x = cmpxchg_lane(x, lane, jj, asc);
+            buf[i] = x;
         }
+        __syncwarp();
     }
 }
 
@@ -230,9 +228,7 @@ __device__ __forceinline__ uint32_t warp_insert_merge0(uint64_t *buf, uint32_t n
     for (uint32_t k = 2; k <= 32; k <<= 1) {
 #pragma unroll
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            const uint64_t y = shfl_xor_u64(key, (int)j);
-            const bool asc = ((lane & k) == 0), lower = ((lane & j) == 0);
-            key = (lower == asc) ? (key < y ? key : y) : (key > y ? key : y);
+            key = cmpxchg_lane(key, lane, j, (lane & k) == 0);
         }
     }
     // insertion point of each new key in U: number of U elements <= key (ties keep U first)
