@@ -134,11 +134,15 @@ __device__ __forceinline__ void count_key(const uint8_t *__restrict__ filt, cons
                     }
                     j = lo;
                 }
-                const uint2 c0 = uiv[j], c1 = uiv[j + 1];
-                const bool skip = (int)c0.y <= s;
-                const int ax = (int)(skip ? c1.x : c0.x);
-                // more than one union interval ends inside the bin before s: let the exact pass scan
-                flag = (skip && (int)c1.y <= s) || (ax < e);
+                const uint2 c0 = uiv[j];
+                int ax = (int)c0.x;
+                bool more = false;
+                if ((int)c0.y <= s) {               // (~1 lane in 6) the candidate ends before s: take the next one
+                    const uint2 c1 = uiv[j + 1];
+                    ax = (int)c1.x;
+                    more = (int)c1.y <= s;          // still not past s: let the exact pass scan
+                }
+                flag = more || (ax < e);
             }
             const uint32_t m = __ballot_sync(GATB_FULL, flag);
             if (m) {
