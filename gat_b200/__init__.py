@@ -127,11 +127,21 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
 
     ctx = getContext()
     rank, world = parallel.rank_world()
+    import os
+    import sys
+    import time
+    timing = [("start", time.perf_counter())] if os.environ.get("GATB_TIMING") else None
+
+    def mark(name):
+        if timing is not None:
+            torch.cuda.synchronize(ctx.device)
+            timing.append((name, time.perf_counter()))
 
     # observed counts (gat/__init__.py:932-940)
     observed_counts = [Engine.computeCounts(counter=c, aggregator=sum, segments=segments,
                                             annotations=annotations, workspace=workspace,
                                             workspace_generator=workspace_generator) for c in counters]
+    mark("observed")
 
     sampled = {}
     annos_cache = {}
@@ -146,6 +156,7 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
             sampled[track] = (atracks, None, None, None)
             continue
         out_u, out_f, ids = out
+        mark("sampling")
         # one collective: all-gather the S/G x A slabs of every counter
         out_u = parallel.allgather_samples(out_u, num_samples, dim=1)
         if out_f is not None:
@@ -155,6 +166,7 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
             _dumpSamples(track, ntrack, segs, workspace, sampler, num_samples, output_samples_pattern)
     for a in annos_cache.values():
         a.close()
+    mark("allgather")
 
     # statistics per (counter, track): one batched column-stats call over all annotations
     annotator_results = []
@@ -207,6 +219,10 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
                     outfile.write("%s\t%s\t%i\t%s\n" % (o.track, o.annotation, o.observed,
                                                         ",".join(["%i" % x for x in o.samples])))
     torch.cuda.synchronize(ctx.device)
+    mark("statistics+results")
+    if timing is not None and rank == 0:
+        sys.stderr.write("# gat_b200.run phases: " + ", ".join(
+            "%s %.3fs" % (timing[i][0], timing[i][1] - timing[i - 1][1]) for i in range(1, len(timing))) + "\n")
     return annotator_results
 
 

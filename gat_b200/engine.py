@@ -474,17 +474,16 @@ class AnnotatorResult(object):
         self.annotation = annotation
         self.counter = counter
         self.observed = float(observed)
-        self._samples = np.array(samples, dtype=np.float64)
-        self.nsamples = len(self._samples)
+        # the samples stay in whatever array they arrive in (a strided uint32 column of the S x A count
+        # matrix when built by gat_b200.run) and are converted to float64 only when asked for
+        self._source = samples if isinstance(samples, np.ndarray) else np.array(samples, dtype=np.float64)
+        self.nsamples = len(self._source)
         self.format_observed = "%i"
         self.qvalue = 1.0
         if self.nsamples < 1:
             raise ValueError("no samples")
         if stats is None:
-            is_int = bool(np.all(self._samples == np.floor(self._samples)) and self._samples.min() >= 0
-                          and self._samples.max() < 2 ** 32)
-            col = self._samples.reshape(-1, 1)
-            col = col.astype(np.uint32) if is_int else col
+            col = self._column()
             ref = None if reference is None else [reference.fold]
             st = getContext().column_stats(col, [self.observed], pseudo_count=pseudo_count, ref_fold=ref)
             stats = dict((k, float(v[0])) for k, v in st.items())
@@ -495,18 +494,25 @@ class AnnotatorResult(object):
         self.fold = stats["fold"]
         self.pvalue = stats["pvalue"]
 
+    def _column(self):
+        """the samples as an (n,1) uint32 (integer counters) or float64 column for gatb_column_stats"""
+        a = self._source
+        if a.dtype.kind in "ui":
+            return np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, 1)
+        a = np.asarray(a, dtype=np.float64)
+        if np.all(a == np.floor(a)) and a.min() >= 0 and a.max() < 2 ** 32:
+            return np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, 1)
+        return np.ascontiguousarray(a).reshape(-1, 1)
+
     @property
     def samples(self):
-        return self._samples.copy()
+        return np.array(self._source, dtype=np.float64)
 
     def getSample(self, sample_id):
-        return self._samples[sample_id]
+        return float(self._source[sample_id])
 
     def getEmpiricalPValue(self, value):
-        is_int = bool(np.all(self._samples == np.floor(self._samples)))
-        col = self._samples.reshape(-1, 1)
-        col = col.astype(np.uint32) if is_int else col
-        st = getContext().column_stats(col, [float(value)])
+        st = getContext().column_stats(self._column(), [float(value)])
         # the reference compares against the stored expected value (gat/Engine.pyx:1556)
         return float(st["pvalue"][0])
 
