@@ -18,6 +18,50 @@ namespace gatb {
 constexpr uint32_t QCAP = 64;            // queue entries per warp; flushed whenever 32 are waiting
 struct __align__(16) QEntry { int s, e; uint32_t is, j; }; // segment; its index in the list (< 2^24) | sample slot << 24; union start index
 
+// ---------------------------------------------------------------------------------------------------
+// TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers for the filter staging
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
 size_t count_smem_overhead(int threads, uint32_t schunk, bool density)
 {
     // integer accumulators [schunk][KMAX] (+ for density: (sum, compensation) doubles per slot)
@@ -194,6 +238,9 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
         acc_u[i] = 0u;
         if (DENSITY) { acc_d[2 * i] = 0.0; acc_d[2 * i + 1] = 0.0; }
     }
+    __shared__ __align__(8) uint64_t stage_bar;           // mbarrier of the filter staging (one arrival + tx bytes)
+    uint32_t stage_phase = 0;
+    if (threadIdx.x == 0) mbar_init(&stage_bar, 1);
 
     for (uint32_t k = 0; k < p.n_keys; k++) {
         const uint8_t *tile_g = p.tiles + p.tile_off[(uint64_t)g * p.n_keys + k];
@@ -203,12 +250,22 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
         if (h.n_union == 0) continue;                     // no interval of any track on this key
         if (DENSITY && p.key_ws_nseg[k] == 0) continue;   // counter returns 0 (gat/Engine.pyx:1438-1440)
         if (staged) {
-            // header + bin index + the union intervals actually present (+ 2 sentinels)
+            // header + bin index + the union intervals actually present (+ 2 sentinels): ONE bulk copy
+            // by the TMA engine (cp.async.bulk, 1-D), completion signalled on an mbarrier; meanwhile the
+            // next key's filter is prefetched into L2
             const uint32_t bytes = (h.uiv_off + (h.n_union + 2) * 8 + 15u) & ~15u;
-            const uint4 *src = reinterpret_cast<const uint4 *>(tile_g);
-            uint4 *dst = reinterpret_cast<uint4 *>(filt_s);
-            for (uint32_t i = threadIdx.x; i < (bytes >> 4); i += blockDim.x) dst[i] = src[i];
-            __syncthreads();
+            if (threadIdx.x == 0) {
+                fence_proxy_async();                          // order earlier generic reads of filt_s before the async write
+                mbar_expect_tx(&stage_bar, bytes);
+                bulk_copy_g2s(filt_s, tile_g, bytes, &stage_bar);
+                if (k + 1 < p.n_keys) {
+                    const uint32_t nb = p.tile_stage[(uint64_t)g * p.n_keys + k + 1];
+                    if (nb <= p.smem_tile_budget)
+                        bulk_prefetch_l2(p.tiles + p.tile_off[(uint64_t)g * p.n_keys + k + 1], nb);
+                }
+            }
+            mbar_wait(&stage_bar, stage_phase);
+            stage_phase ^= 1u;
         }
         if (staged) {
             if (h.nbins) count_key<COUNTER, true>(filt_s, tile_g, h, p, k, s_begin, s_end, lane, warp, nwarps, queue, acc_u);
