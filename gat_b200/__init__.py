@@ -15,7 +15,7 @@ import numpy as np
 from . import device
 from . import engine as Engine
 from . import stats as Stats
-from .engine import (IntervalCollection, IntervalDictionary, SamplerAnnotator, UnconditionalWorkspace,
+from .engine import (IntervalCollection, IntervalDictionary, SamplerAnnotator, SamplerSegments, UnconditionalWorkspace,
                      AnnotatorResult, AnnotatorResultExtended, getContext, seed)
 from .segmentlist import SegmentList
 
@@ -87,6 +87,11 @@ def sampleTrack(track_index, segs, annotations, workspace, sampler, counters, nu
         if e.code == device._lib.ERR_TOO_LARGE:
             raise ValueError(str(e))
         raise
+    if getattr(sampler, "kind", "annotator") != "annotator":
+        try:
+            smp.set_kind(sampler.kind)
+        except device._lib.GatB200Error as e:
+            raise AssertionError(str(e))       # the reference's counters assert on unnormalized samples
     begin, end = sample_range if sample_range is not None else (0, num_samples)
     n_local = end - begin
     dev = torch.device("cuda", ctx.device)

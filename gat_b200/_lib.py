@@ -19,7 +19,7 @@ SYMBOLS = [
     "gatb_synchronize", "gatb_launch_count", "gatb_set_batch_size", "gatb_profile", "gatb_profile_read",
     "gatb_annotations_create", "gatb_annotations_destroy", "gatb_count_lists",
     "gatb_sampler_create", "gatb_sampler_destroy", "gatb_sampler_sample_capacity",
-    "gatb_sampler_place", "gatb_run", "gatb_column_stats",
+    "gatb_sampler_set_kind", "gatb_sampler_place", "gatb_run", "gatb_column_stats",
 ]
 
 
@@ -77,6 +77,8 @@ def load():
     L.gatb_sampler_destroy.argtypes = [vp]
     L.gatb_sampler_sample_capacity.restype = u64
     L.gatb_sampler_sample_capacity.argtypes = [vp]
+    L.gatb_sampler_set_kind.restype = i32
+    L.gatb_sampler_set_kind.argtypes = [vp, i32]
     L.gatb_sampler_place.restype = i32
     L.gatb_sampler_place.argtypes = [vp, u64, u32, u64, u64, vp, vp, vp, vp, vp]
     L.gatb_run.restype = i32

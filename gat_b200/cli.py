@@ -157,9 +157,12 @@ def fromSegments(options, log=None):
         restrict_workspace=options.restrict_workspace)
     if log:
         log("intervals loaded in %.1f seconds" % (time.time() - t0))
-    if options.sampler != "annotator":
-        raise NotImplementedError("--sampler=%s is not accelerated by gat_b200 (use annotator)" % options.sampler)
-    sampler = Engine.SamplerAnnotator(bucket_size=options.bucket_size, nbuckets=options.nbuckets)
+    if options.sampler == "annotator":
+        sampler = Engine.SamplerAnnotator(bucket_size=options.bucket_size, nbuckets=options.nbuckets)
+    elif options.sampler == "segments":
+        sampler = Engine.SamplerSegments()
+    else:
+        raise NotImplementedError("--sampler=%s is not accelerated by gat_b200 (annotator, segments)" % options.sampler)
     counters = [Engine.COUNTER_CLASSES[c]() for c in options.counters]
     if options.conditional != "unconditional":
         raise NotImplementedError("--conditional=%s is not accelerated by gat_b200" % options.conditional)

@@ -513,6 +513,7 @@ struct gatb_sampler {
     gatb_ctx *ctx = nullptr;
     uint32_t n_units = 0, n_contigs = 0;
     bool has_iso = false;
+    int kind = 0;                       // 0 SamplerAnnotator, 1 SamplerSegments
     std::vector<UnitDesc> h_units;
     std::vector<uint64_t> h_contig_base;
     std::vector<uint32_t> h_contig_cap;
@@ -682,6 +683,18 @@ extern "C" void gatb_sampler_destroy(gatb_sampler *s)
 
 extern "C" uint64_t gatb_sampler_sample_capacity(const gatb_sampler *s) { return s ? s->placed_stride : 0; }
 
+extern "C" int gatb_sampler_set_kind(gatb_sampler *s, int kind)
+{
+    if (!s) return GATB_ERR_INVALID;
+    if (kind != 0 && kind != 1) return fail(s->ctx, GATB_ERR_INVALID, "sampler kind must be 0 (annotator) or 1 (segments)");
+    // SamplerSegments returns unsorted, overlapping placements; only fromIsochores' merge(0) normalizes
+    // them, and without it the reference's counters assert (gat/SegmentList.pyx:1032-1033)
+    if (kind == 1 && !s->has_iso)
+        return fail(s->ctx, GATB_ERR_INVALID, "SamplerSegments needs an isochore workspace: its samples are not normalized");
+    s->kind = kind;
+    return GATB_OK;
+}
+
 static uint32_t pick_batch(const gatb_sampler *s, uint64_t n_samples)
 {
     uint64_t per_sample = (s->unit_stride + s->placed_stride) * 8 + (uint64_t)(s->n_units + s->n_contigs) * 5;
@@ -747,7 +760,7 @@ static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t 
         p.out_n = s->placed_n.p; p.out_n_stride = s->n_contigs; p.out_by_contig = 1;
     }
     p.status = s->status.p; p.n_units = s->n_units; p.n_samples = B; p.sample_begin = sample_begin;
-    p.seed = seed; p.track = track;
+    p.seed = seed; p.track = track; p.sampler_kind = s->kind;
     { ProfScope ps(ctx, PROF_PLACE); launch_place(st, p); }
     CU(ctx, cudaGetLastError());
     if (s->has_iso) {

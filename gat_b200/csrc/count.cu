@@ -6,10 +6,10 @@
 // key through it: lane = segment, one bin probe + two 8-byte shared-memory loads decide whether the
 // segment can overlap ANY of the group's tracks.  The ~7 % that can are pushed on a per-warp queue in
 // shared memory and resolved 32 at a time, all lanes busy, by the exact per-track pass over the
-// union interval's constituents (global memory / L2).  Per-track totals: `redux.sync` per track, then
-// a shared-memory accumulator per (sample, track) that only the owning warp touches -- no atomics,
-// deterministic, and the float64 nucleotide-density sum runs in the same key order (and with the same
-// compensated summation) as the reference's Python sum() (gat/__init__.py:583-587).
+// union interval's constituents (global memory / L2), which adds every overlap to the (sample, track)
+// accumulator in shared memory with integer atomics (order-independent, hence deterministic).  The
+// float64 nucleotide-density sum is formed per key from those integers, in the same key order and with
+// the same compensated summation as the reference's Python sum() (gat/__init__.py:583-587).
 #include "count.cuh"
 #include "../../include/gat_b200.h"
 

@@ -174,7 +174,16 @@ __global__ void __launch_bounds__(128) place_kernel(PlaceParams p)
     uint32_t nu = 0, np = 0, t0 = 0, status = 0;
     bool dirty = false;
 
-    if (d.tab_n > 0) {
+    if (d.tab_n > 0 && p.sampler_kind == 1) {
+        // SamplerSegments.sample (gat/Engine.pyx:719-735): exactly len(segments) placements, every one
+        // kept, returned in draw order (unsorted, unmerged); fromIsochores' merge(0) normalizes them later
+        for (uint32_t t = lane; t < d.seg_n; t += 32) {
+            const TurnDraw td = draw_turn(d, ws, tab, t, c1base, unit, sample, k0, k1);
+            buf[t] = pack_seg(td.start, td.end);
+        }
+        nu = d.seg_n;
+        __syncwarp();
+    } else if (d.tab_n > 0) {
         while (true_remaining > 0 && fails < 20) {
             // ---- speculative batch of 32 turns ------------------------------------------------------
             TurnDraw t = draw_turn(d, ws, tab, t0 + lane, c1base, unit, sample, k0, k1);
@@ -342,7 +351,7 @@ __global__ void __launch_bounds__(128) prep_units_kernel(UnitDesc *units, uint32
         d.tab_n = nw;
         d.bucket = bucket ? bucket : 1u;
         d.ltotal = (int32_t)lt;
-        d.cap = next_pow2(2u * nw + 64u);
+        d.cap = next_pow2(max(2u * nw + 64u, d.seg_n));   // SamplerSegments places seg_n segments
         d.error = err;
         units[unit] = d;
     }

@@ -45,6 +45,7 @@ struct PlaceParams {
     uint64_t sample_begin;       // global index of the first sample
     uint64_t seed;
     uint32_t track;
+    int sampler_kind;            // 0: SamplerAnnotator (gat/Engine.pyx:445-646), 1: SamplerSegments (:653-737)
 };
 
 struct MergeParams {             // K2: per (sample, contig) concat + merge(0) of the contig's units

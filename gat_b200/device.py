@@ -209,6 +209,11 @@ class Sampler(object):
         except Exception:
             pass
 
+    def set_kind(self, kind):
+        """'annotator' (default) or 'segments' (SamplerSegments, isochore workspaces only)"""
+        k = {"annotator": 0, "segments": 1}[kind] if isinstance(kind, str) else int(kind)
+        self.ctx.check(self.ctx.lib.gatb_sampler_set_kind(self.handle, k))
+
     def place(self, seed, track, sample_begin, n_samples):
         """-> (samples, status): samples[s][c] = (n,2) uint32 array of contig c; status [n_samples][n_units]"""
         cap = self.capacity

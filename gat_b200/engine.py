@@ -334,6 +334,7 @@ class SamplerAnnotator(Sampler):
     (all units x all samples) to the GPU in one batched call instead."""
 
     accelerated = True
+    kind = "annotator"
 
     def __init__(self, bucket_size=1, nbuckets=100000, nunsuccessful_rounds=0):
         self.bucket_size = bucket_size
@@ -364,6 +365,32 @@ class SamplerAnnotator(Sampler):
         r = SegmentList(array=placed[0][0])
         r._normalized = True
         return r
+
+
+class SamplerSegments(Sampler):
+    """sample exactly len(segments) segments from the length distribution (gat/Engine.pyx:653-737).  Its
+    samples are unsorted and may overlap; like in the reference they only become countable through the
+    merge(0) of IntervalDictionary.fromIsochores, so gat_b200.run() accepts it with isochore workspaces."""
+
+    accelerated = True
+    kind = "segments"
+
+    def __init__(self, bucket_size=1, nbuckets=100000):
+        self.bucket_size = bucket_size
+        self.nbuckets = nbuckets
+
+    def __reduce__(self):
+        return (SamplerSegments, (self.bucket_size, self.nbuckets))
+
+    def sample(self, segments, workspace):
+        assert workspace.isNormalized, "workspace is not normalized"
+        if len(segments) == 0 or len(workspace) == 0:
+            return SegmentList()
+        ctx = getContext()
+        # a single unit is placed through a two-key isochore problem so that the raw draw-order list
+        # cannot be returned by the C ABI (it only hands back contig-level, merged samples): use run()
+        raise NotImplementedError("SamplerSegments.sample() of a single list returns an unnormalized list; "
+                                  "use gat_b200.run() with an isochore workspace")
 
 
 # ----------------------------------------------------------------------------------------- counters

@@ -121,6 +121,12 @@ void gatb_sampler_destroy(gatb_sampler *s);
 /* capacity (in segments) of one sample's contig-level output, and of contig c inside it */
 uint64_t gatb_sampler_sample_capacity(const gatb_sampler *s);
 
+/* Sampler used for placement: 0 = SamplerAnnotator (default), 1 = SamplerSegments (gat/Engine.pyx:653-737:
+ * exactly len(segments[key]) placements per unit, all kept).  SamplerSegments' samples are unsorted and
+ * overlapping; they are only normalized by fromIsochores' merge(0), so kind 1 requires has_isochores
+ * (without it the reference's counters fail their isNormalized assertion). */
+int  gatb_sampler_set_kind(gatb_sampler *s, int kind);
+
 /* Place samples [sample_begin, sample_begin+n_samples) and return the contig-level segment sets
  * (what `sample` holds after sample.fromIsochores(), gat/__init__.py:563) to the host:
  * counts[s*n_contigs+c] segments for contig c of sample s, stored at start/end[s*capacity + contig_base[c] ...]

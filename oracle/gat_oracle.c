@@ -538,6 +538,50 @@ void go_count_placed(int C, int A, const uint64_t *placed_off, const go_seg *pla
         }
 }
 
+/* gat/Engine.pyx:653-737 SamplerSegments.sample(segments, workspace): exactly len(segments) placements
+ * (lengths from the workspace-overlapping segments), returned in draw order -- unsorted, unmerged */
+long go_sampler_segments(const go_seg *segments, size_t n, const go_seg *workspace, size_t m,
+                         uint32_t bucket_size, uint32_t nbuckets,
+                         go_randint_fn rnd, go_turn_fn next_turn, void *ctx, go_seg *out, size_t cap)
+{
+    long result = -3;
+    go_seg *working = (go_seg *)malloc(sizeof(go_seg) * (n ? n : 1));
+    int64_t *histogram = (int64_t *)malloc(sizeof(int64_t) * nbuckets);
+    uint32_t *hcdf = (uint32_t *)malloc(sizeof(uint32_t) * nbuckets);
+    uint32_t *wcdf = NULL;
+    if (!working || !histogram || !hcdf) goto done;
+    size_t nw = go_filter(segments, n, workspace, m, working);           /* :704-708 */
+    if (nw == 0) { result = 0; goto done; }
+    uint32_t bucket = go_length_distribution(working, nw, bucket_size, nbuckets, histogram);   /* :711-714 */
+    if (bucket == 0) { result = -2; goto done; }
+    uint32_t htotal = 0;
+    for (uint32_t i = 0; i < nbuckets; i++) { htotal += (uint32_t)histogram[i]; hcdf[i] = htotal; }
+    uint32_t wtotal = 0;
+    wcdf = build_ws_cdf(workspace, m, &wtotal);                           /* :717 */
+    if (!wcdf) goto done;
+    if (n > cap) { result = -1; goto done; }
+    for (size_t x = 0; x < n; x++) {                                      /* :719 for x in xrange(len(segments)) */
+        if (next_turn) next_turn(ctx);
+        uint32_t r = 1;
+        if (htotal > 1) r = (uint32_t)rnd(ctx, GO_SLOT_LEN, 1, (int64_t)htotal);
+        uint32_t base = (uint32_t)go_searchsorted_u32(hcdf, nbuckets, r) * bucket;
+        if (bucket > 1) base += (uint32_t)rnd(ctx, GO_SLOT_JITTER, 0, (int64_t)bucket);
+        uint32_t start, end;
+        int32_t overlap;
+        if (go_segmentlist_sample(workspace, m, wcdf, wtotal, base, rnd, ctx, GO_SLOT_WS_R, GO_SLOT_WS_P,
+                                  &start, &end, &overlap) != 0) { result = -4; goto done; }
+        out[x].start = start; out[x].end = end;
+    }
+    result = (long)n;
+done:
+    free(working); free(histogram); free(hcdf); free(wcdf);
+    return result;
+}
+
+/* which sampler go_compute_sample_philox places with: 0 = SamplerAnnotator, 1 = SamplerSegments */
+static int g_sampler_kind = 0;
+void go_set_sampler_kind(int kind) { g_sampler_kind = kind; }
+
 /* gat/__init__.py:494-591 computeSample, with the Philox stream of the CUDA kernel */
 int go_compute_sample_philox(int U, int C, int A, const int32_t *unit_contig, int has_isochores,
                              const uint64_t *seg_off, const go_seg *seg,
@@ -568,9 +612,11 @@ int go_compute_sample_philox(int U, int C, int A, const int32_t *unit_contig, in
         if (n == 0 || m == 0) { unit_n[u] = 0; o += cap; continue; }
         go_philox_ctx ctx;
         go_philox_begin(&ctx, seed, track, (uint32_t)u, sample);
-        long r = go_sampler_annotator(seg + seg_off[u], n, ws + ws_off[u], m, bucket_size, nbuckets,
-                                      go_philox_randint, go_philox_next_turn, &ctx,
-                                      unit_out + o, cap, NULL);
+        long r = g_sampler_kind == 1
+            ? go_sampler_segments(seg + seg_off[u], n, ws + ws_off[u], m, bucket_size, nbuckets,
+                                  go_philox_randint, go_philox_next_turn, &ctx, unit_out + o, cap)
+            : go_sampler_annotator(seg + seg_off[u], n, ws + ws_off[u], m, bucket_size, nbuckets,
+                                   go_philox_randint, go_philox_next_turn, &ctx, unit_out + o, cap, NULL);
         if (r < 0) { rc = (int)r; goto done; }
         unit_n[u] = (size_t)r;
         o += cap;

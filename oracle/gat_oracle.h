@@ -93,6 +93,14 @@ long go_sampler_annotator(const go_seg *segments, size_t n, const go_seg *worksp
                           go_randint_fn rnd, go_turn_fn next_turn, void *ctx,
                           go_seg *out, size_t cap, go_sample_info *info);
 
+/* SamplerSegments.sample (gat/Engine.pyx:653-737): len(segments) placements in draw order (unsorted,
+ * unmerged).  Returns the count, or -1/-2/-3 as above. */
+long go_sampler_segments(const go_seg *segments, size_t n, const go_seg *workspace, size_t m,
+                         uint32_t bucket_size, uint32_t nbuckets,
+                         go_randint_fn rnd, go_turn_fn next_turn, void *ctx, go_seg *out, size_t cap);
+/* sampler used by go_compute_sample_philox: 0 = SamplerAnnotator (default), 1 = SamplerSegments */
+void go_set_sampler_kind(int kind);
+
 /* --- counters (gat/Engine.pyx:1412-1472) ----------------------------------------------------------
  * counter ids are shared with include/gat_b200.h */
 enum { GO_NUCLEOTIDE_OVERLAP = 0, GO_NUCLEOTIDE_DENSITY = 1, GO_SEGMENT_OVERLAP = 2,

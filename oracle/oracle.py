@@ -229,6 +229,43 @@ def sampler_annotator_philox(segments, workspace, seed, track, unit, sample,
     return out[:n].copy(), info
 
 
+def sampler_segments(segments, workspace, bucket_size=1, nbuckets=100000, philox=None):
+    """SamplerSegments.sample (gat/Engine.pyx:653-737): driven by numpy.random (seed it first) when
+    philox is None, else by the Philox stream philox=(seed, track, unit, sample)."""
+    L = lib()
+    L.go_sampler_segments.restype = ctypes.c_long
+    L.go_sampler_segments.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                      ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    a, w = as_segs(segments), as_segs(workspace)
+    cap = len(a) + 8
+    out = np.zeros((cap, 2), dtype=np.uint32)
+    if philox is None:
+        cb = _numpy_randint_callback()
+        n = L.go_sampler_segments(_p(a), len(a), _p(w), len(w), bucket_size, nbuckets,
+                                  ctypes.cast(cb, ctypes.c_void_p), None, None, _p(out), cap)
+    else:
+        ctx = PhiloxCtx()
+        L.go_philox_begin(ctypes.addressof(ctx), *philox)
+        n = L.go_sampler_segments(_p(a), len(a), _p(w), len(w), bucket_size, nbuckets,
+                                  ctypes.cast(L.go_philox_randint, ctypes.c_void_p),
+                                  ctypes.cast(L.go_philox_next_turn, ctypes.c_void_p),
+                                  ctypes.addressof(ctx), _p(out), cap)
+    if n == -2:
+        raise ValueError("segment too large: increase nbuckets or bucket_size")
+    if n < 0:
+        raise RuntimeError("oracle sampler failed: %i" % n)
+    return out[:n].copy()
+
+
+def set_sampler_kind(kind):
+    """sampler used by compute_sample_philox: 'annotator' (default) or 'segments'"""
+    L = lib()
+    L.go_set_sampler_kind.restype = None
+    L.go_set_sampler_kind.argtypes = [ctypes.c_int]
+    L.go_set_sampler_kind({"annotator": 0, "segments": 1}[kind])
+
+
 def philox4x32_10(ctr, key):
     c = np.array(ctr, dtype=np.uint32)
     k = np.array(key, dtype=np.uint32)

@@ -138,6 +138,24 @@ def make_sampler_units(rng):
     return dict(units=units, too_large=dict(segments=L(sl), workspace=L(wl), bucket_size=1, nbuckets=1000, error=err))
 
 
+def make_sampler_segments(rng):
+    """SamplerSegments.sample (gat/Engine.pyx:653-737) under numpy.random.seed: placements in draw order"""
+    units = []
+    for it in range(40):
+        nws = int(rng.integers(1, 6))
+        span = int(rng.choice([5000, 200000, 30000000]))
+        pts = np.sort(rng.choice(span, size=2 * nws, replace=False))
+        ws = [(int(pts[2 * i]), int(pts[2 * i + 1])) for i in range(nws)]
+        segs = rlist(rng, span, int(rng.integers(1, 50)), int(rng.choice([5, 80, 900])))
+        bucket = int(rng.choice([1, 1, 4]))
+        sl = RS.SegmentList(iter=segs, normalize=True)
+        wl = RS.SegmentList(iter=ws, normalize=True)
+        np.random.seed(5000 + it)
+        out = RE.SamplerSegments(bucket_size=bucket, nbuckets=100000).sample(sl, wl)
+        units.append(dict(segments=L(sl), workspace=L(wl), bucket_size=bucket, seed=5000 + it, placed=L(out)))
+    return units
+
+
 def counter_objs():
     return [RE.CounterNucleotideOverlap(), RE.CounterNucleotideDensity(), RE.CounterSegmentOverlap(),
             RE.CounterSegmentMidpointOverlap(), RE.CounterAnnotationOverlap(), RE.CounterAnnotationMidpointOverlap()]
@@ -413,6 +431,17 @@ def make_observed_tutorial():
 
 
 def main():
+    # fixtures added after the first generation have their own seeds and can be (re)made alone:
+    #   python tests/golden/make_golden.py sampler_segments
+    extra = {"sampler_segments": (make_sampler_segments, 20260102)}
+    only = [a for a in sys.argv[1:] if a in extra]
+    for name in (only or list(extra)):
+        fn, seed = extra[name]
+        with open(os.path.join(HERE, name + ".json"), "w") as f:
+            json.dump(fn(np.random.default_rng(seed)), f)
+        print("wrote", name)
+    if only:
+        return
     rng = np.random.default_rng(20260101)
     for name, fn in (("segmentlist", make_segmentlist), ("sampler_units", make_sampler_units),
                      ("counters", make_counters), ("stats", make_stats), ("qvalues", make_qvalues)):

@@ -208,3 +208,36 @@ def test_invalid_inputs_fail_loudly(ctx):
     out = an.count_lists(COUNTERS, [[good], [np.zeros((0, 2), dtype=np.uint32)]])
     assert out[0, 0, 0] == 0 and out[0, 0, 1] == 20 and (out[:, 1, :] == 0).all()
     an.close()
+
+
+def test_sampler_segments_matches_oracle(ctx, oracle):
+    """SamplerSegments (exactly len(segments) placements per unit, merged per contig by fromIsochores):
+    contig-level samples and counts equal the oracle's; without isochores the call is refused"""
+    from gat_b200 import device, _lib
+    rng = np.random.default_rng(91)
+    pr = helpers.random_problem(rng, n_contigs=3, n_iso=3, n_annot=5)
+    smp = device.Sampler(ctx, pr["unit_contig"], pr["n_contigs"], True, pr["unit_segments"], pr["unit_workspace"])
+    smp.set_kind("segments")
+    an = device.Annotations(ctx, pr["annotations"], key_ws_nseg=pr["cws_nseg"])
+    n = 12
+    placed, status = smp.place(seed=4, track=1, sample_begin=3, n_samples=n)
+    res, _ = smp.run(an, COUNTERS, seed=4, track=1, sample_begin=3, n_samples=n)
+    oracle.set_sampler_kind("segments")
+    try:
+        for s in range(n):
+            exp, exp_placed = oracle.compute_sample_philox(pr["unit_contig"], pr["unit_segments"], pr["unit_workspace"],
+                                                           pr["annotations"], pr["cws_nseg"], COUNTERS, seed=4, track=1,
+                                                           sample=3 + s, has_isochores=True, return_placed=True)
+            for c in range(pr["n_contigs"]):
+                assert np.array_equal(placed[s][c], exp_placed[c]), (s, c)
+            for i, name in enumerate(COUNTERS):
+                assert np.array_equal(np.asarray(res[name][s], dtype=np.float64), exp[i]), (s, name)
+    finally:
+        oracle.set_sampler_kind("annotator")
+    smp.close()
+    an.close()
+    plain = helpers.random_problem(rng, n_contigs=2, n_iso=0)
+    smp = device.Sampler(ctx, plain["unit_contig"], plain["n_contigs"], False, plain["unit_segments"], plain["unit_workspace"])
+    with pytest.raises(_lib.GatB200Error):
+        smp.set_kind("segments")
+    smp.close()

@@ -224,3 +224,14 @@ def test_adjust_pvalues_match_reference(oracle):
         for method, want in c["adjusted"].items():
             got = oracle.adjust_pvalues(c["pvalues"], method)
             assert np.array_equal(got, np.array(want)), method
+
+
+def test_sampler_segments_matches_reference_under_numpy_rng(oracle):
+    """SamplerSegments.sample (gat/Engine.pyx:653-737): placements in draw order equal the reference's"""
+    units = G.load_json("sampler_segments")
+    assert len(units) >= 40
+    for u in units:
+        np.random.seed(u["seed"])
+        got = oracle.sampler_segments(u["segments"], u["workspace"], bucket_size=u["bucket_size"])
+        assert got.tolist() == u["placed"], u["seed"]
+        assert len(got) in (0, len(u["segments"]))
