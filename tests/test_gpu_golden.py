@@ -253,3 +253,41 @@ def test_operator_protocols_single_calls(ctx, oracle):
     assert Engine.SamplerAnnotator().sample(SegmentList(), ws).isEmpty
     with pytest.raises(ValueError):                          # segment too large for the histogram
         Engine.SamplerAnnotator(bucket_size=1, nbuckets=100).sample(segs, ws)
+
+
+@pytest.mark.parametrize("with_isochores", [False, True])
+def test_cli_from_bed_files(ctx, oracle, tmp_path, with_isochores):
+    """gat-run.py-style invocation: BED files in, result table out (--segments/--annotations/--workspace/
+    --isochore-file, --counter, --num-samples, --random-seed); observed column checked against the oracle"""
+    from gat_b200 import cli, synthetic, io as IO
+    import gat_b200
+    genome = [("chrA", 1500000), ("chrB", 700000)]
+    segments, annotations, workspaces, iso = synthetic.make(
+        n_segments=250, n_annotations=4, n_annotation_intervals=300, isochores=with_isochores, genome=genome,
+        isochore_tile=100000, n_isochores=2, seed=99)
+    files = {}
+    for name, coll in (("segments", segments), ("annotations", annotations), ("workspace", workspaces)):
+        files[name] = str(tmp_path / (name + ".bed"))
+        synthetic.write_bed(coll, files[name], with_tracks=name == "annotations")
+    argv = ["gat-run", "--segments=" + files["segments"], "--annotations=" + files["annotations"],
+            "--workspace=" + files["workspace"], "--counter=nucleotide-overlap", "--counter=segment-overlap",
+            "--num-samples=300", "--random-seed=7", "--output-tables-pattern=" + str(tmp_path / "out_%s.tsv")]
+    if with_isochores:
+        files["iso"] = str(tmp_path / "iso.bed")
+        synthetic.write_bed(iso, files["iso"], with_tracks=True)
+        argv.append("--isochore-file=" + files["iso"])
+    assert cli.main(argv + ["-v", "0"]) == 0
+    # expected observed values: the same files through the host preparation and the oracle's counters
+    options, _ = gat_b200.buildParser().parse_args(argv[1:])
+    s2, a2, w2, i2 = IO.buildSegments(options)
+    ws = IO.applyIsochores(s2, a2, w2, options, i2)
+    for counter in ("nucleotide-overlap", "segment-overlap"):
+        rows = [l.rstrip("\n").split("\t") for l in open(str(tmp_path / ("out_%s.tsv" % counter)))]
+        assert rows[0][:11] == ["track", "annotation", "observed", "expected", "CI95low", "CI95high", "stddev", "fold",
+                                "l2fold", "pvalue", "qvalue"]
+        assert len(rows) == 5
+        for r in rows[1:]:
+            want = sum(oracle.counter(counter, s2["merged"][k].asarray(), a2[r[1]][k].asarray(), len(ws[k]))
+                       for k in ws.keys())
+            assert int(r[2]) == int(want), (counter, r[1])
+            assert 0 < float(r[9]) <= 1 and 0 < float(r[10]) <= 1 and float(r[3]) > 0

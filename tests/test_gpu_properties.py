@@ -145,3 +145,26 @@ def test_column_stats_at_scale(ctx):
         else:
             k = n_lt + n_eq
         assert got["pvalue"][a] == max(1.0 / l, k / l), a
+
+
+def test_large_units_match_oracle(ctx, oracle):
+    """tutorial-scale lists (HepG2 DHS x Jurkat DHS shape: ~150 000 segments, ~160 000-interval tracks): units of
+    ~12 000 segments (32 768-slot buffers, multi-stage sorts), filters with > 10 000 union intervals"""
+    import gat_b200
+    from gat_b200 import synthetic, device
+    segments, annotations, workspaces, _ = synthetic.make(150000, 2, 160000)
+    workspace = synthetic.prepare(segments, annotations, workspaces)
+    pr = gat_b200.TrackProblem(segments["merged"], workspace)
+    atracks, lists, nseg = gat_b200.buildContigAnnotations(annotations, workspace, pr.contigs)
+    assert max(len(x) for x in pr.unit_segments) > 10000
+    smp = device.Sampler(ctx, pr.unit_contig, len(pr.contigs), False, pr.unit_segments, pr.unit_workspace)
+    annos = device.Annotations(ctx, lists, key_ws_nseg=nseg)
+    names = ["nucleotide-overlap", "segment-overlap", "annotation-overlap"]
+    res, info = smp.run(annos, names, seed=2, track=0, sample_begin=0, n_samples=24)
+    assert int(info[2]) == 0
+    exp = oracle.compute_sample_philox(pr.unit_contig, pr.unit_segments, pr.unit_workspace, lists, nseg, names,
+                                       seed=2, track=0, sample=23)
+    for i, n in enumerate(names):
+        assert np.array_equal(res[n][23].astype(np.float64), exp[i]), n
+    smp.close()
+    annos.close()
