@@ -238,6 +238,7 @@ struct gatb_annotations {
     gatb_ctx *ctx = nullptr;
     uint32_t n_annot = 0, n_keys = 0, n_groups = 0, ka = 1;
     uint32_t max_stage = 0;             // largest filter (bytes) over all tiles
+    uint32_t max_prefix = 0;            // largest header + bitmap (bytes): staged for every tile
     uint64_t n_intervals = 0;
     DevBuf<uint8_t> tiles;
     DevBuf<uint64_t> tile_off;
@@ -260,8 +261,8 @@ static uint32_t filter_budget(const gatb_ctx *ctx)
 
 // geometry of tile (tracks a0 .. a0+ka-1, key k); see count.cuh.  ok == false: larger than 4 GiB.
 static bool tile_geometry(const uint64_t *offs, const uint32_t *end, uint32_t A, uint32_t K, uint32_t a0,
-                          uint32_t ka, uint32_t k, uint32_t bin_factor, uint32_t budget, TileHeader &h,
-                          uint64_t &bytes)
+                          uint32_t ka, uint32_t k, uint32_t bin_factor, uint32_t budget, uint32_t bm_budget,
+                          uint32_t bm_min_shift, TileHeader &h, uint64_t &bytes)
 {
     memset(&h, 0, sizeof(h));
     uint64_t nc = 0;
@@ -275,14 +276,28 @@ static bool tile_geometry(const uint64_t *offs, const uint32_t *end, uint32_t A,
     if (nc > 0x7fffffffull) return false;
     h.n_cons = (uint32_t)nc;
     const uint64_t hdr = align16(sizeof(TileHeader));
-    const uint64_t uiv_bytes = align16((nc + 2) * 8);
-    // bin index: bin_factor bins per interval, but no more than fit next to the union in the budget
-    // (and never more bins than positions); lists with > 65534 intervals are binary-searched instead
+    const uint64_t civ_bytes = align16((nc + 2) * 8);
+    const uint64_t cslot_bytes = align16(nc + 2);
+    // occupancy bitmap: the finest power-of-two resolution (>= 2^bm_min_shift positions per bit) whose
+    // bits fit bm_budget bytes; one zero word of padding so that bit bm_bits exists and is never set
+    uint64_t bm_bytes = 0;
+    if (nc > 0) {
+        const uint32_t ext1 = extent ? extent - 1 : 0;
+        uint32_t sh = bm_min_shift;
+        while (sh < 31 && ((uint64_t)(ext1 >> sh) + 1) > (uint64_t)bm_budget * 8) sh++;
+        h.bm_shift = sh;
+        h.bm_bits = (ext1 >> sh) + 1;
+        bm_bytes = align16(((uint64_t)(h.bm_bits + 31) / 32 + 1) * 4);
+    }
+    h.bm_off = (uint32_t)hdr;
+    const uint64_t fixed = hdr + bm_bytes + cslot_bytes + civ_bytes;
+    // bin index: bin_factor bins per interval, but no more than fit next to the bitmap and the intervals
+    // in the budget (and never more bins than positions); lists with > 65534 intervals are binary-searched
     uint64_t nbins = 0;
     if (nc > 0 && nc <= 65534 && extent > 1) {
         nbins = (uint64_t)bin_factor * nc;
-        if (hdr + uiv_bytes + 2 * (nbins + 1) + 16 > budget) {
-            const uint64_t room = budget > hdr + uiv_bytes + 64 ? (budget - hdr - uiv_bytes - 32) / 2 : 0;
+        if (fixed + 2 * (nbins + 1) + 16 > budget) {
+            const uint64_t room = budget > fixed + 64 ? (budget - fixed - 32) / 2 : 0;
             nbins = std::max<uint64_t>(std::min<uint64_t>(nbins, room), std::min<uint64_t>(nc, nbins));
         }
         nbins = std::min<uint64_t>(nbins, extent);
@@ -290,18 +305,21 @@ static bool tile_geometry(const uint64_t *offs, const uint32_t *end, uint32_t A,
     h.nbins = (uint32_t)nbins;
     h.inv = nbins ? (uint32_t)(((uint64_t)nbins << 32) / ((uint64_t)extent + 1)) : 0;
     if (nbins && h.inv == 0) { h.nbins = 0; nbins = 0; }
-    uint64_t o = hdr;
+    uint64_t o = hdr + bm_bytes;
     h.idx_off = (uint32_t)o;
     o += nbins ? align16((nbins + 1) * 2) : 0;
-    h.uiv_off = (uint32_t)o;
-    o += uiv_bytes;
+    h.cslot_off = (uint32_t)o;
+    o += cslot_bytes;
+    h.civ_off = (uint32_t)o;
+    o += civ_bytes;
     if (o > 0xfffffff0ull) return false;
     h.stage_bytes = (uint32_t)o;
+    h.uiv_off = (uint32_t)o;
+    o += align16((nc + 2) * 8);
+    if (o > 0xfffffff0ull) return false;
     h.uoff_off = (uint32_t)o;
     o += align16((nc + 2) * 4);
     if (o > 0xfffffff0ull) return false;
-    h.cons_off = (uint32_t)o;
-    o += align16(nc * 16);
     bytes = o;
     return true;
 }
@@ -326,6 +344,9 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
     const uint32_t A = (uint32_t)n_annot, K = (uint32_t)n_keys;
     const uint32_t bin_factor = std::max(1u, env_u32("GATB_BIN_FACTOR", 4));
     const uint32_t budget = filter_budget(ctx);
+    // the bitmap is staged for EVERY tile, so it has to fit whatever a launch leaves (see count_params_annos)
+    const uint32_t bm_budget = std::max(256u, std::min(env_u32("GATB_BITMAP_BYTES", 32768), budget / 4));
+    const uint32_t bm_min_shift = std::min(20u, env_u32("GATB_BITMAP_MIN_SHIFT", 10));
     // largest group size whose every filter fits the budget (floor: one track per tile; oversized
     // filters are then read from global memory by the kernel)
     uint32_t ka = 1;
@@ -335,7 +356,7 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
         bool ok = true;
         for (uint32_t a0 = 0; a0 < A && ok; a0 += cand)
             for (uint32_t k = 0; k < K; k++)
-                if (!tile_geometry(offs, end, A, K, a0, cand, k, bin_factor, budget, h, bytes) || h.stage_bytes > budget) {
+                if (!tile_geometry(offs, end, A, K, a0, cand, k, bin_factor, budget, bm_budget, bm_min_shift, h, bytes) || h.stage_bytes > budget) {
                     ok = false;
                     break;
                 }
@@ -349,21 +370,23 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
     std::vector<uint32_t> tile_stage((size_t)G * K);
     std::vector<TileHeader> headers((size_t)G * K);
     uint64_t total = 0;
-    uint32_t max_stage = 0;
+    uint32_t max_stage = 0, max_prefix = 0;
     for (uint32_t g = 0; g < G; g++)
         for (uint32_t k = 0; k < K; k++) {
             const size_t t = (size_t)g * K + k;
-            if (!tile_geometry(offs, end, A, K, g * ka, ka, k, bin_factor, budget, headers[t], bytes))
+            if (!tile_geometry(offs, end, A, K, g * ka, ka, k, bin_factor, budget, bm_budget, bm_min_shift, headers[t], bytes))
                 return fail(ctx, GATB_ERR_INVALID, "annotations: tile larger than 4 GiB");
             tile_off[t] = total;
             tile_stage[t] = headers[t].stage_bytes;
             max_stage = std::max(max_stage, headers[t].stage_bytes);
+            max_prefix = std::max(max_prefix, headers[t].idx_off);
             total += bytes;
         }
 
     gatb_annotations *a = new gatb_annotations();
     a->ctx = ctx; a->n_annot = A; a->n_keys = K; a->n_groups = G; a->ka = ka;
     a->max_stage = max_stage;
+    a->max_prefix = max_prefix;
     a->n_intervals = offs[n_lists];
     cudaStream_t st = ctx->stream;
     DevBuf<uint64_t> d_offs;
@@ -427,7 +450,9 @@ static void count_params_annos(const gatb_annotations *a, uint32_t n_samples, bo
     // what this launch can stage: the device limit minus its own accumulators and queues
     const size_t over = count_smem_overhead(ctx->count_threads, schunk, density) + 1024;
     const size_t room = ctx->smem_optin > over ? ctx->smem_optin - over : 0;
-    p.smem_tile_budget = (uint32_t)std::min<size_t>(room, a->max_stage);
+    // (the header + bitmap prefix is staged unconditionally; a launch that cannot hold it fails in
+    // cudaFuncSetAttribute rather than overrunning)
+    p.smem_tile_budget = std::max((uint32_t)std::min<size_t>(room, a->max_stage), a->max_prefix);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -460,7 +485,7 @@ extern "C" int gatb_count_lists(gatb_ctx *ctx, const gatb_annotations *annos, in
     uint64_t stride = 0;
     for (uint32_t k = 0; k < K; k++) {
         if (cap[k] >= (1u << 24)) return fail(ctx, GATB_ERR_INVALID, "count_lists: 2^24 or more segments on one key");
-        key_base[k] = stride; stride += cap[k];
+        key_base[k] = stride; stride += (cap[k] + 1u) & ~1u;      // even: the kernel loads segment pairs (16 bytes)
     }
     if (stride == 0) stride = 1;
     std::vector<uint64_t> packed(n_samples * stride, 0);

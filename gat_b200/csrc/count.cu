@@ -1,13 +1,14 @@
 // count.cu -- K3/K4 counting kernel, tile construction, and K5 column statistics.  sm_100a.
 //
 // Counting: a CTA owns (group of <= KMAX annotation tracks) x (chunk of samples) and walks the keys
-// (contigs) in order.  Per key it stages the group's FILTER (bin index + union of the tracks'
-// intervals, see count.cuh) in shared memory, then every warp streams its samples' segments on that
-// key through it: lane = segment, one bin probe + two 8-byte shared-memory loads decide whether the
-// segment can overlap ANY of the group's tracks.  The ~7 % that can are pushed on a per-warp queue in
-// shared memory and resolved 32 at a time, all lanes busy, by the exact per-track pass over the
-// union interval's constituents (global memory / L2), which adds every overlap to the (sample, track)
-// accumulator in shared memory with integer atomics (order-independent, hence deterministic).  The
+// (contigs) in order.  Per key it stages the group's FILTER (occupancy bitmap + bin index + union of
+// the tracks' intervals, see count.cuh) in shared memory, then every warp streams its samples' segments
+// on that key through it: lane = segment, one 4-byte shared-memory load of the bitmap decides whether
+// the segment can overlap ANY of the group's tracks.  The ~11 % that can are pushed on a per-warp queue
+// in shared memory and resolved 32 at a time, all lanes busy: bin probe + union intervals give the exact
+// answer (7 % do overlap), then the per-track pass over the union interval's constituents (global
+// memory / L2) adds every overlap to the (sample, track) accumulator in shared memory with integer
+// atomics (order-independent, hence deterministic).  The
 // float64 nucleotide-density sum is formed per key from those integers, in the same key order and with
 // the same compensated summation as the reference's Python sum() (gat/__init__.py:583-587).
 #include "count.cuh"
@@ -16,7 +17,7 @@
 namespace gatb {
 
 constexpr uint32_t QCAP = 64;            // queue entries per warp; flushed whenever 32 are waiting
-struct __align__(16) QEntry { int s, e; uint32_t is, j; }; // segment; its index in the list (< 2^24) | sample slot << 24; union start index
+struct __align__(16) QEntry { int s, e; uint32_t is, pad; };  // pad is never read // segment; its index in the list (< 2^24) | sample slot << 24
 
 // ---------------------------------------------------------------------------------------------------
 // TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers for the filter staging
@@ -72,62 +73,77 @@ size_t count_smem_overhead(int threads, uint32_t schunk, bool density)
 
 // ---------------------------------------------------------------------------------------------------
 // Exact counts of one queued segment [s,e) against every track of the tile.  Coordinates are < 2^31,
-// so signed compares are exact and the sentinels are (INT_MAX, INT_MAX).  `filt` holds the union
-// intervals (shared or global memory), `tile_g` the constituents (global).
+// so signed compares are exact and the sentinels are (INT_MAX, INT_MAX).  `filt` holds the bin index
+// and the intervals (shared or global memory), `tile_g` is the tile in global memory.
 //   nucleotide-overlap   overlapWithSegments            gat/SegmentList.pyx:1026-1076
 //   segment-overlap      intersectionWithSegments(base) :1078-1146  (a segment counts once per track)
 //   segment-midoverlap   midpoint tested against the FIRST overlapping interval of the track (:1137-1144)
 //   annotation-*         roles swapped: an interval is counted by the first segment overlapping it,
 //                        i.e. when it does not already overlap the previous segment (start >= pe)
+// one overlapping interval [x,y) of track slot t against the queued segment [s,e)
 template <int COUNTER>
-__device__ __forceinline__ void resolve_entry(const uint8_t *__restrict__ filt, const uint8_t *__restrict__ tile_g,
-                                              uint32_t uiv_off, uint32_t uoff_off, uint32_t cons_off,
-                                              const QEntry en, const uint64_t *__restrict__ placed_key,
+__device__ __forceinline__ void count_pair(int s, int e, int x, int y, uint32_t t, int pe, uint32_t *__restrict__ acc,
+                                           uint32_t &seen, uint32_t &hit)
+{
+    if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
+        atomicAdd(acc + t, (uint32_t)(min(e, y) - max(s, x)));
+    } else if (COUNTER == GATB_SEGMENT_OVERLAP) {
+        hit |= 1u << t;
+    } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
+        if (!((seen >> t) & 1u)) {
+            seen |= 1u << t;
+            const int mid = s + ((e - s) >> 1);
+            if (x <= mid && mid < y) hit |= 1u << t;
+        }
+    } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
+        if (x >= pe) atomicAdd(acc + t, 1u);
+    } else {
+        if (x >= pe) {
+            const int m = x + ((y - x) >> 1);
+            if (s <= m && m < e) atomicAdd(acc + t, 1u);
+        }
+    }
+}
+
+// `hs` is the tile header in shared memory (always staged), read here rather than carried in registers
+// through the streaming loop.
+template <int COUNTER>
+__device__ __forceinline__ void resolve_entry(const TileHeader *__restrict__ hs, const uint8_t *__restrict__ filt,
+                                              const uint8_t *__restrict__ tile_g, const QEntry en,
+                                              const uint64_t *__restrict__ placed_key,
                                               uint64_t sample_stride, uint32_t s_begin, uint32_t *__restrict__ acc_s)
 {
     const bool need_prev = (COUNTER == GATB_ANNOTATION_OVERLAP || COUNTER == GATB_ANNOTATION_MIDOVERLAP);
-    const uint2 *uiv = reinterpret_cast<const uint2 *>(filt + uiv_off);
-    const uint32_t *uoff = reinterpret_cast<const uint32_t *>(tile_g + uoff_off);
-    const uint4 *cons = reinterpret_cast<const uint4 *>(tile_g + cons_off);
+    const uint2 *civ = reinterpret_cast<const uint2 *>(filt + hs->civ_off);
     const int s = en.s, e = en.e;
+    // where the walk starts: the first interval of the first union interval with end > (bin of) s
+    uint32_t c;
+    const uint32_t nbins = hs->nbins;
+    if (nbins) {
+        c = reinterpret_cast<const uint16_t *>(filt + hs->idx_off)[min(__umulhi((uint32_t)s, hs->inv), nbins)];
+    } else {
+        const uint2 *uiv = reinterpret_cast<const uint2 *>(tile_g + hs->uiv_off);
+        uint32_t lo = 0, hi = hs->n_union;                 // lower_bound (utils/gat_utils.c:8-32)
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((int)uiv[mid].y <= s) lo = mid + 1; else hi = mid;
+        }
+        c = reinterpret_cast<const uint32_t *>(tile_g + hs->uoff_off)[lo];
+    }
+    uint2 v = civ[c];
+    while ((int)v.y <= s) v = civ[++c];             // the sentinel stops the scan
+    if ((int)v.x >= e) return;                      // bitmap false positive: the segment falls in a gap
+    const uint8_t *cslot = filt + hs->cslot_off;
     const uint32_t slot = en.is >> 24, i = en.is & 0xffffffu;
     uint32_t *acc = acc_s + slot * KMAX;            // shared accumulators of this sample: integer atomics,
     int pe = 0;                                     // so the result does not depend on the order of arrival
     if (need_prev && i > 0)
         pe = (int)seg_end(placed_key[(uint64_t)(s_begin + slot) * sample_stride + i - 1]);
-    uint32_t u = en.j;
-    uint2 a = uiv[u];
-    while ((int)a.y <= s) a = uiv[++u];         // first union interval with end > s; the sentinel stops the scan
     uint32_t seen = 0, hit = 0;
-    while ((int)a.x < e) {
-        uint32_t c = uoff[u];
-        const uint32_t cend = uoff[u + 1];
-        for (; c < cend; c++) {
-            const uint4 v = cons[c];
-            if ((int)v.x >= e) break;           // constituents are sorted by start
-            if ((int)v.y <= s) continue;
-            const uint32_t t = v.z;
-            if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
-                atomicAdd(acc + t, (uint32_t)(min(e, (int)v.y) - max(s, (int)v.x)));
-            } else if (COUNTER == GATB_SEGMENT_OVERLAP) {
-                hit |= 1u << t;
-            } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
-                if (!((seen >> t) & 1u)) {
-                    seen |= 1u << t;
-                    const int mid = s + ((e - s) >> 1);
-                    if ((int)v.x <= mid && mid < (int)v.y) hit |= 1u << t;
-                }
-            } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
-                if ((int)v.x >= pe) atomicAdd(acc + t, 1u);
-            } else {
-                if ((int)v.x >= pe) {
-                    const int m = (int)v.x + (((int)v.y - (int)v.x) >> 1);
-                    if (s <= m && m < e) atomicAdd(acc + t, 1u);
-                }
-            }
-        }
-        a = uiv[++u];
-    }
+    do {                                            // intervals are sorted by start: stop at start >= e
+        if ((int)v.y > s) count_pair<COUNTER>(s, e, (int)v.x, (int)v.y, cslot[c], pe, acc, seen, hit);
+        v = civ[++c];
+    } while ((int)v.x < e);
     if (COUNTER == GATB_SEGMENT_OVERLAP || COUNTER == GATB_SEGMENT_MIDOVERLAP) {
         while (hit) {
             const int t = __ffs(hit) - 1;
@@ -137,79 +153,81 @@ __device__ __forceinline__ void resolve_entry(const uint8_t *__restrict__ filt, 
     }
 }
 
-// All samples of one warp on one key against the tile.  `filt` points into shared memory (staged
-// filters) or global memory; the code is instantiated once per address space.  Segments are loaded two
-// batches ahead; the queue is carried across the warp's samples and drained once per key.
-template <int COUNTER, bool INDEXED>
-__device__ __forceinline__ void count_key(const uint8_t *__restrict__ filt, const uint8_t *__restrict__ tile_g,
-                                          const TileHeader &h, const CountParams &p, uint32_t k,
+// All samples of one warp on one key against the tile.  `bm` is the staged bitmap (shared memory);
+// `filt` points at the staged tile in shared memory or, for filters too large to stage, at the tile in
+// global memory (the code is instantiated once per address space).  A lane loads two segments (16 bytes)
+// per access, 64 per warp, and the two halves of the unrolled loop keep 128 segments in flight ahead of
+// the one being tested (they swap roles, so no register rotation); the queue is carried across the
+// warp's samples and drained once per key.
+//
+// Bitmap test: bit b is set when a union interval touches [b << sh, (b + 2) << sh), so ONE bit decides
+// for every segment no longer than 1 << sh (it lies inside that window); longer segments are candidates
+// outright.  Bits >= bm_bits are zero (padding word), which also retires lanes past the end of the list:
+// they carry the all-ones pattern, whose start lies beyond every coordinate and whose length is 0.
+template <int COUNTER>
+__device__ __forceinline__ void count_key(const TileHeader *__restrict__ hs, const uint32_t *__restrict__ bm,
+                                          const uint8_t *__restrict__ filt, const uint8_t *__restrict__ tile_g,
+                                          const CountParams &p, uint32_t k,
                                           uint32_t s_begin, uint32_t s_end, int lane, int warp, int nwarps,
                                           QEntry *__restrict__ queue, uint32_t *__restrict__ acc_s)
 {
-    const uint2 *uiv = reinterpret_cast<const uint2 *>(filt + h.uiv_off);
-    const uint16_t *idx = reinterpret_cast<const uint16_t *>(filt + h.idx_off);
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t sh = hs->bm_shift, nbits = hs->bm_bits, wlen = 1u << sh;
     const uint64_t *placed_key = p.placed + p.key_base[k];
+    const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
     uint32_t qn = 0;                                                   // warp-uniform queue fill
     for (uint32_t sl = s_begin + warp; sl < s_end; sl += nwarps) {
         if (p.key_present && !p.key_present[(uint64_t)sl * p.n_keys + k]) continue;
         const uint32_t n = p.placed_n[(uint64_t)sl * p.n_keys + k];
         if (n == 0) continue;
-        const uint64_t *segs = placed_key + (uint64_t)sl * p.sample_stride;
+        // (key bases and the sample stride are even, so pairs are 16-byte aligned; reading the unused
+        // slot after an odd n stays inside the key's buffer)
+        const uint4 *segs = reinterpret_cast<const uint4 *>(placed_key + (uint64_t)sl * p.sample_stride) + lane;
         const uint32_t slot24 = (sl - s_begin) << 24;
-        uint64_t x1 = ((uint32_t)lane < n) ? segs[lane] : 0;           // batch b0
-        uint64_t x2 = ((uint32_t)lane + 32 < n) ? segs[lane + 32] : 0; // batch b0 + 32
-        for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-            const uint32_t i = b0 + lane;
-            const uint64_t x = x1;
-            x1 = x2;
-            x2 = (i + 64 < n) ? segs[i + 64] : 0;                     // software prefetch, two batches ahead
-            const int s = (int)seg_start(x), e = (int)seg_end(x);
-            bool flag = false;
-            uint32_t j = 0;
-            if (i < n) {
-                if (INDEXED) {
-                    j = idx[min(__umulhi((uint32_t)s, h.inv), h.nbins)];
-                } else {
-                    uint32_t lo = 0, hi = h.n_union;                   // lower_bound (utils/gat_utils.c:8-32)
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if ((int)uiv[mid].y <= s) lo = mid + 1; else hi = mid;
-                    }
-                    j = lo;
-                }
-                const uint2 c0 = uiv[j];
-                int ax = (int)c0.x;
-                bool more = false;
-                if ((int)c0.y <= s) {               // (~1 lane in 6) the candidate ends before s: take the next one
-                    const uint2 c1 = uiv[j + 1];
-                    ax = (int)c1.x;
-                    more = (int)c1.y <= s;          // still not past s: let the exact pass scan
-                }
-                flag = more || (ax < e);
-            }
-            const uint32_t m = __ballot_sync(GATB_FULL, flag);
-            if (m) {
-                if (flag) {
-                    QEntry en;
-                    en.s = s; en.e = e; en.is = i | slot24; en.j = j;
-                    queue[qn + __popc(m & lt_mask)] = en;
-                }
-                qn += __popc(m);
-                __syncwarp();
-                if (qn >= 32) {
-                    qn -= 32;
-                    resolve_entry<COUNTER>(filt, tile_g, h.uiv_off, h.uoff_off, h.cons_off, queue[qn + lane],
-                                           placed_key, p.sample_stride, s_begin, acc_s);
-                    __syncwarp();
-                }
-            }
+        const uint32_t i0 = 2u * (uint32_t)lane;
+        const uint32_t nl = n > i0 ? n - i0 : 0u;                      // this lane's pair of block b0 exists if b0 < nl
+        uint4 xa = (0u < nl) ? segs[0] : ones;                         // block b0      (64 segments per warp)
+        uint4 xb = (64u < nl) ? segs[32] : ones;                       // block b0 + 64
+        // one segment: test, compact the candidates onto the queue, resolve when 32 are waiting
+#define GATB_COUNT_ONE(S, E, I)                                                                            \
+        {                                                                                                  \
+            const uint32_t s_ = (S), e_ = (E);                                                             \
+            const uint32_t bs_ = min(s_ >> sh, nbits);                                                     \
+            const bool flag_ = (((bm[bs_ >> 5] >> (bs_ & 31u)) & 1u) != 0u) || (e_ - s_ > wlen);           \
+            const uint32_t m_ = __ballot_sync(GATB_FULL, flag_);                                           \
+            if (flag_) {                                                                                   \
+                QEntry en_;                                                                                \
+                en_.s = (int)s_; en_.e = (int)e_; en_.is = (I) | slot24;                                   \
+                queue[qn + __popc(m_ & lt_mask)] = en_;                                                    \
+            }                                                                                              \
+            qn += __popc(m_);                                                                              \
+            if (qn >= 32) {                                                                                \
+                __syncwarp();                                                                              \
+                qn -= 32;                                                                                  \
+                resolve_entry<COUNTER>(hs, filt, tile_g, queue[qn + lane], placed_key, p.sample_stride,    \
+                                       s_begin, acc_s);                                                    \
+                __syncwarp();                                                                              \
+            }                                                                                              \
         }
+#define GATB_COUNT_BLOCK(X, B0)                                                                            \
+        {                                                                                                  \
+            uint4 v_ = X;                                                                                  \
+            if ((B0) + 1u >= nl) { v_.z = ~0u; v_.w = ~0u; }          /* odd n: the pair's second slot */  \
+            X = ((B0) + 128u < nl) ? segs[((B0) + 128u) >> 1] : ones; /* prefetch, two blocks ahead */     \
+            GATB_COUNT_ONE(v_.y, v_.x, (B0) + i0)                                                          \
+            GATB_COUNT_ONE(v_.w, v_.z, (B0) + i0 + 1u)                                                     \
+        }
+        for (uint32_t b0 = 0; b0 < n; b0 += 128) {
+            GATB_COUNT_BLOCK(xa, b0)
+            if (b0 + 64 < n) GATB_COUNT_BLOCK(xb, b0 + 64u)
+        }
+#undef GATB_COUNT_BLOCK
+#undef GATB_COUNT_ONE
     }
     if (qn) {                                                          // drain once per key
+        __syncwarp();
         if ((uint32_t)lane < qn)
-            resolve_entry<COUNTER>(filt, tile_g, h.uiv_off, h.uoff_off, h.cons_off, queue[lane],
-                                   placed_key, p.sample_stride, s_begin, acc_s);
+            resolve_entry<COUNTER>(hs, filt, tile_g, queue[lane], placed_key, p.sample_stride, s_begin, acc_s);
         __syncwarp();
     }
 }
@@ -249,11 +267,11 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
         __syncthreads();                                  // previous filter fully consumed / acc init
         if (h.n_union == 0) continue;                     // no interval of any track on this key
         if (DENSITY && p.key_ws_nseg[k] == 0) continue;   // counter returns 0 (gat/Engine.pyx:1438-1440)
-        if (staged) {
-            // header + bin index + the union intervals actually present (+ 2 sentinels): ONE bulk copy
-            // by the TMA engine (cp.async.bulk, 1-D), completion signalled on an mbarrier; meanwhile the
-            // next key's filter is prefetched into L2
-            const uint32_t bytes = (h.uiv_off + (h.n_union + 2) * 8 + 15u) & ~15u;
+        {
+            // ONE bulk copy by the TMA engine (cp.async.bulk, 1-D), completion signalled on an mbarrier:
+            // header + bitmap + bin index + the intervals, or header + bitmap alone when the whole filter
+            // does not fit; meanwhile the next key's filter is prefetched into L2
+            const uint32_t bytes = staged ? h.stage_bytes : h.idx_off;
             if (threadIdx.x == 0) {
                 fence_proxy_async();                          // order earlier generic reads of filt_s before the async write
                 mbar_expect_tx(&stage_bar, bytes);
@@ -267,13 +285,10 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
             mbar_wait(&stage_bar, stage_phase);
             stage_phase ^= 1u;
         }
-        if (staged) {
-            if (h.nbins) count_key<COUNTER, true>(filt_s, tile_g, h, p, k, s_begin, s_end, lane, warp, nwarps, queue, acc_u);
-            else count_key<COUNTER, false>(filt_s, tile_g, h, p, k, s_begin, s_end, lane, warp, nwarps, queue, acc_u);
-        } else {
-            if (h.nbins) count_key<COUNTER, true>(tile_g, tile_g, h, p, k, s_begin, s_end, lane, warp, nwarps, queue, acc_u);
-            else count_key<COUNTER, false>(tile_g, tile_g, h, p, k, s_begin, s_end, lane, warp, nwarps, queue, acc_u);
-        }
+        const TileHeader *hs = reinterpret_cast<const TileHeader *>(filt_s);
+        const uint32_t *bm = reinterpret_cast<const uint32_t *>(filt_s + h.bm_off);
+        if (staged) count_key<COUNTER>(hs, bm, filt_s, tile_g, p, k, s_begin, s_end, lane, warp, nwarps, queue, acc_u);
+        else count_key<COUNTER>(hs, bm, tile_g, tile_g, p, k, s_begin, s_end, lane, warp, nwarps, queue, acc_u);
         if (DENSITY) {
             // per key: float(overlap) / len(workspace), accumulated in key order like the reference's
             // Python sum(): CPython >= 3.12 sums floats with Neumaier compensation (Python/bltinmodule.c)
@@ -330,11 +345,12 @@ cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int
 
 // ---------------------------------------------------------------------------------------------------
 // Tile construction on the device, one CTA per tile (replaces a host loop over every interval):
-//   A  merge the <= KMAX sorted track lists by start into cons[] (rank = own index + lower/upper bounds
-//      in the other lists: no sort, deterministic ties by slot) and validate the lists
-//   B  union: running max of ends over cons[] -> heads, union intervals, CSR offsets
+//   A  merge the <= KMAX sorted track lists by start into civ[] / cslot[] (rank = own index + lower/upper
+//      bounds in the other lists: no sort, deterministic ties by slot) and validate the lists
+//   B  union: running max of ends over civ[] -> heads, union intervals, CSR offsets
 //   C  sentinels + header
 //   D  bin index over the union ends
+//   E  occupancy bitmap of the union
 constexpr int BT = 256;
 
 __global__ void __launch_bounds__(BT) build_tiles_kernel(BuildTilesParams p)
@@ -349,9 +365,10 @@ __global__ void __launch_bounds__(BT) build_tiles_kernel(BuildTilesParams p)
     const TileHeader h = p.headers[tile];
     uint8_t *tp = p.tiles + p.tile_off[tile];
     uint16_t *idx = reinterpret_cast<uint16_t *>(tp + h.idx_off);
+    uint8_t *cslot = tp + h.cslot_off;
+    uint2 *civ = reinterpret_cast<uint2 *>(tp + h.civ_off);
     uint2 *uiv = reinterpret_cast<uint2 *>(tp + h.uiv_off);
     uint32_t *uoff = reinterpret_cast<uint32_t *>(tp + h.uoff_off);
-    uint4 *cons = reinterpret_cast<uint4 *>(tp + h.cons_off);
     if (tid < (uint32_t)KMAX) {
         uint64_t base = 0;
         uint32_t n = 0;
@@ -388,7 +405,8 @@ __global__ void __launch_bounds__(BT) build_tiles_kernel(BuildTilesParams p)
                 }
                 rank += lo;
             }
-            cons[rank] = make_uint4(x, y, kk, 0u);
+            civ[rank] = make_uint2(x, y);
+            cslot[rank] = (uint8_t)kk;
         }
     }
     if (err) atomicOr(p.error, err);
@@ -399,7 +417,7 @@ __global__ void __launch_bounds__(BT) build_tiles_kernel(BuildTilesParams p)
     const uint32_t chunk = (nc + BT - 1) / BT;
     const uint32_t lo = min(tid * chunk, nc), hi = min(lo + chunk, nc);
     int mx = -1;
-    for (uint32_t i = lo; i < hi; i++) mx = max(mx, (int)cons[i].y);
+    for (uint32_t i = lo; i < hi; i++) mx = max(mx, (int)civ[i].y);
     s_max[tid] = mx;
     __syncthreads();
     if (tid == 0) {                                  // exclusive prefix max over the chunks
@@ -412,7 +430,7 @@ __global__ void __launch_bounds__(BT) build_tiles_kernel(BuildTilesParams p)
         int run = carry;
         uint32_t heads = 0;
         for (uint32_t i = lo; i < hi; i++) {
-            const uint4 v = cons[i];
+            const uint2 v = civ[i];
             if ((int)v.x > run) heads++;             // starts a new union interval (touching ones merge)
             run = max(run, (int)v.y);
         }
@@ -430,7 +448,7 @@ __global__ void __launch_bounds__(BT) build_tiles_kernel(BuildTilesParams p)
         int run = carry;
         uint32_t u = s_cnt[tid];
         for (uint32_t i = lo; i < hi; i++) {
-            const uint4 v = cons[i];
+            const uint2 v = civ[i];
             if ((int)v.x > run) {
                 uiv[u].x = v.x;
                 uoff[u] = i;
@@ -446,13 +464,36 @@ __global__ void __launch_bounds__(BT) build_tiles_kernel(BuildTilesParams p)
         uiv[nu] = make_uint2(0x7fffffffu, 0x7fffffffu);
         uiv[nu + 1] = make_uint2(0x7fffffffu, 0x7fffffffu);
         uoff[nu] = nc;
+        civ[nc] = make_uint2(0x7fffffffu, 0x7fffffffu);
+        civ[nc + 1] = make_uint2(0x7fffffffu, 0x7fffffffu);
+        cslot[nc] = 0;
+        cslot[nc + 1] = 0;
         TileHeader out = h;
         out.n_union = nu;
         *reinterpret_cast<TileHeader *>(tp) = out;
     }
     __syncthreads();
 
-    // ---- D: bin index: idx[b] = first union interval with end > lowest position of bin b
+    // ---- E: occupancy bitmap of the union (bit b: some union interval touches [b << shift, (b+2) << shift))
+    {
+        uint32_t *bm = reinterpret_cast<uint32_t *>(tp + h.bm_off);
+        const uint32_t words = (h.idx_off - h.bm_off) >> 2;
+        for (uint32_t w = tid; w < words; w += BT) bm[w] = 0u;
+        __syncthreads();
+        for (uint32_t u = tid; u < nu; u += BT) {
+            const uint2 v = uiv[u];
+            uint32_t b0 = v.x >> h.bm_shift;
+            const uint32_t b1 = min((v.y - 1u) >> h.bm_shift, h.bm_bits - 1u);
+            if (b0 >= h.bm_bits) continue;           // only with invalid lists, which are rejected anyway
+            if (b0 > 0) b0--;                        // the window of bit b reaches one bin to the right
+            for (uint32_t w = b0 >> 5; w <= (b1 >> 5) && b0 <= b1; w++) {
+                const uint32_t lo = (w == (b0 >> 5)) ? (b0 & 31u) : 0u, hi = (w == (b1 >> 5)) ? (b1 & 31u) : 31u;
+                atomicOr(&bm[w], (0xffffffffu >> (31u - hi)) & (0xffffffffu << lo));
+            }
+        }
+    }
+
+    // ---- D: bin index: idx[b] = first interval of the first union interval with end > lowest position of bin b
     if (h.nbins) {
         for (uint32_t b = tid; b <= h.nbins; b += BT) {
             uint32_t l2 = 0, h2 = nu;
@@ -463,7 +504,7 @@ __global__ void __launch_bounds__(BT) build_tiles_kernel(BuildTilesParams p)
                     if ((uint64_t)uiv[mid].y <= pos) l2 = mid + 1; else h2 = mid;
                 }
             } else l2 = nu;
-            idx[b] = (uint16_t)l2;
+            idx[b] = (uint16_t)uoff[l2];             // uoff[nu] == n_cons -> the sentinel
         }
     }
 }

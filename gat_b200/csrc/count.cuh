@@ -14,28 +14,37 @@ constexpr int KMAX = 8;                 // annotation tracks per tile (register 
 // Tile = up to KMAX annotation tracks on ONE key (contig), contiguous in global memory:
 //
 //   TileHeader
-//   uint16 idx[nbins+1]      bin index over the UNION of the tracks' intervals        } "filter":
-//   uint2  uiv[n_union+2]    union intervals (sorted, disjoint) + 2 sentinels         } staged in smem
-//   uint32 uoff[n_union+1]   CSR: constituents of union interval u = cons[uoff[u] .. uoff[u+1])
-//   uint4  cons[n_cons]      every interval of every track as (start, end, slot, 0), sorted by start
+//   uint32 bm[bm_words]      occupancy bitmap of the UNION of the tracks' intervals      } "filter":
+//   uint16 idx[nbins+1]      bin index: where in civ[] a query starting in the bin begins } staged in
+//   uint8  cslot[n_cons+2]   track slot of civ[c]                                        } shared
+//   uint2  civ[n_cons+2]     every interval of every track, sorted by start, + 2 sentinels } memory
+//   uint2  uiv[n_union+2]    union intervals (sorted, disjoint) + 2 sentinels   } global memory only: build
+//   uint32 uoff[n_union+1]   union interval u = civ[uoff[u] .. uoff[u+1])       } time, and the nbins == 0 path
 //
 // About 93 % of the simulated segments overlap no interval of ANY of the 8 tracks.  The count kernel
-// therefore tests a segment once against the union (one bin probe + two 8-byte shared-memory loads)
-// and only the segments that hit the union go on to the exact per-track pass over the constituents
-// (which stay in global memory / L2).  idx[b] = first union interval whose end is > the lowest
-// position of bin b, bin(x) = umulhi(x, inv) -- a one-probe replacement for the binary search
-// (utils/gat_utils.c:8-32) over sorted interval ends; nbins == 0 (more than 65534 union intervals)
-// falls back to that binary search.
+// therefore tests a segment first against the bitmap -- bit b is set when a union interval touches
+// positions [b << bm_shift, (b+2) << bm_shift); one 4-byte shared-memory load answers "can [s,e) overlap
+// anything?" for every segment no longer than 1 << bm_shift, longer ones are candidates outright -- and
+// only the candidates go on, through a per-warp queue, to the exact pass: idx[bin(s)] = uoff[first union
+// interval whose end is > the lowest position of the bin], bin(x) = umulhi(x, inv) -- a one-probe
+// replacement for the binary search (utils/gat_utils.c:8-32) over sorted interval ends; every interval
+// overlapping [s,e) lies at or after that index, so a forward walk over civ[] until start >= e, skipping
+// ends <= s, visits them all, entirely in shared memory.  nbins == 0 (more than 65534 intervals) falls
+// back to the binary search over uiv[] in global memory.
 struct TileHeader {
     uint32_t n_union;       // written by the build kernel
     uint32_t n_cons;
     uint32_t nbins;
     uint32_t inv;           // bin(x) = min(umulhi(x, inv), nbins)
-    uint32_t idx_off;       // byte offsets from the tile start
+    uint32_t bm_off;        // byte offsets from the tile start; bitmap: one zero word of padding at the end
+    uint32_t bm_shift;      // log2 of the positions per bit
+    uint32_t bm_bits;       // bits that can be set: positions >= bm_bits << bm_shift hold no interval
+    uint32_t idx_off;       // [0, idx_off) = header + bitmap: staged for every tile
+    uint32_t cslot_off;
+    uint32_t civ_off;
+    uint32_t stage_bytes;   // [0, stage_bytes) = header .. civ: staged when it fits
     uint32_t uiv_off;
     uint32_t uoff_off;
-    uint32_t cons_off;
-    uint32_t stage_bytes;   // header + idx + uiv sized for n_union == n_cons (upper bound)
     uint32_t pad[3];
 };
 
