@@ -71,14 +71,6 @@ def sampleTrack(track_index, segs, annotations, workspace, sampler, counters, nu
     atracks = list(annotations.tracks)
     if not problem.unit_keys:
         return atracks, [np.zeros((num_samples, len(atracks))) for _ in counters], np.zeros(3, dtype=np.uint64)
-    key = tuple(problem.contigs)
-    if annos_cache is not None and key in annos_cache:
-        annos = annos_cache[key]
-    else:
-        _, lists, nseg = buildContigAnnotations(annotations, workspace, problem.contigs)
-        annos = device.Annotations(ctx, lists, key_ws_nseg=nseg)
-        if annos_cache is not None:
-            annos_cache[key] = annos
     try:
         smp = device.Sampler(ctx, problem.unit_contig, len(problem.contigs), problem.has_isochores,
                              problem.unit_segments, problem.unit_workspace,
@@ -92,6 +84,16 @@ def sampleTrack(track_index, segs, annotations, workspace, sampler, counters, nu
             smp.set_kind(sampler.kind)
         except device._lib.GatB200Error as e:
             raise AssertionError(str(e))       # the reference's counters assert on unnormalized samples
+    # (the sampler first: its small uploads must not queue behind the annotation arrays on the copy
+    # engine; the annotations then upload and build while the placement kernel runs)
+    key = tuple(problem.contigs)
+    if annos_cache is not None and key in annos_cache:
+        annos = annos_cache[key]
+    else:
+        _, lists, nseg = buildContigAnnotations(annotations, workspace, problem.contigs)
+        annos = device.Annotations(ctx, lists, key_ws_nseg=nseg, lazy=True)
+        if annos_cache is not None:
+            annos_cache[key] = annos
     begin, end = sample_range if sample_range is not None else (0, num_samples)
     n_local = end - begin
     dev = torch.device("cuda", ctx.device)

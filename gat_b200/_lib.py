@@ -17,7 +17,8 @@ ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_TOO_LARGE, ERR_RANGE = -1, -2, -3, -4, 
 SYMBOLS = [
     "gatb_version", "gatb_create", "gatb_destroy", "gatb_last_error", "gatb_set_stream",
     "gatb_synchronize", "gatb_launch_count", "gatb_set_batch_size", "gatb_profile", "gatb_profile_read",
-    "gatb_annotations_create", "gatb_annotations_destroy", "gatb_count_lists",
+    "gatb_annotations_create", "gatb_annotations_create_async", "gatb_annotations_wait",
+    "gatb_annotations_destroy", "gatb_count_lists",
     "gatb_sampler_create", "gatb_sampler_destroy", "gatb_sampler_sample_capacity",
     "gatb_sampler_set_kind", "gatb_sampler_place", "gatb_run", "gatb_column_stats",
 ]
@@ -67,6 +68,10 @@ def load():
     L.gatb_profile_read.argtypes = [vp, vp, vp]
     L.gatb_annotations_create.restype = i32
     L.gatb_annotations_create.argtypes = [vp, i32, i32, vp, vp, vp, vp, ctypes.POINTER(vp)]
+    L.gatb_annotations_create_async.restype = i32
+    L.gatb_annotations_create_async.argtypes = [vp, i32, i32, vp, vp, vp, vp, ctypes.POINTER(vp)]
+    L.gatb_annotations_wait.restype = i32
+    L.gatb_annotations_wait.argtypes = [vp]
     L.gatb_annotations_destroy.restype = None
     L.gatb_annotations_destroy.argtypes = [vp]
     L.gatb_count_lists.restype = i32

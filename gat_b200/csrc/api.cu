@@ -23,6 +23,9 @@ struct gatb_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t upload_stream = nullptr;   // gatb_annotations_create_async: copies + tile build, off the compute stream
+    uint32_t *err_slots = nullptr;          // pinned validation words of pending asynchronous creates
+    std::vector<int> err_free;
     std::string err;
     uint64_t launches = 0;
     uint32_t batch = 0;                 // 0 = default
@@ -41,18 +44,18 @@ struct gatb_ctx {
 enum { PROF_PLACE = 0, PROF_MERGE = 1, PROF_COUNT = 2, PROF_OTHER = 3, PROF_NCLS = 4 };
 
 struct ProfScope {
-    gatb_ctx *ctx; int cls; cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(gatb_ctx *c, int k) : ctx(c), cls(k)
+    gatb_ctx *ctx; int cls; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(gatb_ctx *c, int k, cudaStream_t stream = nullptr) : ctx(c), cls(k), st(stream ? stream : c->stream)
     {
         ctx->launches++;
         if (!ctx->profiling) return;
         cudaEventCreate(&a); cudaEventCreate(&b);
-        cudaEventRecord(a, ctx->stream);
+        cudaEventRecord(a, st);
     }
     ~ProfScope()
     {
         if (!a) return;
-        cudaEventRecord(b, ctx->stream);
+        cudaEventRecord(b, st);
         ctx->spans.push_back({cls, a, b});
     }
 };
@@ -133,6 +136,10 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, GATB_ERR_CUDA, cudaGetErrorString(e)); }
     ctx->stream = ctx->own_stream;
+    e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->err_slots, 256 * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaStreamDestroy(ctx->own_stream); delete ctx; return fail(nullptr, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    for (int i = 255; i >= 0; i--) ctx->err_free.push_back(i);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     {
@@ -157,6 +164,8 @@ extern "C" void gatb_destroy(gatb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+    if (ctx->err_slots) cudaFreeHost(ctx->err_slots);
     delete ctx;
 }
 
@@ -245,7 +254,32 @@ struct gatb_annotations {
     DevBuf<uint32_t> tile_stage;
     DevBuf<uint32_t> key_ws_nseg;
     bool has_nseg = false;
+    // asynchronous create: `ready` is recorded on the upload stream after the tile build; until the
+    // first wait the validation word (pinned, err_slot) has not been looked at
+    cudaEvent_t ready = nullptr;
+    int err_slot = -1;
+    bool pending = false;
+    int status = GATB_OK;
+    ~gatb_annotations()
+    {
+        if (ready) { cudaEventSynchronize(ready); cudaEventDestroy(ready); }
+        if (err_slot >= 0) ctx->err_free.push_back(err_slot);
+    }
 };
+
+// host-blocking: the asynchronous build has finished; -> validation result
+static int annotations_finish(gatb_annotations *a)
+{
+    if (!a->pending) return a->status;
+    gatb_ctx *ctx = a->ctx;
+    a->pending = false;
+    cudaError_t e = cudaEventSynchronize(a->ready);
+    if (e != cudaSuccess) return a->status = fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e));
+    const uint32_t h_err = ctx->err_slots[a->err_slot];
+    if (h_err & 1u) return a->status = fail(ctx, GATB_ERR_RANGE, "annotations: coordinate >= 2^31");
+    if (h_err) return a->status = fail(ctx, GATB_ERR_INVALID, "annotations: empty or inverted segment, or list not sorted/normalized");
+    return a->status = GATB_OK;
+}
 
 static inline uint64_t align16(uint64_t x) { return (x + 15u) & ~(uint64_t)15u; }
 
@@ -324,9 +358,9 @@ static bool tile_geometry(const uint64_t *offs, const uint32_t *end, uint32_t A,
     return true;
 }
 
-extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
-                                       const uint32_t *start, const uint32_t *end, const uint32_t *key_ws_nseg,
-                                       gatb_annotations **out)
+extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
+                                             const uint32_t *start, const uint32_t *end, const uint32_t *key_ws_nseg,
+                                             gatb_annotations **out)
 {
     if (!ctx || !out) return GATB_ERR_INVALID;
     *out = nullptr;
@@ -339,7 +373,8 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
         if (offs[l + 1] < offs[l]) return fail(ctx, GATB_ERR_INVALID, "annotations: offsets not monotone");
     if (offs[n_lists] > 0xffffffffull) return fail(ctx, GATB_ERR_INVALID, "annotations: more than 2^32 intervals");
     CU(ctx, cudaSetDevice(ctx->device));
-    tl_stream = ctx->stream;
+    if (ctx->err_free.empty()) return fail(ctx, GATB_ERR_INVALID, "annotations: more than 256 sets pending validation");
+    tl_stream = ctx->upload_stream;       // every allocation, copy and free below is ordered on the upload stream
 
     const uint32_t A = (uint32_t)n_annot, K = (uint32_t)n_keys;
     const uint32_t bin_factor = std::max(1u, env_u32("GATB_BIN_FACTOR", 4));
@@ -388,19 +423,23 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
     a->max_stage = max_stage;
     a->max_prefix = max_prefix;
     a->n_intervals = offs[n_lists];
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->upload_stream;
     DevBuf<uint64_t> d_offs;
     DevBuf<uint32_t> d_start, d_end, d_err;
     DevBuf<TileHeader> d_headers;
-    uint32_t h_err = 0;
+    a->err_slot = ctx->err_free.back();
+    ctx->err_free.pop_back();
+    ctx->err_slots[a->err_slot] = 0;
+    // the small host-built tables first (pageable memory: staged before the call returns), then the
+    // caller's arrays, which must stay valid until gatb_annotations_wait() or the first use returns
     cudaError_t e = a->tiles.alloc(total);
     if (e == cudaSuccess) e = a->tile_off.upload(tile_off.data(), tile_off.size(), st);
     if (e == cudaSuccess) e = a->tile_stage.upload(tile_stage.data(), tile_stage.size(), st);
+    if (e == cudaSuccess) e = d_headers.upload(headers.data(), headers.size(), st);
     if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, st); a->has_nseg = true; }
     if (e == cudaSuccess) e = d_offs.upload(offs, n_lists + 1, st);
     if (e == cudaSuccess) e = d_start.upload(start, offs[n_lists], st);
     if (e == cudaSuccess) e = d_end.upload(end, offs[n_lists], st);
-    if (e == cudaSuccess) e = d_headers.upload(headers.data(), headers.size(), st);
     if (e == cudaSuccess) e = d_err.alloc(1);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_err.p, 0, sizeof(uint32_t), st);
     if (e == cudaSuccess) {
@@ -408,26 +447,47 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
         bp.tiles = a->tiles.p; bp.tile_off = a->tile_off.p; bp.headers = d_headers.p;
         bp.offs = d_offs.p; bp.start = d_start.p; bp.end = d_end.p;
         bp.n_annot = A; bp.n_keys = K; bp.n_groups = G; bp.ka = ka; bp.error = d_err.p;
-        ProfScope ps(ctx, PROF_OTHER);
+        ProfScope ps(ctx, PROF_OTHER, st);
         launch_build_tiles(st, bp);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_err, d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // host vectors die at return
-    if (e != cudaSuccess) { delete a; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
-    if (h_err) {
-        delete a;
-        if (h_err & 1u) return fail(ctx, GATB_ERR_RANGE, "annotations: coordinate >= 2^31");
-        return fail(ctx, GATB_ERR_INVALID, "annotations: empty or inverted segment, or list not sorted/normalized");
-    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->err_slots + a->err_slot, d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(a->ready, st);
+    if (e != cudaSuccess) { cudaStreamSynchronize(st); delete a; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    a->pending = true;
     *out = a;
-    return GATB_OK;
+    return GATB_OK;       // (the temporaries are freed in stream order, after the build kernel)
+}
+
+extern "C" int gatb_annotations_wait(gatb_annotations *a)
+{
+    if (!a) return GATB_ERR_INVALID;
+    cudaSetDevice(a->ctx->device);
+    return annotations_finish(a);
+}
+
+extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
+                                       const uint32_t *start, const uint32_t *end, const uint32_t *key_ws_nseg,
+                                       gatb_annotations **out)
+{
+    int rc = gatb_annotations_create_async(ctx, n_annot, n_keys, offs, start, end, key_ws_nseg, out);
+    if (rc) return rc;
+    rc = annotations_finish(*out);
+    if (rc) {
+        tl_stream = ctx->stream;
+        delete *out;
+        *out = nullptr;
+    }
+    return rc;
 }
 
 extern "C" void gatb_annotations_destroy(gatb_annotations *a)
 {
     if (!a) return;
     cudaSetDevice(a->ctx->device);
+    // free in the order of the compute stream, where the tiles were last read
+    a->tiles.st = a->tile_off.st = a->tile_stage.st = a->key_ws_nseg.st = a->ctx->stream;
     delete a;
 }
 
@@ -473,6 +533,8 @@ extern "C" int gatb_count_lists(gatb_ctx *ctx, const gatb_annotations *annos, in
             return fail(ctx, GATB_ERR_INVALID, "nucleotide-density needs key_ws_nseg at gatb_annotations_create");
     }
     CU(ctx, cudaSetDevice(ctx->device));
+    rc = annotations_finish(const_cast<gatb_annotations *>(annos));
+    if (rc) return rc;
     tl_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
 
@@ -866,6 +928,7 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
     if (any_density && (!annos->has_nseg || !out_density)) return fail(ctx, GATB_ERR_INVALID, "nucleotide-density needs key_ws_nseg and out_density");
     if (any_int && !out_counts) return fail(ctx, GATB_ERR_INVALID, "run: out_counts is NULL");
     if (n_samples == 0) return GATB_OK;
+    if (!annos->pending && annos->status) return fail(ctx, annos->status, "run: the annotations failed validation");
     CU(ctx, cudaSetDevice(ctx->device));
     tl_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
@@ -895,6 +958,9 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
             double *dst_f = out_density ? out_density + done * A : nullptr;
             p.out_u32 = out_is_device ? dst_u : s->out_tmp.p;
             p.out_f64 = out_is_device ? dst_f : s->out_tmp_f.p;
+            // annotations still uploading / building (gatb_annotations_create_async): the placement above
+            // did not need them, the count does
+            if (annos->pending) CU(ctx, cudaStreamWaitEvent(st, annos->ready, 0));
             { ProfScope ps(ctx, PROF_COUNT); CU(ctx, launch_count(st, counters[c], p, ctx->count_threads)); }
             if (!out_is_device) {
                 if (dens) CU(ctx, cudaMemcpyAsync(dst_f, s->out_tmp_f.p, (uint64_t)b * A * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -906,6 +972,8 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
     CU(ctx, cudaMemcpyAsync(tally, s->tally.p, sizeof(tally), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     if (info) { info[0] = tally[0]; info[1] = tally[1]; info[2] = tally[2]; }
+    rc = annotations_finish(const_cast<gatb_annotations *>(annos));      // invalid lists: the counts mean nothing
+    if (rc) return rc;
     if (tally[2]) return fail(ctx, GATB_ERR_CAPACITY, "placement unit overflowed its segment buffer");
     return GATB_OK;
 }

@@ -382,28 +382,52 @@ __global__ void __launch_bounds__(BT) build_tiles_kernel(BuildTilesParams p)
     }
     __syncthreads();
 
-    // ---- A: rank merge + validation
+    // ---- A: rank merge + validation.  Warp = list, lane = a contiguous chunk of it: the ranks of
+    // consecutive elements in the other lists only move forward, so after one binary search per list
+    // for the chunk's first element the lane just gallops
     uint32_t err = 0;
-    for (uint32_t kk = 0; kk < (uint32_t)KMAX; kk++) {
+    for (uint32_t kk = tid >> 5; kk < (uint32_t)KMAX; kk += BT / 32) {
         const uint32_t n = s_n[kk];
         const uint32_t *ls = p.start + s_base[kk], *le = p.end + s_base[kk];
-        for (uint32_t i = tid; i < n; i += BT) {
+        const uint32_t chunk = (n + 31u) / 32u;
+        const uint32_t lo = min((tid & 31u) * chunk, n), hi = min(lo + chunk, n);
+        if (lo >= hi) continue;
+        uint32_t pos[KMAX];
+        const uint32_t x0 = ls[lo];
+#pragma unroll
+        for (uint32_t t = 0; t < (uint32_t)KMAX; t++) {
+            pos[t] = 0;
+            const uint32_t m = s_n[t];
+            if (t == kk || m == 0) continue;
+            const uint32_t *os = p.start + s_base[t];
+            uint32_t l2 = 0, h2 = m;                 // elements of list t placed before (x0, kk)
+            while (l2 < h2) {
+                const uint32_t mid = (l2 + h2) >> 1;
+                const uint32_t v = os[mid];
+                if (v < x0 || (v == x0 && t < kk)) l2 = mid + 1; else h2 = mid;
+            }
+            pos[t] = l2;
+        }
+        uint32_t py = lo > 0 ? le[lo - 1] : 0u;
+        for (uint32_t i = lo; i < hi; i++) {
             const uint32_t x = ls[i], y = le[i];
             if (y >= 0x80000000u) err |= 1u;
             if (x >= y) err |= 2u;
-            if (i > 0 && le[i - 1] > x) err |= 2u;
+            if (i > 0 && py > x) err |= 2u;
+            py = y;
             uint32_t rank = i;
+#pragma unroll
             for (uint32_t t = 0; t < (uint32_t)KMAX; t++) {
                 const uint32_t m = s_n[t];
                 if (t == kk || m == 0) continue;
                 const uint32_t *os = p.start + s_base[t];
-                uint32_t lo = 0, hi = m;             // elements of list t placed before (x, kk)
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    const uint32_t v = os[mid];
-                    if (v < x || (v == x && t < kk)) lo = mid + 1; else hi = mid;
+                uint32_t q = pos[t];
+                while (q < m) {
+                    const uint32_t v = os[q];
+                    if (v < x || (v == x && t < kk)) q++; else break;
                 }
-                rank += lo;
+                pos[t] = q;
+                rank += q;
             }
             civ[rank] = make_uint2(x, y);
             cslot[rank] = (uint8_t)kk;
@@ -493,18 +517,23 @@ __global__ void __launch_bounds__(BT) build_tiles_kernel(BuildTilesParams p)
         }
     }
 
-    // ---- D: bin index: idx[b] = first interval of the first union interval with end > lowest position of bin b
+    // ---- D: bin index: idx[b] = first interval of the first union interval with end > lowest position of
+    // bin b.  Scattered from the union side: union u owns the bins whose lowest position lies in
+    // [end(u-1), end(u)); the first bin whose lowest position is >= y is bin(y - 1) + 1.
     if (h.nbins) {
-        for (uint32_t b = tid; b <= h.nbins; b += BT) {
-            uint32_t l2 = 0, h2 = nu;
-            if (b < h.nbins) {
-                const uint64_t pos = (((uint64_t)b << 32) + h.inv - 1) / h.inv;
-                while (l2 < h2) {
-                    const uint32_t mid = (l2 + h2) >> 1;
-                    if ((uint64_t)uiv[mid].y <= pos) l2 = mid + 1; else h2 = mid;
-                }
-            } else l2 = nu;
-            idx[b] = (uint16_t)uoff[l2];             // uoff[nu] == n_cons -> the sentinel
+        for (uint32_t u = tid; u <= nu; u += BT) {
+            const uint32_t yp = u > 0 ? uiv[u - 1].y : 0u;
+            const uint32_t b_lo = yp ? min(__umulhi(yp - 1u, h.inv) + 1u, h.nbins) : 0u;
+            uint32_t b_hi, val;
+            if (u < nu) {
+                const uint32_t y = uiv[u].y;
+                b_hi = y ? min(__umulhi(y - 1u, h.inv) + 1u, h.nbins) : 0u;
+                val = uoff[u];
+            } else {
+                b_hi = h.nbins + 1u;                 // the rest, including entry nbins: the sentinel
+                val = nc;
+            }
+            for (uint32_t b = b_lo; b < b_hi; b++) idx[b] = (uint16_t)val;
         }
     }
 }

@@ -134,8 +134,12 @@ class Annotations(object):
 
     lists[a][k]: intervals of track a on key k (n_annot x n_keys)."""
 
-    def __init__(self, ctx, lists, key_ws_nseg=None, csr=None):
-        """lists[a][k], or csr=(n_annot, n_keys, offs, start, end) already flattened annotation-major"""
+    def __init__(self, ctx, lists, key_ws_nseg=None, csr=None, lazy=False):
+        """lists[a][k], or csr=(n_annot, n_keys, offs, start, end) already flattened annotation-major.
+
+        lazy: gatb_annotations_create_async -- upload and tile build run on the library's upload stream
+        while the caller goes on (e.g. to the placement kernel); the first run / count_lists waits on the
+        device and reports invalid lists.  The arrays are kept alive here until then."""
         self.ctx = ctx
         if csr is not None:
             self.n_annot, self.n_keys, offs, start, end = csr
@@ -146,15 +150,23 @@ class Annotations(object):
             offs, start, end = to_csr(flat)
         nseg = None if key_ws_nseg is None else np.ascontiguousarray(key_ws_nseg, dtype=np.uint32)
         h = ctypes.c_void_p()
-        ctx.check(ctx.lib.gatb_annotations_create(ctx.handle, self.n_annot, self.n_keys, _p(offs), _p(start),
-                                                  _p(end), _p(nseg), ctypes.byref(h)))
+        create = ctx.lib.gatb_annotations_create_async if lazy else ctx.lib.gatb_annotations_create
+        ctx.check(create(ctx.handle, self.n_annot, self.n_keys, _p(offs), _p(start), _p(end), _p(nseg),
+                         ctypes.byref(h)))
         self.handle = h
         self.n_intervals = int(offs[-1])
+        self._pending = (offs, start, end, nseg) if lazy else None
+
+    def wait(self):
+        """block until an asynchronous build has finished; raises if the lists were invalid"""
+        self.ctx.check(self.ctx.lib.gatb_annotations_wait(self.handle))
+        self._pending = None
 
     def close(self):
         if getattr(self, "handle", None):
-            self.ctx.lib.gatb_annotations_destroy(self.handle)
+            self.ctx.lib.gatb_annotations_destroy(self.handle)       # waits for a pending build
             self.handle = None
+            self._pending = None
 
     def __del__(self):
         try:

@@ -241,3 +241,40 @@ def test_sampler_segments_matches_oracle(ctx, oracle):
     with pytest.raises(_lib.GatB200Error):
         smp.set_kind("segments")
     smp.close()
+
+
+def test_async_annotations_same_counts_and_deferred_errors(ctx, oracle):
+    """gatb_annotations_create_async: upload + tile build on the upload stream; the first run waits on the
+    device.  Counts equal the synchronous path; invalid lists surface at wait() / at the run that used them"""
+    from gat_b200 import device, _lib
+    rng = np.random.default_rng(123)
+    pr = helpers.random_problem(rng, n_contigs=3, n_iso=0, n_annot=9)
+    smp = device.Sampler(ctx, pr["unit_contig"], pr["n_contigs"], False, pr["unit_segments"], pr["unit_workspace"])
+    sync = device.Annotations(ctx, pr["annotations"], key_ws_nseg=pr["cws_nseg"])
+    want, _ = smp.run(sync, COUNTERS, seed=8, track=0, sample_begin=0, n_samples=40)
+    for use_wait in (False, True):
+        lazy = device.Annotations(ctx, pr["annotations"], key_ws_nseg=pr["cws_nseg"], lazy=True)
+        if use_wait:
+            lazy.wait()
+        got, _ = smp.run(lazy, COUNTERS, seed=8, track=0, sample_begin=0, n_samples=40)
+        for name in COUNTERS:
+            assert np.array_equal(np.asarray(got[name]), np.asarray(want[name])), (use_wait, name)
+        lazy.close()
+    # destroyed while still pending: must not crash or leak the validation slot
+    for _ in range(300):
+        device.Annotations(ctx, pr["annotations"], lazy=True).close()
+    bad_lists = [[np.array([[10, 20], [15, 40]], dtype=np.uint32) for _ in range(pr["n_contigs"])]]
+    bad = device.Annotations(ctx, bad_lists, lazy=True)
+    with pytest.raises(_lib.GatB200Error) as e:
+        bad.wait()
+    assert e.value.code == _lib.ERR_INVALID
+    with pytest.raises(_lib.GatB200Error):
+        smp.run(bad, ["nucleotide-overlap"], seed=8, track=0, sample_begin=0, n_samples=4)
+    bad.close()
+    bad = device.Annotations(ctx, bad_lists, lazy=True)
+    with pytest.raises(_lib.GatB200Error) as e:                      # first use reports it
+        smp.run(bad, ["nucleotide-overlap"], seed=8, track=0, sample_begin=0, n_samples=4)
+    assert e.value.code == _lib.ERR_INVALID
+    bad.close()
+    sync.close()
+    smp.close()

@@ -28,12 +28,19 @@ def P(csr):
 pa, ps, pw = P(wl["anno_csr"]), P(wl["seg_csr"]), P(wl["ws_csr"])
 host = torch.empty((B, Aa), dtype=torch.int32).pin_memory(); hnp = host.numpy().view(np.uint32)
 ids = device.counter_ids([args.counter]); info = np.zeros(3, dtype=np.uint64)
+lazy = 'lazy' in sys.argv
+ctx.profile(True)
 for it in range(4):
     t = [time.perf_counter()]
-    a2 = device.Annotations(ctx, None, key_ws_nseg=wl["nseg"], csr=(Aa, C) + pa); ctx.synchronize(); t.append(time.perf_counter())
-    s2 = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(ps, pw)); ctx.synchronize(); t.append(time.perf_counter())
+    if lazy: s2 = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(ps, pw))
+    a2 = device.Annotations(ctx, None, key_ws_nseg=wl["nseg"], csr=(Aa, C) + pa, lazy=lazy)
+    if not lazy: ctx.synchronize()
+    t.append(time.perf_counter())
+    if not lazy: s2 = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(ps, pw)); ctx.synchronize()
+    t.append(time.perf_counter())
     ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), 1, 0, it * B, B, device._p(hnp), None, 0, device._p(info))); t.append(time.perf_counter())
     s2.close(); t.append(time.perf_counter())
     a2.close(); t.append(time.perf_counter())
     names = ["annotations_create", "sampler_create", "run", "sampler_destroy", "annotations_destroy"]
     print(it, " ".join("%s=%.1fms" % (n, 1e3 * (t[i + 1] - t[i])) for i, n in enumerate(names)), "total=%.1fms" % (1e3 * (t[-1] - t[0])))
+print("kernel classes (ms, launches) over 4 steps:", ctx.profile_read())
