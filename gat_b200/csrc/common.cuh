@@ -201,11 +201,74 @@ __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n
     return nout;
 }
 
-// sort + merge(0) of n arbitrary packed segments in a buffer with at least next_pow2(n) slots
-__device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n)
+// ---------------------------------------------------------------------------------------------------
+// Counting sort for placements: their starts are spread evenly over the workspace, so bucketing by
+// start (NB buckets over [min, max]) leaves about one key per bucket; a key's final position is its
+// bucket's offset plus its rank among the bucket's few keys.  O(n) instead of the bitonic network's
+// O(n log^2 n).  `tmp` = n free slots (not overlapping buf), `cnt` = GATB_SORT_NB words of this warp's
+// shared memory.  Returns false, with buf untouched, when the keys are too clustered to gain anything
+// (fragmented workspaces); the caller then runs the bitonic sort.  Equal keys are interchangeable, so
+// the result is the same sequence either way.
+constexpr uint32_t GATB_SORT_NB = 512;
+
+__device__ __forceinline__ bool warp_bucket_sort(uint64_t *buf, uint32_t n, uint64_t *tmp, uint32_t *cnt)
+{
+    const int lane = lane_id();
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t s = seg_start(buf[i]);
+        lo = min(lo, s); hi = max(hi, s);
+    }
+    lo = __reduce_min_sync(GATB_FULL, lo);
+    hi = __reduce_max_sync(GATB_FULL, hi);
+    const uint32_t NB = min(GATB_SORT_NB, max(64u, next_pow2(n)));
+    const uint64_t q = ((uint64_t)NB << 32) / ((uint64_t)(hi - lo) + 1u);
+    const uint32_t inv = q > 0xffffffffull ? 0xffffffffu : (uint32_t)q;
+    for (uint32_t b = lane; b < NB; b += 32) cnt[b] = 0u;
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32)
+        atomicAdd(&cnt[min(__umulhi(seg_start(buf[i]) - lo, inv), NB - 1u)], 1u);
+    __syncwarp();
+    uint32_t base = 0, mx = 0;                      // counts -> exclusive offsets, 32 buckets at a time
+    for (uint32_t r = 0; r < NB; r += 32) {
+        const uint32_t v = cnt[r + lane];
+        mx = max(mx, v);
+        const uint32_t incl = warp_incl_scan_add_u32(v);
+        cnt[r + lane] = base + incl - v;
+        base += __shfl_sync(GATB_FULL, incl, 31);
+    }
+    mx = __reduce_max_sync(GATB_FULL, mx);
+    __syncwarp();
+    if (mx > 64u && mx > 8u * (n / NB + 1u)) return false;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint64_t key = buf[i];
+        tmp[atomicAdd(&cnt[min(__umulhi(seg_start(key) - lo, inv), NB - 1u)], 1u)] = key;
+    }
+    __syncwarp();                                   // now cnt[b] = end of bucket b = start of bucket b + 1
+    for (uint32_t j = lane; j < n; j += 32) {
+        const uint64_t key = tmp[j];
+        const uint32_t b = min(__umulhi(seg_start(key) - lo, inv), NB - 1u);
+        const uint32_t first = b ? cnt[b - 1u] : 0u, last = cnt[b];
+        uint32_t r = 0;
+        for (uint32_t k = first; k < last; k++) {
+            const uint64_t other = tmp[k];
+            r += (other < key || (other == key && k < j)) ? 1u : 0u;
+        }
+        buf[first + r] = key;
+    }
+    __syncwarp();
+    return true;
+}
+
+// sort + merge(0) of n arbitrary packed segments in a buffer with at least next_pow2(n) slots; with
+// `tmp` (n more free slots) and `cnt` given, mid-sized runs take the counting sort
+__device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n, uint64_t *tmp = nullptr,
+                                                     uint32_t *cnt = nullptr)
 {
     if (n == 0) return 0;
     const int lane = lane_id();
+    if (tmp != nullptr && n >= 96u && n <= 32768u && warp_bucket_sort(buf, n, tmp, cnt))
+        return warp_merge0_sorted(buf, n);
     uint32_t N = next_pow2(n);
     for (uint32_t i = n + lane; i < N; i += 32) buf[i] = GATB_KEY_INF;
     __syncwarp();

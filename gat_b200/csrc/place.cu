@@ -152,11 +152,16 @@ __device__ __forceinline__ uint32_t warp_filter_ws(uint64_t *buf, uint32_t n, co
 
 // ---------------------------------------------------------------------------------------------------
 // K1: one warp per (unit, sample)
-__global__ void __launch_bounds__(128) place_kernel(PlaceParams p)
+#ifndef GATB_PLACE_MINBLOCKS
+#define GATB_PLACE_MINBLOCKS 8      // 64 registers: occupancy beats the few spilled values (measured)
+#endif
+__global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceParams p)
 {
+    __shared__ uint32_t sort_cnt[4][GATB_SORT_NB];         // counting-sort buckets, one set per warp
     const uint64_t item = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (item >= (uint64_t)p.n_units * p.n_samples) return;
     const int lane = lane_id();
+    uint32_t *cnt = sort_cnt[threadIdx.x >> 5];
     const uint32_t unit = p.order[item / p.n_samples];
     const uint32_t sl = (uint32_t)(item % p.n_samples);
     const UnitDesc d = p.units[unit];
@@ -214,7 +219,10 @@ __global__ void __launch_bounds__(128) place_kernel(PlaceParams p)
             // late checkpoints add a handful of placements to an already merged list: insert them
             // instead of re-sorting everything (same result, see warp_insert_merge0)
             if (nu > 0 && np < 32 && !dirty) nu = warp_insert_merge0(buf, nu, np);
-            else nu = warp_sort_merge0(buf, nu + np);
+            else {
+                const uint32_t n = nu + np;         // the free upper part of the buffer is the sort's scratch
+                nu = warp_sort_merge0(buf, n, 2u * n <= d.cap ? buf + n : nullptr, cnt);
+            }
             np = 0; dirty = false;
             remaining = d.ltotal - (int32_t)warp_coverage(buf, nu, ws);
             if (true_remaining == remaining) fails++; else true_remaining = remaining;
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(128) place_kernel(PlaceParams p)
         // result = unintersected.merge(0).filter(workspace) (gat/Engine.pyx:639-646); placements
         // still pending (appended after the last checkpoint) are dropped, as in the reference
         __syncwarp();
-        if (dirty) nu = warp_sort_merge0(buf, nu);
+        if (dirty) nu = warp_sort_merge0(buf, nu, 2u * nu <= d.cap ? buf + nu : nullptr, cnt);
         nu = warp_filter_ws(buf, nu, ws);
     }
     if (lane == 0) {
@@ -263,6 +271,7 @@ void launch_place(cudaStream_t st, const PlaceParams &p)
 // isochore unit's list (unit order) then merge(0).  One warp per (contig, sample).
 __global__ void __launch_bounds__(128) contig_merge_kernel(MergeParams p)
 {
+    __shared__ uint32_t sort_cnt[4][GATB_SORT_NB];
     const uint64_t item = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (item >= (uint64_t)p.n_contigs * p.n_samples) return;
     const int lane = lane_id();
@@ -278,7 +287,8 @@ __global__ void __launch_bounds__(128) contig_merge_kernel(MergeParams p)
         total += n;
     }
     __syncwarp();
-    uint32_t n = warp_sort_merge0(dst, total);
+    const uint64_t cap = (c + 1 < p.n_contigs ? p.contig_base[c + 1] : p.placed_stride) - p.contig_base[c];
+    uint32_t n = warp_sort_merge0(dst, total, 2ull * total <= cap ? dst + total : nullptr, sort_cnt[threadIdx.x >> 5]);
     if (lane == 0) p.placed_n[(uint64_t)sl * p.n_contigs + c] = n;
 }
 
