@@ -90,5 +90,7 @@ def load():
     L.gatb_run.argtypes = [vp, vp, i32, vp, u64, u32, u64, u64, vp, vp, i32, vp]
     L.gatb_column_stats.restype = i32
     L.gatb_column_stats.argtypes = [vp, vp, i32, i32, u64, i32, vp, vp, dbl, vp, vp, vp, vp, vp, vp]
+    L.gatb_compare_stats.restype = i32
+    L.gatb_compare_stats.argtypes = [vp, u64, vp, i32, vp, i32, u64, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L

@@ -1067,3 +1067,51 @@ extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float
     }
     return GATB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// gat-compare: statistics of the sampled log ratio of two fold-change columns, pair by pair
+extern "C" int gatb_compare_stats(gatb_ctx *ctx, uint64_t n_samples, const double *m1, int n_cols1,
+                                  const double *m2, int n_cols2, uint64_t n_pairs, const int32_t *col1,
+                                  const int32_t *col2, const double *obs1, const double *obs2, const double *delta,
+                                  double pseudo_count, double *expected, double *stddev, double *lower95,
+                                  double *upper95, double *fold, double *pvalue)
+{
+    if (!ctx || !m1 || !m2 || !col1 || !col2 || !obs1 || !obs2 || !delta || n_cols1 <= 0 || n_cols2 <= 0)
+        return GATB_ERR_INVALID;
+    if (n_samples < 1) return fail(ctx, GATB_ERR_INVALID, "compare_stats: no samples");
+    for (uint64_t q = 0; q < n_pairs; q++)
+        if (col1[q] < 0 || col1[q] >= n_cols1 || col2[q] < 0 || col2[q] >= n_cols2)
+            return fail(ctx, GATB_ERR_INVALID, "compare_stats: column index out of range");
+    if (n_pairs == 0) return GATB_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    DevBuf<double> d_m1, d_m2, d_o1, d_o2, d_delta, d_out;
+    DevBuf<int32_t> d_c1, d_c2;
+    CU(ctx, d_m1.upload(m1, n_samples * (uint64_t)n_cols1, st));
+    if (m2 != m1) CU(ctx, d_m2.upload(m2, n_samples * (uint64_t)n_cols2, st));
+    CU(ctx, d_c1.upload(col1, n_pairs, st)); CU(ctx, d_c2.upload(col2, n_pairs, st));
+    CU(ctx, d_o1.upload(obs1, n_pairs, st)); CU(ctx, d_o2.upload(obs2, n_pairs, st));
+    CU(ctx, d_delta.upload(delta, n_pairs, st));
+    // pairs in chunks of at most ~256 MB of derived samples
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n_pairs, (256ull << 20) / (8ull * n_samples)));
+    CU(ctx, d_out.alloc(chunk * n_samples));
+    for (uint64_t p0 = 0; p0 < n_pairs; p0 += chunk) {
+        const uint32_t np = (uint32_t)std::min<uint64_t>(chunk, n_pairs - p0);
+        CompareParams cp;
+        cp.m1 = d_m1.p; cp.m2 = (m2 != m1) ? d_m2.p : d_m1.p;
+        cp.n_cols1 = (uint32_t)n_cols1; cp.n_cols2 = (uint32_t)n_cols2; cp.n_samples = n_samples;
+        cp.col1 = d_c1.p + p0; cp.col2 = d_c2.p + p0;
+        cp.obs1 = d_o1.p + p0; cp.obs2 = d_o2.p + p0; cp.delta = d_delta.p + p0;
+        cp.n_pairs = np; cp.pseudo_count = pseudo_count; cp.out = d_out.p;
+        { ProfScope ps(ctx, PROF_OTHER); launch_compare_derive(st, cp); }
+        CU(ctx, cudaGetLastError());
+        // AnnotatorResult(..., observed_delta_fold, sampled_delta_fold, pseudo_count=0)
+        int rc = gatb_column_stats(ctx, d_out.p, 1, 1, n_samples, (int)np, delta + p0, nullptr, 0.0,
+                                   expected ? expected + p0 : nullptr, stddev ? stddev + p0 : nullptr,
+                                   lower95 ? lower95 + p0 : nullptr, upper95 ? upper95 + p0 : nullptr,
+                                   fold ? fold + p0 : nullptr, pvalue ? pvalue + p0 : nullptr);
+        if (rc) return rc;
+    }
+    return GATB_OK;
+}

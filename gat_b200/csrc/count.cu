@@ -11,6 +11,7 @@
 // atomics (order-independent, hence deterministic).  The
 // float64 nucleotide-density sum is formed per key from those integers, in the same key order and with
 // the same compensated summation as the reference's Python sum() (gat/__init__.py:583-587).
+#include <algorithm>
 #include "count.cuh"
 #include "../../include/gat_b200.h"
 
@@ -657,6 +658,27 @@ __global__ void __launch_bounds__(256) stats_select_kernel(StatsParams p)
         p.q_lo[col] = key_val(p.is_float, prefix_s[0]);
         p.q_hi[col] = key_val(p.is_float, prefix_s[1]);
     }
+}
+
+__global__ void __launch_bounds__(256) compare_derive_kernel(CompareParams p)
+{
+    const uint64_t total = p.n_samples * p.n_pairs;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = i / p.n_pairs;
+        const uint32_t q = (uint32_t)(i % p.n_pairs);
+        // same operation order as the numpy expressions: divide, add the fold pseudo-count, divide, log, shift
+        const double f1 = p.obs1[q] / (p.m1[s * p.n_cols1 + (uint32_t)p.col1[q]] + p.pseudo_count) + 0.0001;
+        const double f2 = p.obs2[q] / (p.m2[s * p.n_cols2 + (uint32_t)p.col2[q]] + p.pseudo_count) + 0.0001;
+        p.out[i] = log(f1 / f2) + p.delta[q];
+    }
+}
+
+void launch_compare_derive(cudaStream_t st, const CompareParams &p)
+{
+    const uint64_t total = p.n_samples * p.n_pairs;
+    if (total == 0) return;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, 148u * 16u);
+    compare_derive_kernel<<<blocks, 256, 0, st>>>(p);
 }
 
 void launch_stats_pass1(cudaStream_t st, const StatsParams &p)

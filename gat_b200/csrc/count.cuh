@@ -105,6 +105,21 @@ struct StatsParams {
     uint64_t rank_lo, rank_hi;
     const double *mean;             // device [n_cols] (second pass)
 };
+// gat-compare (scripts/gat-compare.py:218-241, :300-323): the sampled log ratio of two fold-change columns,
+//   out[s][p] = log((obs1[p] / (m1[s][col1[p]] + pc) + 1e-4) / (obs2[p] / (m2[s][col2[p]] + pc) + 1e-4)) + delta[p]
+// for pairs p0 <= p < p0 + n_pairs; out is [n_samples][n_pairs] float64, ready for the column statistics
+struct CompareParams {
+    const double *m1, *m2;          // [n_samples][n_cols1], [n_samples][n_cols2]
+    uint32_t n_cols1, n_cols2;
+    uint64_t n_samples;
+    const int32_t *col1, *col2;     // [n_pairs] (already offset to the chunk)
+    const double *obs1, *obs2, *delta;
+    uint32_t n_pairs;
+    double pseudo_count;
+    double *out;
+};
+void launch_compare_derive(cudaStream_t st, const CompareParams &p);
+
 void launch_stats_pass1(cudaStream_t st, const StatsParams &p);
 void launch_stats_pass2(cudaStream_t st, const StatsParams &p);
 void launch_stats_select(cudaStream_t st, const StatsParams &p);

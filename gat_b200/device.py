@@ -129,6 +129,24 @@ class Context(object):
         return dict(zip(["expected", "stddev", "lower95", "upper95", "fold", "pvalue"], outs))
 
 
+    def compare_stats(self, m1, m2, col1, col2, obs1, obs2, delta, pseudo_count=1.0):
+        """gat-compare's pairwise statistics (scripts/gat-compare.py:218-241, :300-323) for pairs
+        (column col1[q] of m1, column col2[q] of m2); m1, m2: [n_samples][n_cols] float64 sample matrices"""
+        m1 = np.ascontiguousarray(m1, dtype=np.float64)
+        m2 = m1 if m2 is None else np.ascontiguousarray(m2, dtype=np.float64)
+        if m1.shape[0] != m2.shape[0]:
+            raise ValueError("sample matrices differ in the number of samples")
+        c1 = np.ascontiguousarray(col1, dtype=np.int32)
+        c2 = np.ascontiguousarray(col2, dtype=np.int32)
+        arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (obs1, obs2, delta)]
+        n = len(c1)
+        outs = [np.zeros(n, dtype=np.float64) for _ in range(6)]
+        self.check(self.lib.gatb_compare_stats(self.handle, int(m1.shape[0]), _p(m1), int(m1.shape[1]), _p(m2),
+                                               int(m2.shape[1]), n, _p(c1), _p(c2), *[_p(a) for a in arrs],
+                                               float(pseudo_count), *[_p(o) for o in outs]))
+        return dict(zip(["expected", "stddev", "lower95", "upper95", "fold", "pvalue"], outs))
+
+
 class Annotations(object):
     """annotation tracks staged on the GPU for counting (gatb_annotations).
 

@@ -178,6 +178,20 @@ int  gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float, int coun
                        double pseudo_count, double *expected, double *stddev, double *lower95,
                        double *upper95, double *fold, double *pvalue);
 
+/* ---- gat-compare: pairwise comparison of fold changes ----------------------------------------------
+ * Replaces the inner loop of scripts/gat-compare.py (:218-241 within one counts file, :300-323 between
+ * two): for pair q of columns (col1[q] of m1, col2[q] of m2)
+ *     fc1 = obs1[q] / (m1[:, col1[q]] + pseudo_count) + 1e-4,   fc2 likewise
+ *     sampled = log(fc1 / fc2) + delta[q]            (delta = fold2 - fold1, the observed value)
+ *     AnnotatorResult(observed = delta[q], samples = sampled, pseudo_count = 0)
+ * i.e. the column statistics of gatb_column_stats on the derived samples, which never leave the GPU.
+ * m1 / m2: host, [n_samples][n_cols] float64 (m2 may equal m1); all other arrays host, n_pairs long. */
+int  gatb_compare_stats(gatb_ctx *ctx, uint64_t n_samples, const double *m1, int n_cols1,
+                        const double *m2, int n_cols2, uint64_t n_pairs, const int32_t *col1,
+                        const int32_t *col2, const double *obs1, const double *obs2, const double *delta,
+                        double pseudo_count, double *expected, double *stddev, double *lower95,
+                        double *upper95, double *fold, double *pvalue);
+
 #ifdef __cplusplus
 }
 #endif

@@ -385,3 +385,18 @@ def adjust_pvalues(pvalues, method="BH"):
     else:
         raise NotImplementedError(method)
     return np.minimum(p0, np.ones(len(p0)))
+
+
+def compare_pair(observed1, samples1, fold1, observed2, samples2, fold2, pseudo_count=1.0):
+    """scripts/gat-compare.py:218-241 (== :300-323): the relative fold change of two results.
+    -> (observed_delta_fold, Stats of AnnotatorResult(observed_delta, sampled_delta, pseudo_count=0))"""
+    s1 = np.asarray(samples1, dtype=np.float64)
+    s2 = np.asarray(samples2, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        fc1 = observed1 / (s1 + pseudo_count)
+        fc2 = observed2 / (s2 + pseudo_count)
+        fc1 = fc1 + 0.0001
+        fc2 = fc2 + 0.0001
+        delta = fold2 - fold1
+        sampled = np.log(fc1 / fc2) + delta
+    return 0.0 + delta, enrichment_statistics(0.0 + delta, sampled, pseudo_count=0.0)

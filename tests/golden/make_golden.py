@@ -21,6 +21,8 @@ for them, so that tests can pin the oracle and the CUDA path without the referen
   observed_testdata.npz  the reference's own golden run test/data/output_single.tsv: prepared
                      intervals + the 28 observed values of that file (checked here against a live run)
   observed_tutorial.npz  tutorial SRF x Jurkat DHS: prepared intervals + published observed 20183
+  compare.json       scripts/gat-compare.py on small count tables (one file / several files / options): the
+                     input tables and the result tables the reference printed
 """
 import gzip
 import io
@@ -430,10 +432,55 @@ def make_observed_tutorial():
     np.savez_compressed(os.path.join(HERE, "observed_tutorial.npz"), **store)
 
 
+def make_compare(rng):
+    """scripts/gat-compare.py run by the reference on small count tables: within one file and between files"""
+    import runpy
+
+    def counts_text(tracks, annos, S, scale, zero_every=0):
+        lines = ["track\tannotation\tobserved\tcounts\n"]
+        for t in tracks:
+            for i, a in enumerate(annos):
+                lam = scale * (i + 1) * 2.5
+                samples = rng.poisson(lam, S)
+                if zero_every:
+                    samples[::zero_every] = 0
+                obs = int(rng.poisson(lam * rng.choice([0.4, 1.0, 2.5])))
+                lines.append("%s\t%s\t%i\t%s\n" % (t, a, obs, ",".join(str(x) for x in samples)))
+        return "".join(lines)
+
+    files = {"a.tsv": counts_text(["merged"], ["x1", "x2", "x3", "x4", "x5"], 200, 1.0, zero_every=17),
+             "b.tsv": counts_text(["merged"], ["x1", "x2", "x3", "x5", "x9"], 200, 1.6),
+             "c.tsv": counts_text(["merged", "other"], ["x1", "x2", "x5"], 200, 0.7, zero_every=5)}
+    script = os.path.join(ROOT, "oracle", "_ref", "scripts", "gat-compare.py")
+    cases = []
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            for name, text in files.items():
+                with open(name, "w") as f:
+                    f.write(text)
+            for args in (["a.tsv"], ["a.tsv", "b.tsv"], ["a.tsv", "b.tsv", "c.tsv"],
+                         ["a.tsv", "--pseudo-count=0.5", "--order=annotation", "--qvalue-method=bonferroni"]):
+                out, old_out, old_argv = io.StringIO(), sys.stdout, sys.argv
+                sys.stdout, sys.argv = out, ["gat-compare.py"] + args + ["--log=/dev/null"]
+                try:
+                    runpy.run_path(script, run_name="__main__")
+                except SystemExit:
+                    pass
+                finally:
+                    sys.stdout, sys.argv = old_out, old_argv
+                table = [l for l in out.getvalue().splitlines() if l and not l.startswith("#")]
+                cases.append({"args": args, "table": table})
+        finally:
+            os.chdir(cwd)
+    return {"files": files, "cases": cases}
+
+
 def main():
     # fixtures added after the first generation have their own seeds and can be (re)made alone:
     #   python tests/golden/make_golden.py sampler_segments
-    extra = {"sampler_segments": (make_sampler_segments, 20260102)}
+    extra = {"sampler_segments": (make_sampler_segments, 20260102), "compare": (make_compare, 20260103)}
     only = [a for a in sys.argv[1:] if a in extra]
     for name in (only or list(extra)):
         fn, seed = extra[name]

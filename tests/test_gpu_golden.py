@@ -291,3 +291,46 @@ def test_cli_from_bed_files(ctx, oracle, tmp_path, with_isochores):
                        for k in ws.keys())
             assert int(r[2]) == int(want), (counter, r[1])
             assert 0 < float(r[9]) <= 1 and 0 < float(r[10]) <= 1 and float(r[3]) > 0
+
+
+def test_compare_cli_matches_reference_tables(ctx, tmp_path, monkeypatch):
+    """gat_b200.compare (gatb_compare_stats: derived log-ratio samples + column statistics on the GPU) prints the
+    rows the reference's scripts/gat-compare.py printed for the same count tables (tests/golden/compare.json)"""
+    from gat_b200 import compare
+    data = G.load_json("compare")
+    monkeypatch.chdir(tmp_path)
+    for name, text in data["files"].items():
+        with open(name, "w") as f:
+            f.write(text)
+    for k, case in enumerate(data["cases"]):
+        out = "out%i.tsv" % k
+        assert compare.main(["gat-compare"] + case["args"] + ["--stdout=" + out]) == 0
+        got = [l.rstrip("\n") for l in open(out)]
+        assert got[0] == case["table"][0]
+        assert sorted(got[1:]) == sorted(case["table"][1:]), case["args"]
+        if "--order=annotation" in case["args"]:
+            assert got == case["table"]                       # no ties in this order: same sequence too
+
+
+def test_compare_stats_large_matches_oracle(ctx, oracle):
+    """5 000 samples x 40 columns, all 780 pairs in one call: statistics against the oracle's restatement"""
+    rng = np.random.default_rng(31)
+    S, A = 5000, 40
+    lam = rng.uniform(0.5, 60, A)
+    m = rng.poisson(lam, size=(S, A)).astype(np.float64)
+    obs = rng.poisson(lam * rng.choice([0.5, 1, 2], A)).astype(np.float64)
+    base = ctx.column_stats(m.astype(np.uint32), obs, pseudo_count=1.0)
+    pairs = [(i, j) for i in range(A) for j in range(i + 1, A)]
+    c1, c2 = [p[0] for p in pairs], [p[1] for p in pairs]
+    delta = base["fold"][c2] - base["fold"][c1]
+    got = ctx.compare_stats(m, None, c1, c2, obs[c1], obs[c2], delta, pseudo_count=1.0)
+    for q in range(0, len(pairs), 37):
+        i, j = pairs[q]
+        d, st = oracle.compare_pair(obs[i], m[:, i], base["fold"][i], obs[j], m[:, j], base["fold"][j], 1.0)
+        assert d == delta[q]
+        assert got["pvalue"][q] == st.pvalue                                    # counts of x<obs, x==obs: exact
+        assert got["lower95"][q] == pytest.approx(st.lower95, rel=1e-12, abs=1e-12)   # log(): <= 1 ulp apart
+        assert got["upper95"][q] == pytest.approx(st.upper95, rel=1e-12, abs=1e-12)
+        assert got["expected"][q] == pytest.approx(st.expected, rel=1e-10, abs=1e-12)
+        assert got["stddev"][q] == pytest.approx(st.stddev, rel=1e-10)
+        assert got["fold"][q] == pytest.approx(st.fold, rel=1e-9)

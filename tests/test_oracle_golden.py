@@ -235,3 +235,49 @@ def test_sampler_segments_matches_reference_under_numpy_rng(oracle):
         got = oracle.sampler_segments(u["segments"], u["workspace"], bucket_size=u["bucket_size"])
         assert got.tolist() == u["placed"], u["seed"]
         assert len(got) in (0, len(u["segments"]))
+
+
+def _parse_counts(text):
+    rows = []
+    for line in text.splitlines()[1:]:
+        track, annotation, observed, counts = line.split("\t")
+        rows.append((track, annotation, float(observed), np.array([float(x) for x in counts.split(",")])))
+    return rows
+
+
+def test_compare_matches_reference_script(oracle):
+    """gat-compare restatement (oracle.compare_pair on top of the statistics oracle) against the tables the
+    reference's scripts/gat-compare.py printed (tests/golden/compare.json): every printed column of every row"""
+    data = G.load_json("compare")
+    tables = dict((name, _parse_counts(text)) for name, text in data["files"].items())
+    stats = {}
+    for name, rows in tables.items():
+        for track, annotation, observed, samples in rows:
+            stats[(name, track, annotation)] = (observed, samples, oracle.enrichment_statistics(observed, samples).fold)
+    for case in data["cases"]:
+        files = [a for a in case["args"] if not a.startswith("-")]
+        pc = 1.0
+        for a in case["args"]:
+            if a.startswith("--pseudo-count="):
+                pc = float(a.split("=")[1])
+        want = dict(((r.split("\t")[0], r.split("\t")[1], r.split("\t")[2]), r.split("\t")) for r in case["table"][1:])
+        got = []
+        if len(files) == 1:
+            rows = tables[files[0]]
+            for i in range(len(rows)):
+                for j in range(i + 1, len(rows)):
+                    a, b = stats[(files[0],) + rows[i][:2]], stats[(files[0],) + rows[j][:2]]
+                    got.append((rows[i][1], rows[j][1]) + oracle.compare_pair(a[0], a[1], a[2], b[0], b[1], b[2], pc))
+        else:
+            for x in range(len(files)):
+                for y in range(x + 1, len(files)):
+                    keys_a = set(r[:2] for r in tables[files[x]])
+                    for track, annotation in sorted(keys_a.intersection(r[:2] for r in tables[files[y]])):
+                        a, b = stats[(files[x], track, annotation)], stats[(files[y], track, annotation)]
+                        got.append((track, annotation) + oracle.compare_pair(a[0], a[1], a[2], b[0], b[1], b[2], pc))
+        assert len(got) == len(case["table"]) - 1
+        for track, annotation, delta, st in got:
+            row = want[(track, annotation, "%6.4f" % delta)]
+            assert row[3] == "%6.4f" % st.expected and row[4] == "%6.4f" % st.lower95, (case["args"], row)
+            assert row[5] == "%6.4f" % st.upper95 and row[6] == "%6.4f" % st.stddev, (case["args"], row)
+            assert row[7] == "%6.4f" % st.fold and row[9] == "%6.4e" % st.pvalue, (case["args"], row)
