@@ -20,7 +20,7 @@ SYMBOLS = [
     "gatb_annotations_create", "gatb_annotations_create_async", "gatb_annotations_wait",
     "gatb_annotations_destroy", "gatb_count_lists",
     "gatb_sampler_create", "gatb_sampler_destroy", "gatb_sampler_sample_capacity",
-    "gatb_sampler_set_kind", "gatb_sampler_place", "gatb_run", "gatb_column_stats",
+    "gatb_sampler_set_kind", "gatb_sampler_place", "gatb_run", "gatb_column_stats", "gatb_compare_stats",
 ]
 
 
