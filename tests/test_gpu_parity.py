@@ -278,3 +278,43 @@ def test_async_annotations_same_counts_and_deferred_errors(ctx, oracle):
     bad.close()
     sync.close()
     smp.close()
+
+
+def test_count_filter_edge_geometries(ctx, oracle):
+    """the bitmap / bin-index filter at its edges: coordinates just below 2^31, an extent of a few positions,
+    segments far beyond the last interval, segments longer than a bitmap window and than 32 windows, segments
+    starting exactly on window boundaries, annotations touching each other across tracks"""
+    from gat_b200 import device
+    rng = np.random.default_rng(2718)
+    top = 2 ** 31 - 1
+    K = 4
+    # (build [s, s+len) lists by hand so that ends stay <= 2^31 - 1)
+    def near_top(n, maxlen):
+        s = top - rng.integers(2, 5000000, n)
+        l = rng.integers(1, maxlen + 1, n)
+        e = np.minimum(s + l, top)
+        return helpers.normalize(np.stack([s, e], axis=1))
+    tiny = np.array([[1, 2], [3, 5]], dtype=np.uint32)
+    grid = np.array([[i * 1024, i * 1024 + 1] for i in range(1, 400, 3)], dtype=np.uint32)       # window boundaries
+    touching_a = np.array([[i * 100, i * 100 + 50] for i in range(200)], dtype=np.uint32)
+    touching_b = np.array([[i * 100 + 50, i * 100 + 100] for i in range(200)], dtype=np.uint32)
+    annos = [[near_top(300, 4000), tiny, grid, touching_a],
+             [near_top(50, 100000), np.zeros((0, 2), dtype=np.uint32), helpers.random_list(rng, 500000, 300, 2000), touching_b],
+             [near_top(5, 10), tiny, np.array([[0, 1]], dtype=np.uint32), helpers.random_list(rng, 20000, 100, 30)]]
+    nseg = [1, 2, 3, 1]
+    samples = []
+    for s in range(12):
+        samples.append([
+            near_top(200, int(rng.choice([50, 1500, 60000]))),                                       # near 2^31
+            helpers.random_list(rng, 40, 8, 6),                                                      # tiny extent
+            helpers.normalize(np.stack([np.arange(0, 600) * 1024, np.arange(0, 600) * 1024 + rng.integers(1, 1025, 600)], axis=1)),
+            helpers.random_list(rng, 40000, 60, int(rng.choice([20, 1025, 40000]))),                 # long segments
+        ])
+    samples.append([np.array([[top - 5, top]], dtype=np.uint32), np.array([[1000, 2000]], dtype=np.uint32),
+                    np.array([[10 ** 9, 10 ** 9 + 5]], dtype=np.uint32), np.array([[0, 2 * 10 ** 9]], dtype=np.uint32)])
+    an = device.Annotations(ctx, annos, key_ws_nseg=nseg)
+    got = an.count_lists(COUNTERS, samples)
+    an.close()
+    for s in range(len(samples)):
+        exp = oracle.count_placed(samples[s], annos, nseg, COUNTERS)
+        assert np.array_equal(got[:, s, :], exp), s
