@@ -89,6 +89,10 @@ def sampleTrack(track_index, segs, annotations, workspace, sampler, counters, nu
     key = tuple(problem.contigs)
     if annos_cache is not None and key in annos_cache:
         annos = annos_cache[key]
+    elif not problem.has_isochores:
+        # no isochores: fromIsochores changes nothing, the contig-level annotations are the loaded ones
+        annos, _ = Engine.deviceAnnotations(annotations, problem.contigs, [len(workspace[c]) for c in problem.contigs],
+                                            annos_cache, lazy=True)
     else:
         _, lists, nseg = buildContigAnnotations(annotations, workspace, problem.contigs)
         annos = device.Annotations(ctx, lists, key_ws_nseg=nseg, lazy=True)
@@ -145,13 +149,14 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
             timing.append((name, time.perf_counter()))
 
     # observed counts (gat/__init__.py:932-940)
+    annos_cache = {}      # key tuple -> device.Annotations: one upload + tile build per key set for the whole run
     observed_counts = [Engine.computeCounts(counter=c, aggregator=sum, segments=segments,
                                             annotations=annotations, workspace=workspace,
-                                            workspace_generator=workspace_generator) for c in counters]
+                                            workspace_generator=workspace_generator, annos_cache=annos_cache)
+                       for c in counters]
     mark("observed")
 
     sampled = {}
-    annos_cache = {}
     begin, end = parallel.shard_range(num_samples, rank, world)
     for ntrack, track in enumerate(segments.tracks):
         segs = segments[track]
@@ -171,9 +176,19 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
         sampled[track] = (atracks, out_u, out_f, ids)
         if output_samples_pattern and rank == 0:
             _dumpSamples(track, ntrack, segs, workspace, sampler, num_samples, output_samples_pattern)
+    mark("allgather")
+
+    # size / overlap columns of AnnotatorResultExtended: once per track and per annotation, the overlap of a
+    # track with every annotation in one GPU call (gat/Engine.pyx:1911-1928 does one intersect per result)
+    workspace_size = workspace.sum()
+    anno_sizes = dict((a, (annotations[a].counts(), annotations[a].sum())) for a in annotations.tracks)
+    track_sizes = {}
+    for track in sampled:
+        track_sizes[track] = (segments[track].counts(), segments[track].sum(),
+                              Engine.overlapColumns(segments[track], annotations, annos_cache))
     for a in annos_cache.values():
         a.close()
-    mark("allgather")
+    mark("overlap columns")
 
     # statistics per (counter, track): one batched column-stats call over all annotations
     annotator_results = []
@@ -212,7 +227,13 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
                     samples=host[:, ai], track_segments=segments[track],
                     annotation_segments=annotations[annotation], workspace=workspace,
                     reference=reference[track][annotation] if reference else None,
-                    pseudo_count=pseudo_count, stats=row))
+                    pseudo_count=pseudo_count, stats=row,
+                    sizes=dict(track_nsegments=track_sizes[track][0], track_size=track_sizes[track][1],
+                               annotation_nsegments=anno_sizes[annotation][0],
+                               annotation_size=anno_sizes[annotation][1],
+                               overlap_nsegments=track_sizes[track][2][annotation][0],
+                               overlap_size=track_sizes[track][2][annotation][1],
+                               workspace_size=workspace_size)))
 
     # dump (large) table with counts (gat/__init__.py:1072-1086)
     if output_counts_pattern and rank == 0:

@@ -96,6 +96,8 @@ __device__ __forceinline__ void count_pair(int s, int e, int x, int y, uint32_t 
             const int mid = s + ((e - s) >> 1);
             if (x <= mid && mid < y) hit |= 1u << t;
         }
+    } else if (COUNTER == GATB_OVERLAP_PIECES) {
+        atomicAdd(acc + t, 1u);                     // every overlapping pair is one piece of intersect()
     } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
         if (x >= pe) atomicAdd(acc + t, 1u);
     } else {
@@ -340,6 +342,7 @@ cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int
     case GATB_SEGMENT_MIDOVERLAP:    return launch_count_t<GATB_SEGMENT_MIDOVERLAP, false>(st, p, threads);
     case GATB_ANNOTATION_OVERLAP:    return launch_count_t<GATB_ANNOTATION_OVERLAP, false>(st, p, threads);
     case GATB_ANNOTATION_MIDOVERLAP: return launch_count_t<GATB_ANNOTATION_MIDOVERLAP, false>(st, p, threads);
+    case GATB_OVERLAP_PIECES:        return launch_count_t<GATB_OVERLAP_PIECES, false>(st, p, threads);
     }
     return cudaErrorInvalidValue;
 }

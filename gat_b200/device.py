@@ -12,7 +12,8 @@ import numpy as np
 from . import _lib
 
 COUNTERS = ["nucleotide-overlap", "nucleotide-density", "segment-overlap",
-            "segment-midoverlap", "annotation-overlap", "annotation-midoverlap"]
+            "segment-midoverlap", "annotation-overlap", "annotation-midoverlap",
+            "overlap-pieces"]          # the last one is internal (GATB_OVERLAP_PIECES), not a --counter
 COUNTER_ID = {name: i for i, name in enumerate(COUNTERS)}
 DENSITY = COUNTER_ID["nucleotide-density"]
 

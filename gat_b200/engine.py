@@ -448,7 +448,24 @@ class UnconditionalWorkspace(object):
 
 
 # ------------------------------------------------------------------------------------ observed counts
-def computeCounts(counter, aggregator, segments, annotations, workspace, workspace_generator, append=False):
+def deviceAnnotations(annotations, keys, nseg=None, cache=None, lazy=False):
+    """the annotation tracks on `keys` as a device.Annotations set; `cache` (dict keyed by the key tuple) lets
+    the observed counts of every counter, the sampling and the overlap columns of one run share ONE upload
+    and tile build.  -> (set, owned): the caller closes the set iff owned."""
+    k = tuple(keys)
+    if cache is not None and k in cache:
+        return cache[k], False
+    empty = np.zeros((0, 2), dtype=np.uint32)
+    lists = [[annotations[a][key].asarray() if key in annotations[a] else empty for key in keys]
+             for a in annotations.tracks]
+    obj = _dev.Annotations(getContext(), lists, key_ws_nseg=nseg, lazy=lazy)
+    if cache is not None:
+        cache[k] = obj
+    return obj, cache is None
+
+
+def computeCounts(counter, aggregator, segments, annotations, workspace, workspace_generator, append=False,
+                  annos_cache=None):
     """observed counts of every (track, annotation) pair: aggregator over workspace keys of
     counter(segs[key], annos[key], workspace[key]) (gat/Engine.pyx:2164-2204).  One batched GPU call
     per counter; only the `sum` aggregator of the reference's call site is supported."""
@@ -463,11 +480,12 @@ def computeCounts(counter, aggregator, segments, annotations, workspace, workspa
     atracks = list(annotations.tracks)
     if not keys or not tracks or not atracks:
         return counts
-    ctx = getContext()
-    annos = _dev.Annotations(ctx, [[annotations[a][k].asarray() for k in keys] for a in atracks],
-                             key_ws_nseg=[len(workspace[k]) for k in keys])
-    out = annos.count_lists([counter.name], [[segments[t][k].asarray() for k in keys] for t in tracks])
-    annos.close()
+    annos, owned = deviceAnnotations(annotations, keys, [len(workspace[k]) for k in keys], annos_cache)
+    empty = np.zeros((0, 2), dtype=np.uint32)
+    out = annos.count_lists([counter.name], [[segments[t][k].asarray() if k in segments[t] else empty for k in keys]
+                                             for t in tracks])
+    if owned:
+        annos.close()
     is_float = counter.name == "nucleotide-density"
     for ti, track in enumerate(tracks):
         for ai, annotation in enumerate(atracks):
@@ -478,6 +496,23 @@ def computeCounts(counter, aggregator, segments, annotations, workspace, workspa
             else:
                 counts[track][annotation] = v
     return counts
+
+
+def overlapColumns(track_segments, annotations, annos_cache=None):
+    """{annotation: (overlap_nsegments, overlap_size)} of one track against every annotation track: the
+    counts() and sum() of track_segments.intersect(annotation_segments) that AnnotatorResultExtended reports
+    (gat/Engine.pyx:1911-1928), for all annotations in ONE batched GPU call instead of one host intersect
+    per result.  For normalized lists the pieces of intersect() are the overlapping (segment, interval)
+    pairs and their total length is the nucleotide overlap."""
+    atracks = list(annotations.tracks)
+    keys = [k for k in track_segments.keys()]
+    if not keys or not atracks:
+        return dict((a, (0, 0)) for a in atracks)
+    annos, owned = deviceAnnotations(annotations, keys, None, annos_cache)
+    out = annos.count_lists(["overlap-pieces", "nucleotide-overlap"], [[track_segments[k].asarray() for k in keys]])
+    if owned:
+        annos.close()
+    return dict((a, (int(out[0, 0, i]), int(out[1, 0, i]))) for i, a in enumerate(atracks))
 
 
 # ------------------------------------------------------------------------------------------- results
@@ -569,9 +604,17 @@ class AnnotatorResultExtended(AnnotatorResult):
         "percent_overlap_nsegments_annotation", "percent_overlap_size_annotation"]
 
     def __init__(self, track, annotation, counter, observed, samples, track_segments, annotation_segments,
-                 workspace, reference=None, pseudo_count=1.0, stats=None):
+                 workspace, reference=None, pseudo_count=1.0, stats=None, sizes=None):
+        """sizes: optional precomputed dict with track_nsegments, track_size, annotation_nsegments,
+        annotation_size, overlap_nsegments, overlap_size, workspace_size (gat_b200.run computes them once per
+        track / annotation, the overlap columns on the GPU via overlapColumns)"""
         AnnotatorResult.__init__(self, track, annotation, counter, observed, samples,
                                  reference=reference, pseudo_count=pseudo_count, stats=stats)
+        if sizes is not None:
+            for k in ("track_nsegments", "track_size", "annotation_nsegments", "annotation_size",
+                      "overlap_nsegments", "overlap_size", "workspace_size"):
+                setattr(self, k, sizes[k])
+            return
         self.track_nsegments = track_segments.counts()
         self.track_size = track_segments.sum()
         self.annotation_nsegments = annotation_segments.counts()

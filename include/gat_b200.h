@@ -51,7 +51,11 @@ extern "C" {
 #define GATB_SEGMENT_MIDOVERLAP    3   /* CounterSegmentMidpointOverlap  :1450-1456 */
 #define GATB_ANNOTATION_OVERLAP    4   /* CounterAnnotationOverlap       :1458-1463 */
 #define GATB_ANNOTATION_MIDOVERLAP 5   /* CounterAnnotationMidpointOverlap :1465-1472 */
-#define GATB_NCOUNTERS             6
+#define GATB_OVERLAP_PIECES        6   /* not a --counter: len(a.intersect(b)) for normalized lists = number of
+                                        * overlapping (segment, interval) pairs; with nucleotide-overlap (= its
+                                        * .sum()) it gives AnnotatorResultExtended's overlap_nsegments / overlap_size
+                                        * columns (gat/Engine.pyx:1911-1928) for every annotation in one call */
+#define GATB_NCOUNTERS             7
 
 typedef struct gatb_ctx gatb_ctx;           /* one GPU + one stream                                  */
 typedef struct gatb_annotations gatb_annotations;   /* annotation tracks staged for counting         */

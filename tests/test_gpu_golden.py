@@ -213,6 +213,15 @@ def test_run_api_results_and_output(ctx, tmp_path):
     assert lines[0].split("\t") == Engine.AnnotatorResultExtended.headers and len(lines) == 6
     folds = [float(l.split("\t")[7]) for l in lines[1:]]
     assert folds == sorted(folds)
+    # the size / overlap columns come from one batched GPU call per track (Engine.overlapColumns); the
+    # per-result host path of the reference's constructor (intersect per result) must give the same row
+    for r in res:
+        host = Engine.AnnotatorResultExtended(
+            r.track, r.annotation, r.counter, r.observed, r.samples, segments[r.track], annotations[r.annotation],
+            workspace, stats=dict((k, getattr(r, k)) for k in ("expected", "stddev", "lower95", "upper95", "fold", "pvalue")))
+        host.qvalue, host.format_observed = r.qvalue, r.format_observed
+        assert str(host) == str(r)
+        assert r.overlap_size > 0 and r.overlap_nsegments > 0
     assert all(0 < r.qvalue <= 1 for r in res)
     q = Engine.getQValues([r.pvalue for r in res], method="BH")
     assert np.allclose([r.qvalue for r in res], q)

@@ -318,3 +318,24 @@ def test_count_filter_edge_geometries(ctx, oracle):
     for s in range(len(samples)):
         exp = oracle.count_placed(samples[s], annos, nseg, COUNTERS)
         assert np.array_equal(got[:, s, :], exp), s
+
+
+def test_overlap_pieces_counter_matches_intersect(ctx, oracle):
+    """GATB_OVERLAP_PIECES = len(a.intersect(b)) (with nucleotide-overlap = its sum): the overlap columns of
+    AnnotatorResultExtended (gat/Engine.pyx:1911-1928) against the oracle's SegmentList.intersect"""
+    from gat_b200 import device
+    rng = np.random.default_rng(404)
+    K, A, S = 3, 11, 7
+    span = 300000
+    annos = [[helpers.random_list(rng, span, int(rng.integers(0, 400)), int(rng.choice([40, 3000]))) for _ in range(K)]
+             for _ in range(A)]
+    samples = [[helpers.random_list(rng, span, int(rng.integers(0, 300)), int(rng.choice([25, 900, 20000]))) for _ in range(K)]
+               for _ in range(S)]
+    an = device.Annotations(ctx, annos)
+    got = an.count_lists(["overlap-pieces", "nucleotide-overlap"], samples)
+    an.close()
+    for s in range(S):
+        for a in range(A):
+            pieces = [oracle.intersect(samples[s][k], annos[a][k]) for k in range(K)]
+            assert got[0, s, a] == sum(len(p) for p in pieces), (s, a)
+            assert got[1, s, a] == sum(oracle.total(p) for p in pieces), (s, a)

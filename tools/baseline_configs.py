@@ -23,6 +23,7 @@ CONFIGS = {
     "c3": (10000, 50, True, "segment-overlap", 10000),
     "c4": (50000, 1000, False, "nucleotide-overlap", 12500),      # one GPU's share of 100k samples on 8 GPUs
     "c5": (10000, 200, False, "nucleotide-overlap", 1000000),
+    "ns": (10000, 1000, False, "nucleotide-overlap", 100000),     # north-star shape, 1e5 samples
 }
 
 
