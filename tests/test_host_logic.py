@@ -186,3 +186,50 @@ def test_input_preparation_matches_reference_io():
         assert sorted([t, k] for t, vv in coll.items() for k in vv.keys() if len(vv[k])) == ref_keys
         for track, key in ref_keys:
             assert np.array_equal(coll[track][key].asarray(), G.undelta(z["%s/%s/%s" % (name, track, key)])), (track, key)
+
+
+def test_bed_fast_reader_equals_line_reader(tmp_path, monkeypatch):
+    """the Arrow fast path of IO.readFromBed and the line-by-line reader give the same tracks, the same key
+    order and the same intervals; files it cannot take (track lines, comments, ragged rows) fall back"""
+    import gzip
+    from gat_b200 import io as IO
+    rng = np.random.default_rng(12)
+    contigs = ["chr2", "chr1", "chrX", "chr10"]
+    lines = []
+    for i in range(5000):
+        s = int(rng.integers(0, 10 ** 8))
+        lines.append("%s\t%i\t%i\t%s\n" % (contigs[int(rng.integers(0, 4))], s, s + int(rng.integers(1, 5000)),
+                                           ["tB", "tA", "", "tC"][int(rng.integers(0, 4))]))
+    plain = str(tmp_path / "plain.bed")
+    open(plain, "w").write("".join(lines))
+    three = str(tmp_path / "three.bed")
+    open(three, "w").write("".join("\t".join(l.split("\t")[:3]) + "\n" for l in lines))
+    gz = str(tmp_path / "z.bed.gz")
+    with gzip.open(gz, "wt") as f:
+        f.write("".join(lines))
+    tracked = str(tmp_path / "tracked.bed")
+    open(tracked, "w").write("chr1\t5\t9\n# comment\ntrack name=\"q r\"\n" + "".join(lines[:50]) + "track name=z\nchr1\t1\t2\n")
+
+    def both(files, **kw):
+        fast = IO.readFromBed(files, **kw)
+        with monkeypatch.context() as m:
+            m.setattr(IO, "_readBedColumns", lambda fn: None)
+            slow = IO.readFromBed(files, **kw)
+        assert list(fast.keys()) == list(slow.keys())
+        for t in slow:
+            assert list(fast[t].keys()) == list(slow[t].keys()), t
+            for c in slow[t].keys():
+                assert np.array_equal(fast[t][c].asarray(), slow[t][c].asarray()), (t, c)
+        return fast
+
+    assert IO._readBedColumns(plain) is not None and IO._readBedColumns(gz) is not None
+    assert IO._readBedColumns(tracked) is None
+    r = both([plain])
+    assert set(r.keys()) == {"tA", "tB", "tC", "plain.bed"}
+    assert list(both([three]).keys()) == ["three.bed"]
+    assert list(both([gz], ignore_tracks=True).keys()) == ["merged"]
+    r = both([tracked])
+    assert set(r.keys()) == {"tracked.bed", "q r", "z"}
+    both([plain, three, tracked], allow_multiple=True)
+    with pytest.raises(ValueError):
+        IO.readFromBed([plain, gz])                                # same tracks in two files
