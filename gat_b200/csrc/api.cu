@@ -24,7 +24,7 @@ struct gatb_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t upload_stream = nullptr;   // gatb_annotations_create_async: copies + tile build, off the compute stream
-    uint32_t *err_slots = nullptr;          // pinned validation words of pending asynchronous creates
+    uint32_t *err_slots = nullptr;          // pinned words of pending asynchronous creates: 4 per set (validation, -, entries needed lo/hi)
     std::vector<int> err_free;
     std::string err;
     uint64_t launches = 0;
@@ -32,9 +32,9 @@ struct gatb_ctx {
     int sm_count = 148;
     size_t smem_optin = 0;
     // tunables (env overrides, for profiling)
-    uint32_t tile_budget = 0;
     int count_threads = 1024;
-    uint32_t schunk_max = 256;
+    uint32_t schunk_max = 0;            // samples per count CTA; 0: whatever shared memory allows
+    uint32_t count_lps = 16, count_depth = 2;
     // optional per-kernel timing (bench.py roofline): CUDA events around every launch
     bool profiling = false;
     struct Span { int cls; cudaEvent_t a, b; };
@@ -137,7 +137,7 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, GATB_ERR_CUDA, cudaGetErrorString(e)); }
     ctx->stream = ctx->own_stream;
     e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMallocHost(&ctx->err_slots, 256 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->err_slots, 256 * 4 * sizeof(uint32_t));
     if (e != cudaSuccess) { cudaStreamDestroy(ctx->own_stream); delete ctx; return fail(nullptr, GATB_ERR_CUDA, cudaGetErrorString(e)); }
     for (int i = 255; i >= 0; i--) ctx->err_free.push_back(i);
     cudaDeviceProp prop;
@@ -152,8 +152,9 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     ctx->count_threads = (int)std::min(1024u, std::max(32u, env_u32("GATB_COUNT_THREADS", 1024) / 32 * 32));
-    ctx->schunk_max = std::min(256u, std::max(32u, env_u32("GATB_SCHUNK", 256)));
-    ctx->tile_budget = env_u32("GATB_TILE_BUDGET", 0);
+    ctx->schunk_max = env_u32("GATB_SCHUNK", 0);
+    ctx->count_lps = env_u32("GATB_COUNT_LPS", 16);
+    ctx->count_depth = env_u32("GATB_COUNT_DEPTH", 2);
     ctx->batch = env_u32("GATB_BATCH", 0);
     *out = ctx;
     return GATB_OK;
@@ -246,16 +247,24 @@ static int check_lists(gatb_ctx *ctx, const char *what, uint64_t n_lists, const 
 struct gatb_annotations {
     gatb_ctx *ctx = nullptr;
     uint32_t n_annot = 0, n_keys = 0, n_groups = 0, ka = 1;
-    uint32_t max_stage = 0;             // largest filter (bytes) over all tiles
-    uint32_t max_prefix = 0;            // largest header + bitmap (bytes): staged for every tile
     uint64_t n_intervals = 0;
-    DevBuf<uint8_t> tiles;
-    DevBuf<uint64_t> tile_off;
-    DevBuf<uint32_t> tile_stage;
+    uint64_t n_boff = 0, capacity = 0;
+    std::vector<KeyBins> h_keybins;
+    DevBuf<KeyBins> keybins;
+    DevBuf<uint32_t> boff;
+    DevBuf<uint2> civ;
+    DevBuf<uint16_t> ctrk;
+    DevBuf<uint32_t> cprev;
     DevBuf<uint32_t> key_ws_nseg;
     bool has_nseg = false;
-    // asynchronous create: `ready` is recorded on the upload stream after the tile build; until the
-    // first wait the validation word (pinned, err_slot) has not been looked at
+    // kept until the build has been checked (annotations_finish): the raw lists on the device, so that an
+    // index that outgrew the estimated capacity can be rebuilt at its exact size without the caller's arrays
+    DevBuf<uint64_t> d_offs;
+    DevBuf<uint32_t> d_start, d_end, d_err;
+    DevBuf<unsigned long long> d_total;
+    DevBuf<uint8_t> scan_tmp;
+    // asynchronous create: `ready` is recorded on the upload stream after the index build; until the
+    // first wait the validation words (pinned, err_slot) have not been looked at
     cudaEvent_t ready = nullptr;
     int err_slot = -1;
     bool pending = false;
@@ -267,96 +276,74 @@ struct gatb_annotations {
     }
 };
 
-// host-blocking: the asynchronous build has finished; -> validation result
+// queue (on the upload stream) the construction of the grid index from the device copies of the lists,
+// then the read-back of the validation word and of the number of entries the index needs
+static cudaError_t annotations_build(gatb_annotations *a)
+{
+    gatb_ctx *ctx = a->ctx;
+    cudaStream_t st = ctx->upload_stream;
+    uint32_t *slot = ctx->err_slots + 4 * a->err_slot;
+    cudaError_t e = cudaMemsetAsync(a->d_err.p, 0, sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->d_total.p, 0, sizeof(unsigned long long), st);
+    if (e == cudaSuccess && a->n_boff) e = cudaMemsetAsync(a->boff.p, 0, a->n_boff * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    BuildBinsParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.offs = a->d_offs.p; bp.start = a->d_start.p; bp.end = a->d_end.p; bp.n_intervals = a->n_intervals;
+    bp.keybins = a->keybins.p; bp.boff = a->boff.p; bp.n_boff = a->n_boff;
+    bp.civ = a->civ.p; bp.ctrk = a->ctrk.p; bp.cprev = a->cprev.p; bp.capacity = a->capacity;
+    bp.n_annot = a->n_annot; bp.n_keys = a->n_keys; bp.n_groups = a->n_groups; bp.ka = a->ka;
+    bp.error = a->d_err.p; bp.total = a->d_total.p;
+    {
+        ProfScope ps(ctx, PROF_OTHER, st);
+        ctx->launches += 3;                 // count, scan, check, fill
+        e = launch_build_bins(st, bp, a->scan_tmp.p, a->scan_tmp.n);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(slot, a->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(slot + 2, a->d_total.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(a->ready, st);
+    return e;
+}
+
+// host-blocking: the asynchronous build has finished; -> validation result.  An index that needed more
+// entries than estimated is rebuilt here at its exact size.
 static int annotations_finish(gatb_annotations *a)
 {
     if (!a->pending) return a->status;
     gatb_ctx *ctx = a->ctx;
     a->pending = false;
+    const uint32_t *slot = ctx->err_slots + 4 * a->err_slot;
+    cudaStream_t saved = tl_stream;
+    tl_stream = ctx->upload_stream;
     cudaError_t e = cudaEventSynchronize(a->ready);
+    uint32_t h_err = slot[0];
+    if (e == cudaSuccess && !(h_err & 3u) && (h_err & 4u)) {
+        unsigned long long need;
+        memcpy(&need, slot + 2, sizeof(need));
+        if (need > 0xfffffff0ull) {
+            tl_stream = saved;
+            return a->status = fail(ctx, GATB_ERR_INVALID, "annotations: index needs 2^32 or more entries");
+        }
+        a->capacity = need;
+        e = a->civ.alloc(need);
+        if (e == cudaSuccess) e = a->ctrk.alloc(need);
+        if (e == cudaSuccess) e = a->cprev.alloc(need);
+        if (e == cudaSuccess) e = annotations_build(a);
+        if (e == cudaSuccess) e = cudaEventSynchronize(a->ready);
+        h_err = slot[0];
+    }
+    // the raw lists and the scan scratch are no longer needed (freed in upload-stream order)
+    a->d_offs.release(); a->d_start.release(); a->d_end.release(); a->d_err.release(); a->d_total.release();
+    a->scan_tmp.release();
+    tl_stream = saved;
     if (e != cudaSuccess) return a->status = fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e));
-    const uint32_t h_err = ctx->err_slots[a->err_slot];
     if (h_err & 1u) return a->status = fail(ctx, GATB_ERR_RANGE, "annotations: coordinate >= 2^31");
-    if (h_err) return a->status = fail(ctx, GATB_ERR_INVALID, "annotations: empty or inverted segment, or list not sorted/normalized");
+    if (h_err & 2u) return a->status = fail(ctx, GATB_ERR_INVALID, "annotations: empty or inverted segment, or list not sorted/normalized");
+    if (h_err) return a->status = fail(ctx, GATB_ERR_CUDA, "annotations: index build failed");
     return a->status = GATB_OK;
 }
 
-static inline uint64_t align16(uint64_t x) { return (x + 15u) & ~(uint64_t)15u; }
-
-// shared memory left for a staged filter
-static uint32_t filter_budget(const gatb_ctx *ctx)
-{
-    if (ctx->tile_budget) return ctx->tile_budget;
-    // sized for the integer counters; a nucleotide-density launch (larger accumulators) reads the
-    // few filters that no longer fit from global memory
-    const size_t over = count_smem_overhead(ctx->count_threads, ctx->schunk_max, false) + 1024;
-    return (uint32_t)(ctx->smem_optin > over + 16384 ? ctx->smem_optin - over : 16384);
-}
-
-// geometry of tile (tracks a0 .. a0+ka-1, key k); see count.cuh.  ok == false: larger than 4 GiB.
-static bool tile_geometry(const uint64_t *offs, const uint32_t *end, uint32_t A, uint32_t K, uint32_t a0,
-                          uint32_t ka, uint32_t k, uint32_t bin_factor, uint32_t budget, uint32_t bm_budget,
-                          uint32_t bm_min_shift, TileHeader &h, uint64_t &bytes)
-{
-    memset(&h, 0, sizeof(h));
-    uint64_t nc = 0;
-    uint32_t extent = 0;
-    for (uint32_t kk = 0; kk < ka && a0 + kk < A; kk++) {
-        const uint64_t l = (uint64_t)(a0 + kk) * K + k;
-        const uint64_t n = offs[l + 1] - offs[l];
-        nc += n;
-        if (n) extent = std::max(extent, end[offs[l + 1] - 1]);
-    }
-    if (nc > 0x7fffffffull) return false;
-    h.n_cons = (uint32_t)nc;
-    const uint64_t hdr = align16(sizeof(TileHeader));
-    const uint64_t civ_bytes = align16((nc + 2) * 8);
-    const uint64_t cslot_bytes = align16(nc + 2);
-    // occupancy bitmap: the finest power-of-two resolution (>= 2^bm_min_shift positions per bit) whose
-    // bits fit bm_budget bytes; one zero word of padding so that bit bm_bits exists and is never set
-    uint64_t bm_bytes = 0;
-    if (nc > 0) {
-        const uint32_t ext1 = extent ? extent - 1 : 0;
-        uint32_t sh = bm_min_shift;
-        while (sh < 31 && ((uint64_t)(ext1 >> sh) + 1) > (uint64_t)bm_budget * 8) sh++;
-        h.bm_shift = sh;
-        h.bm_bits = (ext1 >> sh) + 1;
-        bm_bytes = align16(((uint64_t)(h.bm_bits + 31) / 32 + 1) * 4);
-    }
-    h.bm_off = (uint32_t)hdr;
-    const uint64_t fixed = hdr + bm_bytes + cslot_bytes + civ_bytes;
-    // bin index: bin_factor bins per interval, but no more than fit next to the bitmap and the intervals
-    // in the budget (and never more bins than positions); lists with > 65534 intervals are binary-searched
-    uint64_t nbins = 0;
-    if (nc > 0 && nc <= 65534 && extent > 1) {
-        nbins = (uint64_t)bin_factor * nc;
-        if (fixed + 2 * (nbins + 1) + 16 > budget) {
-            const uint64_t room = budget > fixed + 64 ? (budget - fixed - 32) / 2 : 0;
-            nbins = std::max<uint64_t>(std::min<uint64_t>(nbins, room), std::min<uint64_t>(nc, nbins));
-        }
-        nbins = std::min<uint64_t>(nbins, extent);
-    }
-    h.nbins = (uint32_t)nbins;
-    h.inv = nbins ? (uint32_t)(((uint64_t)nbins << 32) / ((uint64_t)extent + 1)) : 0;
-    if (nbins && h.inv == 0) { h.nbins = 0; nbins = 0; }
-    uint64_t o = hdr + bm_bytes;
-    h.idx_off = (uint32_t)o;
-    o += nbins ? align16((nbins + 1) * 2) : 0;
-    h.cslot_off = (uint32_t)o;
-    o += cslot_bytes;
-    h.civ_off = (uint32_t)o;
-    o += civ_bytes;
-    if (o > 0xfffffff0ull) return false;
-    h.stage_bytes = (uint32_t)o;
-    h.uiv_off = (uint32_t)o;
-    o += align16((nc + 2) * 8);
-    if (o > 0xfffffff0ull) return false;
-    h.uoff_off = (uint32_t)o;
-    o += align16((nc + 2) * 4);
-    if (o > 0xfffffff0ull) return false;
-    bytes = o;
-    return true;
-}
+static inline uint32_t floor_log2(uint64_t x) { uint32_t l = 0; while (x >>= 1) l++; return l; }
 
 extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
                                              const uint32_t *start, const uint32_t *end, const uint32_t *key_ws_nseg,
@@ -371,93 +358,83 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     if (offs[0] != 0) return fail(ctx, GATB_ERR_INVALID, "annotations: offsets must start at 0");
     for (uint64_t l = 0; l < n_lists; l++)
         if (offs[l + 1] < offs[l]) return fail(ctx, GATB_ERR_INVALID, "annotations: offsets not monotone");
-    if (offs[n_lists] > 0xffffffffull) return fail(ctx, GATB_ERR_INVALID, "annotations: more than 2^32 intervals");
+    const uint64_t n_iv = offs[n_lists];
+    if (n_iv > 0xffffffffull) return fail(ctx, GATB_ERR_INVALID, "annotations: more than 2^32 intervals");
     CU(ctx, cudaSetDevice(ctx->device));
     if (ctx->err_free.empty()) return fail(ctx, GATB_ERR_INVALID, "annotations: more than 256 sets pending validation");
     tl_stream = ctx->upload_stream;       // every allocation, copy and free below is ordered on the upload stream
 
     const uint32_t A = (uint32_t)n_annot, K = (uint32_t)n_keys;
-    const uint32_t bin_factor = std::max(1u, env_u32("GATB_BIN_FACTOR", 4));
-    const uint32_t budget = filter_budget(ctx);
-    // the bitmap is staged for EVERY tile, so it has to fit whatever a launch leaves (see count_params_annos)
-    const uint32_t bm_budget = std::max(256u, std::min(env_u32("GATB_BITMAP_BYTES", 32768), budget / 4));
-    const uint32_t bm_min_shift = std::min(20u, env_u32("GATB_BITMAP_MIN_SHIFT", 10));
-    // largest group size whose every filter fits the budget (floor: one track per tile; oversized
-    // filters are then read from global memory by the kernel)
-    uint32_t ka = 1;
-    TileHeader h;
-    uint64_t bytes = 0;
-    for (uint32_t cand = (uint32_t)KMAX; cand >= 1; cand--) {
-        bool ok = true;
-        for (uint32_t a0 = 0; a0 < A && ok; a0 += cand)
-            for (uint32_t k = 0; k < K; k++)
-                if (!tile_geometry(offs, end, A, K, a0, cand, k, bin_factor, budget, bm_budget, bm_min_shift, h, bytes) || h.stage_bytes > budget) {
-                    ok = false;
-                    break;
-                }
-        if (ok || cand == 1) { ka = cand; break; }
-    }
+    const uint32_t ka = std::min(A, std::min(GROUP_TRACKS_MAX, std::max(1u, env_u32("GATB_GROUP_TRACKS", GROUP_TRACKS_MAX))));
     const uint32_t G = (A + ka - 1) / ka;
 
-    // tile headers on the host (O(tracks x keys)); everything else is written by build_tiles_kernel
-    // from the raw CSR arrays, which also validates the lists
-    std::vector<uint64_t> tile_off((size_t)G * K);
-    std::vector<uint32_t> tile_stage((size_t)G * K);
-    std::vector<TileHeader> headers((size_t)G * K);
-    uint64_t total = 0;
-    uint32_t max_stage = 0, max_prefix = 0;
-    for (uint32_t g = 0; g < G; g++)
-        for (uint32_t k = 0; k < K; k++) {
-            const size_t t = (size_t)g * K + k;
-            if (!tile_geometry(offs, end, A, K, g * ka, ka, k, bin_factor, budget, bm_budget, bm_min_shift, headers[t], bytes))
-                return fail(ctx, GATB_ERR_INVALID, "annotations: tile larger than 4 GiB");
-            tile_off[t] = total;
-            tile_stage[t] = headers[t].stage_bytes;
-            max_stage = std::max(max_stage, headers[t].stage_bytes);
-            max_prefix = std::max(max_prefix, headers[t].idx_off);
-            total += bytes;
-        }
-
+    // Bin width: about the mean interval length (estimated from a few thousand intervals; any value is
+    // correct, it only trades entries per interval against entries per bin), but per key no more than
+    // ~4 bins per interval, so that sparse lists do not pay for empty bins.
+    uint32_t shift = env_u32("GATB_BIN_SHIFT", 0);
+    uint64_t mean_len = 1;
+    if (n_iv) {
+        const uint64_t step = std::max<uint64_t>(1, n_iv / 4096);
+        uint64_t sum = 0, cnt = 0;
+        for (uint64_t i = 0; i < n_iv; i += step) { sum += (end[i] > start[i]) ? end[i] - start[i] : 0u; cnt++; }
+        mean_len = std::max<uint64_t>(1, sum / cnt);
+    }
+    if (shift == 0) shift = floor_log2(mean_len);
+    shift = std::min(30u, std::max(4u, shift));
     gatb_annotations *a = new gatb_annotations();
     a->ctx = ctx; a->n_annot = A; a->n_keys = K; a->n_groups = G; a->ka = ka;
-    a->max_stage = max_stage;
-    a->max_prefix = max_prefix;
-    a->n_intervals = offs[n_lists];
+    a->n_intervals = n_iv;
+    a->h_keybins.resize((size_t)G * K);
+    uint64_t n_boff = 0;
+    double est = 0;
+    for (uint32_t g = 0; g < G; g++)
+        for (uint32_t k = 0; k < K; k++) {
+            uint64_t n = 0;
+            uint32_t extent = 0;
+            for (uint32_t t = g * ka; t < std::min(A, (g + 1) * ka); t++) {
+                const uint64_t l = (uint64_t)t * K + k;
+                if (offs[l + 1] > offs[l]) { n += offs[l + 1] - offs[l]; extent = std::max(extent, end[offs[l + 1] - 1]); }
+            }
+            KeyBins &kb = a->h_keybins[(size_t)g * K + k];
+            kb.base = n_boff; kb.nbins = 0; kb.shift = shift;
+            if (n == 0 || extent == 0) continue;
+            extent = std::min(extent, 0x7fffffffu);            // (larger coordinates fail validation)
+            uint32_t sh = shift;
+            while (sh < 30 && ((uint64_t)(extent - 1) >> sh) + 1 > 4 * n + 16) sh++;
+            kb.shift = sh;
+            kb.nbins = (uint32_t)(((uint64_t)(extent - 1) >> sh) + 1);
+            n_boff += (uint64_t)kb.nbins + 1;
+            est += (double)n * (1.0 + (double)mean_len / (double)(1ull << sh));
+        }
+    if (n_boff > 0x7fffffffull) { delete a; return fail(ctx, GATB_ERR_INVALID, "annotations: index too large"); }
+    a->n_boff = n_boff;
+    a->capacity = (uint64_t)(est * 1.25) + 4096;
+    if (env_u32("GATB_INDEX_CAPACITY", 0)) a->capacity = env_u32("GATB_INDEX_CAPACITY", 0);    // (tests: forces the rebuild)
+
     cudaStream_t st = ctx->upload_stream;
-    DevBuf<uint64_t> d_offs;
-    DevBuf<uint32_t> d_start, d_end, d_err;
-    DevBuf<TileHeader> d_headers;
     a->err_slot = ctx->err_free.back();
     ctx->err_free.pop_back();
-    ctx->err_slots[a->err_slot] = 0;
+    memset(ctx->err_slots + 4 * a->err_slot, 0, 4 * sizeof(uint32_t));
     // the small host-built tables first (pageable memory: staged before the call returns), then the
     // caller's arrays, which must stay valid until gatb_annotations_wait() or the first use returns
-    cudaError_t e = a->tiles.alloc(total);
-    if (e == cudaSuccess) e = a->tile_off.upload(tile_off.data(), tile_off.size(), st);
-    if (e == cudaSuccess) e = a->tile_stage.upload(tile_stage.data(), tile_stage.size(), st);
-    if (e == cudaSuccess) e = d_headers.upload(headers.data(), headers.size(), st);
+    cudaError_t e = a->keybins.upload(a->h_keybins.data(), a->h_keybins.size(), st);
     if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, st); a->has_nseg = true; }
-    if (e == cudaSuccess) e = d_offs.upload(offs, n_lists + 1, st);
-    if (e == cudaSuccess) e = d_start.upload(start, offs[n_lists], st);
-    if (e == cudaSuccess) e = d_end.upload(end, offs[n_lists], st);
-    if (e == cudaSuccess) e = d_err.alloc(1);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_err.p, 0, sizeof(uint32_t), st);
-    if (e == cudaSuccess) {
-        BuildTilesParams bp;
-        bp.tiles = a->tiles.p; bp.tile_off = a->tile_off.p; bp.headers = d_headers.p;
-        bp.offs = d_offs.p; bp.start = d_start.p; bp.end = d_end.p;
-        bp.n_annot = A; bp.n_keys = K; bp.n_groups = G; bp.ka = ka; bp.error = d_err.p;
-        ProfScope ps(ctx, PROF_OTHER, st);
-        launch_build_tiles(st, bp);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->err_slots + a->err_slot, d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = a->boff.alloc(n_boff + 1);
+    if (e == cudaSuccess) e = a->civ.alloc(a->capacity);
+    if (e == cudaSuccess) e = a->ctrk.alloc(a->capacity);
+    if (e == cudaSuccess) e = a->cprev.alloc(a->capacity);
+    if (e == cudaSuccess) e = a->scan_tmp.alloc(build_bins_scan_bytes(n_boff + 1));
+    if (e == cudaSuccess) e = a->d_offs.upload(offs, n_lists + 1, st);
+    if (e == cudaSuccess) e = a->d_start.upload(start, n_iv, st);
+    if (e == cudaSuccess) e = a->d_end.upload(end, n_iv, st);
+    if (e == cudaSuccess) e = a->d_err.alloc(1);
+    if (e == cudaSuccess) e = a->d_total.alloc(1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ready, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventRecord(a->ready, st);
+    if (e == cudaSuccess) e = annotations_build(a);
     if (e != cudaSuccess) { cudaStreamSynchronize(st); delete a; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
     a->pending = true;
     *out = a;
-    return GATB_OK;       // (the temporaries are freed in stream order, after the build kernel)
+    return GATB_OK;
 }
 
 extern "C" int gatb_annotations_wait(gatb_annotations *a)
@@ -486,33 +463,32 @@ extern "C" void gatb_annotations_destroy(gatb_annotations *a)
 {
     if (!a) return;
     cudaSetDevice(a->ctx->device);
-    // free in the order of the compute stream, where the tiles were last read
-    a->tiles.st = a->tile_off.st = a->tile_stage.st = a->key_ws_nseg.st = a->ctx->stream;
+    if (a->pending) annotations_finish(a);
+    // free in the order of the compute stream, where the index was last read
+    a->keybins.st = a->boff.st = a->civ.st = a->ctrk.st = a->cprev.st = a->key_ws_nseg.st = a->ctx->stream;
     delete a;
 }
 
 // fill the annotation side of CountParams and pick the sample chunk
-static void count_params_annos(const gatb_annotations *a, uint32_t n_samples, bool density, CountParams &p)
+static int count_params_annos(const gatb_annotations *a, uint32_t n_samples, bool density, CountParams &p)
 {
-    const gatb_ctx *ctx = a->ctx;
-    p.tiles = a->tiles.p; p.tile_off = a->tile_off.p; p.tile_stage = a->tile_stage.p;
+    gatb_ctx *ctx = a->ctx;
+    p.keybins = a->keybins.p; p.boff = a->boff.p; p.civ = a->civ.p; p.ctrk = a->ctrk.p; p.cprev = a->cprev.p;
     p.key_ws_nseg = a->has_nseg ? a->key_ws_nseg.p : nullptr;
     p.n_annot = a->n_annot; p.n_keys = a->n_keys; p.n_groups = a->n_groups; p.ka = a->ka;
+    p.lps = ctx->count_lps; p.depth = ctx->count_depth;
     p.n_samples = n_samples;
-    // enough CTAs for ~4 waves, chunk a multiple of the warps per CTA
-    const uint32_t nwarps = (uint32_t)ctx->count_threads / 32;
-    const uint32_t target = (uint32_t)ctx->sm_count * 4;
-    uint32_t chunks = std::max(1u, (target + a->n_groups - 1) / a->n_groups);
-    uint32_t schunk = (n_samples + chunks - 1) / chunks;
-    schunk = ((schunk + nwarps - 1) / nwarps) * nwarps;
-    schunk = std::max(nwarps, std::min(schunk, std::max(nwarps, ctx->schunk_max)));
-    p.schunk = schunk;
-    // what this launch can stage: the device limit minus its own accumulators and queues
-    const size_t over = count_smem_overhead(ctx->count_threads, schunk, density) + 1024;
-    const size_t room = ctx->smem_optin > over ? ctx->smem_optin - over : 0;
-    // (the header + bitmap prefix is staged unconditionally; a launch that cannot hold it fails in
-    // cudaFuncSetAttribute rather than overrunning)
-    p.smem_tile_budget = std::max((uint32_t)std::min<size_t>(room, a->max_stage), a->max_prefix);
+    // samples per CTA: what the shared-memory accumulators allow, then as few whole waves of CTAs as that needs
+    const size_t cell = density ? 20u : 4u;
+    const size_t room = ctx->smem_optin > 1024 ? ctx->smem_optin - 1024 : 0;
+    uint32_t smax = (uint32_t)std::min<size_t>(room / (cell * a->ka), 4096);
+    if (ctx->schunk_max) smax = std::min(smax, ctx->schunk_max);
+    if (smax == 0) return fail(ctx, GATB_ERR_INVALID, "count: accumulators of one sample do not fit shared memory");
+    const uint64_t per_wave = std::max<uint64_t>(1, (uint64_t)ctx->sm_count / a->n_groups);
+    uint64_t chunks = (n_samples + smax - 1) / smax;
+    if (n_samples >= per_wave) chunks = (chunks + per_wave - 1) / per_wave * per_wave;
+    p.schunk = (uint32_t)std::max<uint64_t>(1, (n_samples + chunks - 1) / chunks);
+    return GATB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -547,7 +523,7 @@ extern "C" int gatb_count_lists(gatb_ctx *ctx, const gatb_annotations *annos, in
     uint64_t stride = 0;
     for (uint32_t k = 0; k < K; k++) {
         if (cap[k] >= (1u << 24)) return fail(ctx, GATB_ERR_INVALID, "count_lists: 2^24 or more segments on one key");
-        key_base[k] = stride; stride += (cap[k] + 1u) & ~1u;      // even: the kernel loads segment pairs (16 bytes)
+        key_base[k] = stride; stride += cap[k];
     }
     if (stride == 0) stride = 1;
     std::vector<uint64_t> packed(n_samples * stride, 0);
@@ -572,14 +548,14 @@ extern "C" int gatb_count_lists(gatb_ctx *ctx, const gatb_annotations *annos, in
 
     CountParams p;
     memset(&p, 0, sizeof(p));
-    count_params_annos(annos, (uint32_t)n_samples, false, p);
     p.placed = d_packed.p; p.sample_stride = stride; p.key_base = d_base.p; p.placed_n = d_n.p;
     p.key_present = key_present ? d_present.p : nullptr;
     p.out_u32 = d_out.p; p.out_f64 = d_outf.p;
 
     std::vector<uint32_t> h_u(n_samples * A);
     for (int c = 0; c < n_counters; c++) {
-        count_params_annos(annos, (uint32_t)n_samples, counters[c] == GATB_NUCLEOTIDE_DENSITY, p);
+        rc = count_params_annos(annos, (uint32_t)n_samples, counters[c] == GATB_NUCLEOTIDE_DENSITY, p);
+        if (rc) return rc;
         { ProfScope ps(ctx, PROF_COUNT); CU(ctx, launch_count(st, counters[c], p, ctx->count_threads)); }
         double *o = out + (uint64_t)c * n_samples * A;
         if (counters[c] == GATB_NUCLEOTIDE_DENSITY) {
@@ -948,19 +924,24 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
         if (rc) return rc;
         CountParams p;
         memset(&p, 0, sizeof(p));
-        count_params_annos(annos, b, false, p);
         p.placed = s->placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
         p.placed_n = s->placed_n.p; p.key_present = nullptr;
         for (int c = 0; c < n_counters; c++) {
             const bool dens = counters[c] == GATB_NUCLEOTIDE_DENSITY;
-            count_params_annos(annos, b, dens, p);
+            rc = count_params_annos(annos, b, dens, p);
+            if (rc) return rc;
             uint32_t *dst_u = out_counts ? out_counts + ((uint64_t)c * n_samples + done) * A : nullptr;
             double *dst_f = out_density ? out_density + done * A : nullptr;
             p.out_u32 = out_is_device ? dst_u : s->out_tmp.p;
             p.out_f64 = out_is_device ? dst_f : s->out_tmp_f.p;
-            // annotations still uploading / building (gatb_annotations_create_async): the placement above
-            // did not need them, the count does
-            if (annos->pending) CU(ctx, cudaStreamWaitEvent(st, annos->ready, 0));
+            // annotations still uploading / building (gatb_annotations_create_async): the placement queued
+            // above did not need them, the count does.  The host waits here (the GPU keeps placing) because
+            // the build's outcome decides what may be launched: invalid lists or an index to rebuild.
+            if (annos->pending) {
+                rc = annotations_finish(const_cast<gatb_annotations *>(annos));
+                tl_stream = ctx->stream;
+                if (rc) { cudaStreamSynchronize(st); return rc; }
+            }
             { ProfScope ps(ctx, PROF_COUNT); CU(ctx, launch_count(st, counters[c], p, ctx->count_threads)); }
             if (!out_is_device) {
                 if (dens) CU(ctx, cudaMemcpyAsync(dst_f, s->out_tmp_f.p, (uint64_t)b * A * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -1,4 +1,4 @@
-// count.cuh -- counting kernel (K3/K4), the annotation tile format and column statistics (K5).
+// count.cuh -- counting kernel (K3/K4), the annotation grid index and column statistics (K5).
 //
 // Replaces overlapWithSegments / intersectionWithSegments (gat/SegmentList.pyx:1026-1146) as used by
 // the Counter* classes (gat/Engine.pyx:1412-1472) inside computeSample (gat/__init__.py:580-587) and
@@ -9,53 +9,42 @@
 
 namespace gatb {
 
-constexpr int KMAX = 8;                 // annotation tracks per tile (register accumulators)
+constexpr uint32_t GROUP_TRACKS_MAX = 4096;   // annotation tracks per group (shared-memory accumulators per sample)
 
-// Tile = up to KMAX annotation tracks on ONE key (contig), contiguous in global memory:
+// Annotation index = a uniform GRID over every key (contig), shared by all tracks of a group (normally:
+// all tracks).  Bin b of a key covers positions [b << shift, (b+1) << shift); its ENTRIES are the
+// intervals of every track that touch it, each stored with its track slot, so an interval spanning m bins
+// is stored m times.  A segment [s,e) covering bins b0..b1 finds every interval that can overlap it in
+// ONE contiguous run of entries, boff[b0] .. boff[b1+1]: a two-load replacement for the binary search
+// (utils/gat_utils.c:8-32) that answers all tracks at once.  A pair (segment, interval) met in several
+// bins is counted in the bin that holds the first base of their intersection: an interval starting at
+// or after s counts at its FIRST entry (flag in ctrk), one starting before s counts in bin b0 (entry index
+// < boff[b0+1]).  Entries of a bin are in no particular order; all accumulation is by integer atomics,
+// so results do not depend on it.
 //
-//   TileHeader
-//   uint32 bm[bm_words]      occupancy bitmap of the UNION of the tracks' intervals      } "filter":
-//   uint16 idx[nbins+1]      bin index: where in civ[] a query starting in the bin begins } staged in
-//   uint8  cslot[n_cons+2]   track slot of civ[c]                                        } shared
-//   uint2  civ[n_cons+2]     every interval of every track, sorted by start, + 2 sentinels } memory
-//   uint2  uiv[n_union+2]    union intervals (sorted, disjoint) + 2 sentinels   } global memory only: build
-//   uint32 uoff[n_union+1]   union interval u = civ[uoff[u] .. uoff[u+1])       } time, and the nbins == 0 path
-//
-// About 93 % of the simulated segments overlap no interval of ANY of the 8 tracks.  The count kernel
-// therefore tests a segment first against the bitmap -- bit b is set when a union interval touches
-// positions [b << bm_shift, (b+2) << bm_shift); one 4-byte shared-memory load answers "can [s,e) overlap
-// anything?" for every segment no longer than 1 << bm_shift, longer ones are candidates outright -- and
-// only the candidates go on, through a per-warp queue, to the exact pass: idx[bin(s)] = uoff[first union
-// interval whose end is > the lowest position of the bin], bin(x) = umulhi(x, inv) -- a one-probe
-// replacement for the binary search (utils/gat_utils.c:8-32) over sorted interval ends; every interval
-// overlapping [s,e) lies at or after that index, so a forward walk over civ[] until start >= e, skipping
-// ends <= s, visits them all, entirely in shared memory.  nbins == 0 (more than 65534 intervals) falls
-// back to the binary search over uiv[] in global memory.
-struct TileHeader {
-    uint32_t n_union;       // written by the build kernel
-    uint32_t n_cons;
-    uint32_t nbins;
-    uint32_t inv;           // bin(x) = min(umulhi(x, inv), nbins)
-    uint32_t bm_off;        // byte offsets from the tile start; bitmap: one zero word of padding at the end
-    uint32_t bm_shift;      // log2 of the positions per bit
-    uint32_t bm_bits;       // bits that can be set: positions >= bm_bits << bm_shift hold no interval
-    uint32_t idx_off;       // [0, idx_off) = header + bitmap: staged for every tile
-    uint32_t cslot_off;
-    uint32_t civ_off;
-    uint32_t stage_bytes;   // [0, stage_bytes) = header .. civ: staged when it fits
-    uint32_t uiv_off;
-    uint32_t uoff_off;
-    uint32_t pad[3];
+//   KeyBins keybins[n_groups][n_keys]    where the key's bins start in boff[], how many, log2(bin width)
+//   uint32  boff[]                       per (group, key): nbins+1 entry offsets (absolute, into the arrays below)
+//   uint2   civ[n_entries]               the interval (start, end)
+//   uint16  ctrk[n_entries]              track slot within the group | 0x8000 on the interval's first bin
+//   uint32  cprev[n_entries]             end of the previous interval of the same track on this key (0: none):
+//                                        "is this the first interval of its track overlapping [s,e)?" = cprev <= s
+struct KeyBins {
+    uint64_t base;      // index into boff[] of the key's first offset
+    uint32_t nbins;     // 0: no interval of any track of the group on this key
+    uint32_t shift;
 };
 
 struct CountParams {
     // annotations
-    const uint8_t *tiles;           // tile blob
-    const uint64_t *tile_off;       // [n_groups][n_keys] byte offset
-    const uint32_t *tile_stage;     // [n_groups][n_keys] bytes of the filter part (stage_bytes)
+    const KeyBins *keybins;         // [n_groups][n_keys]
+    const uint32_t *boff;
+    const uint2 *civ;
+    const uint16_t *ctrk;
+    const uint32_t *cprev;
     const uint32_t *key_ws_nseg;    // [n_keys] or NULL
     uint32_t n_annot, n_keys, n_groups, ka;   // ka = tracks per group
-    uint32_t smem_tile_budget;      // filters up to this many bytes are staged in shared memory
+    uint32_t lps;                   // lanes that share one segment's run of entries (1, 2, 4, 8, 16, 32)
+    uint32_t depth;                 // software-pipeline depth of the entry loads (1, 2, 4)
     // segment sets
     const uint64_t *placed;         // [n_samples][sample_stride] packed
     uint64_t sample_stride;
@@ -69,22 +58,29 @@ struct CountParams {
     double *out_f64;                // [n_samples][n_annot] (nucleotide-density)
 };
 
-// shared memory a count launch needs besides the staged filter (accumulators + per-warp queues)
-size_t count_smem_overhead(int threads, uint32_t schunk, bool density);
+// shared memory of a count launch: accumulators [schunk][ka] (u32; density: + (sum, compensation) doubles)
+size_t count_smem_bytes(uint32_t schunk, uint32_t ka, bool density);
 
-// Builds every tile from the raw annotation CSR arrays on the device (one CTA per tile): merges the
-// tracks' lists by start, derives the union and its bin index, and validates the lists (error bit 0:
-// coordinate >= 2^31, bit 1: empty / unsorted / overlapping = not normalized).
-struct BuildTilesParams {
-    uint8_t *tiles;
-    const uint64_t *tile_off;       // [n_groups][n_keys]
-    const TileHeader *headers;      // [n_groups][n_keys], geometry computed on the host
+// Builds the grid index from the raw annotation CSR arrays on the device and validates the lists
+// (error bit 0: coordinate >= 2^31, bit 1: empty / unsorted / overlapping = not normalized, bit 2: more
+// entries than `capacity`).  Three launches: count entries per bin, exclusive scan, fill.
+struct BuildBinsParams {
     const uint64_t *offs;           // [n_annot*n_keys+1]
     const uint32_t *start, *end;
+    uint64_t n_intervals;
+    const KeyBins *keybins;         // [n_groups][n_keys]
+    uint32_t *boff;                 // [n_boff], zeroed by the caller
+    uint64_t n_boff;
+    uint2 *civ;
+    uint16_t *ctrk;
+    uint32_t *cprev;
+    uint64_t capacity;              // entries the arrays hold
     uint32_t n_annot, n_keys, n_groups, ka;
     uint32_t *error;
+    unsigned long long *total;      // out: entries needed
 };
-void launch_build_tiles(cudaStream_t st, const BuildTilesParams &p);
+size_t build_bins_scan_bytes(uint64_t n_boff);
+cudaError_t launch_build_bins(cudaStream_t st, const BuildBinsParams &p, void *scan_tmp, size_t scan_bytes);
 
 // counter: GATB_* id.  Returns cudaError from the launch configuration.
 cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int threads);

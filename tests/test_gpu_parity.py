@@ -157,26 +157,39 @@ def _fallback_problem(rng, oracle, big_list=False):
     return annos, nseg, samples
 
 
-def test_count_fallback_paths_match_oracle(ctx, oracle, monkeypatch):
-    """the slow-but-general code paths of the count kernel: filters read from global memory (tile budget
-    forced tiny), unions without a bin index (> 65534 intervals), groups with fewer than 8 tracks"""
+def test_count_index_geometries_match_oracle(ctx, oracle, monkeypatch):
+    """every geometry of the annotation grid index gives the oracle's counts: several track groups per
+    launch, bins much narrower / much wider than the intervals, an index that outgrows its estimated
+    capacity and is rebuilt at the exact size, lists with > 65534 intervals, every work split of the kernel"""
     from gat_b200 import device
     rng = np.random.default_rng(77)
-    for big_list, budget in ((False, "256"), (True, "0"), (True, "256")):
+    knobs = ("GATB_GROUP_TRACKS", "GATB_BIN_SHIFT", "GATB_INDEX_CAPACITY", "GATB_COUNT_LPS", "GATB_COUNT_DEPTH",
+             "GATB_SCHUNK")
+    cases = [
+        (False, {}),
+        (False, {"GATB_GROUP_TRACKS": "4"}),
+        (False, {"GATB_BIN_SHIFT": "4", "GATB_COUNT_LPS": "1"}),
+        (False, {"GATB_BIN_SHIFT": "20", "GATB_COUNT_LPS": "4", "GATB_COUNT_DEPTH": "4"}),
+        (False, {"GATB_INDEX_CAPACITY": "16", "GATB_COUNT_LPS": "8", "GATB_COUNT_DEPTH": "1"}),
+        (True, {"GATB_COUNT_LPS": "32", "GATB_SCHUNK": "2"}),
+        (True, {"GATB_GROUP_TRACKS": "3", "GATB_INDEX_CAPACITY": "1000", "GATB_COUNT_LPS": "16"}),
+    ]
+    for big_list, env in cases:
         annos, nseg, samples = _fallback_problem(rng, oracle, big_list)
-        if budget != "0":
-            monkeypatch.setenv("GATB_TILE_BUDGET", budget)
-        else:
-            monkeypatch.delenv("GATB_TILE_BUDGET", raising=False)
-        c2 = device.Context(0)                       # the budget is read when the context is created
+        for k in knobs:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c2 = device.Context(0)                       # the knobs are read when the context / the set is created
         an = device.Annotations(c2, annos, key_ws_nseg=nseg)
         got = an.count_lists(COUNTERS, samples)
         an.close()
         c2.close()
         for s in range(len(samples)):
             exp = oracle.count_placed(samples[s], annos, nseg, COUNTERS)
-            assert np.array_equal(got[:, s, :], exp), (big_list, budget, s)
-    monkeypatch.delenv("GATB_TILE_BUDGET", raising=False)
+            assert np.array_equal(got[:, s, :], exp), (big_list, env, s)
+    for k in knobs:
+        monkeypatch.delenv(k, raising=False)
 
 
 def test_invalid_inputs_fail_loudly(ctx):
