@@ -34,7 +34,7 @@ struct gatb_ctx {
     // tunables (env overrides, for profiling)
     int count_threads = 1024;
     uint32_t schunk_max = 0;            // samples per count CTA; 0: whatever shared memory allows
-    uint32_t count_lps = 16, count_depth = 2;
+    uint32_t kgrp_max = 0;              // keys per item table; 0: whatever fits
     // optional per-kernel timing (bench.py roofline): CUDA events around every launch
     bool profiling = false;
     struct Span { int cls; cudaEvent_t a, b; };
@@ -153,8 +153,7 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     ctx->count_threads = (int)std::min(1024u, std::max(32u, env_u32("GATB_COUNT_THREADS", 1024) / 32 * 32));
     ctx->schunk_max = env_u32("GATB_SCHUNK", 0);
-    ctx->count_lps = env_u32("GATB_COUNT_LPS", 16);
-    ctx->count_depth = env_u32("GATB_COUNT_DEPTH", 2);
+    ctx->kgrp_max = env_u32("GATB_KEY_GROUP", 0);
     ctx->batch = env_u32("GATB_BATCH", 0);
     *out = ctx;
     return GATB_OK;
@@ -253,7 +252,7 @@ struct gatb_annotations {
     DevBuf<KeyBins> keybins;
     DevBuf<uint32_t> boff;
     DevBuf<uint2> civ;
-    DevBuf<uint16_t> ctrk;
+    DevBuf<uint2> cent;
     DevBuf<uint32_t> cprev;
     DevBuf<uint32_t> key_ws_nseg;
     bool has_nseg = false;
@@ -291,7 +290,7 @@ static cudaError_t annotations_build(gatb_annotations *a)
     memset(&bp, 0, sizeof(bp));
     bp.offs = a->d_offs.p; bp.start = a->d_start.p; bp.end = a->d_end.p; bp.n_intervals = a->n_intervals;
     bp.keybins = a->keybins.p; bp.boff = a->boff.p; bp.n_boff = a->n_boff;
-    bp.civ = a->civ.p; bp.ctrk = a->ctrk.p; bp.cprev = a->cprev.p; bp.capacity = a->capacity;
+    bp.cent = a->cent.p; bp.civ = a->civ.p; bp.cprev = a->cprev.p; bp.capacity = a->capacity;
     bp.n_annot = a->n_annot; bp.n_keys = a->n_keys; bp.n_groups = a->n_groups; bp.ka = a->ka;
     bp.error = a->d_err.p; bp.total = a->d_total.p;
     {
@@ -326,7 +325,7 @@ static int annotations_finish(gatb_annotations *a)
         }
         a->capacity = need;
         e = a->civ.alloc(need);
-        if (e == cudaSuccess) e = a->ctrk.alloc(need);
+        if (e == cudaSuccess) e = a->cent.alloc(need);
         if (e == cudaSuccess) e = a->cprev.alloc(need);
         if (e == cudaSuccess) e = annotations_build(a);
         if (e == cudaSuccess) e = cudaEventSynchronize(a->ready);
@@ -380,7 +379,7 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
         mean_len = std::max<uint64_t>(1, sum / cnt);
     }
     if (shift == 0) shift = floor_log2(mean_len);
-    shift = std::min(30u, std::max(4u, shift));
+    shift = std::min(20u, std::max(4u, shift));
     gatb_annotations *a = new gatb_annotations();
     a->ctx = ctx; a->n_annot = A; a->n_keys = K; a->n_groups = G; a->ka = ka;
     a->n_intervals = n_iv;
@@ -400,7 +399,7 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
             if (n == 0 || extent == 0) continue;
             extent = std::min(extent, 0x7fffffffu);            // (larger coordinates fail validation)
             uint32_t sh = shift;
-            while (sh < 30 && ((uint64_t)(extent - 1) >> sh) + 1 > 4 * n + 16) sh++;
+            while (sh < 20 && ((uint64_t)(extent - 1) >> sh) + 1 > 4 * n + 16) sh++;
             kb.shift = sh;
             kb.nbins = (uint32_t)(((uint64_t)(extent - 1) >> sh) + 1);
             n_boff += (uint64_t)kb.nbins + 1;
@@ -421,7 +420,7 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, st); a->has_nseg = true; }
     if (e == cudaSuccess) e = a->boff.alloc(n_boff + 1);
     if (e == cudaSuccess) e = a->civ.alloc(a->capacity);
-    if (e == cudaSuccess) e = a->ctrk.alloc(a->capacity);
+    if (e == cudaSuccess) e = a->cent.alloc(a->capacity);
     if (e == cudaSuccess) e = a->cprev.alloc(a->capacity);
     if (e == cudaSuccess) e = a->scan_tmp.alloc(build_bins_scan_bytes(n_boff + 1));
     if (e == cudaSuccess) e = a->d_offs.upload(offs, n_lists + 1, st);
@@ -465,7 +464,7 @@ extern "C" void gatb_annotations_destroy(gatb_annotations *a)
     cudaSetDevice(a->ctx->device);
     if (a->pending) annotations_finish(a);
     // free in the order of the compute stream, where the index was last read
-    a->keybins.st = a->boff.st = a->civ.st = a->ctrk.st = a->cprev.st = a->key_ws_nseg.st = a->ctx->stream;
+    a->keybins.st = a->boff.st = a->civ.st = a->cent.st = a->cprev.st = a->key_ws_nseg.st = a->ctx->stream;
     delete a;
 }
 
@@ -473,21 +472,25 @@ extern "C" void gatb_annotations_destroy(gatb_annotations *a)
 static int count_params_annos(const gatb_annotations *a, uint32_t n_samples, bool density, CountParams &p)
 {
     gatb_ctx *ctx = a->ctx;
-    p.keybins = a->keybins.p; p.boff = a->boff.p; p.civ = a->civ.p; p.ctrk = a->ctrk.p; p.cprev = a->cprev.p;
+    p.keybins = a->keybins.p; p.boff = a->boff.p; p.cent = a->cent.p; p.civ = a->civ.p; p.cprev = a->cprev.p;
     p.key_ws_nseg = a->has_nseg ? a->key_ws_nseg.p : nullptr;
     p.n_annot = a->n_annot; p.n_keys = a->n_keys; p.n_groups = a->n_groups; p.ka = a->ka;
-    p.lps = ctx->count_lps; p.depth = ctx->count_depth;
     p.n_samples = n_samples;
-    // samples per CTA: what the shared-memory accumulators allow, then as few whole waves of CTAs as that needs
+    // samples per CTA: what shared memory allows next to the staging and ITEM_TABLE_BYTES of item tables,
+    // then as few whole waves of CTAs as that needs
+    const size_t ITEM_TABLE_BYTES = 24576;
     const size_t cell = density ? 20u : 4u;
-    const size_t room = ctx->smem_optin > 1024 ? ctx->smem_optin - 1024 : 0;
-    uint32_t smax = (uint32_t)std::min<size_t>(room / (cell * a->ka), 4096);
+    const size_t fixed = count_smem_bytes(0, 0, 0, ctx->count_threads, density) + ITEM_TABLE_BYTES + 1024;
+    const size_t room = ctx->smem_optin > fixed ? ctx->smem_optin - fixed : 0;
+    uint32_t smax = (uint32_t)std::min<size_t>(room / (cell * a->ka), 2048);
     if (ctx->schunk_max) smax = std::min(smax, ctx->schunk_max);
     if (smax == 0) return fail(ctx, GATB_ERR_INVALID, "count: accumulators of one sample do not fit shared memory");
     const uint64_t per_wave = std::max<uint64_t>(1, (uint64_t)ctx->sm_count / a->n_groups);
     uint64_t chunks = (n_samples + smax - 1) / smax;
     if (n_samples >= per_wave) chunks = (chunks + per_wave - 1) / per_wave * per_wave;
     p.schunk = (uint32_t)std::max<uint64_t>(1, (n_samples + chunks - 1) / chunks);
+    p.kgrp = (uint32_t)std::max<size_t>(1, std::min<size_t>(a->n_keys, ITEM_TABLE_BYTES / (8u * p.schunk + 8u)));
+    if (ctx->kgrp_max) p.kgrp = std::min(p.kgrp, ctx->kgrp_max);
     return GATB_OK;
 }
 

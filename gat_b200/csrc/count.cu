@@ -1,16 +1,19 @@
 // count.cu -- K3/K4 counting kernel, construction of the annotation grid index, and K5 column statistics.  sm_100a.
 //
 // Counting: a CTA owns (group of tracks -- normally ALL tracks) x (chunk of samples) and keeps the chunk's
-// count matrix [sample][track] in shared memory.  It walks the keys (contigs) in order; the warps of the
-// CTA share the chunk's segment lists in blocks of 32 segments (lane = segment).  A lane turns its segment
-// into the run of grid-index entries that can overlap it (count.cuh: two or three 4-byte loads), then the
-// warp works the 32 runs off cooperatively, LPS lanes per run: one 8-byte + one 2-byte load per entry,
-// the overlap test, and an integer atomic into the (sample, track) accumulator.  The entry loads of the
-// next runs are issued before the current one is consumed (software pipeline in registers), which is what
-// hides the L2 latency of this gather-bound kernel.  The index of one key (a few tens of MB at 1000 tracks)
-// stays in L2 while the CTAs walk the keys in the same order.  The float64 nucleotide-density sum is formed
-// per key from the integers, in the same key order and with the same compensated summation as the
-// reference's Python sum() (gat/__init__.py:583-587).
+// count matrix [sample][track] in shared memory.  It walks the keys (contigs) in order; the work of a key is
+// cut into ITEMS of 32 consecutive segments of one sample (lane = segment), handed to the warps through a
+// shared-memory counter, so that no warp waits for another.  A lane turns its segment into the run of
+// grid-index entries that can overlap it (count.cuh: two or three 4-byte loads); the warp then works the 32
+// runs off as ONE flat sequence of entries, 32 per round with every lane busy: which run a flat position
+// belongs to comes from a warp OR-reduction (redux.sync) of the runs' first positions, the run's segment
+// from a 16-byte shared-memory load.  Per entry: one 8-byte load, the overlap test, an integer atomic into
+// the (sample, track) accumulator.  Three items are in flight per warp -- segment load / bin-offset loads /
+// entry rounds -- and the entry loads run one round ahead: that is what hides the L2 latency of this
+// gather-bound kernel.  The index of one key (a few tens of MB at 1000 tracks) stays in L2 while the CTAs
+// walk the keys in the same order.  The float64 nucleotide-density sum is formed per key from the integers,
+// in the same key order and with the same compensated summation as the reference's Python sum()
+// (gat/__init__.py:583-587).
 #include <algorithm>
 #include <cub/device/device_scan.cuh>
 #include "count.cuh"
@@ -18,139 +21,133 @@
 
 namespace gatb {
 
-size_t count_smem_bytes(uint32_t schunk, uint32_t ka, bool density)
-{
-    return (size_t)schunk * ka * (density ? 20u : 4u) + 16u;
-}
+constexpr uint32_t NO_ITEM = 0xffffffffu;
 
-// ---------------------------------------------------------------------------------------------------
-// One overlapping, de-duplicated pair: interval [x,y) of track slot t (previous interval of the track ends
-// at pv) against segment [s,e) (previous segment of the list ends at pe).  Coordinates are < 2^31.
-//   nucleotide-overlap   overlapWithSegments            gat/SegmentList.pyx:1026-1076
-//   segment-overlap      intersectionWithSegments(base) :1078-1146  (a segment counts once per track:
-//                        at the first interval of the track that overlaps it, i.e. pv <= s)
-//   segment-midoverlap   midpoint tested against that FIRST overlapping interval only (:1137-1144)
-//   annotation-*         roles swapped: an interval is counted by the first segment overlapping it,
-//                        i.e. when it does not already overlap the previous segment (x >= pe)
-//   overlap-pieces       len(a.intersect(b)): every overlapping pair is one piece (:1469-1549)
-template <int COUNTER>
-__device__ __forceinline__ void count_pair(uint32_t s, uint32_t e, uint32_t pe, uint32_t x, uint32_t y, uint32_t pv,
-                                           uint32_t *__restrict__ cell)
+// shared memory: per-warp staging (32 x 16 B segments + 32 x 4 B previous ends), accumulators, item tables
+__host__ __device__ __forceinline__ size_t count_smem_fixed(uint32_t nwarps) { return (size_t)nwarps * 32u * 20u; }
+
+size_t count_smem_bytes(uint32_t schunk, uint32_t ka, uint32_t kgrp, int threads, bool density)
 {
-    if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
-        atomicAdd(cell, min(e, y) - max(s, x));
-    } else if (COUNTER == GATB_SEGMENT_OVERLAP) {
-        if (pv <= s) atomicAdd(cell, 1u);
-    } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
-        const uint32_t mid = s + ((e - s) >> 1);
-        if (pv <= s && x <= mid && mid < y) atomicAdd(cell, 1u);
-    } else if (COUNTER == GATB_OVERLAP_PIECES) {
-        atomicAdd(cell, 1u);
-    } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
-        if (x >= pe) atomicAdd(cell, 1u);
-    } else {
-        const uint32_t m = x + ((y - x) >> 1);
-        if (x >= pe && s <= m && m < e) atomicAdd(cell, 1u);
-    }
+    return count_smem_fixed((uint32_t)threads / 32u) + (size_t)schunk * ka * (density ? 20u : 4u) +
+           (size_t)kgrp * (2u * schunk + 2u) * 4u + 16u;
 }
 
 template <int COUNTER> struct NeedPrevInterval { static constexpr bool value = COUNTER == GATB_SEGMENT_OVERLAP || COUNTER == GATB_SEGMENT_MIDOVERLAP; };
 template <int COUNTER> struct NeedPrevSegment { static constexpr bool value = COUNTER == GATB_ANNOTATION_OVERLAP || COUNTER == GATB_ANNOTATION_MIDOVERLAP; };
 
-// one entry in flight: loaded ahead of its use
+// one entry of the flat sequence, loaded one round ahead of its use
 struct Flight {
-    uint2 v;            // interval
-    uint32_t t, pv;     // track slot | first flag; previous end of the track
+    uint4 o;            // its segment: start, end, (first entry of the run) - (its flat position), end of bin b0's entries
+    uint2 w;            // packed entry
+    uint2 iv;           // exact interval (annotation-* counters)
+    uint32_t pv;        // end of the previous interval of the track (segment-* counters)
+    uint32_t pe;        // end of the previous segment (annotation-* counters)
     uint32_t j;         // entry index
-    int pass;           // which run(s) of the block it belongs to; -1: none left
+    bool live;
 };
 
-// One block of 32 segments (lane = segment i of sample slot `slot` on this key) against the grid index.
-template <int COUNTER, int LPS, int DEPTH>
-__device__ __forceinline__ void count_block(const CountParams &p, const uint32_t *__restrict__ boff, uint32_t nbins,
-                                            uint32_t shift, const uint64_t *__restrict__ segs, uint32_t n, uint32_t b,
-                                            int lane, uint32_t *__restrict__ acc)
+// ---------------------------------------------------------------------------------------------------
+// One live entry against its segment [s,e).  A pair met in several bins counts in the bin that holds the
+// first base of the intersection (count.cuh).  Coordinates are < 2^31.
+//   nucleotide-overlap   overlapWithSegments            gat/SegmentList.pyx:1026-1076
+//   segment-overlap      intersectionWithSegments(base) :1078-1146  (a segment counts once per track:
+//                        at the first interval of the track that overlaps it, i.e. previous end <= s)
+//   segment-midoverlap   midpoint tested against that FIRST overlapping interval only (:1137-1144)
+//   annotation-*         roles swapped: an interval is counted by the first segment overlapping it,
+//                        i.e. when it does not already overlap the previous segment (x >= pe)
+//   overlap-pieces       len(a.intersect(b)): every overlapping pair is one piece (:1469-1549)
+template <int COUNTER>
+__device__ __forceinline__ void count_entry(const CountParams &p, const Flight &f, uint32_t *__restrict__ acc)
 {
-    constexpr int SPP = 32 / LPS;                  // segments (runs) worked on per pass
-    const uint32_t i = b * 32u + (uint32_t)lane;
-    uint32_t s = 0, e = 0, r0 = 0, rf = 0, r1 = 0, pe = 0;
-    if (i < n) {
-        const uint64_t sg = segs[i];
-        s = seg_start(sg); e = seg_end(sg);
-        const uint32_t b0 = s >> shift;
-        if (b0 < nbins) {
-            const uint32_t b1 = min((e - 1u) >> shift, nbins - 1u);
-            r0 = boff[b0]; rf = boff[b0 + 1u];
-            r1 = (b1 == b0) ? rf : boff[b1 + 1u];
-        }
+    const uint32_t s = f.o.x, e = f.o.y;
+    const bool first = (f.w.x >> 31) != 0u;
+    const uint32_t t = f.w.y >> 20;
+    uint32_t x, y;
+    if (NeedPrevSegment<COUNTER>::value) { x = f.iv.x; y = f.iv.y; }
+    else {
+        // a continuation entry starts before its bin, hence before every segment that meets it in bin b0
+        x = first ? (f.w.x & 0x7fffffffu) : 0u;
+        const uint32_t l = f.w.y & ENTRY_LEN_MASK;
+        y = first ? x + l : f.w.x;
+        if (first && l == ENTRY_LEN_MASK) y = p.civ[f.j].y;          // 2^20 - 1 bases or longer: rare
     }
-    if (NeedPrevSegment<COUNTER>::value) {
-        pe = __shfl_up_sync(GATB_FULL, e, 1);
-        if (lane == 0) pe = (i > 0 && i < n) ? seg_end(segs[i - 1u]) : 0u;
-    }
-    const uint32_t have = __ballot_sync(GATB_FULL, r1 > r0);
-    if (!have) return;
-    const int sub = lane & (LPS - 1), own = lane / LPS;
-
-    int next_pass = 0;
-    // issue the loads of the first entries of the next non-empty pass
-    auto fetch = [&](Flight &f) {
-        f.pass = -1;
-        while (next_pass < LPS) {
-            const uint32_t om = (SPP == 32) ? GATB_FULL : (((1u << SPP) - 1u) << (next_pass * SPP));
-            if (have & om) break;
-            next_pass++;
-        }
-        if (next_pass >= LPS) return;
-        const int owner = next_pass * SPP + own;
-        const uint32_t q0 = (LPS == 1) ? r0 : __shfl_sync(GATB_FULL, r0, owner);
-        const uint32_t q1 = (LPS == 1) ? r1 : __shfl_sync(GATB_FULL, r1, owner);
-        f.j = q0 + (uint32_t)sub;
-        f.pass = next_pass++;
-        if (f.j < q1) {
-            f.v = p.civ[f.j];
-            f.t = p.ctrk[f.j];
-            if (NeedPrevInterval<COUNTER>::value) f.pv = p.cprev[f.j];
-        }
-    };
-    auto consume = [&](Flight &f) {
-        const int owner = f.pass * SPP + own;
-        const uint32_t os = (LPS == 1) ? s : __shfl_sync(GATB_FULL, s, owner);
-        const uint32_t oe = (LPS == 1) ? e : __shfl_sync(GATB_FULL, e, owner);
-        const uint32_t of = (LPS == 1) ? rf : __shfl_sync(GATB_FULL, rf, owner);
-        const uint32_t o1 = (LPS == 1) ? r1 : __shfl_sync(GATB_FULL, r1, owner);
-        uint32_t ope = 0;
-        if (NeedPrevSegment<COUNTER>::value) ope = (LPS == 1) ? pe : __shfl_sync(GATB_FULL, pe, owner);
-        uint32_t j = f.j;
-        uint2 v = f.v;
-        uint32_t t = f.t, pv = NeedPrevInterval<COUNTER>::value ? f.pv : 0u;
-        while (j < o1) {
-            // overlapping, and met in the bin that holds the first base of the intersection
-            if (v.x < oe && v.y > os && ((v.x >= os) ? (t & 0x8000u) != 0u : j < of))
-                count_pair<COUNTER>(os, oe, ope, v.x, v.y, pv, acc + (t & 0x7fffu));
-            j += LPS;
-            if (j < o1) {                                   // runs longer than LPS: not prefetched
-                v = p.civ[j];
-                t = p.ctrk[j];
-                if (NeedPrevInterval<COUNTER>::value) pv = p.cprev[j];
-            }
-        }
-    };
-
-    Flight fl[DEPTH];
-#pragma unroll
-    for (int d = 0; d < DEPTH; d++) fetch(fl[d]);
-    while (true) {
-#pragma unroll
-        for (int d = 0; d < DEPTH; d++) {
-            if (fl[d].pass < 0) return;                     // warp-uniform
-            consume(fl[d]);
-            fetch(fl[d]);
-        }
+    const bool here = (first && x >= s) ? (x < e) : (f.j < f.o.w && y > s);
+    if (!here) return;
+    uint32_t *cell = acc + t;
+    if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
+        atomicAdd(cell, min(e, y) - max(s, x));
+    } else if (COUNTER == GATB_SEGMENT_OVERLAP) {
+        if (f.pv <= s) atomicAdd(cell, 1u);
+    } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
+        const uint32_t mid = s + ((e - s) >> 1);
+        if (f.pv <= s && x <= mid && mid < y) atomicAdd(cell, 1u);
+    } else if (COUNTER == GATB_OVERLAP_PIECES) {
+        atomicAdd(cell, 1u);
+    } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
+        if (x >= f.pe) atomicAdd(cell, 1u);
+    } else {
+        const uint32_t m = x + ((y - x) >> 1);
+        if (x >= f.pe && s <= m && m < e) atomicAdd(cell, 1u);
     }
 }
 
-template <int COUNTER, bool DENSITY, int LPS, int DEPTH>
+// an item whose bin offsets have been requested: lane = segment
+struct Indexed {
+    uint32_t slot;              // sample slot in the chunk, NO_ITEM: none
+    uint32_t s, e, pe, r0, rf, r1;
+};
+
+// The 32 runs [r0, r1) of an item as one flat sequence of entries.
+template <int COUNTER>
+__device__ __forceinline__ void run_item(const CountParams &p, const Indexed &it, int lane, uint4 *__restrict__ stg,
+                                         uint32_t *__restrict__ stg_pe, uint32_t *__restrict__ acc)
+{
+    const uint32_t len = it.r1 - it.r0;
+    const uint32_t incl = warp_incl_scan_add_u32(len);
+    const uint32_t total = __shfl_sync(GATB_FULL, incl, 31);
+    if (total == 0) return;
+    const uint32_t excl = incl - len;
+    const uint32_t have = __ballot_sync(GATB_FULL, len != 0u);
+    const uint32_t rank = __popc(have & ((1u << lane) - 1u));
+    __syncwarp();                                   // the previous item's readers are done with the staging
+    if (len) {
+        stg[rank] = make_uint4(it.s, it.e, it.r0 - excl, it.rf);
+        if (NeedPrevSegment<COUNTER>::value) stg_pe[rank] = it.pe;
+    }
+    __syncwarp();
+    const uint32_t le_mask = 0xffffffffu >> (31 - lane);
+    uint32_t started = 0;                           // non-empty runs that begin before the round
+
+    // flat positions base .. base+31: who owns them, and the entry loads
+    auto fetch = [&](uint32_t base, Flight &f) {
+        const uint32_t d = excl - base;
+        const uint32_t mask = __reduce_or_sync(GATB_FULL, (len != 0u && d < 32u) ? (1u << d) : 0u);
+        const uint32_t owner = started + __popc(mask & le_mask) - 1u;
+        started += __popc(mask);
+        f.live = base + (uint32_t)lane < total;
+        if (f.live) {
+            f.o = stg[owner];
+            f.j = base + (uint32_t)lane + f.o.z;
+            f.w = p.cent[f.j];
+            if (NeedPrevInterval<COUNTER>::value) f.pv = p.cprev[f.j];
+            if (NeedPrevSegment<COUNTER>::value) { f.iv = p.civ[f.j]; f.pe = stg_pe[owner]; }
+        }
+    };
+    Flight fa, fb;
+    fetch(0, fa);
+    for (uint32_t base = 0;;) {
+        base += 32;
+        if (base < total) fetch(base, fb);
+        if (fa.live) count_entry<COUNTER>(p, fa, acc);
+        if (base >= total) break;
+        base += 32;
+        if (base < total) fetch(base, fa);
+        if (fb.live) count_entry<COUNTER>(p, fb, acc);
+        if (base >= total) break;
+    }
+}
+
+template <int COUNTER, bool DENSITY>
 __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -161,54 +158,133 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
     const uint32_t s_begin = blockIdx.y * p.schunk;
     const uint32_t s_end = min(s_begin + p.schunk, p.n_samples);
     const uint32_t ns = s_end - s_begin, ncells = ns * ka;
-    // layout: [density only: (sum, compensation) doubles per cell][u32 per cell]
-    double *acc_d = reinterpret_cast<double *>(smem);
-    uint32_t *acc_u = reinterpret_cast<uint32_t *>(smem + (DENSITY ? (size_t)p.schunk * p.ka * 16u : 0u));
+    // layout: [staging][density only: (sum, compensation) doubles per cell][u32 per cell][item tables]
+    uint4 *stg = reinterpret_cast<uint4 *>(smem) + warp * 32;
+    uint32_t *stg_pe = reinterpret_cast<uint32_t *>(smem + (size_t)nwarps * 32u * 16u) + warp * 32;
+    uint8_t *base = smem + count_smem_fixed((uint32_t)nwarps);
+    double *acc_d = reinterpret_cast<double *>(base);
+    uint32_t *acc_u = reinterpret_cast<uint32_t *>(base + (DENSITY ? (size_t)p.schunk * p.ka * 16u : 0u));
+    // per key of the current key group: pre[slot] = items before sample slot (ns + 1), nn[slot] = its
+    // number of segments on the key, cnt = next item to hand out
+    uint32_t *pre = acc_u + (size_t)p.schunk * p.ka;
+    uint32_t *nn = pre + (size_t)p.kgrp * (p.schunk + 1u);
+    uint32_t *cnt = nn + (size_t)p.kgrp * p.schunk;
 
     for (uint32_t i = threadIdx.x; i < ncells; i += blockDim.x) {
         acc_u[i] = 0u;
         if (DENSITY) { acc_d[2 * i] = 0.0; acc_d[2 * i + 1] = 0.0; }
     }
-    __syncthreads();
 
-    for (uint32_t k = 0; k < p.n_keys; k++) {
-        const KeyBins kb = p.keybins[(uint64_t)g * p.n_keys + k];
-        if (kb.nbins == 0) continue;                      // no interval of any track on this key
-        if (DENSITY && p.key_ws_nseg[k] == 0) continue;   // counter returns 0 (gat/Engine.pyx:1438-1440)
-        const uint32_t *boff = p.boff + kb.base;
-        const uint64_t *placed_key = p.placed + p.key_base[k];
-        // the blocks of 32 segments of every sample of the chunk, dealt out to the warps round-robin
-        for (uint32_t q0 = 0; q0 < ns; q0 += 32) {
-            uint32_t my_n = 0;
-            if (q0 + lane < ns) {
-                const uint64_t sl = s_begin + q0 + lane;
-                if (!p.key_present || p.key_present[sl * p.n_keys + k]) my_n = p.placed_n[sl * p.n_keys + k];
+    for (uint32_t k0 = 0; k0 < p.n_keys; k0 += p.kgrp) {
+        const uint32_t nk = min(p.kgrp, p.n_keys - k0);
+        __syncthreads();                                   // everyone is done with the previous tables
+        for (uint32_t kk = (uint32_t)warp; kk < nk; kk += (uint32_t)nwarps) {
+            const uint32_t k = k0 + kk;
+            const KeyBins kb = p.keybins[(uint64_t)g * p.n_keys + k];
+            // no interval of any track on this key / density: counter returns 0 (gat/Engine.pyx:1438-1440)
+            const bool dead = kb.nbins == 0 || (DENSITY && p.key_ws_nseg[k] == 0);
+            uint32_t run = 0;
+            for (uint32_t q0 = 0; q0 < ns; q0 += 32) {
+                const uint32_t slot = q0 + (uint32_t)lane;
+                uint32_t n = 0;
+                if (slot < ns && !dead) {
+                    const uint64_t sl = s_begin + slot;
+                    if (!p.key_present || p.key_present[sl * p.n_keys + k]) n = p.placed_n[sl * p.n_keys + k];
+                }
+                const uint32_t incl = warp_incl_scan_add_u32((n + 31u) >> 5);
+                if (slot < ns) {
+                    nn[kk * p.schunk + slot] = n;
+                    pre[kk * (p.schunk + 1u) + slot + 1u] = run + incl;
+                }
+                run += __shfl_sync(GATB_FULL, incl, 31);
             }
-            const uint32_t cnt = min(32u, ns - q0);
-            for (uint32_t q = 0; q < cnt; q++) {
-                const uint32_t n = __shfl_sync(GATB_FULL, my_n, q);
-                const uint32_t slot = q0 + q;
-                const uint64_t *segs = placed_key + (uint64_t)(s_begin + slot) * p.sample_stride;
-                for (uint32_t b = ((uint32_t)warp + (uint32_t)nwarps - slot % (uint32_t)nwarps) % (uint32_t)nwarps;
-                     b * 32u < n; b += nwarps)
-                    count_block<COUNTER, LPS, DEPTH>(p, boff, kb.nbins, kb.shift, segs, n, b, lane, acc_u + slot * ka);
-            }
+            if (lane == 0) { pre[kk * (p.schunk + 1u)] = 0u; cnt[kk] = 0u; }
         }
-        if (DENSITY) {
-            // per key: float(overlap) / len(workspace), accumulated in key order like the reference's
-            // Python sum(): CPython >= 3.12 sums floats with Neumaier compensation (Python/bltinmodule.c)
-            __syncthreads();
-            const double den = (double)p.key_ws_nseg[k];
-            for (uint32_t i = threadIdx.x; i < ncells; i += blockDim.x) {
-                const uint32_t v = acc_u[i];
-                if (v) {
-                    const double x = (double)v / den, f = acc_d[2 * i], t = f + x;
-                    acc_d[2 * i + 1] += (fabs(f) >= fabs(x)) ? ((f - t) + x) : ((x - t) + f);
-                    acc_d[2 * i] = t;
-                    acc_u[i] = 0u;
+        __syncthreads();
+
+        for (uint32_t kk = 0; kk < nk; kk++) {
+            const uint32_t k = k0 + kk;
+            const uint32_t *pre_k = pre + kk * (p.schunk + 1u);
+            const uint32_t *nn_k = nn + kk * p.schunk;
+            const uint32_t n_items = pre_k[ns];
+            if (n_items) {
+                const KeyBins kb = p.keybins[(uint64_t)g * p.n_keys + k];
+                const uint32_t *__restrict__ boff = p.boff + kb.base;
+                const uint64_t *__restrict__ placed_key = p.placed + p.key_base[k] + (uint64_t)s_begin * p.sample_stride;
+                // three items in flight: A = segment requested, B = bin offsets requested, then run
+                uint32_t a_slot = NO_ITEM, a_i = 0, a_n = 0, a_prev = 0;
+                uint64_t a_sg = 0;
+                Indexed b;
+                b.slot = NO_ITEM;
+                bool more = true;
+                uint32_t cursor = 0;
+                while (more || a_slot != NO_ITEM || b.slot != NO_ITEM) {
+                    // A -> B': the segment has arrived; request its bin offsets
+                    Indexed nb;
+                    nb.slot = a_slot;
+                    nb.s = nb.e = nb.pe = nb.r0 = nb.rf = nb.r1 = 0u;
+                    if (a_slot != NO_ITEM) {
+                        if (a_i < a_n) {
+                            nb.s = seg_start(a_sg); nb.e = seg_end(a_sg);
+                            const uint32_t b0 = nb.s >> kb.shift;
+                            if (b0 < kb.nbins) {
+                                const uint32_t b1 = min((nb.e - 1u) >> kb.shift, kb.nbins - 1u);
+                                nb.r0 = boff[b0]; nb.rf = boff[b0 + 1u];
+                                nb.r1 = (b1 == b0) ? nb.rf : boff[b1 + 1u];
+                            }
+                        }
+                        if (NeedPrevSegment<COUNTER>::value) {
+                            nb.pe = __shfl_up_sync(GATB_FULL, nb.e, 1);
+                            if (lane == 0) nb.pe = a_prev;
+                        }
+                    }
+                    // next A: take an item, request its segments
+                    a_slot = NO_ITEM;
+                    if (more) {
+                        uint32_t w = 0;
+                        if (lane == 0) w = atomicAdd(cnt + kk, 1u);
+                        w = __shfl_sync(GATB_FULL, w, 0);
+                        if (w >= n_items) more = false;
+                        else {
+                            while (true) {                  // items come in increasing order: scan forward
+                                const uint32_t idx = cursor + (uint32_t)lane;
+                                const uint32_t m = __ballot_sync(GATB_FULL, idx >= ns || pre_k[idx + 1u] > w);
+                                if (m) { cursor += (uint32_t)__ffs(m) - 1u; break; }
+                                cursor += 32u;
+                            }
+                            a_slot = cursor;
+                            a_n = nn_k[cursor];
+                            a_i = (w - pre_k[cursor]) * 32u + (uint32_t)lane;
+                            const uint64_t *segs = placed_key + (uint64_t)cursor * p.sample_stride;
+                            if (a_i < a_n) a_sg = segs[a_i];
+                            if (NeedPrevSegment<COUNTER>::value)
+                                a_prev = (lane == 0 && a_i > 0u && a_i < a_n) ? seg_end(segs[a_i - 1u]) : 0u;
+                        }
+                    }
+                    // run B (its offsets were requested one turn ago), then B <- B'
+                    if (b.slot != NO_ITEM) run_item<COUNTER>(p, b, lane, stg, stg_pe, acc_u + b.slot * ka);
+                    b = nb;
                 }
             }
-            __syncthreads();
+            if (DENSITY) {
+                // per key: float(overlap) / len(workspace), accumulated in key order like the reference's
+                // Python sum(): CPython >= 3.12 sums floats with Neumaier compensation (Python/bltinmodule.c)
+                __syncthreads();
+                const uint32_t nseg = p.key_ws_nseg[k];
+                if (n_items && nseg) {
+                    const double den = (double)nseg;
+                    for (uint32_t i = threadIdx.x; i < ncells; i += blockDim.x) {
+                        const uint32_t v = acc_u[i];
+                        if (v) {
+                            const double x = (double)v / den, f = acc_d[2 * i], t = f + x;
+                            acc_d[2 * i + 1] += (fabs(f) >= fabs(x)) ? ((f - t) + x) : ((x - t) + f);
+                            acc_d[2 * i] = t;
+                            acc_u[i] = 0u;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
     __syncthreads();
@@ -221,36 +297,15 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
     }
 }
 
-template <int COUNTER, bool DENSITY, int LPS, int DEPTH>
-static cudaError_t launch_count_t3(cudaStream_t st, const CountParams &p, int threads)
-{
-    const size_t smem = count_smem_bytes(p.schunk, p.ka, DENSITY);
-    cudaError_t e = cudaFuncSetAttribute(count_kernel<COUNTER, DENSITY, LPS, DEPTH>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid(p.n_groups, (p.n_samples + p.schunk - 1) / p.schunk);
-    count_kernel<COUNTER, DENSITY, LPS, DEPTH><<<grid, threads, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
-template <int COUNTER, bool DENSITY, int LPS>
-static cudaError_t launch_count_t2(cudaStream_t st, const CountParams &p, int threads)
-{
-    if (LPS == 1 || p.depth <= 1) return launch_count_t3<COUNTER, DENSITY, LPS, 1>(st, p, threads);
-    if (p.depth == 2) return launch_count_t3<COUNTER, DENSITY, LPS, 2>(st, p, threads);
-    return launch_count_t3<COUNTER, DENSITY, LPS, 4>(st, p, threads);
-}
-
 template <int COUNTER, bool DENSITY>
 static cudaError_t launch_count_t(cudaStream_t st, const CountParams &p, int threads)
 {
-    switch (p.lps) {
-    case 1:  return launch_count_t2<COUNTER, DENSITY, 1>(st, p, threads);
-    case 4:  return launch_count_t2<COUNTER, DENSITY, 4>(st, p, threads);
-    case 8:  return launch_count_t2<COUNTER, DENSITY, 8>(st, p, threads);
-    case 16: return launch_count_t2<COUNTER, DENSITY, 16>(st, p, threads);
-    default: return launch_count_t2<COUNTER, DENSITY, 32>(st, p, threads);
-    }
+    const size_t smem = count_smem_bytes(p.schunk, p.ka, p.kgrp, threads, DENSITY);
+    cudaError_t e = cudaFuncSetAttribute(count_kernel<COUNTER, DENSITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(p.n_groups, (p.n_samples + p.schunk - 1) / p.schunk);
+    count_kernel<COUNTER, DENSITY><<<grid, threads, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int threads)
@@ -315,8 +370,9 @@ __global__ void __launch_bounds__(256) bins_pass_kernel(BuildBinsParams p)
         else {
             const uint64_t pos = atomicAdd(cur + b, 1u);
             if (pos < p.capacity) {
+                p.cent[pos] = (b == b0) ? make_uint2(0x80000000u | x, (t << 20) | min(y - x, ENTRY_LEN_MASK))
+                                        : make_uint2(y, t << 20);
                 p.civ[pos] = make_uint2(x, y);
-                p.ctrk[pos] = (uint16_t)(t | (b == b0 ? 0x8000u : 0u));
                 p.cprev[pos] = py;
             }
         }

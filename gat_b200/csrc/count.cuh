@@ -11,6 +11,8 @@ namespace gatb {
 
 constexpr uint32_t GROUP_TRACKS_MAX = 4096;   // annotation tracks per group (shared-memory accumulators per sample)
 
+constexpr uint32_t ENTRY_LEN_MASK = 0xfffffu;
+
 // Annotation index = a uniform GRID over every key (contig), shared by all tracks of a group (normally:
 // all tracks).  Bin b of a key covers positions [b << shift, (b+1) << shift); its ENTRIES are the
 // intervals of every track that touch it, each stored with its track slot, so an interval spanning m bins
@@ -18,33 +20,37 @@ constexpr uint32_t GROUP_TRACKS_MAX = 4096;   // annotation tracks per group (sh
 // ONE contiguous run of entries, boff[b0] .. boff[b1+1]: a two-load replacement for the binary search
 // (utils/gat_utils.c:8-32) that answers all tracks at once.  A pair (segment, interval) met in several
 // bins is counted in the bin that holds the first base of their intersection: an interval starting at
-// or after s counts at its FIRST entry (flag in ctrk), one starting before s counts in bin b0 (entry index
+// or after s counts at its FIRST entry, one starting before s counts in bin b0 (entry index
 // < boff[b0+1]).  Entries of a bin are in no particular order; all accumulation is by integer atomics,
 // so results do not depend on it.
 //
 //   KeyBins keybins[n_groups][n_keys]    where the key's bins start in boff[], how many, log2(bin width)
 //   uint32  boff[]                       per (group, key): nbins+1 entry offsets (absolute, into the arrays below)
-//   uint2   civ[n_entries]               the interval (start, end)
-//   uint16  ctrk[n_entries]              track slot within the group | 0x8000 on the interval's first bin
+//   uint2   cent[n_entries]              the entry the counting kernel streams, 8 bytes:
+//                                          first entry of its interval:  .x = 1<<31 | start,  .y = slot<<20 | min(length, 2^20-1)
+//                                          continuation (later bins):    .x = end,            .y = slot<<20
+//                                        (slot = track within the group, < 4096; a continuation starts before its
+//                                        bin, which is all the counters need to know of its start; a length field
+//                                        of 2^20-1 sends the kernel to civ[] for the end)
+//   uint2   civ[n_entries]               the exact interval (start, end): annotation-* counters, long intervals
 //   uint32  cprev[n_entries]             end of the previous interval of the same track on this key (0: none):
 //                                        "is this the first interval of its track overlapping [s,e)?" = cprev <= s
 struct KeyBins {
     uint64_t base;      // index into boff[] of the key's first offset
     uint32_t nbins;     // 0: no interval of any track of the group on this key
-    uint32_t shift;
+    uint32_t shift;     // 4 .. 20
 };
 
 struct CountParams {
     // annotations
     const KeyBins *keybins;         // [n_groups][n_keys]
     const uint32_t *boff;
+    const uint2 *cent;
     const uint2 *civ;
-    const uint16_t *ctrk;
     const uint32_t *cprev;
     const uint32_t *key_ws_nseg;    // [n_keys] or NULL
     uint32_t n_annot, n_keys, n_groups, ka;   // ka = tracks per group
-    uint32_t lps;                   // lanes that share one segment's run of entries (1, 2, 4, 8, 16, 32)
-    uint32_t depth;                 // software-pipeline depth of the entry loads (1, 2, 4)
+    uint32_t kgrp;                  // keys whose item tables are held in shared memory at a time
     // segment sets
     const uint64_t *placed;         // [n_samples][sample_stride] packed
     uint64_t sample_stride;
@@ -58,8 +64,9 @@ struct CountParams {
     double *out_f64;                // [n_samples][n_annot] (nucleotide-density)
 };
 
-// shared memory of a count launch: accumulators [schunk][ka] (u32; density: + (sum, compensation) doubles)
-size_t count_smem_bytes(uint32_t schunk, uint32_t ka, bool density);
+// shared memory of a count launch: per-warp staging, accumulators [schunk][ka] (u32; density: + (sum,
+// compensation) doubles), item tables of kgrp keys
+size_t count_smem_bytes(uint32_t schunk, uint32_t ka, uint32_t kgrp, int threads, bool density);
 
 // Builds the grid index from the raw annotation CSR arrays on the device and validates the lists
 // (error bit 0: coordinate >= 2^31, bit 1: empty / unsorted / overlapping = not normalized, bit 2: more
@@ -71,8 +78,8 @@ struct BuildBinsParams {
     const KeyBins *keybins;         // [n_groups][n_keys]
     uint32_t *boff;                 // [n_boff], zeroed by the caller
     uint64_t n_boff;
+    uint2 *cent;
     uint2 *civ;
-    uint16_t *ctrk;
     uint32_t *cprev;
     uint64_t capacity;              // entries the arrays hold
     uint32_t n_annot, n_keys, n_groups, ka;

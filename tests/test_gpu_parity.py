@@ -151,6 +151,9 @@ def _fallback_problem(rng, oracle, big_list=False):
     if big_list:
         starts = np.arange(0, 70000, dtype=np.int64) * 50
         annos[3][1] = np.stack([starts, starts + rng.integers(1, 40, len(starts))], axis=1).astype(np.uint32)
+        # intervals at and beyond the 2^20 - 1 bases the packed index entry can hold
+        annos[5][0] = np.array([[1000, 3500000]], dtype=np.uint32)
+        annos[6][1] = np.array([[10, 10 + 1048575], [2000000, 2000000 + 1048574]], dtype=np.uint32)
     nseg = [2, 3]
     samples = [[helpers.random_list(rng, span, int(rng.integers(1, 400)), int(rng.choice([30, 700, 9000]))) for _ in range(K)]
                for _ in range(S)]
@@ -160,19 +163,21 @@ def _fallback_problem(rng, oracle, big_list=False):
 def test_count_index_geometries_match_oracle(ctx, oracle, monkeypatch):
     """every geometry of the annotation grid index gives the oracle's counts: several track groups per
     launch, bins much narrower / much wider than the intervals, an index that outgrows its estimated
-    capacity and is rebuilt at the exact size, lists with > 65534 intervals, every work split of the kernel"""
+    capacity and is rebuilt at the exact size, lists with > 65534 intervals, intervals longer than a packed
+    entry holds, item tables of one key at a time, small CTAs"""
     from gat_b200 import device
     rng = np.random.default_rng(77)
-    knobs = ("GATB_GROUP_TRACKS", "GATB_BIN_SHIFT", "GATB_INDEX_CAPACITY", "GATB_COUNT_LPS", "GATB_COUNT_DEPTH",
+    knobs = ("GATB_GROUP_TRACKS", "GATB_BIN_SHIFT", "GATB_INDEX_CAPACITY", "GATB_KEY_GROUP", "GATB_COUNT_THREADS",
              "GATB_SCHUNK")
     cases = [
         (False, {}),
         (False, {"GATB_GROUP_TRACKS": "4"}),
-        (False, {"GATB_BIN_SHIFT": "4", "GATB_COUNT_LPS": "1"}),
-        (False, {"GATB_BIN_SHIFT": "20", "GATB_COUNT_LPS": "4", "GATB_COUNT_DEPTH": "4"}),
-        (False, {"GATB_INDEX_CAPACITY": "16", "GATB_COUNT_LPS": "8", "GATB_COUNT_DEPTH": "1"}),
-        (True, {"GATB_COUNT_LPS": "32", "GATB_SCHUNK": "2"}),
-        (True, {"GATB_GROUP_TRACKS": "3", "GATB_INDEX_CAPACITY": "1000", "GATB_COUNT_LPS": "16"}),
+        (False, {"GATB_BIN_SHIFT": "4", "GATB_KEY_GROUP": "1"}),
+        (False, {"GATB_BIN_SHIFT": "20", "GATB_COUNT_THREADS": "64"}),
+        (False, {"GATB_INDEX_CAPACITY": "16", "GATB_SCHUNK": "1"}),
+        (True, {}),
+        (True, {"GATB_SCHUNK": "2", "GATB_BIN_SHIFT": "6"}),
+        (True, {"GATB_GROUP_TRACKS": "3", "GATB_INDEX_CAPACITY": "1000", "GATB_KEY_GROUP": "1"}),
     ]
     for big_list, env in cases:
         annos, nseg, samples = _fallback_problem(rng, oracle, big_list)

@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """Sweep the count kernel's knobs on the bench workload in ONE process (the workload is built once).
 
-    python tools/count_sweep.py "LPS=16,DEPTH=2" "LPS=32,DEPTH=1,SHIFT=9" ...
+    python tools/count_sweep.py "" "SHIFT=9" "THREADS=512,SCHUNK=14" ...
 
 Knobs (environment variables read by the library at context / annotation-set creation):
-LPS -> GATB_COUNT_LPS, DEPTH -> GATB_COUNT_DEPTH, SHIFT -> GATB_BIN_SHIFT, SCHUNK -> GATB_SCHUNK,
+KGRP -> GATB_KEY_GROUP, SHIFT -> GATB_BIN_SHIFT, SCHUNK -> GATB_SCHUNK,
 THREADS -> GATB_COUNT_THREADS, GROUP -> GATB_GROUP_TRACKS.  Prints per configuration the CUDA-event time of
 the count and placement kernels (3 profiled steps after 2 warm-up steps) and the device-resident step time.
 """
@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-ENV = {"LPS": "GATB_COUNT_LPS", "DEPTH": "GATB_COUNT_DEPTH", "SHIFT": "GATB_BIN_SHIFT", "SCHUNK": "GATB_SCHUNK",
+ENV = {"KGRP": "GATB_KEY_GROUP", "SHIFT": "GATB_BIN_SHIFT", "SCHUNK": "GATB_SCHUNK",
        "THREADS": "GATB_COUNT_THREADS", "GROUP": "GATB_GROUP_TRACKS", "BATCH": "BATCH"}
 
 
