@@ -35,15 +35,54 @@ size_t count_smem_bytes(uint32_t schunk, uint32_t ka, uint32_t kgrp, int threads
 template <int COUNTER> struct NeedPrevInterval { static constexpr bool value = COUNTER == GATB_SEGMENT_OVERLAP || COUNTER == GATB_SEGMENT_MIDOVERLAP; };
 template <int COUNTER> struct NeedPrevSegment { static constexpr bool value = COUNTER == GATB_ANNOTATION_OVERLAP || COUNTER == GATB_ANNOTATION_MIDOVERLAP; };
 
+// shared-memory accesses by 32-bit shared address (the base is computed once, not per access)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_shared(uint32_t addr, uint32_t v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// read-only 8-byte global load by 64-bit global address
+__device__ __forceinline__ uint2 ldg_nc_u2(uint64_t addr)
+{
+    uint2 v;
+    asm("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(addr));
+    return v;
+}
+// v << n, 0 for n >= 32 (PTX shl clamps the shift amount, C++ << does not)
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n)
+{
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+}
+
 // one entry of the flat sequence, loaded one round ahead of its use
 struct Flight {
     uint4 o;            // its segment: start, end, (first entry of the run) - (its flat position), end of bin b0's entries
     uint2 w;            // packed entry
-    uint2 iv;           // exact interval (annotation-* counters)
     uint32_t pv;        // end of the previous interval of the track (segment-* counters)
     uint32_t pe;        // end of the previous segment (annotation-* counters)
     uint32_t j;         // entry index
-    bool live;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -57,37 +96,31 @@ struct Flight {
 //                        i.e. when it does not already overlap the previous segment (x >= pe)
 //   overlap-pieces       len(a.intersect(b)): every overlapping pair is one piece (:1469-1549)
 template <int COUNTER>
-__device__ __forceinline__ void count_entry(const CountParams &p, const Flight &f, uint32_t *__restrict__ acc)
+__device__ __forceinline__ void count_entry(const uint2 *__restrict__ civ, const Flight &f, uint32_t acc_addr)
 {
     const uint32_t s = f.o.x, e = f.o.y;
-    const bool first = (f.w.x >> 31) != 0u;
-    const uint32_t t = f.w.y >> 20;
-    uint32_t x, y;
-    if (NeedPrevSegment<COUNTER>::value) { x = f.iv.x; y = f.iv.y; }
-    else {
-        // a continuation entry starts before its bin, hence before every segment that meets it in bin b0
-        x = first ? (f.w.x & 0x7fffffffu) : 0u;
-        const uint32_t l = f.w.y & ENTRY_LEN_MASK;
-        y = first ? x + l : f.w.x;
-        if (first && l == ENTRY_LEN_MASK) y = p.civ[f.j].y;          // 2^20 - 1 bases or longer: rare
-    }
-    const bool here = (first && x >= s) ? (x < e) : (f.j < f.o.w && y > s);
-    if (!here) return;
-    uint32_t *cell = acc + t;
+    const bool first = (int32_t)f.w.x < 0;
+    const uint32_t x = f.w.x & 0x7fffffffu, l = f.w.y & ENTRY_LEN_MASK;
+    uint32_t y = x + l;
+    if (l == ENTRY_LEN_MASK) y = civ[f.j].y;                // 2^20 - 1 bases or longer: rare
+    const bool overlap = (x < e) & (y > s);
+    const bool mine = (x >= s) ? first : (f.j < f.o.w);     // the bin of the intersection's first base
+    if (!(overlap & mine)) return;
+    const uint32_t cell = acc_addr + ((f.w.y >> 20) << 2);
     if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
-        atomicAdd(cell, min(e, y) - max(s, x));
+        red_add_shared(cell, min(e, y) - max(s, x));
     } else if (COUNTER == GATB_SEGMENT_OVERLAP) {
-        if (f.pv <= s) atomicAdd(cell, 1u);
+        if (f.pv <= s) red_add_shared(cell, 1u);
     } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
         const uint32_t mid = s + ((e - s) >> 1);
-        if (f.pv <= s && x <= mid && mid < y) atomicAdd(cell, 1u);
+        if (f.pv <= s && x <= mid && mid < y) red_add_shared(cell, 1u);
     } else if (COUNTER == GATB_OVERLAP_PIECES) {
-        atomicAdd(cell, 1u);
+        red_add_shared(cell, 1u);
     } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
-        if (x >= f.pe) atomicAdd(cell, 1u);
+        if (x >= f.pe) red_add_shared(cell, 1u);
     } else {
         const uint32_t m = x + ((y - x) >> 1);
-        if (x >= f.pe && s <= m && m < e) atomicAdd(cell, 1u);
+        if (x >= f.pe && s <= m && m < e) red_add_shared(cell, 1u);
     }
 }
 
@@ -97,10 +130,11 @@ struct Indexed {
     uint32_t s, e, pe, r0, rf, r1;
 };
 
-// The 32 runs [r0, r1) of an item as one flat sequence of entries.
+// The 32 runs [r0, r1) of an item as one flat sequence of entries.  stg / stg_pe: shared addresses of the
+// warp's staging, acc_addr: of the sample's accumulators.
 template <int COUNTER>
-__device__ __forceinline__ void run_item(const CountParams &p, const Indexed &it, int lane, uint4 *__restrict__ stg,
-                                         uint32_t *__restrict__ stg_pe, uint32_t *__restrict__ acc)
+__device__ __forceinline__ void run_item(const CountParams &p, const Indexed &it, uint32_t lane, uint32_t stg,
+                                         uint32_t stg_pe, uint32_t acc_addr)
 {
     const uint32_t len = it.r1 - it.r0;
     const uint32_t incl = warp_incl_scan_add_u32(len);
@@ -111,26 +145,33 @@ __device__ __forceinline__ void run_item(const CountParams &p, const Indexed &it
     const uint32_t rank = __popc(have & ((1u << lane) - 1u));
     __syncwarp();                                   // the previous item's readers are done with the staging
     if (len) {
-        stg[rank] = make_uint4(it.s, it.e, it.r0 - excl, it.rf);
-        if (NeedPrevSegment<COUNTER>::value) stg_pe[rank] = it.pe;
+        sts128(stg + rank * 16u, make_uint4(it.s, it.e, it.r0 - excl, it.rf));
+        if (NeedPrevSegment<COUNTER>::value) sts32(stg_pe + rank * 4u, it.pe);
     }
     __syncwarp();
-    const uint32_t le_mask = 0xffffffffu >> (31 - lane);
-    uint32_t started = 0;                           // non-empty runs that begin before the round
+    uint64_t cent = (uint64_t)__cvta_generic_to_global(p.cent);
+    const uint32_t *__restrict__ cprev = p.cprev;
+    uint32_t le_mask = 0xffffffffu >> (31u - lane);
+    asm volatile("" : "+l"(cent), "+r"(le_mask));   // registers, not re-derived every round
+    const uint32_t first_pos = len ? excl : 0xffffffffu;    // flat position of the run's first entry
+    uint32_t started = 0xffffffffu;                 // (non-empty runs that begin before the round) - 1
 
     // flat positions base .. base+31: who owns them, and the entry loads
     auto fetch = [&](uint32_t base, Flight &f) {
-        const uint32_t d = excl - base;
-        const uint32_t mask = __reduce_or_sync(GATB_FULL, (len != 0u && d < 32u) ? (1u << d) : 0u);
-        const uint32_t owner = started + __popc(mask & le_mask) - 1u;
+        const uint32_t mask = __reduce_or_sync(GATB_FULL, shl_clamp(1u, first_pos - base));
+        const uint32_t owner = started + __popc(mask & le_mask);
         started += __popc(mask);
-        f.live = base + (uint32_t)lane < total;
-        if (f.live) {
-            f.o = stg[owner];
-            f.j = base + (uint32_t)lane + f.o.z;
-            f.w = p.cent[f.j];
-            if (NeedPrevInterval<COUNTER>::value) f.pv = p.cprev[f.j];
-            if (NeedPrevSegment<COUNTER>::value) { f.iv = p.civ[f.j]; f.pe = stg_pe[owner]; }
+        const uint32_t pos = base + lane;
+        if (pos < total) {
+            f.o = lds128(stg + owner * 16u);
+            f.j = pos + f.o.z;
+            f.w = ldg_nc_u2(cent + (uint64_t)f.j * 8u);
+            if (NeedPrevInterval<COUNTER>::value) f.pv = cprev[f.j];
+            if (NeedPrevSegment<COUNTER>::value) f.pe = lds32(stg_pe + owner * 4u);
+        } else {                                    // past the end (last round): an entry that overlaps nothing
+            f.o = make_uint4(0u, 0u, 0u, 0u);
+            f.w = make_uint2(0u, 0u);
+            f.j = 0u; f.pv = 0u; f.pe = 0u;
         }
     };
     Flight fa, fb;
@@ -138,11 +179,11 @@ __device__ __forceinline__ void run_item(const CountParams &p, const Indexed &it
     for (uint32_t base = 0;;) {
         base += 32;
         if (base < total) fetch(base, fb);
-        if (fa.live) count_entry<COUNTER>(p, fa, acc);
+        count_entry<COUNTER>(p.civ, fa, acc_addr);
         if (base >= total) break;
         base += 32;
         if (base < total) fetch(base, fa);
-        if (fb.live) count_entry<COUNTER>(p, fb, acc);
+        count_entry<COUNTER>(p.civ, fb, acc_addr);
         if (base >= total) break;
     }
 }
@@ -151,7 +192,9 @@ template <int COUNTER, bool DENSITY>
 __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t lane = threadIdx.x & 31u;
+    asm volatile("" : "+r"(lane));                  // keep it in a register (the hot loop would re-read %tid)
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t g = blockIdx.x;
     const uint32_t a0 = g * p.ka;
     const uint32_t ka = min(p.ka, p.n_annot - a0);
@@ -159,8 +202,8 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
     const uint32_t s_end = min(s_begin + p.schunk, p.n_samples);
     const uint32_t ns = s_end - s_begin, ncells = ns * ka;
     // layout: [staging][density only: (sum, compensation) doubles per cell][u32 per cell][item tables]
-    uint4 *stg = reinterpret_cast<uint4 *>(smem) + warp * 32;
-    uint32_t *stg_pe = reinterpret_cast<uint32_t *>(smem + (size_t)nwarps * 32u * 16u) + warp * 32;
+    const uint32_t stg = smem_addr(smem) + (uint32_t)warp * 512u;
+    const uint32_t stg_pe = smem_addr(smem) + (uint32_t)nwarps * 512u + (uint32_t)warp * 128u;
     uint8_t *base = smem + count_smem_fixed((uint32_t)nwarps);
     double *acc_d = reinterpret_cast<double *>(base);
     uint32_t *acc_u = reinterpret_cast<uint32_t *>(base + (DENSITY ? (size_t)p.schunk * p.ka * 16u : 0u));
@@ -185,7 +228,7 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
             const bool dead = kb.nbins == 0 || (DENSITY && p.key_ws_nseg[k] == 0);
             uint32_t run = 0;
             for (uint32_t q0 = 0; q0 < ns; q0 += 32) {
-                const uint32_t slot = q0 + (uint32_t)lane;
+                const uint32_t slot = q0 + lane;
                 uint32_t n = 0;
                 if (slot < ns && !dead) {
                     const uint64_t sl = s_begin + slot;
@@ -247,14 +290,14 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
                         if (w >= n_items) more = false;
                         else {
                             while (true) {                  // items come in increasing order: scan forward
-                                const uint32_t idx = cursor + (uint32_t)lane;
+                                const uint32_t idx = cursor + lane;
                                 const uint32_t m = __ballot_sync(GATB_FULL, idx >= ns || pre_k[idx + 1u] > w);
                                 if (m) { cursor += (uint32_t)__ffs(m) - 1u; break; }
                                 cursor += 32u;
                             }
                             a_slot = cursor;
                             a_n = nn_k[cursor];
-                            a_i = (w - pre_k[cursor]) * 32u + (uint32_t)lane;
+                            a_i = (w - pre_k[cursor]) * 32u + lane;
                             const uint64_t *segs = placed_key + (uint64_t)cursor * p.sample_stride;
                             if (a_i < a_n) a_sg = segs[a_i];
                             if (NeedPrevSegment<COUNTER>::value)
@@ -262,7 +305,7 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
                         }
                     }
                     // run B (its offsets were requested one turn ago), then B <- B'
-                    if (b.slot != NO_ITEM) run_item<COUNTER>(p, b, lane, stg, stg_pe, acc_u + b.slot * ka);
+                    if (b.slot != NO_ITEM) run_item<COUNTER>(p, b, lane, stg, stg_pe, smem_addr(acc_u) + b.slot * ka * 4u);
                     b = nb;
                 }
             }
@@ -370,8 +413,7 @@ __global__ void __launch_bounds__(256) bins_pass_kernel(BuildBinsParams p)
         else {
             const uint64_t pos = atomicAdd(cur + b, 1u);
             if (pos < p.capacity) {
-                p.cent[pos] = (b == b0) ? make_uint2(0x80000000u | x, (t << 20) | min(y - x, ENTRY_LEN_MASK))
-                                        : make_uint2(y, t << 20);
+                p.cent[pos] = make_uint2((b == b0 ? 0x80000000u : 0u) | x, (t << 20) | min(y - x, ENTRY_LEN_MASK));
                 p.civ[pos] = make_uint2(x, y);
                 p.cprev[pos] = py;
             }

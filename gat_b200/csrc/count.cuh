@@ -27,12 +27,10 @@ constexpr uint32_t ENTRY_LEN_MASK = 0xfffffu;
 //   KeyBins keybins[n_groups][n_keys]    where the key's bins start in boff[], how many, log2(bin width)
 //   uint32  boff[]                       per (group, key): nbins+1 entry offsets (absolute, into the arrays below)
 //   uint2   cent[n_entries]              the entry the counting kernel streams, 8 bytes:
-//                                          first entry of its interval:  .x = 1<<31 | start,  .y = slot<<20 | min(length, 2^20-1)
-//                                          continuation (later bins):    .x = end,            .y = slot<<20
-//                                        (slot = track within the group, < 4096; a continuation starts before its
-//                                        bin, which is all the counters need to know of its start; a length field
-//                                        of 2^20-1 sends the kernel to civ[] for the end)
-//   uint2   civ[n_entries]               the exact interval (start, end): annotation-* counters, long intervals
+//                                          .x = start | 1<<31 on the interval's first bin,  .y = slot<<20 | min(length, 2^20-1)
+//                                        (slot = track within the group, < 4096; a length field of 2^20-1
+//                                        sends the kernel to civ[] for the end)
+//   uint2   civ[n_entries]               the exact interval (start, end), read for intervals of 2^20-1 bases or more
 //   uint32  cprev[n_entries]             end of the previous interval of the same track on this key (0: none):
 //                                        "is this the first interval of its track overlapping [s,e)?" = cprev <= s
 struct KeyBins {
