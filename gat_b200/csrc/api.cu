@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -35,6 +36,8 @@ struct gatb_ctx {
     int count_threads = 1024;
     uint32_t schunk_max = 0;            // samples per count CTA; 0: whatever shared memory allows
     uint32_t kgrp_max = 0;              // keys per item table; 0: whatever fits
+    struct BatchScratch *scratch = nullptr;
+    bool trace = false;                 // GATB_TRACE=1: host-side phase times of gatb_run on stderr
     // optional per-kernel timing (bench.py roofline): CUDA events around every launch
     bool profiling = false;
     struct Span { int cls; cudaEvent_t a, b; };
@@ -108,6 +111,18 @@ struct DevBuf {
     }
 };
 
+// Batch buffers of the sampling loop, owned by the context and only ever grown: samplers created and
+// destroyed per call (one per track in gat.run) re-use them instead of allocating hundreds of MB each.
+// Calls on a context are serialised by the caller and every entry point that uses the buffers returns
+// with the stream drained, so sharing them between samplers is safe.
+struct BatchScratch {
+    DevBuf<uint64_t> unit_buf, placed;
+    DevBuf<uint32_t> unit_n, placed_n;
+    DevBuf<uint8_t> status;
+    DevBuf<uint32_t> out_tmp;
+    DevBuf<double> out_tmp_f;
+};
+
 static uint32_t env_u32(const char *name, uint32_t dflt)
 {
     const char *v = getenv(name);
@@ -154,6 +169,8 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     ctx->count_threads = (int)std::min(1024u, std::max(32u, env_u32("GATB_COUNT_THREADS", 1024) / 32 * 32));
     ctx->schunk_max = env_u32("GATB_SCHUNK", 0);
     ctx->kgrp_max = env_u32("GATB_KEY_GROUP", 0);
+    ctx->trace = env_u32("GATB_TRACE", 0) != 0;
+    ctx->scratch = new BatchScratch();
     ctx->batch = env_u32("GATB_BATCH", 0);
     *out = ctx;
     return GATB_OK;
@@ -163,6 +180,8 @@ extern "C" void gatb_destroy(gatb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    delete ctx->scratch;
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
     if (ctx->err_slots) cudaFreeHost(ctx->err_slots);
@@ -259,7 +278,8 @@ struct gatb_annotations {
     // kept until the build has been checked (annotations_finish): the raw lists on the device, so that an
     // index that outgrew the estimated capacity can be rebuilt at its exact size without the caller's arrays
     DevBuf<uint64_t> d_offs;
-    DevBuf<uint32_t> d_start, d_end, d_err;
+    DevBuf<uint32_t> d_start, d_end, d_err, d_jmax;
+    uint32_t jmax_all = 0;
     DevBuf<unsigned long long> d_total;
     DevBuf<uint8_t> scan_tmp;
     // asynchronous create: `ready` is recorded on the upload stream after the index build; until the
@@ -289,7 +309,7 @@ static cudaError_t annotations_build(gatb_annotations *a)
     BuildBinsParams bp;
     memset(&bp, 0, sizeof(bp));
     bp.offs = a->d_offs.p; bp.start = a->d_start.p; bp.end = a->d_end.p; bp.n_intervals = a->n_intervals;
-    bp.keybins = a->keybins.p; bp.boff = a->boff.p; bp.n_boff = a->n_boff;
+    bp.keybins = a->keybins.p; bp.key_jmax = a->d_jmax.p; bp.jmax_all = a->jmax_all; bp.boff = a->boff.p; bp.n_boff = a->n_boff;
     bp.cent = a->cent.p; bp.civ = a->civ.p; bp.cprev = a->cprev.p; bp.capacity = a->capacity;
     bp.n_annot = a->n_annot; bp.n_keys = a->n_keys; bp.n_groups = a->n_groups; bp.ka = a->ka;
     bp.error = a->d_err.p; bp.total = a->d_total.p;
@@ -333,6 +353,7 @@ static int annotations_finish(gatb_annotations *a)
     }
     // the raw lists and the scan scratch are no longer needed (freed in upload-stream order)
     a->d_offs.release(); a->d_start.release(); a->d_end.release(); a->d_err.release(); a->d_total.release();
+    a->d_jmax.release();
     a->scan_tmp.release();
     tl_stream = saved;
     if (e != cudaSuccess) return a->status = fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e));
@@ -386,6 +407,11 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     a->h_keybins.resize((size_t)G * K);
     uint64_t n_boff = 0;
     double est = 0;
+    std::vector<uint32_t> jmax(K, 0);
+    for (uint32_t t = 0; t < A; t++)
+        for (uint32_t k = 0; k < K; k++)
+            jmax[k] = std::max(jmax[k], (uint32_t)(offs[(uint64_t)t * K + k + 1] - offs[(uint64_t)t * K + k]));
+    for (uint32_t k = 0; k < K; k++) a->jmax_all = std::max(a->jmax_all, jmax[k]);
     for (uint32_t g = 0; g < G; g++)
         for (uint32_t k = 0; k < K; k++) {
             uint64_t n = 0;
@@ -418,6 +444,7 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     // caller's arrays, which must stay valid until gatb_annotations_wait() or the first use returns
     cudaError_t e = a->keybins.upload(a->h_keybins.data(), a->h_keybins.size(), st);
     if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, st); a->has_nseg = true; }
+    if (e == cudaSuccess) e = a->d_jmax.upload(jmax.data(), K, st);
     if (e == cudaSuccess) e = a->boff.alloc(n_boff + 1);
     if (e == cudaSuccess) e = a->civ.alloc(a->capacity);
     if (e == cudaSuccess) e = a->cent.alloc(a->capacity);
@@ -461,10 +488,18 @@ extern "C" int gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, c
 extern "C" void gatb_annotations_destroy(gatb_annotations *a)
 {
     if (!a) return;
-    cudaSetDevice(a->ctx->device);
+    gatb_ctx *ctx = a->ctx;
+    cudaSetDevice(ctx->device);
     if (a->pending) annotations_finish(a);
-    // free in the order of the compute stream, where the index was last read
-    a->keybins.st = a->boff.st = a->civ.st = a->cent.st = a->cprev.st = a->key_ws_nseg.st = a->ctx->stream;
+    // The index was allocated on the upload stream and last read on the compute stream: free it on the
+    // upload stream once the compute stream has got this far, so that the next set's allocations (same
+    // stream) re-use the memory without the pool having to reconcile two streams.
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+        cudaEventRecord(ev, ctx->stream);
+        cudaStreamWaitEvent(ctx->upload_stream, ev, 0);
+        cudaEventDestroy(ev);
+    } else cudaStreamSynchronize(ctx->stream);
     delete a;
 }
 
@@ -589,14 +624,7 @@ struct gatb_sampler {
     DevBuf<uint32_t> ws_start, ws_end, ws_cuminc, len_tab;
     DevBuf<uint32_t> contig_unit_off, contig_units;
     DevBuf<uint64_t> contig_base;
-    // batch buffers
-    uint32_t batch_alloc = 0;
-    DevBuf<uint64_t> unit_buf, placed;
-    DevBuf<uint32_t> unit_n, placed_n;
-    DevBuf<uint8_t> status;
     DevBuf<unsigned long long> tally;     // [3]: placed segments, round-cap units, overflow units
-    DevBuf<uint32_t> out_tmp;
-    DevBuf<double> out_tmp_f;
 };
 
 extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *unit_contig, int n_contigs,
@@ -774,16 +802,14 @@ static uint32_t pick_batch(const gatb_sampler *s, uint64_t n_samples)
 static int ensure_batch(gatb_sampler *s, uint32_t B)
 {
     gatb_ctx *ctx = s->ctx;
-    if (B <= s->batch_alloc) return GATB_OK;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CU(ctx, s->placed.alloc((uint64_t)B * s->placed_stride));
-    CU(ctx, s->placed_n.alloc((uint64_t)B * s->n_contigs));
+    BatchScratch *sc = ctx->scratch;
+    CU(ctx, sc->placed.ensure((uint64_t)B * s->placed_stride));
+    CU(ctx, sc->placed_n.ensure((uint64_t)B * s->n_contigs));
     if (s->has_iso) {
-        CU(ctx, s->unit_buf.alloc((uint64_t)B * s->unit_stride));
-        CU(ctx, s->unit_n.alloc((uint64_t)B * s->n_units));
+        CU(ctx, sc->unit_buf.ensure((uint64_t)B * s->unit_stride));
+        CU(ctx, sc->unit_n.ensure((uint64_t)B * s->n_units));
     }
-    CU(ctx, s->status.alloc((uint64_t)B * s->n_units));
-    s->batch_alloc = B;
+    CU(ctx, sc->status.ensure((uint64_t)B * s->n_units));
     return GATB_OK;
 }
 
@@ -819,13 +845,13 @@ static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t 
     p.units = s->units.p; p.order = s->order.p;
     p.ws_start = s->ws_start.p; p.ws_end = s->ws_end.p; p.ws_cuminc = s->ws_cuminc.p; p.len_tab = s->len_tab.p;
     if (s->has_iso) {
-        p.buf = s->unit_buf.p; p.sample_stride = s->unit_stride;
-        p.out_n = s->unit_n.p; p.out_n_stride = s->n_units; p.out_by_contig = 0;
+        p.buf = s->ctx->scratch->unit_buf.p; p.sample_stride = s->unit_stride;
+        p.out_n = s->ctx->scratch->unit_n.p; p.out_n_stride = s->n_units; p.out_by_contig = 0;
     } else {
-        p.buf = s->placed.p; p.sample_stride = s->placed_stride;
-        p.out_n = s->placed_n.p; p.out_n_stride = s->n_contigs; p.out_by_contig = 1;
+        p.buf = s->ctx->scratch->placed.p; p.sample_stride = s->placed_stride;
+        p.out_n = s->ctx->scratch->placed_n.p; p.out_n_stride = s->n_contigs; p.out_by_contig = 1;
     }
-    p.status = s->status.p; p.n_units = s->n_units; p.n_samples = B; p.sample_begin = sample_begin;
+    p.status = s->ctx->scratch->status.p; p.n_units = s->n_units; p.n_samples = B; p.sample_begin = sample_begin;
     p.seed = seed; p.track = track; p.sampler_kind = s->kind;
     { ProfScope ps(ctx, PROF_PLACE); launch_place(st, p); }
     CU(ctx, cudaGetLastError());
@@ -833,16 +859,16 @@ static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t 
         MergeParams m;
         memset(&m, 0, sizeof(m));
         m.units = s->units.p; m.contig_unit_off = s->contig_unit_off.p; m.contig_units = s->contig_units.p;
-        m.contig_base = s->contig_base.p; m.unit_buf = s->unit_buf.p; m.unit_stride = s->unit_stride;
-        m.unit_n = s->unit_n.p; m.placed = s->placed.p; m.placed_stride = s->placed_stride;
-        m.placed_n = s->placed_n.p; m.n_units = s->n_units; m.n_contigs = s->n_contigs; m.n_samples = B;
+        m.contig_base = s->contig_base.p; m.unit_buf = s->ctx->scratch->unit_buf.p; m.unit_stride = s->unit_stride;
+        m.unit_n = s->ctx->scratch->unit_n.p; m.placed = s->ctx->scratch->placed.p; m.placed_stride = s->placed_stride;
+        m.placed_n = s->ctx->scratch->placed_n.p; m.n_units = s->n_units; m.n_contigs = s->n_contigs; m.n_samples = B;
         { ProfScope ps(ctx, PROF_MERGE); launch_contig_merge(st, m); }
         CU(ctx, cudaGetLastError());
     }
     {
         ProfScope ps(ctx, PROF_OTHER);
         tally_kernel<<<std::min<uint32_t>(1024, (uint32_t)(((uint64_t)B * s->n_units + 255) / 256)), 256, 0, st>>>(
-            s->placed_n.p, (uint64_t)B * s->n_contigs, s->status.p, (uint64_t)B * s->n_units, s->tally.p);
+            s->ctx->scratch->placed_n.p, (uint64_t)B * s->n_contigs, s->ctx->scratch->status.p, (uint64_t)B * s->n_units, s->tally.p);
     }
     CU(ctx, cudaGetLastError());
     return GATB_OK;
@@ -869,10 +895,10 @@ extern "C" int gatb_sampler_place(gatb_sampler *s, uint64_t seed, uint32_t track
         const uint32_t b = (uint32_t)std::min<uint64_t>(B, n_samples - done);
         rc = place_batch(s, seed, track, sample_begin + done, b);
         if (rc) return rc;
-        CU(ctx, cudaMemcpyAsync(h.data(), s->placed.p, (uint64_t)b * s->placed_stride * 8, cudaMemcpyDeviceToHost, st));
-        CU(ctx, cudaMemcpyAsync(counts + done * s->n_contigs, s->placed_n.p, (uint64_t)b * s->n_contigs * 4, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(h.data(), s->ctx->scratch->placed.p, (uint64_t)b * s->placed_stride * 8, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(counts + done * s->n_contigs, s->ctx->scratch->placed_n.p, (uint64_t)b * s->n_contigs * 4, cudaMemcpyDeviceToHost, st));
         if (unit_status)
-            CU(ctx, cudaMemcpyAsync(unit_status + done * s->n_units, s->status.p, (uint64_t)b * s->n_units, cudaMemcpyDeviceToHost, st));
+            CU(ctx, cudaMemcpyAsync(unit_status + done * s->n_units, s->ctx->scratch->status.p, (uint64_t)b * s->n_units, cudaMemcpyDeviceToHost, st));
         CU(ctx, cudaStreamSynchronize(st));
         for (uint64_t sl = 0; sl < b; sl++)
             for (uint32_t c = 0; c < s->n_contigs; c++) {
@@ -913,11 +939,15 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
     cudaStream_t st = ctx->stream;
     const uint32_t A = annos->n_annot;
     const uint32_t B = pick_batch(s, n_samples);
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_alloc = 0, t_placeq = 0, t_annos = 0, t_countq = 0;
     int rc = ensure_batch(s, B);
     if (rc) return rc;
+    t_alloc = since();
     if (!out_is_device) {
-        if (any_int) CU(ctx, s->out_tmp.ensure((uint64_t)B * A));
-        if (any_density) CU(ctx, s->out_tmp_f.ensure((uint64_t)B * A));
+        if (any_int) CU(ctx, s->ctx->scratch->out_tmp.ensure((uint64_t)B * A));
+        if (any_density) CU(ctx, s->ctx->scratch->out_tmp_f.ensure((uint64_t)B * A));
     }
     CU(ctx, cudaMemsetAsync(s->tally.p, 0, 3 * sizeof(unsigned long long), st));
 
@@ -925,18 +955,19 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
         const uint32_t b = (uint32_t)std::min<uint64_t>(B, n_samples - done);
         rc = place_batch(s, seed, track, sample_begin + done, b);
         if (rc) return rc;
+        if (done == 0) t_placeq = since();
         CountParams p;
         memset(&p, 0, sizeof(p));
-        p.placed = s->placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
-        p.placed_n = s->placed_n.p; p.key_present = nullptr;
+        p.placed = s->ctx->scratch->placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
+        p.placed_n = s->ctx->scratch->placed_n.p; p.key_present = nullptr;
         for (int c = 0; c < n_counters; c++) {
             const bool dens = counters[c] == GATB_NUCLEOTIDE_DENSITY;
             rc = count_params_annos(annos, b, dens, p);
             if (rc) return rc;
             uint32_t *dst_u = out_counts ? out_counts + ((uint64_t)c * n_samples + done) * A : nullptr;
             double *dst_f = out_density ? out_density + done * A : nullptr;
-            p.out_u32 = out_is_device ? dst_u : s->out_tmp.p;
-            p.out_f64 = out_is_device ? dst_f : s->out_tmp_f.p;
+            p.out_u32 = out_is_device ? dst_u : s->ctx->scratch->out_tmp.p;
+            p.out_f64 = out_is_device ? dst_f : s->ctx->scratch->out_tmp_f.p;
             // annotations still uploading / building (gatb_annotations_create_async): the placement queued
             // above did not need them, the count does.  The host waits here (the GPU keeps placing) because
             // the build's outcome decides what may be launched: invalid lists or an index to rebuild.
@@ -944,17 +975,22 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
                 rc = annotations_finish(const_cast<gatb_annotations *>(annos));
                 tl_stream = ctx->stream;
                 if (rc) { cudaStreamSynchronize(st); return rc; }
+                t_annos = since();
             }
             { ProfScope ps(ctx, PROF_COUNT); CU(ctx, launch_count(st, counters[c], p, ctx->count_threads)); }
             if (!out_is_device) {
-                if (dens) CU(ctx, cudaMemcpyAsync(dst_f, s->out_tmp_f.p, (uint64_t)b * A * sizeof(double), cudaMemcpyDeviceToHost, st));
-                else CU(ctx, cudaMemcpyAsync(dst_u, s->out_tmp.p, (uint64_t)b * A * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                if (dens) CU(ctx, cudaMemcpyAsync(dst_f, s->ctx->scratch->out_tmp_f.p, (uint64_t)b * A * sizeof(double), cudaMemcpyDeviceToHost, st));
+                else CU(ctx, cudaMemcpyAsync(dst_u, s->ctx->scratch->out_tmp.p, (uint64_t)b * A * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             }
         }
     }
+    t_countq = since();
     unsigned long long tally[3];
     CU(ctx, cudaMemcpyAsync(tally, s->tally.p, sizeof(tally), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
+    if (ctx->trace)
+        fprintf(stderr, "gatb_run: batch buffers %.2f ms, placement queued %.2f, annotations ready %.2f, all queued %.2f, done %.2f\n",
+                t_alloc, t_placeq, t_annos, t_countq, since());
     if (info) { info[0] = tally[0]; info[1] = tally[1]; info[2] = tally[2]; }
     rc = annotations_finish(const_cast<gatb_annotations *>(annos));      // invalid lists: the counts mean nothing
     if (rc) return rc;

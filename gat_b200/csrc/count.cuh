@@ -74,6 +74,8 @@ struct BuildBinsParams {
     const uint32_t *start, *end;
     uint64_t n_intervals;
     const KeyBins *keybins;         // [n_groups][n_keys]
+    const uint32_t *key_jmax;       // [n_keys] longest list (over all tracks) on the key
+    uint32_t jmax_all;              // largest of them
     uint32_t *boff;                 // [n_boff], zeroed by the caller
     uint64_t n_boff;
     uint2 *cent;
