@@ -15,7 +15,7 @@ exchange step) inside the timed region.
 
 value   whole-job samples/s, inputs resident in HBM, counts left in HBM (CUDA events, max over ranks)
 e2e     same metric through the C ABI with HOST buffers: every step uploads segments, workspace and
-        annotations (gatb_sampler_create / gatb_annotations_create_async: the annotation upload and tile
+        annotations (gatb_sampler_create / gatb_annotations_create_async: the annotation upload and index
         build overlap the placement kernel), runs, and reads the count matrix back to the host
 roofline  dominant kernel (counting): SURVEY 8d algorithmic bytes per launch / CUDA-event kernel time
 cpu_baseline  the reference itself (oracle/_ref) on the host cores, bounded sample, rank 0, N=1
@@ -86,9 +86,9 @@ def config_of(args, wl, world):
             "global_samples_per_step": args.samples_per_step * world,
             "parallelism": "samples sharded over %i GPU(s), inputs replicated, one NCCL all-gather of the "
                            "count slab per step" % world if world > 1 else "1 GPU",
-            "l2": "inputs larger than L2: annotation filters (bitmap + bin index + intervals) ~%.0f MB, re-read "
-                  "once per 256-sample chunk, + %.0f MB of placed segments per batch"
-                  % (wl["n_a_total"] * 17 / 1e6 + 48, args.samples_per_step * wl["n_segments"] * 8 / 1e6),
+            "l2": "inputs larger than L2: annotation grid index (offsets + 8-byte entries, ~2.3 entries per "
+                  "interval) ~%.0f MB + %.0f MB of placed segments per batch; sample indices advance every step"
+                  % (wl["n_a_total"] * 2.33 * 8 / 1e6 + 12, args.samples_per_step * wl["n_segments"] * 8 / 1e6),
             "data_seed": 20260101}
 
 
@@ -318,10 +318,11 @@ def run_ours(args):
                 "traffic": (traffic["dram_bytes_per_sample"] * B) if traffic and "dram_bytes_per_sample" in traffic else None,
                 "traffic_source": traffic.get("capture") if traffic else None,
                 "note": "algorithmic bytes = what the reference's two-pointer merge streams per (sample, annotation, "
-                        "contig) cell (SURVEY 8d); the kernel answers the same cells through a shared-memory bitmap "
-                        "+ interval filter per group of 8 tracks and touches only `traffic` DRAM bytes, so frac > 1 "
-                        "is expected: its real bounds are issue slots (72 % busy) and shared-memory wavefronts "
-                        "(62 % of peak) (profiles/r01_count_kernel_v7.txt)",
+                        "contig) cell (SURVEY 8d); the kernel answers the same cells from one grid index over all "
+                        "tracks (a segment's candidates = one contiguous run of 8-byte entries) and touches only "
+                        "`traffic` DRAM bytes, so frac > 1 is expected: its real bound is the issue rate (1.76 G warp "
+                        "instructions per launch, issue slots 70 % busy; L2 serves 10.6 GB per launch at 87 % hits) "
+                        "(profiles/r01_count_kernel_v10.txt)",
                 "algorithmic_bytes_per_launch": count_bytes, "kernel_ms": count_ms,
                 "kernel_share_of_step": prof["count"][0] / max(sum(v[0] for v in prof.values()), 1e-9),
                 "other_kernels": {"place_kernel_ms": place_ms, "contig_merge_kernel_ms": merge_ms,
@@ -348,8 +349,8 @@ def run_ours(args):
         info_np = np.zeros(3, dtype=np.uint64)
 
         def e2e_step(i):
-            # sampler first (small copies), then the annotations asynchronously: their upload and tile
-            # build overlap the placement kernel; gatb_run waits for them on the device before counting
+            # sampler first (small copies), then the annotations asynchronously: their upload and index
+            # build overlap the placement kernel; gatb_run waits for them only before it launches the count
             s2 = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(ps, pw))
             a2 = device.Annotations(ctx, None, key_ws_nseg=wl["nseg"], csr=(A, C) + pa, lazy=True)
             begin = (i * world + rank) * B

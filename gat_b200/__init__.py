@@ -149,7 +149,7 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
             timing.append((name, time.perf_counter()))
 
     # observed counts (gat/__init__.py:932-940)
-    annos_cache = {}      # key tuple -> device.Annotations: one upload + tile build per key set for the whole run
+    annos_cache = {}      # key tuple -> device.Annotations: one upload + index build per key set for the whole run
     observed_counts = [Engine.computeCounts(counter=c, aggregator=sum, segments=segments,
                                             annotations=annotations, workspace=workspace,
                                             workspace_generator=workspace_generator, annos_cache=annos_cache)

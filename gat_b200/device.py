@@ -156,7 +156,7 @@ class Annotations(object):
     def __init__(self, ctx, lists, key_ws_nseg=None, csr=None, lazy=False):
         """lists[a][k], or csr=(n_annot, n_keys, offs, start, end) already flattened annotation-major.
 
-        lazy: gatb_annotations_create_async -- upload and tile build run on the library's upload stream
+        lazy: gatb_annotations_create_async -- upload and index build run on the library's upload stream
         while the caller goes on (e.g. to the placement kernel); the first run / count_lists waits on the
         device and reports invalid lists.  The arrays are kept alive here until then."""
         self.ctx = ctx

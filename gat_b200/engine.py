@@ -451,7 +451,7 @@ class UnconditionalWorkspace(object):
 def deviceAnnotations(annotations, keys, nseg=None, cache=None, lazy=False):
     """the annotation tracks on `keys` as a device.Annotations set; `cache` (dict keyed by the key tuple) lets
     the observed counts of every counter, the sampling and the overlap columns of one run share ONE upload
-    and tile build.  -> (set, owned): the caller closes the set iff owned."""
+    and index build.  -> (set, owned): the caller closes the set iff owned."""
     k = tuple(keys)
     if cache is not None and k in cache:
         return cache[k], False

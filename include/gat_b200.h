@@ -88,9 +88,9 @@ int         gatb_profile_read(gatb_ctx *ctx, double *ms /*[4]*/, uint64_t *launc
 int  gatb_annotations_create(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
                              const uint32_t *start, const uint32_t *end, const uint32_t *key_ws_nseg,
                              gatb_annotations **out);
-/* The same without waiting: the copies and the tile build are queued on a separate upload stream and
- * the call returns; the first gatb_run / gatb_count_lists using the set waits for them ON THE DEVICE
- * (gatb_run only before its first counting kernel, so the upload overlaps the placement kernel) and
+/* The same without waiting: the copies and the index build are queued on a separate upload stream and
+ * the call returns; the first gatb_run / gatb_count_lists using the set waits for them (gatb_run
+ * only after it has queued its first placement kernel, so upload and build overlap the placement) and
  * reports a failed validation (GATB_ERR_INVALID / GATB_ERR_RANGE) when it returns.  offs / start / end
  * must stay valid and unchanged until that call or gatb_annotations_wait() has returned; pinned host
  * memory makes the copies truly asynchronous.  gatb_annotations_wait blocks until the set is built and
