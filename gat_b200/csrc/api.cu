@@ -344,9 +344,9 @@ static int annotations_finish(gatb_annotations *a)
             return a->status = fail(ctx, GATB_ERR_INVALID, "annotations: index needs 2^32 or more entries");
         }
         a->capacity = need;
-        e = a->civ.alloc(need);
-        if (e == cudaSuccess) e = a->cent.alloc(need);
-        if (e == cudaSuccess) e = a->cprev.alloc(need);
+        e = a->civ.alloc(need + 1);
+        if (e == cudaSuccess) e = a->cent.alloc(need + 1);
+        if (e == cudaSuccess) e = a->cprev.alloc(need + 1);
         if (e == cudaSuccess) e = annotations_build(a);
         if (e == cudaSuccess) e = cudaEventSynchronize(a->ready);
         h_err = slot[0];
@@ -446,9 +446,9 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, st); a->has_nseg = true; }
     if (e == cudaSuccess) e = a->d_jmax.upload(jmax.data(), K, st);
     if (e == cudaSuccess) e = a->boff.alloc(n_boff + 1);
-    if (e == cudaSuccess) e = a->civ.alloc(a->capacity);
-    if (e == cudaSuccess) e = a->cent.alloc(a->capacity);
-    if (e == cudaSuccess) e = a->cprev.alloc(a->capacity);
+    if (e == cudaSuccess) e = a->civ.alloc(a->capacity + 1);
+    if (e == cudaSuccess) e = a->cent.alloc(a->capacity + 1);
+    if (e == cudaSuccess) e = a->cprev.alloc(a->capacity + 1);
     if (e == cudaSuccess) e = a->scan_tmp.alloc(build_bins_scan_bytes(n_boff + 1));
     if (e == cudaSuccess) e = a->d_offs.upload(offs, n_lists + 1, st);
     if (e == cudaSuccess) e = a->d_start.upload(start, n_iv, st);
@@ -507,7 +507,7 @@ extern "C" void gatb_annotations_destroy(gatb_annotations *a)
 static int count_params_annos(const gatb_annotations *a, uint32_t n_samples, bool density, CountParams &p)
 {
     gatb_ctx *ctx = a->ctx;
-    p.keybins = a->keybins.p; p.boff = a->boff.p; p.cent = a->cent.p; p.civ = a->civ.p; p.cprev = a->cprev.p;
+    p.keybins = a->keybins.p; p.boff = a->boff.p; p.cent = a->cent.p; p.civ = a->civ.p; p.cprev = a->cprev.p; p.sentinel = (uint32_t)a->capacity;
     p.key_ws_nseg = a->has_nseg ? a->key_ws_nseg.p : nullptr;
     p.n_annot = a->n_annot; p.n_keys = a->n_keys; p.n_groups = a->n_groups; p.ka = a->ka;
     p.n_samples = n_samples;

@@ -100,13 +100,13 @@ __device__ __forceinline__ void count_entry(const uint2 *__restrict__ civ, const
 {
     const uint32_t s = f.o.x, e = f.o.y;
     const bool first = (int32_t)f.w.x < 0;
-    const uint32_t x = f.w.x & 0x7fffffffu, l = f.w.y & ENTRY_LEN_MASK;
+    const uint32_t x = f.w.x & 0x7fffffffu, l = f.w.y >> 12;
     uint32_t y = x + l;
     if (l == ENTRY_LEN_MASK) y = civ[f.j].y;                // 2^20 - 1 bases or longer: rare
     const bool overlap = (x < e) & (y > s);
     const bool mine = (x >= s) ? first : (f.j < f.o.w);     // the bin of the intersection's first base
     if (!(overlap & mine)) return;
-    const uint32_t cell = acc_addr + ((f.w.y >> 20) << 2);
+    const uint32_t cell = acc_addr + ((f.w.y & 0xfffu) << 2);
     if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
         red_add_shared(cell, min(e, y) - max(s, x));
     } else if (COUNTER == GATB_SEGMENT_OVERLAP) {
@@ -132,10 +132,18 @@ struct Indexed {
 
 // The 32 runs [r0, r1) of an item as one flat sequence of entries.  stg / stg_pe: shared addresses of the
 // warp's staging, acc_addr: of the sample's accumulators.
+struct WarpConsts {
+    uint32_t lane, le_mask, stg, stg_pe, sentinel;
+    uint64_t cent;                                  // global address of the entry array
+};
+// A value that ptxas must keep in a register: it re-derives anything it can trace to a kernel parameter or a
+// special register (LDC / S2R + arithmetic in every round of the hot loop) but not the result of a shuffle.
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v) { return __shfl_sync(GATB_FULL, v, (int)(threadIdx.x & 31u)); }
+
 template <int COUNTER>
-__device__ __forceinline__ void run_item(const CountParams &p, const Indexed &it, uint32_t lane, uint32_t stg,
-                                         uint32_t stg_pe, uint32_t acc_addr)
+__device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts &wc, const Indexed &it, uint32_t acc_addr)
 {
+    const uint32_t lane = wc.lane, stg = wc.stg, stg_pe = wc.stg_pe;
     const uint32_t len = it.r1 - it.r0;
     const uint32_t incl = warp_incl_scan_add_u32(len);
     const uint32_t total = __shfl_sync(GATB_FULL, incl, 31);
@@ -149,10 +157,9 @@ __device__ __forceinline__ void run_item(const CountParams &p, const Indexed &it
         if (NeedPrevSegment<COUNTER>::value) sts32(stg_pe + rank * 4u, it.pe);
     }
     __syncwarp();
-    uint64_t cent = (uint64_t)__cvta_generic_to_global(p.cent);
+    const uint64_t cent = wc.cent;
     const uint32_t *__restrict__ cprev = p.cprev;
-    uint32_t le_mask = 0xffffffffu >> (31u - lane);
-    asm volatile("" : "+l"(cent), "+r"(le_mask));   // registers, not re-derived every round
+    const uint32_t le_mask = wc.le_mask, sentinel = wc.sentinel;
     const uint32_t first_pos = len ? excl : 0xffffffffu;    // flat position of the run's first entry
     uint32_t started = 0xffffffffu;                 // (non-empty runs that begin before the round) - 1
 
@@ -162,17 +169,11 @@ __device__ __forceinline__ void run_item(const CountParams &p, const Indexed &it
         const uint32_t owner = started + __popc(mask & le_mask);
         started += __popc(mask);
         const uint32_t pos = base + lane;
-        if (pos < total) {
-            f.o = lds128(stg + owner * 16u);
-            f.j = pos + f.o.z;
-            f.w = ldg_nc_u2(cent + (uint64_t)f.j * 8u);
-            if (NeedPrevInterval<COUNTER>::value) f.pv = cprev[f.j];
-            if (NeedPrevSegment<COUNTER>::value) f.pe = lds32(stg_pe + owner * 4u);
-        } else {                                    // past the end (last round): an entry that overlaps nothing
-            f.o = make_uint4(0u, 0u, 0u, 0u);
-            f.w = make_uint2(0u, 0u);
-            f.j = 0u; f.pv = 0u; f.pe = 0u;
-        }
+        f.o = lds128(stg + owner * 16u);
+        f.j = (pos < total) ? pos + f.o.z : sentinel;       // past the end (last round): the entry that overlaps nothing
+        f.w = ldg_nc_u2(cent + (uint64_t)f.j * 8u);
+        if (NeedPrevInterval<COUNTER>::value) f.pv = cprev[f.j];
+        if (NeedPrevSegment<COUNTER>::value) f.pe = lds32(stg_pe + owner * 4u);
     };
     Flight fa, fb;
     fetch(0, fa);
@@ -192,8 +193,7 @@ template <int COUNTER, bool DENSITY>
 __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint32_t lane = threadIdx.x & 31u;
-    asm volatile("" : "+r"(lane));                  // keep it in a register (the hot loop would re-read %tid)
+    const uint32_t lane = pin_reg(threadIdx.x & 31u);
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t g = blockIdx.x;
     const uint32_t a0 = g * p.ka;
@@ -202,8 +202,16 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
     const uint32_t s_end = min(s_begin + p.schunk, p.n_samples);
     const uint32_t ns = s_end - s_begin, ncells = ns * ka;
     // layout: [staging][density only: (sum, compensation) doubles per cell][u32 per cell][item tables]
-    const uint32_t stg = smem_addr(smem) + (uint32_t)warp * 512u;
-    const uint32_t stg_pe = smem_addr(smem) + (uint32_t)nwarps * 512u + (uint32_t)warp * 128u;
+    WarpConsts wc;
+    wc.lane = lane;
+    wc.le_mask = pin_reg(0xffffffffu >> (31u - lane));
+    wc.stg = pin_reg(smem_addr(smem) + (uint32_t)warp * 512u);
+    wc.stg_pe = pin_reg(smem_addr(smem) + (uint32_t)nwarps * 512u + (uint32_t)warp * 128u);
+    wc.sentinel = pin_reg(p.sentinel);
+    {
+        const uint64_t c = (uint64_t)__cvta_generic_to_global(p.cent);
+        wc.cent = ((uint64_t)pin_reg((uint32_t)(c >> 32)) << 32) | pin_reg((uint32_t)c);
+    }
     uint8_t *base = smem + count_smem_fixed((uint32_t)nwarps);
     double *acc_d = reinterpret_cast<double *>(base);
     uint32_t *acc_u = reinterpret_cast<uint32_t *>(base + (DENSITY ? (size_t)p.schunk * p.ka * 16u : 0u));
@@ -212,6 +220,7 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
     uint32_t *pre = acc_u + (size_t)p.schunk * p.ka;
     uint32_t *nn = pre + (size_t)p.kgrp * (p.schunk + 1u);
     uint32_t *cnt = nn + (size_t)p.kgrp * p.schunk;
+    const uint32_t acc_base = pin_reg(smem_addr(acc_u));
 
     for (uint32_t i = threadIdx.x; i < ncells; i += blockDim.x) {
         acc_u[i] = 0u;
@@ -305,7 +314,7 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
                         }
                     }
                     // run B (its offsets were requested one turn ago), then B <- B'
-                    if (b.slot != NO_ITEM) run_item<COUNTER>(p, b, lane, stg, stg_pe, smem_addr(acc_u) + b.slot * ka * 4u);
+                    if (b.slot != NO_ITEM) run_item<COUNTER>(p, wc, b, acc_base + b.slot * ka * 4u);
                     b = nb;
                 }
             }
@@ -415,7 +424,7 @@ __global__ void __launch_bounds__(256) bins_pass_kernel(BuildBinsParams p)
         else {
             const uint64_t pos = atomicAdd(cur + b, 1u);
             if (pos < p.capacity) {
-                p.cent[pos] = make_uint2((b == b0 ? 0x80000000u : 0u) | x, (t << 20) | min(y - x, ENTRY_LEN_MASK));
+                p.cent[pos] = make_uint2((b == b0 ? 0x80000000u : 0u) | x, (min(y - x, ENTRY_LEN_MASK) << 12) | t);
                 if (y - x >= ENTRY_LEN_MASK) p.civ[pos] = make_uint2(x, y);      // only ever read for these
                 p.cprev[pos] = py;
             }
@@ -438,6 +447,9 @@ __global__ void __launch_bounds__(256) bins_pass_kernel(BuildBinsParams p)
 __global__ void bins_total_kernel(BuildBinsParams p)
 {
     if (*p.total > p.capacity) atomicOr(p.error, 4u);
+    // entry `capacity` is the sentinel: a continuation entry at the largest coordinate overlaps no segment
+    p.cent[p.capacity] = make_uint2(0x7fffffffu, 0u);
+    p.cprev[p.capacity] = 0u;
 }
 
 size_t build_bins_scan_bytes(uint64_t n_boff)

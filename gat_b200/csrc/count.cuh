@@ -27,7 +27,7 @@ constexpr uint32_t ENTRY_LEN_MASK = 0xfffffu;
 //   KeyBins keybins[n_groups][n_keys]    where the key's bins start in boff[], how many, log2(bin width)
 //   uint32  boff[]                       per (group, key): nbins+1 entry offsets (absolute, into the arrays below)
 //   uint2   cent[n_entries]              the entry the counting kernel streams, 8 bytes:
-//                                          .x = start | 1<<31 on the interval's first bin,  .y = slot<<20 | min(length, 2^20-1)
+//                                          .x = start | 1<<31 on the interval's first bin,  .y = min(length, 2^20-1)<<12 | slot
 //                                        (slot = track within the group, < 4096; a length field of 2^20-1
 //                                        sends the kernel to civ[] for the end)
 //   uint2   civ[n_entries]               the exact interval (start, end), read for intervals of 2^20-1 bases or more
@@ -46,6 +46,7 @@ struct CountParams {
     const uint2 *cent;
     const uint2 *civ;
     const uint32_t *cprev;
+    uint32_t sentinel;              // index of the entry that overlaps nothing (= capacity; arrays hold capacity + 1)
     const uint32_t *key_ws_nseg;    // [n_keys] or NULL
     uint32_t n_annot, n_keys, n_groups, ka;   // ka = tracks per group
     uint32_t kgrp;                  // keys whose item tables are held in shared memory at a time
@@ -81,7 +82,7 @@ struct BuildBinsParams {
     uint2 *cent;
     uint2 *civ;
     uint32_t *cprev;
-    uint64_t capacity;              // entries the arrays hold
+    uint64_t capacity;              // entries the arrays hold, + 1 for the sentinel entry
     uint32_t n_annot, n_keys, n_groups, ka;
     uint32_t *error;
     unsigned long long *total;      // out: entries needed

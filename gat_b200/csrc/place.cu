@@ -150,6 +150,25 @@ __device__ __forceinline__ uint32_t warp_filter_ws(uint64_t *buf, uint32_t n, co
     return nout;
 }
 
+// After trim_ends the list is still sorted and merged (segments only shrank or were emptied, and
+// merge(0) had left a gap between neighbours), so sort + merge(0) reduces to dropping the empty segments.
+__device__ __forceinline__ uint32_t warp_drop_empty(uint64_t *buf, uint32_t n)
+{
+    const int lane = lane_id();
+    uint32_t nout = 0;
+    for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+        uint32_t i = b0 + lane;
+        uint64_t x = (i < n) ? buf[i] : 0;
+        bool keep = (i < n) && (seg_start(x) != seg_end(x));
+        uint32_t m = __ballot_sync(GATB_FULL, keep);
+        __syncwarp();
+        if (keep) buf[nout + __popc(m & ((1u << lane) - 1))] = x;
+        nout += __popc(m);
+        __syncwarp();
+    }
+    return nout;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K1: one warp per (unit, sample)
 #ifndef GATB_PLACE_MINBLOCKS
@@ -191,11 +210,20 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
     } else if (d.tab_n > 0) {
         while (true_remaining > 0 && fails < 20) {
             // ---- speculative batch of 32 turns ------------------------------------------------------
-            TurnDraw t = draw_turn(d, ws, tab, t0 + lane, c1base, unit, sample, k0, k1);
-            int32_t incl = warp_incl_scan_add(t.ov);
-            int32_t rem_before = remaining - (incl - t.ov);
-            uint32_t trig = __ballot_sync(GATB_FULL, rem_before <= (int32_t)t.L);
-            uint32_t f = trig ? (uint32_t)__ffs(trig) - 1 : 32u;
+            // (remaining <= 0: turn t0 triggers the checkpoint whatever its length, so its draw is put
+            // off until the checkpoint has shown that the turn is placed at all -- usually it is not)
+            const bool certain = remaining <= 0;
+            TurnDraw t;
+            t.L = 0; t.start = 0; t.end = 0; t.ov = 0;
+            uint32_t f = 0;
+            int32_t incl = 0;
+            if (!certain) {
+                t = draw_turn(d, ws, tab, t0 + lane, c1base, unit, sample, k0, k1);
+                incl = warp_incl_scan_add(t.ov);
+                int32_t rem_before = remaining - (incl - t.ov);
+                uint32_t trig = __ballot_sync(GATB_FULL, rem_before <= (int32_t)t.L);
+                f = trig ? (uint32_t)__ffs(trig) - 1 : 32u;
+            }
             if (nu + np + f + 1 > d.cap) {
                 // buffer full: merge now.  merge(0) is idempotent and associative on the set of
                 // accepted placements, so an early merge does not change any later result.
@@ -210,15 +238,14 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
             if (f == 32) continue;
 
             // ---- turn t0: `remaining <= length` -> checkpoint (gat/Engine.pyx:582-605) ---------------
-            const uint32_t Lf = __shfl_sync(GATB_FULL, t.L, (int)f);
-            const uint32_t sf = __shfl_sync(GATB_FULL, t.start, (int)f);
-            const uint32_t ef = __shfl_sync(GATB_FULL, t.end, (int)f);
-            const int32_t ovf = __shfl_sync(GATB_FULL, t.ov, (int)f);
-            (void)Lf;
+            uint32_t sf = __shfl_sync(GATB_FULL, t.start, (int)f);
+            uint32_t ef = __shfl_sync(GATB_FULL, t.end, (int)f);
+            int32_t ovf = __shfl_sync(GATB_FULL, t.ov, (int)f);
             __syncwarp();
             // late checkpoints add a handful of placements to an already merged list: insert them
             // instead of re-sorting everything (same result, see warp_insert_merge0)
-            if (nu > 0 && np < 32 && !dirty) nu = warp_insert_merge0(buf, nu, np);
+            if (dirty && np == 0) nu = warp_drop_empty(buf, nu);       // straight after a trim
+            else if (nu > 0 && np < 32 && !dirty) nu = warp_insert_merge0(buf, nu, np);
             else {
                 const uint32_t n = nu + np;         // the free upper part of the buffer is the sort's scratch
                 nu = warp_sort_merge0(buf, n, 2u * n <= d.cap ? buf + n : nullptr, cnt);
@@ -237,6 +264,10 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
                 continue;
             }
             if (true_remaining > 0) {           // gat/Engine.pyx:632-634
+                if (certain) {                  // the draw that was put off (every lane computes turn t0)
+                    const TurnDraw t1 = draw_turn(d, ws, tab, t0, c1base, unit, sample, k0, k1);
+                    sf = t1.start; ef = t1.end; ovf = t1.ov;
+                }
                 if (lane == 0) buf[nu + np] = pack_seg(sf, ef);
                 np += 1;
                 remaining -= ovf;
@@ -247,7 +278,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
         // result = unintersected.merge(0).filter(workspace) (gat/Engine.pyx:639-646); placements
         // still pending (appended after the last checkpoint) are dropped, as in the reference
         __syncwarp();
-        if (dirty) nu = warp_sort_merge0(buf, nu, 2u * nu <= d.cap ? buf + nu : nullptr, cnt);
+        if (dirty) nu = warp_drop_empty(buf, nu);
         nu = warp_filter_ws(buf, nu, ws);
     }
     if (lane == 0) {
