@@ -76,13 +76,12 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n)
     return r;
 }
 
-// one entry of the flat sequence, loaded one round ahead of its use
+// one entry of the flat sequence, loaded two rounds ahead of its use
 struct Flight {
-    uint4 o;            // its segment: start, end, (first entry of the run) - (its flat position), end of bin b0's entries
     uint2 w;            // packed entry
-    uint32_t pv;        // end of the previous interval of the track (segment-* counters)
-    uint32_t pe;        // end of the previous segment (annotation-* counters)
+    uint32_t owner;     // staging slot of its segment
     uint32_t j;         // entry index
+    uint32_t pv;        // end of the previous interval of the track (segment-* counters)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -96,15 +95,20 @@ struct Flight {
 //                        i.e. when it does not already overlap the previous segment (x >= pe)
 //   overlap-pieces       len(a.intersect(b)): every overlapping pair is one piece (:1469-1549)
 template <int COUNTER>
-__device__ __forceinline__ void count_entry(const uint2 *__restrict__ civ, const Flight &f, uint32_t acc_addr)
+__device__ __forceinline__ void count_entry(const uint2 *__restrict__ civ, const Flight &f, uint32_t stg, uint32_t stg_pe,
+                                            uint32_t acc_addr)
 {
-    const uint32_t s = f.o.x, e = f.o.y;
+    // the entry's segment: start, end, -, end of bin b0's entries
+    const uint4 o = lds128(stg + f.owner * 16u);
+    const uint32_t s = o.x, e = o.y;
+    uint32_t pe = 0;
+    if (NeedPrevSegment<COUNTER>::value) pe = lds32(stg_pe + f.owner * 4u);
     const bool first = (int32_t)f.w.x < 0;
     const uint32_t x = f.w.x & 0x7fffffffu, l = f.w.y >> 12;
     uint32_t y = x + l;
     if (l == ENTRY_LEN_MASK) y = civ[f.j].y;                // 2^20 - 1 bases or longer: rare
     const bool overlap = (x < e) & (y > s);
-    const bool mine = (x >= s) ? first : (f.j < f.o.w);     // the bin of the intersection's first base
+    const bool mine = (x >= s) ? first : (f.j < o.w);       // the bin of the intersection's first base
     if (!(overlap & mine)) return;
     const uint32_t cell = acc_addr + ((f.w.y & 0xfffu) << 2);
     if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
@@ -117,10 +121,10 @@ __device__ __forceinline__ void count_entry(const uint2 *__restrict__ civ, const
     } else if (COUNTER == GATB_OVERLAP_PIECES) {
         red_add_shared(cell, 1u);
     } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
-        if (x >= f.pe) red_add_shared(cell, 1u);
+        if (x >= pe) red_add_shared(cell, 1u);
     } else {
         const uint32_t m = x + ((y - x) >> 1);
-        if (x >= f.pe && s <= m && m < e) red_add_shared(cell, 1u);
+        if (x >= pe && s <= m && m < e) red_add_shared(cell, 1u);
     }
 }
 
@@ -166,25 +170,30 @@ __device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts 
     // flat positions base .. base+31: who owns them, and the entry loads
     auto fetch = [&](uint32_t base, Flight &f) {
         const uint32_t mask = __reduce_or_sync(GATB_FULL, shl_clamp(1u, first_pos - base));
-        const uint32_t owner = started + __popc(mask & le_mask);
+        f.owner = started + __popc(mask & le_mask);
         started += __popc(mask);
         const uint32_t pos = base + lane;
-        f.o = lds128(stg + owner * 16u);
-        f.j = (pos < total) ? pos + f.o.z : sentinel;       // past the end (last round): the entry that overlaps nothing
+        const uint32_t z = lds32(stg + f.owner * 16u + 8u);         // (first entry of the run) - (its flat position)
+        f.j = (pos < total) ? pos + z : sentinel;           // past the end (last round): the entry that overlaps nothing
         f.w = ldg_nc_u2(cent + (uint64_t)f.j * 8u);
         if (NeedPrevInterval<COUNTER>::value) f.pv = cprev[f.j];
-        if (NeedPrevSegment<COUNTER>::value) f.pe = lds32(stg_pe + owner * 4u);
     };
-    Flight fa, fb;
-    fetch(0, fa);
+    // rounds in order; the entry loads run two rounds ahead of their use
+    Flight f0, f1, f2;
+    fetch(0, f0);
+    if (32u < total) fetch(32u, f1);
     for (uint32_t base = 0;;) {
-        base += 32;
-        if (base < total) fetch(base, fb);
-        count_entry<COUNTER>(p.civ, fa, acc_addr);
+        if (base + 64u < total) fetch(base + 64u, f2);
+        count_entry<COUNTER>(p.civ, f0, stg, stg_pe, acc_addr);
+        base += 32u;
         if (base >= total) break;
-        base += 32;
-        if (base < total) fetch(base, fa);
-        count_entry<COUNTER>(p.civ, fb, acc_addr);
+        if (base + 64u < total) fetch(base + 64u, f0);
+        count_entry<COUNTER>(p.civ, f1, stg, stg_pe, acc_addr);
+        base += 32u;
+        if (base >= total) break;
+        if (base + 64u < total) fetch(base + 64u, f1);
+        count_entry<COUNTER>(p.civ, f2, stg, stg_pe, acc_addr);
+        base += 32u;
         if (base >= total) break;
     }
 }

@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
     int32_t remaining = d.ltotal, true_remaining = d.ltotal;
     int fails = 0;
     uint32_t nu = 0, np = 0, t0 = 0, status = 0;
-    bool dirty = false;
+    uint32_t cov = 0;                   // workspace coverage of buf[0,nu) at the last checkpoint
+    bool dirty = false, cov_known = false;
 
     if (d.tab_n > 0 && p.sampler_kind == 1) {
         // SamplerSegments.sample (gat/Engine.pyx:719-735): exactly len(segments) placements, every one
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
                 // accepted placements, so an early merge does not change any later result.
                 __syncwarp();
                 nu = warp_sort_merge0(buf, nu + np);
-                np = 0; dirty = false;
+                np = 0; dirty = false; cov_known = false;
                 if (nu + 33 > d.cap) { status |= UNIT_OVERFLOW; break; }
             }
             if ((uint32_t)lane < f) buf[nu + np + lane] = pack_seg(t.start, t.end);
@@ -244,21 +245,33 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
             __syncwarp();
             // late checkpoints add a handful of placements to an already merged list: insert them
             // instead of re-sorting everything (same result, see warp_insert_merge0)
+            bool cov_valid = false;
             if (dirty && np == 0) nu = warp_drop_empty(buf, nu);       // straight after a trim
-            else if (nu > 0 && np < 32 && !dirty) nu = warp_insert_merge0(buf, nu, np);
-            else {
+            else if (nu > 0 && np < 32 && !dirty) {
+                // when nothing merges (the count grows by np) the coverage just grows by the new segments'
+                uint32_t add = 0;
+                if (cov_known && (uint32_t)lane < np) {
+                    const uint64_t x = buf[nu + lane];
+                    add = ws_overlap(ws, seg_start(x), seg_end(x));
+                }
+                const uint32_t before = nu;
+                nu = warp_insert_merge0(buf, before, np);
+                if (cov_known && nu == before + np) { cov += __reduce_add_sync(GATB_FULL, add); cov_valid = true; }
+            } else {
                 const uint32_t n = nu + np;         // the free upper part of the buffer is the sort's scratch
                 nu = warp_sort_merge0(buf, n, 2u * n <= d.cap ? buf + n : nullptr, cnt);
             }
             np = 0; dirty = false;
-            remaining = d.ltotal - (int32_t)warp_coverage(buf, nu, ws);
+            if (!cov_valid) cov = warp_coverage(buf, nu, ws);
+            cov_known = true;
+            remaining = d.ltotal - (int32_t)cov;
             if (true_remaining == remaining) fails++; else true_remaining = remaining;
 
             if (true_remaining < 0) {           // overshoot (gat/Engine.pyx:608-625)
                 Philox4 b2 = philox4x32_10(t0, 2u | c1base, unit, sample, k0, k1);
                 Philox4 b3 = philox4x32_10(t0, 3u | c1base, unit, sample, k0, k1);
                 warp_trim(buf, nu, (uint32_t)(-true_remaining), b2, b3);
-                dirty = true;
+                dirty = true; cov_known = false;
                 true_remaining = 1;
                 t0 += 1;
                 continue;
