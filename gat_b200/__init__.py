@@ -204,6 +204,9 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
             ref = None
             if reference:
                 ref = np.array([reference[track][a].fold for a in atracks], dtype=np.float64)
+            # the S x A matrix stays on the GPU (Engine.SampleMatrix): results copy it to the host only
+            # when their samples are asked for
+            matrix = None
             if out_u is None:
                 host = np.zeros((num_samples, len(atracks)))
                 st = ctx.column_stats(host.astype(np.uint32), obs, pseudo_count=pseudo_count, ref_fold=ref)
@@ -211,20 +214,20 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
                 st = ctx.column_stats(None, obs, pseudo_count=pseudo_count, ref_fold=ref,
                                       device_ptr=out_f.data_ptr(), n_samples=num_samples,
                                       n_cols=len(atracks), is_float=1)
-                host = out_f.cpu().numpy()
+                matrix = Engine.SampleMatrix(out_f, False)
             else:
                 plane = out_u[counter_id]
                 st = ctx.column_stats(None, obs, pseudo_count=pseudo_count, ref_fold=ref,
                                       device_ptr=plane.data_ptr(), n_samples=num_samples,
                                       n_cols=len(atracks), is_float=0)
-                host = plane.cpu().numpy().view(np.uint32)
+                matrix = Engine.SampleMatrix(plane, True)
             for ai, annotation in enumerate(atracks):
                 if annotation not in annos_in_result:
                     continue
                 row = dict((k, float(v[ai])) for k, v in st.items())
                 annotator_results.append(AnnotatorResultExtended(
                     track=track, annotation=annotation, counter=counter.name, observed=r[annotation],
-                    samples=host[:, ai], track_segments=segments[track],
+                    samples=(matrix, ai) if matrix is not None else host[:, ai], track_segments=segments[track],
                     annotation_segments=annotations[annotation], workspace=workspace,
                     reference=reference[track][annotation] if reference else None,
                     pseudo_count=pseudo_count, stats=row,

@@ -74,7 +74,13 @@ class IntervalContainer(object):
         pass
 
     def sum(self):
-        return sum(s.sum() for s in self.getSegmentLists())
+        # one vectorised pass over all lists (a Python-level sum of per-list sums costs ~5 us per list, and
+        # gat.run asks for the size of every annotation)
+        arrays = [s.asarray() for s in self.getSegmentLists() if len(s)]
+        if not arrays:
+            return 0
+        a = arrays[0] if len(arrays) == 1 else np.concatenate(arrays, axis=0)
+        return int(a[:, 1].sum(dtype=np.int64)) - int(a[:, 0].sum(dtype=np.int64))
 
     def counts(self):
         return sum(len(s) for s in self.getSegmentLists())
@@ -516,6 +522,28 @@ def overlapColumns(track_segments, annotations, annos_cache=None):
 
 
 # ------------------------------------------------------------------------------------------- results
+class SampleMatrix(object):
+    """The S x A matrix of sampled counts of one (track, counter), left on the GPU where gat_b200.run computed
+    it and its statistics.  Result objects hold (matrix, column); the host copy is made once, when the first
+    result is asked for its samples (output_counts_pattern, getSample, user code) -- outputResults never is."""
+
+    def __init__(self, tensor, as_uint32):
+        self._tensor = tensor
+        self._as_uint32 = as_uint32
+        self._host = None
+        self.nsamples = int(tensor.shape[0])
+
+    def host(self):
+        if self._host is None:
+            h = self._tensor.cpu().numpy()
+            self._host = h.view(np.uint32) if self._as_uint32 else h
+            self._tensor = None
+        return self._host
+
+    def column(self, index):
+        return self.host()[:, index]
+
+
 class AnnotatorResult(object):
     """observed vs simulated counts of one (track, annotation, counter) with expected, CI95, stddev,
     fold, empirical p-value and q-value (gat/Engine.pyx:1725-1852).  The statistics are computed on
@@ -536,10 +564,15 @@ class AnnotatorResult(object):
         self.annotation = annotation
         self.counter = counter
         self.observed = float(observed)
-        # the samples stay in whatever array they arrive in (a strided uint32 column of the S x A count
-        # matrix when built by gat_b200.run) and are converted to float64 only when asked for
-        self._source = samples if isinstance(samples, np.ndarray) else np.array(samples, dtype=np.float64)
-        self.nsamples = len(self._source)
+        # the samples stay wherever they arrive -- a column of a SampleMatrix still on the GPU when built by
+        # gat_b200.run, else an array -- and are converted to float64 only when asked for
+        if isinstance(samples, tuple) and isinstance(samples[0], SampleMatrix):
+            self._lazy, self._array = samples, None
+            self.nsamples = samples[0].nsamples
+        else:
+            self._lazy = None
+            self._array = samples if isinstance(samples, np.ndarray) else np.array(samples, dtype=np.float64)
+            self.nsamples = len(self._array)
         self.format_observed = "%i"
         self.qvalue = 1.0
         if self.nsamples < 1:
@@ -555,6 +588,12 @@ class AnnotatorResult(object):
         self.upper95 = stats["upper95"]
         self.fold = stats["fold"]
         self.pvalue = stats["pvalue"]
+
+    @property
+    def _source(self):
+        if self._array is None:
+            self._array = self._lazy[0].column(self._lazy[1])
+        return self._array
 
     def _column(self):
         """the samples as an (n,1) uint32 (integer counters) or float64 column for gatb_column_stats"""
