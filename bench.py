@@ -234,6 +234,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # NCCL's version banner goes to stdout: keep it to ONE JSON line
         torch.cuda.set_device(local)
         dist.init_process_group(backend="nccl")
     dev = torch.device("cuda", local)

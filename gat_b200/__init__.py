@@ -238,17 +238,26 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
                                overlap_size=track_sizes[track][2][annotation][1],
                                workspace_size=workspace_size)))
 
-    # dump (large) table with counts (gat/__init__.py:1072-1086)
+    # dump (large) table with counts (gat/__init__.py:1072-1086).  The reference formats every sample with
+    # "%i" in a Python loop; here the text of a whole S x A matrix comes from one GPU call (gatb_format_counts)
     if output_counts_pattern and rank == 0:
         for counter in counters:
             filename = re.sub("%s", counter.name, output_counts_pattern)
+            texts = {}                    # id(SampleMatrix) -> (text, column offsets)
             with _open(filename, "w") as outfile:
                 outfile.write("track\tannotation\tobserved\tcounts\n")
                 for o in annotator_results:
                     if o.counter != counter.name:
                         continue
-                    outfile.write("%s\t%s\t%i\t%s\n" % (o.track, o.annotation, o.observed,
-                                                        ",".join(["%i" % x for x in o.samples])))
+                    lazy = getattr(o, "_lazy", None)
+                    if lazy is not None and lazy[0]._as_uint32:
+                        if id(lazy[0]) not in texts:
+                            texts[id(lazy[0])] = lazy[0].text()
+                        text, off = texts[id(lazy[0])]
+                        column = text[int(off[lazy[1]]):int(off[lazy[1] + 1])].tobytes().decode("ascii")
+                    else:
+                        column = ",".join(["%i" % x for x in o.samples])
+                    outfile.write("%s\t%s\t%i\t%s\n" % (o.track, o.annotation, o.observed, column))
     torch.cuda.synchronize(ctx.device)
     mark("statistics+results")
     if timing is not None and rank == 0:

@@ -21,6 +21,7 @@ SYMBOLS = [
     "gatb_annotations_destroy", "gatb_count_lists",
     "gatb_sampler_create", "gatb_sampler_destroy", "gatb_sampler_sample_capacity",
     "gatb_sampler_set_kind", "gatb_sampler_place", "gatb_run", "gatb_column_stats", "gatb_compare_stats",
+    "gatb_format_counts",
 ]
 
 
@@ -92,5 +93,7 @@ def load():
     L.gatb_column_stats.argtypes = [vp, vp, i32, i32, u64, i32, vp, vp, dbl, vp, vp, vp, vp, vp, vp]
     L.gatb_compare_stats.restype = i32
     L.gatb_compare_stats.argtypes = [vp, u64, vp, i32, vp, i32, u64, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp]
+    L.gatb_format_counts.restype = i32
+    L.gatb_format_counts.argtypes = [vp, vp, i32, u64, i32, vp, vp, u64]
     _lib = L
     return L

@@ -1135,3 +1135,41 @@ extern "C" int gatb_compare_stats(gatb_ctx *ctx, uint64_t n_samples, const doubl
     }
     return GATB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// counts table text (--output-counts-pattern)
+extern "C" int gatb_format_counts(gatb_ctx *ctx, const uint32_t *counts, int counts_is_device, uint64_t n_samples,
+                                  int n_cols, uint64_t *col_off, char *text, uint64_t capacity)
+{
+    if (!ctx || !counts || !col_off || n_cols <= 0) return GATB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    const uint32_t A = (uint32_t)n_cols;
+    DevBuf<uint32_t> d_counts;
+    const uint32_t *dc = counts;
+    if (!counts_is_device) {
+        CU(ctx, d_counts.upload(counts, n_samples * A, st));
+        dc = d_counts.p;
+    }
+    DevBuf<unsigned long long> d_len, d_off;
+    CU(ctx, d_len.alloc(A));
+    { ProfScope ps(ctx, PROF_OTHER); launch_format_counts(st, dc, n_samples, A, d_len.p, nullptr, nullptr); }
+    CU(ctx, cudaGetLastError());
+    std::vector<unsigned long long> h_len(A), h_off(A + 1, 0);
+    CU(ctx, cudaMemcpyAsync(h_len.data(), d_len.p, A * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    for (uint32_t a = 0; a < A; a++) h_off[a + 1] = h_off[a] + h_len[a];
+    for (uint32_t a = 0; a <= A; a++) col_off[a] = h_off[a];
+    if (!text) return GATB_OK;
+    if (capacity < h_off[A]) return fail(ctx, GATB_ERR_CAPACITY, "format_counts: text buffer too small");
+    if (h_off[A] == 0) return GATB_OK;
+    DevBuf<char> d_text;
+    CU(ctx, d_off.upload(h_off.data(), A + 1, st));
+    CU(ctx, d_text.alloc(h_off[A]));
+    { ProfScope ps(ctx, PROF_OTHER); launch_format_counts(st, dc, n_samples, A, nullptr, d_off.p, d_text.p); }
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(text, d_text.p, h_off[A], cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return GATB_OK;
+}

@@ -16,6 +16,7 @@
 // (gat/__init__.py:583-587).
 #include <algorithm>
 #include <cub/device/device_scan.cuh>
+#include <cub/block/block_scan.cuh>
 #include "count.cuh"
 #include "../../include/gat_b200.h"
 
@@ -615,6 +616,55 @@ void launch_compare_derive(cudaStream_t st, const CompareParams &p)
     if (total == 0) return;
     const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, 148u * 16u);
     compare_derive_kernel<<<blocks, 256, 0, st>>>(p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// counts table text.  One CTA per column walks the samples in chunks of 256 (thread = sample); a block scan
+// of the lengths (digits + separator) places every number.
+__device__ __forceinline__ uint32_t decimal_digits(uint32_t v)
+{
+    return v < 10u ? 1u : v < 100u ? 2u : v < 1000u ? 3u : v < 10000u ? 4u : v < 100000u ? 5u : v < 1000000u ? 6u
+         : v < 10000000u ? 7u : v < 100000000u ? 8u : v < 1000000000u ? 9u : 10u;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) format_counts_kernel(const uint32_t *__restrict__ counts, uint64_t n_samples,
+                                                            uint32_t n_cols, unsigned long long *__restrict__ col_len,
+                                                            const unsigned long long *__restrict__ col_off,
+                                                            char *__restrict__ text)
+{
+    typedef cub::BlockScan<uint32_t, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const uint32_t col = blockIdx.x;
+    unsigned long long running = 0;                 // bytes of the samples before this chunk (block-uniform)
+    char *out = WRITE ? text + col_off[col] : nullptr;
+    for (uint64_t s0 = 0; s0 < n_samples; s0 += 256) {
+        const uint64_t s = s0 + threadIdx.x;
+        uint32_t v = 0, len = 0;
+        if (s < n_samples) {
+            v = counts[s * n_cols + col];
+            len = decimal_digits(v) + (s + 1 < n_samples ? 1u : 0u);
+        }
+        uint32_t excl, total;
+        Scan(tmp).ExclusiveSum(len, excl, total);
+        if (WRITE && s < n_samples) {
+            char *q = out + running + excl;
+            uint32_t d = decimal_digits(v);
+            if (s + 1 < n_samples) q[d] = ',';
+            while (d) { q[--d] = (char)('0' + v % 10u); v /= 10u; }
+        }
+        running += total;
+        __syncthreads();                            // tmp is reused by the next chunk
+    }
+    if (!WRITE && threadIdx.x == 0) col_len[col] = running;
+}
+
+void launch_format_counts(cudaStream_t st, const uint32_t *counts, uint64_t n_samples, uint32_t n_cols,
+                          unsigned long long *col_len, const unsigned long long *col_off, char *text)
+{
+    if (n_cols == 0) return;
+    if (text == nullptr) format_counts_kernel<false><<<n_cols, 256, 0, st>>>(counts, n_samples, n_cols, col_len, col_off, text);
+    else format_counts_kernel<true><<<n_cols, 256, 0, st>>>(counts, n_samples, n_cols, col_len, col_off, text);
 }
 
 void launch_stats_pass1(cudaStream_t st, const StatsParams &p)

@@ -124,6 +124,11 @@ struct CompareParams {
 };
 void launch_compare_derive(cudaStream_t st, const CompareParams &p);
 
+// counts table text (gat/__init__.py:1072-1086): column a of counts[n_samples][n_cols] as "c0,c1,...".
+// Pass 1 (text == NULL): col_len[a] = bytes of column a.  Pass 2: the bytes, column a at text + col_off[a].
+void launch_format_counts(cudaStream_t st, const uint32_t *counts, uint64_t n_samples, uint32_t n_cols,
+                          unsigned long long *col_len, const unsigned long long *col_off, char *text);
+
 void launch_stats_pass1(cudaStream_t st, const StatsParams &p);
 void launch_stats_pass2(cudaStream_t st, const StatsParams &p);
 void launch_stats_select(cudaStream_t st, const StatsParams &p);

@@ -130,6 +130,22 @@ class Context(object):
         return dict(zip(["expected", "stddev", "lower95", "upper95", "fold", "pvalue"], outs))
 
 
+    def format_counts(self, counts=None, device_ptr=None, n_samples=None, n_cols=None):
+        """the text of the counts table (gat/__init__.py:1072-1086): -> (text uint8[], col_off uint64[n_cols+1]);
+        column a of the [n_samples][n_cols] uint32 matrix is text[col_off[a]:col_off[a+1]] = b"c0,c1,..."."""
+        if device_ptr is None:
+            counts = np.ascontiguousarray(counts, dtype=np.uint32)
+            n_samples, n_cols = counts.shape
+            ptr, on_dev = _p(counts), 0
+        else:
+            ptr, on_dev = ctypes.c_void_p(device_ptr), 1
+        off = np.zeros(n_cols + 1, dtype=np.uint64)
+        self.check(self.lib.gatb_format_counts(self.handle, ptr, on_dev, int(n_samples), int(n_cols), _p(off), None, 0))
+        text = np.empty(max(int(off[-1]), 1), dtype=np.uint8)
+        self.check(self.lib.gatb_format_counts(self.handle, ptr, on_dev, int(n_samples), int(n_cols), _p(off),
+                                               _p(text), int(text.size)))
+        return text[:int(off[-1])], off
+
     def compare_stats(self, m1, m2, col1, col2, obs1, obs2, delta, pseudo_count=1.0):
         """gat-compare's pairwise statistics (scripts/gat-compare.py:218-241, :300-323) for pairs
         (column col1[q] of m1, column col2[q] of m2); m1, m2: [n_samples][n_cols] float64 sample matrices"""

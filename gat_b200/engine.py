@@ -543,6 +543,16 @@ class SampleMatrix(object):
     def column(self, index):
         return self.host()[:, index]
 
+    def text(self):
+        """-> (text uint8[], col_off): every column as b"c0,c1,..." (the counts-table format), formatted on
+        the GPU (gatb_format_counts); integer counters only"""
+        if not self._as_uint32:
+            raise TypeError("float sample matrices are formatted on the host")
+        if self._tensor is not None:
+            return getContext().format_counts(device_ptr=self._tensor.data_ptr(), n_samples=self.nsamples,
+                                              n_cols=int(self._tensor.shape[1]))
+        return getContext().format_counts(counts=self._host)
+
 
 class AnnotatorResult(object):
     """observed vs simulated counts of one (track, annotation, counter) with expected, CI95, stddev,

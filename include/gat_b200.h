@@ -196,6 +196,17 @@ int  gatb_compare_stats(gatb_ctx *ctx, uint64_t n_samples, const double *m1, int
                         double pseudo_count, double *expected, double *stddev, double *lower95,
                         double *upper95, double *fold, double *pvalue);
 
+/* ---- counts table: the text of --output-counts-pattern ------------------------------------------------
+ * Replaces the Python loop of gat/__init__.py:1072-1086, which writes for every result
+ *     ",".join(["%i" % x for x in samples])
+ * (2e8 numbers at 1e6 samples x 200 annotations).  For an [n_samples][n_cols] uint32 count matrix (host, or
+ * device with counts_is_device) the decimal text of every COLUMN, comma separated, no trailing separator, is
+ * formatted on the GPU.  col_off[n_cols + 1] (host) receives the byte offset of every column's text;
+ * text (host, `capacity` bytes) receives the bytes and may be NULL to ask for the sizes only
+ * (col_off[n_cols] = bytes needed).  GATB_ERR_CAPACITY when capacity is too small (col_off is still filled). */
+int  gatb_format_counts(gatb_ctx *ctx, const uint32_t *counts, int counts_is_device, uint64_t n_samples,
+                        int n_cols, uint64_t *col_off, char *text, uint64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -197,6 +197,26 @@ def test_count_index_geometries_match_oracle(ctx, oracle, monkeypatch):
         monkeypatch.delenv(k, raising=False)
 
 
+def test_format_counts_matches_python_formatting(ctx):
+    """gatb_format_counts: the text of the counts table, column by column, equals the reference's
+    ",".join("%i" % x) (gat/__init__.py:1081-1086) -- digit boundaries, 2^32-1, one sample, chunk edges"""
+    import torch
+    rng = np.random.default_rng(5)
+    edge = np.array([0, 9, 10, 99, 100, 999, 1000, 99999, 100000, 999999999, 1000000000, 4294967295], dtype=np.uint32)
+    for S, A in ((1, 1), (1, 5), (12, 3), (256, 2), (257, 7), (1000, 4), (5000, 33)):
+        m = rng.integers(0, 2 ** 32, size=(S, A), dtype=np.uint64).astype(np.uint32)
+        m >>= rng.integers(0, 32, size=(S, A)).astype(np.uint32)          # every number of digits
+        m[:min(S, len(edge)), 0] = edge[:min(S, len(edge))]
+        want = [",".join("%i" % x for x in m[:, a]) for a in range(A)]
+        text, off = ctx.format_counts(counts=m)
+        got = [text[int(off[a]):int(off[a + 1])].tobytes().decode("ascii") for a in range(A)]
+        assert got == want, (S, A)
+        t = torch.from_numpy(m.view(np.int32)).cuda()
+        text, off = ctx.format_counts(device_ptr=t.data_ptr(), n_samples=S, n_cols=A)
+        got = [text[int(off[a]):int(off[a + 1])].tobytes().decode("ascii") for a in range(A)]
+        assert got == want, (S, A, "device")
+
+
 def test_invalid_inputs_fail_loudly(ctx):
     """error behaviour at the boundary: non-normalized lists, out-of-range coordinates, too-large segments"""
     from gat_b200 import device, _lib
