@@ -168,32 +168,41 @@ __device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts 
     const uint32_t first_pos = len ? excl : 0xffffffffu;    // flat position of the run's first entry
     uint32_t started = 0xffffffffu;                 // (non-empty runs that begin before the round) - 1
 
-    // flat positions base .. base+31: who owns them, and the entry loads
-    auto fetch = [&](uint32_t base, Flight &f) {
+    // Rounds of 32 flat positions, software-pipelined without branches: stage A (who owns the positions of a
+    // round: one warp OR-reduction) runs three rounds ahead of the round being counted, stage B (the entry loads)
+    // two rounds ahead.  Rounds past the end are harmless: no run starts there (owner = the last run) and
+    // their positions are >= total (the sentinel entry).
+    auto stage_a = [&](uint32_t base) -> uint32_t {
         const uint32_t mask = __reduce_or_sync(GATB_FULL, shl_clamp(1u, first_pos - base));
-        f.owner = started + __popc(mask & le_mask);
+        const uint32_t owner = started + __popc(mask & le_mask);
         started += __popc(mask);
+        return owner;
+    };
+    auto stage_b = [&](uint32_t base, Flight &f) {
         const uint32_t pos = base + lane;
         const uint32_t z = lds32(stg + f.owner * 16u + 8u);         // (first entry of the run) - (its flat position)
-        f.j = (pos < total) ? pos + z : sentinel;           // past the end (last round): the entry that overlaps nothing
+        f.j = (pos < total) ? pos + z : sentinel;
         f.w = ldg_nc_u2(cent + (uint64_t)f.j * 8u);
         if (NeedPrevInterval<COUNTER>::value) f.pv = cprev[f.j];
     };
-    // rounds in order; the entry loads run two rounds ahead of their use
     Flight f0, f1, f2;
-    fetch(0, f0);
-    if (32u < total) fetch(32u, f1);
+    f0.owner = stage_a(0u); f1.owner = stage_a(32u); f2.owner = stage_a(64u);
+    stage_b(0u, f0);
+    stage_b(32u, f1);
     for (uint32_t base = 0;;) {
-        if (base + 64u < total) fetch(base + 64u, f2);
+        stage_b(base + 64u, f2);
         count_entry<COUNTER>(p.civ, f0, stg, stg_pe, acc_addr);
+        f0.owner = stage_a(base + 96u);
         base += 32u;
         if (base >= total) break;
-        if (base + 64u < total) fetch(base + 64u, f0);
+        stage_b(base + 64u, f0);
         count_entry<COUNTER>(p.civ, f1, stg, stg_pe, acc_addr);
+        f1.owner = stage_a(base + 96u);
         base += 32u;
         if (base >= total) break;
-        if (base + 64u < total) fetch(base + 64u, f1);
+        stage_b(base + 64u, f1);
         count_entry<COUNTER>(p.civ, f2, stg, stg_pe, acc_addr);
+        f2.owner = stage_a(base + 96u);
         base += 32u;
         if (base >= total) break;
     }
