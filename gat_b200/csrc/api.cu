@@ -304,7 +304,7 @@ static cudaError_t annotations_build(gatb_annotations *a)
     uint32_t *slot = ctx->err_slots + 4 * a->err_slot;
     cudaError_t e = cudaMemsetAsync(a->d_err.p, 0, sizeof(uint32_t), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(a->d_total.p, 0, sizeof(unsigned long long), st);
-    if (e == cudaSuccess && a->n_boff) e = cudaMemsetAsync(a->boff.p, 0, a->n_boff * sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->boff.p, 0, (a->n_boff + 1) * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     BuildBinsParams bp;
     memset(&bp, 0, sizeof(bp));
@@ -315,7 +315,7 @@ static cudaError_t annotations_build(gatb_annotations *a)
     bp.error = a->d_err.p; bp.total = a->d_total.p;
     {
         ProfScope ps(ctx, PROF_OTHER, st);
-        ctx->launches += 3;                 // count, scan, check, fill
+        ctx->launches += 6;                 // count, even, scan (2), total, fill, pad
         e = launch_build_bins(st, bp, a->scan_tmp.p, a->scan_tmp.n);
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(slot, a->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
@@ -343,10 +343,10 @@ static int annotations_finish(gatb_annotations *a)
             tl_stream = saved;
             return a->status = fail(ctx, GATB_ERR_INVALID, "annotations: index needs 2^32 or more entries");
         }
-        a->capacity = need;
-        e = a->civ.alloc(need + 1);
-        if (e == cudaSuccess) e = a->cent.alloc(need + 1);
-        if (e == cudaSuccess) e = a->cprev.alloc(need + 1);
+        a->capacity = need;                 // (even: every bin has an even number of slots)
+        e = a->civ.alloc(need + 2);
+        if (e == cudaSuccess) e = a->cent.alloc(need + 2);
+        if (e == cudaSuccess) e = a->cprev.alloc(need + 2);
         if (e == cudaSuccess) e = annotations_build(a);
         if (e == cudaSuccess) e = cudaEventSynchronize(a->ready);
         h_err = slot[0];
@@ -433,8 +433,10 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
         }
     if (n_boff > 0x7fffffffull) { delete a; return fail(ctx, GATB_ERR_INVALID, "annotations: index too large"); }
     a->n_boff = n_boff;
-    a->capacity = (uint64_t)(est * 1.25) + 4096;
+    // (+ up to one padding slot per bin: bins hold an even number of entries)
+    a->capacity = (uint64_t)(est * 1.25) + n_boff / 2 + 4096;
     if (env_u32("GATB_INDEX_CAPACITY", 0)) a->capacity = env_u32("GATB_INDEX_CAPACITY", 0);    // (tests: forces the rebuild)
+    a->capacity = (a->capacity + 1) & ~(uint64_t)1;
 
     cudaStream_t st = ctx->upload_stream;
     a->err_slot = ctx->err_free.back();
@@ -446,9 +448,9 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, st); a->has_nseg = true; }
     if (e == cudaSuccess) e = a->d_jmax.upload(jmax.data(), K, st);
     if (e == cudaSuccess) e = a->boff.alloc(n_boff + 1);
-    if (e == cudaSuccess) e = a->civ.alloc(a->capacity + 1);
-    if (e == cudaSuccess) e = a->cent.alloc(a->capacity + 1);
-    if (e == cudaSuccess) e = a->cprev.alloc(a->capacity + 1);
+    if (e == cudaSuccess) e = a->civ.alloc(a->capacity + 2);
+    if (e == cudaSuccess) e = a->cent.alloc(a->capacity + 2);
+    if (e == cudaSuccess) e = a->cprev.alloc(a->capacity + 2);
     if (e == cudaSuccess) e = a->scan_tmp.alloc(build_bins_scan_bytes(n_boff + 1));
     if (e == cudaSuccess) e = a->d_offs.upload(offs, n_lists + 1, st);
     if (e == cudaSuccess) e = a->d_start.upload(start, n_iv, st);

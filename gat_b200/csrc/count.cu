@@ -69,6 +69,13 @@ __device__ __forceinline__ uint2 ldg_nc_u2(uint64_t addr)
     asm("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(addr));
     return v;
 }
+// read-only 16-byte global load (address 16-byte aligned)
+__device__ __forceinline__ uint4 ldg_nc_u4(uint64_t addr)
+{
+    uint4 v;
+    asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr));
+    return v;
+}
 // v << n, 0 for n >= 32 (PTX shl clamps the shift amount, C++ << does not)
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n)
 {
@@ -77,12 +84,12 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n)
     return r;
 }
 
-// one entry of the flat sequence, loaded two rounds ahead of its use
+// one PAIR of adjacent entries of the flat sequence, loaded two rounds ahead of its use
 struct Flight {
-    uint2 w;            // packed entry
-    uint32_t owner;     // staging slot of its segment
-    uint32_t j;         // entry index
-    uint32_t pv;        // end of the previous interval of the track (segment-* counters)
+    uint4 w;            // the two packed entries (one 16-byte load: runs start and end on even indices)
+    uint32_t owner;     // staging slot of their segment
+    uint32_t j;         // index of the first of the two
+    uint2 pv;           // ends of the previous intervals of their tracks (segment-* counters)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -96,29 +103,25 @@ struct Flight {
 //                        i.e. when it does not already overlap the previous segment (x >= pe)
 //   overlap-pieces       len(a.intersect(b)): every overlapping pair is one piece (:1469-1549)
 template <int COUNTER>
-__device__ __forceinline__ void count_entry(const uint2 *__restrict__ civ, const Flight &f, uint32_t stg, uint32_t stg_pe,
-                                            uint32_t acc_addr)
+__device__ __forceinline__ void count_entry(const uint2 *__restrict__ civ, uint32_t wx, uint32_t wy, uint32_t j,
+                                            uint32_t pv, const uint4 o, uint32_t pe, uint32_t acc_addr)
 {
-    // the entry's segment: start, end, -, end of bin b0's entries
-    const uint4 o = lds128(stg + f.owner * 16u);
-    const uint32_t s = o.x, e = o.y;
-    uint32_t pe = 0;
-    if (NeedPrevSegment<COUNTER>::value) pe = lds32(stg_pe + f.owner * 4u);
-    const bool first = (int32_t)f.w.x < 0;
-    const uint32_t x = f.w.x & 0x7fffffffu, l = f.w.y >> 12;
+    const uint32_t s = o.x, e = o.y;                        // the entry's segment; o.w = end of bin b0's entries
+    const bool first = (int32_t)wx < 0;
+    const uint32_t x = wx & 0x7fffffffu, l = wy >> 12;
     uint32_t y = x + l;
-    if (l == ENTRY_LEN_MASK) y = civ[f.j].y;                // 2^20 - 1 bases or longer: rare
+    if (l == ENTRY_LEN_MASK) y = civ[j].y;                  // 2^20 - 1 bases or longer: rare
     const bool overlap = (x < e) & (y > s);
-    const bool mine = (x >= s) ? first : (f.j < o.w);       // the bin of the intersection's first base
+    const bool mine = (x >= s) ? first : (j < o.w);         // the bin of the intersection's first base
     if (!(overlap & mine)) return;
-    const uint32_t cell = acc_addr + ((f.w.y & 0xfffu) << 2);
+    const uint32_t cell = acc_addr + ((wy & 0xfffu) << 2);
     if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
         red_add_shared(cell, min(e, y) - max(s, x));
     } else if (COUNTER == GATB_SEGMENT_OVERLAP) {
-        if (f.pv <= s) red_add_shared(cell, 1u);
+        if (pv <= s) red_add_shared(cell, 1u);
     } else if (COUNTER == GATB_SEGMENT_MIDOVERLAP) {
         const uint32_t mid = s + ((e - s) >> 1);
-        if (f.pv <= s && x <= mid && mid < y) red_add_shared(cell, 1u);
+        if (pv <= s && x <= mid && mid < y) red_add_shared(cell, 1u);
     } else if (COUNTER == GATB_OVERLAP_PIECES) {
         red_add_shared(cell, 1u);
     } else if (COUNTER == GATB_ANNOTATION_OVERLAP) {
@@ -127,6 +130,18 @@ __device__ __forceinline__ void count_entry(const uint2 *__restrict__ civ, const
         const uint32_t m = x + ((y - x) >> 1);
         if (x >= pe && s <= m && m < e) red_add_shared(cell, 1u);
     }
+}
+
+// the two entries of a flight against their segment
+template <int COUNTER>
+__device__ __forceinline__ void count_pair(const uint2 *__restrict__ civ, const Flight &f, uint32_t stg, uint32_t stg_pe,
+                                           uint32_t acc_addr)
+{
+    const uint4 o = lds128(stg + f.owner * 16u);
+    uint32_t pe = 0;
+    if (NeedPrevSegment<COUNTER>::value) pe = lds32(stg_pe + f.owner * 4u);
+    count_entry<COUNTER>(civ, f.w.x, f.w.y, f.j, f.pv.x, o, pe, acc_addr);
+    count_entry<COUNTER>(civ, f.w.z, f.w.w, f.j + 1u, f.pv.y, o, pe, acc_addr);
 }
 
 // an item whose bin offsets have been requested: lane = segment
@@ -149,7 +164,9 @@ template <int COUNTER>
 __device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts &wc, const Indexed &it, uint32_t acc_addr)
 {
     const uint32_t lane = wc.lane, stg = wc.stg, stg_pe = wc.stg_pe;
-    const uint32_t len = it.r1 - it.r0;
+    // every bin holds an even number of entries (padded with an entry that overlaps nothing) and starts on an
+    // even index, so runs are whole PAIRS of entries: a lane takes a pair per round with one 16-byte load
+    const uint32_t len = (it.r1 - it.r0) >> 1;              // pairs
     const uint32_t incl = warp_incl_scan_add_u32(len);
     const uint32_t total = __shfl_sync(GATB_FULL, incl, 31);
     if (total == 0) return;
@@ -158,20 +175,20 @@ __device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts 
     const uint32_t rank = __popc(have & ((1u << lane) - 1u));
     __syncwarp();                                   // the previous item's readers are done with the staging
     if (len) {
-        sts128(stg + rank * 16u, make_uint4(it.s, it.e, it.r0 - excl, it.rf));
+        sts128(stg + rank * 16u, make_uint4(it.s, it.e, it.r0 - 2u * excl, it.rf));
         if (NeedPrevSegment<COUNTER>::value) sts32(stg_pe + rank * 4u, it.pe);
     }
     __syncwarp();
     const uint64_t cent = wc.cent;
     const uint32_t *__restrict__ cprev = p.cprev;
     const uint32_t le_mask = wc.le_mask, sentinel = wc.sentinel;
-    const uint32_t first_pos = len ? excl : 0xffffffffu;    // flat position of the run's first entry
+    const uint32_t first_pos = len ? excl : 0xffffffffu;    // flat pair position of the run's first pair
     uint32_t started = 0xffffffffu;                 // (non-empty runs that begin before the round) - 1
 
-    // Rounds of 32 flat positions, software-pipelined without branches: stage A (who owns the positions of a
-    // round: one warp OR-reduction) runs three rounds ahead of the round being counted, stage B (the entry loads)
-    // two rounds ahead.  Rounds past the end are harmless: no run starts there (owner = the last run) and
-    // their positions are >= total (the sentinel entry).
+    // Rounds of 32 flat pair positions, software-pipelined without branches: stage A (who owns the positions of
+    // a round: one warp OR-reduction) runs three rounds ahead of the round being counted, stage B (the entry
+    // loads) two rounds ahead.  Rounds past the end are harmless: no run starts there (owner = the last run)
+    // and their positions are >= total (the sentinel pair).
     auto stage_a = [&](uint32_t base) -> uint32_t {
         const uint32_t mask = __reduce_or_sync(GATB_FULL, shl_clamp(1u, first_pos - base));
         const uint32_t owner = started + __popc(mask & le_mask);
@@ -180,10 +197,10 @@ __device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts 
     };
     auto stage_b = [&](uint32_t base, Flight &f) {
         const uint32_t pos = base + lane;
-        const uint32_t z = lds32(stg + f.owner * 16u + 8u);         // (first entry of the run) - (its flat position)
-        f.j = (pos < total) ? pos + z : sentinel;
-        f.w = ldg_nc_u2(cent + (uint64_t)f.j * 8u);
-        if (NeedPrevInterval<COUNTER>::value) f.pv = cprev[f.j];
+        const uint32_t z = lds32(stg + f.owner * 16u + 8u);         // (first entry of the run) - 2 * (its flat pair position)
+        f.j = (pos < total) ? 2u * pos + z : sentinel;
+        f.w = ldg_nc_u4(cent + (uint64_t)f.j * 8u);
+        if (NeedPrevInterval<COUNTER>::value) f.pv = *reinterpret_cast<const uint2 *>(cprev + f.j);
     };
     Flight f0, f1, f2;
     f0.owner = stage_a(0u); f1.owner = stage_a(32u); f2.owner = stage_a(64u);
@@ -191,17 +208,17 @@ __device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts 
     stage_b(32u, f1);
     for (uint32_t base = 0;;) {
         stage_b(base + 64u, f2);
-        count_entry<COUNTER>(p.civ, f0, stg, stg_pe, acc_addr);
+        count_pair<COUNTER>(p.civ, f0, stg, stg_pe, acc_addr);
         f0.owner = stage_a(base + 96u);
         base += 32u;
         if (base >= total) break;
         stage_b(base + 64u, f0);
-        count_entry<COUNTER>(p.civ, f1, stg, stg_pe, acc_addr);
+        count_pair<COUNTER>(p.civ, f1, stg, stg_pe, acc_addr);
         f1.owner = stage_a(base + 96u);
         base += 32u;
         if (base >= total) break;
         stage_b(base + 64u, f1);
-        count_entry<COUNTER>(p.civ, f2, stg, stg_pe, acc_addr);
+        count_pair<COUNTER>(p.civ, f2, stg, stg_pe, acc_addr);
         f2.owner = stage_a(base + 96u);
         base += 32u;
         if (base >= total) break;
@@ -408,7 +425,6 @@ cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int
 template <bool FILL>
 __global__ void __launch_bounds__(256) bins_pass_kernel(BuildBinsParams p)
 {
-    __shared__ unsigned long long s_total[8];
     const uint32_t k = blockIdx.y;
     const uint64_t J = p.key_jmax[k];
     const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -449,26 +465,38 @@ __global__ void __launch_bounds__(256) bins_pass_kernel(BuildBinsParams p)
             }
         }
     }
-    if (!FILL) {                                    // entries needed, in 64 bits: one atomic per CTA
-        unsigned long long nb = (b1 >= b0) ? (unsigned long long)(b1 - b0 + 1u) : 0ull;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) nb += __shfl_xor_sync(GATB_FULL, nb, d);
-        if ((threadIdx.x & 31) == 0) s_total[threadIdx.x >> 5] = nb;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long sum = 0;
-            for (int w = 0; w < 8; w++) sum += s_total[w];
-            if (sum) atomicAdd(p.total, sum);
-        }
+}
+
+// every bin gets an even number of slots
+__global__ void __launch_bounds__(256) bins_even_kernel(uint32_t *__restrict__ boff, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) boff[i] = (boff[i] + 1u) & ~1u;
+}
+
+// after the fill: a bin with an odd number of entries ends on an odd index (all bins start on even ones);
+// its spare slot takes the entry that overlaps nothing
+__global__ void __launch_bounds__(256) bins_pad_kernel(BuildBinsParams p)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_boff) return;
+    const uint32_t v = p.boff[i];
+    if (v & 1u) {
+        if (v < p.capacity) { p.cent[v] = make_uint2(0x7fffffffu, 0u); p.cprev[v] = 0u; }
+        p.boff[i] = v + 1u;
     }
 }
 
 __global__ void bins_total_kernel(BuildBinsParams p)
 {
-    if (*p.total > p.capacity) atomicOr(p.error, 4u);
-    // entry `capacity` is the sentinel: a continuation entry at the largest coordinate overlaps no segment
-    p.cent[p.capacity] = make_uint2(0x7fffffffu, 0u);
-    p.cprev[p.capacity] = 0u;
+    // the scan ran over n_boff + 1 elements: the last one is the number of slots all bins need
+    const unsigned long long total = p.boff[p.n_boff];
+    *p.total = total;
+    if (total > p.capacity) atomicOr(p.error, 4u);
+    // entries `capacity`, `capacity + 1` (capacity is even) are the sentinel pair: a continuation entry at the
+    // largest coordinate overlaps no segment
+    p.cent[p.capacity] = p.cent[p.capacity + 1u] = make_uint2(0x7fffffffu, 0u);
+    p.cprev[p.capacity] = p.cprev[p.capacity + 1u] = 0u;
 }
 
 size_t build_bins_scan_bytes(uint64_t n_boff)
@@ -483,11 +511,14 @@ cudaError_t launch_build_bins(cudaStream_t st, const BuildBinsParams &p, void *s
     if (p.n_intervals == 0 || p.n_boff == 0) return cudaSuccess;
     if (p.jmax_all == 0) return cudaSuccess;
     const dim3 blocks((unsigned)(((uint64_t)p.jmax_all * p.n_annot + 255) / 256), p.n_keys);
+    const unsigned nb = (unsigned)((p.n_boff + 255) / 256);
     bins_pass_kernel<false><<<blocks, 256, 0, st>>>(p);
-    cudaError_t e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, p.boff, p.boff, (int)p.n_boff, st);
+    bins_even_kernel<<<nb, 256, 0, st>>>(p.boff, p.n_boff);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, p.boff, p.boff, (int)(p.n_boff + 1), st);
     if (e != cudaSuccess) return e;
     bins_total_kernel<<<1, 1, 0, st>>>(p);
     bins_pass_kernel<true><<<blocks, 256, 0, st>>>(p);
+    bins_pad_kernel<<<nb, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -22,7 +22,9 @@ constexpr uint32_t ENTRY_LEN_MASK = 0xfffffu;
 // bins is counted in the bin that holds the first base of their intersection: an interval starting at
 // or after s counts at its FIRST entry, one starting before s counts in bin b0 (entry index
 // < boff[b0+1]).  Entries of a bin are in no particular order; all accumulation is by integer atomics,
-// so results do not depend on it.
+// so results do not depend on it.  Every bin holds an EVEN number of entries (an odd bin is padded with an
+// entry that overlaps nothing: start 2^31-1) and so starts on an even index: the counting kernel reads
+// entries two at a time (16-byte loads) and a pair never straddles two segments' runs.
 //
 //   KeyBins keybins[n_groups][n_keys]    where the key's bins start in boff[], how many, log2(bin width)
 //   uint32  boff[]                       per (group, key): nbins+1 entry offsets (absolute, into the arrays below)
@@ -46,7 +48,7 @@ struct CountParams {
     const uint2 *cent;
     const uint2 *civ;
     const uint32_t *cprev;
-    uint32_t sentinel;              // index of the entry that overlaps nothing (= capacity; arrays hold capacity + 1)
+    uint32_t sentinel;              // index of the pair of entries that overlap nothing (= capacity, even; arrays hold capacity + 2)
     const uint32_t *key_ws_nseg;    // [n_keys] or NULL
     uint32_t n_annot, n_keys, n_groups, ka;   // ka = tracks per group
     uint32_t kgrp;                  // keys whose item tables are held in shared memory at a time
@@ -69,7 +71,7 @@ size_t count_smem_bytes(uint32_t schunk, uint32_t ka, uint32_t kgrp, int threads
 
 // Builds the grid index from the raw annotation CSR arrays on the device and validates the lists
 // (error bit 0: coordinate >= 2^31, bit 1: empty / unsorted / overlapping = not normalized, bit 2: more
-// entries than `capacity`).  Three launches: count entries per bin, exclusive scan, fill.
+// entries than `capacity`).  Launches: count entries per bin, round up to even, exclusive scan, fill, pad.
 struct BuildBinsParams {
     const uint64_t *offs;           // [n_annot*n_keys+1]
     const uint32_t *start, *end;
@@ -77,12 +79,12 @@ struct BuildBinsParams {
     const KeyBins *keybins;         // [n_groups][n_keys]
     const uint32_t *key_jmax;       // [n_keys] longest list (over all tracks) on the key
     uint32_t jmax_all;              // largest of them
-    uint32_t *boff;                 // [n_boff], zeroed by the caller
+    uint32_t *boff;                 // [n_boff + 1], zeroed by the caller
     uint64_t n_boff;
     uint2 *cent;
     uint2 *civ;
     uint32_t *cprev;
-    uint64_t capacity;              // entries the arrays hold, + 1 for the sentinel entry
+    uint64_t capacity;              // entries the arrays hold (even), + 2 for the sentinel pair
     uint32_t n_annot, n_keys, n_groups, ka;
     uint32_t *error;
     unsigned long long *total;      // out: entries needed
