@@ -164,15 +164,51 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t *buf, uint32_t N)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Workspace of one unit: sorted disjoint pieces + inclusive cumulative lengths.
+struct WsView {
+    const uint32_t *start;
+    const uint32_t *end;
+    const uint32_t *cuminc;   // cuminc[i] = sum_{j<=i} len_j   (SegmentListSampler.cdf + 1, gat/Engine.pyx:274-277)
+    uint32_t n;
+};
+
+// workspace bases in [0, x): prefix-coverage closed form (SURVEY App. A.2) -- replaces the two-pointer
+// SegmentList.intersect + sum (gat/SegmentList.pyx:1469-1549, :1607-1616) used at every checkpoint.
+__device__ __forceinline__ uint32_t ws_cov(const WsView &w, uint32_t x)
+{
+    if (w.n == 1) {
+        uint32_t s = w.start[0], e = w.end[0];
+        return x <= s ? 0u : (min(x, e) - s);
+    }
+    uint32_t lo = 0, hi = w.n;
+    while (lo < hi) {                       // number of pieces with start < x
+        uint32_t mid = (lo + hi) >> 1;
+        if (w.start[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0) return 0u;
+    uint32_t p = lo - 1;
+    uint32_t before = p ? w.cuminc[p - 1] : 0u;
+    return before + (min(x, w.end[p]) - w.start[p]);
+}
+
+__device__ __forceinline__ uint32_t ws_overlap(const WsView &w, uint32_t s, uint32_t e)
+{
+    return ws_cov(w, e) - ws_cov(w, s);
+}
+// ---------------------------------------------------------------------------------------------------
 // In-place merge(0) of a SORTED run of n packed segments (gat/SegmentList.pyx:756-816 with
 // distance 0, after its sort): drop empty segments, join when start <= running max end (overlapping
 // AND adjacent).  Returns the new count.  Warp-cooperative: prefix-max of ends across lanes, heads
 // compacted with ballot/popc; the end of a merged segment is patched when the next head is met.
-__device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n)
+// With `ws` and `cov` the pass also returns the workspace coverage of the merged list
+// (intersect(workspace).sum(), gat/Engine.pyx:593-599): element i adds the workspace bases of
+// [max(start_i, running max end), end_i), the part of it that no earlier element covers.
+__device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n, const WsView *ws = nullptr,
+                                                       uint32_t *cov = nullptr)
 {
     const int lane = lane_id();
     int32_t carry = -1;          // running max end of everything seen (int32 like the reference)
-    uint32_t nout = 0;
+    uint32_t nout = 0, covered = 0;
     for (uint32_t b0 = 0; b0 < n; b0 += 32) {
         uint32_t i = b0 + lane;
         uint64_t x = (i < n) ? buf[i] : 0;
@@ -183,6 +219,10 @@ __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n
         int32_t excl = __shfl_up_sync(GATB_FULL, incl, 1);
         if (lane == 0) excl = -1;
         int32_t prev_max = max(carry, excl);
+        if (ws != nullptr && valid) {
+            const int32_t lo = max(s, prev_max);
+            if (e > lo) covered += ws_cov(*ws, (uint32_t)e) - ws_cov(*ws, (uint32_t)lo);
+        }
         bool head = valid && (s > prev_max);
         uint32_t hmask = __ballot_sync(GATB_FULL, head);
         uint32_t pos = nout + __popc(hmask & ((1u << lane) - 1));
@@ -197,6 +237,7 @@ __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n
         __syncwarp();
     }
     if (nout > 0 && lane == 0) reinterpret_cast<uint32_t *>(buf + nout - 1)[0] = (uint32_t)carry;
+    if (cov != nullptr) *cov = __reduce_add_sync(GATB_FULL, covered);
     __syncwarp();
     return nout;
 }
@@ -263,17 +304,18 @@ __device__ __forceinline__ bool warp_bucket_sort(uint64_t *buf, uint32_t n, uint
 // sort + merge(0) of n arbitrary packed segments in a buffer with at least next_pow2(n) slots; with
 // `tmp` (n more free slots) and `cnt` given, mid-sized runs take the counting sort
 __device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n, uint64_t *tmp = nullptr,
-                                                     uint32_t *cnt = nullptr)
+                                                     uint32_t *cnt = nullptr, const WsView *ws = nullptr,
+                                                     uint32_t *cov = nullptr)
 {
-    if (n == 0) return 0;
+    if (n == 0) { if (cov != nullptr) *cov = 0; return 0; }
     const int lane = lane_id();
     if (tmp != nullptr && n >= 96u && n <= 32768u && warp_bucket_sort(buf, n, tmp, cnt))
-        return warp_merge0_sorted(buf, n);
+        return warp_merge0_sorted(buf, n, ws, cov);
     uint32_t N = next_pow2(n);
     for (uint32_t i = n + lane; i < N; i += 32) buf[i] = GATB_KEY_INF;
     __syncwarp();
     warp_bitonic_sort(buf, N);
-    return warp_merge0_sorted(buf, n);
+    return warp_merge0_sorted(buf, n, ws, cov);
 }
 
 // merge(0) of a sorted, merged run U = buf[0,nu) with np <= 32 new segments stored behind it
@@ -282,7 +324,8 @@ __device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n, 
 // right in place (top chunk first) by the number of new keys that precede each element, the new
 // keys are dropped into the gaps and the usual merge(0) scan runs once.  O(nu/32) instead of a
 // full bitonic sort.  Same result as warp_sort_merge0(buf, nu + np).
-__device__ __forceinline__ uint32_t warp_insert_merge0(uint64_t *buf, uint32_t nu, uint32_t np)
+__device__ __forceinline__ uint32_t warp_insert_merge0(uint64_t *buf, uint32_t nu, uint32_t np,
+                                                       const WsView *ws = nullptr, uint32_t *cov = nullptr)
 {
     const int lane = lane_id();
     uint64_t key = ((uint32_t)lane < np) ? buf[nu + lane] : GATB_KEY_INF;
@@ -325,41 +368,9 @@ __device__ __forceinline__ uint32_t warp_insert_merge0(uint64_t *buf, uint32_t n
     }
     if ((uint32_t)lane < np) buf[pos + lane] = key;
     __syncwarp();
-    return warp_merge0_sorted(buf, nu + np);
+    return warp_merge0_sorted(buf, nu + np, ws, cov);
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Workspace of one unit: sorted disjoint pieces + inclusive cumulative lengths.
-struct WsView {
-    const uint32_t *start;
-    const uint32_t *end;
-    const uint32_t *cuminc;   // cuminc[i] = sum_{j<=i} len_j   (SegmentListSampler.cdf + 1, gat/Engine.pyx:274-277)
-    uint32_t n;
-};
-
-// workspace bases in [0, x): prefix-coverage closed form (SURVEY App. A.2) -- replaces the two-pointer
-// SegmentList.intersect + sum (gat/SegmentList.pyx:1469-1549, :1607-1616) used at every checkpoint.
-__device__ __forceinline__ uint32_t ws_cov(const WsView &w, uint32_t x)
-{
-    if (w.n == 1) {
-        uint32_t s = w.start[0], e = w.end[0];
-        return x <= s ? 0u : (min(x, e) - s);
-    }
-    uint32_t lo = 0, hi = w.n;
-    while (lo < hi) {                       // number of pieces with start < x
-        uint32_t mid = (lo + hi) >> 1;
-        if (w.start[mid] < x) lo = mid + 1; else hi = mid;
-    }
-    if (lo == 0) return 0u;
-    uint32_t p = lo - 1;
-    uint32_t before = p ? w.cuminc[p - 1] : 0u;
-    return before + (min(x, w.end[p]) - w.start[p]);
-}
-
-__device__ __forceinline__ uint32_t ws_overlap(const WsView &w, uint32_t s, uint32_t e)
-{
-    return ws_cov(w, e) - ws_cov(w, s);
-}
 #endif  // __CUDACC__
 
 }  // namespace gatb

@@ -54,17 +54,6 @@ __device__ __forceinline__ TurnDraw draw_turn(const UnitDesc &d, const WsView &w
     return t;
 }
 
-// sum over the merged list of its workspace coverage (intersect(workspace).sum(), gat/Engine.pyx:593-599)
-__device__ __forceinline__ uint32_t warp_coverage(const uint64_t *buf, uint32_t n, const WsView &ws)
-{
-    uint32_t acc = 0;
-    for (uint32_t i = lane_id(); i < n; i += 32) {
-        uint64_t x = buf[i];
-        acc += ws_overlap(ws, seg_start(x), seg_end(x));
-    }
-    return __reduce_add_sync(GATB_FULL, acc);
-}
-
 // SegmentList._getInsertionPoint (gat/SegmentList.pyx:853-887) on packed segments
 __device__ __forceinline__ int insertion_point(const uint64_t *buf, uint32_t n, uint32_t ostart, uint32_t oend)
 {
@@ -152,20 +141,23 @@ __device__ __forceinline__ uint32_t warp_filter_ws(uint64_t *buf, uint32_t n, co
 
 // After trim_ends the list is still sorted and merged (segments only shrank or were emptied, and
 // merge(0) had left a gap between neighbours), so sort + merge(0) reduces to dropping the empty segments.
-__device__ __forceinline__ uint32_t warp_drop_empty(uint64_t *buf, uint32_t n)
+// *cov = workspace coverage of what is left (the segments are disjoint).
+__device__ __forceinline__ uint32_t warp_drop_empty(uint64_t *buf, uint32_t n, const WsView &ws, uint32_t *cov)
 {
     const int lane = lane_id();
-    uint32_t nout = 0;
+    uint32_t nout = 0, covered = 0;
     for (uint32_t b0 = 0; b0 < n; b0 += 32) {
         uint32_t i = b0 + lane;
         uint64_t x = (i < n) ? buf[i] : 0;
         bool keep = (i < n) && (seg_start(x) != seg_end(x));
+        if (keep) covered += ws_overlap(ws, seg_start(x), seg_end(x));
         uint32_t m = __ballot_sync(GATB_FULL, keep);
         __syncwarp();
         if (keep) buf[nout + __popc(m & ((1u << lane) - 1))] = x;
         nout += __popc(m);
         __syncwarp();
     }
+    *cov = __reduce_add_sync(GATB_FULL, covered);
     return nout;
 }
 
@@ -196,8 +188,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
     int32_t remaining = d.ltotal, true_remaining = d.ltotal;
     int fails = 0;
     uint32_t nu = 0, np = 0, t0 = 0, status = 0;
-    uint32_t cov = 0;                   // workspace coverage of buf[0,nu) at the last checkpoint
-    bool dirty = false, cov_known = false;
+    bool dirty = false;
 
     if (d.tab_n > 0 && p.sampler_kind == 1) {
         // SamplerSegments.sample (gat/Engine.pyx:719-735): exactly len(segments) placements, every one
@@ -230,7 +221,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
                 // accepted placements, so an early merge does not change any later result.
                 __syncwarp();
                 nu = warp_sort_merge0(buf, nu + np);
-                np = 0; dirty = false; cov_known = false;
+                np = 0; dirty = false;
                 if (nu + 33 > d.cap) { status |= UNIT_OVERFLOW; break; }
             }
             if ((uint32_t)lane < f) buf[nu + np + lane] = pack_seg(t.start, t.end);
@@ -245,25 +236,15 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
             __syncwarp();
             // late checkpoints add a handful of placements to an already merged list: insert them
             // instead of re-sorting everything (same result, see warp_insert_merge0)
-            bool cov_valid = false;
-            if (dirty && np == 0) nu = warp_drop_empty(buf, nu);       // straight after a trim
-            else if (nu > 0 && np < 32 && !dirty) {
-                // when nothing merges (the count grows by np) the coverage just grows by the new segments'
-                uint32_t add = 0;
-                if (cov_known && (uint32_t)lane < np) {
-                    const uint64_t x = buf[nu + lane];
-                    add = ws_overlap(ws, seg_start(x), seg_end(x));
-                }
-                const uint32_t before = nu;
-                nu = warp_insert_merge0(buf, before, np);
-                if (cov_known && nu == before + np) { cov += __reduce_add_sync(GATB_FULL, add); cov_valid = true; }
-            } else {
+            // the merge pass of every variant also returns the workspace coverage of the merged list
+            uint32_t cov = 0;
+            if (dirty && np == 0) nu = warp_drop_empty(buf, nu, ws, &cov);      // straight after a trim
+            else if (nu > 0 && np < 32 && !dirty) nu = warp_insert_merge0(buf, nu, np, &ws, &cov);
+            else {
                 const uint32_t n = nu + np;         // the free upper part of the buffer is the sort's scratch
-                nu = warp_sort_merge0(buf, n, 2u * n <= d.cap ? buf + n : nullptr, cnt);
+                nu = warp_sort_merge0(buf, n, 2u * n <= d.cap ? buf + n : nullptr, cnt, &ws, &cov);
             }
             np = 0; dirty = false;
-            if (!cov_valid) cov = warp_coverage(buf, nu, ws);
-            cov_known = true;
             remaining = d.ltotal - (int32_t)cov;
             if (true_remaining == remaining) fails++; else true_remaining = remaining;
 
@@ -271,7 +252,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
                 Philox4 b2 = philox4x32_10(t0, 2u | c1base, unit, sample, k0, k1);
                 Philox4 b3 = philox4x32_10(t0, 3u | c1base, unit, sample, k0, k1);
                 warp_trim(buf, nu, (uint32_t)(-true_remaining), b2, b3);
-                dirty = true; cov_known = false;
+                dirty = true;
                 true_remaining = 1;
                 t0 += 1;
                 continue;
@@ -291,7 +272,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
         // result = unintersected.merge(0).filter(workspace) (gat/Engine.pyx:639-646); placements
         // still pending (appended after the last checkpoint) are dropped, as in the reference
         __syncwarp();
-        if (dirty) nu = warp_drop_empty(buf, nu);
+        if (dirty) { uint32_t unused; nu = warp_drop_empty(buf, nu, ws, &unused); }
         nu = warp_filter_ws(buf, nu, ws);
     }
     if (lane == 0) {
