@@ -321,10 +321,10 @@ def run_ours(args):
                 "traffic_source": traffic.get("capture") if traffic else None,
                 "note": "algorithmic bytes = what the reference's two-pointer merge streams per (sample, annotation, "
                         "contig) cell (SURVEY 8d); the kernel answers the same cells from one grid index over all "
-                        "tracks (a segment's candidates = one contiguous run of 8-byte entries) and touches only "
-                        "`traffic` DRAM bytes, so frac > 1 is expected: its real bound is the issue rate (1.76 G warp "
-                        "instructions per launch, issue slots 70 % busy; L2 serves 10.6 GB per launch at 87 % hits) "
-                        "(profiles/r01_count_kernel_v10.txt)",
+                        "tracks (a segment's candidates = one contiguous run of 8-byte entries, read two at a time) "
+                        "and touches only `traffic` DRAM bytes, so frac > 1 is expected: its real bound is the issue "
+                        "rate (1.44 G warp instructions per launch, issue slots 82 % busy; L2 serves ~11 GB per "
+                        "launch at 87 % hits) (profiles/r01_count_kernel_v16.txt)",
                 "algorithmic_bytes_per_launch": count_bytes, "kernel_ms": count_ms,
                 "kernel_share_of_step": prof["count"][0] / max(sum(v[0] for v in prof.values()), 1e-9),
                 "other_kernels": {"place_kernel_ms": place_ms, "contig_merge_kernel_ms": merge_ms,

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgat_b200.so")
+# GATB_LIB: another build of the same library (kernel tuning experiments), never a different implementation
+LIB_PATH = os.environ.get("GATB_LIB") or os.path.join(_HERE, "lib", "libgat_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_TOO_LARGE, ERR_RANGE = -1, -2, -3, -4, -5
