@@ -5,12 +5,13 @@
 // cut into ITEMS of 32 consecutive segments of one sample (lane = segment), handed to the warps through a
 // shared-memory counter, so that no warp waits for another.  A lane turns its segment into the run of
 // grid-index entries that can overlap it (count.cuh: two or three 4-byte loads); the warp then works the 32
-// runs off as ONE flat sequence of entries, 32 per round with every lane busy: which run a flat position
-// belongs to comes from a warp OR-reduction (redux.sync) of the runs' first positions, the run's segment
-// from a 16-byte shared-memory load.  Per entry: one 8-byte load, the overlap test, an integer atomic into
-// the (sample, track) accumulator.  Three items are in flight per warp -- segment load / bin-offset loads /
-// entry rounds -- and the entry loads run one round ahead: that is what hides the L2 latency of this
-// gather-bound kernel.  The index of one key (a few tens of MB at 1000 tracks) stays in L2 while the CTAs
+// runs off as ONE flat sequence of entry PAIRS (bins hold an even number of entries), 32 pairs per round with
+// every lane busy: which run a flat position belongs to comes from a warp OR-reduction (redux.sync) of the
+// runs' first positions, the run's segment from a 16-byte shared-memory load.  Per pair: one 16-byte load; per
+// entry the overlap test and an integer atomic into the (sample, track) accumulator.  Three items are in
+// flight per warp -- segment load / bin-offset loads / entry rounds -- and the rounds themselves run as a
+// branch-free three-stage pipeline (ownership, entry loads, counting), which hides the L2, shared-memory and
+// REDUX latencies of this gather-bound kernel.  The index of one key (a few tens of MB at 1000 tracks) stays in L2 while the CTAs
 // walk the keys in the same order.  The float64 nucleotide-density sum is formed per key from the integers,
 // in the same key order and with the same compensated summation as the reference's Python sum()
 // (gat/__init__.py:583-587).
@@ -413,10 +414,13 @@ cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int
 
 // ---------------------------------------------------------------------------------------------------
 // Grid index construction (replaces a host loop over every interval).
-//   1  bins_pass_kernel<false>: validate, and count the entries of every bin into boff[base + 1 + b]
-//   2  exclusive scan of boff[] (cub): boff[base + 1 + b] = first entry of bin b, boff[base] = of the key
-//   3  bins_pass_kernel<true>: entry position = atomicAdd(boff[base + 1 + b], 1); afterwards boff[base + 1 + b]
-//      is the END of bin b = the start of bin b + 1, i.e. boff[base + b] .. boff[base + b + 1] is bin b
+//   1  bins_pass_kernel<false>: validate, and count the entries of every bin into boff[base + 1 + b];
+//      bins_even_kernel rounds every count up to even
+//   2  exclusive scan of boff[] (cub): boff[base + 1 + b] = first slot of bin b, boff[base] = of the key,
+//      boff[n_boff] = slots needed (bins_total_kernel checks it against the capacity)
+//   3  bins_pass_kernel<true>: entry position = atomicAdd(boff[base + 1 + b], 1); bins_pad_kernel fills the
+//      spare slot of odd bins; afterwards boff[base + 1 + b] is the END of bin b = the start of bin b + 1,
+//      i.e. boff[base + b] .. boff[base + b + 1] is bin b
 // Thread = (key, rank slot j, track): with J = the longest list on the key, slot j of a list of n intervals
 // is interval j*n/J (if that differs from slot j+1's).  Consecutive threads are the same slot of consecutive
 // tracks, so the threads running at any time work on one neighbourhood of the key across all tracks and
