@@ -24,7 +24,8 @@ struct gatb_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaStream_t upload_stream = nullptr;   // gatb_annotations_create_async: copies + tile build, off the compute stream
+    cudaStream_t upload_stream = nullptr;   // gatb_annotations_create_async: copies (+ a rebuild), off the compute stream
+    cudaStream_t build_stream = nullptr;    // index build kernels, chunk by chunk behind the copies
     uint32_t *err_slots = nullptr;          // pinned words of pending asynchronous creates: 4 per set (validation, -, entries needed lo/hi)
     std::vector<int> err_free;
     std::string err;
@@ -152,6 +153,7 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, GATB_ERR_CUDA, cudaGetErrorString(e)); }
     ctx->stream = ctx->own_stream;
     e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->build_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->err_slots, 256 * 4 * sizeof(uint32_t));
     if (e != cudaSuccess) { cudaStreamDestroy(ctx->own_stream); delete ctx; return fail(nullptr, GATB_ERR_CUDA, cudaGetErrorString(e)); }
     for (int i = 255; i >= 0; i--) ctx->err_free.push_back(i);
@@ -184,6 +186,7 @@ extern "C" void gatb_destroy(gatb_ctx *ctx)
     delete ctx->scratch;
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+    if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
     if (ctx->err_slots) cudaFreeHost(ctx->err_slots);
     delete ctx;
 }
@@ -295,32 +298,50 @@ struct gatb_annotations {
     }
 };
 
-// queue (on the upload stream) the construction of the grid index from the device copies of the lists,
-// then the read-back of the validation word and of the number of entries the index needs
-static cudaError_t annotations_build(gatb_annotations *a)
+static void build_params(const gatb_annotations *a, BuildBinsParams &bp)
 {
-    gatb_ctx *ctx = a->ctx;
-    cudaStream_t st = ctx->upload_stream;
-    uint32_t *slot = ctx->err_slots + 4 * a->err_slot;
-    cudaError_t e = cudaMemsetAsync(a->d_err.p, 0, sizeof(uint32_t), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(a->d_total.p, 0, sizeof(unsigned long long), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(a->boff.p, 0, (a->n_boff + 1) * sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
-    BuildBinsParams bp;
     memset(&bp, 0, sizeof(bp));
     bp.offs = a->d_offs.p; bp.start = a->d_start.p; bp.end = a->d_end.p; bp.n_intervals = a->n_intervals;
     bp.keybins = a->keybins.p; bp.key_jmax = a->d_jmax.p; bp.jmax_all = a->jmax_all; bp.boff = a->boff.p; bp.n_boff = a->n_boff;
     bp.cent = a->cent.p; bp.civ = a->civ.p; bp.cprev = a->cprev.p; bp.capacity = a->capacity;
     bp.n_annot = a->n_annot; bp.n_keys = a->n_keys; bp.n_groups = a->n_groups; bp.ka = a->ka;
+    bp.a_begin = 0; bp.a_count = a->n_annot;
     bp.error = a->d_err.p; bp.total = a->d_total.p;
+}
+
+// queue on `st`: scan + fill of the index (the per-bin counts are in place), the read-back of the validation
+// word and of the number of entries the index needs, and the `ready` event
+static cudaError_t annotations_build_finish(gatb_annotations *a, cudaStream_t st)
+{
+    gatb_ctx *ctx = a->ctx;
+    uint32_t *slot = ctx->err_slots + 4 * a->err_slot;
+    BuildBinsParams bp;
+    build_params(a, bp);
+    cudaError_t e;
     {
         ProfScope ps(ctx, PROF_OTHER, st);
-        ctx->launches += 6;                 // count, even, scan (2), total, fill, pad
-        e = launch_build_bins(st, bp, a->scan_tmp.p, a->scan_tmp.n);
+        ctx->launches += 5;                 // even, scan (2), total, fill, pad
+        e = launch_bins_finish(st, bp, a->scan_tmp.p, a->scan_tmp.n);
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(slot, a->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(slot + 2, a->d_total.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaEventRecord(a->ready, st);
+    return e;
+}
+
+// queue (on the upload stream) the whole construction of the grid index from the device copies of the lists
+static cudaError_t annotations_build(gatb_annotations *a)
+{
+    gatb_ctx *ctx = a->ctx;
+    cudaStream_t st = ctx->upload_stream;
+    cudaError_t e = cudaMemsetAsync(a->d_err.p, 0, sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->d_total.p, 0, sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->boff.p, 0, (a->n_boff + 1) * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    BuildBinsParams bp;
+    build_params(a, bp);
+    { ProfScope ps(ctx, PROF_OTHER, st); e = launch_bins_count(st, bp); }
+    if (e == cudaSuccess) e = annotations_build_finish(a, st);
     return e;
 }
 
@@ -453,13 +474,42 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     if (e == cudaSuccess) e = a->cprev.alloc(a->capacity + 2);
     if (e == cudaSuccess) e = a->scan_tmp.alloc(build_bins_scan_bytes(n_boff + 1));
     if (e == cudaSuccess) e = a->d_offs.upload(offs, n_lists + 1, st);
-    if (e == cudaSuccess) e = a->d_start.upload(start, n_iv, st);
-    if (e == cudaSuccess) e = a->d_end.upload(end, n_iv, st);
+    if (e == cudaSuccess) e = a->d_start.alloc(n_iv);
+    if (e == cudaSuccess) e = a->d_end.alloc(n_iv);
     if (e == cudaSuccess) e = a->d_err.alloc(1);
     if (e == cudaSuccess) e = a->d_total.alloc(1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ready, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = annotations_build(a);
-    if (e != cudaSuccess) { cudaStreamSynchronize(st); delete a; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->d_err.p, 0, sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->d_total.p, 0, sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->boff.p, 0, (n_boff + 1) * sizeof(uint32_t), st);
+    // The intervals go up in chunks of tracks; the build stream counts the bin entries of a chunk (step 1 of
+    // the build) while the next chunk is still on the bus, and runs scan + fill behind the last one.
+    {
+        const uint32_t n_chunks = n_iv >= (4u << 20) ? std::min(4u, A) : 1u;
+        BuildBinsParams bp;
+        build_params(a, bp);
+        for (uint32_t c = 0; c < n_chunks && e == cudaSuccess; c++) {
+            const uint32_t a0 = (uint32_t)((uint64_t)A * c / n_chunks), a1 = (uint32_t)((uint64_t)A * (c + 1) / n_chunks);
+            const uint64_t i0 = offs[(uint64_t)a0 * K], i1 = offs[(uint64_t)a1 * K];
+            if (i1 > i0) {
+                e = cudaMemcpyAsync(a->d_start.p + i0, start + i0, (i1 - i0) * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(a->d_end.p + i0, end + i0, (i1 - i0) * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+            }
+            cudaEvent_t ev = nullptr;
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(ev, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->build_stream, ev, 0);
+            if (ev) cudaEventDestroy(ev);           // (released once it has completed)
+            bp.a_begin = a0; bp.a_count = a1 - a0;
+            if (e == cudaSuccess) { ProfScope ps(ctx, PROF_OTHER, ctx->build_stream); e = launch_bins_count(ctx->build_stream, bp); }
+        }
+        if (e == cudaSuccess) e = annotations_build_finish(a, ctx->build_stream);
+    }
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(st); cudaStreamSynchronize(ctx->build_stream);
+        delete a;
+        return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e));
+    }
     a->pending = true;
     *out = a;
     return GATB_OK;

@@ -434,9 +434,9 @@ __global__ void __launch_bounds__(256) bins_pass_kernel(BuildBinsParams p)
     const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t b0 = 1, b1 = 0, x = 0, y = 0, py = 0, t = 0;       // no bins unless there is a valid interval
     uint32_t *cur = nullptr;
-    if (id < J * p.n_annot) {
-        const uint64_t j = id / p.n_annot;
-        const uint32_t a = (uint32_t)(id % p.n_annot);
+    if (id < J * p.a_count) {
+        const uint64_t j = id / p.a_count;
+        const uint32_t a = p.a_begin + (uint32_t)(id % p.a_count);
         const uint64_t l = (uint64_t)a * p.n_keys + k;
         const uint64_t o0 = p.offs[l], n = p.offs[l + 1] - o0;
         const uint64_t r = j * n / J;
@@ -510,19 +510,29 @@ size_t build_bins_scan_bytes(uint64_t n_boff)
     return bytes;
 }
 
-cudaError_t launch_build_bins(cudaStream_t st, const BuildBinsParams &p, void *scan_tmp, size_t scan_bytes)
+// step 1 for the tracks [p.a_begin, p.a_begin + p.a_count): may be launched per chunk of tracks as their
+// intervals arrive on the device
+cudaError_t launch_bins_count(cudaStream_t st, const BuildBinsParams &p)
 {
-    if (p.n_intervals == 0 || p.n_boff == 0) return cudaSuccess;
-    if (p.jmax_all == 0) return cudaSuccess;
-    const dim3 blocks((unsigned)(((uint64_t)p.jmax_all * p.n_annot + 255) / 256), p.n_keys);
-    const unsigned nb = (unsigned)((p.n_boff + 255) / 256);
+    if (p.n_intervals == 0 || p.n_boff == 0 || p.jmax_all == 0 || p.a_count == 0) return cudaSuccess;
+    const dim3 blocks((unsigned)(((uint64_t)p.jmax_all * p.a_count + 255) / 256), p.n_keys);
     bins_pass_kernel<false><<<blocks, 256, 0, st>>>(p);
-    bins_even_kernel<<<nb, 256, 0, st>>>(p.boff, p.n_boff);
+    return cudaGetLastError();
+}
+
+// steps 2 and 3 (all tracks: p.a_begin = 0, p.a_count = n_annot)
+cudaError_t launch_bins_finish(cudaStream_t st, const BuildBinsParams &p, void *scan_tmp, size_t scan_bytes)
+{
+    const unsigned nb = (unsigned)((p.n_boff + 1 + 255) / 256);
+    if (p.n_boff) bins_even_kernel<<<nb, 256, 0, st>>>(p.boff, p.n_boff);
     cudaError_t e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, p.boff, p.boff, (int)(p.n_boff + 1), st);
     if (e != cudaSuccess) return e;
     bins_total_kernel<<<1, 1, 0, st>>>(p);
-    bins_pass_kernel<true><<<blocks, 256, 0, st>>>(p);
-    bins_pad_kernel<<<nb, 256, 0, st>>>(p);
+    if (p.n_intervals && p.n_boff && p.jmax_all) {
+        const dim3 blocks((unsigned)(((uint64_t)p.jmax_all * p.a_count + 255) / 256), p.n_keys);
+        bins_pass_kernel<true><<<blocks, 256, 0, st>>>(p);
+        bins_pad_kernel<<<nb, 256, 0, st>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -86,11 +86,13 @@ struct BuildBinsParams {
     uint32_t *cprev;
     uint64_t capacity;              // entries the arrays hold (even), + 2 for the sentinel pair
     uint32_t n_annot, n_keys, n_groups, ka;
+    uint32_t a_begin, a_count;      // tracks this launch works on
     uint32_t *error;
     unsigned long long *total;      // out: entries needed
 };
 size_t build_bins_scan_bytes(uint64_t n_boff);
-cudaError_t launch_build_bins(cudaStream_t st, const BuildBinsParams &p, void *scan_tmp, size_t scan_bytes);
+cudaError_t launch_bins_count(cudaStream_t st, const BuildBinsParams &p);
+cudaError_t launch_bins_finish(cudaStream_t st, const BuildBinsParams &p, void *scan_tmp, size_t scan_bytes);
 
 // counter: GATB_* id.  Returns cudaError from the launch configuration.
 cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int threads);
