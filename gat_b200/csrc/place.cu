@@ -72,10 +72,13 @@ __device__ __forceinline__ int insertion_point(const uint64_t *buf, uint32_t n, 
 
 // overshoot repair (gat/Engine.pyx:608-625): SegmentListSampler(U).sample(1) picks a base of U,
 // trim_ends (gat/SegmentList.pyx:545-597) removes `size` bases from that segment's start or end
+// -> *removed = workspace bases the trim took away, *emptied = segments it left empty
 __device__ __forceinline__ void warp_trim(uint64_t *buf, uint32_t nu, uint32_t size,
-                                          const Philox4 &b2, const Philox4 &b3)
+                                          const Philox4 &b2, const Philox4 &b3, const WsView &ws,
+                                          uint32_t *removed, uint32_t *emptied)
 {
     const int lane = lane_id();
+    uint32_t rem = 0, emp = 0;
     // total length of U
     uint32_t acc = 0;
     for (uint32_t i = lane; i < nu; i += 32) { uint64_t x = buf[i]; acc += seg_end(x) - seg_start(x); }
@@ -108,10 +111,15 @@ __device__ __forceinline__ void warp_trim(uint64_t *buf, uint32_t nu, uint32_t s
         while (sz > 0) {
             uint64_t y = buf[k];
             int32_t l = (int32_t)seg_end(y) - (int32_t)seg_start(y);
-            if (l < sz) { buf[k] = 0; sz -= l; }
+            const uint32_t before = ws_overlap(ws, seg_start(y), seg_end(y));
+            if (l < sz) { buf[k] = 0; sz -= l; rem += before; emp += (l > 0) ? 1u : 0u; }
             else {
-                if (forward) buf[k] = pack_seg(seg_start(y) + (uint32_t)sz, seg_end(y));
-                else buf[k] = pack_seg(seg_start(y), (uint32_t)((int32_t)seg_end(y) - sz));
+                uint64_t z;
+                if (forward) z = pack_seg(seg_start(y) + (uint32_t)sz, seg_end(y));
+                else z = pack_seg(seg_start(y), (uint32_t)((int32_t)seg_end(y) - sz));
+                buf[k] = z;
+                rem += before - ws_overlap(ws, seg_start(z), seg_end(z));
+                emp += (l == sz) ? 1u : 0u;
                 sz = 0;
             }
             if (forward) { k += 1; if (k == (int)nu) k = 0; }
@@ -119,6 +127,42 @@ __device__ __forceinline__ void warp_trim(uint64_t *buf, uint32_t nu, uint32_t s
         }
     }
     __syncwarp();
+    *removed = __shfl_sync(GATB_FULL, rem, 0);
+    *emptied = __shfl_sync(GATB_FULL, emp, 0);
+}
+
+// ONE new segment behind a sorted, merged list (the usual late checkpoint): when it touches neither
+// neighbour, merge(0) of the whole amounts to sliding it into place.  false: it does touch one (the general
+// insert-and-merge path takes over, nothing was changed).
+__device__ __forceinline__ bool warp_insert_one(uint64_t *buf, uint32_t &nu, const WsView &ws, uint32_t &cov)
+{
+    const int lane = lane_id();
+    const uint64_t key = buf[nu];
+    const uint32_t xs = seg_start(key), xe = seg_end(key);
+    if (xs == xe) return true;                      // empty: merge(0) drops it
+    uint32_t lo = 0, hi = nu;                       // elements with key <= the new one (same probes in every lane)
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (buf[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t pos = lo;
+    if (pos > 0 && seg_end(buf[pos - 1]) >= xs) return false;       // overlaps or touches its left neighbour
+    if (pos < nu && xe >= seg_start(buf[pos])) return false;        // ... its right neighbour
+    __syncwarp();
+    if (nu > pos) {
+        for (int c = (int)((nu - 1) >> 5); c >= (int)(pos >> 5); c--) {     // slide up by one, top chunk first
+            const uint32_t i = ((uint32_t)c << 5) + lane;
+            const uint64_t x = (i < nu) ? buf[i] : 0;
+            __syncwarp();
+            if (i < nu && i >= pos) buf[i + 1] = x;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) buf[pos] = key;
+    __syncwarp();
+    nu += 1;
+    cov += ws_overlap(ws, xs, xe);
+    return true;
 }
 
 // keep segments overlapping the workspace by >= 1 base (SegmentList.filter, gat/SegmentList.pyx:1401-1467)
@@ -188,6 +232,8 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
     int32_t remaining = d.ltotal, true_remaining = d.ltotal;
     int fails = 0;
     uint32_t nu = 0, np = 0, t0 = 0, status = 0;
+    uint32_t cov = 0;                   // workspace coverage of buf[0,nu) as of the last checkpoint / trim
+    uint32_t trim_emptied = 0;          // segments the last trim left empty
     bool dirty = false;
 
     if (d.tab_n > 0 && p.sampler_kind == 1) {
@@ -220,7 +266,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
                 // buffer full: merge now.  merge(0) is idempotent and associative on the set of
                 // accepted placements, so an early merge does not change any later result.
                 __syncwarp();
-                nu = warp_sort_merge0(buf, nu + np);
+                nu = warp_sort_merge0(buf, nu + np, nullptr, nullptr, &ws, &cov);
                 np = 0; dirty = false;
                 if (nu + 33 > d.cap) { status |= UNIT_OVERFLOW; break; }
             }
@@ -237,9 +283,10 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
             // late checkpoints add a handful of placements to an already merged list: insert them
             // instead of re-sorting everything (same result, see warp_insert_merge0)
             // the merge pass of every variant also returns the workspace coverage of the merged list
-            uint32_t cov = 0;
-            if (dirty && np == 0) nu = warp_drop_empty(buf, nu, ws, &cov);      // straight after a trim
-            else if (nu > 0 && np < 32 && !dirty) nu = warp_insert_merge0(buf, nu, np, &ws, &cov);
+            if (dirty && np == 0) {                 // straight after a trim: still sorted and merged
+                if (trim_emptied) nu = warp_drop_empty(buf, nu, ws, &cov);
+            } else if (nu > 0 && np == 1 && !dirty && warp_insert_one(buf, nu, ws, cov)) {
+            } else if (nu > 0 && np < 32 && !dirty) nu = warp_insert_merge0(buf, nu, np, &ws, &cov);
             else {
                 const uint32_t n = nu + np;         // the free upper part of the buffer is the sort's scratch
                 nu = warp_sort_merge0(buf, n, 2u * n <= d.cap ? buf + n : nullptr, cnt, &ws, &cov);
@@ -251,7 +298,9 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
             if (true_remaining < 0) {           // overshoot (gat/Engine.pyx:608-625)
                 Philox4 b2 = philox4x32_10(t0, 2u | c1base, unit, sample, k0, k1);
                 Philox4 b3 = philox4x32_10(t0, 3u | c1base, unit, sample, k0, k1);
-                warp_trim(buf, nu, (uint32_t)(-true_remaining), b2, b3);
+                uint32_t removed;
+                warp_trim(buf, nu, (uint32_t)(-true_remaining), b2, b3, ws, &removed, &trim_emptied);
+                cov -= removed;
                 dirty = true;
                 true_remaining = 1;
                 t0 += 1;
@@ -272,7 +321,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
         // result = unintersected.merge(0).filter(workspace) (gat/Engine.pyx:639-646); placements
         // still pending (appended after the last checkpoint) are dropped, as in the reference
         __syncwarp();
-        if (dirty) { uint32_t unused; nu = warp_drop_empty(buf, nu, ws, &unused); }
+        if (dirty && trim_emptied) nu = warp_drop_empty(buf, nu, ws, &cov);
         nu = warp_filter_ws(buf, nu, ws);
     }
     if (lane == 0) {
