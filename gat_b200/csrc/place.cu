@@ -72,13 +72,14 @@ __device__ __forceinline__ int insertion_point(const uint64_t *buf, uint32_t n, 
 
 // overshoot repair (gat/Engine.pyx:608-625): SegmentListSampler(U).sample(1) picks a base of U,
 // trim_ends (gat/SegmentList.pyx:545-597) removes `size` bases from that segment's start or end
-// -> *removed = workspace bases the trim took away, *emptied = segments it left empty
+// -> *removed = workspace bases the trim took away, *emptied = segments it left empty, *orphaned = segments
+// it left non-empty but without a base in the workspace
 __device__ __forceinline__ void warp_trim(uint64_t *buf, uint32_t nu, uint32_t size,
                                           const Philox4 &b2, const Philox4 &b3, const WsView &ws,
-                                          uint32_t *removed, uint32_t *emptied)
+                                          uint32_t *removed, uint32_t *emptied, uint32_t *orphaned)
 {
     const int lane = lane_id();
-    uint32_t rem = 0, emp = 0;
+    uint32_t rem = 0, emp = 0, orph = 0;
     // total length of U
     uint32_t acc = 0;
     for (uint32_t i = lane; i < nu; i += 32) { uint64_t x = buf[i]; acc += seg_end(x) - seg_start(x); }
@@ -118,8 +119,10 @@ __device__ __forceinline__ void warp_trim(uint64_t *buf, uint32_t nu, uint32_t s
                 if (forward) z = pack_seg(seg_start(y) + (uint32_t)sz, seg_end(y));
                 else z = pack_seg(seg_start(y), (uint32_t)((int32_t)seg_end(y) - sz));
                 buf[k] = z;
-                rem += before - ws_overlap(ws, seg_start(z), seg_end(z));
+                const uint32_t after = ws_overlap(ws, seg_start(z), seg_end(z));
+                rem += before - after;
                 emp += (l == sz) ? 1u : 0u;
+                orph += (l != sz && after == 0u) ? 1u : 0u;
                 sz = 0;
             }
             if (forward) { k += 1; if (k == (int)nu) k = 0; }
@@ -129,6 +132,7 @@ __device__ __forceinline__ void warp_trim(uint64_t *buf, uint32_t nu, uint32_t s
     __syncwarp();
     *removed = __shfl_sync(GATB_FULL, rem, 0);
     *emptied = __shfl_sync(GATB_FULL, emp, 0);
+    *orphaned = __shfl_sync(GATB_FULL, orph, 0);
 }
 
 // ONE new segment behind a sorted, merged list (the usual late checkpoint): when it touches neither
@@ -234,6 +238,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
     uint32_t nu = 0, np = 0, t0 = 0, status = 0;
     uint32_t cov = 0;                   // workspace coverage of buf[0,nu) as of the last checkpoint / trim
     uint32_t trim_emptied = 0;          // segments the last trim left empty
+    uint32_t orphans = 0;               // segments any trim left outside the workspace
     bool dirty = false;
 
     if (d.tab_n > 0 && p.sampler_kind == 1) {
@@ -298,9 +303,9 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
             if (true_remaining < 0) {           // overshoot (gat/Engine.pyx:608-625)
                 Philox4 b2 = philox4x32_10(t0, 2u | c1base, unit, sample, k0, k1);
                 Philox4 b3 = philox4x32_10(t0, 3u | c1base, unit, sample, k0, k1);
-                uint32_t removed;
-                warp_trim(buf, nu, (uint32_t)(-true_remaining), b2, b3, ws, &removed, &trim_emptied);
-                cov -= removed;
+                uint32_t removed, orphaned;
+                warp_trim(buf, nu, (uint32_t)(-true_remaining), b2, b3, ws, &removed, &trim_emptied, &orphaned);
+                cov -= removed; orphans += orphaned;
                 dirty = true;
                 true_remaining = 1;
                 t0 += 1;
@@ -322,7 +327,9 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
         // still pending (appended after the last checkpoint) are dropped, as in the reference
         __syncwarp();
         if (dirty && trim_emptied) nu = warp_drop_empty(buf, nu, ws, &cov);
-        nu = warp_filter_ws(buf, nu, ws);
+        // every placement has a base in the workspace piece it was drawn for, hence so has every merged
+        // segment: only a trim can have left one outside
+        if (orphans) nu = warp_filter_ws(buf, nu, ws);
     }
     if (lane == 0) {
         uint32_t slot = p.out_by_contig ? d.contig : unit;
