@@ -203,12 +203,13 @@ __device__ __forceinline__ uint32_t ws_overlap(const WsView &w, uint32_t s, uint
 // With `ws` and `cov` the pass also returns the workspace coverage of the merged list
 // (intersect(workspace).sum(), gat/Engine.pyx:593-599): element i adds the workspace bases of
 // [max(start_i, running max end), end_i), the part of it that no earlier element covers.
+// and `len` the total length of the merged list.
 __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n, const WsView *ws = nullptr,
-                                                       uint32_t *cov = nullptr)
+                                                       uint32_t *cov = nullptr, uint32_t *len = nullptr)
 {
     const int lane = lane_id();
     int32_t carry = -1;          // running max end of everything seen (int32 like the reference)
-    uint32_t nout = 0, covered = 0;
+    uint32_t nout = 0, covered = 0, length = 0;
     for (uint32_t b0 = 0; b0 < n; b0 += 32) {
         uint32_t i = b0 + lane;
         uint64_t x = (i < n) ? buf[i] : 0;
@@ -221,7 +222,10 @@ __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n
         int32_t prev_max = max(carry, excl);
         if (ws != nullptr && valid) {
             const int32_t lo = max(s, prev_max);
-            if (e > lo) covered += ws_cov(*ws, (uint32_t)e) - ws_cov(*ws, (uint32_t)lo);
+            if (e > lo) {
+                covered += ws_cov(*ws, (uint32_t)e) - ws_cov(*ws, (uint32_t)lo);
+                length += (uint32_t)(e - lo);
+            }
         }
         bool head = valid && (s > prev_max);
         uint32_t hmask = __ballot_sync(GATB_FULL, head);
@@ -238,6 +242,7 @@ __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n
     }
     if (nout > 0 && lane == 0) reinterpret_cast<uint32_t *>(buf + nout - 1)[0] = (uint32_t)carry;
     if (cov != nullptr) *cov = __reduce_add_sync(GATB_FULL, covered);
+    if (len != nullptr) *len = __reduce_add_sync(GATB_FULL, length);
     __syncwarp();
     return nout;
 }
@@ -252,16 +257,22 @@ __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n
 // the result is the same sequence either way.
 constexpr uint32_t GATB_SORT_NB = 512;
 
-__device__ __forceinline__ bool warp_bucket_sort(uint64_t *buf, uint32_t n, uint64_t *tmp, uint32_t *cnt)
+// `range_lo` <= every start, `range_hi` ~ the largest (starts beyond it share the last bucket): when the
+// caller knows them (range_hi > range_lo) the min / max pass over the keys is skipped.
+__device__ __forceinline__ bool warp_bucket_sort(uint64_t *buf, uint32_t n, uint64_t *tmp, uint32_t *cnt,
+                                                 uint32_t range_lo = 0, uint32_t range_hi = 0)
 {
     const int lane = lane_id();
-    uint32_t lo = 0xffffffffu, hi = 0u;
-    for (uint32_t i = lane; i < n; i += 32) {
-        const uint32_t s = seg_start(buf[i]);
-        lo = min(lo, s); hi = max(hi, s);
+    uint32_t lo = range_lo, hi = range_hi;
+    if (range_hi <= range_lo) {
+        lo = 0xffffffffu; hi = 0u;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t s = seg_start(buf[i]);
+            lo = min(lo, s); hi = max(hi, s);
+        }
+        lo = __reduce_min_sync(GATB_FULL, lo);
+        hi = __reduce_max_sync(GATB_FULL, hi);
     }
-    lo = __reduce_min_sync(GATB_FULL, lo);
-    hi = __reduce_max_sync(GATB_FULL, hi);
     const uint32_t NB = min(GATB_SORT_NB, max(64u, next_pow2(n)));
     const uint64_t q = ((uint64_t)NB << 32) / ((uint64_t)(hi - lo) + 1u);
     const uint32_t inv = q > 0xffffffffull ? 0xffffffffu : (uint32_t)q;
@@ -305,17 +316,18 @@ __device__ __forceinline__ bool warp_bucket_sort(uint64_t *buf, uint32_t n, uint
 // `tmp` (n more free slots) and `cnt` given, mid-sized runs take the counting sort
 __device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n, uint64_t *tmp = nullptr,
                                                      uint32_t *cnt = nullptr, const WsView *ws = nullptr,
-                                                     uint32_t *cov = nullptr)
+                                                     uint32_t *cov = nullptr, uint32_t *len = nullptr,
+                                                     uint32_t range_lo = 0, uint32_t range_hi = 0)
 {
-    if (n == 0) { if (cov != nullptr) *cov = 0; return 0; }
+    if (n == 0) { if (cov != nullptr) *cov = 0; if (len != nullptr) *len = 0; return 0; }
     const int lane = lane_id();
-    if (tmp != nullptr && n >= 96u && n <= 32768u && warp_bucket_sort(buf, n, tmp, cnt))
-        return warp_merge0_sorted(buf, n, ws, cov);
+    if (tmp != nullptr && n >= 96u && n <= 32768u && warp_bucket_sort(buf, n, tmp, cnt, range_lo, range_hi))
+        return warp_merge0_sorted(buf, n, ws, cov, len);
     uint32_t N = next_pow2(n);
     for (uint32_t i = n + lane; i < N; i += 32) buf[i] = GATB_KEY_INF;
     __syncwarp();
     warp_bitonic_sort(buf, N);
-    return warp_merge0_sorted(buf, n, ws, cov);
+    return warp_merge0_sorted(buf, n, ws, cov, len);
 }
 
 // merge(0) of a sorted, merged run U = buf[0,nu) with np <= 32 new segments stored behind it
@@ -325,7 +337,8 @@ __device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n, 
 // keys are dropped into the gaps and the usual merge(0) scan runs once.  O(nu/32) instead of a
 // full bitonic sort.  Same result as warp_sort_merge0(buf, nu + np).
 __device__ __forceinline__ uint32_t warp_insert_merge0(uint64_t *buf, uint32_t nu, uint32_t np,
-                                                       const WsView *ws = nullptr, uint32_t *cov = nullptr)
+                                                       const WsView *ws = nullptr, uint32_t *cov = nullptr,
+                                                       uint32_t *len = nullptr)
 {
     const int lane = lane_id();
     uint64_t key = ((uint32_t)lane < np) ? buf[nu + lane] : GATB_KEY_INF;
@@ -368,7 +381,7 @@ __device__ __forceinline__ uint32_t warp_insert_merge0(uint64_t *buf, uint32_t n
     }
     if ((uint32_t)lane < np) buf[pos + lane] = key;
     __syncwarp();
-    return warp_merge0_sorted(buf, nu + np, ws, cov);
+    return warp_merge0_sorted(buf, nu + np, ws, cov, len);
 }
 
 #endif  // __CUDACC__

@@ -74,16 +74,13 @@ __device__ __forceinline__ int insertion_point(const uint64_t *buf, uint32_t n, 
 // trim_ends (gat/SegmentList.pyx:545-597) removes `size` bases from that segment's start or end
 // -> *removed = workspace bases the trim took away, *emptied = segments it left empty, *orphaned = segments
 // it left non-empty but without a base in the workspace
-__device__ __forceinline__ void warp_trim(uint64_t *buf, uint32_t nu, uint32_t size,
+// `total` = total length of U (kept by the caller from checkpoint to checkpoint)
+__device__ __forceinline__ void warp_trim(uint64_t *buf, uint32_t nu, uint32_t size, uint32_t total,
                                           const Philox4 &b2, const Philox4 &b3, const WsView &ws,
                                           uint32_t *removed, uint32_t *emptied, uint32_t *orphaned)
 {
     const int lane = lane_id();
     uint32_t rem = 0, emp = 0, orph = 0;
-    // total length of U
-    uint32_t acc = 0;
-    for (uint32_t i = lane; i < nu; i += 32) { uint64_t x = buf[i]; acc += seg_end(x) - seg_start(x); }
-    uint32_t total = __reduce_add_sync(GATB_FULL, acc);
     uint32_t r = bounded_u32(b2.x, b2.y, total);
     // first idx with inclusive cumulative length > r
     uint32_t running = 0, idx = nu;
@@ -138,7 +135,8 @@ __device__ __forceinline__ void warp_trim(uint64_t *buf, uint32_t nu, uint32_t s
 // ONE new segment behind a sorted, merged list (the usual late checkpoint): when it touches neither
 // neighbour, merge(0) of the whole amounts to sliding it into place.  false: it does touch one (the general
 // insert-and-merge path takes over, nothing was changed).
-__device__ __forceinline__ bool warp_insert_one(uint64_t *buf, uint32_t &nu, const WsView &ws, uint32_t &cov)
+__device__ __forceinline__ bool warp_insert_one(uint64_t *buf, uint32_t &nu, const WsView &ws, uint32_t &cov,
+                                                uint32_t &ulen)
 {
     const int lane = lane_id();
     const uint64_t key = buf[nu];
@@ -166,6 +164,7 @@ __device__ __forceinline__ bool warp_insert_one(uint64_t *buf, uint32_t &nu, con
     __syncwarp();
     nu += 1;
     cov += ws_overlap(ws, xs, xe);
+    ulen += xe - xs;
     return true;
 }
 
@@ -233,10 +232,19 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
     const uint32_t c1base = p.track << 8;
 
+    // every placement starts in [first workspace start - longest length, last workspace end): the range of
+    // the counting sort's buckets, known without a pass over the keys
+    uint32_t sort_lo = 0, sort_hi = 0;
+    if (d.tab_n > 0) {
+        const uint32_t lmax = tab[d.tab_n - 1] + d.bucket, w0 = ws.start[0];
+        sort_lo = w0 > lmax ? w0 - lmax : 0u;
+        sort_hi = ws.end[ws.n - 1];
+    }
     int32_t remaining = d.ltotal, true_remaining = d.ltotal;
     int fails = 0;
     uint32_t nu = 0, np = 0, t0 = 0, status = 0;
     uint32_t cov = 0;                   // workspace coverage of buf[0,nu) as of the last checkpoint / trim
+    uint32_t ulen = 0;                  // its total length
     uint32_t trim_emptied = 0;          // segments the last trim left empty
     uint32_t orphans = 0;               // segments any trim left outside the workspace
     bool dirty = false;
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
                 // buffer full: merge now.  merge(0) is idempotent and associative on the set of
                 // accepted placements, so an early merge does not change any later result.
                 __syncwarp();
-                nu = warp_sort_merge0(buf, nu + np, nullptr, nullptr, &ws, &cov);
+                nu = warp_sort_merge0(buf, nu + np, nullptr, nullptr, &ws, &cov, &ulen);
                 np = 0; dirty = false;
                 if (nu + 33 > d.cap) { status |= UNIT_OVERFLOW; break; }
             }
@@ -290,11 +298,12 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
             // the merge pass of every variant also returns the workspace coverage of the merged list
             if (dirty && np == 0) {                 // straight after a trim: still sorted and merged
                 if (trim_emptied) nu = warp_drop_empty(buf, nu, ws, &cov);
-            } else if (nu > 0 && np == 1 && !dirty && warp_insert_one(buf, nu, ws, cov)) {
-            } else if (nu > 0 && np < 32 && !dirty) nu = warp_insert_merge0(buf, nu, np, &ws, &cov);
+            } else if (nu > 0 && np == 1 && !dirty && warp_insert_one(buf, nu, ws, cov, ulen)) {
+            } else if (nu > 0 && np < 32 && !dirty) nu = warp_insert_merge0(buf, nu, np, &ws, &cov, &ulen);
             else {
                 const uint32_t n = nu + np;         // the free upper part of the buffer is the sort's scratch
-                nu = warp_sort_merge0(buf, n, 2u * n <= d.cap ? buf + n : nullptr, cnt, &ws, &cov);
+                nu = warp_sort_merge0(buf, n, 2u * n <= d.cap ? buf + n : nullptr, cnt, &ws, &cov, &ulen,
+                                      sort_lo, sort_hi);
             }
             np = 0; dirty = false;
             remaining = d.ltotal - (int32_t)cov;
@@ -304,8 +313,9 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
                 Philox4 b2 = philox4x32_10(t0, 2u | c1base, unit, sample, k0, k1);
                 Philox4 b3 = philox4x32_10(t0, 3u | c1base, unit, sample, k0, k1);
                 uint32_t removed, orphaned;
-                warp_trim(buf, nu, (uint32_t)(-true_remaining), b2, b3, ws, &removed, &trim_emptied, &orphaned);
+                warp_trim(buf, nu, (uint32_t)(-true_remaining), ulen, b2, b3, ws, &removed, &trim_emptied, &orphaned);
                 cov -= removed; orphans += orphaned;
+                ulen -= (uint32_t)(-true_remaining);
                 dirty = true;
                 true_remaining = 1;
                 t0 += 1;
