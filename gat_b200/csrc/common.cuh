@@ -257,29 +257,48 @@ __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n
 // the result is the same sequence either way.
 constexpr uint32_t GATB_SORT_NB = 512;
 
-// `range_lo` <= every start, `range_hi` ~ the largest (starts beyond it share the last bucket): when the
-// caller knows them (range_hi > range_lo) the min / max pass over the keys is skipped.
+// A plan = bucket range and count.  The caller may fix it beforehand (`plan`: lo <= every start, starts beyond
+// the range share the last bucket) -- that saves the min / max pass over the keys -- and may even have
+// counted the keys into `cnt` as it produced them (`prehist`), which saves the histogram pass as well.
+struct SortPlan { uint32_t lo, inv, nb; };
+
+__device__ __forceinline__ SortPlan make_sort_plan(uint32_t n, uint32_t lo, uint32_t hi)
+{
+    SortPlan pl;
+    pl.lo = lo;
+    pl.nb = min(GATB_SORT_NB, max(64u, next_pow2(n) >> 1));
+    const uint64_t q = ((uint64_t)pl.nb << 32) / ((uint64_t)(hi - lo) + 1u);
+    pl.inv = q > 0xffffffffull ? 0xffffffffu : (uint32_t)q;
+    return pl;
+}
+
+__device__ __forceinline__ uint32_t sort_bucket(const SortPlan &pl, uint32_t start)
+{
+    return min(__umulhi(start - pl.lo, pl.inv), pl.nb - 1u);
+}
+
 __device__ __forceinline__ bool warp_bucket_sort(uint64_t *buf, uint32_t n, uint64_t *tmp, uint32_t *cnt,
-                                                 uint32_t range_lo = 0, uint32_t range_hi = 0)
+                                                 const SortPlan *plan = nullptr, bool prehist = false)
 {
     const int lane = lane_id();
-    uint32_t lo = range_lo, hi = range_hi;
-    if (range_hi <= range_lo) {
-        lo = 0xffffffffu; hi = 0u;
+    SortPlan pl;
+    if (plan != nullptr) pl = *plan;
+    else {
+        uint32_t lo = 0xffffffffu, hi = 0u;
         for (uint32_t i = lane; i < n; i += 32) {
             const uint32_t s = seg_start(buf[i]);
             lo = min(lo, s); hi = max(hi, s);
         }
         lo = __reduce_min_sync(GATB_FULL, lo);
         hi = __reduce_max_sync(GATB_FULL, hi);
+        pl = make_sort_plan(n, lo, hi);
     }
-    const uint32_t NB = min(GATB_SORT_NB, max(64u, next_pow2(n)));
-    const uint64_t q = ((uint64_t)NB << 32) / ((uint64_t)(hi - lo) + 1u);
-    const uint32_t inv = q > 0xffffffffull ? 0xffffffffu : (uint32_t)q;
-    for (uint32_t b = lane; b < NB; b += 32) cnt[b] = 0u;
-    __syncwarp();
-    for (uint32_t i = lane; i < n; i += 32)
-        atomicAdd(&cnt[min(__umulhi(seg_start(buf[i]) - lo, inv), NB - 1u)], 1u);
+    const uint32_t NB = pl.nb;
+    if (!prehist) {
+        for (uint32_t b = lane; b < NB; b += 32) cnt[b] = 0u;
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) atomicAdd(&cnt[sort_bucket(pl, seg_start(buf[i]))], 1u);
+    }
     __syncwarp();
     uint32_t base = 0, mx = 0;                      // counts -> exclusive offsets, 32 buckets at a time
     for (uint32_t r = 0; r < NB; r += 32) {
@@ -294,12 +313,12 @@ __device__ __forceinline__ bool warp_bucket_sort(uint64_t *buf, uint32_t n, uint
     if (mx > 64u && mx > 8u * (n / NB + 1u)) return false;
     for (uint32_t i = lane; i < n; i += 32) {
         const uint64_t key = buf[i];
-        tmp[atomicAdd(&cnt[min(__umulhi(seg_start(key) - lo, inv), NB - 1u)], 1u)] = key;
+        tmp[atomicAdd(&cnt[sort_bucket(pl, seg_start(key))], 1u)] = key;
     }
     __syncwarp();                                   // now cnt[b] = end of bucket b = start of bucket b + 1
     for (uint32_t j = lane; j < n; j += 32) {
         const uint64_t key = tmp[j];
-        const uint32_t b = min(__umulhi(seg_start(key) - lo, inv), NB - 1u);
+        const uint32_t b = sort_bucket(pl, seg_start(key));
         const uint32_t first = b ? cnt[b - 1u] : 0u, last = cnt[b];
         uint32_t r = 0;
         for (uint32_t k = first; k < last; k++) {
@@ -317,11 +336,11 @@ __device__ __forceinline__ bool warp_bucket_sort(uint64_t *buf, uint32_t n, uint
 __device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n, uint64_t *tmp = nullptr,
                                                      uint32_t *cnt = nullptr, const WsView *ws = nullptr,
                                                      uint32_t *cov = nullptr, uint32_t *len = nullptr,
-                                                     uint32_t range_lo = 0, uint32_t range_hi = 0)
+                                                     const SortPlan *plan = nullptr, bool prehist = false)
 {
     if (n == 0) { if (cov != nullptr) *cov = 0; if (len != nullptr) *len = 0; return 0; }
     const int lane = lane_id();
-    if (tmp != nullptr && n >= 96u && n <= 32768u && warp_bucket_sort(buf, n, tmp, cnt, range_lo, range_hi))
+    if (tmp != nullptr && n >= 96u && n <= 32768u && warp_bucket_sort(buf, n, tmp, cnt, plan, prehist))
         return warp_merge0_sorted(buf, n, ws, cov, len);
     uint32_t N = next_pow2(n);
     for (uint32_t i = n + lane; i < N; i += 32) buf[i] = GATB_KEY_INF;

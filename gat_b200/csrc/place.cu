@@ -234,11 +234,18 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
 
     // every placement starts in [first workspace start - longest length, last workspace end): the range of
     // the counting sort's buckets, known without a pass over the keys
-    uint32_t sort_lo = 0, sort_hi = 0;
+    // (and as many placements as segments are expected): the sort's plan is fixed now, and the bulk phase
+    // counts every placement it accepts into the plan's buckets, so the first checkpoint's sort starts with
+    // its histogram done
+    SortPlan plan;
+    plan.lo = 0; plan.inv = 0; plan.nb = 0;
+    bool prehist = false;
     if (d.tab_n > 0) {
         const uint32_t lmax = tab[d.tab_n - 1] + d.bucket, w0 = ws.start[0];
-        sort_lo = w0 > lmax ? w0 - lmax : 0u;
-        sort_hi = ws.end[ws.n - 1];
+        plan = make_sort_plan(d.tab_n, w0 > lmax ? w0 - lmax : 0u, ws.end[ws.n - 1]);
+        for (uint32_t b = lane; b < plan.nb; b += 32) cnt[b] = 0u;
+        __syncwarp();
+        prehist = p.sampler_kind == 0;
     }
     int32_t remaining = d.ltotal, true_remaining = d.ltotal;
     int fails = 0;
@@ -270,20 +277,31 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
             int32_t incl = 0;
             if (!certain) {
                 t = draw_turn(d, ws, tab, t0 + lane, c1base, unit, sample, k0, k1);
-                incl = warp_incl_scan_add(t.ov);
-                int32_t rem_before = remaining - (incl - t.ov);
-                uint32_t trig = __ballot_sync(GATB_FULL, rem_before <= (int32_t)t.L);
-                f = trig ? (uint32_t)__ffs(trig) - 1 : 32u;
+                // no turn can trigger while what is left after ALL 32 still exceeds the longest of their lengths
+                // (two warp reductions instead of the prefix scan: the usual case until the unit is nearly full)
+                const int32_t all = __reduce_add_sync(GATB_FULL, t.ov);
+                if (remaining - all > (int32_t)__reduce_max_sync(GATB_FULL, t.L)) {
+                    f = 32u;
+                    incl = all;                     // (only lane 31's value is read below)
+                } else {
+                    incl = warp_incl_scan_add(t.ov);
+                    int32_t rem_before = remaining - (incl - t.ov);
+                    uint32_t trig = __ballot_sync(GATB_FULL, rem_before <= (int32_t)t.L);
+                    f = trig ? (uint32_t)__ffs(trig) - 1 : 32u;
+                }
             }
             if (nu + np + f + 1 > d.cap) {
                 // buffer full: merge now.  merge(0) is idempotent and associative on the set of
                 // accepted placements, so an early merge does not change any later result.
                 __syncwarp();
                 nu = warp_sort_merge0(buf, nu + np, nullptr, nullptr, &ws, &cov, &ulen);
-                np = 0; dirty = false;
+                np = 0; dirty = false; prehist = false;
                 if (nu + 33 > d.cap) { status |= UNIT_OVERFLOW; break; }
             }
-            if ((uint32_t)lane < f) buf[nu + np + lane] = pack_seg(t.start, t.end);
+            if ((uint32_t)lane < f) {
+                buf[nu + np + lane] = pack_seg(t.start, t.end);
+                if (prehist) atomicAdd(&cnt[sort_bucket(plan, t.start)], 1u);
+            }
             if (f > 0) remaining -= __shfl_sync(GATB_FULL, incl, (int)f - 1);
             np += f; t0 += f;
             if (f == 32) continue;
@@ -303,7 +321,8 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
             else {
                 const uint32_t n = nu + np;         // the free upper part of the buffer is the sort's scratch
                 nu = warp_sort_merge0(buf, n, 2u * n <= d.cap ? buf + n : nullptr, cnt, &ws, &cov, &ulen,
-                                      sort_lo, sort_hi);
+                                      &plan, prehist && nu == 0);
+                prehist = false;
             }
             np = 0; dirty = false;
             remaining = d.ltotal - (int32_t)cov;
