@@ -210,9 +210,13 @@ __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n
     const int lane = lane_id();
     int32_t carry = -1;          // running max end of everything seen (int32 like the reference)
     uint32_t nout = 0, covered = 0, length = 0;
+    // the element of the NEXT chunk is requested before this chunk's scan (the writes below stay behind the
+    // chunk being read, so reading ahead is safe): the load latency hides behind the shuffles
+    uint64_t ahead = ((uint32_t)lane < n) ? buf[lane] : 0;
     for (uint32_t b0 = 0; b0 < n; b0 += 32) {
         uint32_t i = b0 + lane;
-        uint64_t x = (i < n) ? buf[i] : 0;
+        uint64_t x = ahead;
+        ahead = (i + 32u < n) ? buf[i + 32u] : 0;
         int32_t s = (int32_t)seg_start(x), e = (int32_t)seg_end(x);
         bool valid = (i < n) && (s != e);
         int32_t ev = valid ? e : -1;
@@ -316,16 +320,29 @@ __device__ __forceinline__ bool warp_bucket_sort(uint64_t *buf, uint32_t n, uint
         tmp[atomicAdd(&cnt[sort_bucket(pl, seg_start(key))], 1u)] = key;
     }
     __syncwarp();                                   // now cnt[b] = end of bucket b = start of bucket b + 1
-    for (uint32_t j = lane; j < n; j += 32) {
-        const uint64_t key = tmp[j];
-        const uint32_t b = sort_bucket(pl, seg_start(key));
-        const uint32_t first = b ? cnt[b - 1u] : 0u, last = cnt[b];
-        uint32_t r = 0;
-        for (uint32_t k = first; k < last; k++) {
-            const uint64_t other = tmp[k];
-            r += (other < key || (other == key && k < j)) ? 1u : 0u;
+    // rank inside the bucket; two keys per lane and pass, so that their dependent loads (key -> bucket bounds
+    // -> bucket mates) overlap
+    for (uint32_t j0 = lane; j0 < n; j0 += 64) {
+        const uint32_t j1 = j0 + 32u;
+        const bool has1 = j1 < n;
+        const uint64_t key0 = tmp[j0], key1 = has1 ? tmp[j1] : 0ull;
+        const uint32_t b0 = sort_bucket(pl, seg_start(key0)), b1 = has1 ? sort_bucket(pl, seg_start(key1)) : 0u;
+        const uint32_t first0 = b0 ? cnt[b0 - 1u] : 0u, last0 = cnt[b0];
+        const uint32_t first1 = has1 ? (b1 ? cnt[b1 - 1u] : 0u) : 0u, last1 = has1 ? cnt[b1] : 0u;
+        const uint32_t m0 = last0 - first0, m1 = last1 - first1;
+        uint32_t r0 = 0, r1 = 0;
+        for (uint32_t t = 0; t < max(m0, m1); t++) {
+            if (t < m0) {
+                const uint64_t other = tmp[first0 + t];
+                r0 += (other < key0 || (other == key0 && first0 + t < j0)) ? 1u : 0u;
+            }
+            if (t < m1) {
+                const uint64_t other = tmp[first1 + t];
+                r1 += (other < key1 || (other == key1 && first1 + t < j1)) ? 1u : 0u;
+            }
         }
-        buf[first + r] = key;
+        buf[first0 + r0] = key0;
+        if (has1) buf[first1 + r1] = key1;
     }
     __syncwarp();
     return true;
