@@ -1,0 +1,40 @@
+"""Randomised placement parity beyond the test suite's budget: many random units (tests/helpers.random_unit),
+every sample compared bit for bit with the oracle under the same Philox stream -- verification aid
+
+    python tools/stress_place.py [n_units] [seed]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import helpers  # noqa: E402
+from gat_b200 import device  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+n_units = int(sys.argv[1]) if len(sys.argv) > 1 else 600
+seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 2024
+rng = np.random.default_rng(seed0)
+ctx = device.Context(0)
+ntrim = ncp = nround = 0
+for it in range(n_units):
+    segs, ws = helpers.random_unit(rng)
+    bucket = int(rng.choice([1, 1, 1, 3, 7]))
+    smp = device.Sampler(ctx, [0], 1, False, [segs], [ws], bucket_size=bucket, nbuckets=100000)
+    n = 8
+    placed, status = smp.place(seed=seed0 + it, track=it % 5, sample_begin=100, n_samples=n)
+    smp.close()
+    for s in range(n):
+        exp, info = oracle.sampler_annotator_philox(segs, ws, seed0 + it, it % 5, 0, 100 + s, bucket_size=bucket)
+        ntrim += info.ntrims
+        ncp += info.ncheckpoints
+        nround += info.nunsuccessful >= 20
+        if not np.array_equal(placed[s][0], exp):
+            print("MISMATCH unit %i sample %i" % (it, s), placed[s][0][:4], exp[:4])
+            sys.exit(1)
+print("ok: %i units x 8 samples identical to the oracle (%i trims, %i checkpoints, %i round caps)"
+      % (n_units, ntrim, ncp, nround))
+ctx.close()
