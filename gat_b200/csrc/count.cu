@@ -104,18 +104,19 @@ struct Flight {
 //                        i.e. when it does not already overlap the previous segment (x >= pe)
 //   overlap-pieces       len(a.intersect(b)): every overlapping pair is one piece (:1469-1549)
 template <int COUNTER>
-__device__ __forceinline__ void count_entry(const uint2 *__restrict__ civ, uint32_t wx, uint32_t wy, uint32_t j,
-                                            uint32_t pv, const uint4 o, uint32_t pe, uint32_t acc_addr)
+__device__ __forceinline__ void count_entry(uint32_t wx, uint32_t wy, uint32_t y, uint32_t j, uint32_t pv,
+                                            const uint4 o, uint32_t pe, uint32_t acc_addr)
 {
     const uint32_t s = o.x, e = o.y;                        // the entry's segment; o.w = end of bin b0's entries
     const bool first = (int32_t)wx < 0;
-    const uint32_t x = wx & 0x7fffffffu, l = wy >> 12;
-    uint32_t y = x + l;
-    if (l == ENTRY_LEN_MASK) y = civ[j].y;                  // 2^20 - 1 bases or longer: rare
+    const uint32_t x = wx & 0x7fffffffu;
     const bool overlap = (x < e) & (y > s);
-    const bool mine = (x >= s) ? first : (j < o.w);         // the bin of the intersection's first base
+    // counted in the bin of the intersection's first base: every entry of the segment's first bin b0 (an
+    // interval met there starts in b0 or before it), and in later bins the interval's first entry only
+    const bool mine = (j < o.w) | first;
     if (!(overlap & mine)) return;
-    const uint32_t cell = acc_addr + ((wy & 0xfffu) << 2);
+    uint32_t cell;
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(cell) : "r"(wy & 0xfffu), "r"(acc_addr));
     if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
         red_add_shared(cell, min(e, y) - max(s, x));
     } else if (COUNTER == GATB_SEGMENT_OVERLAP) {
@@ -141,8 +142,12 @@ __device__ __forceinline__ void count_pair(const uint2 *__restrict__ civ, const 
     const uint4 o = lds128(stg + f.owner * 16u);
     uint32_t pe = 0;
     if (NeedPrevSegment<COUNTER>::value) pe = lds32(stg_pe + f.owner * 4u);
-    count_entry<COUNTER>(civ, f.w.x, f.w.y, f.j, f.pv.x, o, pe, acc_addr);
-    count_entry<COUNTER>(civ, f.w.z, f.w.w, f.j + 1u, f.pv.y, o, pe, acc_addr);
+    // end = start + length; a length field of 2^20 - 1 sends us to civ[] for the end (rare)
+    uint32_t y0 = (f.w.x & 0x7fffffffu) + (f.w.y >> 12), y1 = (f.w.z & 0x7fffffffu) + (f.w.w >> 12);
+    if ((f.w.y >> 12) == ENTRY_LEN_MASK) y0 = civ[f.j].y;
+    if ((f.w.w >> 12) == ENTRY_LEN_MASK) y1 = civ[f.j + 1u].y;
+    count_entry<COUNTER>(f.w.x, f.w.y, y0, f.j, f.pv.x, o, pe, acc_addr);
+    count_entry<COUNTER>(f.w.z, f.w.w, y1, f.j + 1u, f.pv.y, o, pe, acc_addr);
 }
 
 // an item whose bin offsets have been requested: lane = segment

@@ -19,9 +19,9 @@ constexpr uint32_t ENTRY_LEN_MASK = 0xfffffu;
 // is stored m times.  A segment [s,e) covering bins b0..b1 finds every interval that can overlap it in
 // ONE contiguous run of entries, boff[b0] .. boff[b1+1]: a two-load replacement for the binary search
 // (utils/gat_utils.c:8-32) that answers all tracks at once.  A pair (segment, interval) met in several
-// bins is counted in the bin that holds the first base of their intersection: an interval starting at
-// or after s counts at its FIRST entry, one starting before s counts in bin b0 (entry index
-// < boff[b0+1]).  Entries of a bin are in no particular order; all accumulation is by integer atomics,
+// bins is counted in the bin that holds the first base of their intersection: in the segment's first bin b0
+// (entry index < boff[b0+1]) every entry counts -- an interval met there starts in b0 or before it -- and in
+// the later bins only an interval's FIRST entry does.  Entries of a bin are in no particular order; all accumulation is by integer atomics,
 // so results do not depend on it.  Every bin holds an EVEN number of entries (an odd bin is padded with an
 // entry that overlaps nothing: start 2^31-1) and so starts on an even index: the counting kernel reads
 // entries two at a time (16-byte loads) and a pair never straddles two segments' runs.
