@@ -11,7 +11,8 @@ A step = one pass of the hot path (placement of every unit + counting against ev
 one batch of `--samples-per-step` Monte-Carlo samples per GPU; sample indices advance every step, so no
 step repeats another's work.  Weak scaling: every rank runs the same batch size on its own shard of the
 global sample index space; for N > 1 the per-step count slab is all-gathered over NCCL (the path's one
-exchange step) inside the timed region.
+exchange step) inside the timed region; the all-gather of a step runs asynchronously and overlaps the next
+step's kernels (two output slabs), the last ones are waited for before the closing event.
 
 value   whole-job samples/s, inputs resident in HBM, counts left in HBM (CUDA events, max over ranks)
 e2e     same metric through the C ABI with HOST buffers: every step uploads segments, workspace and
@@ -234,8 +235,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"       # NCCL's version banner goes to stdout: keep it to ONE JSON line
+        # NCCL writes its version banner / debug lines to stdout by default: stdout carries ONE JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local)
         dist.init_process_group(backend="nccl")
     dev = torch.device("cuda", local)
@@ -255,18 +256,33 @@ def run_ours(args):
     ctx.set_batch_size(B)
     annos = device.Annotations(ctx, None, key_ws_nseg=wl["nseg"], csr=(A, C) + wl["anno_csr"])
     smp = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(wl["seg_csr"], wl["ws_csr"]))
-    out_u = torch.zeros((1, B, A), dtype=torch.int32, device=dev)
-    out_f = torch.zeros((B, A), dtype=torch.float64, device=dev) if is_density else None
-    gathered = torch.empty((world * B, A), dtype=torch.float64 if is_density else torch.int32, device=dev) \
-        if world > 1 else None
+    # two output slabs, used alternately: for N > 1 the all-gather of step i (NCCL, asynchronous, its own stream)
+    # overlaps the placement and counting of step i + 1, which write the other slab
+    nbuf = 2 if world > 1 else 1
+    out_us = [torch.zeros((1, B, A), dtype=torch.int32, device=dev) for _ in range(nbuf)]
+    out_fs = [torch.zeros((B, A), dtype=torch.float64, device=dev) if is_density else None for _ in range(nbuf)]
+    gathers = [torch.empty((world * B, A), dtype=torch.float64 if is_density else torch.int32, device=dev)
+               for _ in range(nbuf)] if world > 1 else None
+    pending = [None] * nbuf
 
     def step(i):
+        b = i % nbuf
+        if pending[b] is not None:                 # the slab's previous all-gather must have read it
+            pending[b].wait()
+            pending[b] = None
         begin = (i * world + rank) * B             # global sample indices of this rank's shard
-        info = smp.run(annos, [args.counter], 20260101, 0, begin, B, out_counts_ptr=out_u.data_ptr(),
-                       out_density_ptr=out_f.data_ptr() if is_density else None)
+        info = smp.run(annos, [args.counter], 20260101, 0, begin, B, out_counts_ptr=out_us[b].data_ptr(),
+                       out_density_ptr=out_fs[b].data_ptr() if is_density else None)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out_f if is_density else out_u[0])
+            pending[b] = dist.all_gather_into_tensor(gathers[b], out_fs[b] if is_density else out_us[b][0],
+                                                     async_op=True)
         return info
+
+    def drain():                                   # every all-gather in flight joins the launching stream
+        for b in range(nbuf):
+            if pending[b] is not None:
+                pending[b].wait()
+                pending[b] = None
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -276,6 +292,7 @@ def run_ours(args):
 
     for i in range(args.warmup):
         info = step(i)
+    drain()
     placed_per_sample = float(info[0]) / B if args.warmup else None
 
     clocks = ClockSampler(local)
@@ -287,6 +304,7 @@ def run_ours(args):
     e0.record(stream)
     for i in range(args.steps):
         info = step(args.warmup + i)
+    drain()                                        # the last all-gathers are inside the timed region
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -304,6 +322,7 @@ def run_ours(args):
     nprof = max(1, min(args.steps, 3))
     for i in range(nprof):
         step(args.warmup + args.steps + i)
+    drain()
     prof = ctx.profile_read()
     ctx.profile(False)
     count_ms = prof["count"][0] / max(prof["count"][1], 1)
