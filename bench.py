@@ -233,10 +233,13 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries ONE JSON line: whatever libraries print there (NCCL's version banner, ...) is sent to
+    # stderr by pointing file descriptor 1 at it; the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version banner / debug lines to stdout by default: stdout carries ONE JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local)
         dist.init_process_group(backend="nccl")
     dev = torch.device("cuda", local)
@@ -415,7 +418,8 @@ def run_ours(args):
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "placed_segments_per_sample": placed_per_sample,
                 "segment_placements_per_s": value * placed_per_sample}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     smp.close()
     annos.close()
     ctx.close()
