@@ -191,9 +191,24 @@ __device__ __forceinline__ uint32_t ws_cov(const WsView &w, uint32_t x)
     return before + (min(x, w.end[p]) - w.start[p]);
 }
 
+// workspace bases in [s, e) = ws_cov(e) - ws_cov(s), with ONE search: the first piece ending after s, then the
+// few pieces that start before e (segments are short against the pieces of an isochore workspace)
 __device__ __forceinline__ uint32_t ws_overlap(const WsView &w, uint32_t s, uint32_t e)
 {
-    return ws_cov(w, e) - ws_cov(w, s);
+    if (w.n == 1) return ws_cov(w, e) - ws_cov(w, s);
+    if (e <= s) return 0u;
+    uint32_t lo = 0, hi = w.n;
+    while (lo < hi) {                       // first piece with end > s
+        const uint32_t mid = (lo + hi) >> 1;
+        if (w.end[mid] > s) hi = mid; else lo = mid + 1;
+    }
+    uint32_t acc = 0;
+    for (uint32_t p = lo; p < w.n; p++) {
+        const uint32_t ps = w.start[p];
+        if (ps >= e) break;
+        acc += min(e, w.end[p]) - max(s, ps);
+    }
+    return acc;
 }
 // ---------------------------------------------------------------------------------------------------
 // In-place merge(0) of a SORTED run of n packed segments (gat/SegmentList.pyx:756-816 with
@@ -227,7 +242,7 @@ __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n
         if (ws != nullptr && valid) {
             const int32_t lo = max(s, prev_max);
             if (e > lo) {
-                covered += ws_cov(*ws, (uint32_t)e) - ws_cov(*ws, (uint32_t)lo);
+                covered += ws_overlap(*ws, (uint32_t)lo, (uint32_t)e);
                 length += (uint32_t)(e - lo);
             }
         }
