@@ -372,7 +372,7 @@ __device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n, 
 {
     if (n == 0) { if (cov != nullptr) *cov = 0; if (len != nullptr) *len = 0; return 0; }
     const int lane = lane_id();
-    if (tmp != nullptr && n >= 96u && n <= 32768u && warp_bucket_sort(buf, n, tmp, cnt, plan, prehist))
+    if (tmp != nullptr && n >= 40u && n <= 32768u && warp_bucket_sort(buf, n, tmp, cnt, plan, prehist))
         return warp_merge0_sorted(buf, n, ws, cov, len);
     uint32_t N = next_pow2(n);
     for (uint32_t i = n + lane; i < N; i += 32) buf[i] = GATB_KEY_INF;
