@@ -578,9 +578,175 @@ done:
     return result;
 }
 
-/* which sampler go_compute_sample_philox places with: 0 = SamplerAnnotator, 1 = SamplerSegments */
+/* ------------------------------------------------------------------------------------------------
+ * gat/Engine.pyx:998-1111 SamplerShift.sample(segments, workspace): every workspace-overlapping segment is
+ * moved to a random position of the workspace within +-shift_area of its midpoint and wrapped around the
+ * ends of that local workspace.  The C integer conversions of the Cython code (Position = uint32,
+ * PositionDifference = int32) are kept as they are. */
+typedef struct { go_seg *s; size_t n, cap; } seg_vec;
+static int vec_push(seg_vec *v, go_seg x)
+{
+    if (v->n == v->cap) {
+        size_t c = v->cap ? 2 * v->cap : 64;
+        go_seg *t = (go_seg *)realloc(v->s, c * sizeof(go_seg));
+        if (!t) return -1;
+        v->s = t; v->cap = c;
+    }
+    v->s[v->n++] = x;
+    return 0;
+}
+
+/* gat/SegmentList.pyx:1314-1355 getFilledSegmentsFromStart(start, remainder); `out` receives the
+ * normalized result (:1354) */
+static int shift_fill_from_start(const go_seg *w, size_t n, uint32_t start, int32_t remainder, seg_vec *out)
+{
+    size_t first = out->n;
+    if ((uint32_t)remainder > go_sum(w, n)) {                             /* :1325-1326 clone of self */
+        for (size_t i = 0; i < n; i++) if (vec_push(out, w[i])) return -1;
+        return 0;
+    }
+    go_seg probe = { start, start + 1u };
+    int idx = go_get_insertion_point(w, n, probe);                         /* :1331 */
+    if (idx == (int)n) idx -= 1; else if (idx == -1) idx = 0;              /* :1336-1337 */
+    while (remainder > 0) {                                                /* :1340-1352 */
+        if (w[idx].end < start) {
+        } else {
+            start = (uint32_t)i32max((int32_t)w[idx].start, (int32_t)start);
+            uint32_t end = (uint32_t)i32min((int32_t)w[idx].end, (int32_t)(start + (uint32_t)remainder));
+            remainder -= (int32_t)(end - start);
+            go_seg x = { start, end };
+            if (vec_push(out, x)) return -1;
+        }
+        idx += 1;
+        if (idx == (int)n) { idx = 0; start = w[idx].start; }
+    }
+    out->n = first + go_normalize(out->s + first, out->n - first);
+    return 0;
+}
+
+/* gat/SegmentList.pyx:1357-1399 getFilledSegmentsFromEnd(end, remainder) */
+static int shift_fill_from_end(const go_seg *w, size_t n, uint32_t end, int32_t remainder, seg_vec *out)
+{
+    size_t first = out->n;
+    if ((uint32_t)remainder > go_sum(w, n)) {
+        for (size_t i = 0; i < n; i++) if (vec_push(out, w[i])) return -1;
+        return 0;
+    }
+    go_seg probe = { end, end + 1u };
+    int idx = go_get_insertion_point(w, n, probe);
+    if (idx == (int)n) idx -= 1; else if (idx == -1) idx = 0;
+    while (remainder > 0) {
+        if (w[idx].start > end) {
+        } else {
+            end = (uint32_t)i32min((int32_t)w[idx].end, (int32_t)end);
+            uint32_t start = (uint32_t)i32max((int32_t)w[idx].start, (int32_t)(end - (uint32_t)remainder));
+            remainder -= (int32_t)(end - start);
+            go_seg x = { start, end };
+            if (vec_push(out, x)) return -1;
+        }
+        idx -= 1;
+        if (idx < 0) { idx = (int)n - 1; end = w[idx].end; }
+    }
+    out->n = first + go_normalize(out->s + first, out->n - first);
+    return 0;
+}
+
+/* Returns the number of segments written to out (normalized), -1 capacity, -3 memory, -5 where the
+ * reference would stop (unused now: an empty local workspace drops the segment, see below).
+ * Draws per working segment x (turn x): GO_SLOT_SHIFT_POS = getRandomPosition (:1083),
+ * GO_SLOT_SHIFT_DIR = direction (:1084). */
+long go_sampler_shift(const go_seg *segments, size_t n, const go_seg *workspace, size_t m,
+                      double radius, int32_t extension,
+                      go_randint_fn rnd, go_turn_fn next_turn, void *ctx, go_seg *out, size_t cap)
+{
+    long result = -3;
+    const double half_radius = radius / 2;                                /* :1054 */
+    const int32_t half_extension = extension / 2;                         /* :1055 (extension >= 0) */
+    go_seg *working = (go_seg *)malloc(sizeof(go_seg) * (n ? n : 1));
+    go_seg *ws = (go_seg *)malloc(sizeof(go_seg) * (m ? m : 1));
+    seg_vec sample = { NULL, 0, 0 };
+    if (!working || !ws) goto done;
+    size_t nw = go_filter(segments, n, workspace, m, working);            /* :1060-1062 */
+    if (nw == 0) { result = 0; goto done; }                               /* :1067-1068 */
+    for (size_t x = 0; x < nw; x++) {                                     /* :1070 */
+        if (next_turn) next_turn(ctx);
+        const go_seg segment = working[x];
+        const uint32_t length = segment.end - segment.start;
+        const uint32_t midpoint = segment.start + length / 2;
+        int32_t shift_area;
+        if (extension) shift_area = half_extension;                        /* :1074-1077 */
+        else shift_area = (int32_t)(uint32_t)floor((double)length * half_radius);
+        int32_t ws_start = i32max(0, (int32_t)(midpoint - (uint32_t)shift_area));      /* :1080-1081 */
+        int32_t ws_end = i32max(0, (int32_t)(midpoint + (uint32_t)shift_area));
+        /* :1082 workspace.getOverlappingSegmentsWithRange(ws_start, ws_end) = getOverlappingSegments
+         * (gat/SegmentList.pyx:957-985): from the insertion point while start <= range end */
+        go_seg other = { (uint32_t)ws_start, (uint32_t)ws_end };
+        int idx = go_get_insertion_point(workspace, m, other);
+        if (idx == (int)m) idx -= 1; else if (idx == -1) idx = 0;
+        size_t k = 0;
+        while (idx < (int)m && workspace[idx].start <= other.end) ws[k++] = workspace[idx++];
+        /* :1083 ws.truncate(Segment(ws_start, ws_end)) (gat/SegmentList.pyx:1186-1202) */
+        for (size_t i = 0; i < k; i++) {
+            go_seg *s = &ws[i];
+            if (s->end < other.start) s->start = s->end = 0;
+            else if (s->start > other.end) s->start = s->end = 0;
+            else {
+                if (s->start < other.start) s->start = other.start;
+                if (s->end > other.end) s->end = other.end;
+            }
+        }
+        k = go_normalize(ws, k);
+        /* :1085 ws.getRandomPosition() (gat/SegmentList.pyx:902-915) */
+        const uint32_t total = go_sum(ws, k);
+        if (total == 0) {
+            /* numpy.random.randint(0, 0) raises ValueError inside the cpdef getRandomPosition, whose C return
+             * type cannot carry it: the exception is printed and ignored, 0 comes back (:902-905), the direction
+             * is still drawn (:1084) and every fill of the empty local workspace returns nothing -- the segment
+             * silently drops out of the sample */
+            (void)rnd(ctx, GO_SLOT_SHIFT_DIR, 0, 2);
+            continue;
+        }
+        uint32_t pos = (uint32_t)rnd(ctx, GO_SLOT_SHIFT_POS, 0, (int64_t)total);
+        int32_t start = 0, end;
+        int found = 0;
+        for (size_t i = 0; i < k; i++) {
+            uint32_t l = ws[i].end - ws[i].start;
+            if (pos > l) pos -= l;
+            else { start = (int32_t)(ws[i].start + pos); found = 1; break; }
+        }
+        if (!found) { result = -6; goto done; }                           /* `assert False` :915 */
+        if (rnd(ctx, GO_SLOT_SHIFT_DIR, 0, 2)) end = (int32_t)((uint32_t)start + length);      /* :1086-1090 */
+        else { end = start; start = (int32_t)((uint32_t)end - length); }
+        ws_start = (int32_t)ws[0].start; ws_end = (int32_t)ws[k - 1].end;  /* :1093 ws.min(), ws.max() */
+        int32_t remainder;
+        int rc;
+        if (start < ws_start) {                                            /* :1096-1100 */
+            remainder = i32min(ws_start - start, (int32_t)length);
+            rc = shift_fill_from_start(ws, k, (uint32_t)start, (int32_t)(length - (uint32_t)remainder), &sample);
+            if (!rc) rc = shift_fill_from_end(ws, k, (uint32_t)ws_end, remainder, &sample);
+        } else if (end > ws_end) {                                         /* :1101-1105 */
+            remainder = i32min(end - ws_end, (int32_t)length);
+            rc = shift_fill_from_end(ws, k, (uint32_t)end, (int32_t)(length - (uint32_t)remainder), &sample);
+            if (!rc) rc = shift_fill_from_start(ws, k, (uint32_t)ws_start, remainder, &sample);
+        } else rc = shift_fill_from_start(ws, k, (uint32_t)start, (int32_t)length, &sample);   /* :1107 */
+        if (rc) goto done;
+    }
+    sample.n = go_normalize(sample.s, sample.n);                          /* :1109 */
+    if (sample.n > cap) { result = -1; goto done; }
+    memcpy(out, sample.s, sizeof(go_seg) * sample.n);
+    result = (long)sample.n;
+done:
+    free(working); free(ws); free(sample.s);
+    return result;
+}
+
+/* which sampler go_compute_sample_philox places with: 0 = SamplerAnnotator, 1 = SamplerSegments,
+ * 2 = SamplerShift (parameters from go_set_shift_params) */
 static int g_sampler_kind = 0;
+static double g_shift_radius = 2.0;
+static int32_t g_shift_extension = 0;
 void go_set_sampler_kind(int kind) { g_sampler_kind = kind; }
+void go_set_shift_params(double radius, int32_t extension) { g_shift_radius = radius; g_shift_extension = extension; }
 
 /* gat/__init__.py:494-591 computeSample, with the Philox stream of the CUDA kernel */
 int go_compute_sample_philox(int U, int C, int A, const int32_t *unit_contig, int has_isochores,
@@ -595,7 +761,9 @@ int go_compute_sample_philox(int U, int C, int A, const int32_t *unit_contig, in
 {
     /* per-unit placement (:531-546); units with empty segments/workspace are skipped (:536-538) */
     size_t total_cap = 0;
-    for (int u = 0; u < U; u++) total_cap += 2 * (size_t)(seg_off[u + 1] - seg_off[u]) + 64;
+    /* SamplerShift cuts a moved segment at workspace gaps: room for more pieces (exceeding it is reported) */
+    const size_t cap_mul = g_sampler_kind == 2 ? 4 : 2;
+    for (int u = 0; u < U; u++) total_cap += cap_mul * (size_t)(seg_off[u + 1] - seg_off[u]) + 64;
     go_seg *unit_out = (go_seg *)malloc(sizeof(go_seg) * (total_cap ? total_cap : 1));
     size_t *unit_n = (size_t *)calloc((size_t)(U ? U : 1), sizeof(size_t));
     size_t *unit_o = (size_t *)calloc((size_t)(U ? U : 1), sizeof(size_t));
@@ -607,12 +775,15 @@ int go_compute_sample_philox(int U, int C, int A, const int32_t *unit_contig, in
     size_t o = 0;
     for (int u = 0; u < U; u++) {
         size_t n = (size_t)(seg_off[u + 1] - seg_off[u]), m = (size_t)(ws_off[u + 1] - ws_off[u]);
-        size_t cap = 2 * n + 64;
+        size_t cap = cap_mul * n + 64;
         unit_o[u] = o;
         if (n == 0 || m == 0) { unit_n[u] = 0; o += cap; continue; }
         go_philox_ctx ctx;
         go_philox_begin(&ctx, seed, track, (uint32_t)u, sample);
-        long r = g_sampler_kind == 1
+        long r = g_sampler_kind == 2
+            ? go_sampler_shift(seg + seg_off[u], n, ws + ws_off[u], m, g_shift_radius, g_shift_extension,
+                               go_philox_randint, go_philox_next_turn, &ctx, unit_out + o, cap)
+            : g_sampler_kind == 1
             ? go_sampler_segments(seg + seg_off[u], n, ws + ws_off[u], m, bucket_size, nbuckets,
                                   go_philox_randint, go_philox_next_turn, &ctx, unit_out + o, cap)
             : go_sampler_annotator(seg + seg_off[u], n, ws + ws_off[u], m, bucket_size, nbuckets,

@@ -55,7 +55,9 @@ uint32_t go_length_distribution(const go_seg *s, size_t n, uint32_t bucket_size,
  * `slot` names the draw inside the current loop turn; next_turn(ctx) is called at the top of every
  * turn of the placement loop (gat/Engine.pyx:572).  A sequential generator ignores both. */
 enum { GO_SLOT_LEN = 0, GO_SLOT_JITTER = 1, GO_SLOT_WS_R = 2, GO_SLOT_WS_P = 3,
-       GO_SLOT_TRIM_R = 4, GO_SLOT_TRIM_P = 5, GO_SLOT_TRIM_DIR = 6 };
+       GO_SLOT_TRIM_R = 4, GO_SLOT_TRIM_P = 5, GO_SLOT_TRIM_DIR = 6,
+       /* SamplerShift: one Philox block per segment (block 0: words 0,1 = position, words 2,3 = direction) */
+       GO_SLOT_SHIFT_POS = 0, GO_SLOT_SHIFT_DIR = 2 };
 typedef int64_t (*go_randint_fn)(void *ctx, int slot, int64_t lo, int64_t hi);
 typedef void    (*go_turn_fn)(void *ctx);
 
@@ -100,6 +102,11 @@ long go_sampler_segments(const go_seg *segments, size_t n, const go_seg *workspa
                          go_randint_fn rnd, go_turn_fn next_turn, void *ctx, go_seg *out, size_t cap);
 /* sampler used by go_compute_sample_philox: 0 = SamplerAnnotator (default), 1 = SamplerSegments */
 void go_set_sampler_kind(int kind);
+/* SamplerShift.sample (gat/Engine.pyx:998-1111); -5 where the reference raises ValueError (empty local workspace) */
+long go_sampler_shift(const go_seg *segments, size_t n, const go_seg *workspace, size_t m,
+                      double radius, int32_t extension,
+                      go_randint_fn rnd, go_turn_fn next_turn, void *ctx, go_seg *out, size_t cap);
+void go_set_shift_params(double radius, int32_t extension);
 
 /* --- counters (gat/Engine.pyx:1412-1472) ----------------------------------------------------------
  * counter ids are shared with include/gat_b200.h */

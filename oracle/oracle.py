@@ -258,12 +258,45 @@ def sampler_segments(segments, workspace, bucket_size=1, nbuckets=100000, philox
     return out[:n].copy()
 
 
-def set_sampler_kind(kind):
-    """sampler used by compute_sample_philox: 'annotator' (default) or 'segments'"""
+def sampler_shift(segments, workspace, radius=2, extension=0, philox=None, cap=None):
+    """SamplerShift.sample (gat/Engine.pyx:998-1111): driven by numpy.random (seed it first) when philox is
+    None, else by the Philox stream philox=(seed, track, unit, sample).  ValueError where the reference
+    raises it (no workspace within the shift area of a segment: numpy.random.randint(0, 0))."""
+    L = lib()
+    L.go_sampler_shift.restype = ctypes.c_long
+    L.go_sampler_shift.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                   ctypes.c_double, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    a, w = as_segs(segments), as_segs(workspace)
+    cap = cap or (len(a) * (min(len(w), 64) + 2) + 64)
+    out = np.zeros((cap, 2), dtype=np.uint32)
+    if philox is None:
+        cb = _numpy_randint_callback()
+        n = L.go_sampler_shift(_p(a), len(a), _p(w), len(w), float(radius), int(extension),
+                               ctypes.cast(cb, ctypes.c_void_p), None, None, _p(out), cap)
+    else:
+        ctx = PhiloxCtx()
+        L.go_philox_begin(ctypes.addressof(ctx), *philox)
+        n = L.go_sampler_shift(_p(a), len(a), _p(w), len(w), float(radius), int(extension),
+                               ctypes.cast(L.go_philox_randint, ctypes.c_void_p),
+                               ctypes.cast(L.go_philox_next_turn, ctypes.c_void_p),
+                               ctypes.addressof(ctx), _p(out), cap)
+    if n == -5:
+        raise ValueError("low >= high")
+    if n < 0:
+        raise RuntimeError("oracle sampler failed: %i" % n)
+    return out[:n].copy()
+
+
+def set_sampler_kind(kind, radius=2, extension=0):
+    """sampler used by compute_sample_philox: 'annotator' (default), 'segments' or 'shift'"""
     L = lib()
     L.go_set_sampler_kind.restype = None
     L.go_set_sampler_kind.argtypes = [ctypes.c_int]
-    L.go_set_sampler_kind({"annotator": 0, "segments": 1}[kind])
+    L.go_set_shift_params.restype = None
+    L.go_set_shift_params.argtypes = [ctypes.c_double, ctypes.c_int32]
+    L.go_set_sampler_kind({"annotator": 0, "segments": 1, "shift": 2}[kind])
+    L.go_set_shift_params(float(radius), int(extension))
 
 
 def philox4x32_10(ctr, key):

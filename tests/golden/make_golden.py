@@ -158,6 +158,31 @@ def make_sampler_segments(rng):
     return units
 
 
+def make_sampler_shift(rng):
+    """SamplerShift.sample (gat/Engine.pyx:998-1111) under numpy.random.seed: default radius, other radii and
+    --shift-extension; fragmented workspaces, segments at the contig start (negative shifted starts), windows
+    that hold no workspace (the reference drops such a segment: getRandomPosition's ValueError is ignored)"""
+    import contextlib
+    units = []
+    for it in range(60):
+        nws = int(rng.integers(1, 9))
+        span = int(rng.choice([3000, 200000, 30000000]))
+        pts = np.sort(rng.choice(span, size=2 * nws, replace=False))
+        ws = [(int(pts[2 * i]), int(pts[2 * i + 1])) for i in range(nws)]
+        if it % 5 == 0:
+            ws[0] = (0, ws[0][1])
+        segs = rlist(rng, span, int(rng.integers(1, 50)), int(rng.choice([5, 80, 900, 4000])))
+        kw = [{}, {"radius": float(rng.choice([0.5, 1, 3, 7.5]))}, {"extension": int(rng.choice([10, 101, 1000, 5000]))}][it % 3]
+        sl = RS.SegmentList(iter=segs, normalize=True)
+        wl = RS.SegmentList(iter=ws, normalize=True)
+        np.random.seed(7000 + it)
+        with open(os.devnull, "w") as devnull, contextlib.redirect_stderr(devnull):
+            out = RE.SamplerShift(**kw).sample(sl, wl)
+        units.append(dict(segments=L(sl), workspace=L(wl), radius=kw.get("radius", 2), extension=kw.get("extension", 0),
+                          seed=7000 + it, placed=L(out)))
+    return units
+
+
 def counter_objs():
     return [RE.CounterNucleotideOverlap(), RE.CounterNucleotideDensity(), RE.CounterSegmentOverlap(),
             RE.CounterSegmentMidpointOverlap(), RE.CounterAnnotationOverlap(), RE.CounterAnnotationMidpointOverlap()]
@@ -480,7 +505,8 @@ def make_compare(rng):
 def main():
     # fixtures added after the first generation have their own seeds and can be (re)made alone:
     #   python tests/golden/make_golden.py sampler_segments
-    extra = {"sampler_segments": (make_sampler_segments, 20260102), "compare": (make_compare, 20260103)}
+    extra = {"sampler_segments": (make_sampler_segments, 20260102), "compare": (make_compare, 20260103),
+             "sampler_shift": (make_sampler_shift, 20260104)}
     only = [a for a in sys.argv[1:] if a in extra]
     for name in (only or list(extra)):
         fn, seed = extra[name]

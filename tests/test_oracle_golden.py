@@ -237,6 +237,21 @@ def test_sampler_segments_matches_reference_under_numpy_rng(oracle):
         assert len(got) in (0, len(u["segments"]))
 
 
+def test_sampler_shift_matches_reference_under_numpy_rng(oracle):
+    """SamplerShift.sample (gat/Engine.pyx:998-1111): the normalized sample equals the reference's for the
+    default radius, other radii and extensions (fixtures include wrapped shifts, fragmented workspaces and
+    segments whose window holds no workspace)"""
+    units = G.load_json("sampler_shift")
+    assert len(units) >= 60
+    nonempty = 0
+    for u in units:
+        np.random.seed(u["seed"])
+        got = oracle.sampler_shift(u["segments"], u["workspace"], radius=u["radius"], extension=u["extension"])
+        assert got.tolist() == u["placed"], u["seed"]
+        nonempty += len(got) > 0
+    assert nonempty >= 50
+
+
 def _parse_counts(text):
     rows = []
     for line in text.splitlines()[1:]:
