@@ -15,7 +15,7 @@ import numpy as np
 from . import device
 from . import engine as Engine
 from . import stats as Stats
-from .engine import (IntervalCollection, IntervalDictionary, SamplerAnnotator, SamplerSegments, UnconditionalWorkspace,
+from .engine import (IntervalCollection, IntervalDictionary, SamplerAnnotator, SamplerSegments, SamplerShift, UnconditionalWorkspace,
                      AnnotatorResult, AnnotatorResultExtended, getContext, seed)
 from .segmentlist import SegmentList
 
@@ -79,7 +79,9 @@ def sampleTrack(track_index, segs, annotations, workspace, sampler, counters, nu
         if e.code == device._lib.ERR_TOO_LARGE:
             raise ValueError(str(e))
         raise
-    if getattr(sampler, "kind", "annotator") != "annotator":
+    if getattr(sampler, "kind", "annotator") == "shift":
+        smp.set_shift(sampler.radius, sampler.extension)
+    elif getattr(sampler, "kind", "annotator") != "annotator":
         try:
             smp.set_kind(sampler.kind)
         except device._lib.GatB200Error as e:
@@ -287,6 +289,10 @@ def _dumpSamples(track, track_index, segs, workspace, sampler, num_samples, patt
     smp = device.Sampler(ctx, problem.unit_contig, len(problem.contigs), problem.has_isochores,
                          problem.unit_segments, problem.unit_workspace,
                          bucket_size=sampler.bucket_size, nbuckets=sampler.nbuckets)
+    if getattr(sampler, "kind", "annotator") == "shift":
+        smp.set_shift(sampler.radius, sampler.extension)
+    elif getattr(sampler, "kind", "annotator") != "annotator":
+        smp.set_kind(sampler.kind)
     with _open(filename, "w") as outf:
         step = 256
         for b in range(0, num_samples, step):

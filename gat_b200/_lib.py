@@ -21,7 +21,7 @@ SYMBOLS = [
     "gatb_annotations_create", "gatb_annotations_create_async", "gatb_annotations_wait",
     "gatb_annotations_destroy", "gatb_count_lists",
     "gatb_sampler_create", "gatb_sampler_destroy", "gatb_sampler_sample_capacity",
-    "gatb_sampler_set_kind", "gatb_sampler_place", "gatb_run", "gatb_column_stats", "gatb_compare_stats",
+    "gatb_sampler_set_kind", "gatb_sampler_set_shift", "gatb_sampler_place", "gatb_run", "gatb_column_stats", "gatb_compare_stats",
     "gatb_format_counts",
 ]
 
@@ -86,6 +86,8 @@ def load():
     L.gatb_sampler_sample_capacity.argtypes = [vp]
     L.gatb_sampler_set_kind.restype = i32
     L.gatb_sampler_set_kind.argtypes = [vp, i32]
+    L.gatb_sampler_set_shift.restype = i32
+    L.gatb_sampler_set_shift.argtypes = [vp, ctypes.c_double, i32]
     L.gatb_sampler_place.restype = i32
     L.gatb_sampler_place.argtypes = [vp, u64, u32, u64, u64, vp, vp, vp, vp, vp]
     L.gatb_run.restype = i32

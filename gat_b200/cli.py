@@ -75,8 +75,8 @@ _OPTIONS = [
      dict(dest="sampler", type="choice", choices=SAMPLER_CHOICES, help="sampling method (accelerated: annotator)")),
     ("Sampling algorithm options", ("-n", "--num-samples"),
      dict(dest="num_samples", type="int", help="number of samples to compute")),
-    ("Sampling algorithm options", ("--shift-extension",), dict(dest="shift_extension", type="float", help="unused")),
-    ("Sampling algorithm options", ("--shift-expansion",), dict(dest="shift_expansion", type="float", help="unused")),
+    ("Sampling algorithm options", ("--shift-extension",), dict(dest="shift_extension", type="float", help="--sampler=shift: size of the window a segment is shifted in, in bases (0 = use --shift-expansion)")),
+    ("Sampling algorithm options", ("--shift-expansion",), dict(dest="shift_expansion", type="float", help="--sampler=shift: window as a multiple of the segment length")),
     ("Sampling algorithm options", ("--bucket-size",),
      dict(dest="bucket_size", type="int", help="bin size of the segment length histogram, 0 = automatic")),
     ("Sampling algorithm options", ("--nbuckets",),
@@ -161,8 +161,10 @@ def fromSegments(options, log=None):
         sampler = Engine.SamplerAnnotator(bucket_size=options.bucket_size, nbuckets=options.nbuckets)
     elif options.sampler == "segments":
         sampler = Engine.SamplerSegments()
+    elif options.sampler == "shift":            # scripts/gat-run.py:129-132
+        sampler = Engine.SamplerShift(radius=options.shift_expansion, extension=options.shift_extension)
     else:
-        raise NotImplementedError("--sampler=%s is not accelerated by gat_b200 (annotator, segments)" % options.sampler)
+        raise NotImplementedError("--sampler=%s is not accelerated by gat_b200 (annotator, segments, shift)" % options.sampler)
     counters = [Engine.COUNTER_CLASSES[c]() for c in options.counters]
     if options.conditional != "unconditional":
         raise NotImplementedError("--conditional=%s is not accelerated by gat_b200" % options.conditional)

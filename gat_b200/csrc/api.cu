@@ -666,7 +666,9 @@ struct gatb_sampler {
     gatb_ctx *ctx = nullptr;
     uint32_t n_units = 0, n_contigs = 0;
     bool has_iso = false;
-    int kind = 0;                       // 0 SamplerAnnotator, 1 SamplerSegments
+    int kind = 0;                       // 0 SamplerAnnotator, 1 SamplerSegments, 2 SamplerShift
+    double shift_radius = 2.0;          // SamplerShift(radius, extension), gat/Engine.pyx:1021-1026
+    int32_t shift_extension = 0;
     std::vector<UnitDesc> h_units;
     std::vector<uint64_t> h_contig_base;
     std::vector<uint32_t> h_contig_cap;
@@ -674,10 +676,70 @@ struct gatb_sampler {
     DevBuf<UnitDesc> units;
     DevBuf<uint32_t> order;
     DevBuf<uint32_t> ws_start, ws_end, ws_cuminc, len_tab;
+    DevBuf<uint32_t> seg_start, seg_end;  // the units' raw segments (preparation; SamplerShift moves them)
     DevBuf<uint32_t> contig_unit_off, contig_units;
     DevBuf<uint64_t> contig_base;
     DevBuf<unsigned long long> tally;     // [3]: placed segments, round-cap units, overflow units
 };
+
+// Buffer layout from the units' capacities (UnitDesc.cap): offsets of the unit buffers inside one sample's
+// region, contig-level capacities, the heaviest-first unit order; uploads the descriptors.  *why is set
+// (and nothing uploaded) when a contig would need too large a buffer.
+#define TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
+static cudaError_t sampler_layout(gatb_sampler *s, cudaStream_t st, const char **why)
+{
+    const uint32_t U = s->n_units, C = s->n_contigs;
+    // buffer layout
+    s->h_contig_base.assign(C, 0);
+    s->h_contig_cap.assign(C, 0);
+    std::vector<uint32_t> cu_off(C + 1, 0), cu(U);
+    for (uint32_t u = 0; u < U; u++) cu_off[s->h_units[u].contig + 1]++;
+    for (uint32_t c = 0; c < C; c++) cu_off[c + 1] += cu_off[c];
+    {
+        std::vector<uint32_t> fill(cu_off.begin(), cu_off.end() - 1);
+        for (uint32_t u = 0; u < U; u++) cu[fill[s->h_units[u].contig]++] = u;
+    }
+    if (s->has_iso) {
+        uint64_t o = 0;
+        for (uint32_t u = 0; u < U; u++) { s->h_units[u].buf_off = o; o += s->h_units[u].cap; }
+        s->unit_stride = o;
+        uint64_t b = 0;
+        for (uint32_t c = 0; c < C; c++) {
+            uint64_t sum = 0;
+            for (uint32_t k = cu_off[c]; k < cu_off[c + 1]; k++) sum += s->h_units[cu[k]].cap;
+            s->h_contig_cap[c] = next_pow2((uint32_t)std::max<uint64_t>(sum, 1));
+            s->h_contig_base[c] = b;
+            b += s->h_contig_cap[c];
+        }
+        s->placed_stride = b;
+    } else {
+        uint64_t b = 0;
+        for (uint32_t c = 0; c < C; c++) {
+            uint32_t capc = 64;
+            for (uint32_t k = cu_off[c]; k < cu_off[c + 1]; k++) capc = s->h_units[cu[k]].cap;
+            s->h_contig_cap[c] = capc;
+            s->h_contig_base[c] = b;
+            for (uint32_t k = cu_off[c]; k < cu_off[c + 1]; k++) s->h_units[cu[k]].buf_off = b;
+            b += capc;
+        }
+        s->placed_stride = b;
+        s->unit_stride = 0;
+    }
+    for (uint32_t c = 0; c < C; c++)
+        if (s->h_contig_cap[c] > (1u << 24)) { *why = "sampler: more than 2^23 segments on one contig"; return cudaSuccess; }
+    std::vector<uint32_t> order(U);
+    for (uint32_t u = 0; u < U; u++) order[u] = u;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return s->h_units[a].tab_n > s->h_units[b].tab_n; });
+    cudaError_t e = cudaSuccess;
+    TRY(cudaMemcpyAsync(s->units.p, s->h_units.data(), U * sizeof(UnitDesc), cudaMemcpyHostToDevice, st));
+    TRY(s->order.upload(order.data(), U, st));
+    TRY(s->contig_unit_off.upload(cu_off.data(), C + 1, st));
+    TRY(s->contig_units.upload(cu.data(), U, st));
+    TRY(s->contig_base.upload(s->h_contig_base.data(), C, st));
+    TRY(cudaStreamSynchronize(st));         // (the host vectors above are the copies' sources)
+    return e;
+}
+#undef TRY
 
 extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *unit_contig, int n_contigs,
                                    int has_isochores,
@@ -731,7 +793,7 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
         scratch_off[u] = scratch_total;
         scratch_total += next_pow2(std::max(d.seg_n, 1u));
     }
-    DevBuf<uint32_t> d_seg_start, d_seg_end;
+    DevBuf<uint32_t> &d_seg_start = s->seg_start, &d_seg_end = s->seg_end;
     DevBuf<uint64_t> d_scratch, d_scratch_off;
     cudaError_t e = cudaSuccess;
 #define TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
@@ -763,55 +825,11 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
     for (uint32_t u = 0; u < U; u++) lsum += (uint64_t)(uint32_t)s->h_units[u].ltotal;
     if (lsum > 0xffffffffull) { delete s; return fail(ctx, GATB_ERR_RANGE, "sampler: more than 2^32 bases to place (uint32 counts would overflow)"); }
 
-    // buffer layout
-    s->h_contig_base.assign(C, 0);
-    s->h_contig_cap.assign(C, 0);
-    std::vector<uint32_t> cu_off(C + 1, 0), cu(U);
-    for (uint32_t u = 0; u < U; u++) cu_off[s->h_units[u].contig + 1]++;
-    for (uint32_t c = 0; c < C; c++) cu_off[c + 1] += cu_off[c];
     {
-        std::vector<uint32_t> fill(cu_off.begin(), cu_off.end() - 1);
-        for (uint32_t u = 0; u < U; u++) cu[fill[s->h_units[u].contig]++] = u;
+        const char *why = nullptr;
+        TRY(sampler_layout(s, st, &why));
+        if (why) { delete s; return fail(ctx, GATB_ERR_INVALID, why); }
     }
-    if (s->has_iso) {
-        uint64_t o = 0;
-        for (uint32_t u = 0; u < U; u++) { s->h_units[u].buf_off = o; o += s->h_units[u].cap; }
-        s->unit_stride = o;
-        uint64_t b = 0;
-        for (uint32_t c = 0; c < C; c++) {
-            uint64_t sum = 0;
-            for (uint32_t k = cu_off[c]; k < cu_off[c + 1]; k++) sum += s->h_units[cu[k]].cap;
-            s->h_contig_cap[c] = next_pow2((uint32_t)std::max<uint64_t>(sum, 1));
-            s->h_contig_base[c] = b;
-            b += s->h_contig_cap[c];
-        }
-        s->placed_stride = b;
-    } else {
-        uint64_t b = 0;
-        for (uint32_t c = 0; c < C; c++) {
-            uint32_t capc = 64;
-            for (uint32_t k = cu_off[c]; k < cu_off[c + 1]; k++) capc = s->h_units[cu[k]].cap;
-            s->h_contig_cap[c] = capc;
-            s->h_contig_base[c] = b;
-            for (uint32_t k = cu_off[c]; k < cu_off[c + 1]; k++) s->h_units[cu[k]].buf_off = b;
-            b += capc;
-        }
-        s->placed_stride = b;
-        s->unit_stride = 0;
-    }
-    for (uint32_t c = 0; c < C; c++)
-        if (s->h_contig_cap[c] > (1u << 24)) {
-            delete s;
-            return fail(ctx, GATB_ERR_INVALID, "sampler: more than 2^23 segments on one contig");
-        }
-    std::vector<uint32_t> order(U);
-    for (uint32_t u = 0; u < U; u++) order[u] = u;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return s->h_units[a].tab_n > s->h_units[b].tab_n; });
-    TRY(cudaMemcpyAsync(s->units.p, s->h_units.data(), U * sizeof(UnitDesc), cudaMemcpyHostToDevice, st));
-    TRY(s->order.upload(order.data(), U, st));
-    TRY(s->contig_unit_off.upload(cu_off.data(), C + 1, st));
-    TRY(s->contig_units.upload(cu.data(), U, st));
-    TRY(s->contig_base.upload(s->h_contig_base.data(), C, st));
     TRY(s->tally.alloc(3));
     TRY(cudaStreamSynchronize(st));
 #undef TRY
@@ -838,6 +856,31 @@ extern "C" int gatb_sampler_set_kind(gatb_sampler *s, int kind)
     if (kind == 1 && !s->has_iso)
         return fail(s->ctx, GATB_ERR_INVALID, "SamplerSegments needs an isochore workspace: its samples are not normalized");
     s->kind = kind;
+    return GATB_OK;
+}
+
+extern "C" int gatb_sampler_set_shift(gatb_sampler *s, double radius, int32_t extension)
+{
+    if (!s) return GATB_ERR_INVALID;
+    gatb_ctx *ctx = s->ctx;
+    if (!(radius >= 0.0) || radius > 1e6) return fail(ctx, GATB_ERR_INVALID, "SamplerShift: radius must be in [0, 1e6]");
+    if (extension < 0) return fail(ctx, GATB_ERR_INVALID, "SamplerShift: extension must be >= 0");
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    // A moved segment is cut at the gaps of the workspace inside its window: at most one piece per workspace
+    // piece and fill, two fills per segment.  Room for eight pieces per segment (never more than that bound);
+    // a unit that needs more reports GATB_ERR_CAPACITY instead of a wrong sample.
+    for (uint32_t u = 0; u < s->n_units; u++) {
+        UnitDesc &d = s->h_units[u];
+        const uint64_t bound = 2ull * d.tab_n * ((uint64_t)d.ws_n + 1u);
+        d.cap = next_pow2((uint32_t)std::min<uint64_t>(std::min<uint64_t>(bound, 8ull * d.tab_n + 256u) + 64u, 1u << 30));
+    }
+    const char *why = nullptr;
+    cudaError_t e = sampler_layout(s, ctx->stream, &why);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e));
+    if (why) return fail(ctx, GATB_ERR_INVALID, why);
+    s->kind = 2; s->shift_radius = radius; s->shift_extension = extension;
     return GATB_OK;
 }
 
@@ -905,6 +948,8 @@ static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t 
     }
     p.status = s->ctx->scratch->status.p; p.n_units = s->n_units; p.n_samples = B; p.sample_begin = sample_begin;
     p.seed = seed; p.track = track; p.sampler_kind = s->kind;
+    p.seg_start = s->seg_start.p; p.seg_end = s->seg_end.p;
+    p.shift_half_radius = s->shift_radius / 2; p.shift_extension = s->shift_extension;
     { ProfScope ps(ctx, PROF_PLACE); launch_place(st, p); }
     CU(ctx, cudaGetLastError());
     if (s->has_iso) {

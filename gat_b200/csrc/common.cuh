@@ -219,6 +219,9 @@ __device__ __forceinline__ uint32_t ws_overlap(const WsView &w, uint32_t s, uint
 // (intersect(workspace).sum(), gat/Engine.pyx:593-599): element i adds the workspace bases of
 // [max(start_i, running max end), end_i), the part of it that no earlier element covers.
 // and `len` the total length of the merged list.
+// NORMALIZE = true gives SegmentList.normalize instead (gat/SegmentList.pyx:697-754): only overlapping
+// segments are joined, adjacent ones stay apart (`start >= max_end` opens a new segment).
+template <bool NORMALIZE = false>
 __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n, const WsView *ws = nullptr,
                                                        uint32_t *cov = nullptr, uint32_t *len = nullptr)
 {
@@ -246,7 +249,7 @@ __device__ __forceinline__ uint32_t warp_merge0_sorted(uint64_t *buf, uint32_t n
                 length += (uint32_t)(e - lo);
             }
         }
-        bool head = valid && (s > prev_max);
+        bool head = valid && (NORMALIZE ? (s >= prev_max) : (s > prev_max));
         uint32_t hmask = __ballot_sync(GATB_FULL, head);
         uint32_t pos = nout + __popc(hmask & ((1u << lane) - 1));
         __syncwarp();                           // all lanes have read their element before any write
@@ -365,6 +368,7 @@ __device__ __forceinline__ bool warp_bucket_sort(uint64_t *buf, uint32_t n, uint
 
 // sort + merge(0) of n arbitrary packed segments in a buffer with at least next_pow2(n) slots; with
 // `tmp` (n more free slots) and `cnt` given, mid-sized runs take the counting sort
+template <bool NORMALIZE = false>
 __device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n, uint64_t *tmp = nullptr,
                                                      uint32_t *cnt = nullptr, const WsView *ws = nullptr,
                                                      uint32_t *cov = nullptr, uint32_t *len = nullptr,
@@ -373,12 +377,12 @@ __device__ __forceinline__ uint32_t warp_sort_merge0(uint64_t *buf, uint32_t n, 
     if (n == 0) { if (cov != nullptr) *cov = 0; if (len != nullptr) *len = 0; return 0; }
     const int lane = lane_id();
     if (tmp != nullptr && n >= 40u && n <= 32768u && warp_bucket_sort(buf, n, tmp, cnt, plan, prehist))
-        return warp_merge0_sorted(buf, n, ws, cov, len);
+        return warp_merge0_sorted<NORMALIZE>(buf, n, ws, cov, len);
     uint32_t N = next_pow2(n);
     for (uint32_t i = n + lane; i < N; i += 32) buf[i] = GATB_KEY_INF;
     __syncwarp();
     warp_bitonic_sort(buf, N);
-    return warp_merge0_sorted(buf, n, ws, cov, len);
+    return warp_merge0_sorted<NORMALIZE>(buf, n, ws, cov, len);
 }
 
 // merge(0) of a sorted, merged run U = buf[0,nu) with np <= 32 new segments stored behind it

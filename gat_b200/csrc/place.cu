@@ -367,13 +367,188 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// SamplerShift.sample (gat/Engine.pyx:998-1111): every workspace-overlapping segment is moved to a random
+// position of the workspace within +-shift_area of its midpoint and wrapped around the ends of that local
+// workspace.  Segments are independent of each other: one warp per (unit, sample), lane = segment; the
+// pieces go to the unit buffer through a per-warp counter, then the warp sorts and normalizes them (:1109).
+// The uint32 / int32 conversions of the Cython code are kept (oracle/gat_oracle.c:go_sampler_shift).
+
+// workspace pieces clipped to the window [w0, w1): getOverlappingSegmentsWithRange + truncate
+// (gat/SegmentList.pyx:957-985, 1186-1202); the clipped pieces are never empty
+struct LocalWs {
+    const uint32_t *ws_s, *ws_e;
+    uint32_t k, w0, w1;
+    __device__ __forceinline__ uint32_t s(uint32_t i) const { return max(ws_s[i], w0); }
+    __device__ __forceinline__ uint32_t e(uint32_t i) const { return min(ws_e[i], w1); }
+};
+
+// _getInsertionPoint(Segment(x, x + 1)) on the local workspace (gat/SegmentList.pyx:853-887) with the
+// border fix of its callers (:1336-1337)
+__device__ __forceinline__ uint32_t local_insertion_point(const LocalWs &L, uint32_t x)
+{
+    if (x >= L.e(L.k - 1u)) return L.k - 1u;
+    if (x + 1u <= L.s(0)) return 0u;
+    uint32_t lo = 0, hi = L.k;
+    while (lo < hi) {                       // first piece with start >= x
+        const uint32_t mid = (lo + hi) >> 1;
+        if (L.s(mid) < x) lo = mid + 1; else hi = mid;
+    }
+    if (lo == L.k || L.s(lo) != x) return lo - 1u;      // (lo >= 1 here: x + 1 > s(0) and s(0) != x)
+    return lo;
+}
+
+struct PieceSink {
+    uint64_t *buf;
+    uint32_t *counter;
+    uint32_t cap;
+    __device__ __forceinline__ void operator()(uint32_t s, uint32_t e) const
+    {
+        if (s == e) return;                 // (normalize drops empty segments)
+        const uint32_t pos = atomicAdd(counter, 1u);
+        if (pos < cap) buf[pos] = pack_seg(s, e);
+    }
+};
+
+// getFilledSegmentsFromStart (gat/SegmentList.pyx:1314-1355)
+__device__ __forceinline__ void fill_from_start(const LocalWs &L, uint32_t total, uint32_t start, int32_t remainder,
+                                                const PieceSink &emit)
+{
+    if ((uint32_t)remainder > total) {
+        for (uint32_t i = 0; i < L.k; i++) emit(L.s(i), L.e(i));
+        return;
+    }
+    uint32_t idx = local_insertion_point(L, start);
+    for (uint32_t it = 0; remainder > 0 && it < 2u * L.k + 4u; it++) {      // (the walk ends within two rounds)
+        const uint32_t ps = L.s(idx), pe = L.e(idx);
+        if (!(pe < start)) {
+            start = (uint32_t)max((int32_t)ps, (int32_t)start);
+            const uint32_t end = (uint32_t)min((int32_t)pe, (int32_t)(start + (uint32_t)remainder));
+            remainder -= (int32_t)(end - start);
+            emit(start, end);
+        }
+        idx += 1;
+        if (idx == L.k) { idx = 0; start = L.s(0); }
+    }
+}
+
+// getFilledSegmentsFromEnd (gat/SegmentList.pyx:1357-1399)
+__device__ __forceinline__ void fill_from_end(const LocalWs &L, uint32_t total, uint32_t end, int32_t remainder,
+                                              const PieceSink &emit)
+{
+    if ((uint32_t)remainder > total) {
+        for (uint32_t i = 0; i < L.k; i++) emit(L.s(i), L.e(i));
+        return;
+    }
+    uint32_t idx = local_insertion_point(L, end);
+    for (uint32_t it = 0; remainder > 0 && it < 2u * L.k + 4u; it++) {
+        const uint32_t ps = L.s(idx), pe = L.e(idx);
+        if (!(ps > end)) {
+            end = (uint32_t)min((int32_t)pe, (int32_t)end);
+            const uint32_t start = (uint32_t)max((int32_t)ps, (int32_t)(end - (uint32_t)remainder));
+            remainder -= (int32_t)(end - start);
+            emit(start, end);
+        }
+        if (idx == 0) { idx = L.k - 1u; end = L.e(idx); } else idx -= 1;
+    }
+}
+
+__global__ void __launch_bounds__(128) shift_kernel(PlaceParams p)
+{
+    __shared__ uint32_t sort_cnt[4][GATB_SORT_NB];
+    __shared__ uint32_t emitted[4];
+    const uint64_t item = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= (uint64_t)p.n_units * p.n_samples) return;
+    const int lane = lane_id();
+    const uint32_t unit = p.order[item / p.n_samples];
+    const uint32_t sl = (uint32_t)(item % p.n_samples);
+    const UnitDesc d = p.units[unit];
+    uint64_t *buf = p.buf + (uint64_t)sl * p.sample_stride + d.buf_off;
+    WsView ws;
+    ws.start = p.ws_start + d.ws_off; ws.end = p.ws_end + d.ws_off; ws.cuminc = p.ws_cuminc + d.ws_off;
+    ws.n = d.ws_n;
+    const uint32_t sample = (uint32_t)(p.sample_begin + sl);
+    const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+    const uint32_t c1 = p.track << 8;       // Philox block 0 of turn x: words 0,1 = position, words 2,3 = direction
+    uint32_t *counter = &emitted[threadIdx.x >> 5];
+    if (lane == 0) *counter = 0u;
+    __syncwarp();
+    PieceSink emit;
+    emit.buf = buf; emit.counter = counter; emit.cap = d.cap;
+    const uint32_t *ss = p.seg_start + d.seg_off, *se = p.seg_end + d.seg_off;
+
+    uint32_t nw = 0;                        // working segments so far = segments.filter(workspace) (:1060-1062)
+    for (uint32_t b0 = 0; b0 < d.seg_n; b0 += 32) {
+        const uint32_t i = b0 + lane;
+        uint32_t s = 0, e = 0;
+        bool keep = false;
+        if (i < d.seg_n) { s = ss[i]; e = se[i]; keep = ws_overlap(ws, s, e) > 0; }
+        const uint32_t m = __ballot_sync(GATB_FULL, keep);
+        const uint32_t x = nw + __popc(m & ((1u << lane) - 1));      // index in the working list = Philox turn
+        nw += __popc(m);
+        if (!keep) continue;
+        const uint32_t length = e - s, midpoint = s + length / 2u;
+        int32_t shift_area;
+        if (p.shift_extension) shift_area = p.shift_extension / 2;                       // :1074-1077
+        else shift_area = (int32_t)(uint32_t)floor((double)length * p.shift_half_radius);
+        const int32_t w0 = max(0, (int32_t)(midpoint - (uint32_t)shift_area));          // :1080-1081
+        const int32_t w1 = max(0, (int32_t)(midpoint + (uint32_t)shift_area));
+        if (w0 >= w1) continue;             // empty window: the segment drops out (see below)
+        // pieces of the window: from the first one ending after w0 to the last one starting before w1
+        uint32_t lo = 0, hi = ws.n;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ws.end[mid] > (uint32_t)w0) hi = mid; else lo = mid + 1; }
+        const uint32_t first = lo;
+        hi = ws.n;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ws.start[mid] >= (uint32_t)w1) hi = mid; else lo = mid + 1; }
+        LocalWs L;
+        L.ws_s = ws.start + first; L.ws_e = ws.end + first; L.k = lo - first; L.w0 = (uint32_t)w0; L.w1 = (uint32_t)w1;
+        // No workspace in the window: numpy.random.randint(0, 0) raises inside the cpdef getRandomPosition,
+        // whose C return type cannot carry the exception -- it is ignored, 0 comes back and every fill of the
+        // empty local workspace returns nothing: the segment silently drops out of the sample
+        if (L.k == 0) continue;
+        uint32_t total = 0;
+        for (uint32_t j = 0; j < L.k; j++) total += L.e(j) - L.s(j);
+        const Philox4 r = philox4x32_10(x, c1, unit, sample, k0, k1);
+        uint32_t pos = bounded_u32(r.x, r.y, total);                  // getRandomPosition (gat/SegmentList.pyx:902-915)
+        int32_t start = 0, end;
+        for (uint32_t j = 0; j < L.k; j++) {
+            const uint32_t l = L.e(j) - L.s(j);
+            if (pos > l) pos -= l;
+            else { start = (int32_t)(L.s(j) + pos); break; }
+        }
+        if (bounded_u32(r.z, r.w, 2u)) end = (int32_t)((uint32_t)start + length);       // :1086-1090
+        else { end = start; start = (int32_t)((uint32_t)end - length); }
+        const int32_t lws = (int32_t)L.s(0), lwe = (int32_t)L.e(L.k - 1u);              // :1093 ws.min(), ws.max()
+        if (start < lws) {                                                               // :1096-1100
+            const int32_t remainder = min(lws - start, (int32_t)length);
+            fill_from_start(L, total, (uint32_t)start, (int32_t)(length - (uint32_t)remainder), emit);
+            fill_from_end(L, total, (uint32_t)lwe, remainder, emit);
+        } else if (end > lwe) {                                                          // :1101-1105
+            const int32_t remainder = min(end - lwe, (int32_t)length);
+            fill_from_end(L, total, (uint32_t)end, (int32_t)(length - (uint32_t)remainder), emit);
+            fill_from_start(L, total, (uint32_t)lws, remainder, emit);
+        } else fill_from_start(L, total, (uint32_t)start, (int32_t)length, emit);       // :1107
+    }
+    __syncwarp();
+    const uint32_t n = *counter;
+    uint32_t status = 0, nu = 0;
+    if (n > d.cap) status |= UNIT_OVERFLOW;
+    else nu = warp_sort_merge0<true>(buf, n, 2u * n <= d.cap ? buf + n : nullptr, sort_cnt[threadIdx.x >> 5]);
+    if (lane == 0) {
+        const uint32_t slot = p.out_by_contig ? d.contig : unit;
+        p.out_n[(uint64_t)sl * p.out_n_stride + slot] = nu;
+        if (p.status) p.status[(uint64_t)sl * p.n_units + unit] = (uint8_t)status;
+    }
+}
+
 void launch_place(cudaStream_t st, const PlaceParams &p)
 {
     uint64_t items = (uint64_t)p.n_units * p.n_samples;
     if (items == 0) return;
     const int warps_per_block = 4;
     uint64_t blocks = (items + warps_per_block - 1) / warps_per_block;
-    place_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(p);
+    if (p.sampler_kind == 2) shift_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(p);
+    else place_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(p);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -45,7 +45,11 @@ struct PlaceParams {
     uint64_t sample_begin;       // global index of the first sample
     uint64_t seed;
     uint32_t track;
-    int sampler_kind;            // 0: SamplerAnnotator (gat/Engine.pyx:445-646), 1: SamplerSegments (:653-737)
+    int sampler_kind;            // 0: SamplerAnnotator (gat/Engine.pyx:445-646), 1: SamplerSegments (:653-737),
+                                 // 2: SamplerShift (:998-1111, shift_kernel)
+    const uint32_t *seg_start, *seg_end;   // raw segments of the units (UnitDesc.seg_off / seg_n); kind 2 only
+    double shift_half_radius;    // SamplerShift: radius / 2 (:1054)
+    int32_t shift_extension;     // SamplerShift: extension (0 = use the radius, :1074-1077)
 };
 
 struct MergeParams {             // K2: per (sample, contig) concat + merge(0) of the contig's units

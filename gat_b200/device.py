@@ -261,6 +261,11 @@ class Sampler(object):
         k = {"annotator": 0, "segments": 1}[kind] if isinstance(kind, str) else int(kind)
         self.ctx.check(self.ctx.lib.gatb_sampler_set_kind(self.handle, k))
 
+    def set_shift(self, radius=2, extension=0):
+        """SamplerShift(radius, extension) (gat/Engine.pyx:998-1111); re-sizes the sample buffers"""
+        self.ctx.check(self.ctx.lib.gatb_sampler_set_shift(self.handle, float(radius), int(extension)))
+        self.capacity = int(self.ctx.lib.gatb_sampler_sample_capacity(self.handle))
+
     def place(self, seed, track, sample_begin, n_samples):
         """-> (samples, status): samples[s][c] = (n,2) uint32 array of contig c; status [n_samples][n_units]"""
         cap = self.capacity

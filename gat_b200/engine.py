@@ -373,6 +373,43 @@ class SamplerAnnotator(Sampler):
         return r
 
 
+class SamplerShift(Sampler):
+    """shift every segment by a random amount within *radius* (a multiple of its length) or *extension* bases
+    around its midpoint, wrapping around the ends of the local workspace (gat/Engine.pyx:998-1111) -- on the
+    GPU (`shift_kernel`).  `sample(segments, workspace)` moves ONE unit, like the reference; gat_b200.run()
+    sends the whole track to the GPU in one batched call."""
+
+    accelerated = True
+    kind = "shift"
+    bucket_size = 0         # (the unit preparation shared with the other samplers: automatic bucket size, so
+    nbuckets = 100000       #  that no segment is "too large"; the shift itself uses no length histogram)
+
+    def __init__(self, radius=2, extension=0):
+        self.radius = radius
+        self.extension = int(extension)
+
+    def __reduce__(self):
+        return (SamplerShift, (self.radius, self.extension))
+
+    def sample(self, segments, workspace):
+        assert workspace.isNormalized, "workspace is not normalized"
+        if len(segments) == 0 or len(workspace) == 0:
+            return SegmentList()
+        ctx = getContext()
+        smp = _dev.Sampler(ctx, [0], 1, False, [segments.asarray()], [workspace.asarray()],
+                           bucket_size=self.bucket_size, nbuckets=self.nbuckets)
+        smp.set_shift(self.radius, self.extension)
+        call = _rng_state["calls"]
+        _rng_state["calls"] += 1
+        placed, status = smp.place(getSeed(), 0xFFFFFF, call, 1)
+        smp.close()
+        if status[0, 0] & _dev.UNIT_OVERFLOW:
+            raise MemoryError("SamplerShift: the moved segments were cut into more pieces than the buffer holds")
+        r = SegmentList(array=placed[0][0])
+        r._normalized = True
+        return r
+
+
 class SamplerSegments(Sampler):
     """sample exactly len(segments) segments from the length distribution (gat/Engine.pyx:653-737).  Its
     samples are unsorted and may overlap; like in the reference they only become countable through the

@@ -142,6 +142,17 @@ uint64_t gatb_sampler_sample_capacity(const gatb_sampler *s);
  * (without it the reference's counters fail their isNormalized assertion). */
 int  gatb_sampler_set_kind(gatb_sampler *s, int kind);
 
+/* Sampler kind 2 = SamplerShift(radius, extension) (gat/Engine.pyx:998-1111; gat-run.py --sampler=shift
+ * --shift-expansion=radius --shift-extension=extension, scripts/gat-run.py:129-132): every segment that
+ * overlaps its unit's workspace moves to a random workspace position within floor(length * radius / 2)
+ * bases (or extension / 2 when extension != 0) of its midpoint, wrapped around the ends of that local
+ * workspace; the sample is normalized per unit (adjacent pieces stay apart) and, with isochores, merged per
+ * contig.  Works with and without isochores.  Re-sizes the sampler's buffers (eight pieces per segment); a
+ * unit whose moved segments are cut into more pieces makes gatb_run / gatb_sampler_place return
+ * GATB_ERR_CAPACITY.  A segment whose window holds no workspace drops out of the sample, as in the
+ * reference (where getRandomPosition's ValueError is printed and ignored).  Needs length * radius / 2 < 2^31. */
+int  gatb_sampler_set_shift(gatb_sampler *s, double radius, int32_t extension);
+
 /* Place samples [sample_begin, sample_begin+n_samples) and return the contig-level segment sets
  * (what `sample` holds after sample.fromIsochores(), gat/__init__.py:563) to the host:
  * counts[s*n_contigs+c] segments for contig c of sample s, stored at start/end[s*capacity + contig_base[c] ...]

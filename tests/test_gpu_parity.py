@@ -281,6 +281,58 @@ def test_sampler_segments_matches_oracle(ctx, oracle):
     smp.close()
 
 
+def test_sampler_shift_matches_oracle(ctx, oracle):
+    """SamplerShift (gat/Engine.pyx:998-1111): single units (fragmented workspaces, several radii and
+    extensions, windows without workspace) and whole problems with and without isochores equal the oracle
+    under the same Philox stream -- placed segments and all counters, bit for bit"""
+    from gat_b200 import device
+    rng = np.random.default_rng(2027)
+    npieces = noverflow = 0
+    for it in range(150):
+        segs, ws = helpers.random_unit(rng)
+        kw = [dict(radius=2, extension=0), dict(radius=float(rng.choice([0.5, 1, 3, 7.5])), extension=0),
+              dict(radius=2, extension=int(rng.choice([10, 101, 1000, 5000])))][it % 3]
+        smp = device.Sampler(ctx, [0], 1, False, [segs], [ws], bucket_size=0)
+        smp.set_shift(**kw)
+        n = 6
+        placed, status = smp.place(seed=77 + it, track=it % 4, sample_begin=50, n_samples=n)
+        smp.close()
+        for s in range(n):
+            exp = oracle.sampler_shift(segs, ws, philox=(77 + it, it % 4, 0, 50 + s), **kw)
+            if status[s, 0] & device.UNIT_OVERFLOW:
+                noverflow += 1
+                assert len(exp) > 8 * len(segs)         # (only a sample that really needs more room may say so)
+                continue
+            assert np.array_equal(placed[s][0], exp), (it, s, kw)
+            npieces += len(exp)
+    assert npieces > 5000 and noverflow < 20
+    for n_iso, kw in ((0, dict(radius=2, extension=0)), (3, dict(radius=3, extension=0)), (2, dict(radius=2, extension=400))):
+        pr = helpers.random_problem(rng, n_contigs=3, n_iso=n_iso, n_annot=5)
+        has_iso = n_iso > 0
+        smp = device.Sampler(ctx, pr["unit_contig"], pr["n_contigs"], has_iso, pr["unit_segments"], pr["unit_workspace"],
+                             bucket_size=0)
+        smp.set_shift(**kw)
+        an = device.Annotations(ctx, pr["annotations"], key_ws_nseg=pr["cws_nseg"])
+        n = 10
+        placed, status = smp.place(seed=5, track=2, sample_begin=7, n_samples=n)
+        assert not status.any()
+        res, _ = smp.run(an, COUNTERS, seed=5, track=2, sample_begin=7, n_samples=n)
+        oracle.set_sampler_kind("shift", **kw)
+        try:
+            for s in range(n):
+                exp, exp_placed = oracle.compute_sample_philox(pr["unit_contig"], pr["unit_segments"], pr["unit_workspace"],
+                                                               pr["annotations"], pr["cws_nseg"], COUNTERS, seed=5, track=2,
+                                                               sample=7 + s, has_isochores=has_iso, return_placed=True)
+                for c in range(pr["n_contigs"]):
+                    assert np.array_equal(placed[s][c], exp_placed[c]), (n_iso, s, c)
+                for i, name in enumerate(COUNTERS):
+                    assert np.array_equal(np.asarray(res[name][s], dtype=np.float64), exp[i]), (n_iso, s, name)
+        finally:
+            oracle.set_sampler_kind("annotator")
+        smp.close()
+        an.close()
+
+
 def test_async_annotations_same_counts_and_deferred_errors(ctx, oracle):
     """gatb_annotations_create_async: upload + tile build on the upload stream; the first run waits on the
     device.  Counts equal the synchronous path; invalid lists surface at wait() / at the run that used them"""
