@@ -94,7 +94,12 @@ def run_full(segments, annotations, workspace, counters, num_samples, seed=1, **
     ra = ref_collection(gat, annotations, "annotations")
     rw = ref_dictionary(gat, workspace)
     np.random.seed(seed)
-    return gat.run(rs, ra, rw, gat.Engine.SamplerAnnotator(bucket_size=kwargs.pop("bucket_size", 1),
-                                                           nbuckets=kwargs.pop("nbuckets", 100000)),
+    shift = kwargs.pop("shift", None)           # (radius, extension): the reference's SamplerShift instead
+    if shift is not None:
+        sampler = gat.Engine.SamplerShift(radius=shift[0], extension=shift[1])
+    else:
+        sampler = gat.Engine.SamplerAnnotator(bucket_size=kwargs.pop("bucket_size", 1),
+                                              nbuckets=kwargs.pop("nbuckets", 100000))
+    return gat.run(rs, ra, rw, sampler,
                    ref_counters(gat, counters), gat.Engine.UnconditionalWorkspace(),
                    num_samples=num_samples, **kwargs)

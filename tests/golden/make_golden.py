@@ -329,8 +329,9 @@ def make_run_small():
     np.savez_compressed(os.path.join(HERE, "run_small.npz"), **store)
 
 
-def make_distribution():
-    """reference distributions for the statistical-equivalence tests (KS, 3 SE, binomial CI)"""
+def make_distribution(shift=None, name="distribution"):
+    """reference distributions for the statistical-equivalence tests (KS, 3 SE, binomial CI); with `shift` =
+    (radius, extension) the reference samples with SamplerShift"""
     store, meta = {}, {}
     for tag, iso, counters in (("plain", False, ["nucleotide-overlap", "segment-overlap"]),
                                ("iso", True, ["segment-overlap", "nucleotide-overlap"])):
@@ -341,7 +342,8 @@ def make_distribution():
             meta[tag]["workspace"].append(key)
             store["%s/workspace/%s" % (tag, key)] = s.asarray()
         nsamples = 2000
-        results = ref_bench.run_full(segments, annotations, workspace, counters, nsamples, seed=17)
+        results = ref_bench.run_full(segments, annotations, workspace, counters, nsamples, seed=17,
+                                     **({"shift": shift} if shift else {}))
         meta[tag]["counters"] = counters
         meta[tag]["num_samples"] = nsamples
         annos = sorted(set(r.annotation for r in results))
@@ -359,7 +361,10 @@ def make_distribution():
             store["%s/observed/%s" % (tag, c)] = obs
             store["%s/pvalue/%s" % (tag, c)] = pv
     store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
-    np.savez_compressed(os.path.join(HERE, "distribution.npz"), **store)
+    if shift:
+        meta["shift"] = list(shift)
+        store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
 
 
 # ------------------------------------------------------------------------------- reference's own data
@@ -507,6 +512,10 @@ def main():
     #   python tests/golden/make_golden.py sampler_segments
     extra = {"sampler_segments": (make_sampler_segments, 20260102), "compare": (make_compare, 20260103),
              "sampler_shift": (make_sampler_shift, 20260104)}
+    if "distribution_shift" in sys.argv[1:]:
+        make_distribution(shift=(3.0, 0), name="distribution_shift")
+        print("wrote distribution_shift")
+        return
     only = [a for a in sys.argv[1:] if a in extra]
     for name in (only or list(extra)):
         fn, seed = extra[name]

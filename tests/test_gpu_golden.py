@@ -137,15 +137,29 @@ def ks_statistic(a, b):
 def test_sampled_distributions_equivalent_to_reference(ctx, tag):
     """stochastic outputs differ only through the RNG: per annotation, two-sample KS against 2000
     reference samples, expected within 3 SE, empirical p-values within the binomial CI"""
+    from gat_b200 import engine as Engine
+    _check_distributions("distribution", tag, lambda meta: Engine.SamplerAnnotator())
+
+
+@pytest.mark.parametrize("tag", ["plain", "iso"])
+def test_shift_sampler_distributions_equivalent_to_reference(ctx, tag):
+    """the same equivalence for --sampler=shift: 2000 samples of the reference's SamplerShift(radius=3)
+    against 4000 of the GPU's through gat_b200.run"""
+    from gat_b200 import engine as Engine
+    _check_distributions("distribution_shift", tag,
+                         lambda meta: Engine.SamplerShift(radius=meta["shift"][0], extension=meta["shift"][1]))
+
+
+def _check_distributions(fixture, tag, make_sampler):
     import gat_b200
     from gat_b200 import engine as Engine
-    z, meta = G.load_npz("distribution")
+    z, meta = G.load_npz(fixture)
     m = meta[tag]
     segments, annotations, workspace, _, _, _, _ = _track_problem(z, tag, m)
     counters = m["counters"]
     n = 4000
     Engine.seed(2026)
-    res = gat_b200.run(segments, annotations, workspace, Engine.SamplerAnnotator(), counters_of(counters),
+    res = gat_b200.run(segments, annotations, workspace, make_sampler(meta), counters_of(counters),
                        Engine.UnconditionalWorkspace(), num_samples=n)
     assert len(res) == len(counters) * len(m["annotation_order"])
     nref = m["num_samples"]
@@ -260,6 +274,13 @@ def test_operator_protocols_single_calls(ctx, oracle):
         got = cls()(segs, annos, ws)
         assert got == oracle.counter(name, segs.asarray(), annos.asarray(), len(ws)), name
     assert Engine.SamplerAnnotator().sample(SegmentList(), ws).isEmpty
+    # SamplerShift.sample: the moved segments stay inside the workspace and lose no base except by overlap
+    moved = Engine.SamplerShift(radius=4).sample(segs, ws)
+    assert moved.isNormalized and 0 < moved.sum() <= 450
+    inside = moved.clone()
+    inside.intersect(ws)
+    assert inside.sum() == moved.sum()
+    assert Engine.SamplerShift().sample(SegmentList(), ws).isEmpty
     with pytest.raises(ValueError):                          # segment too large for the histogram
         Engine.SamplerAnnotator(bucket_size=1, nbuckets=100).sample(segs, ws)
 
@@ -300,6 +321,15 @@ def test_cli_from_bed_files(ctx, oracle, tmp_path, with_isochores):
                        for k in ws.keys())
             assert int(r[2]) == int(want), (counter, r[1])
             assert 0 < float(r[9]) <= 1 and 0 < float(r[10]) <= 1 and float(r[3]) > 0
+    # --sampler=shift (scripts/gat-run.py:129-132): same files, same observed column, its own expectation
+    first = dict((r[1], r) for r in rows[1:])
+    shift_argv = [a for a in argv if not a.startswith("--output-tables-pattern")]
+    shift_argv += ["--sampler=shift", "--shift-expansion=3", "--output-tables-pattern=" + str(tmp_path / "shift_%s.tsv")]
+    assert cli.main(shift_argv + ["-v", "0"]) == 0
+    rows = [l.rstrip("\n").split("\t") for l in open(str(tmp_path / "shift_segment-overlap.tsv"))]
+    assert len(rows) == 5
+    for r in rows[1:]:
+        assert r[2] == first[r[1]][2] and float(r[3]) > 0 and 0 < float(r[9]) <= 1
 
 
 def test_compare_cli_matches_reference_tables(ctx, tmp_path, monkeypatch):
