@@ -346,8 +346,8 @@ def run_ours(args):
                         "contig) cell (SURVEY 8d); the kernel answers the same cells from one grid index over all "
                         "tracks (a segment's candidates = one contiguous run of 8-byte entries, read two at a time) "
                         "and touches only `traffic` DRAM bytes, so frac > 1 is expected: its real bound is the issue "
-                        "rate (1.44 G warp instructions per launch, issue slots 82 % busy; L2 serves ~11 GB per "
-                        "launch at 87 % hits) (profiles/r01_count_kernel_v16.txt)",
+                        "rate (1.33 G warp instructions per launch, issue slots 78 % busy, 29 of 32 lanes active; L2 "
+                        "serves ~10.5 GB per launch at 87 % hits) (profiles/r01_count_kernel_v21.txt)",
                 "algorithmic_bytes_per_launch": count_bytes, "kernel_ms": count_ms,
                 "kernel_share_of_step": prof["count"][0] / max(sum(v[0] for v in prof.values()), 1e-9),
                 "other_kernels": {"place_kernel_ms": place_ms, "contig_merge_kernel_ms": merge_ms,
