@@ -519,15 +519,21 @@ __global__ void __launch_bounds__(128) shift_kernel(PlaceParams p)
         if (bounded_u32(r.z, r.w, 2u)) end = (int32_t)((uint32_t)start + length);       // :1086-1090
         else { end = start; start = (int32_t)((uint32_t)end - length); }
         const int32_t lws = (int32_t)L.s(0), lwe = (int32_t)L.e(L.k - 1u);              // :1093 ws.min(), ws.max()
+        // one forward and one backward fill at most; their order does not matter (the pieces are sorted later)
+        // and a fill of 0 bases returns nothing, so each walk is instantiated once in the kernel
+        uint32_t fs_start, fe_end = 0;
+        int32_t fs_rem, fe_rem = 0;
         if (start < lws) {                                                               // :1096-1100
             const int32_t remainder = min(lws - start, (int32_t)length);
-            fill_from_start(L, total, (uint32_t)start, (int32_t)(length - (uint32_t)remainder), emit);
-            fill_from_end(L, total, (uint32_t)lwe, remainder, emit);
+            fs_start = (uint32_t)start; fs_rem = (int32_t)(length - (uint32_t)remainder);
+            fe_end = (uint32_t)lwe; fe_rem = remainder;
         } else if (end > lwe) {                                                          // :1101-1105
             const int32_t remainder = min(end - lwe, (int32_t)length);
-            fill_from_end(L, total, (uint32_t)end, (int32_t)(length - (uint32_t)remainder), emit);
-            fill_from_start(L, total, (uint32_t)lws, remainder, emit);
-        } else fill_from_start(L, total, (uint32_t)start, (int32_t)length, emit);       // :1107
+            fe_end = (uint32_t)end; fe_rem = (int32_t)(length - (uint32_t)remainder);
+            fs_start = (uint32_t)lws; fs_rem = remainder;
+        } else { fs_start = (uint32_t)start; fs_rem = (int32_t)length; }                // :1107
+        if (fs_rem > 0) fill_from_start(L, total, fs_start, fs_rem, emit);
+        if (fe_rem > 0) fill_from_end(L, total, fe_end, fe_rem, emit);
     }
     __syncwarp();
     const uint32_t n = *counter;

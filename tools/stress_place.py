@@ -15,6 +15,35 @@ import helpers  # noqa: E402
 from gat_b200 import device  # noqa: E402
 from oracle import oracle  # noqa: E402
 
+if "--shift" in sys.argv:          # SamplerShift instead: python tools/stress_place.py --shift [n_units] [seed]
+    sys.argv.remove("--shift")
+    n_units = int(sys.argv[1]) if len(sys.argv) > 1 else 600
+    seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 2024
+    rng = np.random.default_rng(seed0)
+    ctx = device.Context(0)
+    npieces = nover = 0
+    for it in range(n_units):
+        segs, ws = helpers.random_unit(rng)
+        kw = [dict(radius=2, extension=0), dict(radius=float(rng.choice([0.25, 0.5, 1, 3, 7.5, 40])), extension=0),
+              dict(radius=2, extension=int(rng.choice([1, 10, 101, 1000, 5000, 200000])))][it % 3]
+        smp = device.Sampler(ctx, [0], 1, False, [segs], [ws], bucket_size=0)
+        smp.set_shift(**kw)
+        placed, status = smp.place(seed=seed0 + it, track=it % 5, sample_begin=100, n_samples=8)
+        smp.close()
+        for s in range(8):
+            exp = oracle.sampler_shift(segs, ws, philox=(seed0 + it, it % 5, 0, 100 + s), **kw)
+            if status[s, 0] & device.UNIT_OVERFLOW:
+                nover += 1
+                continue
+            npieces += len(exp)
+            if not np.array_equal(placed[s][0], exp):
+                print("MISMATCH unit %i sample %i" % (it, s), kw, placed[s][0][:4], exp[:4])
+                sys.exit(1)
+    print("ok: SamplerShift, %i units x 8 samples identical to the oracle (%i pieces, %i samples over capacity)"
+          % (n_units, npieces, nover))
+    ctx.close()
+    sys.exit(0)
+
 n_units = int(sys.argv[1]) if len(sys.argv) > 1 else 600
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 2024
 rng = np.random.default_rng(seed0)
