@@ -90,6 +90,12 @@ def test_isochore_round_trip():
     d3.toIsochores(iso, truncate=True)
     d3.fromIsochores()
     assert d3["chr1"].asList() == [(100, 200)]
+    # a key with a second "." cannot be split into (contig, isochore): ValueError, as in the reference
+    # (gat/Engine.pyx:2864-2865)
+    d4 = Engine.IntervalDictionary()
+    d4.add("chr1.random.lo", SL([(0, 10)]))
+    with pytest.raises(ValueError):
+        d4.fromIsochores()
 
 
 def test_collection_collapse_merge_restrict():
