@@ -401,10 +401,14 @@ class SamplerShift(Sampler):
         smp.set_shift(self.radius, self.extension)
         call = _rng_state["calls"]
         _rng_state["calls"] += 1
-        placed, status = smp.place(getSeed(), 0xFFFFFF, call, 1)
-        smp.close()
-        if status[0, 0] & _dev.UNIT_OVERFLOW:
-            raise MemoryError("SamplerShift: the moved segments were cut into more pieces than the buffer holds")
+        try:
+            placed, status = smp.place(getSeed(), 0xFFFFFF, call, 1)
+        except _dev._lib.GatB200Error as e:
+            if e.code == _dev._lib.ERR_CAPACITY:
+                raise MemoryError("SamplerShift: the moved segments were cut into more pieces than the buffer holds")
+            raise
+        finally:
+            smp.close()
         r = SegmentList(array=placed[0][0])
         r._normalized = True
         return r
