@@ -41,6 +41,39 @@ def allgather_samples(local, num_samples, dim=0):
     return out.movedim(0, dim).contiguous()
 
 
+def column_range(n_columns, rank, world):
+    """[begin, end) of the annotation columns whose statistics `rank` computes (exchange_columns)"""
+    return (rank * n_columns) // world, ((rank + 1) * n_columns) // world
+
+
+def exchange_columns(local, num_samples):
+    """The alternative to allgather_samples for very large S: instead of the whole S x A matrix
+    on every rank, rank g ends up with ALL samples of its own columns column_range(A, g, G) -- 1/G of the
+    all-gather's traffic and memory, and the column statistics (which are independent per column) run on A/G
+    columns per GPU.  `local` = this rank's [shard_range(num_samples) rows][A] slab; returns [num_samples][A_g].
+    One all_to_all_single with uneven splits (NCCL on GPUs, gloo in the CPU test).  gat_b200.run() uses the
+    all-gather (the gathered matrix of every BASELINE configuration is read by the statistics kernels in
+    < 1 ms); this is the building block for runs whose S x A does not fit next to the index."""
+    import torch.distributed as dist
+    rank, world = rank_world()
+    if world == 1:
+        return local
+    A = local.shape[1]
+    rows = [shard_range(num_samples, r, world) for r in range(world)]
+    cols = [column_range(A, r, world) for r in range(world)]
+    n_mine = rows[rank][1] - rows[rank][0]
+    a_mine = cols[rank][1] - cols[rank][0]
+    assert local.shape[0] == n_mine, "slab does not match this rank's shard"
+    # send buffer: for every destination rank its columns of my rows, row-major, back to back
+    send = torch.cat([local[:, b:e].reshape(-1) for b, e in cols])
+    in_splits = [n_mine * (e - b) for b, e in cols]
+    out_splits = [(e - b) * a_mine for b, e in rows]
+    recv = torch.empty(sum(out_splits), dtype=local.dtype, device=local.device)
+    dist.all_to_all_single(recv, send, output_split_sizes=out_splits, input_split_sizes=in_splits)
+    # pieces arrive in source-rank order = global sample order
+    return recv.view(num_samples, a_mine) if a_mine else recv.view(num_samples, 0)
+
+
 def init_from_env(backend=None):
     """join the process group described by RANK/WORLD_SIZE/MASTER_* (set by torch.distributed.run);
     a plain single-process start does nothing."""

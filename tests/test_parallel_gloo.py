@@ -24,6 +24,13 @@ WORKER = textwrap.dedent("""
         assert got.shape == full.shape and torch.equal(got, full), (S, rank)
         got0 = parallel.allgather_samples(full[0, b:e, :].contiguous().double(), S, dim=0)
         assert torch.equal(got0, full[0].double())
+    # all-to-all by annotation column: every rank ends up with all samples of its own columns
+    for S, A in ((10, 6), (11, 5), (3, 1), (7, 9)):
+        b, e = parallel.shard_range(S, rank, world)
+        full = (torch.arange(S, dtype=torch.int32).view(S, 1) * 1000 + torch.arange(A, dtype=torch.int32).view(1, A))
+        mine = parallel.exchange_columns(full[b:e].contiguous(), S)
+        cb, ce = parallel.column_range(A, rank, world)
+        assert mine.shape == (S, ce - cb) and torch.equal(mine, full[:, cb:ce]), (S, A, rank)
     parallel.finalize()
     print("rank", rank, "ok")
 """)
