@@ -252,6 +252,35 @@ def test_sampler_shift_matches_reference_under_numpy_rng(oracle):
     assert nonempty >= 50
 
 
+def test_sampler_shift_invariants_under_philox(oracle):
+    """properties of the shift that hold for any RNG, checked on the oracle under the kernel's Philox stream:
+    the sample is normalized, lies inside the workspace, never holds more bases than the working segments
+    (bases are only lost where two moved segments overlap), is a pure function of (seed, track, unit, sample),
+    and a segment whose window holds no workspace drops out (the reference's ignored ValueError)"""
+    from tests import helpers
+    rng = np.random.default_rng(404)
+    for it in range(60):
+        segs, ws = helpers.random_unit(rng)
+        kw = [dict(radius=2, extension=0), dict(radius=0.5, extension=0), dict(radius=2, extension=600)][it % 3]
+        key = (1000 + it, it % 3, 0, 5)
+        got = oracle.sampler_shift(segs, ws, philox=key, **kw)
+        again = oracle.sampler_shift(segs, ws, philox=key, **kw)
+        assert np.array_equal(got, again)
+        if len(got):
+            assert (got[:, 0] < got[:, 1]).all() and (got[1:, 0] >= got[:-1, 1]).all()       # normalized
+            assert oracle.overlap_with_segments(got, ws) == int((got[:, 1] - got[:, 0]).sum())   # inside
+        working = oracle.filter_(segs, ws)
+        assert int((got[:, 1] - got[:, 0]).sum()) <= int((working[:, 1] - working[:, 0]).sum())
+    # extension = 4: a segment is wrapped inside the 4 workspace bases around its midpoint (a fill longer than
+    # the local workspace returns the local workspace, gat/SegmentList.pyx:1325-1326); the window of the second
+    # segment, [1003, 1007), lies in the workspace gap, so that segment drops out
+    ws = np.array([[0, 1000], [5000, 6000]], dtype=np.uint32)
+    segs = np.array([[100, 200], [990, 1020]], dtype=np.uint32)
+    for sample in range(8):
+        got = oracle.sampler_shift(segs, ws, radius=2, extension=4, philox=(1, 0, 0, sample))
+        assert got.tolist() == [[148, 152]], got.tolist()
+
+
 def _parse_counts(text):
     rows = []
     for line in text.splitlines()[1:]:
