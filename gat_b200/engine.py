@@ -159,18 +159,59 @@ class IntervalDictionary(IntervalContainer):
     def intersect(self, other):
         self._apply(other, "intersect")
 
-    def toIsochores(self, isochores, truncate=False):
+    def toIsochores(self, isochores, truncate=False, _pieces=None):
         """split key `contig` into `contig.isochore` per isochore track (gat/Engine.pyx:2837-2855)"""
         for contig in list(self.intervals.keys()):
             s = self.intervals[contig]
-            for iso_track, iso in isochores.items():
-                n = s.clone()
-                if truncate:
-                    n.intersect(iso[contig])
-                else:
-                    n.filter(iso[contig])
-                self.intervals["%s.%s" % (contig, iso_track)] = n
+            if not (truncate and self._truncate_all(contig, s, isochores, _pieces)):
+                for iso_track, iso in isochores.items():
+                    n = s.clone()
+                    if truncate:
+                        n.intersect(iso[contig])
+                    else:
+                        n.filter(iso[contig])
+                    self.intervals["%s.%s" % (contig, iso_track)] = n
             del self.intervals[contig]
+
+    def _truncate_all(self, contig, s, isochores, cache=None):
+        """`s.clone().intersect(iso[contig])` for every isochore track in ONE pass: the pieces of all tracks on
+        the contig form one sorted disjoint list when the isochores do not overlap each other (the usual case: they
+        partition the genome), so a single pair of searches gives every (segment, piece) pair and the piece's track
+        says where the truncated segment goes.  Same lists, same order as the per-track loop; returns False
+        (nothing done) when the isochore tracks overlap or a list is not normalized."""
+        if cache is not None and contig in cache:          # (the same isochores for every track of a collection)
+            tracks, pieces, label = cache[contig]
+        else:
+            tracks = [(t, iso[contig]) for t, iso in isochores.items()]
+            pieces = label = None
+            arrs = [p.asarray() for _, p in tracks]
+            if all(p.isNormalized for _, p in tracks) and sum(len(a) for a in arrs) > 0:
+                pieces = np.concatenate(arrs)
+                label = np.repeat(np.arange(len(arrs)), [len(a) for a in arrs])
+                order = np.argsort(pieces[:, 0], kind="stable")
+                pieces, label = pieces[order], label[order]
+                if len(pieces) > 1 and (pieces[1:, 0] < pieces[:-1, 1]).any():
+                    pieces = label = None
+            if cache is not None:
+                cache[contig] = (tracks, pieces, label)
+        if pieces is None or len(s) == 0 or not s.isNormalized:
+            return False
+        a = s.asarray()
+        j1 = np.searchsorted(pieces[:, 1], a[:, 0], side="right")       # first piece ending after the start
+        j2 = np.maximum(j1, np.searchsorted(pieces[:, 0], a[:, 1], side="left"))
+        cnt = j2 - j1
+        total = int(cnt.sum())
+        rep = np.repeat(np.arange(len(a)), cnt)
+        pj = np.repeat(j1, cnt) + (np.arange(total) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+        out = np.empty((total, 2), dtype=np.uint32)
+        out[:, 0] = np.maximum(a[rep, 0], pieces[pj, 0])
+        out[:, 1] = np.minimum(a[rep, 1], pieces[pj, 1])
+        where = label[pj]
+        for i, (t, _) in enumerate(tracks):
+            n = SegmentList(array=out[where == i])
+            n._normalized = True
+            self.intervals["%s.%s" % (contig, t)] = n
+        return True
 
     def fromIsochores(self):
         """merge `contig.isochore` keys back into contigs; merge(0) when any key was split
@@ -266,8 +307,9 @@ class IntervalCollection(IntervalContainer):
             del self.intervals[track]
 
     def toIsochores(self, isochores, truncate=False):
+        pieces = {}             # per contig: the isochore pieces of all tracks as one sorted list (shared by the tracks)
         for vv in self.intervals.values():
-            vv.toIsochores(isochores, truncate)
+            vv.toIsochores(isochores, truncate, pieces)
 
     def fromIsochores(self):
         for vv in self.intervals.values():

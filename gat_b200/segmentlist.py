@@ -188,6 +188,9 @@ class SegmentList(object):
         if len(other._a) == 0:
             self._a = _EMPTY.copy()
             return
+        if self._normalized and len(other._a) == 1 and self._a[0, 0] >= other._a[0, 0] \
+                and self._a[-1, 1] <= other._a[0, 1]:
+            return          # every segment lies inside the single piece of other
         j1, j2 = self._overlap_range(other)
         self._a = self._a[j2 > j1]
 
@@ -200,6 +203,8 @@ class SegmentList(object):
         if len(other._a) == 0:
             self._a = _EMPTY.copy()
             return
+        if len(other._a) == 1 and self._a[0, 0] >= other._a[0, 0] and self._a[-1, 1] <= other._a[0, 1]:
+            return          # one piece that holds the whole (sorted) list, e.g. a whole-contig workspace: unchanged
         j1, j2 = self._overlap_range(other)
         cnt = j2 - j1
         total = int(cnt.sum())

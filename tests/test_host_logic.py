@@ -98,6 +98,47 @@ def test_isochore_round_trip():
         d4.fromIsochores()
 
 
+def test_truncating_isochore_split_equals_per_track_intersections():
+    """toIsochores(truncate=True) splits a contig's list over all isochore tracks in one pass when the tracks do
+    not overlap each other; the lists must be those of the reference's loop `clone(); intersect(iso[contig])`
+    per track (gat/Engine.pyx:2845-2852) -- random partitions, gaps, overlapping tracks (per-track path), empty
+    lists, and several tracks of a collection sharing the cached pieces"""
+    from tests import helpers
+
+    def sl(a):
+        x = SegmentList(array=a)
+        x._normalized = True
+        return x
+    rng = np.random.default_rng(9)
+    for it in range(150):
+        span = int(rng.choice([3000, 100000]))
+        niso = int(rng.integers(1, 5))
+        iso = Engine.IntervalCollection("iso")
+        if it % 5 == 0:                               # independent random lists: tracks may overlap each other
+            for i in range(niso):
+                iso.add("g%i" % i, "c", sl(helpers.random_list(rng, span, int(rng.integers(0, 8)), span // 6)))
+        else:                                         # tiles dealt to the tracks, some left out (gaps)
+            bounds = np.arange(0, span + 1, span // 20)
+            lab = rng.integers(0, niso + 1, len(bounds) - 1)
+            for i in range(niso):
+                m = lab == i
+                iso.add("g%i" % i, "c", sl(helpers.normalize(np.stack([bounds[:-1][m], bounds[1:][m]], axis=1))))
+        coll = Engine.IntervalCollection("x")
+        lists = {}
+        for t in range(3):
+            lists[t] = helpers.random_list(rng, span, int(rng.integers(0, 60)), int(rng.choice([20, 400, 5000])))
+            coll.add("t%i" % t, "c", sl(lists[t].copy()))
+        coll.toIsochores(iso, truncate=True)
+        for t in range(3):
+            got = coll["t%i" % t]
+            assert sorted(got.keys()) == sorted("c.%s" % k for k in iso.keys())
+            for k, vv in iso.items():
+                want = sl(lists[t].copy())
+                want.intersect(vv["c"])
+                assert got["c.%s" % k].asList() == want.asList(), (it, t, k)
+                assert got["c.%s" % k].isNormalized
+
+
 def test_collection_collapse_merge_restrict():
     c = Engine.IntervalCollection("ws")
     c.add("a", "chr1", SL([(0, 100)]))
