@@ -462,6 +462,36 @@ def make_observed_tutorial():
     np.savez_compressed(os.path.join(HERE, "observed_tutorial.npz"), **store)
 
 
+def make_prep_isochores(rng):
+    """the reference's own IO (buildSegments + applyIsochores, gat/IO.py:88-293) on small BED files WITH an
+    isochore file, default and --truncate-segments-to-workspace: every prepared list, for the host preparation
+    of gat_b200 (f1) to reproduce.  The BED texts travel in the fixture."""
+    from gat_b200 import synthetic
+    genome = [("chrA", 1500000), ("chrB", 700000), ("chrC", 300000)]
+    segments, annotations, workspaces, iso = synthetic.make(
+        n_segments=400, n_annotations=5, n_annotation_intervals=500, isochores=True, genome=genome,
+        isochore_tile=50000, n_isochores=3, seed=int(rng.integers(1, 1 << 30)))
+    out = {"files": {}, "cases": []}
+    with tempfile.TemporaryDirectory() as d:
+        argv = []
+        for name, coll, flag in (("segments", segments, "--segments"), ("annotations", annotations, "--annotations"),
+                                 ("workspace", workspaces, "--workspace"), ("iso", iso, "--isochore-file")):
+            path = os.path.join(d, name + ".bed")
+            synthetic.write_bed(coll, path, with_tracks=name in ("annotations", "iso"))
+            out["files"][name + ".bed"] = open(path).read()
+            argv.append("%s=%s" % (flag, path))
+        for extra in ([], ["--truncate-segments-to-workspace"]):
+            ropt, _ = gat.buildParser().parse_args(argv + extra)
+            rs, ra, rw, ri = RIO.buildSegments(ropt)
+            rws = RIO.applyIsochores(rs, ra, rw, ropt, ri,
+                                     truncate_segments_to_workspace=ropt.truncate_segments_to_workspace)
+            case = {"extra": extra, "workspace": dict((k, L(rws[k])) for k in rws.keys())}
+            for name, coll in (("segments", rs), ("annotations", ra)):
+                case[name] = dict((t, dict((k, L(coll[t][k])) for k in coll[t].keys())) for t in coll.tracks)
+            out["cases"].append(case)
+    return out
+
+
 def make_compare(rng):
     """scripts/gat-compare.py run by the reference on small count tables: within one file and between files"""
     import runpy
@@ -511,7 +541,7 @@ def main():
     # fixtures added after the first generation have their own seeds and can be (re)made alone:
     #   python tests/golden/make_golden.py sampler_segments
     extra = {"sampler_segments": (make_sampler_segments, 20260102), "compare": (make_compare, 20260103),
-             "sampler_shift": (make_sampler_shift, 20260104)}
+             "sampler_shift": (make_sampler_shift, 20260104), "prep_isochores": (make_prep_isochores, 20260105)}
     if "distribution_shift" in sys.argv[1:]:
         make_distribution(shift=(3.0, 0), name="distribution_shift")
         print("wrote distribution_shift")

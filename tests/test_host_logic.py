@@ -235,6 +235,39 @@ def test_input_preparation_matches_reference_io():
             assert np.array_equal(coll[track][key].asarray(), G.undelta(z["%s/%s/%s" % (name, track, key)])), (track, key)
 
 
+def test_isochore_preparation_matches_reference_io(tmp_path):
+    """buildSegments + applyIsochores WITH an isochore file (toIsochores of workspace, annotations and segments,
+    gat/IO.py:188-293) give the lists the reference's own IO gave for the same BED files -- default (segments
+    filtered per isochore) and --truncate-segments-to-workspace (tests/golden/prep_isochores.json)"""
+    import gat_b200
+    from gat_b200 import io as IO
+    data = G.load_json("prep_isochores")
+    argv = []
+    for name, flag in (("segments", "--segments"), ("annotations", "--annotations"), ("workspace", "--workspace"),
+                       ("iso", "--isochore-file")):
+        path = tmp_path / (name + ".bed")
+        path.write_text(data["files"][name + ".bed"])
+        argv.append("%s=%s" % (flag, path))
+    assert len(data["cases"]) == 2
+    for case in data["cases"]:
+        options, _ = gat_b200.buildParser().parse_args(argv + case["extra"])
+        segments, annotations, workspaces, isochores = IO.buildSegments(options)
+        workspace = IO.applyIsochores(segments, annotations, workspaces, options, isochores,
+                                      truncate_segments_to_workspace=options.truncate_segments_to_workspace)
+        assert sorted(workspace.keys()) == sorted(case["workspace"].keys())
+        for k, want in case["workspace"].items():
+            assert workspace[k].asList() == [tuple(x) for x in want], k
+        n = 0
+        for name, coll in (("segments", segments), ("annotations", annotations)):
+            assert sorted(coll.tracks) == sorted(case[name].keys())
+            for track, lists in case[name].items():
+                for k, want in lists.items():
+                    got = coll[track][k].asList() if k in coll[track] else []
+                    assert got == [tuple(x) for x in want], (name, track, k)
+                    n += 1
+        assert n > 40
+
+
 def test_bed_fast_reader_equals_line_reader(tmp_path, monkeypatch):
     """the Arrow fast path of IO.readFromBed and the line-by-line reader give the same tracks, the same key
     order and the same intervals; files it cannot take (track lines, comments, ragged rows) fall back"""
