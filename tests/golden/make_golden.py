@@ -492,6 +492,39 @@ def make_prep_isochores(rng):
     return out
 
 
+def make_output_tables(rng):
+    """the reference's IO.outputResults (gat/IO.py:457-538) on the results of one of its own small runs: q-values
+    over all results, one table per counter, every --output-order, BH and storey q-values, with and without
+    annotation descriptions.  Stored: what is needed to rebuild the result objects, and the tables' text."""
+    segments, annotations, workspace = small_problem(False, seed=int(rng.integers(1, 1 << 30)))
+    counters = ["nucleotide-overlap", "segment-overlap"]
+    results = ref_bench.run_full(segments, annotations, workspace, counters, 200, seed=5)
+    out = {"results": [], "cases": [], "headers": list(RE.AnnotatorResultExtended.headers),
+           "workspace_size": int(sum(int(workspace[k].sum()) for k in workspace.keys()))}
+    for r in results:
+        row = str(r).split("\t")
+        out["results"].append(dict(track=r.track, annotation=r.annotation, counter=r.counter, observed=float(r.observed),
+                                   expected=r.expected, stddev=r.stddev, fold=r.fold, pvalue=r.pvalue,
+                                   lower95=float(row[4]), upper95=float(row[5]), tail=row[11:]))
+    descriptions = dict((a, ["desc of %s" % a, "x"]) for a in sorted(set(r.annotation for r in results))[:3])
+    with tempfile.TemporaryDirectory() as d:
+        for order in ("track", "observed", "annotation", "fold", "pvalue", "qvalue"):
+            for method, with_desc in (("BH", False), ("storey", False), ("BH", True)):
+                class O(object):
+                    pass
+                O.qvalue_method, O.qvalue_lambda, O.qvalue_pi0_method = method, None, "smoother"
+                O.output_order = order
+                O.output_tables_pattern = os.path.join(d, "t_%s.tsv")
+                O.stdout = sys.stdout
+                rs = list(results)
+                RIO.outputResults(rs, O, RE.AnnotatorResultExtended.headers, ["description", "extra"] if with_desc else [],
+                                  2 if with_desc else 0, descriptions if with_desc else {})
+                tables = dict((c, open(os.path.join(d, "t_%s.tsv" % c)).read()) for c in counters)
+                out["cases"].append(dict(order=order, method=method, with_desc=with_desc, tables=tables))
+    out["descriptions"] = descriptions
+    return out
+
+
 def make_compare(rng):
     """scripts/gat-compare.py run by the reference on small count tables: within one file and between files"""
     import runpy
@@ -541,7 +574,8 @@ def main():
     # fixtures added after the first generation have their own seeds and can be (re)made alone:
     #   python tests/golden/make_golden.py sampler_segments
     extra = {"sampler_segments": (make_sampler_segments, 20260102), "compare": (make_compare, 20260103),
-             "sampler_shift": (make_sampler_shift, 20260104), "prep_isochores": (make_prep_isochores, 20260105)}
+             "sampler_shift": (make_sampler_shift, 20260104), "prep_isochores": (make_prep_isochores, 20260105),
+             "output_tables": (make_output_tables, 20260106)}
     if "distribution_shift" in sys.argv[1:]:
         make_distribution(shift=(3.0, 0), name="distribution_shift")
         print("wrote distribution_shift")

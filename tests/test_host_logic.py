@@ -318,6 +318,41 @@ def test_extended_result_rows_match_reference(tag):
     assert n >= 12
 
 
+def test_output_tables_match_reference(tmp_path):
+    """IO.outputResults (gat/IO.py:457-538): q-values over all results of the run, one table per counter, rows in
+    --output-order, optional annotation descriptions -- the text equals what the reference wrote for its own
+    results (tests/golden/output_tables.json: six orders x {BH, storey, BH with descriptions})"""
+    from gat_b200 import io as IO
+    data = G.load_json("output_tables")
+    sizes_keys = ("track_nsegments", "track_size", "annotation_nsegments", "annotation_size", "overlap_nsegments",
+                  "overlap_size")
+    assert data["headers"] == Engine.AnnotatorResultExtended.headers
+
+    def build():
+        res = []
+        for r in data["results"]:
+            tail = r["tail"]
+            sizes = dict(zip(sizes_keys, [int(tail[0]), int(tail[1]), int(tail[3]), int(tail[4]), int(tail[6]), int(tail[7])]))
+            sizes["workspace_size"] = data["workspace_size"]
+            stats = dict((k, r[k]) for k in ("expected", "stddev", "fold", "pvalue", "lower95", "upper95"))
+            res.append(Engine.AnnotatorResultExtended(r["track"], r["annotation"], r["counter"], r["observed"],
+                                                      np.zeros(1), None, None, None, stats=stats, sizes=sizes))
+        return res
+
+    for case in data["cases"]:
+        class O(object):
+            pass
+        O.qvalue_method, O.qvalue_lambda, O.qvalue_pi0_method = case["method"], None, "smoother"
+        O.output_order = case["order"]
+        O.output_tables_pattern = str(tmp_path / "t_%s.tsv")
+        desc = data["descriptions"] if case["with_desc"] else {}
+        IO.outputResults(build(), O, Engine.AnnotatorResultExtended.headers,
+                         ["description", "extra"] if case["with_desc"] else [], 2 if case["with_desc"] else 0, desc)
+        for counter, want in case["tables"].items():
+            got = open(str(tmp_path / ("t_%s.tsv" % counter))).read()
+            assert got == want, (case["order"], case["method"], case["with_desc"], counter)
+
+
 def test_bed_fast_reader_equals_line_reader(tmp_path, monkeypatch):
     """the Arrow fast path of IO.readFromBed and the line-by-line reader give the same tracks, the same key
     order and the same intervals; files it cannot take (track lines, comments, ragged rows) fall back"""
