@@ -525,6 +525,19 @@ def make_output_tables(rng):
     return out
 
 
+def make_parser_options(rng):
+    """every option of the reference's gat.buildParser() (gat/__init__.py:190-427): flags, action, type, default"""
+    p = gat.buildParser()
+    out = {}
+    for o in p._get_all_options():
+        if o.dest:
+            d = p.defaults.get(o.dest)
+            out[o.dest] = dict(flags=sorted(o._long_opts + o._short_opts), action=o.action, type=o.type,
+                               default=d if isinstance(d, (int, float, str, bool, list, type(None))) else str(d),
+                               choices=list(o.choices) if o.choices else None)
+    return out
+
+
 def make_compare(rng):
     """scripts/gat-compare.py run by the reference on small count tables: within one file and between files"""
     import runpy
@@ -575,7 +588,7 @@ def main():
     #   python tests/golden/make_golden.py sampler_segments
     extra = {"sampler_segments": (make_sampler_segments, 20260102), "compare": (make_compare, 20260103),
              "sampler_shift": (make_sampler_shift, 20260104), "prep_isochores": (make_prep_isochores, 20260105),
-             "output_tables": (make_output_tables, 20260106)}
+             "output_tables": (make_output_tables, 20260106), "parser_options": (make_parser_options, 20260107)}
     if "distribution_shift" in sys.argv[1:]:
         make_distribution(shift=(3.0, 0), name="distribution_shift")
         print("wrote distribution_shift")

@@ -194,6 +194,26 @@ def test_parser_flags_and_defaults():
     assert d.output_order == "fold" and d.pvalue_method == "empirical" and d.counters == []
 
 
+def test_parser_equals_reference_option_for_option():
+    """buildParser() offers every option of the reference's gat.buildParser() with the same flags, action, type,
+    choices and default (tests/golden/parser_options.json), and none of its own"""
+    import gat_b200
+    ref = G.load_json("parser_options")
+    p = gat_b200.buildParser()
+    mine = {}
+    for o in p._get_all_options():
+        if o.dest:
+            mine[o.dest] = dict(flags=sorted(o._long_opts + o._short_opts), action=o.action, type=o.type,
+                                default=p.defaults.get(o.dest), choices=list(o.choices) if o.choices else None)
+    assert sorted(mine) == sorted(ref)
+    for dest, want in ref.items():
+        got = mine[dest]
+        for k in ("flags", "action", "type", "choices"):
+            assert got[k] == want[k], (dest, k, got[k], want[k])
+        # (an absent list default reads as None in the reference and as [] here: both are "no files")
+        assert got["default"] == want["default"] or (not got["default"] and not want["default"]), dest
+
+
 def test_bed_reader_tracks(tmp_path):
     from gat_b200 import io as IO
     f = tmp_path / "x.bed"
