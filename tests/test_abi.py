@@ -26,6 +26,25 @@ def test_library_exports_every_declared_symbol():
     assert lib.gatb_version() == 100
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/gat_b200.h compiles as strict C99 (no C++ or torch types at the boundary) and a C program
+    that uses only the header links against libgat_b200.so and runs (no device needed for gatb_version)"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use.c"
+    src.write_text('#include <stdio.h>\n#include "gat_b200.h"\n'
+                   'int main(void) { gatb_ctx *c = 0; (void)c; printf("%d %d\\n", gatb_version(), GATB_NCOUNTERS); return GATB_OK; }\n')
+    lib_dir = os.path.join(ROOT, "gat_b200", "lib")
+    exe = tmp_path / "use"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", lib_dir, "-lgat_b200", "-Wl,-rpath," + lib_dir])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert out == ["100", "7"]
+
+
 def test_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
