@@ -1,25 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- samples/sec of the GAT simulation hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config ns|c2|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Workload (config.workload): the metric's own shape -- synthetic hg19 (24 contigs), 10 000 segments
-against 1 000 annotation tracks of 20 000 intervals, contig workspace, nucleotide-overlap counter.
+Workload (config.workload): by default the metric's own shape ("ns") -- synthetic hg19 (24 contigs), 10 000
+segments against 1 000 annotation tracks of 20 000 intervals, contig workspace, nucleotide-overlap counter;
+--config c2..c5 are the other BASELINE.json configurations (50 tracks; 8 GC isochores + segment-overlap;
+50 000 segments x 1 000 tracks; 200 tracks).
 A step = one pass of the hot path (placement of every unit + counting against every annotation) over
-one batch of `--samples-per-step` Monte-Carlo samples per GPU; sample indices advance every step, so no
-step repeats another's work.  Weak scaling: every rank runs the same batch size on its own shard of the
-global sample index space; for N > 1 the per-step count slab is all-gathered over NCCL (the path's one
-exchange step) inside the timed region; the all-gather of a step runs asynchronously and overlaps the next
-step's kernels (two output slabs), the last ones are waited for before the closing event.
+`--batches-per-step` internal batches of `--batch` Monte-Carlo samples per GPU (default 24 x 4096 = 98 304 samples,
+~60 ms on one B200, so that 20 steps are > 1 s of sustained load); sample indices advance every step, so no step
+repeats another's work.  Weak scaling: every rank runs the same number of samples on its own shard of the global
+sample index space; for N > 1 the per-step count slab is all-gathered over NCCL (the path's one exchange step)
+inside the timed region; the all-gather of a step runs asynchronously and overlaps the next step's kernels (two
+output slabs), the last ones are waited for before the closing event.
 
 value   whole-job samples/s, inputs resident in HBM, counts left in HBM (CUDA events, max over ranks)
-e2e     same metric through the C ABI with HOST buffers: every step uploads segments, workspace and
-        annotations from pinned host memory (gatb_sampler_create / gatb_annotations_create_async), runs, and
-        reads the count matrix back to the host; double-buffered -- the annotation upload and index build of
-        step i+1 are queued before gatb_run of step i and overlap its kernels
-roofline  dominant kernel (counting): SURVEY 8d algorithmic bytes per launch / CUDA-event kernel time
+e2e     same metric through the C ABI with HOST buffers: every step uploads segments, workspace and annotations
+        from pinned host memory (gatb_sampler_create / gatb_annotations_create_async), runs, (N > 1: all-gathers
+        the slab,) and reads the step's count matrix back to pinned host memory; double-buffered -- the annotation
+        upload and index build of step i+1 are queued before gatb_run of step i and overlap its kernels
+parity_check   two samples of the last timed step's slab recomputed by the CPU oracle (outside the timed region)
+gather_check   N > 1: every rank's rows of the gathered matrix of one step recomputed on rank 0 alone
+roofline  dominant kernel (counting), see roofline_of(): output-sensitive bytes against the measured L2 peak,
+          compulsory DRAM bytes against the measured HBM peak, issue rate against the measured issue peak
 cpu_baseline  the reference itself (oracle/_ref) on the host cores, bounded sample, rank 0, N=1
 """
 import argparse
@@ -36,26 +42,50 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-METRIC = "samples/sec (10k segs x 1k annotations)"
 UNIT = "samples/s"
+SEED = 20260101
+
+# BASELINE.json configs: (segments, annotation tracks, isochores, counter, metric label)
+CONFIGS = {
+    "ns": dict(segments=10000, annotations=1000, isochores=False, counter="nucleotide-overlap",
+               metric="samples/sec (10k segs x 1k annotations)"),
+    "c2": dict(segments=10000, annotations=50, isochores=False, counter="nucleotide-overlap",
+               metric="samples/sec (10k segs x 50 annotations)"),
+    "c3": dict(segments=10000, annotations=50, isochores=True, counter="segment-overlap",
+               metric="samples/sec (10k segs x 50 annotations, 8 GC isochores, segment-overlap)"),
+    "c4": dict(segments=50000, annotations=1000, isochores=False, counter="nucleotide-overlap",
+               metric="samples/sec (50k segs x 1k annotations)"),
+    "c5": dict(segments=10000, annotations=200, isochores=False, counter="nucleotide-overlap",
+               metric="samples/sec (10k segs x 200 annotations)"),
+}
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--segments", type=int, default=10000)
-    ap.add_argument("--annotations", type=int, default=1000)
+    ap.add_argument("--config", default="ns", choices=sorted(CONFIGS))
+    ap.add_argument("--segments", type=int, default=None)
+    ap.add_argument("--annotations", type=int, default=None)
     ap.add_argument("--annotation-intervals", type=int, default=20000)
-    ap.add_argument("--samples-per-step", type=int, default=4096)
-    ap.add_argument("--counter", default="nucleotide-overlap")
-    ap.add_argument("--isochores", action="store_true")
+    ap.add_argument("--batch", type=int, default=4096, help="samples per internal placement / counting batch")
+    ap.add_argument("--batches-per-step", type=int, default=24)
+    ap.add_argument("--counter", default=None)
+    ap.add_argument("--isochores", action="store_true", default=None)
     ap.add_argument("--cpu-samples", type=int, default=0, help="reference samples (0 = about 10-30 s worth)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-checks", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    for k in ("segments", "annotations", "counter", "isochores"):
+        if getattr(args, k) is None:
+            setattr(args, k, cfg[k])
+    args.metric = cfg["metric"]
+    args.samples_per_step = args.batch * args.batches_per_step
+    return args
 
 
 # ------------------------------------------------------------------------------------------- workload
@@ -74,24 +104,25 @@ def build_workload(args):
     ws_csr = device.to_csr(problem.unit_workspace)
     n_a_total = int(anno_csr[0][-1])
     wl = dict(problem=problem, A=A, C=C, nseg=np.array(nseg, dtype=np.uint32), anno_csr=anno_csr, seg_csr=seg_csr,
-              ws_csr=ws_csr, n_a_total=n_a_total, n_segments=int(seg_csr[0][-1]),
+              ws_csr=ws_csr, n_a_total=n_a_total, n_segments=int(seg_csr[0][-1]), lists=lists,
               collections=(segments, annotations, workspace))
     return wl
 
 
 def config_of(args, wl, world):
-    return {"workload": "synthetic hg19 (24 contigs, contig workspace%s): %i segments x %i annotation tracks "
+    return {"workload": "%s: synthetic hg19 (24 contigs, contig workspace%s): %i segments x %i annotation tracks "
                         "(%i intervals after normalize), counter %s, sampler annotator"
-                        % (", 8 GC isochores" if args.isochores else "", wl["n_segments"], wl["A"],
+                        % (args.config, ", 8 GC isochores" if args.isochores else "", wl["n_segments"], wl["A"],
                            wl["n_a_total"], args.counter),
             "samples_per_step_per_gpu": args.samples_per_step,
+            "batch": args.batch, "batches_per_step": args.batches_per_step,
             "global_samples_per_step": args.samples_per_step * world,
             "parallelism": "samples sharded over %i GPU(s), inputs replicated, one NCCL all-gather of the "
                            "count slab per step" % world if world > 1 else "1 GPU",
-            "l2": "inputs larger than L2: annotation grid index (offsets + 8-byte entries, ~2.3 entries per "
-                  "interval) ~%.0f MB + %.0f MB of placed segments per batch; sample indices advance every step"
-                  % (wl["n_a_total"] * 2.33 * 8 / 1e6 + 12, args.samples_per_step * wl["n_segments"] * 8 / 1e6),
-            "data_seed": 20260101}
+            "l2": "inputs larger than L2: annotation grid index ~%.0f MB + %.0f MB of placed segments per batch; "
+                  "sample indices advance every step"
+                  % (wl["n_a_total"] * 2.33 * 8 / 1e6 + 12, args.batch * wl["n_segments"] * 8 / 1e6),
+            "data_seed": SEED}
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -109,7 +140,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -118,9 +149,12 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -128,22 +162,25 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        for t, row in self.rows:
+            if t_begin is not None and not (t_begin <= t <= t_end):
+                continue
             f = [x.strip() for x in row.split(",")]
             if len(f) < 9:
                 continue
             try:
                 sm.append(float(f[1]))
                 smax = float(f[2])
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
 def measured_peak():
@@ -156,8 +193,9 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """DRAM bytes per count-kernel launch from the committed ncu --set full capture, if any"""
+def ncu_facts():
+    """per-launch facts of the counting kernel that only ncu can give (warp instructions, DRAM bytes), from the
+    committed capture of the same command (profiles/count_kernel_traffic.json)"""
     p = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
     if os.path.exists(p):
         try:
@@ -165,6 +203,18 @@ def ncu_traffic():
         except Exception:
             return None
     return None
+
+
+def microbench(lib, device_index):
+    out = {}
+    buf = np.zeros(4, dtype=np.float64)
+    from gat_b200 import device
+    if lib.gatb_microbench(device_index, 0, 48 << 20, 5, device._p(buf)) == 0:
+        out["l2_read_gbs"] = float(buf[0])
+    if lib.gatb_microbench(device_index, 1, 0, 5, device._p(buf)) == 0:
+        out["issue_gwarp_inst_s"] = float(buf[0])
+        out["sms"] = int(buf[3])
+    return out
 
 
 # ---------------------------------------------------------------------------------------- reference arm
@@ -215,7 +265,7 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     t0 = time.perf_counter()
     rate, cores, sample = reference_rate(args, wl, seconds_target=min(30.0, 20.0 * max(args.steps, 1) / 5.0))
-    line = {"metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"metric": args.metric, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * args.samples_per_step / rate,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic", "impl": "reference", "config": config_of(args, wl, world),
@@ -223,6 +273,80 @@ def run_reference(args):
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- roofline
+def roofline_of(args, wl, ctx, smp, annos, prof, local):
+    """The counting kernel against three measured machine limits.  All byte counts are PER LAUNCH (= one batch)
+    and recomputable from `config` plus the counters in `work`:
+
+    l2    output-sensitive bytes = 8 * pairs + 8 * P * batch + index_bytes, where pairs = truly overlapping
+          (segment, interval) pairs of the batch (sum of the GATB_OVERLAP_PIECES plane: every pair's 8-byte
+          index entry has to reach an SM at least once), P = placed segments per sample (8 bytes each, read
+          once), index_bytes = offsets + entries of the grid index (read once);  peak = L2 read bandwidth
+          measured by gatb_microbench on this GPU.  This is the `roofline` the line reports (frac <= 1).
+    hbm   compulsory DRAM bytes = index_bytes + 8 * P * batch + 4 * A * batch (counts out) against the measured
+          HBM copy bandwidth (MEASURED_PEAKS.json): how far from HBM-bound the kernel is.
+    issue warp instructions per launch (ncu capture of the same command, committed) / kernel time against the
+          measured issue peak: what actually limits the kernel.
+    reference_algorithm_equivalent: the SURVEY 8d bytes of the reference's two-pointer merge (every cell streams
+          its sample and its annotation list) -- what the same answers would cost without the index."""
+    from gat_b200 import device
+    import torch
+    B, A = args.batch, wl["A"]
+    count_ms = prof["count"][0] / max(prof["count"][1], 1)
+    place_ms = prof["place"][0] / max(prof["place"][1], 1)
+    merge_ms = prof["merge"][0] / max(prof["merge"][1], 1)
+    # work counters of one batch: pairs from the overlap-pieces counter, tested entries from the index geometry
+    dev = torch.device("cuda", local)
+    plane = torch.zeros((1, B, A), dtype=torch.int32, device=dev)
+    begin = 7 * 10 ** 6
+    info = smp.run(annos, ["overlap-pieces"], SEED, 0, begin, B, out_counts_ptr=plane.data_ptr())
+    pairs = int(plane.to(torch.int64).sum().item())
+    work = np.zeros(4, dtype=np.uint64)
+    ctx.check(ctx.lib.gatb_count_work(smp.handle, annos.handle, B, device._p(work)))
+    segs, tested, n_entries, index_bytes = (int(x) for x in work)
+    placed_per_sample = segs / float(B)
+    mb = microbench(ctx.lib, local)
+    hbm_peak, hbm_src = measured_peak()
+    l2_bytes = 8.0 * pairs + 8.0 * segs + index_bytes
+    hbm_bytes = index_bytes + 8.0 * segs + 4.0 * A * B
+    ref_bytes = B * (8.0 * (A * placed_per_sample + wl["n_a_total"]) + 4.0 * A)
+    sec = count_ms / 1000.0
+    l2_peak = mb.get("l2_read_gbs")
+    facts = ncu_facts() or {}
+    roof = {"bound": "l2", "kernel": "count_kernel", "achieved": l2_bytes / sec / 1e9, "peak": l2_peak, "unit": "GB/s",
+            "frac": (l2_bytes / sec / 1e9 / l2_peak) if l2_peak else None,
+            "peak_source": "gatb_microbench: L2 read bandwidth measured in this run (48 MB buffer, 16-byte loads, all SMs)",
+            "formula": "achieved = (8*pairs + 8*placed_segments + index_bytes) / kernel_ms; all per launch of `batch` samples",
+            "kernel_ms": count_ms, "algorithmic_bytes_per_launch": l2_bytes,
+            "work": {"batch": B, "placed_segments": segs, "overlapping_pairs": pairs, "entries_tested": tested,
+                     "index_entries": n_entries, "index_bytes": index_bytes,
+                     "pairs_per_segment": pairs / max(segs, 1), "entries_tested_per_segment": tested / max(segs, 1),
+                     "tested_per_pair": tested / max(pairs, 1)},
+            "hbm": {"achieved": hbm_bytes / sec / 1e9, "peak": hbm_peak, "frac": hbm_bytes / sec / 1e9 / hbm_peak,
+                    "peak_source": hbm_src, "compulsory_bytes_per_launch": hbm_bytes},
+            "traffic": (facts["dram_bytes_per_sample"] * B) if "dram_bytes_per_sample" in facts else None,
+            "traffic_source": facts.get("capture"),
+            "issue": None,
+            "reference_algorithm_equivalent": {"bytes_per_launch": ref_bytes, "GBps": ref_bytes / sec / 1e9,
+                                               "x_hbm_peak": ref_bytes / sec / 1e9 / hbm_peak,
+                                               "note": "SURVEY 8d: what the reference's per-cell two-pointer merge "
+                                                       "streams; the index answers the same cells without it"},
+            "kernel_share_of_step": prof["count"][0] / max(sum(v[0] for v in prof.values()), 1e-9),
+            "other_kernels": {"place_kernel_ms": place_ms, "contig_merge_kernel_ms": merge_ms,
+                              "place_algorithmic_GBps": 16.0 * segs / max(place_ms, 1e-9) / 1e6,
+                              "placements_per_s": segs / max(place_ms, 1e-9) * 1e3}}
+    if mb.get("issue_gwarp_inst_s") and facts.get("warp_instructions_per_launch") and \
+            facts.get("samples_per_launch_in_capture") == B and facts.get("workload") == args.config:
+        rate = facts["warp_instructions_per_launch"] / sec / 1e9
+        roof["issue"] = {"achieved_gwarp_inst_s": rate, "peak_gwarp_inst_s": mb["issue_gwarp_inst_s"],
+                         "frac": rate / mb["issue_gwarp_inst_s"],
+                         "warp_instructions_per_launch": facts["warp_instructions_per_launch"],
+                         "source": facts.get("capture"),
+                         "peak_source": "gatb_microbench: independent LOP3 chains, 64 warps per SM, measured in this run "
+                                        "(nominal 4 x %i SMs x clock)" % mb.get("sms", 0)}
+    return roof, placed_per_sample
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -247,9 +371,10 @@ def run_ours(args):
     torch.cuda.set_device(dev)
 
     wl = build_workload(args)
-    pr, A, C, B = wl["problem"], wl["A"], wl["C"], args.samples_per_step
+    pr, A, C, S = wl["problem"], wl["A"], wl["C"], args.samples_per_step
     cid = device.COUNTER_ID[args.counter]
     is_density = cid == device.DENSITY
+    odt = torch.float64 if is_density else torch.int32
 
     ctx = device.Context(local)
     # a dedicated (non-default) stream: kernels, NCCL and the timing events all live on it; the legacy
@@ -257,29 +382,32 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    ctx.set_batch_size(B)
+    ctx.set_batch_size(args.batch)
     annos = device.Annotations(ctx, None, key_ws_nseg=wl["nseg"], csr=(A, C) + wl["anno_csr"])
     smp = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(wl["seg_csr"], wl["ws_csr"]))
     # two output slabs, used alternately: for N > 1 the all-gather of step i (NCCL, asynchronous, its own stream)
     # overlaps the placement and counting of step i + 1, which write the other slab
     nbuf = 2 if world > 1 else 1
-    out_us = [torch.zeros((1, B, A), dtype=torch.int32, device=dev) for _ in range(nbuf)]
-    out_fs = [torch.zeros((B, A), dtype=torch.float64, device=dev) if is_density else None for _ in range(nbuf)]
-    gathers = [torch.empty((world * B, A), dtype=torch.float64 if is_density else torch.int32, device=dev)
-               for _ in range(nbuf)] if world > 1 else None
+    outs = [torch.zeros((S, A), dtype=odt, device=dev) for _ in range(nbuf)]
+    gathers = [torch.empty((world * S, A), dtype=odt, device=dev) for _ in range(nbuf)] if world > 1 else None
     pending = [None] * nbuf
+
+    def run_into(t, begin, n):
+        if is_density:
+            return smp.run(annos, [args.counter], SEED, 0, begin, n, out_counts_ptr=None, out_density_ptr=t.data_ptr())
+        return smp.run(annos, [args.counter], SEED, 0, begin, n, out_counts_ptr=t.data_ptr())
+
+    def step_begin(i, r=None):
+        return (i * world + (rank if r is None else r)) * S      # global sample indices of a rank's shard
 
     def step(i):
         b = i % nbuf
         if pending[b] is not None:                 # the slab's previous all-gather must have read it
             pending[b].wait()
             pending[b] = None
-        begin = (i * world + rank) * B             # global sample indices of this rank's shard
-        info = smp.run(annos, [args.counter], 20260101, 0, begin, B, out_counts_ptr=out_us[b].data_ptr(),
-                       out_density_ptr=out_fs[b].data_ptr() if is_density else None)
+        info = run_into(outs[b], step_begin(i), S)
         if world > 1:
-            pending[b] = dist.all_gather_into_tensor(gathers[b], out_fs[b] if is_density else out_us[b][0],
-                                                     async_op=True)
+            pending[b] = dist.all_gather_into_tensor(gathers[b], outs[b], async_op=True)
         return info
 
     def drain():                                   # every all-gather in flight joins the launching stream
@@ -297,62 +425,74 @@ def run_ours(args):
     for i in range(args.warmup):
         info = step(i)
     drain()
-    placed_per_sample = float(info[0]) / B if args.warmup else None
 
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        time.sleep(0.2)
     barrier()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = clocks.mark()
     e0.record(stream)
     for i in range(args.steps):
         info = step(args.warmup + i)
     drain()                                        # the last all-gathers are inside the timed region
     e1.record(stream)
     barrier()
+    t_end = clocks.mark()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    clock_info = clocks.stop() if rank == 0 else None
-    placed_per_sample = float(info[0]) / B
-    value = world * B * args.steps / (ms / 1000.0)
+    clock_info = clocks.stop(t_begin, t_end) if rank == 0 else None
+    value = world * S * args.steps / (ms / 1000.0)
+    last = args.warmup + args.steps - 1
+
+    # ---- checks, outside the timed region: the slab of the last timed step against the CPU oracle, and (N > 1)
+    # the gathered matrix of that step against a single-rank recomputation of every rank's global indices
+    parity_check = gather_check = None
+    if not args.no_checks:
+        if rank == 0:
+            from oracle import oracle as O
+            slab = outs[last % nbuf]
+            bad = []
+            for row in (0, S - 1):
+                exp = O.compute_sample_philox(pr.unit_contig, pr.unit_segments, pr.unit_workspace, wl["lists"],
+                                              wl["nseg"], [args.counter], seed=SEED, track=0,
+                                              sample=step_begin(last) + row, has_isochores=pr.has_isochores)[0]
+                got = slab[row].cpu().numpy().astype(np.float64)
+                if not np.array_equal(got, exp):
+                    bad.append(row)
+            parity_check = "ok" if not bad else "MISMATCH in rows %s" % bad
+        if world > 1:
+            if rank == 0:
+                g = gathers[last % nbuf]
+                tmp = torch.zeros((S, A), dtype=odt, device=dev)
+                bad = []
+                for r in range(world):
+                    run_into(tmp, step_begin(last, r), S)
+                    torch.cuda.synchronize(dev)
+                    if not torch.equal(tmp, g[r * S:(r + 1) * S]):
+                        bad.append(r)
+                del tmp
+                gather_check = "ok" if not bad else "MISMATCH for ranks %s" % bad
+            barrier()
 
     # ---- per-kernel times (CUDA events around each launch, same stream), for the roofline
     ctx.profile(True)
-    nprof = max(1, min(args.steps, 3))
+    nprof = max(1, min(args.steps, 2))
     for i in range(nprof):
-        step(args.warmup + args.steps + i)
+        step(last + 1 + i)
     drain()
     prof = ctx.profile_read()
     ctx.profile(False)
-    count_ms = prof["count"][0] / max(prof["count"][1], 1)
-    place_ms = prof["place"][0] / max(prof["place"][1], 1)
-    merge_ms = prof["merge"][0] / max(prof["merge"][1], 1)
-    # SURVEY 8d algorithmic bytes, per launch = B samples
-    count_bytes = B * (8.0 * (A * placed_per_sample + wl["n_a_total"]) + 4.0 * A)
-    place_bytes = B * 8.0 * 2.0 * placed_per_sample
-    peak, peak_src = measured_peak()
-    achieved = count_bytes / (count_ms / 1000.0) / 1e9
-    traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": (traffic["dram_bytes_per_sample"] * B) if traffic and "dram_bytes_per_sample" in traffic else None,
-                "traffic_source": traffic.get("capture") if traffic else None,
-                "note": "algorithmic bytes = what the reference's two-pointer merge streams per (sample, annotation, "
-                        "contig) cell (SURVEY 8d); the kernel answers the same cells from one grid index over all "
-                        "tracks (a segment's candidates = one contiguous run of 8-byte entries, read two at a time) "
-                        "and touches only `traffic` DRAM bytes, so frac > 1 is expected: its real bound is the issue "
-                        "rate (1.33 G warp instructions per launch, issue slots 78 % busy, 29 of 32 lanes active; L2 "
-                        "serves ~10.5 GB per launch at 87 % hits) (profiles/r01_count_kernel_v21.txt)",
-                "algorithmic_bytes_per_launch": count_bytes, "kernel_ms": count_ms,
-                "kernel_share_of_step": prof["count"][0] / max(sum(v[0] for v in prof.values()), 1e-9),
-                "other_kernels": {"place_kernel_ms": place_ms, "contig_merge_kernel_ms": merge_ms,
-                                  "place_algorithmic_GBps": place_bytes / max(place_ms, 1e-9) / 1e6,
-                                  "placements_per_s": placed_per_sample * B / max(place_ms, 1e-9) * 1e3}}
+    roofline, placed_per_sample = (None, float(info[0]) / S)
+    if rank == 0:
+        roofline, placed_per_sample = roofline_of(args, wl, ctx, smp, annos, prof, local)
+    barrier()
 
     # ---- e2e: host buffers in, host count matrix out, through the C ABI, every step
     e2e = None
@@ -367,9 +507,8 @@ def run_ours(args):
         ps = tuple(t.numpy().view(unsign[t.dtype]) for t in pin[3:6])
         pw = tuple(t.numpy().view(unsign[t.dtype]) for t in pin[6:9])
         h2d = sum(t.numel() * t.element_size() for t in pin)
-        host_out = torch.empty((B, A), dtype=torch.int32).pin_memory()
-        host_np = host_out.numpy().view(np.uint32)
-        host_f = np.zeros((B, A), dtype=np.float64) if is_density else None
+        host_out = torch.empty((S, A), dtype=odt).pin_memory()
+        host_np = host_out.numpy()
         ids = device.counter_ids([args.counter])
         info_np = np.zeros(3, dtype=np.uint64)
 
@@ -388,28 +527,45 @@ def run_ours(args):
             for j in range(n):
                 a2, nxt = nxt, (e2e_upload() if j + 1 < n else None)
                 s2 = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(ps, pw))
-                begin = ((first + j) * world + rank) * B
-                ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), 20260101, 0, begin, B,
-                                           device._p(host_np), device._p(host_f), 0, device._p(info_np)))
+                begin = step_begin(first + j)
+                if world == 1:
+                    # host in, host out: gatb_run copies every batch's counts to the pinned host matrix while
+                    # the next batch is being placed and counted
+                    ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), SEED, 0, begin, S,
+                                               None if is_density else device._p(host_np.view(np.uint32)),
+                                               device._p(host_np) if is_density else None, 0, device._p(info_np)))
+                else:
+                    # N > 1: counts stay on the device for the exchange; every rank then reads ITS rows of the
+                    # gathered matrix back to the host
+                    ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), SEED, 0, begin, S,
+                                               None if is_density else outs[0].data_ptr(),
+                                               outs[0].data_ptr() if is_density else None, 1, device._p(info_np)))
+                    dist.all_gather_into_tensor(gathers[0], outs[0])
+                    host_out.copy_(gathers[0][rank * S:(rank + 1) * S], non_blocking=True)
+                    torch.cuda.current_stream(dev).synchronize()
                 s2.close()
                 a2.close()
-            return int(host_np[0, 0])
+            return int(host_np.view(np.uint8)[0])
 
-        ctx.set_stream(None)                        # host in / host out: the context's own stream
-        e2e_steps(10 ** 5 - 16, max(3, args.warmup))   # warm-up (allocator pools, pinned paths)
+        if world == 1:
+            ctx.set_stream(None)                    # host in / host out: the context's own stream
+        e2e_steps(10 ** 4 - 16, 2)                  # warm-up (allocator pools, pinned paths)
         barrier()
         t0 = time.perf_counter()
-        e2e_steps(10 ** 5 + 1, args.steps)
+        e2e_steps(10 ** 4 + 1, args.steps)
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(B * A * (8 if is_density else 4)),
-               "what": "gatb_sampler_create + gatb_annotations_create_async + gatb_run with host in/out buffers every step; "
-                       "double-buffered: the upload + index build of step i+1 overlap the kernels of step i"}
+        e2e = {"value": world * S * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(S * A * (8 if is_density else 4)),
+               "what": "per step of %i samples per GPU: gatb_sampler_create + gatb_annotations_create_async (every input "
+                       "from pinned host memory, on every rank) + gatb_run%s + the step's count matrix read back to "
+                       "pinned host memory; double-buffered: the upload + index build of step i+1 overlap the "
+                       "kernels of step i" % (S, " + NCCL all-gather of the slab" if world > 1 else
+                                              " (host output: the copy of batch i overlaps batch i+1)")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -421,11 +577,12 @@ def run_ours(args):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": args.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64" if is_density else "u32",
                 "data": "synthetic", "config": config_of(args, wl, world), "clocks": clock_info,
-                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": e2e, "gpu_launches": int(launches), "parity_check": parity_check,
+                "gather_check": gather_check, "roofline": roofline, "cpu_baseline": cpu,
                 "placed_segments_per_sample": placed_per_sample,
                 "segment_placements_per_s": value * placed_per_sample}
         sys.stdout.flush()
@@ -436,6 +593,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity_check not in (None, "ok") or gather_check not in (None, "ok"):
+        sys.exit(3)
 
 
 def main():

@@ -143,6 +143,9 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
     import os
     import sys
     import time
+    # every rank must place with the SAME seed (the matrix is keyed by seed and global sample index): an
+    # unseeded run draws its seed on rank 0 and broadcasts it
+    parallel.share_seed()
     timing = [("start", time.perf_counter())] if os.environ.get("GATB_TIMING") else None
 
     def mark(name):
@@ -276,9 +279,9 @@ def _open(filename, mode):
 
 
 def _dumpSamples(track, track_index, segs, workspace, sampler, num_samples, pattern):
-    """--output-samples-pattern: BED with one `track name=<sample>` block per sample.  The reference
-    writes each unit's list under its isochore key (gat/__init__.py:518-559); the GPU path keeps only
-    the contig-level sample (after fromIsochores), which is what is counted, so keys are contigs."""
+    """--output-samples-pattern: BED with one `track name=<sample>` block per sample; like the reference, every
+    unit's placed list is written under its own key -- `contig` or `contig.isochore` -- before fromIsochores
+    (gat/__init__.py:518-559), so the file feeds the same-placement fixture route of the reference."""
     import os
     ctx = getContext()
     problem = TrackProblem(segs, workspace)
@@ -296,12 +299,12 @@ def _dumpSamples(track, track_index, segs, workspace, sampler, num_samples, patt
     with _open(filename, "w") as outf:
         step = 256
         for b in range(0, num_samples, step):
-            placed, _ = smp.place(Engine.getSeed(), track_index, b, min(step, num_samples - b))
-            for i, per_contig in enumerate(placed):
+            placed, _ = smp.place_units(Engine.getSeed(), track_index, b, min(step, num_samples - b))
+            for i, per_unit in enumerate(placed):
                 outf.write("track name=%i\n" % (b + i))
-                for c, arr in enumerate(per_contig):
-                    for s, e in arr:
-                        outf.write("%s\t%i\t%i\n" % (problem.contigs[c], s, e))
+                for u, arr in enumerate(per_unit):
+                    key = problem.unit_keys[u]
+                    outf.write("".join("%s\t%i\t%i\n" % (key, s, e) for s, e in arr.tolist()))
     smp.close()
 
 

@@ -21,8 +21,9 @@ SYMBOLS = [
     "gatb_annotations_create", "gatb_annotations_create_async", "gatb_annotations_wait",
     "gatb_annotations_destroy", "gatb_count_lists",
     "gatb_sampler_create", "gatb_sampler_destroy", "gatb_sampler_sample_capacity",
-    "gatb_sampler_set_kind", "gatb_sampler_set_shift", "gatb_sampler_place", "gatb_run", "gatb_column_stats", "gatb_compare_stats",
-    "gatb_format_counts",
+    "gatb_sampler_unit_capacity", "gatb_sampler_set_kind", "gatb_sampler_set_shift", "gatb_sampler_place",
+    "gatb_sampler_place_units", "gatb_run", "gatb_column_stats", "gatb_column_pvalue", "gatb_compare_stats",
+    "gatb_format_counts", "gatb_count_work", "gatb_microbench",
 ]
 
 
@@ -90,6 +91,12 @@ def load():
     L.gatb_sampler_set_shift.argtypes = [vp, ctypes.c_double, i32]
     L.gatb_sampler_place.restype = i32
     L.gatb_sampler_place.argtypes = [vp, u64, u32, u64, u64, vp, vp, vp, vp, vp]
+    L.gatb_sampler_unit_capacity.restype = u64
+    L.gatb_sampler_unit_capacity.argtypes = [vp]
+    L.gatb_sampler_place_units.restype = i32
+    L.gatb_sampler_place_units.argtypes = [vp, u64, u32, u64, u64, vp, vp, vp, vp, vp]
+    L.gatb_column_pvalue.restype = i32
+    L.gatb_column_pvalue.argtypes = [vp, vp, i32, i32, u64, i32, vp, vp, vp]
     L.gatb_run.restype = i32
     L.gatb_run.argtypes = [vp, vp, i32, vp, u64, u32, u64, u64, vp, vp, i32, vp]
     L.gatb_column_stats.restype = i32
@@ -98,5 +105,9 @@ def load():
     L.gatb_compare_stats.argtypes = [vp, u64, vp, i32, vp, i32, u64, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp]
     L.gatb_format_counts.restype = i32
     L.gatb_format_counts.argtypes = [vp, vp, i32, u64, i32, vp, vp, u64]
+    L.gatb_count_work.restype = i32
+    L.gatb_count_work.argtypes = [vp, vp, u32, vp]
+    L.gatb_microbench.restype = i32
+    L.gatb_microbench.argtypes = [i32, i32, u64, i32, vp]
     _lib = L
     return L

@@ -26,6 +26,8 @@ struct gatb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t upload_stream = nullptr;   // gatb_annotations_create_async: copies (+ a rebuild), off the compute stream
     cudaStream_t build_stream = nullptr;    // index build kernels, chunk by chunk behind the copies
+    cudaStream_t copy_stream = nullptr;     // gatb_run with host outputs: device-to-host copies of batch i overlap batch i+1
+    cudaEvent_t ev_counted[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     uint32_t *err_slots = nullptr;          // pinned words of pending asynchronous creates: 4 per set (validation, -, entries needed lo/hi)
     std::vector<int> err_free;
     std::string err;
@@ -120,8 +122,8 @@ struct BatchScratch {
     DevBuf<uint64_t> unit_buf, placed;
     DevBuf<uint32_t> unit_n, placed_n;
     DevBuf<uint8_t> status;
-    DevBuf<uint32_t> out_tmp;
-    DevBuf<double> out_tmp_f;
+    DevBuf<uint32_t> out_tmp[2];          // host-output runs: two staging slabs, so that the copy of batch i
+    DevBuf<double> out_tmp_f[2];          // to the host overlaps the kernels of batch i + 1
 };
 
 static uint32_t env_u32(const char *name, uint32_t dflt)
@@ -154,6 +156,11 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     ctx->stream = ctx->own_stream;
     e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->build_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&ctx->ev_counted[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->err_slots, 256 * 4 * sizeof(uint32_t));
     if (e != cudaSuccess) { cudaStreamDestroy(ctx->own_stream); delete ctx; return fail(nullptr, GATB_ERR_CUDA, cudaGetErrorString(e)); }
     for (int i = 255; i >= 0; i--) ctx->err_free.push_back(i);
@@ -187,6 +194,11 @@ extern "C" void gatb_destroy(gatb_ctx *ctx)
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
     if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_counted[i]) cudaEventDestroy(ctx->ev_counted[i]);
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    }
     if (ctx->err_slots) cudaFreeHost(ctx->err_slots);
     delete ctx;
 }
@@ -270,6 +282,7 @@ struct gatb_annotations {
     uint32_t n_annot = 0, n_keys = 0, n_groups = 0, ka = 1;
     uint64_t n_intervals = 0;
     uint64_t n_boff = 0, capacity = 0;
+    uint64_t n_entries = 0;             // entries the built index holds (padding included)
     std::vector<KeyBins> h_keybins;
     DevBuf<KeyBins> keybins;
     DevBuf<uint32_t> boff;
@@ -357,6 +370,7 @@ static int annotations_finish(gatb_annotations *a)
     tl_stream = ctx->upload_stream;
     cudaError_t e = cudaEventSynchronize(a->ready);
     uint32_t h_err = slot[0];
+    memcpy(&a->n_entries, slot + 2, sizeof(uint64_t));
     if (e == cudaSuccess && !(h_err & 3u) && (h_err & 4u)) {
         unsigned long long need;
         memcpy(&need, slot + 2, sizeof(need));
@@ -371,6 +385,7 @@ static int annotations_finish(gatb_annotations *a)
         if (e == cudaSuccess) e = annotations_build(a);
         if (e == cudaSuccess) e = cudaEventSynchronize(a->ready);
         h_err = slot[0];
+        memcpy(&a->n_entries, slot + 2, sizeof(uint64_t));
     }
     // the raw lists and the scan scratch are no longer needed (freed in upload-stream order)
     a->d_offs.release(); a->d_start.release(); a->d_end.release(); a->d_err.release(); a->d_total.release();
@@ -680,6 +695,8 @@ struct gatb_sampler {
     DevBuf<uint32_t> contig_unit_off, contig_units;
     DevBuf<uint64_t> contig_base;
     DevBuf<unsigned long long> tally;     // [3]: placed segments, round-cap units, overflow units
+    DevBuf<uint32_t> unit_over;           // [n_units]: unit overflowed its buffer in the current call
+    bool no_hist = false;                 // created with nbuckets = 0: no length histogram (SamplerShift only)
 };
 
 // Buffer layout from the units' capacities (UnitDesc.cap): offsets of the unit buffers inside one sample's
@@ -750,7 +767,6 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
     if (!ctx || !out) return GATB_ERR_INVALID;
     *out = nullptr;
     if (n_units <= 0 || n_contigs <= 0 || !unit_contig) return fail(ctx, GATB_ERR_INVALID, "sampler: need >=1 unit");
-    if (nbuckets == 0) return fail(ctx, GATB_ERR_INVALID, "sampler: nbuckets is 0");
     const uint32_t U = (uint32_t)n_units, C = (uint32_t)n_contigs;
     int rc = check_lists(ctx, "segments", U, seg_offs, seg_start, seg_end);
     if (rc) return rc;
@@ -774,6 +790,7 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
 
     gatb_sampler *s = new gatb_sampler();
     s->ctx = ctx; s->n_units = U; s->n_contigs = C; s->has_iso = has_isochores != 0;
+    s->no_hist = nbuckets == 0;
     // workspace CDF (SegmentListSampler.__init__, gat/Engine.pyx:261-277) and unit descriptors
     std::vector<uint32_t> cuminc(ws_offs[U]);
     s->h_units.resize(U);
@@ -821,6 +838,9 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
             return fail(ctx, GATB_ERR_TOO_LARGE,
                         "segment too large: increase nbuckets or bucket_size such that nbuckets * bucket_size > largest segment");
         }
+    // (tests: GATB_PLACE_CAP_MAX clamps the estimated capacities so that the grow-and-repeat path runs)
+    if (const uint32_t cap_max = env_u32("GATB_PLACE_CAP_MAX", 0))
+        for (uint32_t u = 0; u < U; u++) s->h_units[u].cap = std::min(s->h_units[u].cap, next_pow2(std::max(cap_max, 64u)));
     uint64_t lsum = 0;
     for (uint32_t u = 0; u < U; u++) lsum += (uint64_t)(uint32_t)s->h_units[u].ltotal;
     if (lsum > 0xffffffffull) { delete s; return fail(ctx, GATB_ERR_RANGE, "sampler: more than 2^32 bases to place (uint32 counts would overflow)"); }
@@ -831,6 +851,7 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
         if (why) { delete s; return fail(ctx, GATB_ERR_INVALID, why); }
     }
     TRY(s->tally.alloc(3));
+    TRY(s->unit_over.alloc(U));
     TRY(cudaStreamSynchronize(st));
 #undef TRY
     if (e != cudaSuccess) { delete s; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
@@ -855,6 +876,8 @@ extern "C" int gatb_sampler_set_kind(gatb_sampler *s, int kind)
     // them, and without it the reference's counters assert (gat/SegmentList.pyx:1032-1033)
     if (kind == 1 && !s->has_iso)
         return fail(s->ctx, GATB_ERR_INVALID, "SamplerSegments needs an isochore workspace: its samples are not normalized");
+    if (s->no_hist)
+        return fail(s->ctx, GATB_ERR_INVALID, "sampler was created without a length histogram (nbuckets = 0): SamplerShift only");
     s->kind = kind;
     return GATB_OK;
 }
@@ -946,7 +969,7 @@ static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t 
         p.buf = s->ctx->scratch->placed.p; p.sample_stride = s->placed_stride;
         p.out_n = s->ctx->scratch->placed_n.p; p.out_n_stride = s->n_contigs; p.out_by_contig = 1;
     }
-    p.status = s->ctx->scratch->status.p; p.n_units = s->n_units; p.n_samples = B; p.sample_begin = sample_begin;
+    p.status = s->ctx->scratch->status.p; p.unit_over = s->unit_over.p; p.n_units = s->n_units; p.n_samples = B; p.sample_begin = sample_begin;
     p.seed = seed; p.track = track; p.sampler_kind = s->kind;
     p.seg_start = s->seg_start.p; p.seg_end = s->seg_end.p;
     p.shift_half_radius = s->shift_radius / 2; p.shift_extension = s->shift_extension;
@@ -971,44 +994,222 @@ static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t 
     return GATB_OK;
 }
 
-extern "C" int gatb_sampler_place(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin,
-                                  uint64_t n_samples, uint32_t *start, uint32_t *end, uint32_t *counts,
-                                  uint64_t *contig_base, uint8_t *unit_status)
+// A unit that outgrew its buffer (UnitDesc.cap is an estimate, see prep_units_kernel): the reference and the
+// oracle grow their lists on demand, so the call must not fail.  The flagged units get twice the room, the
+// buffer layout is rebuilt and the caller runs the whole call again -- every draw is a function of (seed,
+// track, unit, sample, turn), so the second pass reproduces the first one exactly, with room to finish.
+// -> GATB_OK (grown; run again) or GATB_ERR_CAPACITY (a contig would need more than 2^24 slots).
+static int grow_overflowed(gatb_sampler *s)
 {
-    if (!s || !start || !end || !counts) return GATB_ERR_INVALID;
+    gatb_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    std::vector<uint32_t> over(s->n_units);
+    CU(ctx, cudaMemcpyAsync(over.data(), s->unit_over.p, s->n_units * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    bool any = false;
+    for (uint32_t u = 0; u < s->n_units; u++)
+        if (over[u]) {
+            if (s->h_units[u].cap >= (1u << 24)) return fail(ctx, GATB_ERR_CAPACITY, "placement unit overflowed its segment buffer (2^24 slots)");
+            s->h_units[u].cap *= 2u;
+            any = true;
+        }
+    if (!any) return fail(ctx, GATB_ERR_CAPACITY, "placement unit overflowed its segment buffer");
+    const char *why = nullptr;
+    cudaError_t e = sampler_layout(s, st, &why);
+    if (e != cudaSuccess) return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e));
+    if (why) return fail(ctx, GATB_ERR_CAPACITY, std::string("placement unit overflowed its segment buffer; ") + why);
+    return GATB_OK;
+}
+
+static int check_place_args(gatb_sampler *s, uint32_t track, uint64_t sample_begin, uint64_t n_samples)
+{
     gatb_ctx *ctx = s->ctx;
     if (sample_begin + n_samples > 0xffffffffull) return fail(ctx, GATB_ERR_RANGE, "sample index >= 2^32");
     if (track >= (1u << 24)) return fail(ctx, GATB_ERR_RANGE, "track index >= 2^24");
-    CU(ctx, cudaSetDevice(ctx->device));
-    tl_stream = ctx->stream;
+    if (s->no_hist && s->kind != 2)
+        return fail(ctx, GATB_ERR_INVALID, "sampler was created without a length histogram (nbuckets = 0): call gatb_sampler_set_shift first");
+    return GATB_OK;
+}
+
+// one pass of gatb_sampler_place / gatb_sampler_place_units; *overflowed: some unit needs a larger buffer
+static int place_once(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin, uint64_t n_samples,
+                      bool by_unit, uint32_t *start, uint32_t *end, uint32_t *counts, uint64_t *base,
+                      uint8_t *unit_status, bool *overflowed)
+{
+    gatb_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    if (contig_base) for (uint32_t c = 0; c < s->n_contigs; c++) contig_base[c] = s->h_contig_base[c];
+    BatchScratch *sc = ctx->scratch;
+    const bool from_units = by_unit && s->has_iso;          // the unit-level buffers (before fromIsochores)
+    const uint64_t stride = from_units ? s->unit_stride : s->placed_stride;
+    const uint32_t n_lists = by_unit ? s->n_units : s->n_contigs;
+    std::vector<uint64_t> list_base(n_lists);
+    for (uint32_t l = 0; l < n_lists; l++)
+        list_base[l] = !by_unit ? s->h_contig_base[l] : from_units ? s->h_units[l].buf_off : s->h_contig_base[s->h_units[l].contig];
+    if (base) for (uint32_t l = 0; l < n_lists; l++) base[l] = list_base[l];
     const uint32_t B = pick_batch(s, n_samples);
     int rc = ensure_batch(s, B);
     if (rc) return rc;
     CU(ctx, cudaMemsetAsync(s->tally.p, 0, 3 * sizeof(unsigned long long), st));
-    std::vector<uint64_t> h((uint64_t)B * s->placed_stride);
+    CU(ctx, cudaMemsetAsync(s->unit_over.p, 0, s->n_units * sizeof(uint32_t), st));
+    std::vector<uint64_t> h((uint64_t)B * stride);
+    std::vector<uint32_t> hn((uint64_t)B * (from_units ? s->n_units : s->n_contigs));
     for (uint64_t done = 0; done < n_samples; done += B) {
         const uint32_t b = (uint32_t)std::min<uint64_t>(B, n_samples - done);
         rc = place_batch(s, seed, track, sample_begin + done, b);
         if (rc) return rc;
-        CU(ctx, cudaMemcpyAsync(h.data(), s->ctx->scratch->placed.p, (uint64_t)b * s->placed_stride * 8, cudaMemcpyDeviceToHost, st));
-        CU(ctx, cudaMemcpyAsync(counts + done * s->n_contigs, s->ctx->scratch->placed_n.p, (uint64_t)b * s->n_contigs * 4, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(h.data(), from_units ? sc->unit_buf.p : sc->placed.p, (uint64_t)b * stride * 8, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(hn.data(), from_units ? sc->unit_n.p : sc->placed_n.p, (uint64_t)b * (from_units ? s->n_units : s->n_contigs) * 4,
+                                cudaMemcpyDeviceToHost, st));
         if (unit_status)
-            CU(ctx, cudaMemcpyAsync(unit_status + done * s->n_units, s->ctx->scratch->status.p, (uint64_t)b * s->n_units, cudaMemcpyDeviceToHost, st));
+            CU(ctx, cudaMemcpyAsync(unit_status + done * s->n_units, sc->status.p, (uint64_t)b * s->n_units, cudaMemcpyDeviceToHost, st));
         CU(ctx, cudaStreamSynchronize(st));
         for (uint64_t sl = 0; sl < b; sl++)
-            for (uint32_t c = 0; c < s->n_contigs; c++) {
-                const uint32_t n = counts[(done + sl) * s->n_contigs + c];
-                const uint64_t src = sl * s->placed_stride + s->h_contig_base[c];
-                const uint64_t dst = (done + sl) * s->placed_stride + s->h_contig_base[c];
+            for (uint32_t l = 0; l < n_lists; l++) {
+                const uint32_t n = (by_unit && !from_units) ? hn[sl * s->n_contigs + s->h_units[l].contig] : hn[sl * n_lists + l];
+                counts[(done + sl) * n_lists + l] = n;
+                const uint64_t src = sl * stride + list_base[l];
+                const uint64_t dst = (done + sl) * stride + list_base[l];
                 for (uint32_t i = 0; i < n; i++) { start[dst + i] = seg_start(h[src + i]); end[dst + i] = seg_end(h[src + i]); }
             }
     }
     unsigned long long tally[3];
     CU(ctx, cudaMemcpyAsync(tally, s->tally.p, sizeof(tally), cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
-    if (tally[2]) return fail(ctx, GATB_ERR_CAPACITY, "placement unit overflowed its segment buffer");
+    *overflowed = tally[2] != 0;
+    return GATB_OK;
+}
+
+static int place_impl(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin, uint64_t n_samples,
+                      bool by_unit, uint32_t *start, uint32_t *end, uint32_t *counts, uint64_t *base,
+                      uint8_t *unit_status, uint64_t capacity)
+{
+    if (!s || !start || !end || !counts) return GATB_ERR_INVALID;
+    gatb_ctx *ctx = s->ctx;
+    int rc = check_place_args(s, track, sample_begin, n_samples);
+    if (rc) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    for (;;) {
+        // the caller sized start/end from the capacity query: a grown layout may no longer fit them
+        const uint64_t need = (by_unit && s->has_iso) ? s->unit_stride : s->placed_stride;
+        if (capacity && need > capacity)
+            return fail(ctx, GATB_ERR_CAPACITY, "placement buffers were grown: query the sample capacity again and repeat the call");
+        bool overflowed = false;
+        rc = place_once(s, seed, track, sample_begin, n_samples, by_unit, start, end, counts, base, unit_status, &overflowed);
+        if (rc) return rc;
+        if (!overflowed) return GATB_OK;
+        rc = grow_overflowed(s);
+        if (rc) return rc;
+    }
+}
+
+extern "C" int gatb_sampler_place(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin,
+                                  uint64_t n_samples, uint32_t *start, uint32_t *end, uint32_t *counts,
+                                  uint64_t *contig_base, uint8_t *unit_status)
+{
+    // (the arrays hold gatb_sampler_sample_capacity() slots per sample as queried BEFORE the call: a unit that
+    // overflows grows the layout, which the fixed-size arrays cannot follow -> GATB_ERR_CAPACITY, query + repeat)
+    const uint64_t cap = s ? s->placed_stride : 0;
+    return place_impl(s, seed, track, sample_begin, n_samples, false, start, end, counts, contig_base, unit_status, cap);
+}
+
+extern "C" uint64_t gatb_sampler_unit_capacity(const gatb_sampler *s)
+{
+    return s ? (s->has_iso ? s->unit_stride : s->placed_stride) : 0;
+}
+
+extern "C" int gatb_sampler_place_units(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin,
+                                        uint64_t n_samples, uint32_t *start, uint32_t *end, uint32_t *counts,
+                                        uint64_t *unit_base, uint8_t *unit_status)
+{
+    const uint64_t cap = s ? (s->has_iso ? s->unit_stride : s->placed_stride) : 0;
+    return place_impl(s, seed, track, sample_begin, n_samples, true, start, end, counts, unit_base, unit_status, cap);
+}
+
+// one pass of gatb_run over all batches; tally[2] != 0: some unit needs a larger buffer (the counts are void)
+static int run_once(gatb_sampler *s, const gatb_annotations *annos, int n_counters, const int32_t *counters,
+                    uint64_t seed, uint32_t track, uint64_t sample_begin, uint64_t n_samples,
+                    uint32_t *out_counts, double *out_density, int out_is_device, bool any_int, bool any_density,
+                    unsigned long long *tally)
+{
+    gatb_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t A = annos->n_annot;
+    const uint32_t B = pick_batch(s, n_samples);
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_alloc = 0, t_placeq = 0, t_annos = 0, t_countq = 0;
+    int rc = ensure_batch(s, B);
+    if (rc) return rc;
+    t_alloc = since();
+    BatchScratch *sc = ctx->scratch;
+    const int n_stage = (!out_is_device && n_samples > B) ? 2 : 1;
+    if (!out_is_device)
+        for (int i = 0; i < n_stage; i++) {
+            if (any_int) CU(ctx, sc->out_tmp[i].ensure((uint64_t)B * A));
+            if (any_density) CU(ctx, sc->out_tmp_f[i].ensure((uint64_t)B * A));
+        }
+    CU(ctx, cudaMemsetAsync(s->tally.p, 0, 3 * sizeof(unsigned long long), st));
+    CU(ctx, cudaMemsetAsync(s->unit_over.p, 0, s->n_units * sizeof(uint32_t), st));
+    // host outputs: the count kernels write a staging slab; its copy to the host runs on the copy stream while
+    // the compute stream goes on with the next (counter, batch), which uses the other slab
+    uint64_t n_staged = 0;
+    bool copied_pending[2] = {false, false};
+
+    for (uint64_t done = 0; done < n_samples; done += B) {
+        const uint32_t b = (uint32_t)std::min<uint64_t>(B, n_samples - done);
+        rc = place_batch(s, seed, track, sample_begin + done, b);
+        if (rc) return rc;
+        if (done == 0) t_placeq = since();
+        CountParams p;
+        memset(&p, 0, sizeof(p));
+        p.placed = sc->placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
+        p.placed_n = sc->placed_n.p; p.key_present = nullptr;
+        for (int c = 0; c < n_counters; c++) {
+            const bool dens = counters[c] == GATB_NUCLEOTIDE_DENSITY;
+            rc = count_params_annos(annos, b, dens, p);
+            if (rc) return rc;
+            uint32_t *dst_u = out_counts ? out_counts + ((uint64_t)c * n_samples + done) * A : nullptr;
+            double *dst_f = out_density ? out_density + done * A : nullptr;
+            const int slab = (int)(n_staged % (uint64_t)n_stage);
+            p.out_u32 = out_is_device ? dst_u : sc->out_tmp[slab].p;
+            p.out_f64 = out_is_device ? dst_f : sc->out_tmp_f[slab].p;
+            // annotations still uploading / building (gatb_annotations_create_async): the placement queued
+            // above did not need them, the count does.  The host waits here (the GPU keeps placing) because
+            // the build's outcome decides what may be launched: invalid lists or an index to rebuild.
+            if (annos->pending) {
+                rc = annotations_finish(const_cast<gatb_annotations *>(annos));
+                tl_stream = ctx->stream;
+                if (rc) { cudaStreamSynchronize(st); return rc; }
+                t_annos = since();
+            }
+            if (!out_is_device && copied_pending[slab]) CU(ctx, cudaStreamWaitEvent(st, ctx->ev_copied[slab], 0));
+            { ProfScope ps(ctx, PROF_COUNT); CU(ctx, launch_count(st, counters[c], p, ctx->count_threads)); }
+            if (!out_is_device) {
+                cudaStream_t cs = n_stage > 1 ? ctx->copy_stream : st;
+                if (n_stage > 1) {
+                    CU(ctx, cudaEventRecord(ctx->ev_counted[slab], st));
+                    CU(ctx, cudaStreamWaitEvent(cs, ctx->ev_counted[slab], 0));
+                }
+                if (dens) CU(ctx, cudaMemcpyAsync(dst_f, sc->out_tmp_f[slab].p, (uint64_t)b * A * sizeof(double), cudaMemcpyDeviceToHost, cs));
+                else CU(ctx, cudaMemcpyAsync(dst_u, sc->out_tmp[slab].p, (uint64_t)b * A * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+                if (n_stage > 1) {
+                    CU(ctx, cudaEventRecord(ctx->ev_copied[slab], cs));
+                    copied_pending[slab] = true;
+                }
+                n_staged++;
+            }
+        }
+    }
+    // the compute stream joins the last copies: one synchronisation point for the caller
+    for (int i = 0; i < 2; i++)
+        if (copied_pending[i]) CU(ctx, cudaStreamWaitEvent(st, ctx->ev_copied[i], 0));
+    t_countq = since();
+    CU(ctx, cudaMemcpyAsync(tally, s->tally.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    if (ctx->trace)
+        fprintf(stderr, "gatb_run: batch buffers %.2f ms, placement queued %.2f, annotations ready %.2f, all queued %.2f, done %.2f\n",
+                t_alloc, t_placeq, t_annos, t_countq, since());
     return GATB_OK;
 }
 
@@ -1020,8 +1221,8 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
     gatb_ctx *ctx = s->ctx;
     if (annos->ctx != ctx) return fail(ctx, GATB_ERR_INVALID, "run: sampler and annotations belong to different contexts");
     if (annos->n_keys != s->n_contigs) return fail(ctx, GATB_ERR_INVALID, "run: annotations keys != sampler contigs");
-    if (sample_begin + n_samples > 0xffffffffull) return fail(ctx, GATB_ERR_RANGE, "sample index >= 2^32");
-    if (track >= (1u << 24)) return fail(ctx, GATB_ERR_RANGE, "track index >= 2^24");
+    int rc = check_place_args(s, track, sample_begin, n_samples);
+    if (rc) return rc;
     bool any_int = false, any_density = false;
     for (int c = 0; c < n_counters; c++) {
         if (counters[c] < 0 || counters[c] >= GATB_NCOUNTERS) return fail(ctx, GATB_ERR_INVALID, "unknown counter id");
@@ -1033,65 +1234,54 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
     if (!annos->pending && annos->status) return fail(ctx, annos->status, "run: the annotations failed validation");
     CU(ctx, cudaSetDevice(ctx->device));
     tl_stream = ctx->stream;
-    cudaStream_t st = ctx->stream;
-    const uint32_t A = annos->n_annot;
-    const uint32_t B = pick_batch(s, n_samples);
-    const auto t_begin = std::chrono::steady_clock::now();
-    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
-    double t_alloc = 0, t_placeq = 0, t_annos = 0, t_countq = 0;
-    int rc = ensure_batch(s, B);
-    if (rc) return rc;
-    t_alloc = since();
-    if (!out_is_device) {
-        if (any_int) CU(ctx, s->ctx->scratch->out_tmp.ensure((uint64_t)B * A));
-        if (any_density) CU(ctx, s->ctx->scratch->out_tmp_f.ensure((uint64_t)B * A));
-    }
-    CU(ctx, cudaMemsetAsync(s->tally.p, 0, 3 * sizeof(unsigned long long), st));
-
-    for (uint64_t done = 0; done < n_samples; done += B) {
-        const uint32_t b = (uint32_t)std::min<uint64_t>(B, n_samples - done);
-        rc = place_batch(s, seed, track, sample_begin + done, b);
+    unsigned long long tally[3] = {0, 0, 0};
+    for (;;) {
+        rc = run_once(s, annos, n_counters, counters, seed, track, sample_begin, n_samples, out_counts, out_density,
+                      out_is_device, any_int, any_density, tally);
         if (rc) return rc;
-        if (done == 0) t_placeq = since();
-        CountParams p;
-        memset(&p, 0, sizeof(p));
-        p.placed = s->ctx->scratch->placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
-        p.placed_n = s->ctx->scratch->placed_n.p; p.key_present = nullptr;
-        for (int c = 0; c < n_counters; c++) {
-            const bool dens = counters[c] == GATB_NUCLEOTIDE_DENSITY;
-            rc = count_params_annos(annos, b, dens, p);
-            if (rc) return rc;
-            uint32_t *dst_u = out_counts ? out_counts + ((uint64_t)c * n_samples + done) * A : nullptr;
-            double *dst_f = out_density ? out_density + done * A : nullptr;
-            p.out_u32 = out_is_device ? dst_u : s->ctx->scratch->out_tmp.p;
-            p.out_f64 = out_is_device ? dst_f : s->ctx->scratch->out_tmp_f.p;
-            // annotations still uploading / building (gatb_annotations_create_async): the placement queued
-            // above did not need them, the count does.  The host waits here (the GPU keeps placing) because
-            // the build's outcome decides what may be launched: invalid lists or an index to rebuild.
-            if (annos->pending) {
-                rc = annotations_finish(const_cast<gatb_annotations *>(annos));
-                tl_stream = ctx->stream;
-                if (rc) { cudaStreamSynchronize(st); return rc; }
-                t_annos = since();
-            }
-            { ProfScope ps(ctx, PROF_COUNT); CU(ctx, launch_count(st, counters[c], p, ctx->count_threads)); }
-            if (!out_is_device) {
-                if (dens) CU(ctx, cudaMemcpyAsync(dst_f, s->ctx->scratch->out_tmp_f.p, (uint64_t)b * A * sizeof(double), cudaMemcpyDeviceToHost, st));
-                else CU(ctx, cudaMemcpyAsync(dst_u, s->ctx->scratch->out_tmp.p, (uint64_t)b * A * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            }
-        }
+        if (tally[2] == 0) break;
+        rc = grow_overflowed(s);            // (rare: skewed units, see prep_units_kernel) then the call runs again
+        if (rc) return rc;
     }
-    t_countq = since();
-    unsigned long long tally[3];
-    CU(ctx, cudaMemcpyAsync(tally, s->tally.p, sizeof(tally), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaStreamSynchronize(st));
-    if (ctx->trace)
-        fprintf(stderr, "gatb_run: batch buffers %.2f ms, placement queued %.2f, annotations ready %.2f, all queued %.2f, done %.2f\n",
-                t_alloc, t_placeq, t_annos, t_countq, since());
     if (info) { info[0] = tally[0]; info[1] = tally[1]; info[2] = tally[2]; }
     rc = annotations_finish(const_cast<gatb_annotations *>(annos));      // invalid lists: the counts mean nothing
     if (rc) return rc;
-    if (tally[2]) return fail(ctx, GATB_ERR_CAPACITY, "placement unit overflowed its segment buffer");
+    return GATB_OK;
+}
+
+// work of the counting kernel on the LAST batch of the preceding gatb_run on this sampler (its placed segments
+// are still in the context's batch buffers): out[0] = segments, out[1] = index entries in their runs (what the
+// kernel tests, padding included), out[2] = entries of the whole index, out[3] = bytes of the index arrays the
+// kernel reads (offsets + entries)
+extern "C" int gatb_count_work(gatb_sampler *s, const gatb_annotations *annos, uint32_t n_samples, uint64_t *out)
+{
+    if (!s || !annos || !out) return GATB_ERR_INVALID;
+    gatb_ctx *ctx = s->ctx;
+    if (annos->ctx != ctx || annos->n_keys != s->n_contigs) return fail(ctx, GATB_ERR_INVALID, "count_work: sampler / annotations mismatch");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = annotations_finish(const_cast<gatb_annotations *>(annos));
+    if (rc) return rc;
+    tl_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    if (ctx->scratch->placed.n < (uint64_t)n_samples * s->placed_stride || ctx->scratch->placed_n.n < (uint64_t)n_samples * s->n_contigs)
+        return fail(ctx, GATB_ERR_INVALID, "count_work: no batch of that size has been placed");
+    CountParams p;
+    memset(&p, 0, sizeof(p));
+    rc = count_params_annos(annos, n_samples, false, p);
+    if (rc) return rc;
+    p.placed = ctx->scratch->placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
+    p.placed_n = ctx->scratch->placed_n.p;
+    DevBuf<unsigned long long> d_out;
+    CU(ctx, d_out.alloc(2));
+    CU(ctx, cudaMemsetAsync(d_out.p, 0, 2 * sizeof(unsigned long long), st));
+    { ProfScope ps(ctx, PROF_OTHER); launch_count_work(st, p, d_out.p); }
+    CU(ctx, cudaGetLastError());
+    unsigned long long h[2];
+    CU(ctx, cudaMemcpyAsync(h, d_out.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    out[0] = h[0]; out[1] = h[1];
+    out[2] = annos->n_entries;
+    out[3] = (annos->n_boff + 1) * sizeof(uint32_t) + annos->n_entries * sizeof(uint2);
     return GATB_OK;
 }
 
@@ -1181,6 +1371,55 @@ extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float
         if (upper95) upper95[a] = hi;
         if (fold) fold[a] = fo;
         if (pvalue) pvalue[a] = pv;
+    }
+    return GATB_OK;
+}
+
+// empirical p-value of values[a] in column a given the column's STORED expectation
+// (AnnotatorResult.getEmpiricalPValue -> getTwoSidedPValue(&self.stats, value), gat/Engine.pyx:1543-1576, :1829-1831):
+// the over / under-representation branch compares with stats.expected (already multiplied by a reference
+// fold, :1673-1676), not with a recomputed sample mean
+extern "C" int gatb_column_pvalue(gatb_ctx *ctx, const void *counts, int is_float, int counts_is_device,
+                                  uint64_t n_samples, int n_cols, const double *values, const double *expected,
+                                  double *pvalue)
+{
+    if (!ctx || !counts || !values || !expected || !pvalue || n_cols <= 0) return GATB_ERR_INVALID;
+    if (n_samples < 1) return fail(ctx, GATB_ERR_INVALID, "column_pvalue: no samples");
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    const uint32_t A = (uint32_t)n_cols;
+    const uint64_t l = n_samples;
+    const size_t esz = is_float ? sizeof(double) : sizeof(uint32_t);
+    DevBuf<uint8_t> d_counts;
+    const void *dc = counts;
+    if (!counts_is_device) {
+        CU(ctx, d_counts.upload((const uint8_t *)counts, l * A * esz, st));
+        dc = d_counts.p;
+    }
+    DevBuf<double> d_obs, d_sum;
+    DevBuf<unsigned long long> d_cnt;
+    CU(ctx, d_obs.upload(values, A, st));
+    CU(ctx, d_sum.alloc(A));
+    CU(ctx, d_cnt.alloc(2 * (size_t)A));
+    StatsParams p;
+    memset(&p, 0, sizeof(p));
+    p.counts = dc; p.is_float = is_float; p.n_samples = l; p.n_cols = A; p.observed = d_obs.p;
+    p.sum = d_sum.p; p.n_lt = d_cnt.p; p.n_eq = d_cnt.p + A;
+    { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass1(st, p); }
+    CU(ctx, cudaGetLastError());
+    std::vector<unsigned long long> h_cnt(2 * (size_t)A);
+    CU(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt.p, 2 * (size_t)A * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    for (uint32_t a = 0; a < A; a++) {
+        const uint64_t n_lt = h_cnt[a], n_eq = h_cnt[A + a];
+        uint64_t idx = n_lt;
+        if (n_lt == l) idx = 1;
+        else if (values[a] > expected[a]) {
+            if (n_eq > 0 && n_lt > 0) idx = n_lt - 1;
+            idx = l - (idx + 1);
+        } else if (n_eq > 0) idx = n_lt + n_eq;
+        pvalue[a] = std::max(1.0 / (double)l, (double)idx / (double)l);
     }
     return GATB_OK;
 }

@@ -417,6 +417,44 @@ cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int
     return cudaErrorInvalidValue;
 }
 
+// Diagnostic for bench.py's roofline: how many index entries the counting kernel has to test for the placed
+// segments of a batch (the lengths of their runs, padding included) -- next to the number of truly overlapping
+// pairs (the GATB_OVERLAP_PIECES counter) this is the kernel's waste ratio.  out[0] += segments, out[1] += entries.
+__global__ void __launch_bounds__(256) count_work_kernel(CountParams p, unsigned long long *out)
+{
+    const uint32_t sl = blockIdx.x;
+    unsigned long long segs = 0, entries = 0;
+    for (uint32_t g = 0; g < p.n_groups; g++)
+        for (uint32_t k = 0; k < p.n_keys; k++) {
+            const KeyBins kb = p.keybins[(uint64_t)g * p.n_keys + k];
+            const uint32_t n = p.placed_n[(uint64_t)sl * p.n_keys + k];
+            if (g == 0) segs += (threadIdx.x == 0) ? n : 0u;
+            if (kb.nbins == 0) continue;
+            const uint32_t *__restrict__ boff = p.boff + kb.base;
+            const uint64_t *__restrict__ segl = p.placed + p.key_base[k] + (uint64_t)sl * p.sample_stride;
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint64_t sg = segl[i];
+                const uint32_t b0 = seg_start(sg) >> kb.shift;
+                if (b0 >= kb.nbins) continue;
+                const uint32_t b1 = min((seg_end(sg) - 1u) >> kb.shift, kb.nbins - 1u);
+                entries += boff[b1 + 1u] - boff[b0];
+            }
+        }
+    for (int d = 16; d > 0; d >>= 1) {
+        segs += __shfl_xor_sync(GATB_FULL, segs, d);
+        entries += __shfl_xor_sync(GATB_FULL, entries, d);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        if (segs) atomicAdd(out, segs);
+        if (entries) atomicAdd(out + 1, entries);
+    }
+}
+
+void launch_count_work(cudaStream_t st, const CountParams &p, unsigned long long *out)
+{
+    if (p.n_samples) count_work_kernel<<<p.n_samples, 256, 0, st>>>(p, out);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Grid index construction (replaces a host loop over every interval).
 //   1  bins_pass_kernel<false>: validate, and count the entries of every bin into boff[base + 1 + b];

@@ -97,6 +97,9 @@ cudaError_t launch_bins_finish(cudaStream_t st, const BuildBinsParams &p, void *
 // counter: GATB_* id.  Returns cudaError from the launch configuration.
 cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int threads);
 
+// diagnostic: segments and index entries in the runs of the placed segments (bench.py roofline)
+void launch_count_work(cudaStream_t st, const CountParams &p, unsigned long long *out);
+
 // column statistics (K5)
 struct StatsParams {
     const void *counts;             // [n_samples][n_cols] uint32 or float64

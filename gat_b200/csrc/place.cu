@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
     uint32_t orphans = 0;               // segments any trim left outside the workspace
     bool dirty = false;
 
-    if (d.tab_n > 0 && p.sampler_kind == 1) {
+    if (d.tab_n > 0 && p.sampler_kind == 1 && d.seg_n > d.cap) status |= UNIT_OVERFLOW;
+    else if (d.tab_n > 0 && p.sampler_kind == 1) {
         // SamplerSegments.sample (gat/Engine.pyx:719-735): exactly len(segments) placements, every one
         // kept, returned in draw order (unsorted, unmerged); fromIsochores' merge(0) normalizes them later
         for (uint32_t t = lane; t < d.seg_n; t += 32) {
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
         uint32_t slot = p.out_by_contig ? d.contig : unit;
         p.out_n[(uint64_t)sl * p.out_n_stride + slot] = (status & UNIT_OVERFLOW) ? 0u : nu;
         if (p.status) p.status[(uint64_t)sl * p.n_units + unit] = (uint8_t)status;
+        if ((status & UNIT_OVERFLOW) && p.unit_over) p.unit_over[unit] = 1u;
     }
 }
 
@@ -544,6 +546,7 @@ __global__ void __launch_bounds__(128) shift_kernel(PlaceParams p)
         const uint32_t slot = p.out_by_contig ? d.contig : unit;
         p.out_n[(uint64_t)sl * p.out_n_stride + slot] = nu;
         if (p.status) p.status[(uint64_t)sl * p.n_units + unit] = (uint8_t)status;
+        if ((status & UNIT_OVERFLOW) && p.unit_over) p.unit_over[unit] = 1u;
     }
 }
 
@@ -632,13 +635,18 @@ __global__ void __launch_bounds__(128) prep_units_kernel(UnitDesc *units, uint32
     __syncwarp();
 
     uint32_t bucket = bucket_size, err = 0;
+    unsigned long long drawable = 0;        // sum of the table without its last (largest) entry
     if (nw > 0) {
-        if (bucket == 0) bucket = (uint32_t)ceil((double)largest / (double)nbuckets);
+        // nbuckets == 0: no length histogram wanted (SamplerShift never calls getLengthDistribution,
+        // gat/Engine.pyx:1060-1062): the table holds the plain lengths and nothing is "too large"
+        const bool hist = nbuckets != 0;
+        if (!hist) bucket = 1;
+        else if (bucket == 0) bucket = (uint32_t)ceil((double)largest / (double)nbuckets);
         // pass 2: bucket index * bucket, then sort
         for (uint32_t i = lane; i < nw; i += 32) {
             uint32_t l = (uint32_t)keys[i];
             int idx = (int)(((double)l + (double)bucket - 1.0) / (double)bucket);
-            if (idx >= (int)nbuckets) err = 1;
+            if (hist && idx >= (int)nbuckets) err = 1;
             keys[i] = (uint64_t)((uint32_t)idx * bucket);
         }
         err = __any_sync(GATB_FULL, err) ? 1u : 0u;
@@ -646,13 +654,30 @@ __global__ void __launch_bounds__(128) prep_units_kernel(UnitDesc *units, uint32
         for (uint32_t i = nw + lane; i < N; i += 32) keys[i] = GATB_KEY_INF;
         __syncwarp();
         warp_bitonic_sort(keys, N);
-        for (uint32_t i = lane; i < nw; i += 32) len_tab[d.tab_off + i] = (uint32_t)keys[i];
+        for (uint32_t i = lane; i < nw; i += 32) {
+            len_tab[d.tab_off + i] = (uint32_t)keys[i];
+            if (i + 1u < nw || nw == 1u) drawable += keys[i];
+        }
+        drawable = __reduce_add_sync(GATB_FULL, (uint32_t)drawable) + ((unsigned long long)__reduce_add_sync(GATB_FULL, (uint32_t)(drawable >> 32)) << 32);
     }
     if (lane == 0) {
         d.tab_n = nw;
         d.bucket = bucket ? bucket : 1u;
         d.ltotal = (int32_t)lt;
-        d.cap = next_pow2(max(2u * nw + 64u, d.seg_n));   // SamplerSegments places seg_n segments
+        // Buffer capacity: twice the working segments (room for the counting sort's scratch) and, for skewed
+        // units, the expected number of placements -- HistogramSampler draws ranks 1 .. n-1 only
+        // (gat/Engine.pyx:420), so a unit whose largest segment holds most of the bases is refilled with the
+        // smaller lengths and needs far more placements than it has segments.  An estimate: a unit that still
+        // outgrows its buffer is reported (UNIT_OVERFLOW) and the host grows it and runs the call again.
+        uint64_t est = 0;
+        if (nw > 0) {
+            const uint64_t ndraw = nw > 1u ? nw - 1u : 1u;
+            const uint64_t mean = drawable / ndraw > 0 ? drawable / ndraw : 1u;
+            est = (uint64_t)lt / mean;
+            est = est + est / 4u + 64u;
+            if (est > (1u << 24)) est = 1u << 24;
+        }
+        d.cap = next_pow2(max(max(2u * nw + 64u, d.seg_n), (uint32_t)est));   // SamplerSegments places seg_n segments
         d.error = err;
         units[unit] = d;
     }

@@ -40,6 +40,8 @@ struct PlaceParams {
     uint32_t out_n_stride;
     int out_by_contig;           // 1: index out_n by contig (no isochores), 0: by unit
     uint8_t *status;             // [n_samples][n_units]
+    uint32_t *unit_over;         // [n_units]: set when any sample of the unit overflowed its buffer (the caller
+                                 // grows those units and runs the call again)
     uint32_t n_units;
     uint32_t n_samples;          // samples in this launch
     uint64_t sample_begin;       // global index of the first sample

@@ -130,6 +130,23 @@ class Context(object):
         return dict(zip(["expected", "stddev", "lower95", "upper95", "fold", "pvalue"], outs))
 
 
+    def column_pvalue(self, counts, values, expected):
+        """AnnotatorResult.getEmpiricalPValue (gat/Engine.pyx:1829-1831): p-value of values[a] among the samples
+        of column a against the STORED expectation expected[a]; counts: host ndarray [n_samples][n_cols]"""
+        counts = np.ascontiguousarray(counts)
+        if counts.dtype == np.float64:
+            is_float = 1
+        else:
+            counts = np.ascontiguousarray(counts, dtype=np.uint32)
+            is_float = 0
+        n_samples, n_cols = counts.shape
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        e = np.ascontiguousarray(expected, dtype=np.float64)
+        out = np.zeros(n_cols, dtype=np.float64)
+        self.check(self.lib.gatb_column_pvalue(self.handle, _p(counts), is_float, 0, int(n_samples), int(n_cols),
+                                               _p(v), _p(e), _p(out)))
+        return out
+
     def format_counts(self, counts=None, device_ptr=None, n_samples=None, n_cols=None):
         """the text of the counts table (gat/__init__.py:1072-1086): -> (text uint8[], col_off uint64[n_cols+1]);
         column a of the [n_samples][n_cols] uint32 matrix is text[col_off[a]:col_off[a+1]] = b"c0,c1,..."."""
@@ -266,26 +283,44 @@ class Sampler(object):
         self.ctx.check(self.ctx.lib.gatb_sampler_set_shift(self.handle, float(radius), int(extension)))
         self.capacity = int(self.ctx.lib.gatb_sampler_sample_capacity(self.handle))
 
-    def place(self, seed, track, sample_begin, n_samples):
-        """-> (samples, status): samples[s][c] = (n,2) uint32 array of contig c; status [n_samples][n_units]"""
-        cap = self.capacity
-        start = np.zeros(max(n_samples * cap, 1), dtype=np.uint32)
-        end = np.zeros(max(n_samples * cap, 1), dtype=np.uint32)
-        counts = np.zeros(max(n_samples * self.n_contigs, 1), dtype=np.uint32)
-        base = np.zeros(self.n_contigs, dtype=np.uint64)
-        status = np.zeros(max(n_samples * self.n_units, 1), dtype=np.uint8)
-        self.ctx.check(self.ctx.lib.gatb_sampler_place(self.handle, int(seed), int(track), int(sample_begin),
-                                                       int(n_samples), _p(start), _p(end), _p(counts), _p(base),
-                                                       _p(status)))
+    def _place(self, by_unit, seed, track, sample_begin, n_samples):
+        lib = self.ctx.lib
+        fn = lib.gatb_sampler_place_units if by_unit else lib.gatb_sampler_place
+        capfn = lib.gatb_sampler_unit_capacity if by_unit else lib.gatb_sampler_sample_capacity
+        n_lists = self.n_units if by_unit else self.n_contigs
+        while True:
+            cap = int(capfn(self.handle))
+            start = np.zeros(max(n_samples * cap, 1), dtype=np.uint32)
+            end = np.zeros(max(n_samples * cap, 1), dtype=np.uint32)
+            counts = np.zeros(max(n_samples * n_lists, 1), dtype=np.uint32)
+            base = np.zeros(n_lists, dtype=np.uint64)
+            status = np.zeros(max(n_samples * self.n_units, 1), dtype=np.uint8)
+            rc = fn(self.handle, int(seed), int(track), int(sample_begin), int(n_samples), _p(start), _p(end),
+                    _p(counts), _p(base), _p(status))
+            # a unit outgrew its buffer: the library enlarged it; repeat with arrays of the new capacity
+            if rc == _lib.ERR_CAPACITY and int(capfn(self.handle)) > cap:
+                continue
+            self.ctx.check(rc)
+            break
+        self.capacity = int(lib.gatb_sampler_sample_capacity(self.handle))
         out = []
         for s in range(n_samples):
             per = []
-            for c in range(self.n_contigs):
-                n = int(counts[s * self.n_contigs + c])
+            for c in range(n_lists):
+                n = int(counts[s * n_lists + c])
                 o = s * cap + int(base[c])
                 per.append(np.stack([start[o:o + n], end[o:o + n]], axis=1))
             out.append(per)
         return out, status[:n_samples * self.n_units].reshape(n_samples, self.n_units)
+
+    def place(self, seed, track, sample_begin, n_samples):
+        """-> (samples, status): samples[s][c] = (n,2) uint32 array of contig c; status [n_samples][n_units]"""
+        return self._place(False, seed, track, sample_begin, n_samples)
+
+    def place_units(self, seed, track, sample_begin, n_samples):
+        """-> (samples, status): samples[s][u] = (n,2) uint32 array of UNIT u (key of the track), i.e. what
+        sampler.sample(segs[key], workspace[key]) returns before fromIsochores (gat/__init__.py:531-546)"""
+        return self._place(True, seed, track, sample_begin, n_samples)
 
     def run(self, annotations, counters, seed, track, sample_begin, n_samples,
             out_counts_ptr=None, out_density_ptr=None):

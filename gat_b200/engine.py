@@ -423,8 +423,9 @@ class SamplerShift(Sampler):
 
     accelerated = True
     kind = "shift"
-    bucket_size = 0         # (the unit preparation shared with the other samplers: automatic bucket size, so
-    nbuckets = 100000       #  that no segment is "too large"; the shift itself uses no length histogram)
+    bucket_size = 1         # (the unit preparation is shared with the other samplers; nbuckets = 0 asks for no
+    nbuckets = 0            #  length histogram -- the shift never calls getLengthDistribution, so no segment
+                            #  is ever "too large" for it, gat/Engine.pyx:1060-1062)
 
     def __init__(self, radius=2, extension=0):
         self.radius = radius
@@ -472,14 +473,28 @@ class SamplerSegments(Sampler):
         return (SamplerSegments, (self.bucket_size, self.nbuckets))
 
     def sample(self, segments, workspace):
+        """exactly len(working segments) placements, in draw order, unsorted and possibly overlapping -- the list
+        the reference returns (gat/Engine.pyx:719-735); only fromIsochores' merge(0) normalizes it"""
         assert workspace.isNormalized, "workspace is not normalized"
         if len(segments) == 0 or len(workspace) == 0:
             return SegmentList()
         ctx = getContext()
-        # a single unit is placed through a two-key isochore problem so that the raw draw-order list
-        # cannot be returned by the C ABI (it only hands back contig-level, merged samples): use run()
-        raise NotImplementedError("SamplerSegments.sample() of a single list returns an unnormalized list; "
-                                  "use gat_b200.run() with an isochore workspace")
+        # one unit declared as an isochore key: the unit-level list is then handed back as drawn
+        try:
+            smp = _dev.Sampler(ctx, [0], 1, True, [segments.asarray()], [workspace.asarray()],
+                               bucket_size=self.bucket_size, nbuckets=self.nbuckets)
+        except _dev._lib.GatB200Error as e:
+            if e.code == _dev._lib.ERR_TOO_LARGE:
+                raise ValueError(str(e))
+            raise
+        smp.set_kind("segments")
+        call = _rng_state["calls"]
+        _rng_state["calls"] += 1
+        try:
+            placed, _ = smp.place_units(getSeed(), 0xFFFFFF, call, 1)
+        finally:
+            smp.close()
+        return SegmentList(array=placed[0][0])
 
 
 # ----------------------------------------------------------------------------------------- counters
@@ -706,9 +721,8 @@ class AnnotatorResult(object):
         return float(self._source[sample_id])
 
     def getEmpiricalPValue(self, value):
-        st = getContext().column_stats(self._column(), [float(value)])
-        # the reference compares against the stored expected value (gat/Engine.pyx:1556)
-        return float(st["pvalue"][0])
+        # against the STORED expected value (gat/Engine.pyx:1564), which includes a reference fold
+        return float(getContext().column_pvalue(self._column(), [float(value)], [self.expected])[0])
 
     def _columns(self):
         if self.fold > 0:

@@ -15,6 +15,23 @@ def rank_world():
     return 0, 1
 
 
+def share_seed():
+    """make every rank use rank 0's placement seed (an unseeded run draws it from numpy's global generator,
+    which differs between processes)"""
+    import torch.distributed as dist
+    from . import engine
+    rank, world = rank_world()
+    if world == 1:
+        return engine.getSeed()
+    box = [engine.getSeed() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    if rank != 0:
+        calls = engine._rng_state["calls"]
+        engine.seed(box[0])
+        engine._rng_state["calls"] = calls
+    return box[0]
+
+
 def shard_range(num_samples, rank, world):
     """[begin, end) of the global sample indices owned by `rank`"""
     return (rank * num_samples) // world, ((rank + 1) * num_samples) // world

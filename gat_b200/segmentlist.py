@@ -5,7 +5,7 @@ Only input preparation runs here (load -> normalize -> filter/intersect with the
 isochore; gat/IO.py:88-293).  That is one-off O(input) work outside the simulation loop; the per-sample
 interval algebra of the hot path (sort/merge/intersect/overlap inside SamplerAnnotator.sample and the
 Counter classes) runs in the CUDA kernels.  Method names and semantics follow the reference so its
-tests read the same (tests/test_segmentlist.py ports test/test_SegmentList.py).
+tests read the same (tests/test_oracle_golden.py and tests/test_host_logic.py pin it to the reference's results).
 """
 import numpy as np
 

@@ -3,7 +3,7 @@
 Host numpy over at most tracks x annotations x counters numbers, executed once per run by
 `outputResults` (reference call site: gat/IO.py:466-477).  Behaviour follows gat/Stats.py
 (`adjustPValues` :192-258 = R's p.adjust; `computeQValues` :26-160 = Storey's q-value), written
-vectorised; tests/test_stats_host.py pins both against golden vectors produced by the reference.
+vectorised; tests/test_host_logic.py pins both against golden vectors produced by the reference.
 """
 import numpy as np
 

@@ -124,7 +124,10 @@ int  gatb_count_lists(gatb_ctx *ctx, const gatb_annotations *annos, int n_counte
  * first appearance (= sample.keys() order after fromIsochores); has_isochores != 0 when keys carry an
  * isochore suffix, in which case each contig's placed lists are concatenated and merge(0)-ed before
  * counting (gat/Engine.pyx:2857-2876).  bucket_size / nbuckets as in --bucket-size / --nbuckets
- * (0 = automatic, gat/SegmentList.pyx:1164-1165).  Host pointers; data is copied to the device and
+ * (bucket_size 0 = automatic, gat/SegmentList.pyx:1164-1165; GATB_ERR_TOO_LARGE where getLengthDistribution
+ * raises "segment too large", :1170).  nbuckets = 0 builds NO length histogram: such a sampler serves
+ * gatb_sampler_set_shift only -- SamplerShift never calls getLengthDistribution (gat/Engine.pyx:1060-1062),
+ * so no segment is too large for it.  Host pointers; data is copied to the device and
  * the sample-invariant preparation (filter, ltotal, length table, workspace CDF: gat/Engine.pyx:543-565)
  * runs once, on the GPU. */
 int  gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *unit_contig, int n_contigs,
@@ -133,8 +136,12 @@ int  gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *unit_contig,
                          const uint64_t *ws_offs, const uint32_t *ws_start, const uint32_t *ws_end,
                          uint32_t bucket_size, uint32_t nbuckets, gatb_sampler **out);
 void gatb_sampler_destroy(gatb_sampler *s);
-/* capacity (in segments) of one sample's contig-level output, and of contig c inside it */
+/* capacity (in segments) of one sample's contig-level output (gatb_sampler_place) and of its unit-level
+ * output (gatb_sampler_place_units).  Capacities are estimates made at creation; a unit that outgrows its
+ * buffer is grown by the library and the call repeated internally (the reference's lists grow on demand,
+ * gat/SegmentList.pyx:513-537), after which these values are larger. */
 uint64_t gatb_sampler_sample_capacity(const gatb_sampler *s);
+uint64_t gatb_sampler_unit_capacity(const gatb_sampler *s);
 
 /* Sampler used for placement: 0 = SamplerAnnotator (default), 1 = SamplerSegments (gat/Engine.pyx:653-737:
  * exactly len(segments[key]) placements per unit, all kept).  SamplerSegments' samples are unsorted and
@@ -158,11 +165,22 @@ int  gatb_sampler_set_shift(gatb_sampler *s, double radius, int32_t extension);
  * counts[s*n_contigs+c] segments for contig c of sample s, stored at start/end[s*capacity + contig_base[c] ...]
  * where capacity = gatb_sampler_sample_capacity() and contig_base is returned in contig_base[n_contigs].
  * unit_status[s*n_units+u] (may be NULL): bit0 = stopped after 20 non-improving rounds
- * (gat/Engine.pyx:570-572), bit1 = capacity overflow.  For tests, --output-samples-pattern, and the
- * same-placement parity fixture. */
+ * (gat/Engine.pyx:570-572), bit1 = capacity overflow.  For tests and the same-placement parity fixture.
+ * GATB_ERR_CAPACITY: a unit outgrew its buffer and the library enlarged it -- the arrays sized from the
+ * earlier capacity query are too small: query gatb_sampler_sample_capacity() again and repeat the call. */
 int  gatb_sampler_place(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin,
                         uint64_t n_samples, uint32_t *start, uint32_t *end, uint32_t *counts,
                         uint64_t *contig_base, uint8_t *unit_status);
+
+/* The same placement, returned per UNIT (= per key of the track, "contig" or "contig.isochore"), before
+ * fromIsochores: exactly what sampler.sample(segs[key], workspace[key]) returns for every key
+ * (gat/__init__.py:531-546) and what --output-samples-pattern writes under each key (:518-559).  For
+ * SamplerSegments (kind 1) the lists are in draw order, unsorted and unmerged (gat/Engine.pyx:719-735).
+ * counts[s*n_units+u] segments of unit u of sample s at start/end[s*capacity + unit_base[u] ...] with
+ * capacity = gatb_sampler_unit_capacity(); GATB_ERR_CAPACITY as for gatb_sampler_place. */
+int  gatb_sampler_place_units(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin,
+                              uint64_t n_samples, uint32_t *start, uint32_t *end, uint32_t *counts,
+                              uint64_t *unit_base, uint8_t *unit_status);
 
 /* ---- the hot path: place + count ----------------------------------------------------------------
  * Replaces UnconditionalSampler.sample() (gat/__init__.py:704-778) for one track: for every sample
@@ -174,12 +192,27 @@ int  gatb_sampler_place(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t
  *   out_is_device != 0: out_counts / out_density are device pointers (results stay in HBM, no sync);
  *   otherwise host pointers (copied back, stream synchronised).
  *   info (may be NULL, host): [0] total segments placed (contig level), [1] units that hit the
- *   20-round cap, [2] units that overflowed (then GATB_ERR_CAPACITY is returned). */
+ *   20-round cap, [2] 0.  A unit that outgrows its buffer is grown and the call runs again internally
+ *   (same stream of draws, hence the same result as a run with enough room from the start);
+ *   GATB_ERR_CAPACITY only if one contig needed more than 2^24 slots. */
 int  gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_counters, const int32_t *counters,
               uint64_t seed, uint32_t track, uint64_t sample_begin, uint64_t n_samples,
               uint32_t *out_counts, double *out_density, int out_is_device, uint64_t *info);
 /* samples placed + counted per internal batch (memory/parallelism knob; 0 = default) */
 int  gatb_set_batch_size(gatb_ctx *ctx, uint32_t batch);
+
+/* ---- measurement aids (bench.py `roofline`; no reference counterpart) ------------------------------
+ * gatb_count_work: the work of the counting kernel on the LAST internal batch of the preceding gatb_run on
+ * this sampler (n_samples = size of that batch): out[0] placed segments, out[1] index entries in their runs
+ * (= entries the kernel tests, padding included; compare with the truly overlapping pairs given by the
+ * GATB_OVERLAP_PIECES counter), out[2] entries of the whole index, out[3] bytes of the index arrays read.
+ * gatb_microbench: a machine peak measured on `device` with CUDA events, best of `repeats` runs:
+ *   which 0: L2 read bandwidth (a `bytes`-sized buffer, default 48 MB, streamed by every SM with 16-byte
+ *            loads) -> out[0] GB/s;   which 1: warp-instruction issue rate (independent integer chains on
+ *            64 warps per SM) -> out[0] 1e9 warp instructions/s.   out[1] ms of the best run, out[2] its work
+ *            (bytes / warp instructions), out[3] number of SMs. */
+int  gatb_count_work(gatb_sampler *s, const gatb_annotations *annos, uint32_t n_samples, uint64_t *out /*[4]*/);
+int  gatb_microbench(int device, int which, uint64_t bytes, int repeats, double *out /*[4]*/);
 
 /* ---- per-column statistics ------------------------------------------------------------------------
  * Replaces makeEnrichmentStatistics + getTwoSidedPValue (gat/Engine.pyx:1635-1718, :1543-1576) for
@@ -192,6 +225,14 @@ int  gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float, int coun
                        uint64_t n_samples, int n_cols, const double *observed, const double *ref_fold,
                        double pseudo_count, double *expected, double *stddev, double *lower95,
                        double *upper95, double *fold, double *pvalue);
+
+/* Replaces AnnotatorResult.getEmpiricalPValue(value) (gat/Engine.pyx:1829-1831 -> getTwoSidedPValue,
+ * :1543-1576): the two-sided empirical p-value of values[a] among the samples of column a, where the over- /
+ * under-representation branch is chosen against the result's STORED expectation expected[a] (which includes a
+ * --null reference fold, :1673-1676).  counts as in gatb_column_stats; values, expected, pvalue: host, n_cols. */
+int  gatb_column_pvalue(gatb_ctx *ctx, const void *counts, int is_float, int counts_is_device,
+                        uint64_t n_samples, int n_cols, const double *values, const double *expected,
+                        double *pvalue);
 
 /* ---- gat-compare: pairwise comparison of fold changes ----------------------------------------------
  * Replaces the inner loop of scripts/gat-compare.py (:218-241 within one counts file, :300-323 between

@@ -1,0 +1,213 @@
+"""GPU tests of the round-2 additions: buffers that grow on demand (skewed units), SamplerShift without a length
+histogram, unit-level placement (per-key samples, SamplerSegments.sample), getEmpiricalPValue against the stored
+expectation, the per-key --output-samples-pattern file."""
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def test_skewed_unit_grows_its_buffer(ctx, oracle):
+    """HistogramSampler never draws the largest rank, so a unit whose largest segment holds most of
+    the bases is refilled with the small lengths: 200 + 300 + 50 000 bp need > 150 placements against the 128
+    slots a 3-segment unit used to get.  The reference grows its lists on demand; so must the library."""
+    from gat_b200 import device
+    ws = np.array([[0, 4000000]], dtype=np.uint32)
+    segs = np.array([[1000, 1200], [5000, 5300], [100000, 150000]], dtype=np.uint32)
+    smp = device.Sampler(ctx, [0], 1, False, [segs], [ws])
+    n = 5
+    placed, status = smp.place(seed=8, track=0, sample_begin=0, n_samples=n)
+    assert not (status & device.UNIT_OVERFLOW).any()
+    nmax = 0
+    for s in range(n):
+        exp, info = oracle.sampler_annotator_philox(segs, ws, 8, 0, 0, s, cap=8192)
+        assert np.array_equal(placed[s][0], exp), s
+        nmax = max(nmax, info.nplaced)
+    assert nmax > 128
+    # forced: a capacity estimate that is far too small is repaired by the grow-and-repeat path of gatb_run
+    # and of gatb_sampler_place (same results, larger capacity afterwards)
+    rng = np.random.default_rng(3)
+    pr = helpers.random_problem(rng, n_contigs=2, n_iso=0, nseg=300)
+    annos = device.Annotations(ctx, pr["annotations"], key_ws_nseg=pr["cws_nseg"])
+    for c in range(pr["n_contigs"]):        # skew every unit: one huge segment next to the short ones
+        u = pr["unit_segments"][c]
+        last = int(u[-1, 1])
+        pr["unit_segments"][c] = np.concatenate([u, np.array([[last + 10, last + 60000]], dtype=np.uint32)])
+        w = pr["unit_workspace"][c]
+        pr["unit_workspace"][c] = helpers.normalize(np.concatenate([w, np.array([[last, last + 70000]], dtype=np.uint32)]))
+    smp2 = device.Sampler(ctx, pr["unit_contig"], pr["n_contigs"], False, pr["unit_segments"], pr["unit_workspace"])
+    names = ["nucleotide-overlap", "segment-overlap"]
+    res, info = smp2.run(annos, names, seed=2, track=0, sample_begin=0, n_samples=16)
+    assert int(info[2]) == 0
+    for s in (0, 15):
+        exp = oracle.compute_sample_philox(pr["unit_contig"], pr["unit_segments"], pr["unit_workspace"],
+                                           pr["annotations"], pr["cws_nseg"], names, seed=2, track=0, sample=s)
+        for i, name in enumerate(names):
+            assert np.array_equal(res[name][s].astype(np.float64), exp[i]), (s, name)
+    smp.close()
+    smp2.close()
+    annos.close()
+
+
+def test_overflow_growth_is_exercised(ctx, oracle, monkeypatch):
+    """the grow-and-repeat path itself: GATB_PLACE_CAP_MAX clamps the initial capacities so that units DO
+    overflow on the first pass; results must equal an unclamped run and the oracle"""
+    from gat_b200 import device
+    rng = np.random.default_rng(17)
+    pr = helpers.random_problem(rng, n_contigs=3, n_iso=3, nseg=200, n_annot=3)
+    annos = device.Annotations(ctx, pr["annotations"], key_ws_nseg=pr["cws_nseg"])
+    names = ["nucleotide-overlap"]
+    plain = device.Sampler(ctx, pr["unit_contig"], pr["n_contigs"], True, pr["unit_segments"], pr["unit_workspace"])
+    want, _ = plain.run(annos, names, seed=6, track=0, sample_begin=0, n_samples=40)
+    want_placed, _ = plain.place(seed=6, track=0, sample_begin=0, n_samples=4)
+    cap0 = plain.capacity
+    plain.close()
+    monkeypatch.setenv("GATB_PLACE_CAP_MAX", "64")
+    small = device.Sampler(ctx, pr["unit_contig"], pr["n_contigs"], True, pr["unit_segments"], pr["unit_workspace"])
+    monkeypatch.delenv("GATB_PLACE_CAP_MAX")
+    assert small.capacity < cap0
+    got_placed, status = small.place(seed=6, track=0, sample_begin=0, n_samples=4)
+    assert small.capacity > 64 * 3 and not (status & device.UNIT_OVERFLOW).any()
+    for s in range(4):
+        for c in range(pr["n_contigs"]):
+            assert np.array_equal(got_placed[s][c], want_placed[s][c])
+    small.close()
+    monkeypatch.setenv("GATB_PLACE_CAP_MAX", "64")
+    small = device.Sampler(ctx, pr["unit_contig"], pr["n_contigs"], True, pr["unit_segments"], pr["unit_workspace"])
+    monkeypatch.delenv("GATB_PLACE_CAP_MAX")
+    got, info = small.run(annos, names, seed=6, track=0, sample_begin=0, n_samples=40)
+    assert np.array_equal(got[names[0]], want[names[0]]) and int(info[2]) == 0
+    units, _ = small.place_units(seed=6, track=0, sample_begin=0, n_samples=2)
+    for u in range(len(pr["unit_contig"])):
+        exp, _ = oracle.sampler_annotator_philox(pr["unit_segments"][u], pr["unit_workspace"][u], 6, 0, u, 1)
+        assert np.array_equal(units[1][u], exp), u
+    small.close()
+    annos.close()
+
+
+def test_shift_sampler_needs_no_histogram(ctx, oracle):
+    """SamplerShift never calls getLengthDistribution, so a 100 000 bp segment (automatic bucket
+    size -> index == nbuckets -> "segment too large" for the annotator) must not stop --sampler=shift"""
+    import gat_b200
+    from gat_b200 import device, _lib, engine
+    from gat_b200.segmentlist import SegmentList
+    ws = np.array([[0, 3000000]], dtype=np.uint32)
+    segs = np.array([[10000, 110000], [500000, 500400], [900000, 1000000]], dtype=np.uint32)
+    with pytest.raises(_lib.GatB200Error) as e:
+        device.Sampler(ctx, [0], 1, False, [segs], [ws], bucket_size=0, nbuckets=100000)
+    assert e.value.code == _lib.ERR_TOO_LARGE
+    smp = device.Sampler(ctx, [0], 1, False, [segs], [ws], bucket_size=1, nbuckets=0)
+    with pytest.raises(_lib.GatB200Error):          # no histogram: the annotator cannot run on it
+        smp.place(seed=1, track=0, sample_begin=0, n_samples=1)
+    smp.set_shift(2, 0)
+    placed, status = smp.place(seed=1, track=0, sample_begin=0, n_samples=4)
+    smp.close()
+    for s in range(4):
+        assert np.array_equal(placed[s][0], oracle.sampler_shift(segs, ws, radius=2, philox=(1, 0, 0, s)))
+    engine.seed(5)
+    sl, w = SegmentList(array=segs), SegmentList(array=ws)
+    sl._normalized = w._normalized = True
+    out = gat_b200.SamplerShift(radius=2).sample(sl, w)
+    assert out.sum() == 200400
+
+
+def test_unit_level_placement_and_sampler_segments_sample(ctx, oracle):
+    """gatb_sampler_place_units returns what sampler.sample(segs[key], workspace[key]) returns for every key
+    (gat/__init__.py:531-546): annotator units sorted + merged, SamplerSegments units in draw order"""
+    import gat_b200
+    from gat_b200 import device, engine
+    from gat_b200.segmentlist import SegmentList
+    rng = np.random.default_rng(12)
+    for n_iso in (0, 3):
+        pr = helpers.random_problem(rng, n_contigs=3, n_iso=n_iso)
+        smp = device.Sampler(ctx, pr["unit_contig"], pr["n_contigs"], pr["has_isochores"],
+                             pr["unit_segments"], pr["unit_workspace"])
+        units, _ = smp.place_units(seed=21, track=2, sample_begin=5, n_samples=3)
+        for s in range(3):
+            assert len(units[s]) == len(pr["unit_contig"])
+            for u in range(len(pr["unit_contig"])):
+                exp, _ = oracle.sampler_annotator_philox(pr["unit_segments"][u], pr["unit_workspace"][u], 21, 2, u, 5 + s)
+                assert np.array_equal(units[s][u], exp), (n_iso, s, u)
+        if n_iso:
+            smp.set_kind("segments")
+            units, _ = smp.place_units(seed=21, track=2, sample_begin=5, n_samples=2)
+            for u in range(len(pr["unit_contig"])):
+                exp = oracle.sampler_segments(pr["unit_segments"][u], pr["unit_workspace"][u], philox=(21, 2, u, 6))
+                assert np.array_equal(units[1][u], exp), u
+        smp.close()
+    # the per-call protocol of the reference: SamplerSegments().sample(segments, workspace)
+    segs, ws = helpers.random_unit(rng)
+    engine.seed(99)
+    sl, w = SegmentList(array=segs), SegmentList(array=ws)
+    sl._normalized = w._normalized = True
+    sampler = gat_b200.SamplerSegments()
+    first = sampler.sample(sl, w)
+    second = sampler.sample(sl, w)
+    assert np.array_equal(first.asarray(), oracle.sampler_segments(segs, ws, philox=(99, 0xFFFFFF, 0, 0)))
+    assert np.array_equal(second.asarray(), oracle.sampler_segments(segs, ws, philox=(99, 0xFFFFFF, 0, 1)))
+
+
+def test_empirical_pvalue_uses_stored_expectation(ctx, oracle):
+    """with a --null reference the stored expectation is mean * fold; getEmpiricalPValue must pick the
+    over- / under-representation branch against it (gat/Engine.pyx:1564), not against a recomputed mean"""
+    from gat_b200 import engine
+
+    class Ref(object):
+        fold = 3.0
+
+    rng = np.random.default_rng(4)
+    samples = rng.poisson(100, 400).astype(np.float64)
+    r = engine.AnnotatorResult("t", "a", "nucleotide-overlap", 150.0, samples, reference=Ref())
+    assert r.expected == pytest.approx(samples.mean() * 3.0)
+    srt = np.sort(samples)
+    for value in (90.0, 120.0, 200.0, 310.0, float(srt[10]), float(srt[-3])):
+        # getTwoSidedPValue restated on the sorted samples with the stored expectation
+        l = len(srt)
+        idx = int(np.searchsorted(srt, value, side="left"))
+        if idx == l:
+            idx = 1
+        elif value > r.expected:
+            while idx > 0 and srt[idx] == value:
+                idx -= 1
+            idx = l - (idx + 1)
+        else:
+            while idx < l and srt[idx] == value:
+                idx += 1
+        assert r.getEmpiricalPValue(value) == max(1.0 / l, idx / l), value
+    # without a reference it equals the statistic computed at construction
+    r2 = engine.AnnotatorResult("t", "a", "nucleotide-overlap", 93.0, samples)
+    assert r2.getEmpiricalPValue(93.0) == r2.pvalue == oracle.enrichment_statistics(93.0, samples).pvalue
+
+
+def test_output_samples_pattern_has_unit_keys(ctx, oracle, tmp_path):
+    """--output-samples-pattern writes every unit under its own key (contig.isochore), as the reference does
+    (gat/__init__.py:518-559); the blocks are the oracle's per-unit placements"""
+    import gat_b200
+    from gat_b200 import synthetic, engine
+    genome = [("chrA", 400000), ("chrB", 250000)]
+    segments, annotations, workspaces, iso = synthetic.make(300, 3, 200, isochores=True, genome=genome,
+                                                            isochore_tile=20000, n_isochores=3)
+    workspace = synthetic.prepare(segments, annotations, workspaces, iso)
+    engine.seed(31)
+    pattern = str(tmp_path / "samples_%s.bed")
+    gat_b200.run(segments, annotations, workspace, gat_b200.SamplerAnnotator(), [engine.CounterNucleotideOverlap()],
+                 engine.UnconditionalWorkspace(), num_samples=3, output_samples_pattern=pattern)
+    pr = gat_b200.TrackProblem(segments["merged"], workspace)
+    blocks, cur = {}, None
+    with open(str(tmp_path / "samples_merged.bed")) as f:
+        for line in f:
+            if line.startswith("track name="):
+                cur = int(line.strip().split("=")[1])
+                blocks[cur] = {}
+            else:
+                key, s, e = line.rstrip("\n").split("\t")
+                blocks[cur].setdefault(key, []).append((int(s), int(e)))
+    assert sorted(blocks) == [0, 1, 2]
+    assert any("." in k for k in blocks[0])
+    for s in range(3):
+        for u, key in enumerate(pr.unit_keys):
+            exp, _ = oracle.sampler_annotator_philox(pr.unit_segments[u], pr.unit_workspace[u], 31, 0, u, s)
+            got = np.array(blocks[s].get(key, []), dtype=np.uint32).reshape(-1, 2)
+            assert np.array_equal(got, exp), (s, key)
