@@ -545,7 +545,7 @@ def run_ours(args):
                     torch.cuda.current_stream(dev).synchronize()
                 s2.close()
                 a2.close()
-            return int(host_np.view(np.uint8)[0])
+            return int(host_np.reshape(-1)[:1].view(np.uint8)[0])
 
         if world == 1:
             ctx.set_stream(None)                    # host in / host out: the context's own stream

@@ -216,7 +216,8 @@ class Annotations(object):
 
     def close(self):
         if getattr(self, "handle", None):
-            self.ctx.lib.gatb_annotations_destroy(self.handle)       # waits for a pending build
+            if self.ctx.handle:                                          # (a closed context took its objects along)
+                self.ctx.lib.gatb_annotations_destroy(self.handle)       # waits for a pending build
             self.handle = None
             self._pending = None
 
@@ -264,7 +265,8 @@ class Sampler(object):
 
     def close(self):
         if getattr(self, "handle", None):
-            self.ctx.lib.gatb_sampler_destroy(self.handle)
+            if self.ctx.handle:
+                self.ctx.lib.gatb_sampler_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -749,6 +749,11 @@ void go_set_sampler_kind(int kind) { g_sampler_kind = kind; }
 void go_set_shift_params(double radius, int32_t extension) { g_shift_radius = radius; g_shift_extension = extension; }
 
 /* gat/__init__.py:494-591 computeSample, with the Philox stream of the CUDA kernel */
+/* room per unit for the sampler's result (0: twice / four times the unit's segments + 64); tests of skewed units,
+ * whose samples hold many more segments than the input, raise it */
+static size_t g_unit_cap = 0;
+void go_set_unit_cap(size_t cap) { g_unit_cap = cap; }
+
 int go_compute_sample_philox(int U, int C, int A, const int32_t *unit_contig, int has_isochores,
                              const uint64_t *seg_off, const go_seg *seg,
                              const uint64_t *ws_off, const go_seg *ws,
@@ -763,7 +768,10 @@ int go_compute_sample_philox(int U, int C, int A, const int32_t *unit_contig, in
     size_t total_cap = 0;
     /* SamplerShift cuts a moved segment at workspace gaps: room for more pieces (exceeding it is reported) */
     const size_t cap_mul = g_sampler_kind == 2 ? 4 : 2;
-    for (int u = 0; u < U; u++) total_cap += cap_mul * (size_t)(seg_off[u + 1] - seg_off[u]) + 64;
+    for (int u = 0; u < U; u++) {
+        size_t cap = cap_mul * (size_t)(seg_off[u + 1] - seg_off[u]) + 64;
+        total_cap += cap > g_unit_cap ? cap : g_unit_cap;
+    }
     go_seg *unit_out = (go_seg *)malloc(sizeof(go_seg) * (total_cap ? total_cap : 1));
     size_t *unit_n = (size_t *)calloc((size_t)(U ? U : 1), sizeof(size_t));
     size_t *unit_o = (size_t *)calloc((size_t)(U ? U : 1), sizeof(size_t));
@@ -776,6 +784,7 @@ int go_compute_sample_philox(int U, int C, int A, const int32_t *unit_contig, in
     for (int u = 0; u < U; u++) {
         size_t n = (size_t)(seg_off[u + 1] - seg_off[u]), m = (size_t)(ws_off[u + 1] - ws_off[u]);
         size_t cap = cap_mul * n + 64;
+        if (g_unit_cap > cap) cap = g_unit_cap;
         unit_o[u] = o;
         if (n == 0 || m == 0) { unit_n[u] = 0; o += cap; continue; }
         go_philox_ctx ctx;

@@ -123,6 +123,7 @@ double go_counter(int counter, const go_seg *segments, size_t n, const go_seg *a
  *   anno: A*C lists, annotation-major;  cws_nseg[c]: number of contig-workspace segments
  *   counts: ncounters*A doubles, counter-major.  Philox keyed by (seed, track, unit, sample).
  * Optionally returns the contig-level sample (placed_off C+1, placed cap).  Returns 0 or <0. */
+void go_set_unit_cap(size_t cap);   /* room per unit for a sampler's result (0 = default) */
 int go_compute_sample_philox(int U, int C, int A, const int32_t *unit_contig, int has_isochores,
                              const uint64_t *seg_off, const go_seg *seg,
                              const uint64_t *ws_off, const go_seg *ws,

@@ -343,7 +343,7 @@ def count_placed(placed, annotations, cws_nseg, counters):
 
 def compute_sample_philox(unit_contig, unit_segments, unit_workspace, annotations, cws_nseg, counters,
                           seed, track, sample, has_isochores=False, bucket_size=1, nbuckets=100000,
-                          return_placed=False):
+                          return_placed=False, cap=None):
     """one Monte-Carlo sample (gat/__init__.py:494-591) under the Philox stream."""
     U = len(unit_contig)
     A = len(annotations)
@@ -355,9 +355,13 @@ def compute_sample_philox(unit_contig, unit_segments, unit_workspace, annotation
     cw = np.array(cws_nseg, dtype=np.uint32)
     cid = np.array([COUNTER_ID[c] for c in counters], dtype=np.int32)
     out = np.zeros((len(cid), A), dtype=np.float64)
-    cap = int(4 * len(sdat) + 64 * U + 1024)
+    unit_cap = int(cap or 0)
+    cap = int(cap * U if cap else (4 * len(sdat) + 64 * U + 1024))
     poff = np.zeros(C + 1, dtype=np.uint64)
     pdat = np.zeros((cap, 2), dtype=np.uint32)
+    lib().go_set_unit_cap.restype = None
+    lib().go_set_unit_cap.argtypes = [ctypes.c_size_t]
+    lib().go_set_unit_cap(unit_cap)
     rc = lib().go_compute_sample_philox(U, C, A, _p(uc), int(has_isochores), _p(soff), _p(sdat),
                                         _p(woff), _p(wdat), _p(aoff), _p(adat), _p(cw),
                                         bucket_size, nbuckets, seed, track, sample,

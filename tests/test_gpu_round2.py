@@ -43,7 +43,8 @@ def test_skewed_unit_grows_its_buffer(ctx, oracle):
     assert int(info[2]) == 0
     for s in (0, 15):
         exp = oracle.compute_sample_philox(pr["unit_contig"], pr["unit_segments"], pr["unit_workspace"],
-                                           pr["annotations"], pr["cws_nseg"], names, seed=2, track=0, sample=s)
+                                           pr["annotations"], pr["cws_nseg"], names, seed=2, track=0, sample=s,
+                                           cap=1 << 16)
         for i, name in enumerate(names):
             assert np.array_equal(res[name][s].astype(np.float64), exp[i]), (s, name)
     smp.close()
