@@ -349,7 +349,7 @@ static cudaError_t annotations_build(gatb_annotations *a)
     cudaStream_t st = ctx->upload_stream;
     cudaError_t e = cudaMemsetAsync(a->d_err.p, 0, sizeof(uint32_t), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(a->d_total.p, 0, sizeof(unsigned long long), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(a->boff.p, 0, (a->n_boff + 1) * sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->boff.p, 0, 2 * (a->n_boff + 1) * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     BuildBinsParams bp;
     build_params(a, bp);
@@ -435,7 +435,12 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
         for (uint64_t i = 0; i < n_iv; i += step) { sum += (end[i] > start[i]) ? end[i] - start[i] : 0u; cnt++; }
         mean_len = std::max<uint64_t>(1, sum / cnt);
     }
-    if (shift == 0) shift = floor_log2(mean_len);
+    // about half the mean interval length: a segment tests its true overlaps (the C list of its first bin holds
+    // little else) plus the intervals starting within ~W/2 of either end, while an interval is stored
+    // 1 + length / W times (measured on the benchmark shape, mean length 1.4 kb: W = 256 / 512 / 1024 / 2048 ->
+    // 14.5 / 15.8 / 18.9 / 25.4 entries tested per segment for 11.2 true overlaps, index 1.2 / 0.68 / 0.42 /
+    // 0.29 GB, counting kernel 1.40 / 1.40 / 1.47 / 1.70 ms; profiles/r02_bin_width_sweep.txt)
+    if (shift == 0) shift = floor_log2(mean_len) > 4 ? floor_log2(mean_len) - 1 : 4;
     shift = std::min(20u, std::max(4u, shift));
     gatb_annotations *a = new gatb_annotations();
     a->ctx = ctx; a->n_annot = A; a->n_keys = K; a->n_groups = G; a->ka = ka;
@@ -467,10 +472,10 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
             n_boff += (uint64_t)kb.nbins + 1;
             est += (double)n * (1.0 + (double)mean_len / (double)(1ull << sh));
         }
-    if (n_boff > 0x7fffffffull) { delete a; return fail(ctx, GATB_ERR_INVALID, "annotations: index too large"); }
+    if (n_boff > 0x3ffffff0ull) { delete a; return fail(ctx, GATB_ERR_INVALID, "annotations: index too large"); }
     a->n_boff = n_boff;
-    // (+ up to one padding slot per bin: bins hold an even number of entries)
-    a->capacity = (uint64_t)(est * 1.25) + n_boff / 2 + 4096;
+    // (+ up to one padding slot per list, two lists per bin: lists hold an even number of entries)
+    a->capacity = (uint64_t)(est * 1.25) + n_boff + 4096;
     if (env_u32("GATB_INDEX_CAPACITY", 0)) a->capacity = env_u32("GATB_INDEX_CAPACITY", 0);    // (tests: forces the rebuild)
     a->capacity = (a->capacity + 1) & ~(uint64_t)1;
 
@@ -483,11 +488,11 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     cudaError_t e = a->keybins.upload(a->h_keybins.data(), a->h_keybins.size(), st);
     if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, st); a->has_nseg = true; }
     if (e == cudaSuccess) e = a->d_jmax.upload(jmax.data(), K, st);
-    if (e == cudaSuccess) e = a->boff.alloc(n_boff + 1);
+    if (e == cudaSuccess) e = a->boff.alloc(2 * (n_boff + 1));
     if (e == cudaSuccess) e = a->civ.alloc(a->capacity + 2);
     if (e == cudaSuccess) e = a->cent.alloc(a->capacity + 2);
     if (e == cudaSuccess) e = a->cprev.alloc(a->capacity + 2);
-    if (e == cudaSuccess) e = a->scan_tmp.alloc(build_bins_scan_bytes(n_boff + 1));
+    if (e == cudaSuccess) e = a->scan_tmp.alloc(build_bins_scan_bytes(n_boff));
     if (e == cudaSuccess) e = a->d_offs.upload(offs, n_lists + 1, st);
     if (e == cudaSuccess) e = a->d_start.alloc(n_iv);
     if (e == cudaSuccess) e = a->d_end.alloc(n_iv);
@@ -496,7 +501,7 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMemsetAsync(a->d_err.p, 0, sizeof(uint32_t), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(a->d_total.p, 0, sizeof(unsigned long long), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(a->boff.p, 0, (n_boff + 1) * sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->boff.p, 0, 2 * (n_boff + 1) * sizeof(uint32_t), st);
     // The intervals go up in chunks of tracks; the build stream counts the bin entries of a chunk (step 1 of
     // the build) while the next chunk is still on the bus, and runs scan + fill behind the last one.
     {
@@ -574,7 +579,7 @@ extern "C" void gatb_annotations_destroy(gatb_annotations *a)
 static int count_params_annos(const gatb_annotations *a, uint32_t n_samples, bool density, CountParams &p)
 {
     gatb_ctx *ctx = a->ctx;
-    p.keybins = a->keybins.p; p.boff = a->boff.p; p.cent = a->cent.p; p.civ = a->civ.p; p.cprev = a->cprev.p; p.sentinel = (uint32_t)a->capacity;
+    p.keybins = a->keybins.p; p.boff = a->boff.p; p.coff_base = a->n_boff + 1; p.cent = a->cent.p; p.civ = a->civ.p; p.cprev = a->cprev.p; p.sentinel = (uint32_t)a->capacity;
     p.key_ws_nseg = a->has_nseg ? a->key_ws_nseg.p : nullptr;
     p.n_annot = a->n_annot; p.n_keys = a->n_keys; p.n_groups = a->n_groups; p.ka = a->ka;
     p.n_samples = n_samples;
@@ -1281,7 +1286,7 @@ extern "C" int gatb_count_work(gatb_sampler *s, const gatb_annotations *annos, u
     CU(ctx, cudaStreamSynchronize(st));
     out[0] = h[0]; out[1] = h[1];
     out[2] = annos->n_entries;
-    out[3] = (annos->n_boff + 1) * sizeof(uint32_t) + annos->n_entries * sizeof(uint2);
+    out[3] = 2 * (annos->n_boff + 1) * sizeof(uint32_t) + annos->n_entries * sizeof(uint2);
     return GATB_OK;
 }
 

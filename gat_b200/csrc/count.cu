@@ -3,11 +3,12 @@
 // Counting: a CTA owns (group of tracks -- normally ALL tracks) x (chunk of samples) and keeps the chunk's
 // count matrix [sample][track] in shared memory.  It walks the keys (contigs) in order; the work of a key is
 // cut into ITEMS of 32 consecutive segments of one sample (lane = segment), handed to the warps through a
-// shared-memory counter, so that no warp waits for another.  A lane turns its segment into the run of
-// grid-index entries that can overlap it (count.cuh: two or three 4-byte loads); the warp then works the 32
-// runs off as ONE flat sequence of entry PAIRS (bins hold an even number of entries), 32 pairs per round with
-// every lane busy: which run a flat position belongs to comes from a warp OR-reduction (redux.sync) of the
-// runs' first positions, the run's segment from a 16-byte shared-memory load.  Per pair: one 16-byte load; per
+// shared-memory counter, so that no warp waits for another.  A lane turns its segment into the TWO runs of
+// grid-index entries that can overlap it (count.cuh: intervals open at the left edge of its first bin, and
+// intervals starting in its bins; four 4-byte offset loads); the warp then works the up to 64 runs off as ONE flat
+// sequence of entry PAIRS (lists hold an even number of entries), 32 pairs per round with every lane busy:
+// which run a flat position belongs to comes from a warp OR-reduction (redux.sync) of the runs' first
+// positions, the run's segment from a 16-byte shared-memory load.  Per pair: one 16-byte load; per
 // entry the overlap test and an integer atomic into the (sample, track) accumulator.  Three items are in
 // flight per warp -- segment load / bin-offset loads / entry rounds -- and the rounds themselves run as a
 // branch-free three-stage pipeline (ownership, entry loads, counting), which hides the L2, shared-memory and
@@ -25,8 +26,8 @@ namespace gatb {
 
 constexpr uint32_t NO_ITEM = 0xffffffffu;
 
-// shared memory: per-warp staging (32 x 16 B segments + 32 x 4 B previous ends), accumulators, item tables
-__host__ __device__ __forceinline__ size_t count_smem_fixed(uint32_t nwarps) { return (size_t)nwarps * 32u * 20u; }
+// shared memory: per-warp staging (64 runs x (16 B segment + 4 B previous end)), accumulators, item tables
+__host__ __device__ __forceinline__ size_t count_smem_fixed(uint32_t nwarps) { return (size_t)nwarps * 64u * 20u; }
 
 size_t count_smem_bytes(uint32_t schunk, uint32_t ka, uint32_t kgrp, int threads, bool density)
 {
@@ -94,8 +95,8 @@ struct Flight {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// One live entry against its segment [s,e).  A pair met in several bins counts in the bin that holds the
-// first base of the intersection (count.cuh).  Coordinates are < 2^31.
+// One live entry against its segment [s,e).  Every overlapping (segment, interval) pair is met exactly once
+// (count.cuh), so the overlap test is all there is.  Coordinates are < 2^31.
 //   nucleotide-overlap   overlapWithSegments            gat/SegmentList.pyx:1026-1076
 //   segment-overlap      intersectionWithSegments(base) :1078-1146  (a segment counts once per track:
 //                        at the first interval of the track that overlaps it, i.e. previous end <= s)
@@ -104,17 +105,11 @@ struct Flight {
 //                        i.e. when it does not already overlap the previous segment (x >= pe)
 //   overlap-pieces       len(a.intersect(b)): every overlapping pair is one piece (:1469-1549)
 template <int COUNTER>
-__device__ __forceinline__ void count_entry(uint32_t wx, uint32_t wy, uint32_t y, uint32_t j, uint32_t pv,
+__device__ __forceinline__ void count_entry(uint32_t x, uint32_t wy, uint32_t y, uint32_t pv,
                                             const uint4 o, uint32_t pe, uint32_t acc_addr)
 {
-    const uint32_t s = o.x, e = o.y;                        // the entry's segment; o.w = end of bin b0's entries
-    const bool first = (int32_t)wx < 0;
-    const uint32_t x = wx & 0x7fffffffu;
-    const bool overlap = (x < e) & (y > s);
-    // counted in the bin of the intersection's first base: every entry of the segment's first bin b0 (an
-    // interval met there starts in b0 or before it), and in later bins the interval's first entry only
-    const bool mine = (j < o.w) | first;
-    if (!(overlap & mine)) return;
+    const uint32_t s = o.x, e = o.y;                        // the entry's segment
+    if (!((x < e) & (y > s))) return;
     uint32_t cell;
     asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(cell) : "r"(wy & 0xfffu), "r"(acc_addr));
     if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
@@ -143,17 +138,19 @@ __device__ __forceinline__ void count_pair(const uint2 *__restrict__ civ, const 
     uint32_t pe = 0;
     if (NeedPrevSegment<COUNTER>::value) pe = lds32(stg_pe + f.owner * 4u);
     // end = start + length; a length field of 2^20 - 1 sends us to civ[] for the end (rare)
-    uint32_t y0 = (f.w.x & 0x7fffffffu) + (f.w.y >> 12), y1 = (f.w.z & 0x7fffffffu) + (f.w.w >> 12);
+    uint32_t y0 = f.w.x + (f.w.y >> 12), y1 = f.w.z + (f.w.w >> 12);
     if ((f.w.y >> 12) == ENTRY_LEN_MASK) y0 = civ[f.j].y;
     if ((f.w.w >> 12) == ENTRY_LEN_MASK) y1 = civ[f.j + 1u].y;
-    count_entry<COUNTER>(f.w.x, f.w.y, y0, f.j, f.pv.x, o, pe, acc_addr);
-    count_entry<COUNTER>(f.w.z, f.w.w, y1, f.j + 1u, f.pv.y, o, pe, acc_addr);
+    count_entry<COUNTER>(f.w.x, f.w.y, y0, f.pv.x, o, pe, acc_addr);
+    count_entry<COUNTER>(f.w.z, f.w.w, y1, f.pv.y, o, pe, acc_addr);
 }
 
 // an item whose bin offsets have been requested: lane = segment
 struct Indexed {
     uint32_t slot;              // sample slot in the chunk, NO_ITEM: none
-    uint32_t s, e, pe, r0, rf, r1;
+    uint32_t s, e, pe;
+    uint32_t c0, c1;            // C[b0]: intervals open at the left edge of the segment's first bin
+    uint32_t s0, s1;            // S[b0..b1]: intervals starting in the segment's bins
 };
 
 // The 32 runs [r0, r1) of an item as one flat sequence of entries.  stg / stg_pe: shared addresses of the
@@ -170,25 +167,34 @@ template <int COUNTER>
 __device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts &wc, const Indexed &it, uint32_t acc_addr)
 {
     const uint32_t lane = wc.lane, stg = wc.stg, stg_pe = wc.stg_pe;
-    // every bin holds an even number of entries (padded with an entry that overlaps nothing) and starts on an
-    // even index, so runs are whole PAIRS of entries: a lane takes a pair per round with one 16-byte load
-    const uint32_t len = (it.r1 - it.r0) >> 1;              // pairs
+    // every list holds an even number of entries (padded with an entry that overlaps nothing) and starts on an
+    // even index, so runs are whole PAIRS of entries: a lane takes a pair per round with one 16-byte load.
+    // Flat order: lane 0's C run, lane 0's S run, lane 1's C run, ...
+    const uint32_t len_c = (it.c1 - it.c0) >> 1, len_s = (it.s1 - it.s0) >> 1;      // pairs
+    const uint32_t len = len_c + len_s;
     const uint32_t incl = warp_incl_scan_add_u32(len);
     const uint32_t total = __shfl_sync(GATB_FULL, incl, 31);
     if (total == 0) return;
     const uint32_t excl = incl - len;
-    const uint32_t have = __ballot_sync(GATB_FULL, len != 0u);
-    const uint32_t rank = __popc(have & ((1u << lane) - 1u));
+    const uint32_t lt_mask = wc.le_mask >> 1;
+    const uint32_t rank_c = __popc(__ballot_sync(GATB_FULL, len_c != 0u) & lt_mask) +
+                            __popc(__ballot_sync(GATB_FULL, len_s != 0u) & lt_mask);
+    const uint32_t rank_s = rank_c + (len_c != 0u ? 1u : 0u);
     __syncwarp();                                   // the previous item's readers are done with the staging
-    if (len) {
-        sts128(stg + rank * 16u, make_uint4(it.s, it.e, it.r0 - 2u * excl, it.rf));
-        if (NeedPrevSegment<COUNTER>::value) sts32(stg_pe + rank * 4u, it.pe);
+    if (len_c) {
+        sts128(stg + rank_c * 16u, make_uint4(it.s, it.e, it.c0 - 2u * excl, 0u));
+        if (NeedPrevSegment<COUNTER>::value) sts32(stg_pe + rank_c * 4u, it.pe);
+    }
+    if (len_s) {
+        sts128(stg + rank_s * 16u, make_uint4(it.s, it.e, it.s0 - 2u * (excl + len_c), 0u));
+        if (NeedPrevSegment<COUNTER>::value) sts32(stg_pe + rank_s * 4u, it.pe);
     }
     __syncwarp();
     const uint64_t cent = wc.cent;
     const uint32_t *__restrict__ cprev = p.cprev;
     const uint32_t le_mask = wc.le_mask, sentinel = wc.sentinel;
-    const uint32_t first_pos = len ? excl : 0xffffffffu;    // flat pair position of the run's first pair
+    // flat pair positions of the lane's two runs' first pairs (none: never matches a round)
+    const uint32_t first_c = len_c ? excl : 0xffffffffu, first_s = len_s ? excl + len_c : 0xffffffffu;
     uint32_t started = 0xffffffffu;                 // (non-empty runs that begin before the round) - 1
 
     // Rounds of 32 flat pair positions, software-pipelined without branches: stage A (who owns the positions of
@@ -196,7 +202,7 @@ __device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts 
     // loads) two rounds ahead.  Rounds past the end are harmless: no run starts there (owner = the last run)
     // and their positions are >= total (the sentinel pair).
     auto stage_a = [&](uint32_t base) -> uint32_t {
-        const uint32_t mask = __reduce_or_sync(GATB_FULL, shl_clamp(1u, first_pos - base));
+        const uint32_t mask = __reduce_or_sync(GATB_FULL, shl_clamp(1u, first_c - base) | shl_clamp(1u, first_s - base));
         const uint32_t owner = started + __popc(mask & le_mask);
         started += __popc(mask);
         return owner;
@@ -247,8 +253,8 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
     WarpConsts wc;
     wc.lane = lane;
     wc.le_mask = pin_reg(0xffffffffu >> (31u - lane));
-    wc.stg = pin_reg(smem_addr(smem) + (uint32_t)warp * 512u);
-    wc.stg_pe = pin_reg(smem_addr(smem) + (uint32_t)nwarps * 512u + (uint32_t)warp * 128u);
+    wc.stg = pin_reg(smem_addr(smem) + (uint32_t)warp * 1024u);
+    wc.stg_pe = pin_reg(smem_addr(smem) + (uint32_t)nwarps * 1024u + (uint32_t)warp * 256u);
     wc.sentinel = pin_reg(p.sentinel);
     {
         const uint64_t c = (uint64_t)__cvta_generic_to_global(p.cent);
@@ -303,7 +309,8 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
             const uint32_t n_items = pre_k[ns];
             if (n_items) {
                 const KeyBins kb = p.keybins[(uint64_t)g * p.n_keys + k];
-                const uint32_t *__restrict__ boff = p.boff + kb.base;
+                const uint32_t *__restrict__ soff = p.boff + kb.base;
+                const uint32_t *__restrict__ coff = p.boff + p.coff_base + kb.base;
                 const uint64_t *__restrict__ placed_key = p.placed + p.key_base[k] + (uint64_t)s_begin * p.sample_stride;
                 // three items in flight: A = segment requested, B = bin offsets requested, then run
                 uint32_t a_slot = NO_ITEM, a_i = 0, a_n = 0, a_prev = 0;
@@ -316,15 +323,15 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
                     // A -> B': the segment has arrived; request its bin offsets
                     Indexed nb;
                     nb.slot = a_slot;
-                    nb.s = nb.e = nb.pe = nb.r0 = nb.rf = nb.r1 = 0u;
+                    nb.s = nb.e = nb.pe = nb.c0 = nb.c1 = nb.s0 = nb.s1 = 0u;
                     if (a_slot != NO_ITEM) {
                         if (a_i < a_n) {
                             nb.s = seg_start(a_sg); nb.e = seg_end(a_sg);
                             const uint32_t b0 = nb.s >> kb.shift;
                             if (b0 < kb.nbins) {
                                 const uint32_t b1 = min((nb.e - 1u) >> kb.shift, kb.nbins - 1u);
-                                nb.r0 = boff[b0]; nb.rf = boff[b0 + 1u];
-                                nb.r1 = (b1 == b0) ? nb.rf : boff[b1 + 1u];
+                                nb.c0 = coff[b0]; nb.c1 = coff[b0 + 1u];
+                                nb.s0 = soff[b0]; nb.s1 = soff[b1 + 1u];
                             }
                         }
                         if (NeedPrevSegment<COUNTER>::value) {
@@ -430,14 +437,15 @@ __global__ void __launch_bounds__(256) count_work_kernel(CountParams p, unsigned
             const uint32_t n = p.placed_n[(uint64_t)sl * p.n_keys + k];
             if (g == 0) segs += (threadIdx.x == 0) ? n : 0u;
             if (kb.nbins == 0) continue;
-            const uint32_t *__restrict__ boff = p.boff + kb.base;
+            const uint32_t *__restrict__ soff = p.boff + kb.base;
+            const uint32_t *__restrict__ coff = p.boff + p.coff_base + kb.base;
             const uint64_t *__restrict__ segl = p.placed + p.key_base[k] + (uint64_t)sl * p.sample_stride;
             for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
                 const uint64_t sg = segl[i];
                 const uint32_t b0 = seg_start(sg) >> kb.shift;
                 if (b0 >= kb.nbins) continue;
                 const uint32_t b1 = min((seg_end(sg) - 1u) >> kb.shift, kb.nbins - 1u);
-                entries += boff[b1 + 1u] - boff[b0];
+                entries += (coff[b0 + 1u] - coff[b0]) + (soff[b1 + 1u] - soff[b0]);
             }
         }
     for (int d = 16; d > 0; d >>= 1) {
@@ -456,14 +464,16 @@ void launch_count_work(cudaStream_t st, const CountParams &p, unsigned long long
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Grid index construction (replaces a host loop over every interval).
-//   1  bins_pass_kernel<false>: validate, and count the entries of every bin into boff[base + 1 + b];
-//      bins_even_kernel rounds every count up to even
-//   2  exclusive scan of boff[] (cub): boff[base + 1 + b] = first slot of bin b, boff[base] = of the key,
-//      boff[n_boff] = slots needed (bins_total_kernel checks it against the capacity)
-//   3  bins_pass_kernel<true>: entry position = atomicAdd(boff[base + 1 + b], 1); bins_pad_kernel fills the
-//      spare slot of odd bins; afterwards boff[base + 1 + b] is the END of bin b = the start of bin b + 1,
-//      i.e. boff[base + b] .. boff[base + b + 1] is bin b
+// Grid index construction (replaces a host loop over every interval).  boff[] = S half | C half, each n_boff + 1
+// slots; a key owns slots base .. base + nbins of either half.
+//   1  bins_pass_kernel<false>: validate, and count the entries of every list into boff[half + base + 1 + b]
+//      (S: the bin the interval starts in; C: every later bin it reaches into); bins_even_kernel rounds every
+//      count up to even
+//   2  ONE exclusive scan over both halves (cub): boff[half + base + 1 + b] = first slot of list b, the last
+//      element = slots needed (bins_total_kernel checks it against the capacity); the C lists follow the S lists
+//   3  bins_pass_kernel<true>: entry position = atomicAdd(boff[half + base + 1 + b], 1); bins_pad_kernel fills the
+//      spare slot of odd lists; afterwards boff[.. + 1 + b] is the END of list b = the start of list b + 1,
+//      i.e. boff[half + base + b] .. boff[half + base + b + 1] is list b
 // Thread = (key, rank slot j, track): with J = the longest list on the key, slot j of a list of n intervals
 // is interval j*n/J (if that differs from slot j+1's).  Consecutive threads are the same slot of consecutive
 // tracks, so the threads running at any time work on one neighbourhood of the key across all tracks and
@@ -476,7 +486,7 @@ __global__ void __launch_bounds__(256) bins_pass_kernel(BuildBinsParams p)
     const uint64_t J = p.key_jmax[k];
     const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t b0 = 1, b1 = 0, x = 0, y = 0, py = 0, t = 0;       // no bins unless there is a valid interval
-    uint32_t *cur = nullptr;
+    uint32_t *cur_s = nullptr, *cur_c = nullptr;
     if (id < J * p.a_count) {
         const uint64_t j = id / p.a_count;
         const uint32_t a = p.a_begin + (uint32_t)(id % p.a_count);
@@ -495,18 +505,20 @@ __global__ void __launch_bounds__(256) bins_pass_kernel(BuildBinsParams p)
             if (x >= y || py > x) err |= 2u;
             if (err) { if (!FILL) atomicOr(p.error, err); }
             else if (kb.nbins) {
-                cur = p.boff + kb.base + 1u;
+                cur_s = p.boff + kb.base + 1u;
+                cur_c = cur_s + p.n_boff + 1u;
                 b0 = min(x >> kb.shift, kb.nbins - 1u);
                 b1 = min((y - 1u) >> kb.shift, kb.nbins - 1u);
             }
         }
     }
     for (uint32_t b = b0; b <= b1; b++) {
+        uint32_t *cur = (b == b0) ? cur_s : cur_c;
         if (!FILL) atomicAdd(cur + b, 1u);
         else {
             const uint64_t pos = atomicAdd(cur + b, 1u);
             if (pos < p.capacity) {
-                p.cent[pos] = make_uint2((b == b0 ? 0x80000000u : 0u) | x, (min(y - x, ENTRY_LEN_MASK) << 12) | t);
+                p.cent[pos] = make_uint2(x, (min(y - x, ENTRY_LEN_MASK) << 12) | t);
                 if (y - x >= ENTRY_LEN_MASK) p.civ[pos] = make_uint2(x, y);      // only ever read for these
                 p.cprev[pos] = py;
             }
@@ -514,19 +526,19 @@ __global__ void __launch_bounds__(256) bins_pass_kernel(BuildBinsParams p)
     }
 }
 
-// every bin gets an even number of slots
+// every list gets an even number of slots
 __global__ void __launch_bounds__(256) bins_even_kernel(uint32_t *__restrict__ boff, uint64_t n)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) boff[i] = (boff[i] + 1u) & ~1u;
 }
 
-// after the fill: a bin with an odd number of entries ends on an odd index (all bins start on even ones);
+// after the fill: a list with an odd number of entries ends on an odd index (all lists start on even ones);
 // its spare slot takes the entry that overlaps nothing
 __global__ void __launch_bounds__(256) bins_pad_kernel(BuildBinsParams p)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n_boff) return;
+    if (i >= 2u * (p.n_boff + 1u)) return;
     const uint32_t v = p.boff[i];
     if (v & 1u) {
         if (v < p.capacity) { p.cent[v] = make_uint2(0x7fffffffu, 0u); p.cprev[v] = 0u; }
@@ -536,12 +548,13 @@ __global__ void __launch_bounds__(256) bins_pad_kernel(BuildBinsParams p)
 
 __global__ void bins_total_kernel(BuildBinsParams p)
 {
-    // the scan ran over n_boff + 1 elements: the last one is the number of slots all bins need
-    const unsigned long long total = p.boff[p.n_boff];
+    // the scan ran over both halves, 2 * (n_boff + 1) elements: the last one (a slot without a list) is the
+    // number of slots all lists need
+    const unsigned long long total = p.boff[2u * (p.n_boff + 1u) - 1u];
     *p.total = total;
     if (total > p.capacity) atomicOr(p.error, 4u);
-    // entries `capacity`, `capacity + 1` (capacity is even) are the sentinel pair: a continuation entry at the
-    // largest coordinate overlaps no segment
+    // entries `capacity`, `capacity + 1` (capacity is even) are the sentinel pair: an entry at the largest
+    // coordinate overlaps no segment
     p.cent[p.capacity] = p.cent[p.capacity + 1u] = make_uint2(0x7fffffffu, 0u);
     p.cprev[p.capacity] = p.cprev[p.capacity + 1u] = 0u;
 }
@@ -549,7 +562,7 @@ __global__ void bins_total_kernel(BuildBinsParams p)
 size_t build_bins_scan_bytes(uint64_t n_boff)
 {
     size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum((void *)nullptr, bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n_boff);
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(2u * (n_boff + 1u)));
     return bytes;
 }
 
@@ -566,9 +579,10 @@ cudaError_t launch_bins_count(cudaStream_t st, const BuildBinsParams &p)
 // steps 2 and 3 (all tracks: p.a_begin = 0, p.a_count = n_annot)
 cudaError_t launch_bins_finish(cudaStream_t st, const BuildBinsParams &p, void *scan_tmp, size_t scan_bytes)
 {
-    const unsigned nb = (unsigned)((p.n_boff + 1 + 255) / 256);
-    if (p.n_boff) bins_even_kernel<<<nb, 256, 0, st>>>(p.boff, p.n_boff);
-    cudaError_t e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, p.boff, p.boff, (int)(p.n_boff + 1), st);
+    const uint64_t n2 = 2u * (p.n_boff + 1u);
+    const unsigned nb = (unsigned)((n2 + 255) / 256);
+    if (p.n_boff) bins_even_kernel<<<nb, 256, 0, st>>>(p.boff, n2);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, p.boff, p.boff, (int)n2, st);
     if (e != cudaSuccess) return e;
     bins_total_kernel<<<1, 1, 0, st>>>(p);
     if (p.n_intervals && p.n_boff && p.jmax_all) {

@@ -14,22 +14,26 @@ constexpr uint32_t GROUP_TRACKS_MAX = 4096;   // annotation tracks per group (sh
 constexpr uint32_t ENTRY_LEN_MASK = 0xfffffu;
 
 // Annotation index = a uniform GRID over every key (contig), shared by all tracks of a group (normally:
-// all tracks).  Bin b of a key covers positions [b << shift, (b+1) << shift); its ENTRIES are the
-// intervals of every track that touch it, each stored with its track slot, so an interval spanning m bins
-// is stored m times.  A segment [s,e) covering bins b0..b1 finds every interval that can overlap it in
-// ONE contiguous run of entries, boff[b0] .. boff[b1+1]: a two-load replacement for the binary search
-// (utils/gat_utils.c:8-32) that answers all tracks at once.  A pair (segment, interval) met in several
-// bins is counted in the bin that holds the first base of their intersection: in the segment's first bin b0
-// (entry index < boff[b0+1]) every entry counts -- an interval met there starts in b0 or before it -- and in
-// the later bins only an interval's FIRST entry does.  Entries of a bin are in no particular order; all accumulation is by integer atomics,
-// so results do not depend on it.  Every bin holds an EVEN number of entries (an odd bin is padded with an
-// entry that overlaps nothing: start 2^31-1) and so starts on an even index: the counting kernel reads
-// entries two at a time (16-byte loads) and a pair never straddles two segments' runs.
+// all tracks).  Bin b of a key covers positions [b << shift, (b+1) << shift) and owns TWO entry lists:
+//   S[b]  the intervals (of every track) that START in bin b          -- every interval exactly once
+//   C[b]  the intervals that start before bin b and reach into it     -- an interval crossing m bin boundaries m times
+// The S lists of a key are stored back to back in bin order, so the intervals starting anywhere in bins b0..b1 are
+// ONE contiguous run.  A segment [s,e) covering bins b0..b1 meets every interval that can overlap it in exactly
+// two runs -- C[b0] (started earlier, still open at the left edge of b0) and S[b0..b1] -- and meets it ONCE, so no
+// de-duplication is needed: two offset pairs replace the binary search (utils/gat_utils.c:8-32) for all tracks at
+// once.  Nearly every entry of C[b0] truly overlaps the segment (its interval is open at b0's left edge and only has
+// to reach s); the waste is the S entries of bins b0 / b1 outside [s,e): ~W/2 bases' worth at either end.
+// Entries of a list are in no particular order (built with atomics); all accumulation is by integer atomics, so
+// results do not depend on it.  Every list holds an EVEN number of entries (an odd one is padded with an entry
+// that overlaps nothing: start 2^31-1) and so starts on an even index: the counting kernel reads entries two at a
+// time (16-byte loads) and a pair never straddles two segments' runs.
 //
-//   KeyBins keybins[n_groups][n_keys]    where the key's bins start in boff[], how many, log2(bin width)
-//   uint32  boff[]                       per (group, key): nbins+1 entry offsets (absolute, into the arrays below)
+//   KeyBins keybins[n_groups][n_keys]    where the key's bins start in the offset arrays, how many, log2(bin width)
+//   uint32  boff[2 * (n_boff + 1)]       first half: per (group, key) nbins+1 offsets of the S lists, second half
+//                                        (at boff + n_boff + 1): of the C lists; absolute, into the arrays below
+//                                        (all S lists first, then all C lists)
 //   uint2   cent[n_entries]              the entry the counting kernel streams, 8 bytes:
-//                                          .x = start | 1<<31 on the interval's first bin,  .y = min(length, 2^20-1)<<12 | slot
+//                                          .x = start,  .y = min(length, 2^20-1)<<12 | slot
 //                                        (slot = track within the group, < 4096; a length field of 2^20-1
 //                                        sends the kernel to civ[] for the end)
 //   uint2   civ[n_entries]               the exact interval (start, end), read for intervals of 2^20-1 bases or more
@@ -44,7 +48,8 @@ struct KeyBins {
 struct CountParams {
     // annotations
     const KeyBins *keybins;         // [n_groups][n_keys]
-    const uint32_t *boff;
+    const uint32_t *boff;           // S offsets; the C offsets follow at boff + coff_base
+    uint64_t coff_base;             // = n_boff + 1
     const uint2 *cent;
     const uint2 *civ;
     const uint32_t *cprev;
@@ -71,7 +76,8 @@ size_t count_smem_bytes(uint32_t schunk, uint32_t ka, uint32_t kgrp, int threads
 
 // Builds the grid index from the raw annotation CSR arrays on the device and validates the lists
 // (error bit 0: coordinate >= 2^31, bit 1: empty / unsorted / overlapping = not normalized, bit 2: more
-// entries than `capacity`).  Launches: count entries per bin, round up to even, exclusive scan, fill, pad.
+// entries than `capacity`).  Launches: count the S and C entries per bin, round up to even, ONE exclusive scan over
+// both halves of boff[] (so the C lists follow the S lists in the entry arrays), fill, pad.
 struct BuildBinsParams {
     const uint64_t *offs;           // [n_annot*n_keys+1]
     const uint32_t *start, *end;
@@ -79,8 +85,8 @@ struct BuildBinsParams {
     const KeyBins *keybins;         // [n_groups][n_keys]
     const uint32_t *key_jmax;       // [n_keys] longest list (over all tracks) on the key
     uint32_t jmax_all;              // largest of them
-    uint32_t *boff;                 // [n_boff + 1], zeroed by the caller
-    uint64_t n_boff;
+    uint32_t *boff;                 // [2 * (n_boff + 1)], zeroed by the caller: S half, then C half
+    uint64_t n_boff;                // offset slots of one half: sum over (group, key) of nbins + 1
     uint2 *cent;
     uint2 *civ;
     uint32_t *cprev;
