@@ -107,7 +107,8 @@ def sampleTrack(track_index, segs, annotations, workspace, sampler, counters, nu
     out_u = torch.zeros((len(ids), max(n_local, 1), len(atracks)), dtype=torch.int32, device=dev)
     out_f = torch.zeros((max(n_local, 1), len(atracks)), dtype=torch.float64, device=dev) \
         if device.DENSITY in ids else None
-    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    # (torch's legacy default stream has handle 0 = "the library's own stream" at the C ABI: pass cudaStreamLegacy)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream or 1)
     info = smp.run(annos, counter_names, Engine.getSeed(), track_index, begin, n_local,
                    out_counts_ptr=out_u.data_ptr(), out_density_ptr=out_f.data_ptr() if out_f is not None else None)
     smp.close()
@@ -121,8 +122,26 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
 
     kwargs: num_samples (10000), pseudo_count (1.0), reference, output_counts_pattern,
     output_samples_pattern, outfiles, cache / sample_files / num_threads (accepted, unused: the
-    reference's sample cache is dead code and its multiprocessing is replaced by the GPU).
+    reference's sample cache is dead code and its multiprocessing is replaced by the GPU);
+    exchange ("auto" | "allgather" | "columns": how a multi-GPU run combines its slabs, see below).
     """
+    import torch
+    # ONE CUDA stream for the whole run: the library's kernels, torch's tensor operations and the NCCL
+    # collectives are all ordered on it (the library's own stream is non-blocking: it would not even wait for
+    # torch's default stream)
+    ctx = getContext()
+    dev = torch.device("cuda", ctx.device)
+    stream = torch.cuda.Stream(device=dev)
+    stream.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(stream):
+        try:
+            return _run(segments, annotations, workspace, sampler, counters, workspace_generator, **kwargs)
+        finally:
+            torch.cuda.synchronize(dev)
+            ctx.set_stream(None)
+
+
+def _run(segments, annotations, workspace, sampler, counters, workspace_generator, **kwargs):
     from . import parallel
     import torch
 
@@ -161,6 +180,25 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
                        for c in counters]
     mark("observed")
 
+    # How the per-rank slabs [S/G][A] become statistics:
+    #   "allgather"  ONE all-gather per counter: every rank holds the S x A matrix (what north_star names)
+    #   "columns"    ONE all-to-all per counter: rank g holds all S samples of ITS A/G columns, computes their
+    #                statistics, and only the <= 6 x A result doubles are gathered -- 1/G of the traffic and memory
+    #   "auto"       columns once the gathered matrices would exceed 1 GiB per rank (and no counts table is wanted:
+    #                that needs every column on rank 0)
+    exchange = kwargs.get("exchange", os.environ.get("GATB_EXCHANGE", "auto"))
+    if exchange not in ("auto", "allgather", "columns"):
+        raise ValueError("exchange must be auto, allgather or columns")
+    n_atracks = len(list(annotations.tracks))
+    if exchange == "auto":
+        big = 4 * num_samples * n_atracks * len(counters) >= (1 << 30)
+        exchange = "columns" if (world > 1 and big and not output_counts_pattern) else "allgather"
+    if world == 1:
+        exchange = "allgather"
+    if exchange == "columns" and output_counts_pattern:
+        raise ValueError("output_counts_pattern needs every column on rank 0: use exchange='allgather'")
+    col_begin, col_end = parallel.column_range(n_atracks, rank, world) if exchange == "columns" else (0, n_atracks)
+
     sampled = {}
     begin, end = parallel.shard_range(num_samples, rank, world)
     for ntrack, track in enumerate(segments.tracks):
@@ -174,14 +212,21 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
             continue
         out_u, out_f, ids = out
         mark("sampling")
-        # one collective: all-gather the S/G x A slabs of every counter
-        out_u = parallel.allgather_samples(out_u, num_samples, dim=1)
-        if out_f is not None:
-            out_f = parallel.allgather_samples(out_f, num_samples, dim=0)
+        if exchange == "columns":
+            # one collective per counter plane: all-to-all by column
+            planes = [parallel.exchange_columns(out_u[i][:end - begin], num_samples) for i in range(out_u.shape[0])]
+            out_u = torch.stack(planes) if planes else out_u
+            if out_f is not None:
+                out_f = parallel.exchange_columns(out_f[:end - begin], num_samples)
+        else:
+            # one collective: all-gather the S/G x A slabs of every counter
+            out_u = parallel.allgather_samples(out_u, num_samples, dim=1)
+            if out_f is not None:
+                out_f = parallel.allgather_samples(out_f, num_samples, dim=0)
         sampled[track] = (atracks, out_u, out_f, ids)
         if output_samples_pattern and rank == 0:
             _dumpSamples(track, ntrack, segs, workspace, sampler, num_samples, output_samples_pattern)
-    mark("allgather")
+    mark("exchange")
 
     # size / overlap columns of AnnotatorResultExtended: once per track and per annotation, the overlap of a
     # track with every annotation in one GPU call (gat/Engine.pyx:1911-1928 does one intersect per result)
@@ -210,22 +255,34 @@ def run(segments, annotations, workspace, sampler, counters, workspace_generator
             if reference:
                 ref = np.array([reference[track][a].fold for a in atracks], dtype=np.float64)
             # the S x A matrix stays on the GPU (Engine.SampleMatrix): results copy it to the host only
-            # when their samples are asked for
+            # when their samples are asked for.  Column-sharded: this rank's columns [col_begin, col_end)
             matrix = None
+            lo, hi = col_begin, col_end
+            ref_l = None if ref is None else ref[lo:hi]
             if out_u is None:
                 host = np.zeros((num_samples, len(atracks)))
                 st = ctx.column_stats(host.astype(np.uint32), obs, pseudo_count=pseudo_count, ref_fold=ref)
+            elif hi == lo:              # more ranks than columns: nothing to do here
+                st = dict((k, np.zeros(0)) for k in ("expected", "stddev", "lower95", "upper95", "fold", "pvalue"))
+                matrix = Engine.SampleMatrix(out_f if counter.name == "nucleotide-density" else out_u[counter_id],
+                                             counter.name != "nucleotide-density", first_column=lo)
             elif counter.name == "nucleotide-density":
-                st = ctx.column_stats(None, obs, pseudo_count=pseudo_count, ref_fold=ref,
+                st = ctx.column_stats(None, obs[lo:hi], pseudo_count=pseudo_count, ref_fold=ref_l,
                                       device_ptr=out_f.data_ptr(), n_samples=num_samples,
-                                      n_cols=len(atracks), is_float=1)
-                matrix = Engine.SampleMatrix(out_f, False)
+                                      n_cols=hi - lo, is_float=1)
+                matrix = Engine.SampleMatrix(out_f, False, first_column=lo)
             else:
                 plane = out_u[counter_id]
-                st = ctx.column_stats(None, obs, pseudo_count=pseudo_count, ref_fold=ref,
+                st = ctx.column_stats(None, obs[lo:hi], pseudo_count=pseudo_count, ref_fold=ref_l,
                                       device_ptr=plane.data_ptr(), n_samples=num_samples,
-                                      n_cols=len(atracks), is_float=0)
-                matrix = Engine.SampleMatrix(plane, True)
+                                      n_cols=hi - lo, is_float=0)
+                matrix = Engine.SampleMatrix(plane, True, first_column=lo)
+            if exchange == "columns" and out_u is not None:
+                # the result doubles of every rank's columns: one small all-gather
+                keys6 = ("expected", "stddev", "lower95", "upper95", "fold", "pvalue")
+                mine = torch.from_numpy(np.stack([st[k] for k in keys6])).to(torch.device("cuda", ctx.device))
+                full = parallel.allgather_columns(mine, len(atracks)).cpu().numpy()
+                st = dict((k, full[i]) for i, k in enumerate(keys6))
             for ai, annotation in enumerate(atracks):
                 if annotation not in annos_in_result:
                     continue

@@ -594,22 +594,26 @@ cudaError_t launch_bins_finish(cudaStream_t st, const BuildBinsParams &p, void *
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K5 column statistics (gat/Engine.pyx:1635-1718, :1543-1576).  One CTA per column.
-template <typename T>
-__device__ __forceinline__ T block_reduce_sum(T v, T *scratch)
+// K5 column statistics (gat/Engine.pyx:1635-1718, :1543-1576).  The matrix is [sample][column]: a CTA owns a
+// tile of STATS_COLS adjacent columns and streams all samples; thread (c, r) = (column of the tile, row of the
+// pass) reads counts[s][col0 + c] for s = r, r + STATS_ROWS, ..., so a warp reads two 64-byte runs of
+// neighbouring columns per load (every 32-byte sector it touches is used in full; thread = sample with a CTA per
+// column pulled a whole sector per 4-byte value).  Per-thread partials are combined over the rows in a fixed
+// order, so the results are deterministic.
+constexpr int STATS_COLS = 16, STATS_ROWS = 16;
+
+struct StatsThread {
+    uint32_t c, r, col;
+    bool live;
+};
+__device__ __forceinline__ StatsThread stats_thread(const StatsParams &p)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(GATB_FULL, v, d);
-    __syncthreads();
-    if (lane == 0) scratch[warp] = v;
-    __syncthreads();
-    T t = (threadIdx.x < (unsigned)nw) ? scratch[threadIdx.x] : (T)0;
-    if (warp == 0) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(GATB_FULL, t, d);
-    }
-    return t;   // valid in thread 0
+    StatsThread t;
+    t.c = threadIdx.x & (STATS_COLS - 1);
+    t.r = threadIdx.x / STATS_COLS;
+    t.col = blockIdx.x * STATS_COLS + t.c;
+    t.live = t.col < p.n_cols;
+    return t;
 }
 
 __device__ __forceinline__ double load_val(const StatsParams &p, uint64_t s, uint32_t col)
@@ -618,40 +622,51 @@ __device__ __forceinline__ double load_val(const StatsParams &p, uint64_t s, uin
     return (double)reinterpret_cast<const uint32_t *>(p.counts)[s * p.n_cols + col];
 }
 
-__global__ void __launch_bounds__(256) stats_pass1_kernel(StatsParams p)
+__global__ void __launch_bounds__(STATS_COLS * STATS_ROWS) stats_pass1_kernel(StatsParams p)
 {
-    __shared__ unsigned long long su[32];
-    __shared__ double sd[32];
-    const uint32_t col = blockIdx.x;
-    const double obs = p.observed[col];
+    __shared__ unsigned long long su[3][STATS_ROWS][STATS_COLS];
+    __shared__ double sd[STATS_ROWS][STATS_COLS];
+    const StatsThread t = stats_thread(p);
+    const double obs = t.live ? p.observed[t.col] : 0.0;
     unsigned long long isum = 0, nlt = 0, neq = 0;
     double fsum = 0.0;
-    for (uint64_t s = threadIdx.x; s < p.n_samples; s += blockDim.x) {
-        double x;
-        if (p.is_float) { x = reinterpret_cast<const double *>(p.counts)[s * p.n_cols + col]; fsum += x; }
-        else { uint32_t v = reinterpret_cast<const uint32_t *>(p.counts)[s * p.n_cols + col]; isum += v; x = (double)v; }
-        nlt += (x < obs) ? 1ull : 0ull;      // searchargsorted + cmpDouble (gat/Engine.pyx:122-127, 1549-1557)
-        neq += (x == obs) ? 1ull : 0ull;
+    if (t.live)
+        for (uint64_t s = t.r; s < p.n_samples; s += STATS_ROWS) {
+            double x;
+            if (p.is_float) { x = reinterpret_cast<const double *>(p.counts)[s * p.n_cols + t.col]; fsum += x; }
+            else { uint32_t v = reinterpret_cast<const uint32_t *>(p.counts)[s * p.n_cols + t.col]; isum += v; x = (double)v; }
+            nlt += (x < obs) ? 1ull : 0ull;      // searchargsorted + cmpDouble (gat/Engine.pyx:122-127, 1549-1557)
+            neq += (x == obs) ? 1ull : 0ull;
+        }
+    su[0][t.r][t.c] = nlt; su[1][t.r][t.c] = neq; su[2][t.r][t.c] = isum; sd[t.r][t.c] = fsum;
+    __syncthreads();
+    if (t.r == 0 && t.live) {
+        unsigned long long a = 0, b = 0, c = 0;
+        double f = 0.0;
+        for (int r = 0; r < STATS_ROWS; r++) { a += su[0][r][t.c]; b += su[1][r][t.c]; c += su[2][r][t.c]; f += sd[r][t.c]; }
+        p.n_lt[t.col] = a; p.n_eq[t.col] = b;
+        p.sum[t.col] = p.is_float ? f : (double)c;
     }
-    unsigned long long r;
-    r = block_reduce_sum(nlt, su); if (threadIdx.x == 0) p.n_lt[col] = r;
-    r = block_reduce_sum(neq, su); if (threadIdx.x == 0) p.n_eq[col] = r;
-    if (p.is_float) { double t = block_reduce_sum(fsum, sd); if (threadIdx.x == 0) p.sum[col] = t; }
-    else { r = block_reduce_sum(isum, su); if (threadIdx.x == 0) p.sum[col] = (double)r; }
 }
 
-__global__ void __launch_bounds__(256) stats_pass2_kernel(StatsParams p)
+__global__ void __launch_bounds__(STATS_COLS * STATS_ROWS) stats_pass2_kernel(StatsParams p)
 {
-    __shared__ double sd[32];
-    const uint32_t col = blockIdx.x;
-    const double mean = p.mean[col];
+    __shared__ double sd[STATS_ROWS][STATS_COLS];
+    const StatsThread t = stats_thread(p);
+    const double mean = t.live ? p.mean[t.col] : 0.0;
     double acc = 0.0;
-    for (uint64_t s = threadIdx.x; s < p.n_samples; s += blockDim.x) {
-        double d = load_val(p, s, col) - mean;
-        acc += d * d;
+    if (t.live)
+        for (uint64_t s = t.r; s < p.n_samples; s += STATS_ROWS) {
+            const double d = load_val(p, s, t.col) - mean;
+            acc += d * d;
+        }
+    sd[t.r][t.c] = acc;
+    __syncthreads();
+    if (t.r == 0 && t.live) {
+        double f = 0.0;
+        for (int r = 0; r < STATS_ROWS; r++) f += sd[r][t.c];
+        p.sumsq_dev[t.col] = f;
     }
-    double t = block_reduce_sum(acc, sd);
-    if (threadIdx.x == 0) p.sumsq_dev[col] = t;
 }
 
 // order-preserving 64-bit key of a value
@@ -670,41 +685,45 @@ __device__ __forceinline__ double key_val(int is_float, unsigned long long k)
 }
 
 // radix select of two order statistics per column: 8 bits per pass from the top byte
-__global__ void __launch_bounds__(256) stats_select_kernel(StatsParams p)
+__global__ void __launch_bounds__(STATS_COLS * STATS_ROWS) stats_select_kernel(StatsParams p)
 {
-    __shared__ unsigned int hist[2][256];
-    __shared__ unsigned long long prefix_s[2];
-    __shared__ unsigned long long rank_s[2];
-    const uint32_t col = blockIdx.x;
+    __shared__ unsigned int hist[2][STATS_COLS][256];
+    __shared__ unsigned long long prefix_s[2][STATS_COLS];
+    __shared__ unsigned long long rank_s[2][STATS_COLS];
+    const StatsThread t = stats_thread(p);
     const int top = p.is_float ? 56 : 24;
-    if (threadIdx.x == 0) { prefix_s[0] = prefix_s[1] = 0; rank_s[0] = p.rank_lo; rank_s[1] = p.rank_hi; }
+    if (threadIdx.x < 2 * STATS_COLS) {
+        const int w = threadIdx.x / STATS_COLS, c = threadIdx.x % STATS_COLS;
+        prefix_s[w][c] = 0; rank_s[w][c] = w ? p.rank_hi : p.rank_lo;
+    }
     __syncthreads();
     for (int shift = top; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 512; i += blockDim.x) (&hist[0][0])[i] = 0;
+        for (int i = threadIdx.x; i < 2 * STATS_COLS * 256; i += blockDim.x) (&hist[0][0][0])[i] = 0;
         __syncthreads();
-        const unsigned long long pre0 = prefix_s[0], pre1 = prefix_s[1];
+        const unsigned long long pre0 = prefix_s[0][t.c], pre1 = prefix_s[1][t.c];
         const unsigned long long hmask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
-        for (uint64_t s = threadIdx.x; s < p.n_samples; s += blockDim.x) {
-            unsigned long long k = val_key(p, s, col);
-            unsigned int b = (unsigned int)(k >> shift) & 255u;
-            if ((k & hmask) == pre0) atomicAdd(&hist[0][b], 1u);
-            if ((k & hmask) == pre1) atomicAdd(&hist[1][b], 1u);
-        }
+        if (t.live)
+            for (uint64_t s = t.r; s < p.n_samples; s += STATS_ROWS) {
+                const unsigned long long k = val_key(p, s, t.col);
+                const unsigned int b = (unsigned int)(k >> shift) & 255u;
+                if ((k & hmask) == pre0) atomicAdd(&hist[0][t.c][b], 1u);
+                if ((k & hmask) == pre1) atomicAdd(&hist[1][t.c][b], 1u);
+            }
         __syncthreads();
-        if (threadIdx.x < 2) {
-            const int w = threadIdx.x;
-            unsigned long long r = rank_s[w], cum = 0;
+        if (threadIdx.x < 2 * STATS_COLS) {
+            const int w = threadIdx.x / STATS_COLS, c = threadIdx.x % STATS_COLS;
+            unsigned long long r = rank_s[w][c], cum = 0;
             int b = 0;
-            for (; b < 256; b++) { if (cum + hist[w][b] > r) break; cum += hist[w][b]; }
+            for (; b < 256; b++) { if (cum + hist[w][c][b] > r) break; cum += hist[w][c][b]; }
             if (b > 255) b = 255;
-            rank_s[w] = r - cum;
-            prefix_s[w] |= ((unsigned long long)b << shift);
+            rank_s[w][c] = r - cum;
+            prefix_s[w][c] |= ((unsigned long long)b << shift);
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        p.q_lo[col] = key_val(p.is_float, prefix_s[0]);
-        p.q_hi[col] = key_val(p.is_float, prefix_s[1]);
+    if (t.r == 0 && t.live) {
+        p.q_lo[t.col] = key_val(p.is_float, prefix_s[0][t.c]);
+        p.q_hi[t.col] = key_val(p.is_float, prefix_s[1][t.c]);
     }
 }
 
@@ -780,15 +799,15 @@ void launch_format_counts(cudaStream_t st, const uint32_t *counts, uint64_t n_sa
 
 void launch_stats_pass1(cudaStream_t st, const StatsParams &p)
 {
-    if (p.n_cols) stats_pass1_kernel<<<p.n_cols, 256, 0, st>>>(p);
+    if (p.n_cols) stats_pass1_kernel<<<(p.n_cols + STATS_COLS - 1) / STATS_COLS, STATS_COLS * STATS_ROWS, 0, st>>>(p);
 }
 void launch_stats_pass2(cudaStream_t st, const StatsParams &p)
 {
-    if (p.n_cols) stats_pass2_kernel<<<p.n_cols, 256, 0, st>>>(p);
+    if (p.n_cols) stats_pass2_kernel<<<(p.n_cols + STATS_COLS - 1) / STATS_COLS, STATS_COLS * STATS_ROWS, 0, st>>>(p);
 }
 void launch_stats_select(cudaStream_t st, const StatsParams &p)
 {
-    if (p.n_cols) stats_select_kernel<<<p.n_cols, 256, 0, st>>>(p);
+    if (p.n_cols) stats_select_kernel<<<(p.n_cols + STATS_COLS - 1) / STATS_COLS, STATS_COLS * STATS_ROWS, 0, st>>>(p);
 }
 
 }  // namespace gatb

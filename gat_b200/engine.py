@@ -625,11 +625,15 @@ class SampleMatrix(object):
     it and its statistics.  Result objects hold (matrix, column); the host copy is made once, when the first
     result is asked for its samples (output_counts_pattern, getSample, user code) -- outputResults never is."""
 
-    def __init__(self, tensor, as_uint32):
+    def __init__(self, tensor, as_uint32, first_column=0):
         self._tensor = tensor
         self._as_uint32 = as_uint32
         self._host = None
         self.nsamples = int(tensor.shape[0])
+        # a column-sharded run (gat_b200.run, exchange="columns") holds the columns
+        # [first_column, first_column + ncolumns) of the annotation tracks on this rank
+        self.first_column = int(first_column)
+        self.ncolumns = int(tensor.shape[1])
 
     def host(self):
         if self._host is None:
@@ -639,7 +643,12 @@ class SampleMatrix(object):
         return self._host
 
     def column(self, index):
-        return self.host()[:, index]
+        local = index - self.first_column
+        if not 0 <= local < self.ncolumns:
+            raise RuntimeError("column-sharded run: the samples of annotation column %i live on another rank "
+                               "(this rank holds columns %i..%i); run with exchange='allgather' to keep the whole "
+                               "matrix on every rank" % (index, self.first_column, self.first_column + self.ncolumns - 1))
+        return self.host()[:, local]
 
     def text(self):
         """-> (text uint8[], col_off): every column as b"c0,c1,..." (the counts-table format), formatted on

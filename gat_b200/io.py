@@ -55,13 +55,21 @@ def _readBedColumns(filename):
 
         def codes(col):
             arr = table[col].unify_dictionaries().combine_chunks()
-            return arr.indices.to_numpy(zero_copy_only=False).astype(np.int64), arr.dictionary.to_pylist()
+            # (a zero-copy view: `zero_copy_only=False` would import pandas, 1.5-3 s)
+            return np.frombuffer(arr.indices.buffers()[1], dtype=np.int32, count=len(arr), offset=arr.indices.offset * 4
+                                 ).astype(np.int64), arr.dictionary.to_pylist()
 
         contig = codes("c0")
         if any(c.startswith(("track", "#")) for c in contig[1]):
             return None
         name = codes("c3") if ncol > 3 else None
-        return contig, table["c1"].to_numpy(), table["c2"].to_numpy(), name
+        def column(col):
+            a = table[col].combine_chunks()
+            if a.null_count:
+                raise ValueError("empty coordinate")
+            return np.frombuffer(a.buffers()[1], dtype=np.int64, count=len(a), offset=a.offset * 8)
+
+        return contig, column("c1"), column("c2"), name
     except Exception:
         return None
 

@@ -68,9 +68,9 @@ def exchange_columns(local, num_samples):
     on every rank, rank g ends up with ALL samples of its own columns column_range(A, g, G) -- 1/G of the
     all-gather's traffic and memory, and the column statistics (which are independent per column) run on A/G
     columns per GPU.  `local` = this rank's [shard_range(num_samples) rows][A] slab; returns [num_samples][A_g].
-    One all_to_all_single with uneven splits (NCCL on GPUs, gloo in the CPU test).  gat_b200.run() uses the
-    all-gather (the gathered matrix of every BASELINE configuration is read by the statistics kernels in
-    < 1 ms); this is the building block for runs whose S x A does not fit next to the index."""
+    One all_to_all_single with uneven splits (NCCL on GPUs, gloo in the CPU test).  gat_b200.run() takes this
+    route (`exchange="columns"`, or automatically once the gathered matrices would exceed 1 GiB) instead of the
+    all-gather north_star names: 1e6 samples x 1000 tracks are 4 GB per rank gathered, 0.5 GB column-sharded."""
     import torch.distributed as dist
     rank, world = rank_world()
     if world == 1:
@@ -89,6 +89,25 @@ def exchange_columns(local, num_samples):
     dist.all_to_all_single(recv, send, output_split_sizes=out_splits, input_split_sizes=in_splits)
     # pieces arrive in source-rank order = global sample order
     return recv.view(num_samples, a_mine) if a_mine else recv.view(num_samples, 0)
+
+
+def allgather_columns(local, n_columns):
+    """inverse of column_range() for small per-column results: `local` = [..., A_g] (this rank's columns, last
+    dimension) -> [..., A] on every rank.  One all_gather of equal-sized (padded) pieces."""
+    import torch.distributed as dist
+    rank, world = rank_world()
+    if world == 1:
+        return local
+    widths = [column_range(n_columns, r, world) for r in range(world)]
+    widths = [e - b for b, e in widths]
+    widest = max(widths)
+    x = local
+    if x.shape[-1] < widest:
+        pad = torch.zeros(tuple(x.shape[:-1]) + (widest - x.shape[-1],), dtype=x.dtype, device=x.device)
+        x = torch.cat([x, pad], dim=-1)
+    pieces = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(pieces, x.contiguous())
+    return torch.cat([pieces[r][..., :widths[r]] for r in range(world)], dim=-1)
 
 
 def init_from_env(backend=None):

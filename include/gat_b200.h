@@ -66,7 +66,10 @@ int         gatb_version(void);
 int         gatb_create(int device, gatb_ctx **out);
 void        gatb_destroy(gatb_ctx *ctx);
 const char *gatb_last_error(gatb_ctx *ctx);            /* ctx may be NULL: last creation error       */
-int         gatb_set_stream(gatb_ctx *ctx, void *cuda_stream);   /* NULL: the context's own stream  */
+/* cuda_stream: a cudaStream_t; NULL selects the context's own (non-blocking) stream.  A caller that works on the
+ * legacy default stream -- e.g. PyTorch's default stream, whose handle is 0 -- passes cudaStreamLegacy ((void *)1),
+ * otherwise the library's work would not be ordered with the caller's. */
+int         gatb_set_stream(gatb_ctx *ctx, void *cuda_stream);
 int         gatb_synchronize(gatb_ctx *ctx);
 /* number of this library's kernels launched on the context since creation (bench "gpu_launches") */
 uint64_t    gatb_launch_count(gatb_ctx *ctx);

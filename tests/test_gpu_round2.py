@@ -212,3 +212,25 @@ def test_output_samples_pattern_has_unit_keys(ctx, oracle, tmp_path):
             exp, _ = oracle.sampler_annotator_philox(pr.unit_segments[u], pr.unit_workspace[u], 31, 0, u, s)
             got = np.array(blocks[s].get(key, []), dtype=np.uint32).reshape(-1, 2)
             assert np.array_equal(got, exp), (s, key)
+
+
+def test_multirank_run_equals_single_rank():
+    """gat_b200.run under torch.distributed.run over NCCL (2 ranks, S not divisible by 2): statistics and sample
+    matrices equal the 1-rank run for the all-gather and the column-sharded route (tools/multirank_check.py).
+    Needs two GPUs: skipped on a one-GPU box, run explicitly with `gpurun --gpus 2` (profiles/r02_multirank_*.json)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    from tests.test_parallel_gloo import free_port
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+                          os.path.join(root, "tools", "multirank_check.py"), "--samples", "2001", "--tracks", "12"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["ok"]

@@ -31,6 +31,18 @@ WORKER = textwrap.dedent("""
         mine = parallel.exchange_columns(full[b:e].contiguous(), S)
         cb, ce = parallel.column_range(A, rank, world)
         assert mine.shape == (S, ce - cb) and torch.equal(mine, full[:, cb:ce]), (S, A, rank)
+        # per-column results (statistics) of every rank's columns, gathered back to all columns
+        stats = torch.arange(6 * A, dtype=torch.float64).view(6, A)
+        back = parallel.allgather_columns(stats[:, cb:ce].contiguous(), A)
+        assert torch.equal(back, stats), (A, rank)
+    # an unseeded run: every rank ends up with rank 0's seed
+    from gat_b200 import engine
+    import numpy as np
+    np.random.seed(1000 + rank)
+    seed = parallel.share_seed()
+    box = [seed]
+    dist.broadcast_object_list(box, src=0)
+    assert box[0] == seed == engine.getSeed(), (rank, seed, box)
     parallel.finalize()
     print("rank", rank, "ok")
 """)
