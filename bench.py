@@ -300,7 +300,7 @@ def roofline_of(args, wl, ctx, smp, annos, prof, local):
     # work counters of one batch: pairs from the overlap-pieces counter, tested entries from the index geometry
     dev = torch.device("cuda", local)
     plane = torch.zeros((1, B, A), dtype=torch.int32, device=dev)
-    begin = 7 * 10 ** 6
+    begin = 4 * 10 ** 9            # (its own corner of the sample index space, < 2^32)
     info = smp.run(annos, ["overlap-pieces"], SEED, 0, begin, B, out_counts_ptr=plane.data_ptr())
     pairs = int(plane.to(torch.int64).sum().item())
     work = np.zeros(4, dtype=np.uint64)
@@ -549,10 +549,12 @@ def run_ours(args):
 
         if world == 1:
             ctx.set_stream(None)                    # host in / host out: the context's own stream
-        e2e_steps(10 ** 4 - 16, 2)                  # warm-up (allocator pools, pinned paths)
+        # (step indices continue after the device-resident steps: global sample indices stay far below 2^32)
+        e2e_first = last + 8
+        e2e_steps(e2e_first, 2)                     # warm-up (allocator pools, pinned paths)
         barrier()
         t0 = time.perf_counter()
-        e2e_steps(10 ** 4 + 1, args.steps)
+        e2e_steps(e2e_first + 2, args.steps)
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if world > 1:

@@ -164,6 +164,7 @@ def _run(segments, annotations, workspace, sampler, counters, workspace_generato
     import time
     # every rank must place with the SAME seed (the matrix is keyed by seed and global sample index): an
     # unseeded run draws its seed on rank 0 and broadcasts it
+    parallel.join_warm_up()
     parallel.share_seed()
     timing = [("start", time.perf_counter())] if os.environ.get("GATB_TIMING") else None
 

@@ -194,6 +194,7 @@ def main(argv=None):
     parser.add_option("-S", "--stdout", dest="stdout_file", type="string", default=None, help="output file")
     options, _ = parser.parse_args(argv[1:])
     parallel.init_from_env()
+    parallel.warm_up_async()            # NCCL's set-up runs behind the parsing of the input files
     rank, _ = parallel.rank_world()
 
     def log(msg):
@@ -223,8 +224,10 @@ def main(argv=None):
     if options.pvalue_method != "empirical":
         Engine.updatePValues(results, options.pvalue_method)
     if rank == 0:
+        t0 = time.time()
         IO.outputResults(results, options, Engine.AnnotatorResultExtended.headers, description_header,
                          description_width, descriptions)
+        log("output written in %.2f seconds" % (time.time() - t0))
     if options.stdout_file:
         options.stdout.close()
     parallel.finalize()

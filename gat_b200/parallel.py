@@ -110,6 +110,42 @@ def allgather_columns(local, n_columns):
     return torch.cat([pieces[r][..., :widths[r]] for r in range(world)], dim=-1)
 
 
+_warm = {"thread": None}
+
+
+def warm_up_async():
+    """Start NCCL's one-time set-up -- communicator creation and the lazily connected channels of the all-gather and
+    of the all-to-all, several seconds on 8 GPUs -- on a background thread, so that it overlaps input parsing
+    instead of sitting in front of the first exchange.  join_warm_up() waits for it (run() does, before its
+    first collective)."""
+    import threading
+    import torch.distributed as dist
+    rank, world = rank_world()
+    if world == 1 or _warm["thread"] is not None or dist.get_backend() != "nccl":
+        return
+
+    def go():
+        import os
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.cuda.set_device(dev)
+        x = torch.zeros(world, dtype=torch.int32, device=dev)
+        y = torch.empty(world * world, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(y, x)
+        dist.all_to_all_single(torch.empty_like(x), x)
+        dist.all_gather([torch.empty_like(x) for _ in range(world)], x)
+        torch.cuda.synchronize(dev)
+
+    t = threading.Thread(target=go, name="gat_b200-nccl-warm-up", daemon=True)
+    _warm["thread"] = t
+    t.start()
+
+
+def join_warm_up():
+    t = _warm["thread"]
+    if t is not None and t.is_alive():
+        t.join()
+
+
 def init_from_env(backend=None):
     """join the process group described by RANK/WORLD_SIZE/MASTER_* (set by torch.distributed.run);
     a plain single-process start does nothing."""

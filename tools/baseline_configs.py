@@ -3,6 +3,7 @@ and print one JSON line per configuration (wall seconds, samples/s).  Profiling 
 
     python tools/baseline_configs.py [c2 c3 c4 c5]
 """
+import hashlib
 import io
 import json
 import os
@@ -22,6 +23,7 @@ CONFIGS = {
     "c2": (10000, 50, False, "nucleotide-overlap", 10000),
     "c3": (10000, 50, True, "segment-overlap", 10000),
     "c4": (50000, 1000, False, "nucleotide-overlap", 12500),      # one GPU's share of 100k samples on 8 GPUs
+    "c4full": (50000, 1000, False, "nucleotide-overlap", 100000),  # BASELINE config 4 as stated (meant for 8 GPUs)
     "c5": (10000, 200, False, "nucleotide-overlap", 1000000),
     "ns": (10000, 1000, False, "nucleotide-overlap", 100000),     # north-star shape, 1e5 samples
 }
@@ -62,7 +64,8 @@ def main():
             print(json.dumps({"config": name, "segments": nseg, "annotations": nanno, "isochores": iso, "counter": counter,
                               "samples": S, "gpus": world, "prep_s": round(t_prep, 2), "run_s": round(t_run, 3),
                               "output_s": round(t_out, 3), "samples_per_s": round(S / t_run, 1),
-                              "rows": len(rows) - 1, "min_p": min(r.pvalue for r in res),
+                              "rows": len(rows) - 1, "table_md5": hashlib.md5(Opt.stdout.getvalue().encode()).hexdigest(),
+                              "min_p": min(r.pvalue for r in res),
                               "min_q": min(r.qvalue for r in res), "first_row": rows[1][:120]}))
     parallel.finalize()
 
