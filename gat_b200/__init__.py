@@ -95,6 +95,15 @@ def sampleTrack(track_index, segs, annotations, workspace, sampler, counters, nu
         # no isochores: fromIsochores changes nothing, the contig-level annotations are the loaded ones
         annos, _ = Engine.deviceAnnotations(annotations, problem.contigs, [len(workspace[c]) for c in problem.contigs],
                                             annos_cache, lazy=True)
+    elif getattr(annotations, "onDevice", False):
+        # isochores, lists on the GPU: clone + fromIsochores there (gat/__init__.py:716-721), index built in place
+        contig_annotations = annotations.clone()
+        contig_annotations.fromIsochores()
+        contig_workspace = workspace.clone()
+        contig_workspace.fromIsochores()
+        annos, _ = Engine.deviceAnnotations(contig_annotations, problem.contigs,
+                                            [len(contig_workspace[c]) for c in problem.contigs], annos_cache)
+        contig_annotations._drop_device()
     else:
         _, lists, nseg = buildContigAnnotations(annotations, workspace, problem.contigs)
         annos = device.Annotations(ctx, lists, key_ws_nseg=nseg, lazy=True)
@@ -232,7 +241,9 @@ def _run(segments, annotations, workspace, sampler, counters, workspace_generato
     # size / overlap columns of AnnotatorResultExtended: once per track and per annotation, the overlap of a
     # track with every annotation in one GPU call (gat/Engine.pyx:1911-1928 does one intersect per result)
     workspace_size = workspace.sum()
-    anno_sizes = dict((a, (annotations[a].counts(), annotations[a].sum())) for a in annotations.tracks)
+    on_device = getattr(annotations, "onDevice", False)
+    anno_sizes = annotations.trackSizes() if on_device else \
+        dict((a, (annotations[a].counts(), annotations[a].sum())) for a in annotations.tracks)
     track_sizes = {}
     for track in sampled:
         track_sizes[track] = (segments[track].counts(), segments[track].sum(),
@@ -291,7 +302,7 @@ def _run(segments, annotations, workspace, sampler, counters, workspace_generato
                 annotator_results.append(AnnotatorResultExtended(
                     track=track, annotation=annotation, counter=counter.name, observed=r[annotation],
                     samples=(matrix, ai) if matrix is not None else host[:, ai], track_segments=segments[track],
-                    annotation_segments=annotations[annotation], workspace=workspace,
+                    annotation_segments=None if on_device else annotations[annotation], workspace=workspace,
                     reference=reference[track][annotation] if reference else None,
                     pseudo_count=pseudo_count, stats=row,
                     sizes=dict(track_nsegments=track_sizes[track][0], track_size=track_sizes[track][1],

@@ -24,6 +24,9 @@ SYMBOLS = [
     "gatb_sampler_unit_capacity", "gatb_sampler_set_kind", "gatb_sampler_set_shift", "gatb_sampler_place",
     "gatb_sampler_place_units", "gatb_run", "gatb_column_stats", "gatb_column_pvalue", "gatb_compare_stats",
     "gatb_format_counts", "gatb_count_work", "gatb_microbench",
+    "gatb_lists_from_rows", "gatb_lists_from_csr", "gatb_lists_restrict", "gatb_lists_collapse", "gatb_lists_select",
+    "gatb_lists_info", "gatb_lists_sizes", "gatb_lists_download", "gatb_lists_destroy",
+    "gatb_annotations_create_from_lists",
 ]
 
 
@@ -109,5 +112,25 @@ def load():
     L.gatb_count_work.argtypes = [vp, vp, u32, vp]
     L.gatb_microbench.restype = i32
     L.gatb_microbench.argtypes = [i32, i32, u64, i32, vp]
+    L.gatb_lists_from_rows.restype = i32
+    L.gatb_lists_from_rows.argtypes = [vp, u64, vp, vp, vp, u32, i32, ctypes.POINTER(vp)]
+    L.gatb_lists_from_csr.restype = i32
+    L.gatb_lists_from_csr.argtypes = [vp, u32, vp, vp, vp, ctypes.POINTER(vp)]
+    L.gatb_lists_restrict.restype = i32
+    L.gatb_lists_restrict.argtypes = [vp, u32, u32, vp, i32, ctypes.POINTER(vp)]
+    L.gatb_lists_collapse.restype = i32
+    L.gatb_lists_collapse.argtypes = [vp, u32, ctypes.POINTER(vp)]
+    L.gatb_lists_select.restype = i32
+    L.gatb_lists_select.argtypes = [vp, u32, vp, ctypes.POINTER(vp)]
+    L.gatb_lists_info.restype = i32
+    L.gatb_lists_info.argtypes = [vp, vp, vp]
+    L.gatb_lists_sizes.restype = i32
+    L.gatb_lists_sizes.argtypes = [vp, vp, vp]
+    L.gatb_lists_download.restype = i32
+    L.gatb_lists_download.argtypes = [vp, vp, vp, vp]
+    L.gatb_lists_destroy.restype = None
+    L.gatb_lists_destroy.argtypes = [vp]
+    L.gatb_annotations_create_from_lists.restype = i32
+    L.gatb_annotations_create_from_lists.argtypes = [vp, vp, i32, i32, vp, ctypes.POINTER(vp)]
     _lib = L
     return L

@@ -295,6 +295,9 @@ struct gatb_annotations {
     // index that outgrew the estimated capacity can be rebuilt at its exact size without the caller's arrays
     DevBuf<uint64_t> d_offs;
     DevBuf<uint32_t> d_start, d_end, d_err, d_jmax;
+    // where the build reads the lists: the copies above, or device lists owned by the caller (gatb_lists)
+    const uint64_t *src_offs = nullptr;
+    const uint32_t *src_start = nullptr, *src_end = nullptr;
     uint32_t jmax_all = 0;
     DevBuf<unsigned long long> d_total;
     DevBuf<uint8_t> scan_tmp;
@@ -314,7 +317,7 @@ struct gatb_annotations {
 static void build_params(const gatb_annotations *a, BuildBinsParams &bp)
 {
     memset(&bp, 0, sizeof(bp));
-    bp.offs = a->d_offs.p; bp.start = a->d_start.p; bp.end = a->d_end.p; bp.n_intervals = a->n_intervals;
+    bp.offs = a->src_offs; bp.start = a->src_start; bp.end = a->src_end; bp.n_intervals = a->n_intervals;
     bp.keybins = a->keybins.p; bp.key_jmax = a->d_jmax.p; bp.jmax_all = a->jmax_all; bp.boff = a->boff.p; bp.n_boff = a->n_boff;
     bp.cent = a->cent.p; bp.civ = a->civ.p; bp.cprev = a->cprev.p; bp.capacity = a->capacity;
     bp.n_annot = a->n_annot; bp.n_keys = a->n_keys; bp.n_groups = a->n_groups; bp.ka = a->ka;
@@ -401,16 +404,22 @@ static int annotations_finish(gatb_annotations *a)
 
 static inline uint32_t floor_log2(uint64_t x) { uint32_t l = 0; while (x >>= 1) l++; return l; }
 
-extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
-                                             const uint32_t *start, const uint32_t *end, const uint32_t *key_ws_nseg,
-                                             gatb_annotations **out)
+// The lists of an annotation set come either from the host (start / end: copied up in chunks while the build
+// counts behind them) or from device lists the caller owns (dev_*: read in place; `last_end[l]` = end of list l's
+// last interval and `mean_len` then stand in for the host arrays; the caller keeps the lists alive until the
+// build has been waited for).
+static int annotations_create_common(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
+                                     const uint32_t *start, const uint32_t *end, const uint32_t *last_end, uint64_t mean_len_dev,
+                                     const uint64_t *dev_offs, const uint32_t *dev_start, const uint32_t *dev_end,
+                                     const uint32_t *key_ws_nseg, gatb_annotations **out)
 {
     if (!ctx || !out) return GATB_ERR_INVALID;
     *out = nullptr;
     if (n_annot <= 0 || n_keys <= 0) return fail(ctx, GATB_ERR_INVALID, "annotations: need >=1 track and >=1 key");
     const uint64_t n_lists = (uint64_t)n_annot * n_keys;
+    const bool from_device = dev_offs != nullptr;
     // offsets are checked here; the intervals themselves (range, order, normalisation) on the GPU
-    if (!offs || !start || !end) return fail(ctx, GATB_ERR_INVALID, "annotations: NULL array");
+    if (!offs || (!from_device && (!start || !end))) return fail(ctx, GATB_ERR_INVALID, "annotations: NULL array");
     if (offs[0] != 0) return fail(ctx, GATB_ERR_INVALID, "annotations: offsets must start at 0");
     for (uint64_t l = 0; l < n_lists; l++)
         if (offs[l + 1] < offs[l]) return fail(ctx, GATB_ERR_INVALID, "annotations: offsets not monotone");
@@ -428,8 +437,8 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     // correct, it only trades entries per interval against entries per bin), but per key no more than
     // ~4 bins per interval, so that sparse lists do not pay for empty bins.
     uint32_t shift = env_u32("GATB_BIN_SHIFT", 0);
-    uint64_t mean_len = 1;
-    if (n_iv) {
+    uint64_t mean_len = std::max<uint64_t>(1, mean_len_dev);
+    if (n_iv && !from_device) {
         const uint64_t step = std::max<uint64_t>(1, n_iv / 4096);
         uint64_t sum = 0, cnt = 0;
         for (uint64_t i = 0; i < n_iv; i += step) { sum += (end[i] > start[i]) ? end[i] - start[i] : 0u; cnt++; }
@@ -459,7 +468,7 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
             uint32_t extent = 0;
             for (uint32_t t = g * ka; t < std::min(A, (g + 1) * ka); t++) {
                 const uint64_t l = (uint64_t)t * K + k;
-                if (offs[l + 1] > offs[l]) { n += offs[l + 1] - offs[l]; extent = std::max(extent, end[offs[l + 1] - 1]); }
+                if (offs[l + 1] > offs[l]) { n += offs[l + 1] - offs[l]; extent = std::max(extent, from_device ? last_end[l] : end[offs[l + 1] - 1]); }
             }
             KeyBins &kb = a->h_keybins[(size_t)g * K + k];
             kb.base = n_boff; kb.nbins = 0; kb.shift = shift;
@@ -493,9 +502,13 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     if (e == cudaSuccess) e = a->cent.alloc(a->capacity + 2);
     if (e == cudaSuccess) e = a->cprev.alloc(a->capacity + 2);
     if (e == cudaSuccess) e = a->scan_tmp.alloc(build_bins_scan_bytes(n_boff));
-    if (e == cudaSuccess) e = a->d_offs.upload(offs, n_lists + 1, st);
-    if (e == cudaSuccess) e = a->d_start.alloc(n_iv);
-    if (e == cudaSuccess) e = a->d_end.alloc(n_iv);
+    if (from_device) { a->src_offs = dev_offs; a->src_start = dev_start; a->src_end = dev_end; }
+    else {
+        if (e == cudaSuccess) e = a->d_offs.upload(offs, n_lists + 1, st);
+        if (e == cudaSuccess) e = a->d_start.alloc(n_iv);
+        if (e == cudaSuccess) e = a->d_end.alloc(n_iv);
+        a->src_offs = a->d_offs.p; a->src_start = a->d_start.p; a->src_end = a->d_end.p;
+    }
     if (e == cudaSuccess) e = a->d_err.alloc(1);
     if (e == cudaSuccess) e = a->d_total.alloc(1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ready, cudaEventDisableTiming);
@@ -505,13 +518,13 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     // The intervals go up in chunks of tracks; the build stream counts the bin entries of a chunk (step 1 of
     // the build) while the next chunk is still on the bus, and runs scan + fill behind the last one.
     {
-        const uint32_t n_chunks = n_iv >= (4u << 20) ? std::min(4u, A) : 1u;
+        const uint32_t n_chunks = (n_iv >= (4u << 20) && !from_device) ? std::min(4u, A) : 1u;
         BuildBinsParams bp;
         build_params(a, bp);
         for (uint32_t c = 0; c < n_chunks && e == cudaSuccess; c++) {
             const uint32_t a0 = (uint32_t)((uint64_t)A * c / n_chunks), a1 = (uint32_t)((uint64_t)A * (c + 1) / n_chunks);
             const uint64_t i0 = offs[(uint64_t)a0 * K], i1 = offs[(uint64_t)a1 * K];
-            if (i1 > i0) {
+            if (i1 > i0 && !from_device) {
                 e = cudaMemcpyAsync(a->d_start.p + i0, start + i0, (i1 - i0) * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(a->d_end.p + i0, end + i0, (i1 - i0) * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
             }
@@ -533,6 +546,13 @@ extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_k
     a->pending = true;
     *out = a;
     return GATB_OK;
+}
+
+extern "C" int gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_keys, const uint64_t *offs,
+                                             const uint32_t *start, const uint32_t *end, const uint32_t *key_ws_nseg,
+                                             gatb_annotations **out)
+{
+    return annotations_create_common(ctx, n_annot, n_keys, offs, start, end, nullptr, 0, nullptr, nullptr, nullptr, key_ws_nseg, out);
 }
 
 extern "C" int gatb_annotations_wait(gatb_annotations *a)
@@ -1513,4 +1533,328 @@ extern "C" int gatb_format_counts(gatb_ctx *ctx, const uint32_t *counts, int cou
     CU(ctx, cudaMemcpyAsync(text, d_text.p, h_off[A], cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     return GATB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// interval lists on the device (input preparation, prep.cu)
+#include "prep.cuh"
+
+struct gatb_lists {
+    gatb_ctx *ctx = nullptr;
+    uint32_t n_lists = 0;
+    uint64_t n = 0;                      // intervals
+    DevBuf<uint64_t> offs;               // [n_lists + 1]
+    DevBuf<uint32_t> start, end, list_of;   // [n]
+};
+
+static inline int bits_for(uint64_t x) { int b = 0; while (x) { b++; x >>= 1; } return b; }
+
+// device rows (key = list << 32 | start, val = end; unsorted) -> a new gatb_lists: sort, merge, compact.
+// The buffers are consumed.  join_adjacent: 0 = SegmentList.normalize, 1 = merge(0)
+static int lists_from_device_rows(gatb_ctx *ctx, DevBuf<uint64_t> &key, DevBuf<uint32_t> &val, uint64_t n, uint32_t n_lists,
+                                  int join_adjacent, gatb_lists **out)
+{
+    cudaStream_t st = ctx->stream;
+    gatb_lists *L = new gatb_lists();
+    L->ctx = ctx; L->n_lists = n_lists;
+    DevBuf<uint64_t> key_alt;
+    DevBuf<uint32_t> val_alt, head, head_excl;
+    DevBuf<uint8_t> temp;
+    cudaError_t e = cudaSuccess;
+#define TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
+    TRY(L->offs.alloc((size_t)n_lists + 1));
+    if (n == 0) {
+        TRY(cudaMemsetAsync(L->offs.p, 0, ((size_t)n_lists + 1) * sizeof(uint64_t), st));
+        TRY(cudaStreamSynchronize(st));
+        if (e != cudaSuccess) { delete L; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+        *out = L;
+        return GATB_OK;
+    }
+    MergeRows m;
+    memset(&m, 0, sizeof(m));
+    m.n = n; m.end_bit = 32 + std::max(1, bits_for(n_lists)); m.join_adjacent = join_adjacent;
+    m.temp_bytes = sort_temp_bytes(n, m.end_bit);
+    TRY(key_alt.alloc(n)); TRY(val_alt.alloc(n)); TRY(head.alloc(n)); TRY(head_excl.alloc(n)); TRY(temp.alloc(m.temp_bytes));
+    if (e != cudaSuccess) { delete L; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    m.key = key.p; m.key_alt = key_alt.p; m.val = val.p; m.val_alt = val_alt.p; m.head = head.p; m.head_excl = head_excl.p;
+    m.temp = temp.p;
+    { ProfScope ps(ctx, PROF_OTHER); ctx->launches += 6; e = merge_sorted_rows(st, m); }
+    uint32_t tail[2] = {0, 0};          // exclusive head sum and head flag of the last row -> number of merged segments
+    TRY(cudaMemcpyAsync(&tail[0], m.head_excl + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(&tail[1], m.head + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+    L->n = (uint64_t)tail[0] + tail[1];
+    TRY(L->start.alloc(L->n)); TRY(L->end.alloc(L->n)); TRY(L->list_of.alloc(L->n));
+    TRY(cudaMemsetAsync(L->end.p, 0, L->n * sizeof(uint32_t), st));
+    if (e == cudaSuccess) {
+        ProfScope ps(ctx, PROF_OTHER);
+        ctx->launches += 1;
+        launch_rows_emit(st, m, n_lists, L->offs.p, L->start.p, L->end.p, L->list_of.p);
+        e = cudaGetLastError();
+    }
+    TRY(cudaStreamSynchronize(st));
+#undef TRY
+    if (e != cudaSuccess) { delete L; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = L;
+    return GATB_OK;
+}
+
+extern "C" int gatb_lists_from_rows(gatb_ctx *ctx, uint64_t n_rows, const uint32_t *list_id, const uint32_t *start,
+                                    const uint32_t *end, uint32_t n_lists, int join_adjacent, gatb_lists **out)
+{
+    if (!ctx || !out || (n_rows && (!list_id || !start || !end))) return GATB_ERR_INVALID;
+    *out = nullptr;
+    if (n_rows > 0x7fffffffull) return fail(ctx, GATB_ERR_INVALID, "lists: 2^31 or more rows");
+    if (n_lists == 0 || n_lists > 0x7ffffffeu) return fail(ctx, GATB_ERR_INVALID, "lists: need between 1 and 2^31 lists");
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    DevBuf<uint32_t> d_l, d_s, d_e, d_err;
+    DevBuf<uint64_t> key;
+    DevBuf<uint32_t> val;
+    CU(ctx, d_l.upload(list_id, n_rows, st)); CU(ctx, d_s.upload(start, n_rows, st)); CU(ctx, d_e.upload(end, n_rows, st));
+    CU(ctx, d_err.alloc(1));
+    CU(ctx, cudaMemsetAsync(d_err.p, 0, sizeof(uint32_t), st));
+    CU(ctx, key.alloc(n_rows)); CU(ctx, val.alloc(n_rows));
+    { ProfScope ps(ctx, PROF_OTHER); launch_rows_key(st, d_l.p, d_s.p, d_e.p, n_rows, n_lists, key.p, val.p, d_err.p); }
+    uint32_t h_err = 0;
+    CU(ctx, cudaMemcpyAsync(&h_err, d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    if (h_err & 8u) return fail(ctx, GATB_ERR_INVALID, "lists: list id out of range");
+    if (h_err & 1u) return fail(ctx, GATB_ERR_RANGE, "lists: coordinate >= 2^31");
+    if (h_err & 2u) return fail(ctx, GATB_ERR_INVALID, "lists: inverted segment (start > end)");
+    d_l.release(); d_s.release(); d_e.release();
+    return lists_from_device_rows(ctx, key, val, n_rows, n_lists, join_adjacent, out);
+}
+
+extern "C" int gatb_lists_from_csr(gatb_ctx *ctx, uint32_t n_lists, const uint64_t *offs, const uint32_t *start,
+                                   const uint32_t *end, gatb_lists **out)
+{
+    if (!ctx || !out || !offs) return GATB_ERR_INVALID;
+    *out = nullptr;
+    int rc = check_lists(ctx, "lists", n_lists, offs, start, end);
+    if (rc) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    gatb_lists *L = new gatb_lists();
+    L->ctx = ctx; L->n_lists = n_lists; L->n = offs[n_lists];
+    cudaError_t e = L->offs.upload(offs, (size_t)n_lists + 1, st);
+    if (e == cudaSuccess) e = L->start.upload(start, L->n, st);
+    if (e == cudaSuccess) e = L->end.upload(end, L->n, st);
+    if (e == cudaSuccess) e = L->list_of.alloc(L->n);
+    if (e == cudaSuccess) { ProfScope ps(ctx, PROF_OTHER); launch_csr_list(st, L->offs.p, n_lists, L->n, L->list_of.p); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { delete L; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = L;
+    return GATB_OK;
+}
+
+extern "C" void gatb_lists_destroy(gatb_lists *L)
+{
+    if (!L) return;
+    cudaSetDevice(L->ctx->device);
+    delete L;
+}
+
+extern "C" int gatb_lists_info(const gatb_lists *L, uint32_t *n_lists, uint64_t *n_intervals)
+{
+    if (!L) return GATB_ERR_INVALID;
+    if (n_lists) *n_lists = L->n_lists;
+    if (n_intervals) *n_intervals = L->n;
+    return GATB_OK;
+}
+
+extern "C" int gatb_lists_download(const gatb_lists *L, uint64_t *offs, uint32_t *start, uint32_t *end)
+{
+    if (!L) return GATB_ERR_INVALID;
+    gatb_ctx *ctx = L->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (offs) CU(ctx, cudaMemcpyAsync(offs, L->offs.p, ((size_t)L->n_lists + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (start && L->n) CU(ctx, cudaMemcpyAsync(start, L->start.p, L->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (end && L->n) CU(ctx, cudaMemcpyAsync(end, L->end.p, L->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return GATB_OK;
+}
+
+extern "C" int gatb_lists_sizes(const gatb_lists *L, uint64_t *count, uint64_t *bases)
+{
+    if (!L) return GATB_ERR_INVALID;
+    gatb_ctx *ctx = L->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    if (count) {
+        std::vector<uint64_t> h((size_t)L->n_lists + 1);
+        CU(ctx, cudaMemcpyAsync(h.data(), L->offs.p, h.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+        for (uint32_t l = 0; l < L->n_lists; l++) count[l] = h[l + 1] - h[l];
+    }
+    if (bases) {
+        DevBuf<unsigned long long> d;
+        CU(ctx, d.alloc(L->n_lists));
+        CU(ctx, cudaMemsetAsync(d.p, 0, L->n_lists * sizeof(unsigned long long), st));
+        { ProfScope ps(ctx, PROF_OTHER); launch_sizes(st, L->list_of.p, L->start.p, L->end.p, L->n, d.p); }
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaMemcpyAsync(bases, d.p, L->n_lists * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+    }
+    return GATB_OK;
+}
+
+extern "C" int gatb_lists_restrict(const gatb_lists *in, uint32_t n_keys, uint32_t fanout, const gatb_lists *other,
+                                   int truncate, gatb_lists **out)
+{
+    if (!in || !other || !out) return GATB_ERR_INVALID;
+    *out = nullptr;
+    gatb_ctx *ctx = in->ctx;
+    if (other->ctx != ctx) return fail(ctx, GATB_ERR_INVALID, "restrict: lists belong to different contexts");
+    if (n_keys == 0 || fanout == 0 || in->n_lists % n_keys != 0 || (uint64_t)n_keys * fanout != other->n_lists)
+        return fail(ctx, GATB_ERR_INVALID, "restrict: need in.n_lists = tracks * n_keys and other.n_lists = n_keys * fanout");
+    if ((uint64_t)in->n_lists * fanout > 0x7ffffffeull || in->n * fanout > 0x7fffffffull)
+        return fail(ctx, GATB_ERR_INVALID, "restrict: too many lists / intervals");
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    gatb_lists *L = new gatb_lists();
+    L->ctx = ctx; L->n_lists = in->n_lists * fanout;
+    const uint64_t slots = in->n * fanout;
+    DevBuf<uint32_t> cnt, cnt_excl;
+    DevBuf<uint8_t> temp;
+    cudaError_t e = L->offs.alloc((size_t)L->n_lists + 1);
+#define TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
+    RestrictParams p;
+    memset(&p, 0, sizeof(p));
+    p.in_offs = in->offs.p; p.in_start = in->start.p; p.in_end = in->end.p; p.in_list = in->list_of.p; p.n = in->n;
+    p.o_offs = other->offs.p; p.o_start = other->start.p; p.o_end = other->end.p;
+    p.n_keys = n_keys; p.fanout = fanout; p.truncate = truncate ? 1 : 0;
+    uint64_t total = 0;
+    if (slots) {
+        const size_t tb = exclusive_sum_bytes(slots, false);
+        TRY(cnt.alloc(slots)); TRY(cnt_excl.alloc(slots)); TRY(temp.alloc(tb));
+        p.cnt = cnt.p; p.cnt_excl = cnt_excl.p;
+        if (e == cudaSuccess) { ProfScope ps(ctx, PROF_OTHER); e = launch_restrict(st, p, false); }
+        if (e == cudaSuccess) { ctx->launches += 2; e = exclusive_sum_u32(st, temp.p, tb, cnt.p, cnt_excl.p, slots); }
+        uint32_t tail[2] = {0, 0};
+        TRY(cudaMemcpyAsync(&tail[0], cnt_excl.p + (slots - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(&tail[1], cnt.p + (slots - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        TRY(cudaStreamSynchronize(st));
+        total = (uint64_t)tail[0] + tail[1];
+    }
+    L->n = total;
+    TRY(L->start.alloc(total)); TRY(L->end.alloc(total)); TRY(L->list_of.alloc(total));
+    p.out_offs = L->offs.p; p.out_start = L->start.p; p.out_end = L->end.p; p.out_list = L->list_of.p;
+    if (e == cudaSuccess && slots) { ProfScope ps(ctx, PROF_OTHER); e = launch_restrict(st, p, true); }
+    if (e == cudaSuccess) {
+        if (slots) { ProfScope ps(ctx, PROF_OTHER); launch_restrict_offs(st, p, in->n_lists, total); e = cudaGetLastError(); }
+        else e = cudaMemsetAsync(L->offs.p, 0, ((size_t)L->n_lists + 1) * sizeof(uint64_t), st);
+    }
+    TRY(cudaStreamSynchronize(st));
+#undef TRY
+    if (e != cudaSuccess) { delete L; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = L;
+    return GATB_OK;
+}
+
+extern "C" int gatb_lists_collapse(const gatb_lists *in, uint32_t fanout, gatb_lists **out)
+{
+    if (!in || !out) return GATB_ERR_INVALID;
+    *out = nullptr;
+    gatb_ctx *ctx = in->ctx;
+    if (fanout == 0 || in->n_lists % fanout != 0) return fail(ctx, GATB_ERR_INVALID, "collapse: n_lists is not a multiple of fanout");
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    DevBuf<uint64_t> key;
+    DevBuf<uint32_t> val;
+    CU(ctx, key.alloc(in->n)); CU(ctx, val.alloc(in->n));
+    { ProfScope ps(ctx, PROF_OTHER); launch_collapse_key(st, in->list_of.p, in->start.p, in->end.p, in->n, fanout, key.p, val.p); }
+    CU(ctx, cudaGetLastError());
+    return lists_from_device_rows(ctx, key, val, in->n, in->n_lists / fanout, 1, out);
+}
+
+extern "C" int gatb_lists_select(const gatb_lists *in, uint32_t n_out, const uint32_t *src, gatb_lists **out)
+{
+    if (!in || !out || (n_out && !src)) return GATB_ERR_INVALID;
+    *out = nullptr;
+    gatb_ctx *ctx = in->ctx;
+    if (n_out == 0) return fail(ctx, GATB_ERR_INVALID, "select: no lists");
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    gatb_lists *L = new gatb_lists();
+    L->ctx = ctx; L->n_lists = n_out;
+    DevBuf<uint32_t> d_src;
+    DevBuf<unsigned long long> len;
+    DevBuf<uint8_t> temp;
+    const size_t tb = exclusive_sum_bytes((uint64_t)n_out + 1, true);
+    cudaError_t e = d_src.upload(src, n_out, st);
+#define TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
+    TRY(len.alloc((size_t)n_out + 1)); TRY(temp.alloc(tb)); TRY(L->offs.alloc((size_t)n_out + 1));
+    if (e == cudaSuccess) { ProfScope ps(ctx, PROF_OTHER); launch_select_count(st, in->offs.p, d_src.p, n_out, in->n_lists, len.p); e = cudaGetLastError(); }
+    if (e == cudaSuccess) {
+        ctx->launches += 2;
+        e = exclusive_sum_u64(st, temp.p, tb, len.p, reinterpret_cast<unsigned long long *>(L->offs.p), (uint64_t)n_out + 1);
+    }
+    uint64_t total = 0;
+    TRY(cudaMemcpyAsync(&total, L->offs.p + n_out, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+    L->n = total;
+    TRY(L->start.alloc(total)); TRY(L->end.alloc(total)); TRY(L->list_of.alloc(total));
+    if (e == cudaSuccess && total) {
+        ProfScope ps(ctx, PROF_OTHER);
+        launch_select_copy(st, in->offs.p, in->start.p, in->end.p, d_src.p, n_out, in->n_lists,
+                           reinterpret_cast<const unsigned long long *>(L->offs.p), L->start.p, L->end.p, L->list_of.p);
+        e = cudaGetLastError();
+    }
+    TRY(cudaStreamSynchronize(st));
+#undef TRY
+    if (e != cudaSuccess) { delete L; return fail(ctx, GATB_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = L;
+    return GATB_OK;
+}
+
+// annotation set straight from device lists: no host round trip of the intervals ("CSR built once")
+extern "C" int gatb_annotations_create_from_lists(gatb_ctx *ctx, const gatb_lists *L, int n_annot, int n_keys,
+                                                  const uint32_t *key_ws_nseg, gatb_annotations **out)
+{
+    if (!ctx || !L || !out) return GATB_ERR_INVALID;
+    *out = nullptr;
+    if (L->ctx != ctx) return fail(ctx, GATB_ERR_INVALID, "annotations: the lists belong to another context");
+    if (n_annot <= 0 || n_keys <= 0 || (uint64_t)n_annot * n_keys != L->n_lists)
+        return fail(ctx, GATB_ERR_INVALID, "annotations: the lists are not n_annot x n_keys");
+    CU(ctx, cudaSetDevice(ctx->device));
+    tl_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    // the few host-side facts the index geometry needs: list sizes, the extent of every list, the mean length
+    std::vector<uint64_t> offs((size_t)L->n_lists + 1);
+    std::vector<uint32_t> last_end(L->n_lists);
+    DevBuf<uint32_t> d_last;
+    DevBuf<unsigned long long> d_bases;
+    CU(ctx, d_last.alloc(L->n_lists));
+    { ProfScope ps(ctx, PROF_OTHER); launch_last_end(st, L->offs.p, L->end.p, L->n_lists, d_last.p); }
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(offs.data(), L->offs.p, offs.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(last_end.data(), d_last.p, L->n_lists * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    std::vector<unsigned long long> bases(L->n_lists);
+    CU(ctx, d_bases.alloc(L->n_lists));
+    CU(ctx, cudaMemsetAsync(d_bases.p, 0, L->n_lists * sizeof(unsigned long long), st));
+    { ProfScope ps(ctx, PROF_OTHER); launch_sizes(st, L->list_of.p, L->start.p, L->end.p, L->n, d_bases.p); }
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(bases.data(), d_bases.p, L->n_lists * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    unsigned long long total = 0;
+    for (auto b : bases) total += b;
+    const uint64_t mean_len = L->n ? std::max<uint64_t>(1, total / L->n) : 1;
+    int rc = annotations_create_common(ctx, n_annot, n_keys, offs.data(), nullptr, nullptr, last_end.data(), mean_len,
+                                       L->offs.p, L->start.p, L->end.p, key_ws_nseg, out);
+    if (rc) return rc;
+    rc = annotations_finish(*out);          // (synchronous: the lists may be destroyed as soon as this returns)
+    if (rc) {
+        tl_stream = ctx->stream;
+        delete *out;
+        *out = nullptr;
+    }
+    return rc;
 }

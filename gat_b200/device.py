@@ -181,10 +181,100 @@ class Context(object):
         return dict(zip(["expected", "stddev", "lower95", "upper95", "fold", "pvalue"], outs))
 
 
+class Lists(object):
+    """interval lists resident on the GPU as CSR (gatb_lists): the device side of input preparation."""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.handle = handle
+        n_lists, n = ctypes.c_uint32(), ctypes.c_uint64()
+        ctx.check(ctx.lib.gatb_lists_info(handle, ctypes.byref(n_lists), ctypes.byref(n)))
+        self.n_lists, self.n_intervals = int(n_lists.value), int(n.value)
+
+    @classmethod
+    def from_rows(cls, ctx, list_id, start, end, n_lists, join_adjacent=False):
+        """rows in any order -> sorted, normalized (join_adjacent: merge(0)-ed) lists"""
+        l = np.ascontiguousarray(list_id, dtype=np.uint32)
+        s = np.ascontiguousarray(start, dtype=np.uint32)
+        e = np.ascontiguousarray(end, dtype=np.uint32)
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.gatb_lists_from_rows(ctx.handle, len(l), _p(l), _p(s), _p(e), int(n_lists),
+                                               int(bool(join_adjacent)), ctypes.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_lists(cls, ctx, lists):
+        """normalized host lists ((n,2) arrays) -> device lists"""
+        offs, start, end = to_csr(lists)
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.gatb_lists_from_csr(ctx.handle, len(lists), _p(offs), _p(start), _p(end), ctypes.byref(h)))
+        return cls(ctx, h)
+
+    def _new(self, fn, *args):
+        h = ctypes.c_void_p()
+        self.ctx.check(fn(self.handle, *args, ctypes.byref(h)))
+        return Lists(self.ctx, h)
+
+    def restrict(self, n_keys, fanout, other, truncate):
+        """list l against other[(l % n_keys) * fanout + f] for every f: intersect (truncate) or filter"""
+        return self._new(self.ctx.lib.gatb_lists_restrict, int(n_keys), int(fanout), other.handle, int(bool(truncate)))
+
+    def collapse(self, fanout):
+        """every `fanout` consecutive lists -> one, merge(0)-ed (fromIsochores)"""
+        return self._new(self.ctx.lib.gatb_lists_collapse, int(fanout))
+
+    def select(self, src):
+        """out[l] = self[src[l]]; an index >= n_lists gives an empty list"""
+        src = np.ascontiguousarray(src, dtype=np.uint32)
+        return self._new(self.ctx.lib.gatb_lists_select, len(src), _p(src))
+
+    def sizes(self):
+        """-> (len, sum) of every list as uint64 arrays"""
+        count = np.zeros(max(self.n_lists, 1), dtype=np.uint64)
+        bases = np.zeros(max(self.n_lists, 1), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.gatb_lists_sizes(self.handle, _p(count), _p(bases)))
+        return count[:self.n_lists], bases[:self.n_lists]
+
+    def download(self):
+        """-> (offs uint64[n_lists + 1], intervals (n, 2) uint32)"""
+        offs = np.zeros(self.n_lists + 1, dtype=np.uint64)
+        start = np.zeros(max(self.n_intervals, 1), dtype=np.uint32)
+        end = np.zeros(max(self.n_intervals, 1), dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.gatb_lists_download(self.handle, _p(offs), _p(start), _p(end)))
+        return offs, np.stack([start[:self.n_intervals], end[:self.n_intervals]], axis=1)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            if self.ctx.handle:
+                self.ctx.lib.gatb_lists_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Annotations(object):
     """annotation tracks staged on the GPU for counting (gatb_annotations).
 
     lists[a][k]: intervals of track a on key k (n_annot x n_keys)."""
+
+    @classmethod
+    def from_device_lists(cls, ctx, lists, n_annot, n_keys, key_ws_nseg=None):
+        """annotation set straight from n_annot x n_keys device lists (no host round trip of the intervals)"""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.n_annot, self.n_keys = int(n_annot), int(n_keys)
+        nseg = None if key_ws_nseg is None else np.ascontiguousarray(key_ws_nseg, dtype=np.uint32)
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.gatb_annotations_create_from_lists(ctx.handle, lists.handle, self.n_annot, self.n_keys, _p(nseg),
+                                                             ctypes.byref(h)))
+        self.handle = h
+        self.n_intervals = lists.n_intervals
+        self._pending = None
+        return self
 
     def __init__(self, ctx, lists, key_ws_nseg=None, csr=None, lazy=False):
         """lists[a][k], or csr=(n_annot, n_keys, offs, start, end) already flattened annotation-major.

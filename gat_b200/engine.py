@@ -361,6 +361,264 @@ class IntervalCollection(IntervalContainer):
             outfile.write("\t".join((str(self.name), track, "total", "%i" % ts, "%i" % tl)) + "\n")
 
 
+class DeviceIntervalCollection(IntervalCollection):
+    """An IntervalCollection whose lists live on the GPU (device.Lists, CSR: list = track x key) -- the large
+    annotation collection between BED parsing and the index build.  normalize / intersect / filter /
+    toIsochores / fromIsochores / clone / sum / counts run as a few device passes over ALL lists at once instead of
+    one numpy call per (track, contig) list (24 000 of them at 1000 tracks), and gat_b200.run builds the annotation
+    index from the device lists without the intervals returning to the host.
+
+    Reading through the dictionary interface (`coll[track][contig]`, items(), save ...) hands out a host SNAPSHOT of
+    the lists; structural changes that this class does not implement on the device (add, merge, collapse, restrict,
+    deleting tracks) turn it into an ordinary host collection (same results, host speed).  Same semantics as the
+    reference's container: gat/Engine.pyx:2887-3165, gat/IO.py:188-293."""
+
+    def __init__(self, name=None):
+        IntervalContainer.__init__(self)
+        self.name = name
+        self._tracks = []           # track names, in order of first appearance
+        self._keys = []             # keys (contig or contig.isochore), shared by all tracks
+        self._exists = None         # bool [tracks][keys]: the key is in the track's dictionary
+        self._lists = None          # device.Lists, list t * len(keys) + k
+        self._rows = None           # loaded but not yet normalized: (list_id, start, end, grouper)
+        self._fanout = 0            # > 0 after toIsochores: keys = contigs x isochore tracks, contig-major
+        self._snapshot = None       # host view of the device lists
+        self._plain = None          # the host dictionary once the collection has been demoted
+
+    # ---- state -----------------------------------------------------------------------------------------------
+    @property
+    def onDevice(self):
+        return self._plain is None and (self._lists is not None or self._rows is not None)
+
+    @property
+    def intervals(self):
+        if self._plain is not None:
+            return self._plain
+        if self._snapshot is None:
+            self._snapshot = self._materialize()
+        return self._snapshot
+
+    @intervals.setter
+    def intervals(self, value):         # (IntervalCollection.load and friends assign the dictionary)
+        self._plain = value
+        self._drop_device()
+
+    def _drop_device(self):
+        if self._lists is not None:
+            self._lists.close()
+        self._lists = self._rows = self._snapshot = None
+
+    def _demote(self):
+        """become an ordinary host collection (for operations without a device implementation)"""
+        if self._plain is None:
+            snapshot = self.intervals
+            self._plain = snapshot
+            self._drop_device()
+
+    def _materialize(self):
+        out = collections.defaultdict(IntervalDictionary)
+        if self._rows is not None:      # not normalized yet: group the raw rows like the host reader does
+            for track, contigs in self._rows[3]().items():
+                d = IntervalDictionary()
+                for contig, parts in contigs.items():
+                    data = parts[0] if len(parts) == 1 else np.concatenate(parts)
+                    d[contig] = SegmentList(array=data.astype(np.int64).astype(np.uint32))
+                out[track] = d
+            return out
+        offs, data = self._lists.download()
+        K = len(self._keys)
+        for t, track in enumerate(self._tracks):
+            d = IntervalDictionary()
+            for k in np.flatnonzero(self._exists[t]):
+                l = t * K + int(k)
+                s = SegmentList(array=data[int(offs[l]):int(offs[l + 1])])
+                s._normalized = True
+                d[self._keys[int(k)]] = s
+            out[track] = d
+        return out
+
+    def _changed(self, lists):
+        if self._lists is not None and lists is not self._lists:
+            self._lists.close()
+        self._lists = lists
+        self._snapshot = None
+
+    # ---- loading ---------------------------------------------------------------------------------------------
+    def load(self, filenames, allow_multiple=False, ignore_tracks=False):
+        from .io import readFromBed
+        flat = readFromBed(filenames, allow_multiple=allow_multiple, ignore_tracks=ignore_tracks, flat=True)
+        if "grouper" not in flat:           # a file needed the line-by-line reader: host collection
+            self.intervals = flat
+            return
+        self._plain = None
+        self._tracks, self._keys = list(flat["tracks"]), list(flat["contigs"])
+        T, K = len(self._tracks), len(self._keys)
+        list_id = flat["track"].astype(np.int64) * K + flat["contig"]
+        present = np.zeros(T * K, dtype=bool)
+        present[list_id] = True
+        self._exists = present.reshape(T, K)
+        self._rows = (list_id.astype(np.uint32), flat["start"].astype(np.uint32), flat["end"].astype(np.uint32),
+                      flat["grouper"])
+        self._lists, self._snapshot, self._fanout = None, None, 0
+
+    def _other_lists(self, dictionaries):
+        """device lists of `dictionaries[f][key]` for every key of this collection and every f, key-major; None if
+        one of them is not normalized (the device kernels assume sorted, disjoint lists)"""
+        empty = np.zeros((0, 2), dtype=np.uint32)
+        lists = []
+        for key in self._keys:
+            for d in dictionaries:
+                if key in d:
+                    s = d[key]
+                    if not s.isNormalized:
+                        return None
+                    lists.append(s.asarray())
+                else:
+                    lists.append(empty)
+        return _dev.Lists.from_lists(getContext(), lists)
+
+    # ---- operations with a device implementation -----------------------------------------------------------------
+    def normalize(self):
+        if not self.onDevice:
+            return IntervalCollection.normalize(self)
+        if self._rows is not None:
+            list_id, start, end, _ = self._rows
+            lists = _dev.Lists.from_rows(getContext(), list_id, start, end, len(self._tracks) * len(self._keys))
+            self._rows = None
+            self._changed(lists)
+        # (device lists are normalized by construction)
+
+    def _restrict(self, other, truncate):
+        others = self._other_lists([other])
+        if others is None or self._rows is not None:
+            self._demote()
+            return False
+        self._changed(self._lists.restrict(len(self._keys), 1, others, truncate))
+        others.close()
+        keep = np.array([key in other for key in self._keys], dtype=bool)      # contigs absent from other vanish
+        self._exists = self._exists & keep[None, :]
+        return True
+
+    def intersect(self, other):
+        if not self.onDevice or not self._restrict(other, True):
+            IntervalCollection.intersect(self, other)
+
+    def filter(self, other):
+        if not self.onDevice or not self._restrict(other, False):
+            IntervalCollection.filter(self, other)
+
+    def toIsochores(self, isochores, truncate=False):
+        if self.onDevice and self._rows is None and self._fanout == 0:
+            names = list(isochores.keys())
+            others = self._other_lists([isochores[n] for n in names]) if names else None
+            if others is not None:
+                F = len(names)
+                self._changed(self._lists.restrict(len(self._keys), F, others, truncate))
+                others.close()
+                self._keys = ["%s.%s" % (contig, n) for contig in self._keys for n in names]
+                self._exists = np.repeat(self._exists, F, axis=1)
+                self._fanout = F
+                return
+        if self.onDevice:
+            self._demote()
+        IntervalCollection.toIsochores(self, isochores, truncate)
+
+    def fromIsochores(self):
+        if self.onDevice and self._rows is None:
+            if self._fanout == 0 and not any("." in k.strip() and k.strip() != "." for k in self._keys):
+                return                      # no key is split: nothing to do (gat/Engine.pyx:2862-2873)
+            if self._fanout > 0:
+                F = self._fanout
+                self._changed(self._lists.collapse(F))
+                self._keys = [k.strip().split(".")[0] for k in self._keys[::F]]
+                T = len(self._tracks)
+                self._exists = self._exists.reshape(T, -1, F).any(axis=2)
+                self._fanout = 0
+                return
+        if self.onDevice:
+            self._demote()
+        IntervalCollection.fromIsochores(self)
+
+    def clone(self):
+        if not self.onDevice or self._rows is not None:
+            return IntervalCollection.clone(self)
+        new = DeviceIntervalCollection(self.name)
+        new._tracks, new._keys = list(self._tracks), list(self._keys)
+        new._exists, new._fanout = self._exists.copy(), self._fanout
+        new._lists = self._lists.select(np.arange(self._lists.n_lists, dtype=np.uint32))
+        return new
+
+    def sum(self):
+        if not self.onDevice or self._rows is not None:
+            return IntervalCollection.sum(self)
+        return int(self._lists.sizes()[1].sum())
+
+    def counts(self):
+        if not self.onDevice or self._rows is not None:
+            return IntervalCollection.counts(self)
+        return int(self._lists.n_intervals)
+
+    def trackSizes(self):
+        """{track: (number of segments, bases)} -- what run() asks every annotation track for"""
+        if not self.onDevice or self._rows is not None:
+            return dict((t, (self.intervals[t].counts(), self.intervals[t].sum())) for t in self.tracks)
+        count, bases = self._lists.sizes()
+        K = len(self._keys)
+        return dict((t, (int(count[i * K:(i + 1) * K].sum()), int(bases[i * K:(i + 1) * K].sum())))
+                    for i, t in enumerate(self._tracks))
+
+    def deviceLists(self, keys):
+        """device lists [track][key] for the given keys (an unknown key gives empty lists): the caller closes them"""
+        index = dict((k, i) for i, k in enumerate(self._keys))
+        K, n = len(self._keys), self._lists.n_lists
+        col = np.array([index.get(k, -1) for k in keys], dtype=np.int64)
+        src = np.arange(len(self._tracks), dtype=np.int64)[:, None] * K + col[None, :]
+        src[:, col < 0] = n
+        return self._lists.select(src.reshape(-1).astype(np.uint32))
+
+    # ---- reading ---------------------------------------------------------------------------------------------
+    @property
+    def tracks(self):
+        return list(self._tracks) if self.onDevice else self.intervals.keys()
+
+    def keys(self):
+        return self.tracks
+
+    def __len__(self):
+        return len(self._tracks) if self.onDevice else len(self.intervals)
+
+    def __contains__(self, key):
+        return key in self._tracks if self.onDevice else key in self.intervals
+
+    # ---- structural changes: host only ---------------------------------------------------------------------------
+    def __delitem__(self, key):
+        self._demote()
+        IntervalCollection.__delitem__(self, key)
+
+    def add(self, track, contig, segmentlist):
+        self._demote()
+        IntervalCollection.add(self, track, contig, segmentlist)
+
+    def merge(self, delete=False):
+        self._demote()
+        IntervalCollection.merge(self, delete)
+
+    def collapse(self):
+        self._demote()
+        IntervalCollection.collapse(self)
+
+    def restrict(self, restrict):
+        self._demote()
+        IntervalCollection.restrict(self, restrict)
+
+    def sort(self):
+        if not self.onDevice:
+            IntervalCollection.sort(self)
+        elif self._rows is not None:
+            self._demote()
+            IntervalCollection.sort(self)
+
+
 # ------------------------------------------------------------------------------------------ sampler
 class Sampler(object):
     pass
@@ -559,10 +817,16 @@ def deviceAnnotations(annotations, keys, nseg=None, cache=None, lazy=False):
     k = tuple(keys)
     if cache is not None and k in cache:
         return cache[k], False
-    empty = np.zeros((0, 2), dtype=np.uint32)
-    lists = [[annotations[a][key].asarray() if key in annotations[a] else empty for key in keys]
-             for a in annotations.tracks]
-    obj = _dev.Annotations(getContext(), lists, key_ws_nseg=nseg, lazy=lazy)
+    if isinstance(annotations, DeviceIntervalCollection) and annotations.onDevice and annotations._rows is None:
+        # the lists are on the GPU already: pick the keys, build the index in place
+        picked = annotations.deviceLists(keys)
+        obj = _dev.Annotations.from_device_lists(getContext(), picked, len(annotations._tracks), len(keys), nseg)
+        picked.close()
+    else:
+        empty = np.zeros((0, 2), dtype=np.uint32)
+        lists = [[annotations[a][key].asarray() if key in annotations[a] else empty for key in keys]
+                 for a in annotations.tracks]
+        obj = _dev.Annotations(getContext(), lists, key_ws_nseg=nseg, lazy=lazy)
     if cache is not None:
         cache[k] = obj
     return obj, cache is None

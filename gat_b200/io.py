@@ -76,10 +76,13 @@ def _readBedColumns(filename):
 
 def _firstAppearance(codes, n):
     """relabel codes 0..n-1 in order of first appearance -> (new codes, old label of each new code)"""
-    first = np.full(n, len(codes), dtype=np.int64)
-    np.minimum.at(first, codes, np.arange(len(codes)))
+    N = len(codes)
+    first = np.full(n, N, dtype=np.int64)
+    # assigning the row numbers in REVERSE order leaves every code with its smallest row (the last write wins);
+    # np.minimum.at does the same 20x slower
+    first[codes[::-1]] = np.arange(N - 1, -1, -1, dtype=np.int64)
     order = np.argsort(first, kind="stable")
-    order = order[first[order] < len(codes)]
+    order = order[first[order] < N]
     remap = np.zeros(n, dtype=np.int64)
     remap[order] = np.arange(len(order))
     return remap[codes], order
@@ -112,12 +115,62 @@ def _groupRows(result_rows, origin, filename, default_name, cols, allow_multiple
         result_rows[tnames[key[a] // len(cnames)]][cnames[key[a] % len(cnames)]].append(pairs[a:b])
 
 
-def readFromBed(filenames, allow_multiple=False, ignore_tracks=False):
+def _readFlat(filenames, allow_multiple, ignore_tracks):
+    """all files through the column reader -> one table of rows (track index, contig index, start, end) with tracks
+    and contigs numbered in order of first appearance; None when a file needs the line-by-line reader or holds a
+    coordinate the device path does not take (negative, >= 2^31)"""
+    tracks, contigs, origin, per_file = {}, {}, {}, []
+    parts = []
+    for filename in filenames:
+        cols = _readBedColumns(filename)
+        if cols is None:
+            return None
+        (ccodes, cnames), start, end, name = cols
+        if len(start) and (int(start.min()) < 0 or int(end.min()) < 0 or int(start.max()) >= 2 ** 31 or int(end.max()) >= 2 ** 31
+                           or bool((start > end).any())):
+            return None
+        default_name = os.path.basename(filename)
+        n = len(ccodes)
+        if ignore_tracks or name is None:
+            tcodes, tnames = np.zeros(n, dtype=np.int64), ["merged" if ignore_tracks else default_name]
+        else:
+            tcodes, order = _firstAppearance(name[0], len(name[1]))
+            tnames = [name[1][i] if name[1][i] else default_name for i in order]
+        for t in tnames:
+            if t in origin and origin[t] != filename and not allow_multiple:
+                raise ValueError("track '%s' in multiple filenames: %s and %s" % (t, origin[t], filename))
+            origin[t] = filename
+        ccodes2, corder = _firstAppearance(ccodes, len(cnames))
+        tmap = np.array([tracks.setdefault(t, len(tracks)) for t in tnames], dtype=np.int64)
+        cmap = np.array([contigs.setdefault(cnames[i], len(contigs)) for i in corder], dtype=np.int64)
+        parts.append((tmap[tcodes] if n else tcodes, cmap[ccodes2] if n else ccodes2, start, end))
+        per_file.append((filename, default_name, cols))
+
+    def grouper():          # the host reader's grouping of the same rows (only if the collection falls back to the host)
+        rows = collections.defaultdict(lambda: collections.defaultdict(list))
+        seen = {}
+        for filename, default_name, cols in per_file:
+            _groupRows(rows, seen, filename, default_name, cols, True, ignore_tracks)
+        return rows
+
+    cat = (lambda i: np.concatenate([p[i] for p in parts]) if len(parts) > 1 else parts[0][i]) if parts else None
+    if not parts:
+        return None
+    return dict(tracks=list(tracks), contigs=list(contigs), track=cat(0), contig=cat(1), start=cat(2), end=cat(3),
+                grouper=grouper)
+
+
+def readFromBed(filenames, allow_multiple=False, ignore_tracks=False, flat=False):
     """BED files -> {track: IntervalDictionary}.  The track of an interval is the enclosing `track
     name=` line, else column 4, else the file's basename; `ignore_tracks` pools everything into
-    'merged' (gat/Engine.pyx:2470-2556)."""
+    'merged' (gat/Engine.pyx:2470-2556).  flat: -> a table of rows for Engine.DeviceIntervalCollection (see
+    _readFlat) when every file can be read by columns, else the dictionary as usual."""
     if isinstance(filenames, str):
         filenames = [filenames]
+    if flat:
+        table = _readFlat(filenames, allow_multiple, ignore_tracks)
+        if table is not None:
+            return table
     rows = collections.defaultdict(lambda: collections.defaultdict(list))
     origin = {}
     for filename in filenames:
@@ -170,8 +223,9 @@ def readFromBed(filenames, allow_multiple=False, ignore_tracks=False):
     return result
 
 
-def readSegmentList(label, filenames, enable_split_tracks=False, ignore_tracks=False):
-    results = Engine.IntervalCollection(name=label)
+def readSegmentList(label, filenames, enable_split_tracks=False, ignore_tracks=False, on_device=False):
+    """on_device: keep the lists on the GPU (Engine.DeviceIntervalCollection) -- for the large annotation collection"""
+    results = Engine.DeviceIntervalCollection(name=label) if on_device else Engine.IntervalCollection(name=label)
     results.load(filenames, allow_multiple=enable_split_tracks, ignore_tracks=ignore_tracks)
     return results
 
@@ -204,9 +258,12 @@ def buildSegments(options):
         raise ValueError("too many (%i) segment files - use track definitions or --ignore-segment-tracks"
                          % len(segments))
 
+    # the annotations are the large input (1000 tracks x 20 000 intervals): their preparation -- normalize, the
+    # intersection with the workspace, the isochore split -- runs on the GPU (GATB_HOST_PREP=1: on the host)
     annotations = readSegmentList("annotations", options.annotation_files,
                                   enable_split_tracks=options.enable_split_tracks,
-                                  ignore_tracks=options.annotations_label is not None)
+                                  ignore_tracks=options.annotations_label is not None,
+                                  on_device=not os.environ.get("GATB_HOST_PREP"))
     if options.annotations_label is not None:
         annotations.setName(options.annotations_label)
     if getattr(options, "annotations_to_points", None):

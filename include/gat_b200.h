@@ -104,6 +104,44 @@ int  gatb_annotations_create_async(gatb_ctx *ctx, int n_annot, int n_keys, const
 int  gatb_annotations_wait(gatb_annotations *a);
 void gatb_annotations_destroy(gatb_annotations *a);
 
+/* ---- input preparation on the device ---------------------------------------------------------------
+ * Interval lists resident on the GPU as CSR (gatb_lists): what IO.buildSegments / IO.applyIsochores do to a large
+ * collection with per-list host loops (gat/IO.py:88-293) runs as a few sorts and scans over ALL lists at once, and
+ * the annotation set is built from the result without the intervals ever returning to the host.
+ *   gatb_lists_from_rows     rows (list_id, start, end) in any order -> sorted lists with overlapping rows merged:
+ *                            join_adjacent 0 = IntervalCollection.normalize() / SegmentList.normalize
+ *                            (gat/Engine.pyx:2941-2956, gat/SegmentList.pyx:697-754: adjacent segments stay apart),
+ *                            1 = merge(0) (:756-816: adjacent segments join).  Empty rows (start == end) vanish.
+ *   gatb_lists_from_csr      lists that are already normalized on the host (the workspace, the isochore tracks)
+ *   gatb_lists_restrict      list l of `in` (n_tracks x n_keys lists, key = l % n_keys) against the `fanout` lists
+ *                            other[key * fanout + f]: truncate != 0 -> SegmentList.intersect (gat/SegmentList.pyx:
+ *                            1469-1549), else SegmentList.filter (:1401-1467); the result has in.n_lists * fanout
+ *                            lists, list l * fanout + f.  fanout 1 with the workspace = annotations.intersect(workspace)
+ *                            (gat/IO.py:232-236); fanout = number of isochore tracks = toIsochores (gat/Engine.pyx:
+ *                            2837-2855, gat/IO.py:201-210).
+ *   gatb_lists_collapse      every `fanout` consecutive lists extended into one, then merge(0):
+ *                            IntervalDictionary.fromIsochores (gat/Engine.pyx:2857-2876)
+ *   gatb_lists_select        new lists out[l] = in[src[l]] (src[l] >= in.n_lists: an empty list): the key order of
+ *                            another dictionary
+ *   gatb_lists_sizes         len() and sum() of every list (host arrays, n_lists each; either may be NULL)
+ *   gatb_lists_download      the CSR arrays to the host (offs[n_lists + 1], start / end[n_intervals]; any may be NULL)
+ *   gatb_annotations_create_from_lists   gatb_annotations_create reading n_annot x n_keys device lists in place */
+typedef struct gatb_lists gatb_lists;
+int  gatb_lists_from_rows(gatb_ctx *ctx, uint64_t n_rows, const uint32_t *list_id, const uint32_t *start,
+                          const uint32_t *end, uint32_t n_lists, int join_adjacent, gatb_lists **out);
+int  gatb_lists_from_csr(gatb_ctx *ctx, uint32_t n_lists, const uint64_t *offs, const uint32_t *start,
+                         const uint32_t *end, gatb_lists **out);
+int  gatb_lists_restrict(const gatb_lists *in, uint32_t n_keys, uint32_t fanout, const gatb_lists *other,
+                         int truncate, gatb_lists **out);
+int  gatb_lists_collapse(const gatb_lists *in, uint32_t fanout, gatb_lists **out);
+int  gatb_lists_select(const gatb_lists *in, uint32_t n_out, const uint32_t *src, gatb_lists **out);
+int  gatb_lists_info(const gatb_lists *lists, uint32_t *n_lists, uint64_t *n_intervals);
+int  gatb_lists_sizes(const gatb_lists *lists, uint64_t *count, uint64_t *bases);
+int  gatb_lists_download(const gatb_lists *lists, uint64_t *offs, uint32_t *start, uint32_t *end);
+void gatb_lists_destroy(gatb_lists *lists);
+int  gatb_annotations_create_from_lists(gatb_ctx *ctx, const gatb_lists *lists, int n_annot, int n_keys,
+                                        const uint32_t *key_ws_nseg, gatb_annotations **out);
+
 /* ---- counting of given (placed or observed) segment sets ----------------------------------------
  * Replaces, for n_samples segment sets at once, the loop
  *     counts[counter][annotation] = sum(counter(sample[key], annotations[annotation][key],

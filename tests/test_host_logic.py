@@ -255,12 +255,15 @@ def test_input_preparation_matches_reference_io():
             assert np.array_equal(coll[track][key].asarray(), G.undelta(z["%s/%s/%s" % (name, track, key)])), (track, key)
 
 
-def test_isochore_preparation_matches_reference_io(tmp_path):
+def test_isochore_preparation_matches_reference_io(tmp_path, monkeypatch):
     """buildSegments + applyIsochores WITH an isochore file (toIsochores of workspace, annotations and segments,
     gat/IO.py:188-293) give the lists the reference's own IO gave for the same BED files -- default (segments
-    filtered per isochore) and --truncate-segments-to-workspace (tests/golden/prep_isochores.json)"""
+    filtered per isochore) and --truncate-segments-to-workspace (tests/golden/prep_isochores.json).  Host
+    preparation (GATB_HOST_PREP=1) here; tests/test_gpu_prep.py runs the device preparation against the same
+    fixture."""
     import gat_b200
     from gat_b200 import io as IO
+    monkeypatch.setenv("GATB_HOST_PREP", "1")
     data = G.load_json("prep_isochores")
     argv = []
     for name, flag in (("segments", "--segments"), ("annotations", "--annotations"), ("workspace", "--workspace"),
