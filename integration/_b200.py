@@ -141,7 +141,10 @@ def sample_track(track_index, segs, annotations, workspace, sampler, counters, n
     so, ss, se = _csr([segs[k] for k in keys])
     wo, ws, we = _csr([workspace[k] for k in keys])
     kind = type(sampler).__name__
-    args = sampler.__reduce__()[1]                 # (bucket_size, nbuckets, ...) / (radius, extension): cdef fields
+    red = sampler.__reduce__()                     # (constructor, (bucket_size, nbuckets, ...) / (radius, extension)):
+    if len(red) == 1:                              # the fields are cdef; SamplerShift.__reduce__ nests its tuple once more
+        red = red[0]
+    args = red[1]
     bucket_size, nbuckets = (1, 0) if kind == "SamplerShift" else (int(args[0]), int(args[1]))
     smp = _vp()
     _check(L.gatb_sampler_create(ctx, len(keys), _p(unit_contig), len(contigs), has_iso, _p(so), _p(ss), _p(se),
