@@ -721,6 +721,7 @@ struct gatb_sampler {
     DevBuf<uint64_t> contig_base;
     DevBuf<unsigned long long> tally;     // [3]: placed segments, round-cap units, overflow units
     DevBuf<uint32_t> unit_over;           // [n_units]: unit overflowed its buffer in the current call
+    DevBuf<uint32_t> ws_tab;              // bucket tables over the workspace pieces of units with many pieces
     bool no_hist = false;                 // created with nbuckets = 0: no length histogram (SamplerShift only)
 };
 
@@ -820,7 +821,7 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
     std::vector<uint32_t> cuminc(ws_offs[U]);
     s->h_units.resize(U);
     std::vector<uint64_t> scratch_off(U);
-    uint64_t scratch_total = 0;
+    uint64_t scratch_total = 0, ws_tab_total = 0;
     for (uint32_t u = 0; u < U; u++) {
         UnitDesc &d = s->h_units[u];
         memset(&d, 0, sizeof(d));
@@ -834,6 +835,12 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
         d.contig = (uint32_t)unit_contig[u];
         scratch_off[u] = scratch_total;
         scratch_total += next_pow2(std::max(d.seg_n, 1u));
+        // bucket tables (common.cuh WS_NB): worth it from a handful of pieces on; the entries are 16-bit
+        d.ws_tab_off = 0xffffffffu;
+        if (d.ws_n >= 8 && d.ws_n < 65535 && d.ws_total >= 65536 && ws_end[ws_offs[u + 1] - 1] - ws_start[ws_offs[u]] >= 65536) {
+            d.ws_tab_off = (uint32_t)ws_tab_total;
+            ws_tab_total += 2 + (WS_NB + 1);        // words: two multipliers + 2 * (WS_NB + 1) 16-bit entries
+        }
     }
     DevBuf<uint32_t> &d_seg_start = s->seg_start, &d_seg_end = s->seg_end;
     DevBuf<uint64_t> d_scratch, d_scratch_off;
@@ -848,10 +855,11 @@ extern "C" int gatb_sampler_create(gatb_ctx *ctx, int n_units, const int32_t *un
     TRY(s->len_tab.alloc(seg_offs[U]));
     TRY(d_scratch.alloc(scratch_total));
     TRY(d_scratch_off.upload(scratch_off.data(), U, st));
+    TRY(s->ws_tab.alloc(std::max<uint64_t>(ws_tab_total, 2)));
     if (e == cudaSuccess) {
         ProfScope ps(ctx, PROF_OTHER);
         launch_prep_units(st, s->units.p, U, d_seg_start.p, d_seg_end.p, s->ws_start.p, s->ws_end.p, s->ws_cuminc.p,
-                          s->len_tab.p, d_scratch.p, d_scratch_off.p, bucket_size, nbuckets);
+                          s->len_tab.p, d_scratch.p, d_scratch_off.p, bucket_size, nbuckets, s->ws_tab.p);
         e = cudaGetLastError();
     }
     TRY(cudaMemcpyAsync(s->h_units.data(), s->units.p, U * sizeof(UnitDesc), cudaMemcpyDeviceToHost, st));
@@ -987,6 +995,7 @@ static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t 
     memset(&p, 0, sizeof(p));
     p.units = s->units.p; p.order = s->order.p;
     p.ws_start = s->ws_start.p; p.ws_end = s->ws_end.p; p.ws_cuminc = s->ws_cuminc.p; p.len_tab = s->len_tab.p;
+    p.ws_tab = s->ws_tab.p;
     if (s->has_iso) {
         p.buf = s->ctx->scratch->unit_buf.p; p.sample_stride = s->unit_stride;
         p.out_n = s->ctx->scratch->unit_n.p; p.out_n_stride = s->n_units; p.out_by_contig = 0;

@@ -165,12 +165,22 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t *buf, uint32_t N)
 
 // ---------------------------------------------------------------------------------------------------
 // Workspace of one unit: sorted disjoint pieces + inclusive cumulative lengths.
+// Units with many pieces (isochore workspaces: ~160 tiles per unit) carry two BUCKET TABLES of WS_NB + 1 entries
+// that narrow the binary searches below to the one or two pieces a bucket holds:
+//   pick table  tab[b]             = first piece i with cuminc[i] > r_b, r_b = the smallest random base of bucket b
+//   end table   tab[WS_NB + 1 + b] = first piece i with end[i] > x_b,    x_b = the smallest coordinate of bucket b
+// bucket(v) = umulhi(v, inv) is monotone, so the answer for any value of bucket b lies in [tab[b], tab[b + 1]].
+constexpr uint32_t WS_NB = 256;
 struct WsView {
     const uint32_t *start;
     const uint32_t *end;
     const uint32_t *cuminc;   // cuminc[i] = sum_{j<=i} len_j   (SegmentListSampler.cdf + 1, gat/Engine.pyx:274-277)
     uint32_t n;
+    const uint32_t *tabw;     // bucket tables, or nullptr: {pick_inv, end_inv, then 2 * (WS_NB + 1) 16-bit entries};
+                              // bucket of a random base r = umulhi(r, pick_inv), of a coordinate x =
+                              // umulhi(x - first workspace start, end_inv)
 };
+__device__ __forceinline__ const uint16_t *ws_tab16(const WsView &w) { return reinterpret_cast<const uint16_t *>(w.tabw + 2); }
 
 // workspace bases in [0, x): prefix-coverage closed form -- replaces the two-pointer
 // SegmentList.intersect + sum (gat/SegmentList.pyx:1469-1549, :1607-1616) used at every checkpoint.
@@ -198,6 +208,12 @@ __device__ __forceinline__ uint32_t ws_overlap(const WsView &w, uint32_t s, uint
     if (w.n == 1) return ws_cov(w, e) - ws_cov(w, s);
     if (e <= s) return 0u;
     uint32_t lo = 0, hi = w.n;
+    if (w.tabw != nullptr) {
+        const uint32_t first = w.start[0];
+        const uint32_t b = s > first ? min(__umulhi(s - first, w.tabw[1]), WS_NB - 1u) : 0u;
+        const uint16_t *t = ws_tab16(w);
+        lo = t[WS_NB + 1u + b]; hi = t[WS_NB + 2u + b];
+    }
     while (lo < hi) {                       // first piece with end > s
         const uint32_t mid = (lo + hi) >> 1;
         if (w.end[mid] > s) hi = mid; else lo = mid + 1;

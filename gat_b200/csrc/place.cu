@@ -5,7 +5,8 @@
 // (seed, track, unit, sample, t), so a warp evaluates 32 consecutive turns speculatively, prefix-sums
 // their overlaps, accepts the turns before the first one whose length satisfies `remaining <= length`
 // (gat/Engine.pyx:582) and then runs that turn's checkpoint (sort + merge(0) + workspace coverage)
-// cooperatively.  The result is bit-identical to the sequential restatement in oracle/gat_oracle.c
+// cooperatively.  (Keeping the 32 drawn turns as a window that is consumed across checkpoints was measured and
+// dropped: late turns are `certain` ones whose draw is already put off, so it saved nothing and cost registers.)  The result is bit-identical to the sequential restatement in oracle/gat_oracle.c
 // driven by the same Philox stream (tests/test_gpu_parity.py).
 #include "place.cuh"
 
@@ -20,6 +21,11 @@ __device__ __forceinline__ uint32_t ws_pick(const WsView &w, uint32_t r)
     // first i with cuminc[i] > r   == searchsorted(cdf, r) with cdf = cuminc - 1 (gat/Engine.pyx:300-305)
     if (w.n == 1) return 0;
     uint32_t lo = 0, hi = w.n;
+    if (w.tabw != nullptr) {                // bucket table: the answer lies in [tab[b], tab[b + 1]]
+        const uint32_t b = __umulhi(r, w.tabw[0]);
+        const uint16_t *t = ws_tab16(w);
+        lo = t[b]; hi = t[b + 1u];
+    }
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
         if (w.cuminc[mid] > r) hi = mid; else lo = mid + 1;
@@ -227,6 +233,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
     WsView ws;
     ws.start = p.ws_start + d.ws_off; ws.end = p.ws_end + d.ws_off; ws.cuminc = p.ws_cuminc + d.ws_off;
     ws.n = d.ws_n;
+    ws.tabw = d.ws_tab_off != 0xffffffffu ? p.ws_tab + d.ws_tab_off : nullptr;
     const uint32_t *tab = p.len_tab + d.tab_off;
     const uint32_t sample = (uint32_t)(p.sample_begin + sl);
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
@@ -241,8 +248,7 @@ __global__ void __launch_bounds__(128, GATB_PLACE_MINBLOCKS) place_kernel(PlaceP
     plan.lo = 0; plan.inv = 0; plan.nb = 0;
     bool prehist = false;
     if (d.tab_n > 0) {
-        const uint32_t lmax = tab[d.tab_n - 1] + d.bucket, w0 = ws.start[0];
-        plan = make_sort_plan(d.tab_n, w0 > lmax ? w0 - lmax : 0u, ws.end[ws.n - 1]);
+        plan.lo = d.plan_lo; plan.inv = d.plan_inv; plan.nb = d.plan_nb;       // (sample-invariant: prep_units_kernel)
         for (uint32_t b = lane; b < plan.nb; b += 32) cnt[b] = 0u;
         __syncwarp();
         prehist = p.sampler_kind == 0;
@@ -469,6 +475,7 @@ __global__ void __launch_bounds__(128) shift_kernel(PlaceParams p)
     WsView ws;
     ws.start = p.ws_start + d.ws_off; ws.end = p.ws_end + d.ws_off; ws.cuminc = p.ws_cuminc + d.ws_off;
     ws.n = d.ws_n;
+    ws.tabw = d.ws_tab_off != 0xffffffffu ? p.ws_tab + d.ws_tab_off : nullptr;
     const uint32_t sample = (uint32_t)(p.sample_begin + sl);
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
     const uint32_t c1 = p.track << 8;       // Philox block 0 of turn x: words 0,1 = position, words 2,3 = direction
@@ -606,7 +613,7 @@ __global__ void __launch_bounds__(128) prep_units_kernel(UnitDesc *units, uint32
                                                          const uint32_t *ws_start, const uint32_t *ws_end,
                                                          const uint32_t *ws_cuminc, uint32_t *len_tab,
                                                          uint64_t *scratch, const uint64_t *scratch_off,
-                                                         uint32_t bucket_size, uint32_t nbuckets)
+                                                         uint32_t bucket_size, uint32_t nbuckets, uint32_t *ws_tab)
 {
     const uint32_t unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (unit >= n_units) return;
@@ -614,6 +621,28 @@ __global__ void __launch_bounds__(128) prep_units_kernel(UnitDesc *units, uint32
     UnitDesc d = units[unit];
     WsView ws;
     ws.start = ws_start + d.ws_off; ws.end = ws_end + d.ws_off; ws.cuminc = ws_cuminc + d.ws_off; ws.n = d.ws_n;
+    ws.tabw = nullptr;
+    // bucket tables over the unit's workspace pieces (common.cuh), for units with enough pieces to search
+    if (d.ws_tab_off != 0xffffffffu) {
+        const uint32_t first = ws.start[0], span = ws.end[ws.n - 1u] - first;
+        const uint32_t pick_inv = (uint32_t)min(((unsigned long long)WS_NB << 32) / d.ws_total, 0xffffffffull);
+        const uint32_t end_inv = (uint32_t)min(((unsigned long long)WS_NB << 32) / span, 0xffffffffull);
+        uint32_t *tw = ws_tab + d.ws_tab_off;
+        uint16_t *t = reinterpret_cast<uint16_t *>(tw + 2);
+        if (lane == 0) { tw[0] = pick_inv; tw[1] = end_inv; }
+        for (uint32_t b = lane; b <= WS_NB; b += 32) {
+            // smallest value of bucket b (or something below it): floor(b * 2^32 / inv)
+            const unsigned long long r = min(((unsigned long long)b << 32) / pick_inv, (unsigned long long)d.ws_total - 1ull);
+            uint32_t lo = 0, hi = ws.n;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ws.cuminc[mid] > (uint32_t)r) hi = mid; else lo = mid + 1; }
+            t[b] = (uint16_t)(b == WS_NB ? ws.n - 1u : lo);
+            const unsigned long long x = (unsigned long long)first + (((unsigned long long)b << 32) / end_inv);
+            lo = 0; hi = ws.n;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((unsigned long long)ws.end[mid] > x) hi = mid; else lo = mid + 1; }
+            t[WS_NB + 1u + b] = (uint16_t)(b == WS_NB ? ws.n : lo);
+        }
+        __syncwarp();
+    }
     const uint32_t *ss = seg_start + d.seg_off, *se = seg_end + d.seg_off;
     uint64_t *keys = scratch + scratch_off[unit];
 
@@ -679,6 +708,14 @@ __global__ void __launch_bounds__(128) prep_units_kernel(UnitDesc *units, uint32
         }
         d.cap = next_pow2(max(max(2u * nw + 64u, d.seg_n), (uint32_t)est));   // SamplerSegments places seg_n segments
         d.error = err;
+        // the counting sort's bucket plan: every placement starts in [first workspace start - longest length, last
+        // workspace end), and about as many placements as working segments are expected
+        d.plan_lo = d.plan_inv = d.plan_nb = 0;
+        if (nw > 0) {
+            const uint32_t lmax = (uint32_t)keys[nw - 1u] + d.bucket, w0 = ws.start[0];   // (the sorted table's last entry)
+            const SortPlan pl = make_sort_plan(nw, w0 > lmax ? w0 - lmax : 0u, ws.end[ws.n - 1u]);
+            d.plan_lo = pl.lo; d.plan_inv = pl.inv; d.plan_nb = pl.nb;
+        }
         units[unit] = d;
     }
 }
@@ -687,14 +724,14 @@ void launch_prep_units(cudaStream_t st, UnitDesc *units, uint32_t n_units,
                        const uint32_t *seg_start, const uint32_t *seg_end,
                        const uint32_t *ws_start, const uint32_t *ws_end, const uint32_t *ws_cuminc,
                        uint32_t *len_tab, uint64_t *scratch, const uint64_t *scratch_off,
-                       uint32_t bucket_size, uint32_t nbuckets)
+                       uint32_t bucket_size, uint32_t nbuckets, uint32_t *ws_tab)
 {
     if (n_units == 0) return;
     const int warps_per_block = 4;
     unsigned blocks = (n_units + warps_per_block - 1) / warps_per_block;
     prep_units_kernel<<<blocks, warps_per_block * 32, 0, st>>>(units, n_units, seg_start, seg_end, ws_start,
                                                                 ws_end, ws_cuminc, len_tab, scratch, scratch_off,
-                                                                bucket_size, nbuckets);
+                                                                bucket_size, nbuckets, ws_tab);
 }
 
 }  // namespace gatb

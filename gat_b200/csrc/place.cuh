@@ -27,6 +27,8 @@ struct UnitDesc {
     uint32_t contig;      // contig index
     uint32_t error;       // GATB_ERR_TOO_LARGE etc. from preparation
     uint64_t buf_off;     // offset of the working buffer inside one sample's region
+    uint32_t ws_tab_off;  // the unit's bucket tables in PlaceParams.ws_tab (32-bit words; common.cuh), 0xffffffff: none
+    uint32_t plan_lo, plan_inv, plan_nb;   // counting-sort plan of the unit's first checkpoint (common.cuh SortPlan)
 };
 
 struct PlaceParams {
@@ -34,6 +36,7 @@ struct PlaceParams {
     const uint32_t *order;       // unit ids, heaviest first
     const uint32_t *ws_start, *ws_end, *ws_cuminc;
     const uint32_t *len_tab;
+    const uint32_t *ws_tab;      // bucket tables of the units that have them (WsView::tabw)
     uint64_t *buf;               // [n_samples][sample_stride] packed segments
     uint64_t sample_stride;
     uint32_t *out_n;             // [n_samples][out_n_stride]: per unit (isochores) or per contig
@@ -72,7 +75,7 @@ void launch_prep_units(cudaStream_t st, UnitDesc *units, uint32_t n_units,
                        const uint32_t *seg_start, const uint32_t *seg_end,
                        const uint32_t *ws_start, const uint32_t *ws_end, const uint32_t *ws_cuminc,
                        uint32_t *len_tab, uint64_t *scratch, const uint64_t *scratch_off,
-                       uint32_t bucket_size, uint32_t nbuckets);
+                       uint32_t bucket_size, uint32_t nbuckets, uint32_t *ws_tab);
 void launch_place(cudaStream_t st, const PlaceParams &p);
 void launch_contig_merge(cudaStream_t st, const MergeParams &p);
 
