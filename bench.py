@@ -78,6 +78,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-checks", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the per-step count slabs reach every rank -- peer: the counting kernel stores its "
+                         "rows into every rank's matrix over NVLink (output routes); nccl: all_gather_into_tensor")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     for k in ("segments", "annotations", "counter", "isochores"):
@@ -117,8 +120,10 @@ def config_of(args, wl, world):
             "samples_per_step_per_gpu": args.samples_per_step,
             "batch": args.batch, "batches_per_step": args.batches_per_step,
             "global_samples_per_step": args.samples_per_step * world,
-            "parallelism": "samples sharded over %i GPU(s), inputs replicated, one NCCL all-gather of the "
-                           "count slab per step" % world if world > 1 else "1 GPU",
+            "parallelism": ("samples sharded over %i GPU(s), inputs replicated; exchange per step: %s" % (world, (
+                "the counting kernel's epilogue stores every finished row into every rank's [N x samples][tracks] matrix "
+                "(CUDA IPC peer memory over NVLink, gatb_set_output_routes) -- no collective" if args.gather == "peer" else
+                "one NCCL all_gather_into_tensor of the count slab, overlapping the next step's kernels"))) if world > 1 else "1 GPU",
             "l2": "inputs larger than L2: annotation grid index ~%.0f MB + %.0f MB of placed segments per batch; "
                   "sample indices advance every step"
                   % (wl["n_a_total"] * 2.33 * 8 / 1e6 + 12, args.batch * wl["n_segments"] * 8 / 1e6),
@@ -366,7 +371,7 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
-        dist.init_process_group(backend="nccl")
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
 
@@ -388,9 +393,22 @@ def run_ours(args):
     # two output slabs, used alternately: for N > 1 the all-gather of step i (NCCL, asynchronous, its own stream)
     # overlaps the placement and counting of step i + 1, which write the other slab
     nbuf = 2 if world > 1 else 1
-    outs = [torch.zeros((S, A), dtype=odt, device=dev) for _ in range(nbuf)]
-    gathers = [torch.empty((world * S, A), dtype=odt, device=dev) for _ in range(nbuf)] if world > 1 else None
+    peer = world > 1 and args.gather == "peer" and not is_density
+    if world > 1 and not peer:
+        args.gather = "nccl"
     pending = [None] * nbuf
+    if peer:
+        # the gathered matrix of a step lives in memory every rank can write: each rank's counting kernels store
+        # their rows into all of them (two matrices, used alternately like the NCCL slabs)
+        from gat_b200 import parallel
+        peers = [parallel.PeerMatrix(ctx, 1, world * S, A) for _ in range(nbuf)]
+        gathers = [pm.tensor[0] for pm in peers]
+        outs = [g[rank * S:(rank + 1) * S] for g in gathers]
+        routes = [[dict(base=pm.pointer(r), row_stride=A, row0=rank * S, col_begin=0, col_end=A) for r in range(world)]
+                  for pm in peers]
+    else:
+        outs = [torch.zeros((S, A), dtype=odt, device=dev) for _ in range(nbuf)]
+        gathers = [torch.empty((world * S, A), dtype=odt, device=dev) for _ in range(nbuf)] if world > 1 else None
 
     def run_into(t, begin, n):
         if is_density:
@@ -402,6 +420,9 @@ def run_ours(args):
 
     def step(i):
         b = i % nbuf
+        if peer:                                   # the exchange is the kernels' epilogue: nothing to launch after them
+            ctx.set_output_routes(routes[b])
+            return run_into(outs[b], step_begin(i), S)
         if pending[b] is not None:                 # the slab's previous all-gather must have read it
             pending[b].wait()
             pending[b] = None
@@ -419,7 +440,8 @@ def run_ours(args):
     def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
-            dist.barrier()
+            box = [None] * world
+            dist.all_gather_object(box, rank)      # (gloo: a barrier that launches nothing on the GPUs)
         torch.cuda.synchronize(dev)
 
     for i in range(args.warmup):
@@ -444,7 +466,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms], dtype=torch.float64)            # (host tensor: reduced over gloo)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clock_info = clocks.stop(t_begin, t_end) if rank == 0 else None
@@ -472,6 +494,7 @@ def run_ours(args):
                 g = gathers[last % nbuf]
                 tmp = torch.zeros((S, A), dtype=odt, device=dev)
                 bad = []
+                ctx.set_output_routes([])
                 for r in range(world):
                     run_into(tmp, step_begin(last, r), S)
                     torch.cuda.synchronize(dev)
@@ -489,6 +512,7 @@ def run_ours(args):
     drain()
     prof = ctx.profile_read()
     ctx.profile(False)
+    ctx.set_output_routes([])
     roofline, placed_per_sample = (None, float(info[0]) / S)
     if rank == 0:
         roofline, placed_per_sample = roofline_of(args, wl, ctx, smp, annos, prof, local)
@@ -537,10 +561,15 @@ def run_ours(args):
                 else:
                     # N > 1: counts stay on the device for the exchange; every rank then reads ITS rows of the
                     # gathered matrix back to the host
+                    if peer:
+                        ctx.set_output_routes(routes[0])
                     ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), SEED, 0, begin, S,
                                                None if is_density else outs[0].data_ptr(),
                                                outs[0].data_ptr() if is_density else None, 1, device._p(info_np)))
-                    dist.all_gather_into_tensor(gathers[0], outs[0])
+                    if peer:
+                        barrier()           # every rank's rows have arrived in every matrix
+                    else:
+                        dist.all_gather_into_tensor(gathers[0], outs[0])
                     host_out.copy_(gathers[0][rank * S:(rank + 1) * S], non_blocking=True)
                     torch.cuda.current_stream(dev).synchronize()
                 s2.close()
@@ -558,7 +587,7 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            t = torch.tensor([dt], dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * S * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -566,7 +595,7 @@ def run_ours(args):
                "what": "per step of %i samples per GPU: gatb_sampler_create + gatb_annotations_create_async (every input "
                        "from pinned host memory, on every rank) + gatb_run%s + the step's count matrix read back to "
                        "pinned host memory; double-buffered: the upload + index build of step i+1 overlap the "
-                       "kernels of step i" % (S, " + NCCL all-gather of the slab" if world > 1 else
+                       "kernels of step i" % (S, (" + exchange of the slab (%s) + barrier" % args.gather) if world > 1 else
                                               " (host output: the copy of batch i overlaps batch i+1)")}
 
     cpu = None
@@ -589,11 +618,17 @@ def run_ours(args):
                 "segment_placements_per_s": value * placed_per_sample}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
+    ctx.set_output_routes([])
     smp.close()
     annos.close()
+    if world > 1:
+        barrier()
+        if peer:
+            del gathers, outs
+            for pm in peers:
+                pm.close()
     ctx.close()
     if world > 1:
-        dist.barrier()
         dist.destroy_process_group()
     if parity_check not in (None, "ok") or gather_check not in (None, "ok"):
         sys.exit(3)

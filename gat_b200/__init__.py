@@ -61,9 +61,11 @@ def buildContigAnnotations(annotations, workspace, contigs):
 
 
 def sampleTrack(track_index, segs, annotations, workspace, sampler, counters, num_samples,
-                sample_range=None, annos_cache=None, return_device=False):
+                sample_range=None, annos_cache=None, return_device=False, routes=None):
     """all samples of one track: counts[counter_id] = ndarray [num_samples][n_annot]
-    (replaces UnconditionalSampler.sample, gat/__init__.py:704-778)."""
+    (replaces UnconditionalSampler.sample, gat/__init__.py:704-778).
+    routes: output routes (device.Context.set_output_routes) -- the counting kernels deliver the rows straight to
+    their consumers (other ranks' matrices included) instead of a local slab."""
     import torch
     ctx = getContext()
     problem = TrackProblem(segs, workspace)
@@ -113,13 +115,25 @@ def sampleTrack(track_index, segs, annotations, workspace, sampler, counters, nu
     n_local = end - begin
     dev = torch.device("cuda", ctx.device)
     ids = device.counter_ids(counter_names)
-    out_u = torch.zeros((len(ids), max(n_local, 1), len(atracks)), dtype=torch.int32, device=dev)
-    out_f = torch.zeros((max(n_local, 1), len(atracks)), dtype=torch.float64, device=dev) \
-        if device.DENSITY in ids else None
     # (torch's legacy default stream has handle 0 = "the library's own stream" at the C ABI: pass cudaStreamLegacy)
     ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream or 1)
-    info = smp.run(annos, counter_names, Engine.getSeed(), track_index, begin, n_local,
-                   out_counts_ptr=out_u.data_ptr(), out_density_ptr=out_f.data_ptr() if out_f is not None else None)
+    if routes is not None:
+        out_u = out_f = None
+        if n_local > 0:
+            ctx.set_output_routes(routes)
+            try:
+                info = smp.run(annos, counter_names, Engine.getSeed(), track_index, begin, n_local,
+                               out_counts_ptr=routes[0]["base"])
+            finally:
+                ctx.set_output_routes([])
+        else:
+            info = np.zeros(3, dtype=np.uint64)
+    else:
+        out_u = torch.zeros((len(ids), max(n_local, 1), len(atracks)), dtype=torch.int32, device=dev)
+        out_f = torch.zeros((max(n_local, 1), len(atracks)), dtype=torch.float64, device=dev) \
+            if device.DENSITY in ids else None
+        info = smp.run(annos, counter_names, Engine.getSeed(), track_index, begin, n_local,
+                       out_counts_ptr=out_u.data_ptr(), out_density_ptr=out_f.data_ptr() if out_f is not None else None)
     smp.close()
     if annos_cache is None:
         annos.close()
@@ -209,20 +223,51 @@ def _run(segments, annotations, workspace, sampler, counters, workspace_generato
         raise ValueError("output_counts_pattern needs every column on rank 0: use exchange='allgather'")
     col_begin, col_end = parallel.column_range(n_atracks, rank, world) if exchange == "columns" else (0, n_atracks)
 
+    # Transport of a multi-GPU exchange:
+    #   "peer"  the counting kernels store every finished row straight into the destination ranks' matrices (CUDA IPC
+    #           memory over NVLink, output routes of the C ABI): the exchange happens inside the kernels' epilogue,
+    #           no collective follows; integer counters
+    #   "nccl"  the slabs are exchanged with one NCCL collective per counter plane after the kernels
+    transport = kwargs.get("transport", os.environ.get("GATB_TRANSPORT", "peer"))
+    if transport not in ("peer", "nccl"):
+        raise ValueError("transport must be peer or nccl")
+    if world == 1 or any(c.name == "nucleotide-density" for c in counters):
+        transport = "nccl"              # (one rank: nothing to exchange; the float64 density plane is not routed)
+
     sampled = {}
     begin, end = parallel.shard_range(num_samples, rank, world)
     for ntrack, track in enumerate(segments.tracks):
         segs = segments[track]
         if workspace.sum() == 0:
             continue
+        peer = routes = None
+        if transport == "peer":
+            # every rank's destination matrix, writable by all: [counter][S][all columns | its own columns]
+            width = (col_end - col_begin) if exchange == "columns" else n_atracks
+            peer = parallel.PeerMatrix(ctx, len(counters), num_samples, max(width, 1))
+            routes = []
+            for r in range(world):
+                cb, ce = parallel.column_range(n_atracks, r, world) if exchange == "columns" else (0, n_atracks)
+                _, rows_r, cols_r = peer.shape_of(r)
+                if ce > cb:
+                    routes.append(dict(base=peer.pointer(r), plane_stride=rows_r * cols_r, row_stride=cols_r, row0=begin,
+                                       col_begin=cb, col_end=ce))
         atracks, out, info = sampleTrack(ntrack, segs, annotations, workspace, sampler, counters,
-                                         num_samples, sample_range=(begin, end), annos_cache=annos_cache)
+                                         num_samples, sample_range=(begin, end), annos_cache=annos_cache, routes=routes)
         if isinstance(out, list):          # track without any unit
             sampled[track] = (atracks, None, None, None)
+            if peer is not None:
+                parallel.barrier()
+                peer.close()
             continue
         out_u, out_f, ids = out
         mark("sampling")
-        if exchange == "columns":
+        if transport == "peer":
+            parallel.barrier()              # every rank's kernels have delivered their rows
+            out_u = peer.tensor[:, :, :((col_end - col_begin) if exchange == "columns" else n_atracks)].clone()
+            parallel.barrier()              # (nobody frees memory a peer still has mapped for writing)
+            peer.close()
+        elif exchange == "columns":
             # one collective per counter plane: all-to-all by column
             planes = [parallel.exchange_columns(out_u[i][:end - begin], num_samples) for i in range(out_u.shape[0])]
             out_u = torch.stack(planes) if planes else out_u

@@ -27,7 +27,14 @@ SYMBOLS = [
     "gatb_lists_from_rows", "gatb_lists_from_csr", "gatb_lists_restrict", "gatb_lists_collapse", "gatb_lists_select",
     "gatb_lists_info", "gatb_lists_sizes", "gatb_lists_download", "gatb_lists_destroy",
     "gatb_annotations_create_from_lists",
+    "gatb_set_output_routes", "gatb_peer_alloc", "gatb_peer_free", "gatb_peer_open", "gatb_peer_close",
 ]
+
+
+class Route(ctypes.Structure):
+    """gatb_route (include/gat_b200.h)"""
+    _fields_ = [("base", ctypes.c_void_p), ("plane_stride", ctypes.c_uint64), ("row_stride", ctypes.c_uint64),
+                ("row0", ctypes.c_uint64), ("col_begin", ctypes.c_uint32), ("col_end", ctypes.c_uint32)]
 
 
 class GatB200Error(RuntimeError):
@@ -132,5 +139,15 @@ def load():
     L.gatb_lists_destroy.argtypes = [vp]
     L.gatb_annotations_create_from_lists.restype = i32
     L.gatb_annotations_create_from_lists.argtypes = [vp, vp, i32, i32, vp, ctypes.POINTER(vp)]
+    L.gatb_set_output_routes.restype = i32
+    L.gatb_set_output_routes.argtypes = [vp, i32, vp]
+    L.gatb_peer_alloc.restype = i32
+    L.gatb_peer_alloc.argtypes = [vp, u64, ctypes.POINTER(vp), vp]
+    L.gatb_peer_free.restype = i32
+    L.gatb_peer_free.argtypes = [vp, vp]
+    L.gatb_peer_open.restype = i32
+    L.gatb_peer_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
+    L.gatb_peer_close.restype = i32
+    L.gatb_peer_close.argtypes = [vp, vp]
     _lib = L
     return L

@@ -194,7 +194,9 @@ def main(argv=None):
     parser.add_option("-S", "--stdout", dest="stdout_file", type="string", default=None, help="output file")
     options, _ = parser.parse_args(argv[1:])
     parallel.init_from_env()
-    parallel.warm_up_async()            # NCCL's set-up runs behind the parsing of the input files
+    import os
+    if os.environ.get("GATB_TRANSPORT", "peer") == "nccl":
+        parallel.warm_up_async()        # NCCL's set-up runs behind the parsing of the input files
     rank, _ = parallel.rank_world()
 
     def log(msg):

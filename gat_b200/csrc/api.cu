@@ -40,6 +40,9 @@ struct gatb_ctx {
     uint32_t schunk_max = 0;            // samples per count CTA; 0: whatever shared memory allows
     uint32_t kgrp_max = 0;              // keys per item table; 0: whatever fits
     struct BatchScratch *scratch = nullptr;
+    // output routes of gatb_run (gatb_set_output_routes): integer counts delivered to several destinations,
+    // possibly peer GPUs, by the counting kernel's epilogue
+    std::vector<gatb_route> routes;
     bool trace = false;                 // GATB_TRACE=1: host-side phase times of gatb_run on stderr
     // optional per-kernel timing (bench.py roofline): CUDA events around every launch
     bool profiling = false;
@@ -1206,6 +1209,17 @@ static int run_once(gatb_sampler *s, const gatb_annotations *annos, int n_counte
             uint32_t *dst_u = out_counts ? out_counts + ((uint64_t)c * n_samples + done) * A : nullptr;
             double *dst_f = out_density ? out_density + done * A : nullptr;
             const int slab = (int)(n_staged % (uint64_t)n_stage);
+            p.n_routes = 0;
+            if (!dens && !ctx->routes.empty()) {
+                p.n_routes = (uint32_t)ctx->routes.size();
+                for (uint32_t r = 0; r < p.n_routes; r++) {
+                    const gatb_route &g = ctx->routes[r];
+                    p.routes[r].base = g.base + (uint64_t)c * g.plane_stride;
+                    p.routes[r].row_stride = g.row_stride;
+                    p.routes[r].row0 = g.row0 + done;
+                    p.routes[r].col_begin = g.col_begin; p.routes[r].col_end = std::min(g.col_end, A);
+                }
+            }
             p.out_u32 = out_is_device ? dst_u : sc->out_tmp[slab].p;
             p.out_f64 = out_is_device ? dst_f : sc->out_tmp_f[slab].p;
             // annotations still uploading / building (gatb_annotations_create_async): the placement queued
@@ -1263,7 +1277,9 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
         if (counters[c] == GATB_NUCLEOTIDE_DENSITY) any_density = true; else any_int = true;
     }
     if (any_density && (!annos->has_nseg || !out_density)) return fail(ctx, GATB_ERR_INVALID, "nucleotide-density needs key_ws_nseg and out_density");
-    if (any_int && !out_counts) return fail(ctx, GATB_ERR_INVALID, "run: out_counts is NULL");
+    if (!ctx->routes.empty() && (!out_is_device || any_density))
+        return fail(ctx, GATB_ERR_INVALID, "run: output routes deliver integer counters to device memory only");
+    if (any_int && !out_counts && ctx->routes.empty()) return fail(ctx, GATB_ERR_INVALID, "run: out_counts is NULL");
     if (n_samples == 0) return GATB_OK;
     if (!annos->pending && annos->status) return fail(ctx, annos->status, "run: the annotations failed validation");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1866,4 +1882,63 @@ extern "C" int gatb_annotations_create_from_lists(gatb_ctx *ctx, const gatb_list
         *out = nullptr;
     }
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU exchange without a collective: output routes and peer memory (include/gat_b200.h)
+extern "C" int gatb_set_output_routes(gatb_ctx *ctx, int n_routes, const gatb_route *routes)
+{
+    if (!ctx || n_routes < 0 || (n_routes && !routes)) return GATB_ERR_INVALID;
+    if ((uint32_t)n_routes > GATB_MAX_ROUTES) return fail(ctx, GATB_ERR_INVALID, "at most 16 output routes");
+    for (int r = 0; r < n_routes; r++)
+        if (!routes[r].base || routes[r].col_begin > routes[r].col_end || routes[r].row_stride < routes[r].col_end - routes[r].col_begin)
+            return fail(ctx, GATB_ERR_INVALID, "output route: NULL base, inverted column range or rows narrower than the range");
+    ctx->routes.assign(routes, routes + n_routes);
+    return GATB_OK;
+}
+
+extern "C" int gatb_peer_alloc(gatb_ctx *ctx, uint64_t bytes, void **ptr, unsigned char *handle)
+{
+    if (!ctx || !ptr || !handle || bytes == 0) return GATB_ERR_INVALID;
+    *ptr = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    CU(ctx, cudaMalloc(&p, bytes));             // (plain cudaMalloc: pool memory cannot be shared through IPC handles)
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(ctx, GATB_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == GATB_PEER_HANDLE_BYTES, "handle size");
+    memcpy(handle, &h, sizeof(h));
+    *ptr = p;
+    return GATB_OK;
+}
+
+extern "C" int gatb_peer_free(gatb_ctx *ctx, void *ptr)
+{
+    if (!ctx) return GATB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (ptr) CU(ctx, cudaFree(ptr));
+    return GATB_OK;
+}
+
+extern "C" int gatb_peer_open(gatb_ctx *ctx, const unsigned char *handle, void **ptr)
+{
+    if (!ctx || !handle || !ptr) return GATB_ERR_INVALID;
+    *ptr = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, GATB_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+    *ptr = p;
+    return GATB_OK;
+}
+
+extern "C" int gatb_peer_close(gatb_ctx *ctx, void *ptr)
+{
+    if (!ctx) return GATB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (ptr) CU(ctx, cudaIpcCloseMemHandle(ptr));
+    return GATB_OK;
 }

@@ -389,6 +389,18 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
         }
     }
     __syncthreads();
+    if (!DENSITY && p.n_routes) {
+        // routed delivery (count.cuh OutRoute): the finished rows go straight to their consumers, local or on a
+        // peer GPU; consecutive threads write consecutive columns of one row (coalesced 4-byte stores)
+        for (uint32_t i = threadIdx.x; i < ncells; i += blockDim.x) {
+            const uint32_t row = s_begin + i / ka, a = a0 + i % ka, v = acc_u[i];
+            for (uint32_t r = 0; r < p.n_routes; r++) {
+                const OutRoute &rt = p.routes[r];
+                if (a >= rt.col_begin && a < rt.col_end) rt.base[(rt.row0 + row) * rt.row_stride + (a - rt.col_begin)] = v;
+            }
+        }
+        return;
+    }
     for (uint32_t i = threadIdx.x; i < ncells; i += blockDim.x) {
         const uint64_t o = (uint64_t)(s_begin + i / ka) * p.n_annot + a0 + i % ka;
         if (DENSITY) {

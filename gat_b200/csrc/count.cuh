@@ -45,6 +45,20 @@ struct KeyBins {
     uint32_t shift;     // 4 .. 20
 };
 
+// Where a count launch delivers its integer results.  Without routes: out_u32[sample][annotation].  With routes,
+// every route r receives the columns [col_begin, col_end) of every sample row, at
+//     base[(row0 + sample) * row_stride + (annotation - col_begin)]
+// `base` may be memory of ANOTHER GPU of the box (peer-mapped over NVLink, gatb_peer_open): the kernel's epilogue
+// then IS the exchange step of a multi-GPU run -- all columns to every rank = the all-gather of the sample slabs,
+// each rank's own column block = the all-to-all by column -- with no collective launched afterwards.
+constexpr uint32_t GATB_MAX_ROUTES = 16;
+struct OutRoute {
+    uint32_t *base;
+    uint64_t row_stride;
+    uint64_t row0;
+    uint32_t col_begin, col_end;
+};
+
 struct CountParams {
     // annotations
     const KeyBins *keybins;         // [n_groups][n_keys]
@@ -68,6 +82,8 @@ struct CountParams {
     // output
     uint32_t *out_u32;              // [n_samples][n_annot] (integer counters)
     double *out_f64;                // [n_samples][n_annot] (nucleotide-density)
+    uint32_t n_routes;              // > 0: the integer results go to routes[] instead of out_u32
+    OutRoute routes[GATB_MAX_ROUTES];
 };
 
 // shared memory of a count launch: per-warp staging, accumulators [schunk][ka] (u32; density: + (sum,

@@ -130,6 +130,35 @@ class Context(object):
         return dict(zip(["expected", "stddev", "lower95", "upper95", "fold", "pvalue"], outs))
 
 
+    def set_output_routes(self, routes):
+        """routes: list of dicts(base=device pointer, plane_stride, row_stride, row0, col_begin, col_end) -- where the
+        counting kernels of the following gatb_run calls deliver their integer results (gatb_set_output_routes);
+        an empty list restores the plain output"""
+        arr = (_lib.Route * max(len(routes), 1))()
+        for i, r in enumerate(routes):
+            arr[i] = _lib.Route(int(r["base"]), int(r.get("plane_stride", 0)), int(r["row_stride"]), int(r.get("row0", 0)),
+                                int(r["col_begin"]), int(r["col_end"]))
+        self.check(self.lib.gatb_set_output_routes(self.handle, len(routes), ctypes.byref(arr)))
+
+    def peer_alloc(self, nbytes):
+        """shareable device memory -> (pointer, 64-byte IPC handle)"""
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        self.check(self.lib.gatb_peer_alloc(self.handle, int(nbytes), ctypes.byref(ptr), ctypes.byref(handle)))
+        return int(ptr.value), bytes(handle)
+
+    def peer_free(self, ptr):
+        self.check(self.lib.gatb_peer_free(self.handle, ctypes.c_void_p(ptr)))
+
+    def peer_open(self, handle):
+        ptr = ctypes.c_void_p()
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        self.check(self.lib.gatb_peer_open(self.handle, ctypes.byref(buf), ctypes.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr):
+        self.check(self.lib.gatb_peer_close(self.handle, ctypes.c_void_p(ptr)))
+
     def column_pvalue(self, counts, values, expected):
         """AnnotatorResult.getEmpiricalPValue (gat/Engine.pyx:1829-1831): p-value of values[a] among the samples
         of column a against the STORED expectation expected[a]; counts: host ndarray [n_samples][n_cols]"""

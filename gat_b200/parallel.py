@@ -110,6 +110,76 @@ def allgather_columns(local, n_columns):
     return torch.cat([pieces[r][..., :widths[r]] for r in range(world)], dim=-1)
 
 
+class PeerMatrix(object):
+    """One uint32 matrix [planes][rows][cols] per rank in memory that every other rank of the box can write
+    (CUDA IPC over NVLink / NVSwitch): the destination of the counting kernel's output routes, i.e. of an exchange
+    that needs no collective.  Collective constructor: every rank calls it with ITS shape; the IPC handles travel
+    through torch.distributed's object collectives (control plane only).
+
+        mine.tensor          this rank's matrix as a torch tensor (a view of the shared allocation)
+        mine.pointer(r)      device pointer of rank r's matrix as mapped into this process
+        mine.shape_of(r)     its (planes, rows, cols)
+    """
+
+    def __init__(self, ctx, planes, rows, cols):
+        import torch.distributed as dist
+        self.ctx = ctx
+        self.rank, self.world = rank_world()
+        self.shape = (int(planes), int(rows), int(cols))
+        nbytes = max(4 * planes * rows * cols, 4)
+        self.local_ptr, handle = ctx.peer_alloc(nbytes)
+        everyone = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(everyone, (handle, self.shape))
+        else:
+            everyone[0] = (handle, self.shape)
+        self.shapes = [s for _, s in everyone]
+        self.ptrs = []
+        for r, (h, _) in enumerate(everyone):
+            self.ptrs.append(self.local_ptr if r == self.rank else ctx.peer_open(h))
+        self.tensor = self._as_tensor()
+
+    def _as_tensor(self):
+        planes, rows, cols = self.shape
+
+        class _Shared(object):      # the CUDA array interface lets torch view memory it did not allocate
+            pass
+        holder = _Shared()
+        holder.__cuda_array_interface__ = {"shape": (planes, rows, cols), "typestr": "<i4", "data": (self.local_ptr, False),
+                                           "version": 3, "strides": None}
+        self._holder = holder
+        return torch.as_tensor(holder, device=torch.device("cuda", self.ctx.device))
+
+    def pointer(self, r):
+        return self.ptrs[r]
+
+    def shape_of(self, r):
+        return self.shapes[r]
+
+    def close(self):
+        """collective in effect: call it on every rank once nobody writes any more (after a barrier)"""
+        if self.ptrs is None:
+            return
+        self.tensor = None
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                self.ctx.peer_close(p)
+        self.ctx.peer_free(self.local_ptr)
+        self.ptrs = None
+
+
+def barrier():
+    """all ranks reach this point (and their GPUs are idle): after it, what the other ranks' kernels stored into this
+    rank's PeerMatrix is complete"""
+    import torch.distributed as dist
+    rank, world = rank_world()
+    torch.cuda.synchronize()
+    if world > 1:
+        box = [None] * world
+        dist.all_gather_object(box, rank)        # (object collective: rides on the CPU backend when there is one)
+    torch.cuda.synchronize()
+
+
 _warm = {"thread": None}
 
 
@@ -121,7 +191,7 @@ def warm_up_async():
     import threading
     import torch.distributed as dist
     rank, world = rank_world()
-    if world == 1 or _warm["thread"] is not None or dist.get_backend() != "nccl":
+    if world == 1 or _warm["thread"] is not None or "nccl" not in str(dist.get_backend()):
         return
 
     def go():
@@ -156,8 +226,10 @@ def init_from_env(backend=None):
     if dist.is_initialized():
         return True
     if backend is None:
-        backend = "nccl" if torch.cuda.is_available() else "gloo"
-    if backend == "nccl":
+        # NCCL for CUDA tensors, gloo for the small host-side object collectives (IPC handles, barriers, the seed):
+        # a run that exchanges its counts through peer memory then never pays for NCCL's set-up
+        backend = "cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo"
+    if "nccl" in backend:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group(backend=backend)
@@ -167,5 +239,5 @@ def init_from_env(backend=None):
 def finalize():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
-        dist.barrier()
+        barrier()
         dist.destroy_process_group()

@@ -242,6 +242,35 @@ int  gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_counters, co
 /* samples placed + counted per internal batch (memory/parallelism knob; 0 = default) */
 int  gatb_set_batch_size(gatb_ctx *ctx, uint32_t batch);
 
+/* ---- multi-GPU exchange fused into the counting kernel --------------------------------------------------
+ * Samples are independent (gat/__init__.py:738-747, the results are only concatenated :770-774): rank g of G
+ * computes its shard of the global sample indices and the S x A count matrix is assembled from the shards.
+ * Instead of a collective AFTER the kernels, gatb_run can deliver every finished row to several destinations at
+ * once -- OUTPUT ROUTES, written by the counting kernel's epilogue: route r receives the columns
+ * [col_begin, col_end) of counter plane c, sample row s at
+ *     base + c * plane_stride + (row0 + s) * row_stride + (annotation - col_begin)         (uint32 elements)
+ * where s counts from the call's sample_begin.  `base` may be memory of another GPU of the box, mapped with
+ * gatb_peer_open over NVLink / NVSwitch: all columns to every rank's [S][A] matrix is the all-gather of the
+ * sample slabs; every rank's own column block to its [S][A_g] matrix is the all-to-all by column (column-sharded
+ * statistics).  The caller synchronises the ranks (any barrier) after the last gatb_run before reading.
+ * Routes stay set until replaced (n_routes = 0 clears them); with routes, gatb_run needs out_is_device != 0,
+ * integer counters only, and ignores out_counts.
+ * Peer memory: gatb_peer_alloc allocates shareable device memory and returns its 64-byte IPC handle (send it to
+ * the other processes by any means), gatb_peer_open maps another process's allocation into this one. */
+#define GATB_PEER_HANDLE_BYTES 64
+typedef struct gatb_route {
+    uint32_t *base;
+    uint64_t plane_stride;          /* elements between counter planes */
+    uint64_t row_stride;            /* elements between sample rows */
+    uint64_t row0;                  /* row of the call's first sample */
+    uint32_t col_begin, col_end;    /* annotation columns delivered */
+} gatb_route;
+int  gatb_set_output_routes(gatb_ctx *ctx, int n_routes, const gatb_route *routes);
+int  gatb_peer_alloc(gatb_ctx *ctx, uint64_t bytes, void **ptr, unsigned char *handle /*[64]*/);
+int  gatb_peer_free(gatb_ctx *ctx, void *ptr);
+int  gatb_peer_open(gatb_ctx *ctx, const unsigned char *handle /*[64]*/, void **ptr);
+int  gatb_peer_close(gatb_ctx *ctx, void *ptr);
+
 /* ---- measurement aids (bench.py `roofline`; no reference counterpart) ------------------------------
  * gatb_count_work: the work of the counting kernel on the LAST internal batch of the preceding gatb_run on
  * this sampler (n_samples = size of that batch): out[0] placed segments, out[1] index entries in their runs

@@ -234,3 +234,44 @@ def test_multirank_run_equals_single_rank():
     assert out.returncode == 0, out.stdout + out.stderr
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["ok"]
+
+
+def test_output_routes_deliver_rows_and_column_blocks(ctx, oracle):
+    """gatb_set_output_routes: the counting kernel's epilogue writes every finished row to several destinations --
+    whole rows at a row offset (the all-gather layout) and column blocks with their own row stride (the all-to-all
+    by column layout), several counter planes, several internal batches; same numbers as the plain output"""
+    import torch
+    from gat_b200 import device, _lib
+    rng = np.random.default_rng(77)
+    pr = helpers.random_problem(rng, n_contigs=3, n_iso=0, n_annot=11)
+    A, S = 11, 50
+    smp = device.Sampler(ctx, pr["unit_contig"], pr["n_contigs"], False, pr["unit_segments"], pr["unit_workspace"])
+    annos = device.Annotations(ctx, pr["annotations"], key_ws_nseg=pr["cws_nseg"])
+    names = ["nucleotide-overlap", "segment-overlap"]
+    want, _ = smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S)
+    dev = torch.device("cuda", 0)
+    full = torch.full((2, S + 7, A), -1, dtype=torch.int32, device=dev)         # rows 5 .. 5 + S of a taller matrix
+    left = torch.full((2, S, 4), -1, dtype=torch.int32, device=dev)             # columns 0..3
+    right = torch.full((2, S, 7), -1, dtype=torch.int32, device=dev)            # columns 4..10
+    ctx.set_batch_size(16)                                                      # 4 internal batches
+    ctx.set_output_routes([
+        dict(base=full.data_ptr(), plane_stride=(S + 7) * A, row_stride=A, row0=5, col_begin=0, col_end=A),
+        dict(base=left.data_ptr(), plane_stride=S * 4, row_stride=4, row0=0, col_begin=0, col_end=4),
+        dict(base=right.data_ptr(), plane_stride=S * 7, row_stride=7, row0=0, col_begin=4, col_end=A)])
+    try:
+        smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S, out_counts_ptr=full.data_ptr())
+        with pytest.raises(_lib.GatB200Error):          # routes deliver to device memory only
+            smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S)
+    finally:
+        ctx.set_output_routes([])
+        ctx.set_batch_size(0)
+    torch.cuda.synchronize()
+    for i, n in enumerate(names):
+        w = want[n].astype(np.int64)
+        assert np.array_equal(full[i, 5:5 + S].cpu().numpy(), w), n
+        assert (full[i, :5] == -1).all() and (full[i, 5 + S:] == -1).all()
+        assert np.array_equal(left[i].cpu().numpy(), w[:, :4]) and np.array_equal(right[i].cpu().numpy(), w[:, 4:]), n
+    again, _ = smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S)    # routes cleared: plain output
+    assert np.array_equal(again[names[0]], want[names[0]])
+    smp.close()
+    annos.close()

@@ -20,3 +20,12 @@ try:
 except Exception as e:
     print("bench failed", e)
 PY
+timeout 900 $TR bench.py --gpus $N --steps 8 --warmup 3 --gather nccl --no-e2e > gpurun_out/c_bench_${N}gpu_nccl.json 2> gpurun_out/c_bench_${N}gpu_nccl.err
+python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/c_bench_${N}gpu_nccl.json"))
+    print("N=%d (nccl gather) value %.0f ms/step %.2f parity %s gather %s" % (d["n_gpus"], d["value"], d["ms_per_step"], d["parity_check"], d["gather_check"]))
+except Exception as e:
+    print("bench nccl failed", e)
+PY

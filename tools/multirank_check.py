@@ -33,7 +33,8 @@ def main():
     import gat_b200
     from gat_b200 import engine as Engine, parallel, synthetic
 
-    names = ["nucleotide-overlap", "segment-overlap", "nucleotide-density"]
+    # (integer counters: the peer transport routes them; a density counter makes run() use NCCL for everything)
+    names = ["nucleotide-overlap", "segment-overlap", "annotation-overlap"]
 
     def run(**kw):
         segments, annotations, workspaces, iso = synthetic.make(args.segments, args.tracks, 5000, isochores=args.isochores)
@@ -55,8 +56,11 @@ def main():
     report = {"ranks": world, "samples": args.samples, "tracks": args.tracks, "counters": names,
               "isochores": args.isochores, "seconds_1_rank": round(t_alone, 3)}
     ok = True
-    for mode in ("allgather", "columns"):
-        got, dt = run(exchange=mode)
+    for mode, kw in (("allgather", dict(exchange="allgather", transport="nccl")),
+                     ("columns", dict(exchange="columns", transport="nccl")),
+                     ("peer_allgather", dict(exchange="allgather", transport="peer")),
+                     ("peer_columns", dict(exchange="columns", transport="peer"))):
+        got, dt = run(**kw)
         same_stats = bool(np.array_equal(table(alone), table(got)))
         n_cols = n_equal = 0
         for a, g in zip(alone, got):
@@ -71,7 +75,7 @@ def main():
         torch.distributed.all_reduce(flags)
         report[mode] = {"statistics_equal_on_ranks": int(flags[0]), "sample_columns_checked": int(flags[1]),
                         "sample_columns_equal": int(flags[2]), "seconds": round(dt, 3)}
-        expect_cols = len(alone) * (world if mode == "allgather" else 1)
+        expect_cols = len(alone) * (world if mode.endswith("allgather") else 1)
         ok = ok and int(flags[0]) == world and int(flags[1]) == int(flags[2]) == expect_cols
     report["ok"] = ok
     if rank == 0:
