@@ -334,6 +334,7 @@ def roofline_of(args, wl, ctx, smp, annos, prof, local):
             "traffic": (facts["dram_bytes_per_sample"] * B) if "dram_bytes_per_sample" in facts else None,
             "traffic_source": facts.get("capture"),
             "issue": None,
+            "l1tex_data_pipe_pct_of_peak": facts.get("l1tex_throughput_pct"),     # (ncu capture: the unit that saturates)
             "reference_algorithm_equivalent": {"bytes_per_launch": ref_bytes, "GBps": ref_bytes / sec / 1e9,
                                                "x_hbm_peak": ref_bytes / sec / 1e9 / hbm_peak,
                                                "note": "SURVEY 8d: what the reference's per-cell two-pointer merge "
@@ -531,8 +532,11 @@ def run_ours(args):
         ps = tuple(t.numpy().view(unsign[t.dtype]) for t in pin[3:6])
         pw = tuple(t.numpy().view(unsign[t.dtype]) for t in pin[6:9])
         h2d = sum(t.numel() * t.element_size() for t in pin)
-        host_out = torch.empty((S, A), dtype=odt).pin_memory()
+        host_outs = [torch.empty((S, A), dtype=odt).pin_memory() for _ in range(nbuf)]
+        host_out = host_outs[0]
         host_np = host_out.numpy()
+        side = torch.cuda.Stream(device=dev)
+        copied = [None] * nbuf
         ids = device.counter_ids([args.counter])
         info_np = np.zeros(3, dtype=np.uint64)
 
@@ -560,20 +564,30 @@ def run_ours(args):
                                                device._p(host_np) if is_density else None, 0, device._p(info_np)))
                 else:
                     # N > 1: counts stay on the device for the exchange; every rank then reads ITS rows of the
-                    # gathered matrix back to the host
+                    # gathered matrix back to the host -- on a side stream, while the next step already runs
+                    # (two device matrices and two pinned host matrices, used alternately)
+                    b = j % nbuf
+                    if copied[b] is not None:
+                        copied[b].synchronize()     # the copy that last read this matrix / wrote this host buffer
                     if peer:
-                        ctx.set_output_routes(routes[0])
+                        ctx.set_output_routes(routes[b])
                     ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), SEED, 0, begin, S,
-                                               None if is_density else outs[0].data_ptr(),
-                                               outs[0].data_ptr() if is_density else None, 1, device._p(info_np)))
+                                               None if is_density else outs[b].data_ptr(),
+                                               outs[b].data_ptr() if is_density else None, 1, device._p(info_np)))
                     if peer:
                         barrier()           # every rank's rows have arrived in every matrix
                     else:
-                        dist.all_gather_into_tensor(gathers[0], outs[0])
-                    host_out.copy_(gathers[0][rank * S:(rank + 1) * S], non_blocking=True)
-                    torch.cuda.current_stream(dev).synchronize()
+                        dist.all_gather_into_tensor(gathers[b], outs[b])
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        host_outs[b].copy_(gathers[b][rank * S:(rank + 1) * S], non_blocking=True)
+                        copied[b] = torch.cuda.Event()
+                        copied[b].record(side)
                 s2.close()
                 a2.close()
+            for ev in copied:
+                if ev is not None:
+                    ev.synchronize()
             return int(host_np.reshape(-1)[:1].view(np.uint8)[0])
 
         if world == 1:

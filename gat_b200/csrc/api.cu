@@ -27,6 +27,9 @@ struct gatb_ctx {
     cudaStream_t upload_stream = nullptr;   // gatb_annotations_create_async: copies (+ a rebuild), off the compute stream
     cudaStream_t build_stream = nullptr;    // index build kernels, chunk by chunk behind the copies
     cudaStream_t copy_stream = nullptr;     // gatb_run with host outputs: device-to-host copies of batch i overlap batch i+1
+    cudaStream_t place_stream = nullptr;    // GATB_OVERLAP: placement kernels, beside the counting kernels on `stream`
+    cudaEvent_t ev_placed[2] = {nullptr, nullptr}, ev_count_done[2] = {nullptr, nullptr};
+    bool overlap = false;
     cudaEvent_t ev_counted[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     uint32_t *err_slots = nullptr;          // pinned words of pending asynchronous creates: 4 per set (validation, -, entries needed lo/hi)
     std::vector<int> err_free;
@@ -121,10 +124,14 @@ struct DevBuf {
 // destroyed per call (one per track in gat.run) re-use them instead of allocating hundreds of MB each.
 // Calls on a context are serialised by the caller and every entry point that uses the buffers returns
 // with the stream drained, so sharing them between samplers is safe.
-struct BatchScratch {
+struct PlaceBufs {                        // one batch of placed samples
     DevBuf<uint64_t> unit_buf, placed;
     DevBuf<uint32_t> unit_n, placed_n;
     DevBuf<uint8_t> status;
+};
+struct BatchScratch {
+    PlaceBufs pb[2];                      // two sets: with GATB_OVERLAP the placement of batch i + 1 runs (on its own
+                                          // stream) beside the counting of batch i
     DevBuf<uint32_t> out_tmp[2];          // host-output runs: two staging slabs, so that the copy of batch i
     DevBuf<double> out_tmp_f[2];          // to the host overlaps the kernels of batch i + 1
 };
@@ -160,9 +167,12 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->build_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->place_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
         e = cudaEventCreateWithFlags(&ctx->ev_counted[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_placed[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_count_done[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->err_slots, 256 * 4 * sizeof(uint32_t));
     if (e != cudaSuccess) { cudaStreamDestroy(ctx->own_stream); delete ctx; return fail(nullptr, GATB_ERR_CUDA, cudaGetErrorString(e)); }
@@ -182,6 +192,7 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     ctx->schunk_max = env_u32("GATB_SCHUNK", 0);
     ctx->kgrp_max = env_u32("GATB_KEY_GROUP", 0);
     ctx->trace = env_u32("GATB_TRACE", 0) != 0;
+    ctx->overlap = env_u32("GATB_OVERLAP", 0) != 0;
     ctx->scratch = new BatchScratch();
     ctx->batch = env_u32("GATB_BATCH", 0);
     *out = ctx;
@@ -198,9 +209,12 @@ extern "C" void gatb_destroy(gatb_ctx *ctx)
     if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
     if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->place_stream) cudaStreamDestroy(ctx->place_stream);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_counted[i]) cudaEventDestroy(ctx->ev_counted[i]);
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_placed[i]) cudaEventDestroy(ctx->ev_placed[i]);
+        if (ctx->ev_count_done[i]) cudaEventDestroy(ctx->ev_count_done[i]);
     }
     if (ctx->err_slots) cudaFreeHost(ctx->err_slots);
     delete ctx;
@@ -286,6 +300,7 @@ struct gatb_annotations {
     uint64_t n_intervals = 0;
     uint64_t n_boff = 0, capacity = 0;
     uint64_t n_entries = 0;             // entries the built index holds (padding included)
+    bool has_long = false;              // it holds intervals of >= 2^20 - 1 bases
     std::vector<KeyBins> h_keybins;
     DevBuf<KeyBins> keybins;
     DevBuf<uint32_t> boff;
@@ -325,7 +340,7 @@ static void build_params(const gatb_annotations *a, BuildBinsParams &bp)
     bp.cent = a->cent.p; bp.civ = a->civ.p; bp.cprev = a->cprev.p; bp.capacity = a->capacity;
     bp.n_annot = a->n_annot; bp.n_keys = a->n_keys; bp.n_groups = a->n_groups; bp.ka = a->ka;
     bp.a_begin = 0; bp.a_count = a->n_annot;
-    bp.error = a->d_err.p; bp.total = a->d_total.p;
+    bp.error = a->d_err.p; bp.has_long = a->d_err.p + 1; bp.total = a->d_total.p;
 }
 
 // queue on `st`: scan + fill of the index (the per-bin counts are in place), the read-back of the validation
@@ -342,7 +357,7 @@ static cudaError_t annotations_build_finish(gatb_annotations *a, cudaStream_t st
         ctx->launches += 5;                 // even, scan (2), total, fill, pad
         e = launch_bins_finish(st, bp, a->scan_tmp.p, a->scan_tmp.n);
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(slot, a->d_err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(slot, a->d_err.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(slot + 2, a->d_total.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaEventRecord(a->ready, st);
     return e;
@@ -353,7 +368,7 @@ static cudaError_t annotations_build(gatb_annotations *a)
 {
     gatb_ctx *ctx = a->ctx;
     cudaStream_t st = ctx->upload_stream;
-    cudaError_t e = cudaMemsetAsync(a->d_err.p, 0, sizeof(uint32_t), st);
+    cudaError_t e = cudaMemsetAsync(a->d_err.p, 0, 2 * sizeof(uint32_t), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(a->d_total.p, 0, sizeof(unsigned long long), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(a->boff.p, 0, 2 * (a->n_boff + 1) * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
@@ -377,6 +392,7 @@ static int annotations_finish(gatb_annotations *a)
     cudaError_t e = cudaEventSynchronize(a->ready);
     uint32_t h_err = slot[0];
     memcpy(&a->n_entries, slot + 2, sizeof(uint64_t));
+    a->has_long = slot[1] != 0;
     if (e == cudaSuccess && !(h_err & 3u) && (h_err & 4u)) {
         unsigned long long need;
         memcpy(&need, slot + 2, sizeof(need));
@@ -392,6 +408,7 @@ static int annotations_finish(gatb_annotations *a)
         if (e == cudaSuccess) e = cudaEventSynchronize(a->ready);
         h_err = slot[0];
         memcpy(&a->n_entries, slot + 2, sizeof(uint64_t));
+        a->has_long = slot[1] != 0;
     }
     // the raw lists and the scan scratch are no longer needed (freed in upload-stream order)
     a->d_offs.release(); a->d_start.release(); a->d_end.release(); a->d_err.release(); a->d_total.release();
@@ -512,10 +529,10 @@ static int annotations_create_common(gatb_ctx *ctx, int n_annot, int n_keys, con
         if (e == cudaSuccess) e = a->d_end.alloc(n_iv);
         a->src_offs = a->d_offs.p; a->src_start = a->d_start.p; a->src_end = a->d_end.p;
     }
-    if (e == cudaSuccess) e = a->d_err.alloc(1);
+    if (e == cudaSuccess) e = a->d_err.alloc(2);
     if (e == cudaSuccess) e = a->d_total.alloc(1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ready, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMemsetAsync(a->d_err.p, 0, sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->d_err.p, 0, 2 * sizeof(uint32_t), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(a->d_total.p, 0, sizeof(unsigned long long), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(a->boff.p, 0, 2 * (n_boff + 1) * sizeof(uint32_t), st);
     // The intervals go up in chunks of tracks; the build stream counts the bin entries of a chunk (step 1 of
@@ -602,7 +619,7 @@ extern "C" void gatb_annotations_destroy(gatb_annotations *a)
 static int count_params_annos(const gatb_annotations *a, uint32_t n_samples, bool density, CountParams &p)
 {
     gatb_ctx *ctx = a->ctx;
-    p.keybins = a->keybins.p; p.boff = a->boff.p; p.coff_base = a->n_boff + 1; p.cent = a->cent.p; p.civ = a->civ.p; p.cprev = a->cprev.p; p.sentinel = (uint32_t)a->capacity;
+    p.keybins = a->keybins.p; p.boff = a->boff.p; p.coff_base = a->n_boff + 1; p.cent = a->cent.p; p.civ = a->civ.p; p.cprev = a->cprev.p; p.sentinel = (uint32_t)a->capacity; p.has_long = a->has_long ? 1u : 0u;
     p.key_ws_nseg = a->has_nseg ? a->key_ws_nseg.p : nullptr;
     p.n_annot = a->n_annot; p.n_keys = a->n_keys; p.n_groups = a->n_groups; p.ka = a->ka;
     p.n_samples = n_samples;
@@ -953,17 +970,19 @@ static uint32_t pick_batch(const gatb_sampler *s, uint64_t n_samples)
     return (uint32_t)std::max<uint64_t>(b, 1);
 }
 
-static int ensure_batch(gatb_sampler *s, uint32_t B)
+static int ensure_batch(gatb_sampler *s, uint32_t B, int n_sets = 1)
 {
     gatb_ctx *ctx = s->ctx;
-    BatchScratch *sc = ctx->scratch;
-    CU(ctx, sc->placed.ensure((uint64_t)B * s->placed_stride));
-    CU(ctx, sc->placed_n.ensure((uint64_t)B * s->n_contigs));
-    if (s->has_iso) {
-        CU(ctx, sc->unit_buf.ensure((uint64_t)B * s->unit_stride));
-        CU(ctx, sc->unit_n.ensure((uint64_t)B * s->n_units));
+    for (int i = 0; i < n_sets; i++) {
+        PlaceBufs &pb = ctx->scratch->pb[i];
+        CU(ctx, pb.placed.ensure((uint64_t)B * s->placed_stride));
+        CU(ctx, pb.placed_n.ensure((uint64_t)B * s->n_contigs));
+        if (s->has_iso) {
+            CU(ctx, pb.unit_buf.ensure((uint64_t)B * s->unit_stride));
+            CU(ctx, pb.unit_n.ensure((uint64_t)B * s->n_units));
+        }
+        CU(ctx, pb.status.ensure((uint64_t)B * s->n_units));
     }
-    CU(ctx, sc->status.ensure((uint64_t)B * s->n_units));
     return GATB_OK;
 }
 
@@ -990,42 +1009,44 @@ __global__ void tally_kernel(const uint32_t *placed_n, uint64_t n_placed, const 
 }
 
 // enqueue K1 (+K2) for one batch; result in s->placed / s->placed_n
-static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin, uint32_t B)
+static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t sample_begin, uint32_t B, int set = 0,
+                       cudaStream_t on = nullptr)
 {
     gatb_ctx *ctx = s->ctx;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = on ? on : ctx->stream;
+    PlaceBufs &pb = ctx->scratch->pb[set];
     PlaceParams p;
     memset(&p, 0, sizeof(p));
     p.units = s->units.p; p.order = s->order.p;
     p.ws_start = s->ws_start.p; p.ws_end = s->ws_end.p; p.ws_cuminc = s->ws_cuminc.p; p.len_tab = s->len_tab.p;
     p.ws_tab = s->ws_tab.p;
     if (s->has_iso) {
-        p.buf = s->ctx->scratch->unit_buf.p; p.sample_stride = s->unit_stride;
-        p.out_n = s->ctx->scratch->unit_n.p; p.out_n_stride = s->n_units; p.out_by_contig = 0;
+        p.buf = pb.unit_buf.p; p.sample_stride = s->unit_stride;
+        p.out_n = pb.unit_n.p; p.out_n_stride = s->n_units; p.out_by_contig = 0;
     } else {
-        p.buf = s->ctx->scratch->placed.p; p.sample_stride = s->placed_stride;
-        p.out_n = s->ctx->scratch->placed_n.p; p.out_n_stride = s->n_contigs; p.out_by_contig = 1;
+        p.buf = pb.placed.p; p.sample_stride = s->placed_stride;
+        p.out_n = pb.placed_n.p; p.out_n_stride = s->n_contigs; p.out_by_contig = 1;
     }
-    p.status = s->ctx->scratch->status.p; p.unit_over = s->unit_over.p; p.n_units = s->n_units; p.n_samples = B; p.sample_begin = sample_begin;
+    p.status = pb.status.p; p.unit_over = s->unit_over.p; p.n_units = s->n_units; p.n_samples = B; p.sample_begin = sample_begin;
     p.seed = seed; p.track = track; p.sampler_kind = s->kind;
     p.seg_start = s->seg_start.p; p.seg_end = s->seg_end.p;
     p.shift_half_radius = s->shift_radius / 2; p.shift_extension = s->shift_extension;
-    { ProfScope ps(ctx, PROF_PLACE); launch_place(st, p); }
+    { ProfScope ps(ctx, PROF_PLACE, st); launch_place(st, p); }
     CU(ctx, cudaGetLastError());
     if (s->has_iso) {
         MergeParams m;
         memset(&m, 0, sizeof(m));
         m.units = s->units.p; m.contig_unit_off = s->contig_unit_off.p; m.contig_units = s->contig_units.p;
-        m.contig_base = s->contig_base.p; m.unit_buf = s->ctx->scratch->unit_buf.p; m.unit_stride = s->unit_stride;
-        m.unit_n = s->ctx->scratch->unit_n.p; m.placed = s->ctx->scratch->placed.p; m.placed_stride = s->placed_stride;
-        m.placed_n = s->ctx->scratch->placed_n.p; m.n_units = s->n_units; m.n_contigs = s->n_contigs; m.n_samples = B;
-        { ProfScope ps(ctx, PROF_MERGE); launch_contig_merge(st, m); }
+        m.contig_base = s->contig_base.p; m.unit_buf = pb.unit_buf.p; m.unit_stride = s->unit_stride;
+        m.unit_n = pb.unit_n.p; m.placed = pb.placed.p; m.placed_stride = s->placed_stride;
+        m.placed_n = pb.placed_n.p; m.n_units = s->n_units; m.n_contigs = s->n_contigs; m.n_samples = B;
+        { ProfScope ps(ctx, PROF_MERGE, st); launch_contig_merge(st, m); }
         CU(ctx, cudaGetLastError());
     }
     {
-        ProfScope ps(ctx, PROF_OTHER);
+        ProfScope ps(ctx, PROF_OTHER, st);
         tally_kernel<<<std::min<uint32_t>(1024, (uint32_t)(((uint64_t)B * s->n_units + 255) / 256)), 256, 0, st>>>(
-            s->ctx->scratch->placed_n.p, (uint64_t)B * s->n_contigs, s->ctx->scratch->status.p, (uint64_t)B * s->n_units, s->tally.p);
+            pb.placed_n.p, (uint64_t)B * s->n_contigs, pb.status.p, (uint64_t)B * s->n_units, s->tally.p);
     }
     CU(ctx, cudaGetLastError());
     return GATB_OK;
@@ -1075,7 +1096,7 @@ static int place_once(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t s
 {
     gatb_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    BatchScratch *sc = ctx->scratch;
+    PlaceBufs *sc = &ctx->scratch->pb[0];
     const bool from_units = by_unit && s->has_iso;          // the unit-level buffers (before fromIsochores)
     const uint64_t stride = from_units ? s->unit_stride : s->placed_stride;
     const uint32_t n_lists = by_unit ? s->n_units : s->n_contigs;
@@ -1176,10 +1197,16 @@ static int run_once(gatb_sampler *s, const gatb_annotations *annos, int n_counte
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     double t_alloc = 0, t_placeq = 0, t_annos = 0, t_countq = 0;
-    int rc = ensure_batch(s, B);
+    // GATB_OVERLAP: the placement of batch i + 1 runs on its own stream beside the counting of batch i (two sets of
+    // placement buffers; the two kernels stress different units: placement is latency-bound, counting saturates the
+    // L1 data pipe)
+    const bool overlap = ctx->overlap && n_samples > B;
+    cudaStream_t pst = overlap ? ctx->place_stream : st;
+    int rc = ensure_batch(s, B, overlap ? 2 : 1);
     if (rc) return rc;
     t_alloc = since();
     BatchScratch *sc = ctx->scratch;
+    bool count_pending[2] = {false, false};
     const int n_stage = (!out_is_device && n_samples > B) ? 2 : 1;
     if (!out_is_device)
         for (int i = 0; i < n_stage; i++) {
@@ -1193,15 +1220,26 @@ static int run_once(gatb_sampler *s, const gatb_annotations *annos, int n_counte
     uint64_t n_staged = 0;
     bool copied_pending[2] = {false, false};
 
-    for (uint64_t done = 0; done < n_samples; done += B) {
+    if (overlap) {                       // the placement stream starts behind the memsets above
+        CU(ctx, cudaEventRecord(ctx->ev_placed[0], st));
+        CU(ctx, cudaStreamWaitEvent(pst, ctx->ev_placed[0], 0));
+    }
+    uint64_t batch_no = 0;
+    for (uint64_t done = 0; done < n_samples; done += B, batch_no++) {
         const uint32_t b = (uint32_t)std::min<uint64_t>(B, n_samples - done);
-        rc = place_batch(s, seed, track, sample_begin + done, b);
+        const int set = overlap ? (int)(batch_no & 1) : 0;
+        if (overlap && count_pending[set]) CU(ctx, cudaStreamWaitEvent(pst, ctx->ev_count_done[set], 0));   // buffers free again
+        rc = place_batch(s, seed, track, sample_begin + done, b, set, pst);
         if (rc) return rc;
+        if (overlap) {
+            CU(ctx, cudaEventRecord(ctx->ev_placed[set], pst));
+            CU(ctx, cudaStreamWaitEvent(st, ctx->ev_placed[set], 0));
+        }
         if (done == 0) t_placeq = since();
         CountParams p;
         memset(&p, 0, sizeof(p));
-        p.placed = sc->placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
-        p.placed_n = sc->placed_n.p; p.key_present = nullptr;
+        p.placed = sc->pb[set].placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
+        p.placed_n = sc->pb[set].placed_n.p; p.key_present = nullptr;
         for (int c = 0; c < n_counters; c++) {
             const bool dens = counters[c] == GATB_NUCLEOTIDE_DENSITY;
             rc = count_params_annos(annos, b, dens, p);
@@ -1248,6 +1286,14 @@ static int run_once(gatb_sampler *s, const gatb_annotations *annos, int n_counte
                 n_staged++;
             }
         }
+        if (overlap) {
+            CU(ctx, cudaEventRecord(ctx->ev_count_done[set], st));
+            count_pending[set] = true;
+        }
+    }
+    if (overlap) {                       // the tally (placement stream) is read back through `st` below
+        CU(ctx, cudaEventRecord(ctx->ev_placed[0], pst));
+        CU(ctx, cudaStreamWaitEvent(st, ctx->ev_placed[0], 0));
     }
     // the compute stream joins the last copies: one synchronisation point for the caller
     for (int i = 0; i < 2; i++)
@@ -1313,14 +1359,14 @@ extern "C" int gatb_count_work(gatb_sampler *s, const gatb_annotations *annos, u
     if (rc) return rc;
     tl_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
-    if (ctx->scratch->placed.n < (uint64_t)n_samples * s->placed_stride || ctx->scratch->placed_n.n < (uint64_t)n_samples * s->n_contigs)
+    if (ctx->scratch->pb[0].placed.n < (uint64_t)n_samples * s->placed_stride || ctx->scratch->pb[0].placed_n.n < (uint64_t)n_samples * s->n_contigs)
         return fail(ctx, GATB_ERR_INVALID, "count_work: no batch of that size has been placed");
     CountParams p;
     memset(&p, 0, sizeof(p));
     rc = count_params_annos(annos, n_samples, false, p);
     if (rc) return rc;
-    p.placed = ctx->scratch->placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
-    p.placed_n = ctx->scratch->placed_n.p;
+    p.placed = ctx->scratch->pb[0].placed.p; p.sample_stride = s->placed_stride; p.key_base = s->contig_base.p;
+    p.placed_n = ctx->scratch->pb[0].placed_n.p;
     DevBuf<unsigned long long> d_out;
     CU(ctx, d_out.alloc(2));
     CU(ctx, cudaMemsetAsync(d_out.p, 0, 2 * sizeof(unsigned long long), st));

@@ -130,17 +130,20 @@ __device__ __forceinline__ void count_entry(uint32_t x, uint32_t wy, uint32_t y,
 }
 
 // the two entries of a flight against their segment
-template <int COUNTER>
+template <int COUNTER, bool LONG>
 __device__ __forceinline__ void count_pair(const uint2 *__restrict__ civ, const Flight &f, uint32_t stg, uint32_t stg_pe,
                                            uint32_t acc_addr)
 {
     const uint4 o = lds128(stg + f.owner * 16u);
     uint32_t pe = 0;
     if (NeedPrevSegment<COUNTER>::value) pe = lds32(stg_pe + f.owner * 4u);
-    // end = start + length; a length field of 2^20 - 1 sends us to civ[] for the end (rare)
+    // end = start + length; a length field of 2^20 - 1 sends us to civ[] for the end.  LONG = false: the index
+    // holds no such interval (known after the build), and the kernel is compiled without the test
     uint32_t y0 = f.w.x + (f.w.y >> 12), y1 = f.w.z + (f.w.w >> 12);
-    if ((f.w.y >> 12) == ENTRY_LEN_MASK) y0 = civ[f.j].y;
-    if ((f.w.w >> 12) == ENTRY_LEN_MASK) y1 = civ[f.j + 1u].y;
+    if (LONG) {
+        if ((f.w.y >> 12) == ENTRY_LEN_MASK) y0 = civ[f.j].y;
+        if ((f.w.w >> 12) == ENTRY_LEN_MASK) y1 = civ[f.j + 1u].y;
+    }
     count_entry<COUNTER>(f.w.x, f.w.y, y0, f.pv.x, o, pe, acc_addr);
     count_entry<COUNTER>(f.w.z, f.w.w, y1, f.pv.y, o, pe, acc_addr);
 }
@@ -163,7 +166,7 @@ struct WarpConsts {
 // special register (LDC / S2R + arithmetic in every round of the hot loop) but not the result of a shuffle.
 __device__ __forceinline__ uint32_t pin_reg(uint32_t v) { return __shfl_sync(GATB_FULL, v, (int)(threadIdx.x & 31u)); }
 
-template <int COUNTER>
+template <int COUNTER, bool LONG>
 __device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts &wc, const Indexed &it, uint32_t acc_addr)
 {
     const uint32_t lane = wc.lane, stg = wc.stg, stg_pe = wc.stg_pe;
@@ -220,24 +223,24 @@ __device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts 
     stage_b(32u, f1);
     for (uint32_t base = 0;;) {
         stage_b(base + 64u, f2);
-        count_pair<COUNTER>(p.civ, f0, stg, stg_pe, acc_addr);
+        count_pair<COUNTER, LONG>(p.civ, f0, stg, stg_pe, acc_addr);
         f0.owner = stage_a(base + 96u);
         base += 32u;
         if (base >= total) break;
         stage_b(base + 64u, f0);
-        count_pair<COUNTER>(p.civ, f1, stg, stg_pe, acc_addr);
+        count_pair<COUNTER, LONG>(p.civ, f1, stg, stg_pe, acc_addr);
         f1.owner = stage_a(base + 96u);
         base += 32u;
         if (base >= total) break;
         stage_b(base + 64u, f1);
-        count_pair<COUNTER>(p.civ, f2, stg, stg_pe, acc_addr);
+        count_pair<COUNTER, LONG>(p.civ, f2, stg, stg_pe, acc_addr);
         f2.owner = stage_a(base + 96u);
         base += 32u;
         if (base >= total) break;
     }
 }
 
-template <int COUNTER, bool DENSITY>
+template <int COUNTER, bool DENSITY, bool LONG>
 __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
                         }
                     }
                     // run B (its offsets were requested one turn ago), then B <- B'
-                    if (b.slot != NO_ITEM) run_item<COUNTER>(p, wc, b, acc_base + b.slot * ka * 4u);
+                    if (b.slot != NO_ITEM) run_item<COUNTER, LONG>(p, wc, b, acc_base + b.slot * ka * 4u);
                     b = nb;
                 }
             }
@@ -410,15 +413,21 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
     }
 }
 
+template <int COUNTER, bool DENSITY, bool LONG>
+static cudaError_t launch_count_tl(cudaStream_t st, const CountParams &p, int threads)
+{
+    const size_t smem = count_smem_bytes(p.schunk, p.ka, p.kgrp, threads, DENSITY);
+    cudaError_t e = cudaFuncSetAttribute(count_kernel<COUNTER, DENSITY, LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(p.n_groups, (p.n_samples + p.schunk - 1) / p.schunk);
+    count_kernel<COUNTER, DENSITY, LONG><<<grid, threads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 template <int COUNTER, bool DENSITY>
 static cudaError_t launch_count_t(cudaStream_t st, const CountParams &p, int threads)
 {
-    const size_t smem = count_smem_bytes(p.schunk, p.ka, p.kgrp, threads, DENSITY);
-    cudaError_t e = cudaFuncSetAttribute(count_kernel<COUNTER, DENSITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid(p.n_groups, (p.n_samples + p.schunk - 1) / p.schunk);
-    count_kernel<COUNTER, DENSITY><<<grid, threads, smem, st>>>(p);
-    return cudaGetLastError();
+    return p.has_long ? launch_count_tl<COUNTER, DENSITY, true>(st, p, threads) : launch_count_tl<COUNTER, DENSITY, false>(st, p, threads);
 }
 
 cudaError_t launch_count(cudaStream_t st, int counter, const CountParams &p, int threads)
@@ -531,7 +540,7 @@ __global__ void __launch_bounds__(256) bins_pass_kernel(BuildBinsParams p)
             const uint64_t pos = atomicAdd(cur + b, 1u);
             if (pos < p.capacity) {
                 p.cent[pos] = make_uint2(x, (min(y - x, ENTRY_LEN_MASK) << 12) | t);
-                if (y - x >= ENTRY_LEN_MASK) p.civ[pos] = make_uint2(x, y);      // only ever read for these
+                if (y - x >= ENTRY_LEN_MASK) { p.civ[pos] = make_uint2(x, y); *p.has_long = 1u; }     // only ever read for these
                 p.cprev[pos] = py;
             }
         }

@@ -67,6 +67,7 @@ struct CountParams {
     const uint2 *cent;
     const uint2 *civ;
     const uint32_t *cprev;
+    uint32_t has_long;              // the index holds intervals of >= 2^20 - 1 bases (their ends are read from civ[])
     uint32_t sentinel;              // index of the pair of entries that overlap nothing (= capacity, even; arrays hold capacity + 2)
     const uint32_t *key_ws_nseg;    // [n_keys] or NULL
     uint32_t n_annot, n_keys, n_groups, ka;   // ka = tracks per group
@@ -110,6 +111,7 @@ struct BuildBinsParams {
     uint32_t n_annot, n_keys, n_groups, ka;
     uint32_t a_begin, a_count;      // tracks this launch works on
     uint32_t *error;
+    uint32_t *has_long;             // out: set when an interval of >= 2^20 - 1 bases was filed
     unsigned long long *total;      // out: entries needed
 };
 size_t build_bins_scan_bytes(uint64_t n_boff);
