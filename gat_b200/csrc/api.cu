@@ -304,6 +304,7 @@ struct gatb_annotations {
     std::vector<KeyBins> h_keybins;
     DevBuf<KeyBins> keybins;
     DevBuf<uint32_t> boff;
+    DevBuf<uint4> brec;
     DevBuf<uint2> civ;
     DevBuf<uint2> cent;
     DevBuf<uint32_t> cprev;
@@ -336,7 +337,7 @@ static void build_params(const gatb_annotations *a, BuildBinsParams &bp)
 {
     memset(&bp, 0, sizeof(bp));
     bp.offs = a->src_offs; bp.start = a->src_start; bp.end = a->src_end; bp.n_intervals = a->n_intervals;
-    bp.keybins = a->keybins.p; bp.key_jmax = a->d_jmax.p; bp.jmax_all = a->jmax_all; bp.boff = a->boff.p; bp.n_boff = a->n_boff;
+    bp.keybins = a->keybins.p; bp.key_jmax = a->d_jmax.p; bp.jmax_all = a->jmax_all; bp.boff = a->boff.p; bp.brec = a->brec.p; bp.n_boff = a->n_boff;
     bp.cent = a->cent.p; bp.civ = a->civ.p; bp.cprev = a->cprev.p; bp.capacity = a->capacity;
     bp.n_annot = a->n_annot; bp.n_keys = a->n_keys; bp.n_groups = a->n_groups; bp.ka = a->ka;
     bp.a_begin = 0; bp.a_count = a->n_annot;
@@ -354,7 +355,7 @@ static cudaError_t annotations_build_finish(gatb_annotations *a, cudaStream_t st
     cudaError_t e;
     {
         ProfScope ps(ctx, PROF_OTHER, st);
-        ctx->launches += 5;                 // even, scan (2), total, fill, pad
+        ctx->launches += 6;                 // even, scan (2), total, fill, pad, records
         e = launch_bins_finish(st, bp, a->scan_tmp.p, a->scan_tmp.n);
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(slot, a->d_err.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
@@ -518,6 +519,7 @@ static int annotations_create_common(gatb_ctx *ctx, int n_annot, int n_keys, con
     if (e == cudaSuccess && key_ws_nseg) { e = a->key_ws_nseg.upload(key_ws_nseg, K, st); a->has_nseg = true; }
     if (e == cudaSuccess) e = a->d_jmax.upload(jmax.data(), K, st);
     if (e == cudaSuccess) e = a->boff.alloc(2 * (n_boff + 1));
+    if (e == cudaSuccess) e = a->brec.alloc(std::max<uint64_t>(n_boff, 1));
     if (e == cudaSuccess) e = a->civ.alloc(a->capacity + 2);
     if (e == cudaSuccess) e = a->cent.alloc(a->capacity + 2);
     if (e == cudaSuccess) e = a->cprev.alloc(a->capacity + 2);
@@ -619,7 +621,7 @@ extern "C" void gatb_annotations_destroy(gatb_annotations *a)
 static int count_params_annos(const gatb_annotations *a, uint32_t n_samples, bool density, CountParams &p)
 {
     gatb_ctx *ctx = a->ctx;
-    p.keybins = a->keybins.p; p.boff = a->boff.p; p.coff_base = a->n_boff + 1; p.cent = a->cent.p; p.civ = a->civ.p; p.cprev = a->cprev.p; p.sentinel = (uint32_t)a->capacity; p.has_long = a->has_long ? 1u : 0u;
+    p.keybins = a->keybins.p; p.boff = a->boff.p; p.coff_base = a->n_boff + 1; p.brec = a->brec.p; p.cent = a->cent.p; p.civ = a->civ.p; p.cprev = a->cprev.p; p.sentinel = (uint32_t)a->capacity; p.has_long = a->has_long ? 1u : 0u;
     p.key_ws_nseg = a->has_nseg ? a->key_ws_nseg.p : nullptr;
     p.n_annot = a->n_annot; p.n_keys = a->n_keys; p.n_groups = a->n_groups; p.ka = a->ka;
     p.n_samples = n_samples;
@@ -1377,7 +1379,7 @@ extern "C" int gatb_count_work(gatb_sampler *s, const gatb_annotations *annos, u
     CU(ctx, cudaStreamSynchronize(st));
     out[0] = h[0]; out[1] = h[1];
     out[2] = annos->n_entries;
-    out[3] = 2 * (annos->n_boff + 1) * sizeof(uint32_t) + annos->n_entries * sizeof(uint2);
+    out[3] = annos->n_boff * sizeof(uint4) + annos->n_entries * sizeof(uint2);
     return GATB_OK;
 }
 

@@ -312,8 +312,7 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
             const uint32_t n_items = pre_k[ns];
             if (n_items) {
                 const KeyBins kb = p.keybins[(uint64_t)g * p.n_keys + k];
-                const uint32_t *__restrict__ soff = p.boff + kb.base;
-                const uint32_t *__restrict__ coff = p.boff + p.coff_base + kb.base;
+                const uint4 *__restrict__ brec = p.brec + kb.base;
                 const uint64_t *__restrict__ placed_key = p.placed + p.key_base[k] + (uint64_t)s_begin * p.sample_stride;
                 // three items in flight: A = segment requested, B = bin offsets requested, then run
                 uint32_t a_slot = NO_ITEM, a_i = 0, a_n = 0, a_prev = 0;
@@ -333,8 +332,12 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
                             const uint32_t b0 = nb.s >> kb.shift;
                             if (b0 < kb.nbins) {
                                 const uint32_t b1 = min((nb.e - 1u) >> kb.shift, kb.nbins - 1u);
-                                nb.c0 = coff[b0]; nb.c1 = coff[b0 + 1u];
-                                nb.s0 = soff[b0]; nb.s1 = soff[b1 + 1u];
+                                // one 16-byte record holds the C list of b0 and the start of its S list (and the end
+                                // of the S run when the segment stays inside b0): 32 lanes = 32 scattered sectors per
+                                // load, so the NUMBER of loads per item is what the L1 data pipe pays for
+                                const uint4 r0 = brec[b0];
+                                nb.c0 = r0.x; nb.c1 = r0.y; nb.s0 = r0.z;
+                                nb.s1 = (b1 == b0) ? r0.w : brec[b1].w;
                             }
                         }
                         if (NeedPrevSegment<COUNTER>::value) {
@@ -567,6 +570,16 @@ __global__ void __launch_bounds__(256) bins_pad_kernel(BuildBinsParams p)
     }
 }
 
+// what the counting kernel reads per segment: one 16-byte record per bin,
+//   { start of C[b], end of C[b], start of S[b], end of S[b] }     (b1 > b0: the end of the S run is rec[b1].w)
+__global__ void __launch_bounds__(256) bins_rec_kernel(BuildBinsParams p)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_boff) return;
+    const uint32_t *soff = p.boff, *coff = p.boff + p.n_boff + 1u;
+    p.brec[i] = make_uint4(coff[i], coff[i + 1u], soff[i], soff[i + 1u]);
+}
+
 __global__ void bins_total_kernel(BuildBinsParams p)
 {
     // the scan ran over both halves, 2 * (n_boff + 1) elements: the last one (a slot without a list) is the
@@ -611,6 +624,7 @@ cudaError_t launch_bins_finish(cudaStream_t st, const BuildBinsParams &p, void *
         bins_pass_kernel<true><<<blocks, 256, 0, st>>>(p);
         bins_pad_kernel<<<nb, 256, 0, st>>>(p);
     }
+    if (p.n_boff) bins_rec_kernel<<<(unsigned)((p.n_boff + 255) / 256), 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -32,6 +32,9 @@ constexpr uint32_t ENTRY_LEN_MASK = 0xfffffu;
 //   uint32  boff[2 * (n_boff + 1)]       first half: per (group, key) nbins+1 offsets of the S lists, second half
 //                                        (at boff + n_boff + 1): of the C lists; absolute, into the arrays below
 //                                        (all S lists first, then all C lists)
+//   uint4   brec[n_boff]                 the offsets again, as the counting kernel reads them: one 16-byte record per
+//                                        bin {C start, C end, S start, S end} = one load per segment (two when the
+//                                        segment leaves its first bin)
 //   uint2   cent[n_entries]              the entry the counting kernel streams, 8 bytes:
 //                                          .x = start,  .y = min(length, 2^20-1)<<12 | slot
 //                                        (slot = track within the group, < 4096; a length field of 2^20-1
@@ -64,6 +67,7 @@ struct CountParams {
     const KeyBins *keybins;         // [n_groups][n_keys]
     const uint32_t *boff;           // S offsets; the C offsets follow at boff + coff_base
     uint64_t coff_base;             // = n_boff + 1
+    const uint4 *brec;              // the same offsets as one record per bin: {C start, C end, S start, S end}
     const uint2 *cent;
     const uint2 *civ;
     const uint32_t *cprev;
@@ -102,6 +106,7 @@ struct BuildBinsParams {
     const KeyBins *keybins;         // [n_groups][n_keys]
     const uint32_t *key_jmax;       // [n_keys] longest list (over all tracks) on the key
     uint32_t jmax_all;              // largest of them
+    uint4 *brec;                    // [n_boff] out: per-bin records for the counting kernel
     uint32_t *boff;                 // [2 * (n_boff + 1)], zeroed by the caller: S half, then C half
     uint64_t n_boff;                // offset slots of one half: sum over (group, key) of nbins + 1
     uint2 *cent;
