@@ -313,6 +313,8 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
             if (n_items) {
                 const KeyBins kb = p.keybins[(uint64_t)g * p.n_keys + k];
                 const uint4 *__restrict__ brec = p.brec + kb.base;
+                const uint32_t *__restrict__ soff = p.boff + kb.base;
+                const uint32_t *__restrict__ coff = p.boff + p.coff_base + kb.base;
                 const uint64_t *__restrict__ placed_key = p.placed + p.key_base[k] + (uint64_t)s_begin * p.sample_stride;
                 // three items in flight: A = segment requested, B = bin offsets requested, then run
                 uint32_t a_slot = NO_ITEM, a_i = 0, a_n = 0, a_prev = 0;
@@ -332,12 +334,19 @@ __global__ void __launch_bounds__(1024, 1) count_kernel(CountParams p)
                             const uint32_t b0 = nb.s >> kb.shift;
                             if (b0 < kb.nbins) {
                                 const uint32_t b1 = min((nb.e - 1u) >> kb.shift, kb.nbins - 1u);
-                                // one 16-byte record holds the C list of b0 and the start of its S list (and the end
-                                // of the S run when the segment stays inside b0): 32 lanes = 32 scattered sectors per
-                                // load, so the NUMBER of loads per item is what the L1 data pipe pays for
+                                // ONE 16-byte record per segment (count.cuh): 32 lanes = 32 scattered sectors per
+                                // load, so the NUMBER of loads per item is what the L1 data pipe pays for.  A
+                                // segment reaching beyond b0 + 2, or a list too long for the 16-bit fields, reads
+                                // the plain offset arrays instead (few lanes, rarely)
                                 const uint4 r0 = brec[b0];
-                                nb.c0 = r0.x; nb.c1 = r0.y; nb.s0 = r0.z;
-                                nb.s1 = (b1 == b0) ? r0.w : brec[b1].w;
+                                const uint32_t d = b1 - b0;
+                                const uint32_t len_c = r0.z & 0xffffu;
+                                const uint32_t len_s = d == 0u ? (r0.z >> 16) : d == 1u ? (r0.w & 0xffffu) : (r0.w >> 16);
+                                nb.c0 = r0.x; nb.c1 = r0.x + len_c; nb.s0 = r0.y; nb.s1 = r0.y + len_s;
+                                if (d > 2u || len_c == 0xffffu || len_s == 0xffffu) {
+                                    nb.c1 = coff[b0 + 1u];
+                                    nb.s1 = soff[b1 + 1u];
+                                }
                             }
                         }
                         if (NeedPrevSegment<COUNTER>::value) {
@@ -570,14 +579,20 @@ __global__ void __launch_bounds__(256) bins_pad_kernel(BuildBinsParams p)
     }
 }
 
-// what the counting kernel reads per segment: one 16-byte record per bin,
-//   { start of C[b], end of C[b], start of S[b], end of S[b] }     (b1 > b0: the end of the S run is rec[b1].w)
+// what the counting kernel reads per segment: one 16-byte record per bin b,
+//   .x = start of C[b]   .y = start of S[b]   .z = |C[b]| | |S[b]| << 16   .w = |S[b..b+1]| | |S[b..b+2]| << 16
+// (lengths in entries, 0xffff: does not fit -- read the offset arrays): a segment covering bins b0 .. b0 + 2 finds
+// both of its runs in the record of b0
 __global__ void __launch_bounds__(256) bins_rec_kernel(BuildBinsParams p)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_boff) return;
     const uint32_t *soff = p.boff, *coff = p.boff + p.n_boff + 1u;
-    p.brec[i] = make_uint4(coff[i], coff[i + 1u], soff[i], soff[i + 1u]);
+    const uint64_t last = p.n_boff;                 // (offsets exist up to index n_boff; lists of one key are contiguous,
+    const uint32_t s0 = soff[i];                    //  lengths that run into the next key are never used: b1 < nbins)
+    auto fit = [](uint32_t v) { return v < 0xffffu ? v : 0xffffu; };
+    const uint32_t l0 = fit(soff[min(i + 1u, last)] - s0), l1 = fit(soff[min(i + 2u, last)] - s0), l2 = fit(soff[min(i + 3u, last)] - s0);
+    p.brec[i] = make_uint4(coff[i], s0, fit(coff[i + 1u] - coff[i]) | (l0 << 16), l1 | (l2 << 16));
 }
 
 __global__ void bins_total_kernel(BuildBinsParams p)

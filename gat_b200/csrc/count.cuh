@@ -33,8 +33,8 @@ constexpr uint32_t ENTRY_LEN_MASK = 0xfffffu;
 //                                        (at boff + n_boff + 1): of the C lists; absolute, into the arrays below
 //                                        (all S lists first, then all C lists)
 //   uint4   brec[n_boff]                 the offsets again, as the counting kernel reads them: one 16-byte record per
-//                                        bin {C start, C end, S start, S end} = one load per segment (two when the
-//                                        segment leaves its first bin)
+//                                        bin {C start, S start, |C| and |S[b]|, |S[b..b+1]| and |S[b..b+2]|} (16-bit
+//                                        lengths) = ONE load per segment unless it spans more than three bins
 //   uint2   cent[n_entries]              the entry the counting kernel streams, 8 bytes:
 //                                          .x = start,  .y = min(length, 2^20-1)<<12 | slot
 //                                        (slot = track within the group, < 4096; a length field of 2^20-1
@@ -67,7 +67,7 @@ struct CountParams {
     const KeyBins *keybins;         // [n_groups][n_keys]
     const uint32_t *boff;           // S offsets; the C offsets follow at boff + coff_base
     uint64_t coff_base;             // = n_boff + 1
-    const uint4 *brec;              // the same offsets as one record per bin: {C start, C end, S start, S end}
+    const uint4 *brec;              // the same offsets as one packed record per bin (bins_rec_kernel)
     const uint2 *cent;
     const uint2 *civ;
     const uint32_t *cprev;
