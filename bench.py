@@ -402,7 +402,12 @@ def run_ours(args):
         # the gathered matrix of a step lives in memory every rank can write: each rank's counting kernels store
         # their rows into all of them (two matrices, used alternately like the NCCL slabs)
         from gat_b200 import parallel
-        peers = [parallel.PeerMatrix(ctx, 1, world * S, A) for _ in range(nbuf)]
+        try:
+            peers = [parallel.PeerMatrix(ctx, 1, world * S, A) for _ in range(nbuf)]
+        except parallel.PeerUnavailable as e:      # (raised on every rank alike): the collective route instead
+            sys.stderr.write("bench: %s -- falling back to --gather nccl\n" % e)
+            peer, args.gather = False, "nccl"
+    if peer:
         gathers = [pm.tensor[0] for pm in peers]
         outs = [g[rank * S:(rank + 1) * S] for g in gathers]
         routes = [[dict(base=pm.pointer(r), row_stride=A, row0=rank * S, col_begin=0, col_end=A) for r in range(world)]

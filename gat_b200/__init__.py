@@ -244,7 +244,13 @@ def _run(segments, annotations, workspace, sampler, counters, workspace_generato
         if transport == "peer":
             # every rank's destination matrix, writable by all: [counter][S][all columns | its own columns]
             width = (col_end - col_begin) if exchange == "columns" else n_atracks
-            peer = parallel.PeerMatrix(ctx, len(counters), num_samples, max(width, 1))
+            try:
+                peer = parallel.PeerMatrix(ctx, len(counters), num_samples, max(width, 1))
+            except parallel.PeerUnavailable as e:       # (raised on every rank alike)
+                if rank == 0:
+                    sys.stderr.write("# gat_b200.run: %s -- using the NCCL transport\n" % e)
+                transport = "nccl"
+        if transport == "peer":
             routes = []
             for r in range(world):
                 cb, ce = parallel.column_range(n_atracks, r, world) if exchange == "columns" else (0, n_atracks)

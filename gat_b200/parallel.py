@@ -110,6 +110,10 @@ def allgather_columns(local, n_columns):
     return torch.cat([pieces[r][..., :widths[r]] for r in range(world)], dim=-1)
 
 
+class PeerUnavailable(RuntimeError):
+    """the GPUs of this job cannot map each other's memory (no peer access / IPC): use the NCCL transport"""
+
+
 class PeerMatrix(object):
     """One uint32 matrix [planes][rows][cols] per rank in memory that every other rank of the box can write
     (CUDA IPC over NVLink / NVSwitch): the destination of the counting kernel's output routes, i.e. of an exchange
@@ -126,17 +130,47 @@ class PeerMatrix(object):
         self.ctx = ctx
         self.rank, self.world = rank_world()
         self.shape = (int(planes), int(rows), int(cols))
+        self.ptrs = None
         nbytes = max(4 * planes * rows * cols, 4)
-        self.local_ptr, handle = ctx.peer_alloc(nbytes)
+        # every step is agreed on by all ranks, so that a GPU pair without peer access makes ALL of them raise
+        # PeerUnavailable (and take the NCCL route) instead of leaving some waiting in a collective
+        try:
+            self.local_ptr, handle = ctx.peer_alloc(nbytes)
+        except Exception as e:      # noqa: BLE001
+            self.local_ptr, handle = None, None
+            why = str(e)
         everyone = [None] * self.world
         if self.world > 1:
             dist.all_gather_object(everyone, (handle, self.shape))
         else:
             everyone[0] = (handle, self.shape)
+        if any(h is None for h, _ in everyone):
+            if self.local_ptr is not None:
+                ctx.peer_free(self.local_ptr)
+            raise PeerUnavailable("shareable device memory could not be allocated on every rank" +
+                                  (": " + why if handle is None else ""))
         self.shapes = [s for _, s in everyone]
-        self.ptrs = []
+        ptrs, why = [], None
         for r, (h, _) in enumerate(everyone):
-            self.ptrs.append(self.local_ptr if r == self.rank else ctx.peer_open(h))
+            try:
+                ptrs.append(self.local_ptr if r == self.rank else ctx.peer_open(h))
+            except Exception as e:  # noqa: BLE001
+                why = str(e)
+                break
+        oks = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(oks, why is None)
+        else:
+            oks[0] = why is None
+        if not all(oks):
+            for r, p in enumerate(ptrs):
+                if r != self.rank:
+                    ctx.peer_close(p)
+            if self.world > 1:
+                dist.all_gather_object(oks, True)      # (nobody frees memory a peer still has mapped)
+            ctx.peer_free(self.local_ptr)
+            raise PeerUnavailable("peer memory could not be mapped between all GPUs" + (": " + why if why else ""))
+        self.ptrs = ptrs
         self.tensor = self._as_tensor()
 
     def _as_tensor(self):
