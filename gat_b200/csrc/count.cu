@@ -46,6 +46,12 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr)
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 {
     uint32_t v;
@@ -134,7 +140,10 @@ template <int COUNTER, bool LONG>
 __device__ __forceinline__ void count_pair(const uint2 *__restrict__ civ, const Flight &f, uint32_t stg, uint32_t stg_pe,
                                            uint32_t acc_addr)
 {
-    const uint4 o = lds128(stg + f.owner * 16u);
+    // (the segment is the first 8 bytes of the run's staging slot: an 8-byte shared load is 2 data-pipe wavefronts
+    // for a warp, a 16-byte one 4 -- and that pipe is what the kernel saturates)
+    const uint2 so = lds64(stg + f.owner * 16u);
+    const uint4 o = make_uint4(so.x, so.y, 0u, 0u);
     uint32_t pe = 0;
     if (NeedPrevSegment<COUNTER>::value) pe = lds32(stg_pe + f.owner * 4u);
     // end = start + length; a length field of 2^20 - 1 sends us to civ[] for the end.  LONG = false: the index

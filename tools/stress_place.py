@@ -44,13 +44,50 @@ if "--shift" in sys.argv:          # SamplerShift instead: python tools/stress_p
     ctx.close()
     sys.exit(0)
 
+def fragmented_unit(rng):
+    """a unit whose workspace has many pieces (8 .. 600: clustered, evenly tiled or with huge gaps) -- the shapes that
+    search the pieces through the bucket tables (common.cuh WS_NB)"""
+    from gat_b200.segmentlist import SegmentList
+    while True:
+        npieces = int(rng.choice([8, 9, 31, 64, 160, 257, 600]))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:                       # tiles with random gaps
+            gaps = rng.integers(1, 30000, npieces)
+            lens = rng.integers(1, 20000, npieces)
+        elif kind == 1:                     # two far-apart clusters of small pieces
+            gaps = rng.integers(1, 300, npieces)
+            gaps[npieces // 2] = int(rng.integers(10 ** 6, 10 ** 8))
+            lens = rng.integers(200, 3000, npieces)
+        else:                               # a few huge pieces among tiny ones
+            gaps = rng.integers(1, 2000, npieces)
+            lens = rng.integers(1, 50, npieces)
+            lens[rng.integers(0, npieces, 3)] = rng.integers(10 ** 5, 10 ** 7, 3)
+        start = np.cumsum(gaps + np.concatenate([[0], lens[:-1]]))
+        ws = np.stack([start, start + lens], axis=1).astype(np.uint32)
+        span = int(ws[-1, 1])
+        if span >= 2 ** 31 - 10 ** 5:
+            continue
+        n = int(rng.integers(1, 120))
+        pos = rng.integers(0, span, n)
+        ln = rng.integers(1, int(rng.choice([50, 500, 5000])) + 1, n)
+        segs = helpers.normalize(np.stack([pos, pos + ln], axis=1))
+        t = SegmentList(array=segs); t._normalized = True
+        w = SegmentList(array=ws); w._normalized = True
+        t.filter(w)
+        if len(t):
+            return segs, ws
+
+
+fragmented = "--fragmented" in sys.argv      # python tools/stress_place.py --fragmented [n_units] [seed]
+if fragmented:
+    sys.argv.remove("--fragmented")
 n_units = int(sys.argv[1]) if len(sys.argv) > 1 else 600
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 2024
 rng = np.random.default_rng(seed0)
 ctx = device.Context(0)
 ntrim = ncp = nround = 0
 for it in range(n_units):
-    segs, ws = helpers.random_unit(rng)
+    segs, ws = fragmented_unit(rng) if fragmented else helpers.random_unit(rng)
     bucket = int(rng.choice([1, 1, 1, 3, 7]))
     smp = device.Sampler(ctx, [0], 1, False, [segs], [ws], bucket_size=bucket, nbuckets=100000)
     n = 8
@@ -64,6 +101,6 @@ for it in range(n_units):
         if not np.array_equal(placed[s][0], exp):
             print("MISMATCH unit %i sample %i" % (it, s), placed[s][0][:4], exp[:4])
             sys.exit(1)
-print("ok: %i units x 8 samples identical to the oracle (%i trims, %i checkpoints, %i round caps)"
-      % (n_units, ntrim, ncp, nround))
+print("ok: %i %sunits x 8 samples identical to the oracle (%i trims, %i checkpoints, %i round caps)"
+      % (n_units, "fragmented-workspace " if fragmented else "", ntrim, ncp, nround))
 ctx.close()
