@@ -29,6 +29,7 @@ roofline  dominant kernel (counting), see roofline_of(): output-sensitive bytes 
 cpu_baseline  the reference itself (oracle/_ref) on the host cores, bounded sample, rank 0, N=1
 """
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -78,9 +79,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-checks", action="store_true")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: how the per-step count slabs reach every rank -- peer: the counting kernel stores its "
-                         "rows into every rank's matrix over NVLink (output routes); nccl: all_gather_into_tensor")
+    ap.add_argument("--e2e-device-path", action="store_true",
+                    help="diagnostic: at N = 1 run the e2e leg the way N > 1 does (device output, side-stream read-back)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "peer-kernel", "nccl"],
+                    help="N > 1: how the per-step count slabs reach every rank -- peer: output routes into every rank's "
+                         "matrix over NVLink, served by copy engines behind the next batch; peer-kernel: the same routes "
+                         "served by the counting kernel's own stores; nccl: all_gather_into_tensor")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     for k in ("segments", "annotations", "counter", "isochores"):
@@ -121,8 +125,9 @@ def config_of(args, wl, world):
             "batch": args.batch, "batches_per_step": args.batches_per_step,
             "global_samples_per_step": args.samples_per_step * world,
             "parallelism": ("samples sharded over %i GPU(s), inputs replicated; exchange per step: %s" % (world, (
-                "the counting kernel's epilogue stores every finished row into every rank's [N x samples][tracks] matrix "
-                "(CUDA IPC peer memory over NVLink, gatb_set_output_routes) -- no collective" if args.gather == "peer" else
+                "output routes (gatb_set_output_routes) into every rank's [N x samples][tracks] matrix in CUDA IPC peer "
+                "memory over NVLink -- no collective; served by " + ("the counting kernel's own stores" if
+                args.gather == "peer-kernel" else "copy engines while the next batch runs") if args.gather != "nccl" else
                 "one NCCL all_gather_into_tensor of the count slab, overlapping the next step's kernels"))) if world > 1 else "1 GPU",
             "l2": "inputs larger than L2: annotation grid index ~%.0f MB + %.0f MB of placed segments per batch; "
                   "sample indices advance every step"
@@ -393,8 +398,8 @@ def run_ours(args):
     smp = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(wl["seg_csr"], wl["ws_csr"]))
     # two output slabs, used alternately: for N > 1 the all-gather of step i (NCCL, asynchronous, its own stream)
     # overlaps the placement and counting of step i + 1, which write the other slab
-    nbuf = 2 if world > 1 else 1
-    peer = world > 1 and args.gather == "peer" and not is_density
+    nbuf = 2 if (world > 1 or args.e2e_device_path) else 1
+    peer = world > 1 and args.gather != "nccl" and not is_density
     if world > 1 and not peer:
         args.gather = "nccl"
     pending = [None] * nbuf
@@ -408,6 +413,7 @@ def run_ours(args):
             sys.stderr.write("bench: %s -- falling back to --gather nccl\n" % e)
             peer, args.gather = False, "nccl"
     if peer:
+        ctx.set_route_mode(args.gather == "peer-kernel")
         gathers = [pm.tensor[0] for pm in peers]
         outs = [g[rank * S:(rank + 1) * S] for g in gathers]
         routes = [[dict(base=pm.pointer(r), row_stride=A, row0=rank * S, col_begin=0, col_end=A) for r in range(world)]
@@ -556,12 +562,23 @@ def run_ours(args):
             # i, so they overlap its placement and counting kernels (copy engine + build stream next to the
             # compute stream); gatb_run(i) only waits for ITS set before launching the count.  The first
             # step's upload is not hidden behind anything and is inside the timed region like the others.
+            tm = collections.Counter()
+            clock = [time.perf_counter()]
+
+            def lap(name):                          # host-side phase times of the loop (GATB_BENCH_TRACE=1: on stderr)
+                now = time.perf_counter()
+                tm[name] += now - clock[0]
+                clock[0] = now
+
             nxt = e2e_upload()
+            lap("upload")
             for j in range(n):
                 a2, nxt = nxt, (e2e_upload() if j + 1 < n else None)
+                lap("upload")
                 s2 = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(ps, pw))
+                lap("sampler")
                 begin = step_begin(first + j)
-                if world == 1:
+                if world == 1 and not args.e2e_device_path:
                     # host in, host out: gatb_run copies every batch's counts to the pinned host matrix while
                     # the next batch is being placed and counted
                     ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), SEED, 0, begin, S,
@@ -574,28 +591,41 @@ def run_ours(args):
                     b = j % nbuf
                     if copied[b] is not None:
                         copied[b].synchronize()     # the copy that last read this matrix / wrote this host buffer
+                    lap("wait copy")
                     if peer:
                         ctx.set_output_routes(routes[b])
                     ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), SEED, 0, begin, S,
                                                None if is_density else outs[b].data_ptr(),
                                                outs[b].data_ptr() if is_density else None, 1, device._p(info_np)))
+                    lap("run")
                     if peer:
                         barrier()           # every rank's rows have arrived in every matrix
-                    else:
+                    elif world > 1:
                         dist.all_gather_into_tensor(gathers[b], outs[b])
+                    lap("exchange")
                     side.wait_stream(torch.cuda.current_stream(dev))
                     with torch.cuda.stream(side):
-                        host_outs[b].copy_(gathers[b][rank * S:(rank + 1) * S], non_blocking=True)
+                        src = gathers[b][rank * S:(rank + 1) * S] if world > 1 else outs[b]
+                        # (batch-sized pieces: one 393 MB copy would hold the device-to-host engine for 8 ms, and
+                        # the next step's small read-backs -- unit descriptors, validation words -- queue behind it)
+                        for k in range(0, S, args.batch):
+                            host_outs[b][k:k + args.batch].copy_(src[k:k + args.batch], non_blocking=True)
                         copied[b] = torch.cuda.Event()
                         copied[b].record(side)
+                lap("run" if world == 1 else "read-back queue")
                 s2.close()
                 a2.close()
+                lap("close")
             for ev in copied:
                 if ev is not None:
                     ev.synchronize()
+            lap("wait copy")
+            if os.environ.get("GATB_BENCH_TRACE") and rank == 0:
+                sys.stderr.write("e2e host phases over %i steps (ms per step): %s\n"
+                                 % (n, ", ".join("%s %.2f" % (k, 1e3 * v / n) for k, v in tm.items())))
             return int(host_np.reshape(-1)[:1].view(np.uint8)[0])
 
-        if world == 1:
+        if world == 1 and not args.e2e_device_path:
             ctx.set_stream(None)                    # host in / host out: the context's own stream
         # (step indices continue after the device-resident steps: global sample indices stay far below 2^32)
         e2e_first = last + 8

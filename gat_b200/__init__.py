@@ -342,9 +342,10 @@ def _run(segments, annotations, workspace, sampler, counters, workspace_generato
                 matrix = Engine.SampleMatrix(plane, True, first_column=lo)
             if exchange == "columns" and out_u is not None:
                 # the result doubles of every rank's columns: one small all-gather
+                # (host tensors: a few kB over the gloo side of the process group -- no NCCL set-up for this)
                 keys6 = ("expected", "stddev", "lower95", "upper95", "fold", "pvalue")
-                mine = torch.from_numpy(np.stack([st[k] for k in keys6])).to(torch.device("cuda", ctx.device))
-                full = parallel.allgather_columns(mine, len(atracks)).cpu().numpy()
+                mine = torch.from_numpy(np.stack([st[k] for k in keys6]))
+                full = parallel.allgather_columns(mine, len(atracks)).numpy()
                 st = dict((k, full[i]) for i, k in enumerate(keys6))
             for ai, annotation in enumerate(atracks):
                 if annotation not in annos_in_result:

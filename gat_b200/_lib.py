@@ -27,7 +27,7 @@ SYMBOLS = [
     "gatb_lists_from_rows", "gatb_lists_from_csr", "gatb_lists_restrict", "gatb_lists_collapse", "gatb_lists_select",
     "gatb_lists_info", "gatb_lists_sizes", "gatb_lists_download", "gatb_lists_destroy",
     "gatb_annotations_create_from_lists",
-    "gatb_set_output_routes", "gatb_peer_alloc", "gatb_peer_free", "gatb_peer_open", "gatb_peer_close",
+    "gatb_set_output_routes", "gatb_set_route_mode", "gatb_peer_alloc", "gatb_peer_free", "gatb_peer_open", "gatb_peer_close",
 ]
 
 
@@ -141,6 +141,8 @@ def load():
     L.gatb_annotations_create_from_lists.argtypes = [vp, vp, i32, i32, vp, ctypes.POINTER(vp)]
     L.gatb_set_output_routes.restype = i32
     L.gatb_set_output_routes.argtypes = [vp, i32, vp]
+    L.gatb_set_route_mode.restype = i32
+    L.gatb_set_route_mode.argtypes = [vp, i32]
     L.gatb_peer_alloc.restype = i32
     L.gatb_peer_alloc.argtypes = [vp, u64, ctypes.POINTER(vp), vp]
     L.gatb_peer_free.restype = i32

@@ -140,6 +140,10 @@ class Context(object):
                                 int(r["col_begin"]), int(r["col_end"]))
         self.check(self.lib.gatb_set_output_routes(self.handle, len(routes), ctypes.byref(arr)))
 
+    def set_route_mode(self, by_kernel):
+        """False (default): copy engines scatter a staging slab to the routes; True: the kernel's epilogue stores to them"""
+        self.check(self.lib.gatb_set_route_mode(self.handle, int(bool(by_kernel))))
+
     def peer_alloc(self, nbytes):
         """shareable device memory -> (pointer, 64-byte IPC handle)"""
         ptr = ctypes.c_void_p()

@@ -253,24 +253,29 @@ def test_output_routes_deliver_rows_and_column_blocks(ctx, oracle):
     full = torch.full((2, S + 7, A), -1, dtype=torch.int32, device=dev)         # rows 5 .. 5 + S of a taller matrix
     left = torch.full((2, S, 4), -1, dtype=torch.int32, device=dev)             # columns 0..3
     right = torch.full((2, S, 7), -1, dtype=torch.int32, device=dev)            # columns 4..10
-    ctx.set_batch_size(16)                                                      # 4 internal batches
-    ctx.set_output_routes([
-        dict(base=full.data_ptr(), plane_stride=(S + 7) * A, row_stride=A, row0=5, col_begin=0, col_end=A),
-        dict(base=left.data_ptr(), plane_stride=S * 4, row_stride=4, row0=0, col_begin=0, col_end=4),
-        dict(base=right.data_ptr(), plane_stride=S * 7, row_stride=7, row0=0, col_begin=4, col_end=A)])
-    try:
-        smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S, out_counts_ptr=full.data_ptr())
-        with pytest.raises(_lib.GatB200Error):          # routes deliver to device memory only
-            smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S)
-    finally:
-        ctx.set_output_routes([])
-        ctx.set_batch_size(0)
-    torch.cuda.synchronize()
-    for i, n in enumerate(names):
-        w = want[n].astype(np.int64)
-        assert np.array_equal(full[i, 5:5 + S].cpu().numpy(), w), n
-        assert (full[i, :5] == -1).all() and (full[i, 5 + S:] == -1).all()
-        assert np.array_equal(left[i].cpu().numpy(), w[:, :4]) and np.array_equal(right[i].cpu().numpy(), w[:, 4:]), n
+    routes = [dict(base=full.data_ptr(), plane_stride=(S + 7) * A, row_stride=A, row0=5, col_begin=0, col_end=A),
+              dict(base=left.data_ptr(), plane_stride=S * 4, row_stride=4, row0=0, col_begin=0, col_end=4),
+              dict(base=right.data_ptr(), plane_stride=S * 7, row_stride=7, row0=0, col_begin=4, col_end=A)]
+    for by_kernel, batch in ((False, 16), (True, 16), (False, 0)):      # copy engines / kernel stores; 4 batches / 1
+        for t in (full, left, right):
+            t.fill_(-1)
+        ctx.set_batch_size(batch)
+        ctx.set_route_mode(by_kernel)
+        ctx.set_output_routes(routes)
+        try:
+            smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S, out_counts_ptr=full.data_ptr())
+            with pytest.raises(_lib.GatB200Error):          # routes deliver to device memory only
+                smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S)
+        finally:
+            ctx.set_output_routes([])
+            ctx.set_route_mode(False)
+            ctx.set_batch_size(0)
+        torch.cuda.synchronize()
+        for i, n in enumerate(names):
+            w = want[n].astype(np.int64)
+            assert np.array_equal(full[i, 5:5 + S].cpu().numpy(), w), (by_kernel, n)
+            assert (full[i, :5] == -1).all() and (full[i, 5 + S:] == -1).all()
+            assert np.array_equal(left[i].cpu().numpy(), w[:, :4]) and np.array_equal(right[i].cpu().numpy(), w[:, 4:]), n
     again, _ = smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S)    # routes cleared: plain output
     assert np.array_equal(again[names[0]], want[names[0]])
     smp.close()
