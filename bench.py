@@ -573,10 +573,12 @@ def run_ours(args):
             nxt = e2e_upload()
             lap("upload")
             for j in range(n):
-                a2, nxt = nxt, (e2e_upload() if j + 1 < n else None)
-                lap("upload")
+                # (the sampler first: its small uploads and read-backs must not queue behind the next step's 159 MB of
+                # annotation arrays on the copy engine)
                 s2 = device.Sampler(ctx, pr.unit_contig, C, pr.has_isochores, None, None, csr=(ps, pw))
                 lap("sampler")
+                a2, nxt = nxt, (e2e_upload() if j + 1 < n else None)
+                lap("upload")
                 begin = step_begin(first + j)
                 if world == 1 and not args.e2e_device_path:
                     # host in, host out: gatb_run copies every batch's counts to the pinned host matrix while
@@ -584,23 +586,29 @@ def run_ours(args):
                     ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), SEED, 0, begin, S,
                                                None if is_density else device._p(host_np.view(np.uint32)),
                                                device._p(host_np) if is_density else None, 0, device._p(info_np)))
+                elif peer:
+                    # N > 1, peer exchange: one gatb_run delivers every batch's rows to the pinned host matrix AND, through
+                    # the output routes, to every rank's device matrix (copy engines, behind the next batch's kernels)
+                    b = j % nbuf
+                    ctx.set_output_routes(routes[b])
+                    ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), SEED, 0, begin, S,
+                                               device._p(host_outs[b].numpy().view(np.uint32)), None, 0, device._p(info_np)))
+                    lap("run")
+                    barrier()               # every rank's rows have arrived in every matrix
+                    lap("exchange")
                 else:
-                    # N > 1: counts stay on the device for the exchange; every rank then reads ITS rows of the
+                    # N > 1, NCCL: counts stay on the device for the all-gather; every rank then reads ITS rows of the
                     # gathered matrix back to the host -- on a side stream, while the next step already runs
                     # (two device matrices and two pinned host matrices, used alternately)
                     b = j % nbuf
                     if copied[b] is not None:
                         copied[b].synchronize()     # the copy that last read this matrix / wrote this host buffer
                     lap("wait copy")
-                    if peer:
-                        ctx.set_output_routes(routes[b])
                     ctx.check(ctx.lib.gatb_run(s2.handle, a2.handle, 1, device._p(ids), SEED, 0, begin, S,
                                                None if is_density else outs[b].data_ptr(),
                                                outs[b].data_ptr() if is_density else None, 1, device._p(info_np)))
                     lap("run")
-                    if peer:
-                        barrier()           # every rank's rows have arrived in every matrix
-                    elif world > 1:
+                    if world > 1:
                         dist.all_gather_into_tensor(gathers[b], outs[b])
                     lap("exchange")
                     side.wait_stream(torch.cuda.current_stream(dev))
@@ -644,7 +652,8 @@ def run_ours(args):
                "what": "per step of %i samples per GPU: gatb_sampler_create + gatb_annotations_create_async (every input "
                        "from pinned host memory, on every rank) + gatb_run%s + the step's count matrix read back to "
                        "pinned host memory; double-buffered: the upload + index build of step i+1 overlap the "
-                       "kernels of step i" % (S, (" + exchange of the slab (%s) + barrier" % args.gather) if world > 1 else
+                       "kernels of step i" % (S, (" (host output AND output routes into every rank's peer matrix) + barrier" if peer else
+                                                  " + NCCL all-gather of the slab + side-stream read-back") if world > 1 else
                                               " (host output: the copy of batch i overlaps batch i+1)")}
 
     cpu = None

@@ -616,8 +616,8 @@ static int annotations_create_common(gatb_ctx *ctx, int n_annot, int n_keys, con
     if (from_device) { a->src_offs = dev_offs; a->src_start = dev_start; a->src_end = dev_end; }
     else {
         if (e == cudaSuccess) e = a->d_offs.upload(offs, n_lists + 1, st);
-        if (e == cudaSuccess) e = a->d_start.alloc(n_iv);
-        if (e == cudaSuccess) e = a->d_end.alloc(n_iv);
+        if (e == cudaSuccess) e = a->d_start.alloc_cached(ctx->blocks, n_iv);
+        if (e == cudaSuccess) e = a->d_end.alloc_cached(ctx->blocks, n_iv);
         a->src_offs = a->d_offs.p; a->src_start = a->d_start.p; a->src_end = a->d_end.p;
     }
     if (e == cudaSuccess) e = a->d_err.alloc(2);
@@ -1364,7 +1364,7 @@ static int run_once(gatb_sampler *s, const gatb_annotations *annos, int n_counte
             double *dst_f = out_density ? out_density + done * A : nullptr;
             const int slab = (int)(n_staged % (uint64_t)n_stage);
             p.n_routes = 0;
-            if (!dens && routed && !ctx->route_copy) {
+            if (!dens && routed && !ctx->route_copy && out_is_device) {
                 p.n_routes = (uint32_t)ctx->routes.size();
                 for (uint32_t r = 0; r < p.n_routes; r++) {
                     const gatb_route &g = ctx->routes[r];
@@ -1394,7 +1394,7 @@ static int run_once(gatb_sampler *s, const gatb_annotations *annos, int n_counte
                     CU(ctx, cudaEventRecord(ctx->ev_counted[slab], st));
                     CU(ctx, cudaStreamWaitEvent(cs, ctx->ev_counted[slab], 0));
                 }
-                if (out_is_device) {
+                if (routed && !dens) {
                     // the rows of this batch to every route: columns [col_begin, col_end) of the slab -> the route's rows
                     for (const gatb_route &g : ctx->routes) {
                         const uint32_t ce = std::min(g.col_end, A);
@@ -1404,8 +1404,10 @@ static int run_once(gatb_sampler *s, const gatb_annotations *annos, int n_counte
                                                   (size_t)A * sizeof(uint32_t), (size_t)(ce - g.col_begin) * sizeof(uint32_t), b,
                                                   cudaMemcpyDeviceToDevice, cs));
                     }
-                } else if (dens) CU(ctx, cudaMemcpyAsync(dst_f, sc->out_tmp_f[slab].p, (uint64_t)b * A * sizeof(double), cudaMemcpyDeviceToHost, cs));
-                else CU(ctx, cudaMemcpyAsync(dst_u, sc->out_tmp[slab].p, (uint64_t)b * A * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+                }
+                // host outputs (with routes as well: the rows go to the host AND to the routes)
+                if (!out_is_device && dens) CU(ctx, cudaMemcpyAsync(dst_f, sc->out_tmp_f[slab].p, (uint64_t)b * A * sizeof(double), cudaMemcpyDeviceToHost, cs));
+                else if (!out_is_device) CU(ctx, cudaMemcpyAsync(dst_u, sc->out_tmp[slab].p, (uint64_t)b * A * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
                 if (n_stage > 1) {
                     CU(ctx, cudaEventRecord(ctx->ev_copied[slab], cs));
                     copied_pending[slab] = true;
@@ -1450,9 +1452,9 @@ extern "C" int gatb_run(gatb_sampler *s, const gatb_annotations *annos, int n_co
         if (counters[c] == GATB_NUCLEOTIDE_DENSITY) any_density = true; else any_int = true;
     }
     if (any_density && (!annos->has_nseg || !out_density)) return fail(ctx, GATB_ERR_INVALID, "nucleotide-density needs key_ws_nseg and out_density");
-    if (!ctx->routes.empty() && (!out_is_device || any_density))
-        return fail(ctx, GATB_ERR_INVALID, "run: output routes deliver integer counters to device memory only");
-    if (any_int && !out_counts && ctx->routes.empty()) return fail(ctx, GATB_ERR_INVALID, "run: out_counts is NULL");
+    if (!ctx->routes.empty() && any_density)
+        return fail(ctx, GATB_ERR_INVALID, "run: output routes deliver integer counters only");
+    if (any_int && !out_counts && (ctx->routes.empty() || !out_is_device)) return fail(ctx, GATB_ERR_INVALID, "run: out_counts is NULL");
     if (n_samples == 0) return GATB_OK;
     if (!annos->pending && annos->status) return fail(ctx, annos->status, "run: the annotations failed validation");
     CU(ctx, cudaSetDevice(ctx->device));

@@ -253,8 +253,8 @@ int  gatb_set_batch_size(gatb_ctx *ctx, uint32_t batch);
  * gatb_peer_open over NVLink / NVSwitch: all columns to every rank's [S][A] matrix is the all-gather of the
  * sample slabs; every rank's own column block to its [S][A_g] matrix is the all-to-all by column (column-sharded
  * statistics).  The caller synchronises the ranks (any barrier) after the last gatb_run before reading.
- * Routes stay set until replaced (n_routes = 0 clears them); with routes, gatb_run needs out_is_device != 0,
- * integer counters only, and ignores out_counts.
+ * Routes stay set until replaced (n_routes = 0 clears them); with routes, gatb_run takes integer counters only; with
+ * out_is_device != 0 it ignores out_counts, with host outputs the rows go to the host matrix AND to the routes.
  * Two ways to serve the routes (gatb_set_route_mode; same results): by_kernel = 0 (default) -- the kernel writes a
  * staging slab and COPY ENGINES scatter its rows / column blocks to the routes (2-D device-to-device copies on a copy
  * stream, peer GPUs included) while the next batch is already being placed and counted; by_kernel = 1 -- the counting

@@ -264,8 +264,12 @@ def test_output_routes_deliver_rows_and_column_blocks(ctx, oracle):
         ctx.set_output_routes(routes)
         try:
             smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S, out_counts_ptr=full.data_ptr())
-            with pytest.raises(_lib.GatB200Error):          # routes deliver to device memory only
-                smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S)
+            for t in (left, right):                         # host outputs AND routes at once
+                t.fill_(-1)
+            both, _ = smp.run(annos, names, seed=9, track=0, sample_begin=100, n_samples=S)
+            assert all(np.array_equal(both[n], want[n]) for n in names)
+            with pytest.raises(_lib.GatB200Error):          # integer counters only
+                smp.run(annos, ["nucleotide-density"], seed=9, track=0, sample_begin=100, n_samples=S)
         finally:
             ctx.set_output_routes([])
             ctx.set_route_mode(False)
