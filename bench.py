@@ -286,7 +286,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------- roofline
-def roofline_of(args, wl, ctx, smp, annos, prof, local):
+def roofline_of(args, wl, ctx, smp, annos, prof, local, sm_mhz=None):
     """The counting kernel against three measured machine limits.  All byte counts are PER LAUNCH (= one batch)
     and recomputable from `config` plus the counters in `work`:
 
@@ -353,9 +353,11 @@ def roofline_of(args, wl, ctx, smp, annos, prof, local):
         rate = facts["warp_instructions_per_launch"] / sec / 1e9
         roof["issue"] = {"achieved_gwarp_inst_s": rate, "peak_gwarp_inst_s": mb["issue_gwarp_inst_s"],
                          "frac": rate / mb["issue_gwarp_inst_s"],
+                         "nominal_gwarp_inst_s": (4.0 * mb.get("sms", 0) * sm_mhz / 1e3) if sm_mhz else None,
+                         "frac_of_nominal": (rate / (4.0 * mb.get("sms", 0) * sm_mhz / 1e3)) if (sm_mhz and mb.get("sms")) else None,
                          "warp_instructions_per_launch": facts["warp_instructions_per_launch"],
                          "source": facts.get("capture"),
-                         "peak_source": "gatb_microbench: independent LOP3 chains, 64 warps per SM, measured in this run "
+                         "peak_source": "gatb_microbench: interleaved IADD3 / FFMA chains, 64 warps per SM, measured in this run "
                                         "(nominal 4 x %i SMs x clock)" % mb.get("sms", 0)}
     return roof, placed_per_sample
 
@@ -527,7 +529,8 @@ def run_ours(args):
     ctx.set_output_routes([])
     roofline, placed_per_sample = (None, float(info[0]) / S)
     if rank == 0:
-        roofline, placed_per_sample = roofline_of(args, wl, ctx, smp, annos, prof, local)
+        roofline, placed_per_sample = roofline_of(args, wl, ctx, smp, annos, prof, local,
+                                                  sm_mhz=(clock_info or {}).get("sm_mhz"))
     barrier()
 
     # ---- e2e: host buffers in, host count matrix out, through the C ABI, every step

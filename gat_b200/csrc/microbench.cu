@@ -1,8 +1,9 @@
 // microbench.cu -- the two machine peaks the counting kernel is measured against (bench.py `roofline`):
 //   * L2 read bandwidth: every SM streams a buffer that fits in L2 (default 48 MB) with 16-byte read-only loads,
 //     many passes; the first pass warms L2 and is not timed
-//   * warp-instruction issue rate: eight independent integer chains per thread, no memory, all four schedulers
-//     of every SM busy (16 warps per scheduler) -- compared against 4 x SMs x clock
+//   * warp-instruction issue rate: four integer (IADD3) and four FP32 (FFMA) chains per thread, interleaved, no memory,
+//     all four schedulers of every SM busy (16 warps per scheduler) -- compared against 4 x SMs x clock (an
+//     integer-only chain measures the ALU pipe: half of it)
 // HBM copy bandwidth comes from the driver-written MEASURED_PEAKS.json; these two are measured the same way
 // (best of several runs, CUDA events, on the GPU the bench runs on) by gatb_microbench().
 #include "../../include/gat_b200.h"
@@ -31,16 +32,21 @@ constexpr int ISSUE_UNROLL = 64;                // instructions per chain and lo
 
 __global__ void __launch_bounds__(1024) issue_kernel(int iters, uint32_t seed, uint32_t *sink)
 {
-    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u, a4 = a0 ^ 11u, a5 = a0 ^ 13u, a6 = a0 + 17u, a7 = a0 + 19u;
+    // four integer chains (IADD3, ALU pipe) interleaved with four FP32 chains (FFMA, FMA pipe): one pipe alone takes
+    // only every other issue slot of a scheduler, the two together can fill all of them
+    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 ^ 11u;
+    float f0 = (float)(seed & 7u) + 1.0f, f1 = f0 + 0.5f, f2 = f0 + 0.25f, f3 = f0 + 0.125f;
+    const float m = 1.0f + (float)(seed & 1u) * 1e-7f, c = (float)(seed & 3u) * 1e-9f;
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int u = 0; u < ISSUE_UNROLL; u++) {
-            // one LOP3 each; eight independent dependency chains hide the 4-cycle ALU latency
-            a0 = (a0 ^ a1) & ~a2; a1 = (a1 ^ a2) | a3; a2 = (a2 ^ a3) & ~a4; a3 = (a3 ^ a4) | a5;
-            a4 = (a4 ^ a5) & ~a6; a5 = (a5 ^ a6) | a7; a6 = (a6 ^ a7) & ~a0; a7 = (a7 ^ a0) | a1;
+            a0 += a1; f0 = fmaf(f0, m, c);
+            a1 += a2; f1 = fmaf(f1, m, c);
+            a2 += a3; f2 = fmaf(f2, m, c);
+            a3 += a0; f3 = fmaf(f3, m, c);
         }
     }
-    const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ __float_as_uint(f0 + f1 + f2 + f3);
     if (r == 0x9e3779b9u) *sink = r;
 }
 
@@ -97,7 +103,7 @@ extern "C" int gatb_microbench(int device, int which, uint64_t bytes, int repeat
             cudaEventElapsedTime(&ms, e0, e1);
             if (ms < best_ms) best_ms = ms;
         }
-        work = (double)blocks * 32.0 * iters * gatb::ISSUE_UNROLL * 8.0;   // warp instructions (LOP3s; loop overhead not counted)
+        work = (double)blocks * 32.0 * iters * gatb::ISSUE_UNROLL * 8.0;   // warp instructions (4 IADD3 + 4 FFMA per unrolled step; loop overhead not counted)
     } else rc = GATB_ERR_INVALID;
     if (rc == GATB_OK && cudaGetLastError() != cudaSuccess) rc = GATB_ERR_CUDA;
     if (rc == GATB_OK) {

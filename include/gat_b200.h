@@ -284,8 +284,8 @@ int  gatb_peer_close(gatb_ctx *ctx, void *ptr);
  * GATB_OVERLAP_PIECES counter), out[2] entries of the whole index, out[3] bytes of the index arrays read.
  * gatb_microbench: a machine peak measured on `device` with CUDA events, best of `repeats` runs:
  *   which 0: L2 read bandwidth (a `bytes`-sized buffer, default 48 MB, streamed by every SM with 16-byte
- *            loads) -> out[0] GB/s;   which 1: warp-instruction issue rate (independent integer chains on
- *            64 warps per SM) -> out[0] 1e9 warp instructions/s.   out[1] ms of the best run, out[2] its work
+ *            loads) -> out[0] GB/s;   which 1: warp-instruction issue rate (interleaved integer and FP32
+ *            chains on 64 warps per SM) -> out[0] 1e9 warp instructions/s.   out[1] ms of the best run, out[2] its work
  *            (bytes / warp instructions), out[3] number of SMs. */
 int  gatb_count_work(gatb_sampler *s, const gatb_annotations *annos, uint32_t n_samples, uint64_t *out /*[4]*/);
 int  gatb_microbench(int device, int which, uint64_t bytes, int repeats, double *out /*[4]*/);
