@@ -207,11 +207,14 @@ def barrier():
     rank's PeerMatrix is complete"""
     import torch.distributed as dist
     rank, world = rank_world()
-    torch.cuda.synchronize()
+    on_gpu = torch.cuda.is_available()           # (the gloo-only CPU tests of the host logic have none)
+    if on_gpu:
+        torch.cuda.synchronize()
     if world > 1:
         box = [None] * world
         dist.all_gather_object(box, rank)        # (object collective: rides on the CPU backend when there is one)
-    torch.cuda.synchronize()
+    if on_gpu:
+        torch.cuda.synchronize()
 
 
 _warm = {"thread": None}
