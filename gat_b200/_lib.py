@@ -58,6 +58,16 @@ def load():
             "gat_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "or `make -C gat_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
     L = ctypes.CDLL(LIB_PATH)
+    if hasattr(L, "gatb_emulation_marker"):
+        raise ImportError("gat_b200: %s is the host-emulated test build of the kernels (tests/emu), not the CUDA "
+                          "library -- the engine only runs on the GPU" % LIB_PATH)
+    _lib = bind(L)
+    return L
+
+
+def bind(L):
+    """declare the C signatures of include/gat_b200.h on a loaded library (load() does; tests/test_emu_parity.py binds
+    the emulated test build of the same sources this way, without making it the engine's library)"""
     vp, i32, u32, u64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_double
     L.gatb_version.restype = i32
     L.gatb_version.argtypes = []
@@ -151,5 +161,4 @@ def load():
     L.gatb_peer_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
     L.gatb_peer_close.restype = i32
     L.gatb_peer_close.argtypes = [vp, vp]
-    _lib = L
     return L

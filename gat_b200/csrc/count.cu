@@ -20,6 +20,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/block/block_scan.cuh>
 #include "count.cuh"
+#include "ptx.cuh"
 #include "../../include/gat_b200.h"
 
 namespace gatb {
@@ -37,60 +38,6 @@ size_t count_smem_bytes(uint32_t schunk, uint32_t ka, uint32_t kgrp, int threads
 
 template <int COUNTER> struct NeedPrevInterval { static constexpr bool value = COUNTER == GATB_SEGMENT_OVERLAP || COUNTER == GATB_SEGMENT_MIDOVERLAP; };
 template <int COUNTER> struct NeedPrevSegment { static constexpr bool value = COUNTER == GATB_ANNOTATION_OVERLAP || COUNTER == GATB_ANNOTATION_MIDOVERLAP; };
-
-// shared-memory accesses by 32-bit shared address (the base is computed once, not per access)
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint4 lds128(uint32_t addr)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint2 lds64(uint32_t addr)
-{
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v)
-{
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
-{
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void red_add_shared(uint32_t addr, uint32_t v)
-{
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-// read-only 8-byte global load by 64-bit global address
-__device__ __forceinline__ uint2 ldg_nc_u2(uint64_t addr)
-{
-    uint2 v;
-    asm("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(addr));
-    return v;
-}
-// read-only 16-byte global load (address 16-byte aligned)
-__device__ __forceinline__ uint4 ldg_nc_u4(uint64_t addr)
-{
-    uint4 v;
-    asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr));
-    return v;
-}
-// v << n, 0 for n >= 32 (PTX shl clamps the shift amount, C++ << does not)
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n)
-{
-    uint32_t r;
-    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
-    return r;
-}
 
 // one PAIR of adjacent entries of the flat sequence, loaded two rounds ahead of its use
 struct Flight {
@@ -116,8 +63,7 @@ __device__ __forceinline__ void count_entry(uint32_t x, uint32_t wy, uint32_t y,
 {
     const uint32_t s = o.x, e = o.y;                        // the entry's segment
     if (!((x < e) & (y > s))) return;
-    uint32_t cell;
-    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(cell) : "r"(wy & 0xfffu), "r"(acc_addr));
+    const uint32_t cell = acc_cell(wy, acc_addr);
     if (COUNTER == GATB_NUCLEOTIDE_OVERLAP) {
         red_add_shared(cell, min(e, y) - max(s, x));
     } else if (COUNTER == GATB_SEGMENT_OVERLAP) {

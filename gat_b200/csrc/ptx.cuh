@@ -1,0 +1,71 @@
+// ptx.cuh -- the inline-PTX accessors of the counting kernel (sm_100a): shared memory by 32-bit shared address,
+// read-only vector loads by 64-bit global address, a clamping shift and the accumulator address as one IMAD.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gatb {
+
+// shared-memory accesses by 32-bit shared address (the base is computed once, not per access)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_shared(uint32_t addr, uint32_t v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// read-only 8-byte global load by 64-bit global address
+__device__ __forceinline__ uint2 ldg_nc_u2(uint64_t addr)
+{
+    uint2 v;
+    asm("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(addr));
+    return v;
+}
+// read-only 16-byte global load (address 16-byte aligned)
+__device__ __forceinline__ uint4 ldg_nc_u4(uint64_t addr)
+{
+    uint4 v;
+    asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr));
+    return v;
+}
+// v << n, 0 for n >= 32 (PTX shl clamps the shift amount, C++ << does not)
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n)
+{
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+}
+// cell of track (wy & 0xfff) in the accumulators at shared address acc_addr
+__device__ __forceinline__ uint32_t acc_cell(uint32_t wy, uint32_t acc_addr)
+{
+    uint32_t cell;
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(cell) : "r"(wy & 0xfffu), "r"(acc_addr));
+    return cell;
+}
+
+}  // namespace gatb

@@ -72,3 +72,21 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|oracle/_ref|liboracle|gat_oracle\.h", text, flags=re.M):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_product_never_builds_or_loads_the_emulated_kernels():
+    """tests/emu (the SIMT-emulated host build of the .cu sources) is test infrastructure like the oracle: the
+    package must not know how to build or find it; the only trace allowed is the loader's refusal of it"""
+    bad = []
+    for top in ("gat_b200", "integration"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")) or f == "Makefile":
+                    text = open(os.path.join(dirpath, f)).read()
+                    if re.search(r"build_emu|libgat_b200_emu|GATB_EMU|gatb_emu::|emu_runtime", text):
+                        bad.append(os.path.join(dirpath, f))
+    for f in ("bench.py", "__graft_entry__.py"):
+        text = open(os.path.join(ROOT, f)).read()
+        if re.search(r"build_emu|libgat_b200_emu|tests/emu|tests\.emu", text):
+            bad.append(f)
+    assert not bad, bad
