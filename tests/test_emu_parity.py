@@ -8,7 +8,6 @@ refuses it (test_engine_refuses_the_emulated_build).  What it buys: the placemen
 statistics kernels are checked bit for bit against the oracle on every CPU run of the suite, and a kernel whose
 lanes disagree about a warp collective fails here as a reported deadlock instead of hanging a GPU.
 """
-import ctypes
 import importlib
 import os
 import sys
@@ -21,27 +20,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
 
 @pytest.fixture(scope="module")
 def emu_lib():
-    import build_emu
-    from gat_b200 import _lib
-    return _lib.bind(ctypes.CDLL(build_emu.build()))
+    import emu_context
+    return emu_context.library()
 
 
 @pytest.fixture(scope="module")
 def emu_ctx(emu_lib):
-    from gat_b200 import device
-
-    class EmuContext(device.Context):
-        """device.Context on the emulated build (the wrappers only ever use ctx.lib)"""
-
-        def __init__(self, lib):
-            self.lib = lib
-            h = ctypes.c_void_p()
-            rc = lib.gatb_create(0, ctypes.byref(h))
-            assert rc == 0, lib.gatb_last_error(None)
-            self.handle = h
-            self.device = 0
-
-    c = EmuContext(emu_lib)
+    import emu_context
+    c = emu_context.context()
     yield c
     c.close()
 

@@ -15,12 +15,26 @@ import helpers  # noqa: E402
 from gat_b200 import device  # noqa: E402
 from oracle import oracle  # noqa: E402
 
+
+def make_context():
+    """cuda:0, or with --emu the SIMT-emulated build of the kernels (tests/emu: no GPU needed, much slower)"""
+    if EMU:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import emu_context
+        return emu_context.context()
+    return device.Context(0)
+
+
+EMU = "--emu" in sys.argv
+if EMU:
+    sys.argv.remove("--emu")
+
 COUNTERS = ["nucleotide-overlap", "nucleotide-density", "segment-overlap", "segment-midoverlap",
             "annotation-overlap", "annotation-midoverlap"]
 n_problems = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 7
 rng = np.random.default_rng(seed0)
-ctx = device.Context(0)
+ctx = make_context()
 cells = 0
 for it in range(n_problems):
     K = int(rng.integers(1, 5))

@@ -15,12 +15,26 @@ import helpers  # noqa: E402
 from gat_b200 import device  # noqa: E402
 from oracle import oracle  # noqa: E402
 
+
+def make_context():
+    """cuda:0, or with --emu the SIMT-emulated build of the kernels (tests/emu: no GPU needed, much slower)"""
+    if EMU:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import emu_context
+        return emu_context.context()
+    return device.Context(0)
+
+
+EMU = "--emu" in sys.argv
+if EMU:
+    sys.argv.remove("--emu")
+
 if "--shift" in sys.argv:          # SamplerShift instead: python tools/stress_place.py --shift [n_units] [seed]
     sys.argv.remove("--shift")
     n_units = int(sys.argv[1]) if len(sys.argv) > 1 else 600
     seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 2024
     rng = np.random.default_rng(seed0)
-    ctx = device.Context(0)
+    ctx = make_context()
     npieces = nover = 0
     for it in range(n_units):
         segs, ws = helpers.random_unit(rng)
@@ -84,7 +98,7 @@ if fragmented:
 n_units = int(sys.argv[1]) if len(sys.argv) > 1 else 600
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 2024
 rng = np.random.default_rng(seed0)
-ctx = device.Context(0)
+ctx = make_context()
 ntrim = ncp = nround = 0
 for it in range(n_units):
     segs, ws = fragmented_unit(rng) if fragmented else helpers.random_unit(rng)
