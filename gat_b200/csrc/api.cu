@@ -49,6 +49,8 @@ struct gatb_ctx {
     // output routes of gatb_run (gatb_set_output_routes): integer counts delivered to several destinations,
     // possibly peer GPUs, by the counting kernel's epilogue
     std::vector<gatb_route> routes;
+    bool discard_scratch = false;       // GATB_DISCARD=1: the placement kernels discard their dead buffer tails from L2 (halves
+                                        // their DRAM writes, costs 1-3 % of their time: profiles/r02_discard_ab.txt)
     bool route_copy = true;             // routes are served by copy engines from a staging slab (false: by the kernel's stores)
     bool trace = false;                 // GATB_TRACE=1: host-side phase times of gatb_run on stderr
     // optional per-kernel timing (bench.py roofline): CUDA events around every launch
@@ -254,6 +256,7 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     ctx->trace = env_u32("GATB_TRACE", 0) != 0;
     ctx->overlap = env_u32("GATB_OVERLAP", 0) != 0;
     ctx->route_copy = env_u32("GATB_ROUTE_KERNEL", 0) == 0;
+    ctx->discard_scratch = env_u32("GATB_DISCARD", 0) != 0;
     ctx->scratch = new BatchScratch();
     ctx->blocks = new BlockCache();
     ctx->batch = env_u32("GATB_BATCH", 0);
@@ -1140,6 +1143,7 @@ static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t 
     p.seed = seed; p.track = track; p.sampler_kind = s->kind;
     p.seg_start = s->seg_start.p; p.seg_end = s->seg_end.p;
     p.shift_half_radius = s->shift_radius / 2; p.shift_extension = s->shift_extension;
+    p.discard_scratch = ctx->discard_scratch ? 1 : 0;
     { ProfScope ps(ctx, PROF_PLACE, st); launch_place(st, p); }
     CU(ctx, cudaGetLastError());
     if (s->has_iso) {
@@ -1149,6 +1153,7 @@ static int place_batch(gatb_sampler *s, uint64_t seed, uint32_t track, uint64_t 
         m.contig_base = s->contig_base.p; m.unit_buf = pb.unit_buf.p; m.unit_stride = s->unit_stride;
         m.unit_n = pb.unit_n.p; m.placed = pb.placed.p; m.placed_stride = s->placed_stride;
         m.placed_n = pb.placed_n.p; m.n_units = s->n_units; m.n_contigs = s->n_contigs; m.n_samples = B;
+        m.discard_scratch = ctx->discard_scratch ? 1 : 0;
         { ProfScope ps(ctx, PROF_MERGE, st); launch_contig_merge(st, m); }
         CU(ctx, cudaGetLastError());
     }
