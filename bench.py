@@ -362,6 +362,30 @@ def roofline_of(args, wl, ctx, smp, annos, prof, local, sm_mhz=None):
     return roof, placed_per_sample
 
 
+def stats_roofline(ctx, slab, S, A):
+    """K5 (column statistics of the step's count matrix, resident in HBM) against the HBM roofline: the streaming
+    passes of stats_stream.cu read the S x A uint32 matrix once each -- pass 1 plus one select pass per non-zero
+    nibble of the largest count -- so achieved = passes * S * A * 4 bytes / kernel time (CUDA events around every
+    launch, gatb_profile); peak = measured HBM copy bandwidth"""
+    observed = slab[0].cpu().numpy().astype(np.float64)
+    reps = 3
+    ctx.column_stats(None, observed, device_ptr=slab.data_ptr(), n_samples=S, n_cols=A, is_float=False)     # warm-up
+    ctx.profile(True)
+    ctx.profile_read()
+    for _ in range(reps):
+        ctx.column_stats(None, observed, device_ptr=slab.data_ptr(), n_samples=S, n_cols=A, is_float=False)
+    ms, launches = ctx.profile_read()["other"]
+    ctx.profile(False)
+    ms, launches = ms / reps, launches // reps
+    passes = 1 + (launches - 1) // 3                # (a select pass = streaming kernel + pick + commit)
+    peak, src = measured_peak()
+    gbs = passes * S * A * 4.0 / (ms / 1000.0) / 1e9
+    return {"kernel": "stats_stream_kernel (K5 column statistics: TMA bulk copies into a shared-memory ring)",
+            "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": src,
+            "kernel_ms": ms, "passes_over_matrix": passes, "matrix_bytes": S * A * 4, "launches": launches,
+            "formula": "achieved = passes * S * A * 4 / kernel_ms (the matrix of one step, %.0f MB, larger than L2)" % (S * A * 4 / 1e6)}
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -531,6 +555,11 @@ def run_ours(args):
     if rank == 0:
         roofline, placed_per_sample = roofline_of(args, wl, ctx, smp, annos, prof, local,
                                                   sm_mhz=(clock_info or {}).get("sm_mhz"))
+        if odt == torch.int32 and not args.no_checks:
+            try:
+                roofline["statistics_kernel"] = stats_roofline(ctx, outs[last % nbuf], S, A)
+            except Exception as exc:               # (reported, never fatal for the headline)
+                roofline["statistics_kernel"] = {"error": str(exc)}
     barrier()
 
     # ---- e2e: host buffers in, host count matrix out, through the C ABI, every step

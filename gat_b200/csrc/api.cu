@@ -49,6 +49,7 @@ struct gatb_ctx {
     // output routes of gatb_run (gatb_set_output_routes): integer counts delivered to several destinations,
     // possibly peer GPUs, by the counting kernel's epilogue
     std::vector<gatb_route> routes;
+    bool stats_stream = true;           // uint32 column statistics as TMA-streamed passes (GATB_STATS_STREAM=0: the column-tiled kernels)
     bool discard_scratch = false;       // GATB_DISCARD=1: the placement kernels discard their dead buffer tails from L2 (halves
                                         // their DRAM writes, costs 1-3 % of their time: profiles/r02_discard_ab.txt)
     bool route_copy = true;             // routes are served by copy engines from a staging slab (false: by the kernel's stores)
@@ -257,6 +258,7 @@ extern "C" int gatb_create(int device, gatb_ctx **out)
     ctx->overlap = env_u32("GATB_OVERLAP", 0) != 0;
     ctx->route_copy = env_u32("GATB_ROUTE_KERNEL", 0) == 0;
     ctx->discard_scratch = env_u32("GATB_DISCARD", 0) != 0;
+    ctx->stats_stream = env_u32("GATB_STATS_STREAM", 1) != 0;
     ctx->scratch = new BatchScratch();
     ctx->blocks = new BlockCache();
     ctx->batch = env_u32("GATB_BATCH", 0);
@@ -1517,6 +1519,80 @@ extern "C" int gatb_count_work(gatb_sampler *s, const gatb_annotations *annos, u
 
 // ---------------------------------------------------------------------------------------------------
 // column statistics
+// The streaming passes of stats_stream.cu on a device-resident uint32 matrix (what gatb_run leaves behind):
+// pass 1 always; with `full`, pass 2 and the select passes as well.  Outputs as host vectors.
+struct StreamStatsOut {
+    std::vector<double> sum, sumsq, qlo, qhi;       // sumsq = sum (x - mean)^2
+    std::vector<unsigned long long> n_lt, n_eq;
+};
+static int stream_stats(gatb_ctx *ctx, const uint32_t *dc, uint64_t l, uint32_t A, const double *obs_eff,
+                        uint64_t rank_lo, uint64_t rank_hi, bool full, StreamStatsOut &o)
+{
+    cudaStream_t st = ctx->stream;
+    DevBuf<double> d_obs, d_q;
+    DevBuf<unsigned long long> d_acc, d_rank;       // isum | n_lt | n_eq | sq_lo | sq_hi ; rank | rank_out
+    DevBuf<uint32_t> d_small, d_prefix, d_hist;     // vmax, error ; prefix | prefix_out
+    CU(ctx, d_obs.upload(obs_eff, A, st));
+    CU(ctx, d_acc.alloc(5 * (size_t)A));
+    CU(ctx, d_small.alloc(2));
+    CU(ctx, cudaMemsetAsync(d_acc.p, 0, 5 * (size_t)A * sizeof(unsigned long long), st));
+    CU(ctx, cudaMemsetAsync(d_small.p, 0, 2 * sizeof(uint32_t), st));
+    StreamStatsParams p;
+    memset(&p, 0, sizeof(p));
+    p.counts = dc; p.n_samples = l; p.n_cols = A;
+    stats_stream_geometry(p);
+    p.observed = d_obs.p; p.isum = d_acc.p; p.n_lt = d_acc.p + A; p.n_eq = d_acc.p + 2 * (size_t)A;
+    p.sq_lo = d_acc.p + 3 * (size_t)A; p.sq_hi = d_acc.p + 4 * (size_t)A;
+    p.vmax = d_small.p; p.error = d_small.p + 1;
+    { ProfScope ps(ctx, PROF_OTHER); CU(ctx, launch_stats_stream_pass1(st, p, ctx->sm_count)); }
+    std::vector<unsigned long long> h_acc(5 * (size_t)A);
+    uint32_t h_small[2] = {0, 0};
+    CU(ctx, cudaMemcpyAsync(h_acc.data(), d_acc.p, h_acc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(h_small, d_small.p, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    if (h_small[1]) return fail(ctx, GATB_ERR_CUDA, "column statistics: a TMA copy did not complete");
+    o.sum.resize(A); o.sumsq.resize(A);
+    o.n_lt.assign(h_acc.begin() + A, h_acc.begin() + 2 * (size_t)A);
+    o.n_eq.assign(h_acc.begin() + 2 * (size_t)A, h_acc.begin() + 3 * (size_t)A);
+    for (uint32_t a = 0; a < A; a++) {
+        o.sum[a] = (double)h_acc[a];
+        // sum (x - mean)^2 = (n * sum x^2 - (sum x)^2) / n, the numerator exact in 128 bits (x < 2^32, n < 2^32:
+        // both products stay below 2^128), rounded once when it becomes a double
+        const unsigned __int128 sq = ((unsigned __int128)h_acc[4 * (size_t)A + a] << 64) | h_acc[3 * (size_t)A + a];
+        const unsigned __int128 num = (unsigned __int128)l * sq - (unsigned __int128)h_acc[a] * h_acc[a];
+        o.sumsq[a] = (double)num / (double)l;
+    }
+    if (!full) return GATB_OK;
+
+    // radix select, 4 bits per pass, from the highest non-zero nibble of the largest value
+    std::vector<unsigned long long> h_rank(2 * (size_t)A);
+    for (uint32_t a = 0; a < A; a++) { h_rank[a] = rank_lo; h_rank[A + a] = rank_hi; }
+    CU(ctx, d_rank.alloc(4 * (size_t)A));
+    CU(ctx, cudaMemcpyAsync(d_rank.p, h_rank.data(), h_rank.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    CU(ctx, d_prefix.alloc(4 * (size_t)A));
+    CU(ctx, cudaMemsetAsync(d_prefix.p, 0, 4 * (size_t)A * sizeof(uint32_t), st));
+    CU(ctx, d_hist.alloc(32 * (size_t)A));
+    CU(ctx, cudaMemsetAsync(d_hist.p, 0, 32 * (size_t)A * sizeof(uint32_t), st));
+    CU(ctx, d_q.alloc(2 * (size_t)A));
+    p.prefix = d_prefix.p; p.prefix_out = d_prefix.p + 2 * (size_t)A;
+    p.rank = d_rank.p; p.rank_out = d_rank.p + 2 * (size_t)A;
+    p.hist = d_hist.p; p.q_lo = d_q.p; p.q_hi = d_q.p + A;
+    int top = 0;
+    while (top < 28 && (h_small[0] >> (top + 4)) != 0u) top += 4;
+    for (int shift = top; shift >= 0; shift -= 4) {
+        p.shift = (uint32_t)shift;
+        ProfScope ps(ctx, PROF_OTHER);
+        CU(ctx, launch_stats_stream_select(st, p, ctx->sm_count));
+    }
+    o.qlo.resize(A); o.qhi.resize(A);
+    CU(ctx, cudaMemcpyAsync(o.qlo.data(), d_q.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(o.qhi.data(), d_q.p + A, A * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(h_small, d_small.p, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    if (h_small[1]) return fail(ctx, GATB_ERR_CUDA, "column statistics: a TMA copy did not complete");
+    return GATB_OK;
+}
+
 extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float, int counts_is_device,
                                  uint64_t n_samples, int n_cols, const double *observed, const double *ref_fold,
                                  double pseudo_count, double *expected, double *stddev, double *lower95,
@@ -1543,38 +1619,52 @@ extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float
             obs_eff[a] = observed[a] / ref_fold[a];
         } else obs_eff[a] = observed[a];
     }
-    DevBuf<double> d_obs, d_sum, d_sq, d_mean, d_qlo, d_qhi;
-    DevBuf<unsigned long long> d_cnt;
-    CU(ctx, d_obs.upload(obs_eff.data(), A, st));
-    CU(ctx, d_sum.alloc(A)); CU(ctx, d_sq.alloc(A)); CU(ctx, d_qlo.alloc(A)); CU(ctx, d_qhi.alloc(A));
-    CU(ctx, d_cnt.alloc(2 * (size_t)A));
-
-    StatsParams p;
-    memset(&p, 0, sizeof(p));
-    p.counts = dc; p.is_float = is_float; p.n_samples = l; p.n_cols = A; p.observed = d_obs.p;
-    p.sum = d_sum.p; p.sumsq_dev = d_sq.p; p.n_lt = d_cnt.p; p.n_eq = d_cnt.p + A;
-    p.q_lo = d_qlo.p; p.q_hi = d_qhi.p;
     // CI ranks (gat/Engine.pyx:1689-1696)
+    uint64_t rank_lo, rank_hi;
     const uint64_t off = (uint64_t)(0.05 * (double)l);
-    if (off > 0) { p.rank_lo = std::min<uint64_t>(off, l - 1); p.rank_hi = (l > off) ? l - off : 0; }
-    else { p.rank_lo = 0; p.rank_hi = l - 1; }
-    { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass1(st, p); }
-    CU(ctx, cudaGetLastError());
+    if (off > 0) { rank_lo = std::min<uint64_t>(off, l - 1); rank_hi = (l > off) ? l - off : 0; }
+    else { rank_lo = 0; rank_hi = l - 1; }
     std::vector<double> h_sum(A), h_sq(A), h_qlo(A), h_qhi(A), h_mean(A);
     std::vector<unsigned long long> h_cnt(2 * (size_t)A);
-    CU(ctx, cudaMemcpyAsync(h_sum.data(), d_sum.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaStreamSynchronize(st));
-    for (uint32_t a = 0; a < A; a++) h_mean[a] = h_sum[a] / (double)l;        // numpy.mean (:1671)
-    CU(ctx, d_mean.upload(h_mean.data(), A, st));
-    p.mean = d_mean.p;
-    { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass2(st, p); }
-    { ProfScope ps(ctx, PROF_OTHER); launch_stats_select(st, p); }
-    CU(ctx, cudaGetLastError());
-    CU(ctx, cudaMemcpyAsync(h_sq.data(), d_sq.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaMemcpyAsync(h_qlo.data(), d_qlo.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaMemcpyAsync(h_qhi.data(), d_qhi.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt.p, 2 * (size_t)A * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaStreamSynchronize(st));
+    if (!is_float && ctx->stats_stream && stats_stream_fits(dc, l, A, ctx->smem_optin)) {
+        // uint32 counts: HBM-bound streaming passes (stats_stream.cu)
+        StreamStatsOut o;
+        const int rc = stream_stats(ctx, (const uint32_t *)dc, l, A, obs_eff.data(), rank_lo, rank_hi, true, o);
+        if (rc != GATB_OK) return rc;
+        for (uint32_t a = 0; a < A; a++) {
+            h_sum[a] = o.sum[a]; h_sq[a] = o.sumsq[a]; h_qlo[a] = o.qlo[a]; h_qhi[a] = o.qhi[a];
+            h_mean[a] = h_sum[a] / (double)l;
+            h_cnt[a] = o.n_lt[a]; h_cnt[A + a] = o.n_eq[a];
+        }
+    } else {
+        // float64 matrices (nucleotide-density, gat-compare), very wide or unaligned ones: column-tiled kernels (count.cu)
+        DevBuf<double> d_obs, d_sum, d_sq, d_mean, d_qlo, d_qhi;
+        DevBuf<unsigned long long> d_cnt;
+        CU(ctx, d_obs.upload(obs_eff.data(), A, st));
+        CU(ctx, d_sum.alloc(A)); CU(ctx, d_sq.alloc(A)); CU(ctx, d_qlo.alloc(A)); CU(ctx, d_qhi.alloc(A));
+        CU(ctx, d_cnt.alloc(2 * (size_t)A));
+        StatsParams p;
+        memset(&p, 0, sizeof(p));
+        p.counts = dc; p.is_float = is_float; p.n_samples = l; p.n_cols = A; p.observed = d_obs.p;
+        p.sum = d_sum.p; p.sumsq_dev = d_sq.p; p.n_lt = d_cnt.p; p.n_eq = d_cnt.p + A;
+        p.q_lo = d_qlo.p; p.q_hi = d_qhi.p;
+        p.rank_lo = rank_lo; p.rank_hi = rank_hi;
+        { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass1(st, p); }
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaMemcpyAsync(h_sum.data(), d_sum.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+        for (uint32_t a = 0; a < A; a++) h_mean[a] = h_sum[a] / (double)l;        // numpy.mean (:1671)
+        CU(ctx, d_mean.upload(h_mean.data(), A, st));
+        p.mean = d_mean.p;
+        { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass2(st, p); }
+        { ProfScope ps(ctx, PROF_OTHER); launch_stats_select(st, p); }
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaMemcpyAsync(h_sq.data(), d_sq.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(h_qlo.data(), d_qlo.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(h_qhi.data(), d_qhi.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt.p, 2 * (size_t)A * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+    }
 
     for (uint32_t a = 0; a < A; a++) {
         double exp_ = h_mean[a];
@@ -1627,20 +1717,27 @@ extern "C" int gatb_column_pvalue(gatb_ctx *ctx, const void *counts, int is_floa
         CU(ctx, d_counts.upload((const uint8_t *)counts, l * A * esz, st));
         dc = d_counts.p;
     }
-    DevBuf<double> d_obs, d_sum;
-    DevBuf<unsigned long long> d_cnt;
-    CU(ctx, d_obs.upload(values, A, st));
-    CU(ctx, d_sum.alloc(A));
-    CU(ctx, d_cnt.alloc(2 * (size_t)A));
-    StatsParams p;
-    memset(&p, 0, sizeof(p));
-    p.counts = dc; p.is_float = is_float; p.n_samples = l; p.n_cols = A; p.observed = d_obs.p;
-    p.sum = d_sum.p; p.n_lt = d_cnt.p; p.n_eq = d_cnt.p + A;
-    { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass1(st, p); }
-    CU(ctx, cudaGetLastError());
     std::vector<unsigned long long> h_cnt(2 * (size_t)A);
-    CU(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt.p, 2 * (size_t)A * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaStreamSynchronize(st));
+    if (!is_float && ctx->stats_stream && stats_stream_fits(dc, l, A, ctx->smem_optin)) {
+        StreamStatsOut o;
+        const int rc = stream_stats(ctx, (const uint32_t *)dc, l, A, values, 0, 0, false, o);
+        if (rc != GATB_OK) return rc;
+        for (uint32_t a = 0; a < A; a++) { h_cnt[a] = o.n_lt[a]; h_cnt[A + a] = o.n_eq[a]; }
+    } else {
+        DevBuf<double> d_obs, d_sum;
+        DevBuf<unsigned long long> d_cnt;
+        CU(ctx, d_obs.upload(values, A, st));
+        CU(ctx, d_sum.alloc(A));
+        CU(ctx, d_cnt.alloc(2 * (size_t)A));
+        StatsParams p;
+        memset(&p, 0, sizeof(p));
+        p.counts = dc; p.is_float = is_float; p.n_samples = l; p.n_cols = A; p.observed = d_obs.p;
+        p.sum = d_sum.p; p.n_lt = d_cnt.p; p.n_eq = d_cnt.p + A;
+        { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass1(st, p); }
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt.p, 2 * (size_t)A * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+    }
     for (uint32_t a = 0; a < A; a++) {
         const uint64_t n_lt = h_cnt[a], n_eq = h_cnt[A + a];
         uint64_t idx = n_lt;

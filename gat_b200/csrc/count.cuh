@@ -165,6 +165,33 @@ void launch_compare_derive(cudaStream_t st, const CompareParams &p);
 void launch_format_counts(cudaStream_t st, const uint32_t *counts, uint64_t n_samples, uint32_t n_cols,
                           unsigned long long *col_len, const unsigned long long *col_off, char *text);
 
+// K5 as HBM-bound streaming passes over a uint32 matrix (stats_stream.cu): TMA bulk copies of whole rows into a
+// shared-memory ring, thread = column
+struct StreamStatsParams {
+    const uint32_t *counts;         // [n_samples][n_cols], 16-byte aligned
+    uint64_t n_samples;
+    uint32_t n_cols;
+    uint32_t rows_per_stage;        // rows of one ring stage (multiple of 4: every chunk starts 16-byte aligned)
+    uint32_t n_chunks;              // chunks of rows_per_stage rows, dealt to the CTAs round-robin
+    uint32_t n_stages, col_width;   // set by the launchers
+    // pass 1 (outputs zeroed by the caller, accumulated with integer atomics)
+    const double *observed;
+    unsigned long long *isum, *n_lt, *n_eq;
+    unsigned long long *sq_lo, *sq_hi;   // sum of squares, 128 bits
+    uint32_t *vmax;                 // largest value of the matrix
+    // select pass at bit `shift` (4 bits): prefix / rank per (which rank, column), [2][n_cols]
+    uint32_t shift;
+    uint32_t *prefix, *prefix_out;
+    unsigned long long *rank, *rank_out;
+    uint32_t *hist;                 // [2][16][n_cols], zero between passes
+    double *q_lo, *q_hi;            // written by the last pass (shift 0)
+    uint32_t *error;                // set when a TMA wait timed out
+};
+bool stats_stream_fits(const void *counts, uint64_t n_samples, uint32_t n_cols, size_t smem_optin);
+void stats_stream_geometry(StreamStatsParams &p);
+cudaError_t launch_stats_stream_pass1(cudaStream_t st, StreamStatsParams p, int sm_count);
+cudaError_t launch_stats_stream_select(cudaStream_t st, StreamStatsParams p, int sm_count);
+
 void launch_stats_pass1(cudaStream_t st, const StatsParams &p);
 void launch_stats_pass2(cudaStream_t st, const StatsParams &p);
 void launch_stats_select(cudaStream_t st, const StatsParams &p);

@@ -1,6 +1,7 @@
 // ptx.cuh -- the inline-PTX accessors of the kernels (sm_100a).  Counting kernel: shared memory by 32-bit shared
 // address, read-only vector loads by 64-bit global address, a clamping shift and the accumulator address as one IMAD.
-// Placement kernels: L2 discard of dead scratch lines.
+// Placement kernels: L2 discard of dead scratch lines.  Statistics: TMA bulk copies global -> shared with mbarrier
+// completion.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -73,6 +74,36 @@ __device__ __forceinline__ uint32_t acc_cell(uint32_t wy, uint32_t acc_addr)
 __device__ __forceinline__ void discard_l2_line(uint64_t addr)
 {
     asm volatile("discard.global.L2 [%0], 128;" ::"l"(addr) : "memory");
+}
+
+// ---- TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (shared addresses as above) ----
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(arrivals) : "memory");
+}
+// makes the initialised barriers visible to the async proxy (the TMA unit) before the first copy names them
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// the one arrival of a phase, announcing `bytes` of copies that will complete on the barrier
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// dst (shared), src (global) 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+// true once the phase of the given parity has completed (the data of its copies is then visible to the caller)
+__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    return done != 0u;
 }
 
 }  // namespace gatb

@@ -74,6 +74,7 @@ static Fiber *cur_fiber = nullptr;
 static Body *cur_body = nullptr;
 static uint32_t blk_alive = 0, blk_arrived = 0;
 static uint64_t blk_gen = 0;
+static int blk_or_acc = 0, blk_or_result[2] = {0, 0};
 static std::mutex launch_mutex;
 
 static void yield_to_scheduler() { gatb_emu_switch(&cur_fiber->ctx, &sched_ctx); }
@@ -104,12 +105,28 @@ const uint64_t *warp_exchange(uint64_t v, uint32_t *alive)
     return buf;
 }
 
+static void complete_block()
+{
+    blk_or_result[blk_gen & 1u] = blk_or_acc;
+    blk_or_acc = 0;
+    blk_arrived = 0;
+    blk_gen++;
+}
+
+int block_sync_or(int pred)
+{
+    const uint64_t g = blk_gen;
+    if (pred) blk_or_acc = 1;
+    block_sync();
+    return blk_or_result[g & 1u];
+}
+
 void block_sync()
 {
     Fiber *f = cur_fiber;
     const uint64_t g = blk_gen;
     blk_arrived++;
-    if (blk_arrived == blk_alive) { blk_arrived = 0; blk_gen++; }
+    if (blk_arrived == blk_alive) complete_block();
     else {
         f->wait = WAIT_BLOCK;
         f->wait_gen = g;
@@ -117,6 +134,8 @@ void block_sync()
         f->wait = RUNNABLE;
     }
 }
+
+void yield() { yield_to_scheduler(); }
 
 static void fiber_exit(Fiber *f)
 {
@@ -128,7 +147,7 @@ static void fiber_exit(Fiber *f)
     w.alive_mask &= ~(1u << f->th.lane);
     if (w.alive > 0 && w.arrived == w.alive) complete_warp(w);
     blk_alive--;
-    if (blk_alive > 0 && blk_arrived == blk_alive) { blk_arrived = 0; blk_gen++; }
+    if (blk_alive > 0 && blk_arrived == blk_alive) complete_block();
 }
 
 extern "C" void gatb_emu_fiber_main()
@@ -179,6 +198,7 @@ static void run_block(uint32_t nthreads)
     }
     blk_alive = nthreads;
     blk_arrived = 0;
+    blk_or_acc = 0;
     uint32_t live = nthreads;
     while (live > 0) {
         bool progress = false;

@@ -127,6 +127,8 @@ extern Block blk;
 // collective); *alive = lanes that took part (lanes that have left the kernel do not)
 const uint64_t *warp_exchange(uint64_t v, uint32_t *alive);
 void block_sync();
+int block_sync_or(int pred);    // __syncthreads_or
+void yield();                   // let the other threads of the block run (spin loops on shared state)
 
 // run fn() as every thread of a grid (blocks one after the other)
 struct Body { virtual void run() = 0; virtual ~Body() {} };
@@ -164,6 +166,7 @@ template <class T> static inline T from_bits(uint64_t b)
 #define gridDim (gatb_emu::blk.gdim)
 
 static inline void __syncthreads() { gatb_emu::block_sync(); }
+static inline int __syncthreads_or(int pred) { return gatb_emu::block_sync_or(pred); }
 static inline void __syncwarp(unsigned = 0xffffffffu)
 {
     uint32_t alive;

@@ -4,6 +4,8 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace gatb {
 
@@ -23,6 +25,24 @@ __device__ __forceinline__ uint32_t acc_cell(uint32_t wy, uint32_t acc_addr) { r
 __device__ __forceinline__ void discard_l2_line(uint64_t addr)
 {
     memset((void *)addr, 0xDD, 128);                // "undefined afterwards": make a later read of it visible
+}
+
+// mbarrier + TMA bulk copy: the copy happens at once, the barrier word counts completed phases
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t) { emu_sts<uint64_t>(mbar, 0ull); }
+__device__ __forceinline__ void fence_mbar_init() {}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t, uint32_t) {}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    if (((uintptr_t)src & 15u) || (dst & 15u) || (bytes & 15u)) { fprintf(stderr, "gatb_emu: misaligned bulk copy\n"); abort(); }
+    memcpy(gatb_emu::shared_ptr(dst), src, bytes);
+    emu_sts<uint64_t>(mbar, emu_lds<uint64_t>(mbar) + 1ull);
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity)
+{
+    // phases 0 .. n-1 have completed: the phase of parity P is done iff the running phase n has the other parity
+    if ((emu_lds<uint64_t>(mbar) & 1ull) != (uint64_t)parity) return true;
+    gatb_emu::yield();
+    return false;
 }
 
 }  // namespace gatb

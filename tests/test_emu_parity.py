@@ -52,6 +52,7 @@ CASES = [
     ("test_gpu_prep", "test_invalid_rows_fail_loudly", {}),
     ("test_gpu_round2", "test_skewed_unit_grows_its_buffer", {}),
     ("test_gpu_round2", "test_overflow_growth_is_exercised", {}),
+    ("test_gpu_round2", "test_streamed_column_stats_exact_and_layout_independent", {}),
     ("test_gpu_parity", "test_async_annotations_same_counts_and_deferred_errors", {}),
     ("test_gpu_properties", "test_isochore_config_matches_oracle", {}),
 ]

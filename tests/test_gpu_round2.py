@@ -284,3 +284,41 @@ def test_output_routes_deliver_rows_and_column_blocks(ctx, oracle):
     assert np.array_equal(again[names[0]], want[names[0]])
     smp.close()
     annos.close()
+
+
+def test_streamed_column_stats_exact_and_layout_independent(ctx):
+    """K5 as TMA-streamed passes (stats_stream.cu): sums, p-value counts and order statistics exact against numpy for
+    shapes around every boundary of the kernel (1 column ... more columns than threads, one partial chunk ... many
+    super-chunks, values up to 2^32 - 1), stddev to 1e-12, and every column's statistics identical bit for bit
+    whether the column is part of the full matrix or of a column block (the column-sharded layout of run())"""
+    rng = np.random.default_rng(77)
+    shapes = [(1, 1), (5, 3), (1000, 50), (4097, 9), (5000, 125), (3000, 257), (2500, 1000), (1500, 1200), (70000, 16)]
+    for l, A in shapes:
+        hi = int(rng.choice([3, 40, 70000, 2 ** 32 - 1]))
+        counts = rng.integers(0, hi, size=(l, A), endpoint=True).astype(np.uint32)
+        if A > 2:
+            counts[:, 1] = 7                                       # constant column
+            counts[:, 2] = 0
+        obs = np.array([float(np.quantile(counts[:, a], q)) for a, q in zip(range(A), np.linspace(0, 1, A))]).round()
+        got = ctx.column_stats(counts, obs, pseudo_count=1.0)
+        srt = np.sort(counts, axis=0)
+        off = int(0.05 * l)
+        lo, hi_ = (min(off, l - 1), l - off) if off > 0 else (0, l - 1)
+        assert np.array_equal(got["expected"], counts.sum(axis=0, dtype=np.uint64).astype(np.float64) / l), (l, A)
+        assert np.array_equal(got["lower95"], srt[lo].astype(np.float64)), (l, A)
+        assert np.array_equal(got["upper95"], srt[hi_].astype(np.float64)), (l, A)
+        assert np.allclose(got["stddev"], counts.astype(np.float64).std(axis=0), rtol=1e-12, atol=0), (l, A)
+        for a in range(A):
+            n_lt, n_eq = int((counts[:, a] < obs[a]).sum()), int((counts[:, a] == obs[a]).sum())
+            if n_lt == l:
+                k = 1
+            elif obs[a] > got["expected"][a]:
+                k = l - n_lt if (n_eq > 0 and n_lt > 0) else l - n_lt - 1
+            else:
+                k = n_lt + n_eq
+            assert got["pvalue"][a] == max(1.0 / l, k / l), (l, A, a)
+        if A >= 8:
+            b0, b1 = A // 3, A // 3 + max(1, A // 4)
+            block = ctx.column_stats(np.ascontiguousarray(counts[:, b0:b1]), obs[b0:b1], pseudo_count=1.0)
+            for key in ("expected", "stddev", "lower95", "upper95", "fold", "pvalue"):
+                assert np.array_equal(block[key], got[key][b0:b1]), (l, A, key)
