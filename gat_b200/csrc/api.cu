@@ -1529,10 +1529,13 @@ static int stream_stats(gatb_ctx *ctx, const uint32_t *dc, uint64_t l, uint32_t 
                         uint64_t rank_lo, uint64_t rank_hi, bool full, StreamStatsOut &o)
 {
     cudaStream_t st = ctx->stream;
-    DevBuf<double> d_obs, d_q;
+    DevBuf<double> d_q;
+    DevBuf<uint32_t> d_thr;                         // lt_thr | eq_val | flags
     DevBuf<unsigned long long> d_acc, d_rank;       // isum | n_lt | n_eq | sq_lo | sq_hi ; rank | rank_out
     DevBuf<uint32_t> d_small, d_prefix, d_hist;     // vmax, error ; prefix | prefix_out
-    CU(ctx, d_obs.upload(obs_eff, A, st));
+    std::vector<uint32_t> h_thr(3 * (size_t)A);
+    stats_stream_thresholds(obs_eff, A, h_thr.data(), h_thr.data() + A, h_thr.data() + 2 * (size_t)A);
+    CU(ctx, d_thr.upload(h_thr.data(), h_thr.size(), st));
     CU(ctx, d_acc.alloc(5 * (size_t)A));
     CU(ctx, d_small.alloc(2));
     CU(ctx, cudaMemsetAsync(d_acc.p, 0, 5 * (size_t)A * sizeof(unsigned long long), st));
@@ -1541,7 +1544,7 @@ static int stream_stats(gatb_ctx *ctx, const uint32_t *dc, uint64_t l, uint32_t 
     memset(&p, 0, sizeof(p));
     p.counts = dc; p.n_samples = l; p.n_cols = A;
     stats_stream_geometry(p);
-    p.observed = d_obs.p; p.isum = d_acc.p; p.n_lt = d_acc.p + A; p.n_eq = d_acc.p + 2 * (size_t)A;
+    p.lt_thr = d_thr.p; p.eq_val = d_thr.p + A; p.col_flags = d_thr.p + 2 * (size_t)A; p.isum = d_acc.p; p.n_lt = d_acc.p + A; p.n_eq = d_acc.p + 2 * (size_t)A;
     p.sq_lo = d_acc.p + 3 * (size_t)A; p.sq_hi = d_acc.p + 4 * (size_t)A;
     p.vmax = d_small.p; p.error = d_small.p + 1;
     { ProfScope ps(ctx, PROF_OTHER); CU(ctx, launch_stats_stream_pass1(st, p, ctx->sm_count)); }

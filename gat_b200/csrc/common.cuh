@@ -60,6 +60,10 @@ __host__ __device__ __forceinline__ uint32_t bounded_u32(uint32_t rlo, uint32_t 
 // warp primitives
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// A value that ptxas must keep in a register: it re-derives anything it can trace to a kernel parameter or a
+// special register (LDC / S2R + arithmetic in every round of a hot loop) but not the result of a shuffle.
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v) { return __shfl_sync(GATB_FULL, v, (int)(threadIdx.x & 31u)); }
+
 __device__ __forceinline__ int32_t warp_incl_scan_add(int32_t v)
 {
     int lane = lane_id();

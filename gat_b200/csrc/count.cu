@@ -117,9 +117,6 @@ struct WarpConsts {
     uint32_t lane, le_mask, stg, stg_pe, sentinel;
     uint64_t cent;                                  // global address of the entry array
 };
-// A value that ptxas must keep in a register: it re-derives anything it can trace to a kernel parameter or a
-// special register (LDC / S2R + arithmetic in every round of the hot loop) but not the result of a shuffle.
-__device__ __forceinline__ uint32_t pin_reg(uint32_t v) { return __shfl_sync(GATB_FULL, v, (int)(threadIdx.x & 31u)); }
 
 template <int COUNTER, bool LONG>
 __device__ __forceinline__ void run_item(const CountParams &p, const WarpConsts &wc, const Indexed &it, uint32_t acc_addr)

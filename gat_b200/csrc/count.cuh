@@ -175,7 +175,9 @@ struct StreamStatsParams {
     uint32_t n_chunks;              // chunks of rows_per_stage rows, dealt to the CTAs round-robin
     uint32_t n_stages, col_width;   // set by the launchers
     // pass 1 (outputs zeroed by the caller, accumulated with integer atomics)
-    const double *observed;
+    // the comparison with the observed value as integer tests (set by stats_stream_thresholds):
+    //   (double)v < observed  <=>  v < lt_thr  (or every v, flag 1);   (double)v == observed  <=>  flag 2 and v == eq_val
+    const uint32_t *lt_thr, *eq_val, *col_flags;
     unsigned long long *isum, *n_lt, *n_eq;
     unsigned long long *sq_lo, *sq_hi;   // sum of squares, 128 bits
     uint32_t *vmax;                 // largest value of the matrix
@@ -189,6 +191,7 @@ struct StreamStatsParams {
 };
 bool stats_stream_fits(const void *counts, uint64_t n_samples, uint32_t n_cols, size_t smem_optin);
 void stats_stream_geometry(StreamStatsParams &p);
+void stats_stream_thresholds(const double *observed, uint32_t n_cols, uint32_t *lt_thr, uint32_t *eq_val, uint32_t *flags);
 cudaError_t launch_stats_stream_pass1(cudaStream_t st, StreamStatsParams p, int sm_count);
 cudaError_t launch_stats_stream_select(cudaStream_t st, StreamStatsParams p, int sm_count);
 

@@ -106,4 +106,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity)
     return done != 0u;
 }
 
+// ---- 96-bit integer accumulation on the carry chain ----
+// (hi:lo) += v * v   (2^32 terms of < 2^64 each fit 96 bits); ptxas turns this into IMAD.WIDE.U32 with a carry-out
+// and one add-with-carry
+__device__ __forceinline__ void add96_sq(unsigned long long &lo, uint32_t &hi, uint32_t v)
+{
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %2;\n\tadd.cc.u64 %0, %0, t;\n\taddc.u32 %1, %1, 0;\n\t}"
+        : "+l"(lo), "+r"(hi) : "r"(v));
+}
+// n += carry out of a + b (two instructions, no predicate or select): with b = 2^32 - t this counts a >= t (t >= 1),
+// with b = ~t it counts a > t
+__device__ __forceinline__ void count_carry(uint32_t &n, uint32_t a, uint32_t b)
+{
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(n) : "r"(a), "r"(b));
+}
+
+// if (a == b) shared[addr] += 1, as ONE predicated reduction (no branch around it)
+__device__ __forceinline__ void red_inc_shared_if_eq(uint32_t addr, uint32_t a, uint32_t b)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
 }  // namespace gatb

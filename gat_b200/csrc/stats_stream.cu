@@ -14,12 +14,16 @@
 //   select   radix select of the two order statistics (CI bounds), 4 bits per pass from the highest non-zero
 //            nibble of the matrix maximum: per-CTA histograms [rank][nibble][column] in shared memory, flushed to
 //            global counters; stats_pick_kernel narrows prefix and rank between passes
+#include <algorithm>
+#include <cmath>
+
 #include "count.cuh"
 #include "ptx.cuh"
 
 namespace gatb {
 
 constexpr uint32_t SS_STAGE_BYTES = 32768;          // one stage of the ring
+constexpr uint32_t SS_ALL_LESS = 1u, SS_HAS_EQUAL = 2u;   // StreamStatsParams.col_flags
 constexpr uint32_t SS_WAIT_SPINS = 1u << 20;        // mbarrier polls before a CTA gives up (flags p.error: the call fails)
 
 __host__ __device__ __forceinline__ uint32_t ss_hist_stride(uint32_t n_cols) { return ((n_cols + 31u) & ~31u) + 1u; }   // = 1 mod 32
@@ -46,9 +50,15 @@ struct ChunkSeq {
     }
 };
 
-// MODE 0: pass 1, 1: select pass.  KC = columns per thread (thread (c, r) owns columns c, c + CW, ...)
+// the bits above the nibble a select pass at `shift` decides
+__host__ __device__ __forceinline__ uint32_t hmask_of(uint32_t shift) { return shift >= 28u ? 0u : (0xffffffffu << (shift + 4u)); }
+
+// MODE 0: pass 1, 1: select pass.  KC = columns per thread (thread (c, r) owns columns c, c + CW, ...).  The inner
+// loops address shared memory by 32-bit shared address and keep every per-element step to a handful of integer
+// instructions (about 12 in pass 1, 8 in a select pass): at 4 bytes per element the passes only stay HBM-bound if
+// the SMs can issue an element's work in the time its 4 bytes take to arrive.
 template <int MODE, int KC>
-__global__ void __launch_bounds__(512) stats_stream_kernel(StreamStatsParams p)
+__global__ void __launch_bounds__(1024) stats_stream_kernel(StreamStatsParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t T = blockDim.x, tid = threadIdx.x;
@@ -56,9 +66,10 @@ __global__ void __launch_bounds__(512) stats_stream_kernel(StreamStatsParams p)
     const uint32_t c = tid % CW, r = tid / CW;
     const uint32_t stage0 = smem_addr(smem);
     const uint32_t mbar0 = stage0 + p.n_stages * SS_STAGE_BYTES;
-    uint8_t *extra = smem + (size_t)p.n_stages * SS_STAGE_BYTES + 64;
+    const uint32_t hist0 = mbar0 + 64u;                     // MODE 1: [2][16][HS] counters
     const uint32_t row_bytes = p.n_cols * 4u;
     const uint32_t full_bytes = p.rows_per_stage * row_bytes;
+    const uint32_t HS = ss_hist_stride(p.n_cols);
 
     ChunkSeq seq;
     seq.n_local = blockIdx.x < p.n_chunks ? (p.n_chunks - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
@@ -68,10 +79,8 @@ __global__ void __launch_bounds__(512) stats_stream_kernel(StreamStatsParams p)
         for (uint32_t s = 0; s < p.n_stages; s++) mbar_init(mbar0 + 8u * s, 1u);
         fence_mbar_init();
     }
-    uint32_t *hist = reinterpret_cast<uint32_t *>(extra);   // MODE 1: [2][16][HS]
-    const uint32_t HS = ss_hist_stride(p.n_cols);
     if (MODE == 1)
-        for (uint32_t i = tid; i < 2u * 16u * HS; i += T) hist[i] = 0u;
+        for (uint32_t i = tid; i < 2u * 16u * HS; i += T) sts32(hist0 + 4u * i, 0u);
     __syncthreads();
 
     // the TMA producer: one thread; a full chunk is ONE bulk copy (rows are contiguous), the partial chunk at the
@@ -86,58 +95,69 @@ __global__ void __launch_bounds__(512) stats_stream_kernel(StreamStatsParams p)
     if (tid == 0)
         for (uint32_t q = 0; q < p.n_stages; q++) issue(q);
 
-    // per-column state
-    double obs[KC];
-    unsigned long long isum[KC], sq_lo[KC];
-    uint32_t sq_hi[KC], nlt[KC], neq[KC], vmax = 0, pre0[KC], pre1[KC];
+    // per-column state (a column past the end reads column 0 and is dropped when the results go out)
+    bool live[KC];
+    uint32_t coff[KC];                                      // byte offset of the column inside a row
+    uint32_t neg_thr[KC], inv_eq[KC];                       // pass 1: 2^32 - lt_thr and ~eq_val (count_carry)
+    unsigned long long sum[KC], sq_lo[KC];
+    uint32_t sq_hi[KC], nge[KC], ngt[KC], vmax = 0, nrows = 0;
+    uint32_t pre0[KC], pre1[KC], h0[KC];                    // select: prefixes, shared address of the column's counters
 #pragma unroll
     for (int k = 0; k < KC; k++) {
         const uint32_t col = c + (uint32_t)k * CW;
-        const bool live = col < p.n_cols;
-        obs[k] = (MODE == 0 && live) ? p.observed[col] : 0.0;
-        pre0[k] = (MODE == 1 && live) ? p.prefix[col] : 0u;
-        pre1[k] = (MODE == 1 && live) ? p.prefix[p.n_cols + col] : 0u;
-        isum[k] = sq_lo[k] = 0ull; sq_hi[k] = nlt[k] = neq[k] = 0u;
+        live[k] = col < p.n_cols;
+        coff[k] = live[k] ? col * 4u : 0u;
+        neg_thr[k] = (MODE == 0 && live[k]) ? 0u - p.lt_thr[col] : 0u;
+        inv_eq[k] = (MODE == 0 && live[k]) ? ~p.eq_val[col] : 0u;
+        pre0[k] = (MODE == 1 && live[k]) ? p.prefix[col] : 0u;
+        pre1[k] = (MODE == 1 && live[k]) ? p.prefix[p.n_cols + col] : 0u;
+        // (a dead column counts into the padding slot HS - 1 of its rows, which is never flushed)
+        h0[k] = pin_reg(hist0 + 4u * (live[k] ? col : HS - 1u));
+        // while both ranks share their prefix one histogram serves both: the second comparison gets a value that
+        // no masked element can take (bits outside the mask)
+        if (MODE == 1 && pre0[k] == pre1[k]) pre1[k] = ~hmask_of(p.shift);
+        pre0[k] = pin_reg(pre0[k]); pre1[k] = pin_reg(pre1[k]);
+        coff[k] = pin_reg(coff[k]);
+        sum[k] = sq_lo[k] = 0ull;
+        sq_hi[k] = nge[k] = ngt[k] = 0u;
     }
-    const uint32_t hmask = p.shift >= 28 ? 0u : (0xffffffffu << (p.shift + 4));      // bits already decided
+    const uint32_t hmask = pin_reg(hmask_of(p.shift));      // bits already decided
+    const uint32_t HS4 = pin_reg(4u * HS), H1 = pin_reg(4u * 16u * HS), shift = pin_reg(p.shift);
+    const uint32_t stage_base = pin_reg(stage0), rows_full = pin_reg(p.rows_per_stage);
+    const uint32_t dummy = pin_reg(hist0 + 4u * (HS - 1u));  // (padding slot: never flushed)
 
     for (uint32_t q = 0; q < n_chunks; q++) {
         const uint32_t s = q % p.n_stages, rows = seq.rows(p, q);
-        const uint32_t *stage = reinterpret_cast<const uint32_t *>(smem + (size_t)s * SS_STAGE_BYTES);
+        const uint32_t stage = stage_base + s * SS_STAGE_BYTES;
         int timed_out = 0;
-        if (rows == p.rows_per_stage) {
+        if (rows == rows_full) {
             uint32_t spins = 0;
             while (!mbar_try_wait(mbar0 + 8u * s, (q / p.n_stages) & 1u))
                 if (++spins > SS_WAIT_SPINS) { timed_out = 1; break; }
         } else if (rows) {
-            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + (size_t)s * SS_STAGE_BYTES);
             const uint32_t *src = p.counts + seq.row0(p, q) * p.n_cols;
-            for (uint32_t i = tid; i < rows * p.n_cols; i += T) dst[i] = src[i];
+            for (uint32_t i = tid; i < rows * p.n_cols; i += T) sts32(stage + 4u * i, src[i]);
             __syncthreads();
         }
+#pragma unroll 2
         for (uint32_t row = r; row < rows; row += RW) {
-            const uint32_t *rowp = stage + row * p.n_cols;
+            const uint32_t rowa = stage + row * row_bytes;
+            if (MODE == 0) nrows++;
 #pragma unroll
             for (int k = 0; k < KC; k++) {
-                const uint32_t col = c + (uint32_t)k * CW;
-                if (col < p.n_cols) {
-                    const uint32_t v = rowp[col];
-                    if (MODE == 0) {
-                        const double x = (double)v;
-                        const unsigned long long v2 = (unsigned long long)v * v;
-                        isum[k] += v;
-                        sq_lo[k] += v2;
-                        sq_hi[k] += (sq_lo[k] < v2) ? 1u : 0u;   // carry out of the low 64 bits
-                        nlt[k] += (x < obs[k]) ? 1u : 0u;        // searchargsorted + cmpDouble (gat/Engine.pyx:122-127, 1549-1557)
-                        neq[k] += (x == obs[k]) ? 1u : 0u;
-                        vmax = max(vmax, v);
-                    } else {
-                        const uint32_t bin = (v >> p.shift) & 15u;
-                        const bool m0 = (v & hmask) == pre0[k], m1 = (v & hmask) == pre1[k];
-                        // while both ranks still share their prefix one histogram serves both
-                        if (m0) atomicAdd(&hist[bin * HS + col], 1u);
-                        if (m1 && pre0[k] != pre1[k]) atomicAdd(&hist[(16u + bin) * HS + col], 1u);
-                    }
+                const uint32_t v = lds32(rowa + coff[k]);
+                if (MODE == 0) {
+                    sum[k] += v;
+                    add96_sq(sq_lo[k], sq_hi[k], v);
+                    count_carry(nge[k], v, neg_thr[k]);          // v >= lt_thr; searchargsorted + cmpDouble (gat/Engine.pyx:122-127, 1549-1557)
+                    count_carry(ngt[k], v, inv_eq[k]);           // v > eq_val (#equal = #(>= t) - #(> t) when observed is an integer t)
+                    vmax = max(vmax, v);
+                } else {
+                    // unconditional reductions (ptxas branches around a predicated one): an element that does not
+                    // carry the prefix counts into a padding slot, where the hardware merges the lanes' increments
+                    const uint32_t cell = ((v >> shift) & 15u) * HS4 + h0[k], hi = v & hmask;
+                    red_add_shared(hi == pre0[k] ? cell : dummy, 1u);
+                    red_add_shared(hi == pre1[k] ? cell + H1 : dummy, 1u);
                 }
             }
         }
@@ -156,16 +176,22 @@ __global__ void __launch_bounds__(512) stats_stream_kernel(StreamStatsParams p)
 #pragma unroll
         for (int k = 0; k < KC; k++) {
             const uint32_t col = c + (uint32_t)k * CW;
-            if (col < p.n_cols && n_chunks) {
-                if (isum[k]) atomicAdd(p.isum + col, isum[k]);
+            if (live[k] && nrows) {
+                const uint32_t fl = p.col_flags[col];
+                const unsigned long long lo = sq_lo[k];
                 unsigned long long hi = sq_hi[k];
-                if (sq_lo[k]) {
-                    const unsigned long long old = atomicAdd(p.sq_lo + col, sq_lo[k]);
-                    hi += (old + sq_lo[k] < old) ? 1ull : 0ull;
+                if (sum[k]) atomicAdd(p.isum + col, sum[k]);
+                if (lo) {
+                    const unsigned long long old = atomicAdd(p.sq_lo + col, lo);
+                    hi += (old + lo < old) ? 1ull : 0ull;
                 }
                 if (hi) atomicAdd(p.sq_hi + col, hi);
-                if (nlt[k]) atomicAdd(p.n_lt + col, (unsigned long long)nlt[k]);
-                if (neq[k]) atomicAdd(p.n_eq + col, (unsigned long long)neq[k]);
+                // lt_thr = 0: nothing is smaller (and the carry count is void: 2^32 - 0 wraps).  SS_HAS_EQUAL: observed is
+                // an integer t and lt_thr = eq_val = t, so #equal = #(>= t) - #(> t); for t = 0 every row is >= t
+                const uint32_t ge = p.lt_thr[col] ? nge[k] : nrows;
+                const uint32_t lt = (fl & SS_ALL_LESS) ? nrows : nrows - ge, eq = (fl & SS_HAS_EQUAL) ? ge - ngt[k] : 0u;
+                if (lt) atomicAdd(p.n_lt + col, (unsigned long long)lt);
+                if (eq) atomicAdd(p.n_eq + col, (unsigned long long)eq);
             }
         }
         vmax = __reduce_max_sync(GATB_FULL, vmax);
@@ -174,7 +200,7 @@ __global__ void __launch_bounds__(512) stats_stream_kernel(StreamStatsParams p)
     if (MODE == 1) {
         __syncthreads();
         for (uint32_t i = tid; i < 2u * 16u * HS; i += T) {
-            const uint32_t v = hist[i], col = i % HS;
+            const uint32_t v = lds32(hist0 + 4u * i), col = i % HS;
             if (v && col < p.n_cols) atomicAdd(p.hist + (uint64_t)(i / HS) * p.n_cols + col, v);
         }
     }
@@ -214,7 +240,7 @@ __global__ void __launch_bounds__(256) stats_pick_commit_kernel(StreamStatsParam
 template <int MODE>
 static cudaError_t launch_stream_mode(cudaStream_t st, const StreamStatsParams &p, int sm_count)
 {
-    const int threads = MODE == 1 ? 512 : 256;
+    const int threads = MODE == 1 ? 1024 : 512;
     StreamStatsParams q = p;
     uint32_t cw = 1;
     while (cw < p.n_cols && cw < (uint32_t)threads) cw <<= 1;
@@ -229,8 +255,7 @@ static cudaError_t launch_stream_mode(cudaStream_t st, const StreamStatsParams &
     stats_stream_kernel<MODE, KC_><<<grid, threads, smem, st>>>(q);
     if (kc <= 1) { GATB_SS_LAUNCH(1) }
     else if (kc <= 2) { GATB_SS_LAUNCH(2) }
-    else if (kc <= 4) { GATB_SS_LAUNCH(4) }
-    else { GATB_SS_LAUNCH(8) }
+    else { GATB_SS_LAUNCH(4) }                      // (n_cols <= 2048, at least 512 threads)
 #undef GATB_SS_LAUNCH
     return cudaGetLastError();
 }
@@ -242,7 +267,7 @@ bool stats_stream_fits(const void *counts, uint64_t n_samples, uint32_t n_cols, 
     if ((uint64_t)n_cols * 4u * 4u > SS_STAGE_BYTES) return false;                 // at least 4 rows per stage
     StreamStatsParams p;
     p.n_cols = n_cols; p.n_stages = 2;
-    return stats_stream_smem(p, 1, 512) <= smem_optin;
+    return stats_stream_smem(p, 1, 1024) <= smem_optin;
 }
 
 void stats_stream_geometry(StreamStatsParams &p)
@@ -250,6 +275,24 @@ void stats_stream_geometry(StreamStatsParams &p)
     const uint32_t row_bytes = p.n_cols * 4u;
     p.rows_per_stage = std::max(4u, (SS_STAGE_BYTES / row_bytes) & ~3u);            // multiple of 4: chunks start 16-byte aligned
     p.n_chunks = (uint32_t)((p.n_samples + p.rows_per_stage - 1u) / p.rows_per_stage);
+}
+
+// the comparisons of pass 1 without floating point: for an integer v and a real t, v < t <=> v < ceil(t), and v == t
+// only if t is itself an integer in range
+void stats_stream_thresholds(const double *observed, uint32_t n_cols, uint32_t *lt_thr, uint32_t *eq_val, uint32_t *flags)
+{
+    for (uint32_t a = 0; a < n_cols; a++) {
+        const double t = observed[a];
+        lt_thr[a] = 0u; eq_val[a] = 0u; flags[a] = 0u;
+        if (!(t > 0.0)) {                           // t <= 0 or NaN: nothing is smaller
+            if (t == 0.0) flags[a] |= SS_HAS_EQUAL;
+        } else if (t > 4294967295.0) flags[a] |= SS_ALL_LESS;
+        else {
+            const double up = ceil(t);
+            lt_thr[a] = (uint32_t)up;
+            if (up == t) { eq_val[a] = (uint32_t)t; flags[a] |= SS_HAS_EQUAL; }
+        }
+    }
 }
 
 cudaError_t launch_stats_stream_pass1(cudaStream_t st, StreamStatsParams p, int sm_count)

@@ -40,7 +40,9 @@ def main():
         ms, launches = ctx.profile_read()["other"]
         ctx.profile(False)
         ms, launches = ms / args.reps, launches // args.reps
-        passes = 1 + (launches - 1) // 3 if name == "streamed" else 6       # tiled: pass 1, pass 2, 4 radix passes in one kernel
+        # streamed: every profiled scope (pass 1, each select pass) reads the matrix once; tiled: pass 1, pass 2 and the
+        # four radix passes inside its select kernel
+        passes = launches if name == "streamed" else 6
         out[name] = {"kernel_ms": ms, "launches": launches, "passes_over_matrix": passes,
                      "GBps": passes * S * A * 4.0 / (ms / 1000.0) / 1e9}
         ctx.close()
