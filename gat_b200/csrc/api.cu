@@ -1585,7 +1585,7 @@ static int stream_stats(gatb_ctx *ctx, const uint32_t *dc, uint64_t l, uint32_t 
     for (int shift = top; shift >= 0; shift -= 4) {
         p.shift = (uint32_t)shift;
         ProfScope ps(ctx, PROF_OTHER);
-        CU(ctx, launch_stats_stream_select(st, p, ctx->sm_count));
+        CU(ctx, launch_stats_stream_select(st, p, ctx->sm_count, ctx->smem_optin));
     }
     o.qlo.resize(A); o.qhi.resize(A);
     CU(ctx, cudaMemcpyAsync(o.qlo.data(), d_q.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -193,7 +193,7 @@ bool stats_stream_fits(const void *counts, uint64_t n_samples, uint32_t n_cols, 
 void stats_stream_geometry(StreamStatsParams &p);
 void stats_stream_thresholds(const double *observed, uint32_t n_cols, uint32_t *lt_thr, uint32_t *eq_val, uint32_t *flags);
 cudaError_t launch_stats_stream_pass1(cudaStream_t st, StreamStatsParams p, int sm_count);
-cudaError_t launch_stats_stream_select(cudaStream_t st, StreamStatsParams p, int sm_count);
+cudaError_t launch_stats_stream_select(cudaStream_t st, StreamStatsParams p, int sm_count, size_t smem_optin);
 
 void launch_stats_pass1(cudaStream_t st, const StatsParams &p);
 void launch_stats_pass2(cudaStream_t st, const StatsParams &p);

@@ -126,16 +126,21 @@ __global__ void __launch_bounds__(1024) stats_stream_kernel(StreamStatsParams p)
     const uint32_t stage_base = pin_reg(stage0), rows_full = pin_reg(p.rows_per_stage);
     const uint32_t dummy = pin_reg(hist0 + 4u * (HS - 1u));  // (padding slot: never flushed)
 
-    for (uint32_t q = 0; q < n_chunks; q++) {
-        const uint32_t s = q % p.n_stages, rows = seq.rows(p, q);
+    // (stage, parity and first row of the running chunk are carried along: no division per chunk)
+    uint32_t s = 0, parity = 0;
+    uint64_t row0 = (uint64_t)blockIdx.x * rows_full;
+    const uint64_t row_step = (uint64_t)gridDim.x * rows_full;
+    const uint32_t n_stages = pin_reg(p.n_stages);
+    for (uint32_t q = 0; q < n_chunks; q++, row0 += row_step) {
+        const uint32_t rows = row0 + rows_full <= p.n_samples ? rows_full : (uint32_t)(p.n_samples - row0);
         const uint32_t stage = stage_base + s * SS_STAGE_BYTES;
         int timed_out = 0;
         if (rows == rows_full) {
             uint32_t spins = 0;
-            while (!mbar_try_wait(mbar0 + 8u * s, (q / p.n_stages) & 1u))
+            while (!mbar_try_wait(mbar0 + 8u * s, parity))
                 if (++spins > SS_WAIT_SPINS) { timed_out = 1; break; }
         } else if (rows) {
-            const uint32_t *src = p.counts + seq.row0(p, q) * p.n_cols;
+            const uint32_t *src = p.counts + row0 * p.n_cols;
             for (uint32_t i = tid; i < rows * p.n_cols; i += T) sts32(stage + 4u * i, src[i]);
             __syncthreads();
         }
@@ -167,7 +172,8 @@ __global__ void __launch_bounds__(1024) stats_stream_kernel(StreamStatsParams p)
             if (tid == 0) *p.error = 1u;
             break;
         }
-        if (tid == 0) issue(q + p.n_stages);
+        if (tid == 0) issue(q + n_stages);
+        if (++s == n_stages) { s = 0; parity ^= 1u; }
     }
 
     if (MODE == 0) {
@@ -302,9 +308,12 @@ cudaError_t launch_stats_stream_pass1(cudaStream_t st, StreamStatsParams p, int 
 }
 
 // one 4-bit select pass at p.shift (prefix / rank / hist as the previous pass left them)
-cudaError_t launch_stats_stream_select(cudaStream_t st, StreamStatsParams p, int sm_count)
+cudaError_t launch_stats_stream_select(cudaStream_t st, StreamStatsParams p, int sm_count, size_t smem_optin)
 {
-    p.n_stages = 2;
+    // one CTA per SM (the histograms take most of its shared memory): as many stages as fit next to them, so that
+    // more than one copy is in flight while a stage is being worked off
+    p.n_stages = 4;
+    while (p.n_stages > 2 && stats_stream_smem(p, 1, 1024) > smem_optin) p.n_stages--;
     cudaError_t e = launch_stream_mode<1>(st, p, sm_count);
     if (e != cudaSuccess) return e;
     const unsigned nb = (2u * p.n_cols + 255u) / 256u;
