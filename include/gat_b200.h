@@ -296,7 +296,10 @@ int  gatb_microbench(int device, int which, uint64_t bytes, int repeats, double 
  * CI95 low/high (sorted[min(off,l-1)], sorted[max(l-off,0)], off=int(0.05*l)), fold with pseudo-count,
  * empirical two-sided p-value.  counts is [n_samples][n_cols] uint32 (is_float==0) or float64
  * (is_float!=0), device memory if counts_is_device else host.  observed[n_cols], ref_fold[n_cols]
- * (NULL = no --null reference) and all outputs are host arrays of n_cols doubles. */
+ * (NULL = no --null reference) and all outputs are host arrays of n_cols doubles.
+ * uint32 matrices are reduced with integer arithmetic only (sum, 128-bit sum of squares, counts, radix select): every
+ * output but stddev is exact, stddev is the correctly rounded sqrt((n*sum x^2 - (sum x)^2) / n^2) -- within a few ulp
+ * of numpy.std -- and no output depends on the GPU, the grid or on which other columns share the matrix. */
 int  gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float, int counts_is_device,
                        uint64_t n_samples, int n_cols, const double *observed, const double *ref_fold,
                        double pseudo_count, double *expected, double *stddev, double *lower95,
