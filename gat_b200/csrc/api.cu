@@ -1521,6 +1521,15 @@ extern "C" int gatb_count_work(gatb_sampler *s, const gatb_annotations *annos, u
 // column statistics
 // The streaming passes of stats_stream.cu on a device-resident uint32 matrix (what gatb_run leaves behind):
 // pass 1 always; with `full`, pass 2 and the select passes as well.  Outputs as host vectors.
+// sum (x - mean)^2 of n uint32 values from their exact sums: (n * sum x^2 - (sum x)^2) / n with the numerator exact in
+// 128 bits (x < 2^32, n < 2^32: both products stay below 2^128), rounded once when it becomes a double
+static double exact_sumsq_dev(uint64_t n, unsigned long long sum, unsigned long long sq_lo, unsigned long long sq_hi)
+{
+    const unsigned __int128 sq = ((unsigned __int128)sq_hi << 64) | sq_lo;
+    const unsigned __int128 num = (unsigned __int128)n * sq - (unsigned __int128)sum * sum;
+    return (double)num / (double)n;
+}
+
 struct StreamStatsOut {
     std::vector<double> sum, sumsq, qlo, qhi;       // sumsq = sum (x - mean)^2
     std::vector<unsigned long long> n_lt, n_eq;
@@ -1559,11 +1568,7 @@ static int stream_stats(gatb_ctx *ctx, const uint32_t *dc, uint64_t l, uint32_t 
     o.n_eq.assign(h_acc.begin() + 2 * (size_t)A, h_acc.begin() + 3 * (size_t)A);
     for (uint32_t a = 0; a < A; a++) {
         o.sum[a] = (double)h_acc[a];
-        // sum (x - mean)^2 = (n * sum x^2 - (sum x)^2) / n, the numerator exact in 128 bits (x < 2^32, n < 2^32:
-        // both products stay below 2^128), rounded once when it becomes a double
-        const unsigned __int128 sq = ((unsigned __int128)h_acc[4 * (size_t)A + a] << 64) | h_acc[3 * (size_t)A + a];
-        const unsigned __int128 num = (unsigned __int128)l * sq - (unsigned __int128)h_acc[a] * h_acc[a];
-        o.sumsq[a] = (double)num / (double)l;
+        o.sumsq[a] = exact_sumsq_dev(l, h_acc[a], h_acc[3 * (size_t)A + a], h_acc[4 * (size_t)A + a]);
     }
     if (!full) return GATB_OK;
 
@@ -1642,14 +1647,15 @@ extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float
     } else {
         // float64 matrices (nucleotide-density, gat-compare), very wide or unaligned ones: column-tiled kernels (count.cu)
         DevBuf<double> d_obs, d_sum, d_sq, d_mean, d_qlo, d_qhi;
-        DevBuf<unsigned long long> d_cnt;
+        DevBuf<unsigned long long> d_cnt;               // n_lt | n_eq | sq_lo | sq_hi | isum
         CU(ctx, d_obs.upload(obs_eff.data(), A, st));
         CU(ctx, d_sum.alloc(A)); CU(ctx, d_sq.alloc(A)); CU(ctx, d_qlo.alloc(A)); CU(ctx, d_qhi.alloc(A));
-        CU(ctx, d_cnt.alloc(2 * (size_t)A));
+        CU(ctx, d_cnt.alloc(5 * (size_t)A));
         StatsParams p;
         memset(&p, 0, sizeof(p));
         p.counts = dc; p.is_float = is_float; p.n_samples = l; p.n_cols = A; p.observed = d_obs.p;
         p.sum = d_sum.p; p.sumsq_dev = d_sq.p; p.n_lt = d_cnt.p; p.n_eq = d_cnt.p + A;
+        if (!is_float) { p.sq_lo = d_cnt.p + 2 * (size_t)A; p.sq_hi = d_cnt.p + 3 * (size_t)A; p.isum = d_cnt.p + 4 * (size_t)A; }
         p.q_lo = d_qlo.p; p.q_hi = d_qhi.p;
         p.rank_lo = rank_lo; p.rank_hi = rank_hi;
         { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass1(st, p); }
@@ -1659,14 +1665,23 @@ extern "C" int gatb_column_stats(gatb_ctx *ctx, const void *counts, int is_float
         for (uint32_t a = 0; a < A; a++) h_mean[a] = h_sum[a] / (double)l;        // numpy.mean (:1671)
         CU(ctx, d_mean.upload(h_mean.data(), A, st));
         p.mean = d_mean.p;
-        { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass2(st, p); }
+        // float64 matrices: second pass for sum (x - mean)^2; uint32 matrices: the exact integer formula of the streamed
+        // passes, so that a column's statistics do not depend on which of the two kernels its matrix was given to
+        std::vector<unsigned long long> h_sqi;
+        if (is_float) { ProfScope ps(ctx, PROF_OTHER); launch_stats_pass2(st, p); }
+        else {
+            h_sqi.resize(3 * (size_t)A);
+            CU(ctx, cudaMemcpyAsync(h_sqi.data(), d_cnt.p + 2 * (size_t)A, h_sqi.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        }
         { ProfScope ps(ctx, PROF_OTHER); launch_stats_select(st, p); }
         CU(ctx, cudaGetLastError());
-        CU(ctx, cudaMemcpyAsync(h_sq.data(), d_sq.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (is_float) CU(ctx, cudaMemcpyAsync(h_sq.data(), d_sq.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU(ctx, cudaMemcpyAsync(h_qlo.data(), d_qlo.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU(ctx, cudaMemcpyAsync(h_qhi.data(), d_qhi.p, A * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt.p, 2 * (size_t)A * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CU(ctx, cudaStreamSynchronize(st));
+        if (!is_float)
+            for (uint32_t a = 0; a < A; a++) h_sq[a] = exact_sumsq_dev(l, h_sqi[2 * (size_t)A + a], h_sqi[a], h_sqi[A + a]);
     }
 
     for (uint32_t a = 0; a < A; a++) {

@@ -626,28 +626,39 @@ __device__ __forceinline__ double load_val(const StatsParams &p, uint64_t s, uin
 
 __global__ void __launch_bounds__(STATS_COLS * STATS_ROWS) stats_pass1_kernel(StatsParams p)
 {
-    __shared__ unsigned long long su[3][STATS_ROWS][STATS_COLS];
+    __shared__ unsigned long long su[5][STATS_ROWS][STATS_COLS];
     __shared__ double sd[STATS_ROWS][STATS_COLS];
     const StatsThread t = stats_thread(p);
     const double obs = t.live ? p.observed[t.col] : 0.0;
-    unsigned long long isum = 0, nlt = 0, neq = 0;
+    unsigned long long isum = 0, nlt = 0, neq = 0, sq_lo = 0, sq_hi = 0;
     double fsum = 0.0;
     if (t.live)
         for (uint64_t s = t.r; s < p.n_samples; s += STATS_ROWS) {
             double x;
             if (p.is_float) { x = reinterpret_cast<const double *>(p.counts)[s * p.n_cols + t.col]; fsum += x; }
-            else { uint32_t v = reinterpret_cast<const uint32_t *>(p.counts)[s * p.n_cols + t.col]; isum += v; x = (double)v; }
+            else {
+                const uint32_t v = reinterpret_cast<const uint32_t *>(p.counts)[s * p.n_cols + t.col];
+                const unsigned long long v2 = (unsigned long long)v * v;
+                isum += v; x = (double)v;
+                sq_lo += v2; sq_hi += (sq_lo < v2) ? 1ull : 0ull;       // exact sum of squares (as in stats_stream.cu)
+            }
             nlt += (x < obs) ? 1ull : 0ull;      // searchargsorted + cmpDouble (gat/Engine.pyx:122-127, 1549-1557)
             neq += (x == obs) ? 1ull : 0ull;
         }
-    su[0][t.r][t.c] = nlt; su[1][t.r][t.c] = neq; su[2][t.r][t.c] = isum; sd[t.r][t.c] = fsum;
+    su[0][t.r][t.c] = nlt; su[1][t.r][t.c] = neq; su[2][t.r][t.c] = isum; su[3][t.r][t.c] = sq_lo; su[4][t.r][t.c] = sq_hi;
+    sd[t.r][t.c] = fsum;
     __syncthreads();
     if (t.r == 0 && t.live) {
-        unsigned long long a = 0, b = 0, c = 0;
+        unsigned long long a = 0, b = 0, c = 0, lo = 0, hi = 0;
         double f = 0.0;
-        for (int r = 0; r < STATS_ROWS; r++) { a += su[0][r][t.c]; b += su[1][r][t.c]; c += su[2][r][t.c]; f += sd[r][t.c]; }
+        for (int r = 0; r < STATS_ROWS; r++) {
+            a += su[0][r][t.c]; b += su[1][r][t.c]; c += su[2][r][t.c]; f += sd[r][t.c];
+            const unsigned long long l2 = su[3][r][t.c];
+            lo += l2; hi += su[4][r][t.c] + ((lo < l2) ? 1ull : 0ull);
+        }
         p.n_lt[t.col] = a; p.n_eq[t.col] = b;
         p.sum[t.col] = p.is_float ? f : (double)c;
+        if (p.sq_lo) { p.sq_lo[t.col] = lo; p.sq_hi[t.col] = hi; p.isum[t.col] = c; }
     }
 }
 

@@ -141,6 +141,8 @@ struct StatsParams {
     double *sumsq_dev;              // sum (x-mean)^2
     unsigned long long *n_lt;       // #{ x < obs } = insertion point of obs (gat/Engine.pyx:1549-1557)
     unsigned long long *n_eq;       // #{ x == obs }
+    unsigned long long *sq_lo, *sq_hi;   // uint32 matrices: exact sum of squares, 128 bits (the variance follows on the host)
+    unsigned long long *isum;       // uint32 matrices: the exact integer sum
     double *q_lo, *q_hi;            // order statistics at ranks rank_lo / rank_hi
     uint64_t rank_lo, rank_hi;
     const double *mean;             // device [n_cols] (second pass)
@@ -174,6 +176,7 @@ struct StreamStatsParams {
     uint32_t rows_per_stage;        // rows of one ring stage (multiple of 4: every chunk starts 16-byte aligned)
     uint32_t n_chunks;              // chunks of rows_per_stage rows, dealt to the CTAs round-robin
     uint32_t n_stages, col_width;   // set by the launchers
+    int use_tma;                    // 0: the matrix is not 16-byte aligned, the threads copy the chunks themselves
     // pass 1 (outputs zeroed by the caller, accumulated with integer atomics)
     // the comparison with the observed value as integer tests (set by stats_stream_thresholds):
     //   (double)v < observed  <=>  v < lt_thr  (or every v, flag 1);   (double)v == observed  <=>  flag 2 and v == eq_val

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(1024) stats_stream_kernel(StreamStatsParams p)
     // the TMA producer: one thread; a full chunk is ONE bulk copy (rows are contiguous), the partial chunk at the
     // very end of the matrix is copied by the threads themselves
     auto issue = [&](uint32_t q) {
-        if (q < n_chunks && seq.rows(p, q) == p.rows_per_stage) {
+        if (p.use_tma && q < n_chunks && seq.rows(p, q) == p.rows_per_stage) {
             const uint32_t s = q % p.n_stages;
             mbar_expect_tx(mbar0 + 8u * s, full_bytes);
             bulk_copy_g2s(stage0 + s * SS_STAGE_BYTES, p.counts + seq.row0(p, q) * p.n_cols, full_bytes, mbar0 + 8u * s);
@@ -131,15 +131,16 @@ __global__ void __launch_bounds__(1024) stats_stream_kernel(StreamStatsParams p)
     uint64_t row0 = (uint64_t)blockIdx.x * rows_full;
     const uint64_t row_step = (uint64_t)gridDim.x * rows_full;
     const uint32_t n_stages = pin_reg(p.n_stages);
+    const bool use_tma = p.use_tma != 0;
     for (uint32_t q = 0; q < n_chunks; q++, row0 += row_step) {
         const uint32_t rows = row0 + rows_full <= p.n_samples ? rows_full : (uint32_t)(p.n_samples - row0);
         const uint32_t stage = stage_base + s * SS_STAGE_BYTES;
         int timed_out = 0;
-        if (rows == rows_full) {
+        if (rows == rows_full && use_tma) {
             uint32_t spins = 0;
             while (!mbar_try_wait(mbar0 + 8u * s, parity))
                 if (++spins > SS_WAIT_SPINS) { timed_out = 1; break; }
-        } else if (rows) {
+        } else if (rows) {                          // (the partial last chunk; every chunk of an unaligned matrix)
             const uint32_t *src = p.counts + row0 * p.n_cols;
             for (uint32_t i = tid; i < rows * p.n_cols; i += T) sts32(stage + 4u * i, src[i]);
             __syncthreads();
@@ -269,7 +270,7 @@ static cudaError_t launch_stream_mode(cudaStream_t st, const StreamStatsParams &
 // can the streaming passes take this matrix?  (uint32, rows short enough for a stage, histograms that fit)
 bool stats_stream_fits(const void *counts, uint64_t n_samples, uint32_t n_cols, size_t smem_optin)
 {
-    if (((uintptr_t)counts & 15u) != 0 || n_samples == 0 || n_samples >= (1ull << 32)) return false;
+    if (((uintptr_t)counts & 3u) != 0 || n_samples == 0 || n_samples >= (1ull << 32)) return false;
     if ((uint64_t)n_cols * 4u * 4u > SS_STAGE_BYTES) return false;                 // at least 4 rows per stage
     StreamStatsParams p;
     p.n_cols = n_cols; p.n_stages = 2;
@@ -281,6 +282,8 @@ void stats_stream_geometry(StreamStatsParams &p)
     const uint32_t row_bytes = p.n_cols * 4u;
     p.rows_per_stage = std::max(4u, (SS_STAGE_BYTES / row_bytes) & ~3u);            // multiple of 4: chunks start 16-byte aligned
     p.n_chunks = (uint32_t)((p.n_samples + p.rows_per_stage - 1u) / p.rows_per_stage);
+    // (a plane of a [counter][sample][column] tensor may start 4, 8 or 12 bytes off: same passes, the threads copy)
+    p.use_tma = ((uintptr_t)p.counts & 15u) == 0 ? 1 : 0;
 }
 
 // the comparisons of pass 1 without floating point: for an integer v and a real t, v < t <=> v < ceil(t), and v == t

@@ -322,3 +322,44 @@ def test_streamed_column_stats_exact_and_layout_independent(ctx):
             block = ctx.column_stats(np.ascontiguousarray(counts[:, b0:b1]), obs[b0:b1], pseudo_count=1.0)
             for key in ("expected", "stddev", "lower95", "upper95", "fold", "pvalue"):
                 assert np.array_equal(block[key], got[key][b0:b1]), (l, A, key)
+
+
+def test_column_stats_do_not_depend_on_the_kernel_that_computes_them(ctx, monkeypatch):
+    """a uint32 matrix is reduced by the TMA-streamed passes, by the same passes without TMA when its base is not
+    16-byte aligned (a plane of a [counter][sample][column] tensor), or by the column-tiled kernels (very wide
+    matrices, GATB_STATS_STREAM=0): every output must agree bit for bit, stddev included -- a 2-GPU run found the
+    column-sharded statistics differing from the 1-GPU ones in the last bit of stddev when the paths did not"""
+    emulated = hasattr(ctx.lib, "gatb_emulation_marker")
+    monkeypatch.setenv("GATB_STATS_STREAM", "0")
+    if emulated:
+        import emu_context
+        tiled = emu_context.context()
+    else:
+        from gat_b200 import device
+        tiled = device.Context(0)
+    monkeypatch.delenv("GATB_STATS_STREAM")
+    rng = np.random.default_rng(19)
+    try:
+        for l, A in ((3001, 10), (3001, 20), (1000, 33), (4100, 1000)):
+            scale = rng.choice([1, 5, 300, 70000, 4000000, 2 ** 32 - 1], size=A)
+            vals = (rng.random((l, A)) * scale).astype(np.uint32)
+            obs = vals[0].astype(np.float64)
+            a = ctx.column_stats(vals, obs, pseudo_count=1.0)
+            c = tiled.column_stats(vals, obs, pseudo_count=1.0)
+            if emulated:                                   # (emulated device memory is host memory)
+                hold = np.zeros(l * A + 4, dtype=np.uint32)
+                hold[1:1 + l * A] = vals.ravel()
+                ptr = hold.ctypes.data + 4
+            else:
+                import torch
+                hold = torch.zeros(l * A + 4, dtype=torch.int32, device="cuda")
+                hold[1:1 + l * A] = torch.from_numpy(vals.view(np.int32).ravel()).cuda()
+                torch.cuda.synchronize()
+                ptr = hold.data_ptr() + 4
+            assert ptr % 16 == 4
+            b = ctx.column_stats(None, obs, device_ptr=ptr, n_samples=l, n_cols=A, is_float=False)
+            for key in ("expected", "stddev", "lower95", "upper95", "fold", "pvalue"):
+                assert np.array_equal(a[key], b[key]), (l, A, key, "unaligned")
+                assert np.array_equal(a[key], c[key]), (l, A, key, "column-tiled")
+    finally:
+        tiled.close()
