@@ -121,10 +121,4 @@ __device__ __forceinline__ void count_carry(uint32_t &n, uint32_t a, uint32_t b)
     asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(n) : "r"(a), "r"(b));
 }
 
-// if (a == b) shared[addr] += 1, as ONE predicated reduction (no branch around it)
-__device__ __forceinline__ void red_inc_shared_if_eq(uint32_t addr, uint32_t a, uint32_t b)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-
 }  // namespace gatb

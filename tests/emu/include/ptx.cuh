@@ -54,9 +54,4 @@ __device__ __forceinline__ void add96_sq(unsigned long long &lo, uint32_t &hi, u
 
 __device__ __forceinline__ void count_carry(uint32_t &n, uint32_t a, uint32_t b) { n += (uint32_t)(((uint64_t)a + b) >> 32); }
 
-__device__ __forceinline__ void red_inc_shared_if_eq(uint32_t addr, uint32_t a, uint32_t b)
-{
-    if (a == b) emu_sts(addr, emu_lds<uint32_t>(addr) + 1u);
-}
-
 }  // namespace gatb
