@@ -90,3 +90,13 @@ def random_problem(rng, n_contigs=3, n_iso=0, n_annot=4, span=200000, nseg=60, n
     cws = [cws[c] for c in order]
     return dict(unit_contig=unit_contig, unit_segments=unit_segments, unit_workspace=unit_workspace,
                 annotations=annotations, cws_nseg=cws, has_isochores=n_iso > 0, n_contigs=len(order))
+
+
+def new_context_like(ctx):
+    """a fresh context of the same kind as `ctx` (the library reads its environment knobs when a context is created):
+    cuda:0, or the SIMT-emulated build when `ctx` is the emulated one (tests/test_emu_parity.py)"""
+    if hasattr(ctx.lib, "gatb_emulation_marker"):
+        import emu_context
+        return emu_context.context()
+    from gat_b200 import device
+    return device.Context(0)

@@ -55,6 +55,7 @@ CASES = [
     ("test_gpu_round2", "test_streamed_column_stats_exact_and_layout_independent", {}),
     ("test_gpu_round2", "test_column_stats_do_not_depend_on_the_kernel_that_computes_them", {}),
     ("test_gpu_parity", "test_async_annotations_same_counts_and_deferred_errors", {}),
+    ("test_gpu_parity", "test_count_index_geometries_match_oracle", {}),
     ("test_gpu_properties", "test_isochore_config_matches_oracle", {}),
 ]
 

@@ -185,7 +185,7 @@ def test_count_index_geometries_match_oracle(ctx, oracle, monkeypatch):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        c2 = device.Context(0)                       # the knobs are read when the context / the set is created
+        c2 = helpers.new_context_like(ctx)           # the knobs are read when the context / the set is created
         an = device.Annotations(c2, annos, key_ws_nseg=nseg)
         got = an.count_lists(COUNTERS, samples)
         an.close()

@@ -331,12 +331,7 @@ def test_column_stats_do_not_depend_on_the_kernel_that_computes_them(ctx, monkey
     column-sharded statistics differing from the 1-GPU ones in the last bit of stddev when the paths did not"""
     emulated = hasattr(ctx.lib, "gatb_emulation_marker")
     monkeypatch.setenv("GATB_STATS_STREAM", "0")
-    if emulated:
-        import emu_context
-        tiled = emu_context.context()
-    else:
-        from gat_b200 import device
-        tiled = device.Context(0)
+    tiled = helpers.new_context_like(ctx)
     monkeypatch.delenv("GATB_STATS_STREAM")
     rng = np.random.default_rng(19)
     try:
