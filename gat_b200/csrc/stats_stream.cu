@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(1024) stats_stream_kernel(StreamStatsParams p)
             for (uint32_t i = tid; i < rows * p.n_cols; i += T) sts32(stage + 4u * i, src[i]);
             __syncthreads();
         }
-#pragma unroll 2
+#pragma unroll 4
         for (uint32_t row = r; row < rows; row += RW) {
             const uint32_t rowa = stage + row * row_bytes;
             if (MODE == 0) nrows++;
